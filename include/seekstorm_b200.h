@@ -1,0 +1,163 @@
+/*
+ * seekstorm_b200.h — C ABI of libseekstorm_b200.so, the B200 (sm_100a) drop-in for the two query-time hot
+ * paths behind SeekStorm's Index::search():
+ *   (a) BM25 top-k over block-partitioned posting lists (AND / OR with block-max pruning), and
+ *   (b) the brute-force f32 dot / cosine / Euclidean vector scan with fused top-k,
+ * plus their RRF hybrid.  Plain pointers and sizes only; every pointer argument may be a HOST pointer or a
+ * DEVICE pointer of the index's device (detected with cudaPointerGetAttributes) unless stated otherwise.
+ *
+ * The reference has no FFI for this path; the seams this ABI replaces are (all paths relative to
+ * /root/reference/seekstorm/src/):
+ *   ssb_search_lexical  <- SearchLexicalShard::search_lexical_shard  search.rs:2427-2458 (body 2445-3767),
+ *                          i.e. the kernel-level calls single_blockid / union_docid_2 / union_docid_3 /
+ *                          union_blockid / intersection_blockid dispatched at search.rs:3370-3563
+ *   ssb_search_vector   <- SearchVectorShard::search_vector_shard    vector.rs:1105-1115 (body 1202-1514)
+ *   ssb_search_hybrid   <- Search::search, SearchMode::Hybrid        search.rs:1134-1150, RRF 1962-2035
+ *   ssb_lexical_add_level / ssb_lexical_commit <- the committed level as written by commit.rs:203-467 and
+ *                          read back by index.rs:3253-3830 (postings, tf = positions_count, byte4 doc lengths)
+ *   ssb_vector_add_level <- vector.bin level records written by vector.rs:969-1100
+ * INTEGRATION.md shows the Rust `extern "C"` block + shim a maintainer would add.
+ *
+ * Conventions: every call returns int32_t status (0 = OK, <0 = SSB_E_*), never unwinds, never aborts.
+ * Outputs are caller-allocated.  search_* calls on one handle are serialised internally (one stream);
+ * index mutation must be externally serialised against searches (mirrors the reference's RwLock).
+ * Doc ids on the ABI are the reference's shard-local ids: (level << 16) | local (vector.rs:1448,
+ * add_result.rs docid = block_id<<16 | local), widened to u64.
+ */
+#ifndef SEEKSTORM_B200_H
+#define SEEKSTORM_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+#define SSB_K_MAX 32u            /* top-k capacity of the fused kernels (lane-distributed lists)        */
+#define SSB_MAX_QUERY_TERMS 16u  /* unique terms per lexical query                                        */
+
+enum { SSB_OK = 0, SSB_E_INVALID = -1, SSB_E_CUDA = -2, SSB_E_NOMEM = -3, SSB_E_STATE = -4,
+       SSB_E_UNSUPPORTED = -5, SSB_E_NO_DEVICE = -6 };
+
+/* QueryType (search.rs, enum QueryType): Union / Intersection.  Phrase is out of scope. */
+enum { SSB_QUERY_UNION = 0, SSB_QUERY_INTERSECTION = 1 };
+/* ResultType (search.rs:150-175): Count / Topk / TopkCount (default) */
+enum { SSB_RESULT_COUNT = 0, SSB_RESULT_TOPK = 1, SSB_RESULT_TOPKCOUNT = 2 };
+/* VectorSimilarity (vector_similarity.rs:20-30) */
+enum { SSB_SIM_DOT = 0, SSB_SIM_COSINE = 1, SSB_SIM_EUCLIDEAN = 2 };
+/* which vector scan kernel to use */
+enum { SSB_VEC_KERNEL_AUTO = 0, SSB_VEC_KERNEL_FFMA = 1, SSB_VEC_KERNEL_TCGEN05 = 2 };
+
+typedef struct ssb_index ssb_index;
+
+/* min_heap.rs:17-40 `Result` {doc_id, score}; 16 bytes */
+typedef struct { uint64_t doc_id; float score; uint32_t pad; } ssb_hit;
+
+typedef struct {
+    int32_t  device;             /* CUDA device ordinal                                                  */
+    uint32_t max_batch;          /* max queries per search_* call (workspace sizing); 0 -> 4096          */
+    uint32_t vector_dims;        /* 0 = no vector index                                                   */
+    uint32_t vector_similarity;  /* SSB_SIM_*  (meta.inference similarity)                               */
+    uint32_t vector_kernel;      /* SSB_VEC_KERNEL_*                                                      */
+    uint32_t reserved[3];
+} ssb_config;
+
+/* One committed level = one 64K-doc block of the shard, in a neutral (decoded) layout.
+ * Replaces the per-level bytes the reference keeps in index.bin (ARCHITECTURE.md:77-82):
+ *   doc_ids / tfs : per term, ascending local doc ids and positions_count (tf), what
+ *                   intersection.rs:199-247 + add_result.rs:2036-2197 decode per candidate
+ *   doc_len_bytes : the level's byte4 field-length array (index.rs:770-776)                    */
+typedef struct {
+    uint32_t level_id;                /* block id; doc_id = level_id<<16 | local                         */
+    uint32_t n_docs;                  /* <= 65536                                                         */
+    uint32_t n_terms;
+    uint32_t reserved;
+    const uint64_t* term_keys;        /* [n_terms] 64-bit term hash (reference key_hash), any order       */
+    const uint32_t* posting_offsets;  /* [n_terms+1]                                                      */
+    const uint16_t* doc_ids;          /* [n_postings] ascending within a term                            */
+    const uint16_t* tfs;              /* [n_postings]                                                     */
+    const uint8_t*  doc_len_bytes;    /* [n_docs]                                                         */
+} ssb_level_desc;
+
+/* A batch of lexical queries, already tokenised by the host (tokenizer.rs is out of scope): unique terms
+ * per query as 64-bit keys, CSR layout. */
+typedef struct {
+    uint32_t n_queries;
+    uint32_t query_type;              /* SSB_QUERY_* (applies to the whole batch)                         */
+    const uint32_t* term_offsets;     /* [n_queries+1]                                                    */
+    const uint64_t* term_keys;        /* [term_offsets[n_queries]]                                        */
+} ssb_lex_batch;
+
+uint32_t    ssb_abi_version(void);
+const char* ssb_last_error(void);                              /* thread-local, never NULL              */
+
+int32_t ssb_create(const ssb_config* cfg, ssb_index** out);
+int32_t ssb_destroy(ssb_index* ix);
+
+/* ---- lexical index: add immutable levels, then commit global statistics --------------------------- */
+int32_t ssb_lexical_add_level(ssb_index* ix, const ssb_level_desc* level);
+/* n_docs = indexed_doc_count, len_sum_normalized = positions_sum_normalized (commit.rs:318-319) of the
+ * WHOLE shard (all GPUs' levels).  Builds the dictionary, bm25_component_cache (commit.rs:321-325),
+ * per-(term,block) block-max (index.rs:2938-3049) and the bitmap containers for dense lists. */
+int32_t ssb_lexical_commit(ssb_index* ix, uint64_t n_docs, uint64_t len_sum_normalized);
+/* dictionary export / global document-frequency override (multi-GPU block-range sharding: idf uses the
+ * global df, search.rs:3225).  keys/dfs are host pointers. */
+int32_t ssb_lexical_dict_size(const ssb_index* ix, uint64_t* n_terms);
+int32_t ssb_lexical_dict_export(const ssb_index* ix, uint64_t* keys, uint32_t* dfs, uint64_t cap);
+int32_t ssb_lexical_set_global_df(ssb_index* ix, const uint64_t* keys, const uint32_t* dfs, uint64_t n);
+
+/* ---- vector index -------------------------------------------------------------------------------- */
+/* rows: [n, dims] row-major f32 (row_stride_floats >= dims, 0 = dims); local_ids: [n] u16 or NULL (= 0..n-1).
+ * Cosine: rows are L2-normalised on load (vector.rs:585-596 does this at index time). */
+int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride_floats,
+                             const uint16_t* local_ids, uint32_t n, uint32_t dims);
+int32_t ssb_vector_count(const ssb_index* ix, uint64_t* n_rows);
+
+/* ---- search ---------------------------------------------------------------------------------------- */
+/* hits: [n_queries * k] best-first (score desc, doc id asc); n_hits: [n_queries]; count_total: [n_queries] or
+ * NULL (result_count_total: exact for Count/TopkCount, unspecified for Topk — search.rs:196-198). */
+int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, uint32_t result_type,
+                           ssb_hit* hits, uint32_t* n_hits, uint64_t* count_total);
+/* queries: [n_queries, dims] f32; Cosine: normalised by the callee (search.rs:1464-1475).  score = dot
+ * (Dot/Cosine) or -Σ(q-x)² (Euclidean) exactly as Result.score in vector.rs:1489. */
+int32_t ssb_search_vector(ssb_index* ix, const float* queries, uint32_t n_queries, uint32_t k,
+                          ssb_hit* hits, uint32_t* n_hits);
+/* SearchMode::Hybrid: both searches with length k, RRF (k=0.6, rank from 0), sort, truncate to k.
+ * hits: [n_queries * k]. */
+int32_t ssb_search_hybrid(ssb_index* ix, const ssb_lex_batch* q, const float* queries, uint32_t k,
+                          ssb_hit* hits, uint32_t* n_hits);
+
+/* RRF on two host lists (search.rs:1962-2035): out capacity n_lex+n_vec; sorted score desc, doc id asc. */
+int32_t ssb_rrf_fuse(const ssb_hit* lex, uint32_t n_lex, const ssb_hit* vec, uint32_t n_vec,
+                     ssb_hit* out, uint32_t* n_out);
+
+/* ---- device-resident variants (multi-GPU merge, benchmarking with inputs already in HBM) ----------- */
+/* Packed top-k keys: u64 = (ordered(score) << 32) | (0xFFFFFFFF - doc_id); larger = better.  keys_out is a
+ * DEVICE buffer [n_queries * 32]; entry j of query i is its j-th best or 0 if none.  Asynchronous on the
+ * index stream; ssb_sync() waits. */
+int32_t ssb_search_vector_keys(ssb_index* ix, const float* queries, uint32_t n_queries, uint32_t k,
+                               uint64_t* keys_out_dev);
+int32_t ssb_search_lexical_keys(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, uint32_t result_type,
+                                uint64_t* keys_out_dev, uint64_t* count_total_dev);
+/* merge `n_lists` key lists per query ([n_lists][n_queries][32], device) into hits (host) */
+int32_t ssb_merge_keys(ssb_index* ix, const uint64_t* keys_dev, uint32_t n_lists, uint32_t n_queries,
+                       uint32_t k, ssb_hit* hits, uint32_t* n_hits);
+int32_t ssb_sync(ssb_index* ix);
+/* the CUDA stream the index launches on (cudaStream_t as void*), for event timing */
+void*   ssb_stream(ssb_index* ix);
+
+/* ---- statistics of the last search_* call (for roofline accounting) -------------------------------- */
+typedef struct {
+    uint64_t kernel_launches;     /* kernels launched by the last call                                   */
+    uint64_t algorithmic_bytes;   /* SURVEY.md §8(d) bytes the call's kernels had to move                 */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t postings_visited;    /* lexical: postings enumerated after pruning                           */
+    uint64_t reserved[3];
+} ssb_stats;
+int32_t ssb_last_stats(const ssb_index* ix, ssb_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,161 @@
+"""ctypes binding of the CPU oracle (oracle/libssb_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libssb_oracle.so")
+
+QUERY_UNION, QUERY_INTERSECTION = 0, 1
+RESULT_COUNT, RESULT_TOPK, RESULT_TOPKCOUNT = 0, 1, 2
+SIM_DOT, SIM_COSINE, SIM_EUCLIDEAN = 0, 1, 2
+
+
+class OrcHit(C.Structure):
+    _fields_ = [("doc_id", C.c_uint64), ("score", C.c_float), ("pad", C.c_uint32)]
+
+
+class OrcLevel(C.Structure):
+    _fields_ = [("level_id", C.c_uint32), ("n_docs", C.c_uint32), ("n_terms", C.c_uint32),
+                ("reserved", C.c_uint32), ("term_keys", C.c_void_p), ("posting_offsets", C.c_void_p),
+                ("doc_ids", C.c_void_p), ("tfs", C.c_void_p), ("doc_len_bytes", C.c_void_p)]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "ssb_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_int_to_byte4.restype = C.c_uint8
+        L.orc_int_to_byte4.argtypes = [C.c_uint32]
+        L.orc_byte4_to_int.restype = C.c_uint32
+        L.orc_byte4_to_int.argtypes = [C.c_uint8]
+        L.orc_bm25_cache.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+        L.orc_idf.restype = C.c_float
+        L.orc_idf.argtypes = [C.c_uint64, C.c_uint32]
+        L.orc_bm25_term.restype = C.c_float
+        L.orc_bm25_term.argtypes = [C.c_float, C.c_uint32, C.c_float]
+        L.orc_index_new.restype = C.c_void_p
+        L.orc_index_free.argtypes = [C.c_void_p]
+        L.orc_index_add_level.argtypes = [C.c_void_p, C.POINTER(OrcLevel)]
+        L.orc_index_commit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.orc_index_df.restype = C.c_uint32
+        L.orc_index_df.argtypes = [C.c_void_p, C.c_uint64]
+        for f in (L.orc_search_lexical, L.orc_search_lexical_pruned):
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                          C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_normalize_f32.argtypes = [C.c_void_p, C.c_uint32]
+        for f in (L.orc_dot_f32, L.orc_dot_f32_lanes8, L.orc_euclidean_f32):
+            f.restype = C.c_float
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_vector_score_postmap.restype = C.c_float
+        L.orc_vector_score_postmap.argtypes = [C.c_float, C.c_uint32]
+        L.orc_search_vector.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                        C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        C.c_void_p, C.POINTER(C.c_uint32)]
+        L.orc_rrf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                              C.POINTER(C.c_uint32)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _hits_to_list(buf, n):
+    return [(int(buf[i].doc_id), float(np.float32(buf[i].score))) for i in range(n)]
+
+
+class OracleIndex:
+    """Lexical oracle index.  Levels are dicts of numpy arrays as produced by synth.Level.to_numpy()."""
+
+    def __init__(self):
+        self._h = lib().orc_index_new()
+        self.n_docs = 0
+        self.len_sum = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_index_free(self._h)
+            self._h = None
+
+    def add_level(self, lv: dict):
+        keep = [np.ascontiguousarray(lv["term_keys"], dtype=np.uint64),
+                np.ascontiguousarray(lv["posting_offsets"], dtype=np.uint32),
+                np.ascontiguousarray(lv["doc_ids"], dtype=np.uint16),
+                np.ascontiguousarray(lv["tfs"], dtype=np.uint16),
+                np.ascontiguousarray(lv["doc_len_bytes"], dtype=np.uint8)]
+        d = OrcLevel(lv["level_id"], lv["n_docs"], len(keep[0]), 0, *[_ptr(a) for a in keep])
+        rc = lib().orc_index_add_level(self._h, C.byref(d))
+        assert rc == 0
+
+    def commit(self, n_docs: int, len_sum: int):
+        self.n_docs, self.len_sum = n_docs, len_sum
+        assert lib().orc_index_commit(self._h, n_docs, len_sum) == 0
+
+    def df(self, key: int) -> int:
+        return lib().orc_index_df(self._h, C.c_uint64(key))
+
+    def search(self, term_keys, query_type, k, result_type, pruned=False):
+        keys = np.ascontiguousarray(np.array(term_keys, dtype=np.uint64))
+        buf = (OrcHit * max(k, 1))()
+        n = C.c_uint32(0)
+        tot = C.c_uint64(0)
+        f = lib().orc_search_lexical_pruned if pruned else lib().orc_search_lexical
+        rc = f(self._h, _ptr(keys), len(keys), query_type, k, result_type, buf, C.byref(n), C.byref(tot))
+        assert rc == 0, rc
+        return _hits_to_list(buf, n.value), int(tot.value)
+
+
+def bm25_cache(n_docs: int, len_sum: int) -> np.ndarray:
+    out = np.zeros(256, dtype=np.float32)
+    lib().orc_bm25_cache(n_docs, len_sum, _ptr(out))
+    return out
+
+
+def search_vector(rows: np.ndarray, query: np.ndarray, k: int, similarity: int, doc_ids=None,
+                  lanes8: bool = False, n_threads: int = 1):
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    q = np.ascontiguousarray(query, dtype=np.float32)
+    ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint32)
+    buf = (OrcHit * max(k, 1))()
+    n = C.c_uint32(0)
+    rc = lib().orc_search_vector(_ptr(rows), None if ids is None else _ptr(ids), rows.shape[0], rows.shape[1],
+                                 rows.strides[0] // 4, _ptr(q), similarity, k, int(lanes8), n_threads,
+                                 buf, C.byref(n))
+    assert rc == 0
+    return _hits_to_list(buf, n.value)
+
+
+def normalize(v: np.ndarray) -> np.ndarray:
+    v = np.ascontiguousarray(v, dtype=np.float32).copy()
+    lib().orc_normalize_f32(_ptr(v), v.size)
+    return v
+
+
+def rrf(lex, vec):
+    a = (OrcHit * max(len(lex), 1))(*[OrcHit(d, s, 0) for d, s in lex])
+    b = (OrcHit * max(len(vec), 1))(*[OrcHit(d, s, 0) for d, s in vec])
+    out = (OrcHit * max(len(lex) + len(vec), 1))()
+    n = C.c_uint32(0)
+    lib().orc_rrf(a, len(lex), b, len(vec), out, C.byref(n))
+    return _hits_to_list(out, n.value)

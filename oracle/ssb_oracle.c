@@ -1,0 +1,673 @@
+/*
+ * ssb_oracle.c — CPU ORACLE (test infrastructure only; see ssb_oracle.h header comment).
+ *
+ * Restates, function by function, the reference's query-time arithmetic.  Citations are
+ * relative to /root/reference/seekstorm/src/.  Compile with -ffp-contract=off so that every f32
+ * operation is individually rounded like rustc's output (no FMA contraction), except where the
+ * reference itself uses an explicit FMA (dot_f32_avx2).
+ *
+ * PARITY: "unpinned" by the reference's own tests beyond result counts; pinned by the hand-computed
+ * known-answer vectors in tests/golden/ (see tests/test_oracle_golden.py).
+ */
+#include "ssb_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+/* add_result.rs:20-22 */
+static const float ORC_K = 1.2f;
+static const float ORC_B = 0.75f;
+static const float ORC_SIGMA = 0.0f;
+
+/* ------------------------------------------------------------------ codec: index.rs:4232-4279 */
+#define NUM_FREE_VALUES 24u
+
+uint8_t orc_int_to_byte4(uint32_t i) {
+    if (i < NUM_FREE_VALUES) return (uint8_t)i;
+    uint32_t ii = i - NUM_FREE_VALUES;
+    uint32_t num_bits = ii ? 32u - (uint32_t)__builtin_clz(ii) : 0u;
+    if (num_bits < 4) return (uint8_t)(NUM_FREE_VALUES + ii);
+    uint32_t shift = num_bits - 4;
+    return (uint8_t)(NUM_FREE_VALUES + (((ii >> shift) & 0x07u) | ((shift + 1) << 3)));
+}
+
+uint32_t orc_byte4_to_int(uint8_t b) {
+    if ((uint32_t)b < NUM_FREE_VALUES) return b;
+    uint32_t i = (uint32_t)b - NUM_FREE_VALUES;
+    uint32_t bits = i & 0x07u, shift = i >> 3;
+    if (shift == 0) return NUM_FREE_VALUES + bits;
+    return NUM_FREE_VALUES + ((bits | 0x08u) << (shift - 1));
+}
+
+/* ------------------------------------------------------------------ statistics */
+void orc_bm25_cache(uint64_t n_docs, uint64_t len_sum, float cache[256]) {
+    /* commit.rs:318-325 */
+    float avgdl = (float)len_sum / (float)n_docs;
+    for (int i = 0; i < 256; i++) {
+        float q = (float)orc_byte4_to_int((uint8_t)i) / avgdl;
+        cache[i] = ORC_K * (1.0f - ORC_B + ORC_B * q);
+    }
+}
+
+float orc_idf(uint64_t n_docs, uint32_t df) {
+    /* search.rs:3225-3230; Rust f32::ln == logf */
+    return logf((((float)n_docs - (float)df + 0.5f) / ((float)df + 0.5f)) + 1.0f);
+}
+
+float orc_bm25_term(float idf, uint32_t tf_u, float comp) {
+    /* add_result.rs:1450-1452 */
+    float tf = (float)tf_u;
+    return idf * ((tf * (ORC_K + 1.0f) / (tf + comp)) + ORC_SIGMA);
+}
+
+/* ------------------------------------------------------------------ index */
+typedef struct {
+    uint32_t level_id, n_docs, n_terms;
+    uint64_t* term_keys;
+    uint32_t* posting_offsets;
+    uint16_t* doc_ids;
+    uint16_t* tfs;
+    uint8_t* doc_len_bytes;
+    float* max_comp; /* [n_terms] max over postings of tf*(K+1)/(tf+cache[len]) (block-max basis) */
+} lvl_t;
+
+typedef struct { uint64_t key; uint32_t level, idx; } dict_ent;
+
+struct orc_index {
+    lvl_t* levels;
+    uint32_t n_levels, cap_levels;
+    dict_ent* dict; /* sorted by (key, level) */
+    uint64_t n_dict;
+    uint64_t n_docs, len_sum;
+    float cache[256];
+    int committed;
+};
+
+orc_index* orc_index_new(void) { return (orc_index*)calloc(1, sizeof(orc_index)); }
+
+void orc_index_free(orc_index* ix) {
+    if (!ix) return;
+    for (uint32_t i = 0; i < ix->n_levels; i++) {
+        lvl_t* l = &ix->levels[i];
+        free(l->term_keys); free(l->posting_offsets); free(l->doc_ids); free(l->tfs);
+        free(l->doc_len_bytes); free(l->max_comp);
+    }
+    free(ix->levels); free(ix->dict); free(ix);
+}
+
+static void* dup_mem(const void* p, size_t n) {
+    void* q = malloc(n ? n : 1);
+    if (n) memcpy(q, p, n);
+    return q;
+}
+
+int orc_index_add_level(orc_index* ix, const orc_level* d) {
+    if (!ix || !d || d->n_docs > 65536) return -1;
+    if (ix->n_levels == ix->cap_levels) {
+        ix->cap_levels = ix->cap_levels ? ix->cap_levels * 2 : 16;
+        ix->levels = (lvl_t*)realloc(ix->levels, ix->cap_levels * sizeof(lvl_t));
+    }
+    lvl_t* l = &ix->levels[ix->n_levels++];
+    memset(l, 0, sizeof(*l));
+    l->level_id = d->level_id; l->n_docs = d->n_docs; l->n_terms = d->n_terms;
+    uint32_t np = d->n_terms ? d->posting_offsets[d->n_terms] : 0;
+    l->term_keys = (uint64_t*)dup_mem(d->term_keys, (size_t)d->n_terms * 8);
+    l->posting_offsets = (uint32_t*)dup_mem(d->posting_offsets, ((size_t)d->n_terms + 1) * 4);
+    l->doc_ids = (uint16_t*)dup_mem(d->doc_ids, (size_t)np * 2);
+    l->tfs = (uint16_t*)dup_mem(d->tfs, (size_t)np * 2);
+    l->doc_len_bytes = (uint8_t*)dup_mem(d->doc_len_bytes, d->n_docs);
+    ix->committed = 0;
+    return 0;
+}
+
+static int cmp_dict(const void* a, const void* b) {
+    const dict_ent* x = (const dict_ent*)a; const dict_ent* y = (const dict_ent*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    if (x->level != y->level) return x->level < y->level ? -1 : 1;
+    return 0;
+}
+
+/* query-independent part of the score of one posting: tf*(K+1)/(tf+cache[len]) */
+static inline float comp_of(const orc_index* ix, uint32_t tf_u, uint8_t len_byte) {
+    float tf = (float)tf_u;
+    return tf * (ORC_K + 1.0f) / (tf + ix->cache[len_byte]);
+}
+
+int orc_index_commit(orc_index* ix, uint64_t n_docs, uint64_t len_sum) {
+    if (!ix) return -1;
+    ix->n_docs = n_docs; ix->len_sum = len_sum;
+    orc_bm25_cache(n_docs, len_sum, ix->cache);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < ix->n_levels; i++) total += ix->levels[i].n_terms;
+    free(ix->dict);
+    ix->dict = (dict_ent*)malloc((total ? total : 1) * sizeof(dict_ent));
+    uint64_t p = 0;
+    for (uint32_t i = 0; i < ix->n_levels; i++) {
+        lvl_t* l = &ix->levels[i];
+        free(l->max_comp);
+        l->max_comp = (float*)malloc(((size_t)l->n_terms ? l->n_terms : 1) * sizeof(float));
+        for (uint32_t t = 0; t < l->n_terms; t++) {
+            ix->dict[p].key = l->term_keys[t]; ix->dict[p].level = i; ix->dict[p].idx = t; p++;
+            float m = 0.0f;
+            for (uint32_t j = l->posting_offsets[t]; j < l->posting_offsets[t + 1]; j++) {
+                float c = comp_of(ix, l->tfs[j], l->doc_len_bytes[l->doc_ids[j]]);
+                if (c > m) m = c;
+            }
+            l->max_comp[t] = m;
+        }
+    }
+    ix->n_dict = total;
+    qsort(ix->dict, total, sizeof(dict_ent), cmp_dict);
+    ix->committed = 1;
+    return 0;
+}
+
+/* first dict entry with key >= key */
+static uint64_t dict_lower(const orc_index* ix, uint64_t key) {
+    uint64_t lo = 0, hi = ix->n_dict;
+    while (lo < hi) { uint64_t m = (lo + hi) / 2; if (ix->dict[m].key < key) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+uint32_t orc_index_df(const orc_index* ix, uint64_t key) {
+    uint64_t i = dict_lower(ix, key); uint64_t df = 0;
+    for (; i < ix->n_dict && ix->dict[i].key == key; i++) {
+        const lvl_t* l = &ix->levels[ix->dict[i].level];
+        df += l->posting_offsets[ix->dict[i].idx + 1] - l->posting_offsets[ix->dict[i].idx];
+    }
+    return (uint32_t)df;
+}
+
+/* ------------------------------------------------------------------ canonical top-k */
+/* canonical order: score desc, doc id asc.  better(a,b) = a ranks before b. */
+static inline int better(float sa, uint64_t da, float sb, uint64_t db) {
+    return (sa > sb) || (sa == sb && da < db);
+}
+
+typedef struct { orc_hit* h; uint32_t n, k; } topk_t;
+
+/* simple insertion top-k kept sorted best-first */
+static void topk_push(topk_t* t, uint64_t doc, float score) {
+    if (t->k == 0) return;
+    if (t->n == t->k && !better(score, doc, t->h[t->n - 1].score, t->h[t->n - 1].doc_id)) return;
+    uint32_t i = t->n < t->k ? t->n++ : t->k - 1;
+    while (i > 0 && better(score, doc, t->h[i - 1].score, t->h[i - 1].doc_id)) { t->h[i] = t->h[i - 1]; i--; }
+    t->h[i].doc_id = doc; t->h[i].score = score; t->h[i].pad = 0;
+}
+
+/* ------------------------------------------------------------------ exhaustive lexical search */
+typedef struct { uint64_t first, last; float idf; uint32_t df; } qterm_t;
+
+#define ORC_MAX_TERMS 64
+
+static int resolve_terms(const orc_index* ix, const uint64_t* keys, uint32_t n, qterm_t* qt) {
+    for (uint32_t t = 0; t < n; t++) {
+        uint64_t i = dict_lower(ix, keys[t]); uint64_t j = i; uint64_t df = 0;
+        for (; j < ix->n_dict && ix->dict[j].key == keys[t]; j++) {
+            const lvl_t* l = &ix->levels[ix->dict[j].level];
+            df += l->posting_offsets[ix->dict[j].idx + 1] - l->posting_offsets[ix->dict[j].idx];
+        }
+        qt[t].first = i; qt[t].last = j; qt[t].df = (uint32_t)df;
+        qt[t].idf = df ? orc_idf(ix->n_docs, (uint32_t)df) : 0.0f;
+    }
+    return 0;
+}
+
+/* dict entry of term t in level li, or -1 */
+static int64_t term_in_level(const orc_index* ix, const qterm_t* q, uint32_t li) {
+    uint64_t lo = q->first, hi = q->last;
+    while (lo < hi) { uint64_t m = (lo + hi) / 2; if (ix->dict[m].level < li) lo = m + 1; else hi = m; }
+    if (lo < q->last && ix->dict[lo].level == li) return (int64_t)lo;
+    return -1;
+}
+
+int orc_search_lexical(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, uint32_t query_type,
+                       uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
+                       uint64_t* count_total) {
+    if (!ix || !ix->committed || n_terms > ORC_MAX_TERMS) return -1;
+    if (n_hits) *n_hits = 0;
+    if (count_total) *count_total = 0;
+    if (n_terms == 0) return 0;
+    qterm_t qt[ORC_MAX_TERMS];
+    resolve_terms(ix, keys, n_terms, qt);
+    uint32_t n_live = 0; qterm_t live[ORC_MAX_TERMS];
+    for (uint32_t t = 0; t < n_terms; t++) {
+        if (qt[t].df == 0) {
+            /* search.rs:3290-3296: AND with a missing term -> empty; OR drops the term */
+            if (query_type == ORC_QUERY_INTERSECTION) return 0;
+            continue;
+        }
+        live[n_live++] = qt[t];
+    }
+    if (n_live == 0) return 0;
+    /* search.rs:2527-2531 heap capacity min(k, indexed_doc_count) */
+    uint32_t kk = k; if ((uint64_t)kk > ix->n_docs) kk = (uint32_t)ix->n_docs;
+    if (result_type == ORC_RESULT_COUNT) kk = 0;
+    topk_t tk = { hits, 0, kk };
+    float* acc = (float*)malloc(65536 * sizeof(float));
+    uint8_t* cnt = (uint8_t*)malloc(65536);
+    uint64_t total = 0;
+    for (uint32_t li = 0; li < ix->n_levels; li++) {
+        const lvl_t* l = &ix->levels[li];
+        int any = 0;
+        for (uint32_t t = 0; t < n_live; t++) if (term_in_level(ix, &live[t], li) >= 0) { any = 1; break; }
+        if (!any) continue;
+        memset(acc, 0, l->n_docs * sizeof(float));
+        memset(cnt, 0, l->n_docs);
+        for (uint32_t t = 0; t < n_live; t++) {   /* QUERY ORDER: bm25f += ... from 0.0 */
+            int64_t e = term_in_level(ix, &live[t], li);
+            if (e < 0) continue;
+            uint32_t ti = ix->dict[e].idx;
+            for (uint32_t j = l->posting_offsets[ti]; j < l->posting_offsets[ti + 1]; j++) {
+                uint16_t d = l->doc_ids[j];
+                float comp = ix->cache[l->doc_len_bytes[d]];
+                acc[d] += orc_bm25_term(live[t].idf, l->tfs[j], comp);
+                cnt[d]++;
+            }
+        }
+        for (uint32_t d = 0; d < l->n_docs; d++) {
+            int match = query_type == ORC_QUERY_INTERSECTION ? (cnt[d] == n_live) : (cnt[d] > 0);
+            if (!match) continue;
+            total++;
+            if (kk) topk_push(&tk, ((uint64_t)l->level_id << 16) | d, acc[d]);
+        }
+    }
+    free(acc); free(cnt);
+    if (n_hits) *n_hits = tk.n;
+    if (count_total) *count_total = total;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ reference-shaped pruned search
+ * A faithful CPU restatement of the reference control flow, used (a) as the timed CPU baseline and
+ * (b) as a cross-check that pruning == exhaustive.  Heap: min_heap.rs (binary min-heap on score,
+ * strict > replacement, doc-id dedup map for OR).  Here the heap keeps canonical (score, docid) order so
+ * that its result equals the exhaustive canonical top-k even inside tie groups. */
+typedef struct { float s; uint64_t d; } hent;
+typedef struct { hent* e; uint32_t n, k; } heap_t;
+
+static inline int worse(const hent* a, const hent* b) { /* a ranks after b */
+    return better(b->s, b->d, a->s, a->d);
+}
+static void heap_sift_down(heap_t* h, uint32_t i) {
+    for (;;) {
+        uint32_t l = 2 * i + 1, r = l + 1, m = i;
+        if (l < h->n && worse(&h->e[l], &h->e[m])) m = l;
+        if (r < h->n && worse(&h->e[r], &h->e[m])) m = r;
+        if (m == i) return;
+        hent t = h->e[i]; h->e[i] = h->e[m]; h->e[m] = t; i = m;
+    }
+}
+static void heap_sift_up(heap_t* h, uint32_t i) {
+    while (i > 0) {
+        uint32_t p = (i - 1) / 2;
+        if (!worse(&h->e[i], &h->e[p])) return;
+        hent t = h->e[i]; h->e[i] = h->e[p]; h->e[p] = t; i = p;
+    }
+}
+/* min_heap.rs:1193-1259 add_topk, with doc-id dedup (linear over k entries; k is small) */
+static void heap_add(heap_t* h, uint64_t d, float s, int dedup) {
+    if (h->k == 0) return;
+    hent c = { s, d };
+    if (dedup) {
+        for (uint32_t i = 0; i < h->n; i++) if (h->e[i].d == d) {
+            if (s > h->e[i].s) { h->e[i].s = s; heap_sift_down(h, i); heap_sift_up(h, i); }
+            return;
+        }
+    }
+    if (h->n < h->k) { h->e[h->n++] = c; heap_sift_up(h, h->n - 1); return; }
+    if (worse(&h->e[0], &c)) { h->e[0] = c; heap_sift_down(h, 0); }
+}
+static inline float heap_min(const heap_t* h) { return h->e[0].s; }
+static inline int heap_full(const heap_t* h) { return h->n == h->k; }
+
+typedef struct { uint32_t level; uint32_t tidx[ORC_MAX_TERMS]; float bound; } blk_t;
+
+static int cmp_blk_desc(const void* a, const void* b) {
+    float x = ((const blk_t*)a)->bound, y = ((const blk_t*)b)->bound;
+    if (x != y) return x > y ? -1 : 1;
+    uint32_t la = ((const blk_t*)a)->level, lb = ((const blk_t*)b)->level;
+    return la < lb ? -1 : (la > lb);
+}
+
+/* galloping lower bound in a sorted u16 array starting from *pos (intersection.rs:352-362) */
+static inline uint32_t gallop(const uint16_t* a, uint32_t pos, uint32_t n, uint16_t x) {
+    uint32_t step = 1, lo = pos;
+    while (lo + step < n && a[lo + step] < x) { lo += step; step <<= 1; }
+    uint32_t hi = lo + step < n ? lo + step : n;
+    while (lo < hi) { uint32_t m = (lo + hi) / 2; if (a[m] < x) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+/* AND over the given term subset (intersection_blockid + intersection_docid); returns match count */
+static uint64_t and_pass(const orc_index* ix, const qterm_t* terms, const uint32_t* order /*query order idx*/,
+                         uint32_t nt, heap_t* h, int prune_blocks, int dedup) {
+    /* block list = levels where every term occurs; bound = Σ idf*max_comp (intersection.rs:2090-2109) */
+    blk_t* blocks = (blk_t*)malloc((ix->n_levels ? ix->n_levels : 1) * sizeof(blk_t));
+    uint32_t nb = 0;
+    for (uint32_t li = 0; li < ix->n_levels; li++) {
+        blk_t b; b.level = li; b.bound = 0.0f; int ok = 1;
+        for (uint32_t t = 0; t < nt; t++) {
+            int64_t e = term_in_level(ix, &terms[t], li);
+            if (e < 0) { ok = 0; break; }
+            b.tidx[t] = ix->dict[e].idx;
+            b.bound += terms[t].idf * ix->levels[li].max_comp[b.tidx[t]];
+        }
+        if (ok) blocks[nb++] = b;
+    }
+    qsort(blocks, nb, sizeof(blk_t), cmp_blk_desc); /* intersection.rs:2225 */
+    uint64_t count = 0;
+    for (uint32_t bi = 0; bi < nb; bi++) {
+        const blk_t* b = &blocks[bi];
+        int score_block = 1;
+        /* canonical tie rule: an equal-score doc with a smaller id could still displace the heap root, so
+         * only strict < prunes; the reference uses <= (intersection.rs:2227-2233, add_result.rs:3512-3536) */
+        if (h->k > 0 && heap_full(h) && b->bound < heap_min(h)) { if (prune_blocks) break; score_block = 0; }
+        if (h->k == 0) score_block = 0;
+        const lvl_t* l = &ix->levels[b->level];
+        /* drive with the shortest list (intersection.rs:258-273) */
+        uint32_t drv = 0, dn = 0xffffffffu;
+        for (uint32_t t = 0; t < nt; t++) {
+            uint32_t c = l->posting_offsets[b->tidx[t] + 1] - l->posting_offsets[b->tidx[t]];
+            if (c < dn) { dn = c; drv = t; }
+        }
+        uint32_t pos[ORC_MAX_TERMS]; memset(pos, 0, sizeof(pos));
+        const uint16_t* da = l->doc_ids + l->posting_offsets[b->tidx[drv]];
+        for (uint32_t i = 0; i < dn; i++) {
+            uint16_t d = da[i]; int all = 1; uint32_t tfv[ORC_MAX_TERMS];
+            tfv[drv] = l->tfs[l->posting_offsets[b->tidx[drv]] + i];
+            for (uint32_t t = 0; t < nt && all; t++) {
+                if (t == drv) continue;
+                uint32_t off = l->posting_offsets[b->tidx[t]];
+                uint32_t n = l->posting_offsets[b->tidx[t] + 1] - off;
+                uint32_t p = gallop(l->doc_ids + off, pos[t], n, d);
+                pos[t] = p;
+                if (p >= n || l->doc_ids[off + p] != d) all = 0; else tfv[t] = l->tfs[off + p];
+            }
+            if (!all) continue;
+            count++;
+            if (!score_block) continue;
+            float comp = ix->cache[l->doc_len_bytes[d]];
+            /* sum in QUERY ORDER (order[] maps sorted position -> term), from 0.0 */
+            float s = 0.0f;
+            for (uint32_t t = 0; t < nt; t++) s += orc_bm25_term(terms[order[t]].idf, tfv[order[t]], comp);
+            heap_add(h, ((uint64_t)l->level_id << 16) | d, s, dedup);
+        }
+    }
+    free(blocks);
+    return count;
+}
+
+/* single_blockid + single_docid (single.rs:292-417): blocks by bound desc, stop at first block that
+ * cannot beat heap.min; at most k blocks are needed when unfiltered (:375). */
+static void single_pass(const orc_index* ix, const qterm_t* term, heap_t* h, int dedup) {
+    uint64_t nb = term->last - term->first;
+    blk_t* blocks = (blk_t*)malloc((nb ? nb : 1) * sizeof(blk_t));
+    for (uint64_t i = 0; i < nb; i++) {
+        const dict_ent* e = &ix->dict[term->first + i];
+        blocks[i].level = e->level; blocks[i].tidx[0] = e->idx;
+        blocks[i].bound = term->idf * ix->levels[e->level].max_comp[e->idx];
+    }
+    qsort(blocks, nb, sizeof(blk_t), cmp_blk_desc);
+    for (uint64_t bi = 0; bi < nb; bi++) {
+        if (heap_full(h) && blocks[bi].bound < heap_min(h)) break;
+        const lvl_t* l = &ix->levels[blocks[bi].level];
+        uint32_t off = l->posting_offsets[blocks[bi].tidx[0]], end = l->posting_offsets[blocks[bi].tidx[0] + 1];
+        for (uint32_t j = off; j < end; j++) {
+            uint16_t d = l->doc_ids[j];
+            float s = 0.0f; s += orc_bm25_term(term->idf, l->tfs[j], ix->cache[l->doc_len_bytes[d]]);
+            heap_add(h, ((uint64_t)l->level_id << 16) | d, s, dedup);
+        }
+    }
+    free(blocks);
+}
+
+/* exact |union| per level via 64K-bit bitmap OR + popcount (union.rs:807-1164 union_count) */
+static uint64_t union_count_all(const orc_index* ix, const qterm_t* terms, uint32_t nt) {
+    uint64_t total = 0; uint64_t* bm = (uint64_t*)malloc(1024 * 8);
+    for (uint32_t li = 0; li < ix->n_levels; li++) {
+        const lvl_t* l = &ix->levels[li]; int any = 0;
+        for (uint32_t t = 0; t < nt; t++) {
+            int64_t e = term_in_level(ix, &terms[t], li);
+            if (e < 0) continue;
+            if (!any) { memset(bm, 0, 8192); any = 1; }
+            uint32_t ti = ix->dict[e].idx;
+            for (uint32_t j = l->posting_offsets[ti]; j < l->posting_offsets[ti + 1]; j++)
+                bm[l->doc_ids[j] >> 6] |= 1ull << (l->doc_ids[j] & 63);
+        }
+        if (any) for (int w = 0; w < 1024; w++) total += (uint64_t)__builtin_popcountll(bm[w]);
+    }
+    free(bm);
+    return total;
+}
+
+/* OR over a term subset: MAXSCORE-style sub-query enumeration in the spirit of union_docid_2/3
+ * (union.rs:1168-1479): AND of all terms first, then every (n-1)-subset whose Σ max_list_score can still
+ * beat heap.min, recursively, down to single terms. Scores of docs found by a sub-query are FULL scores
+ * (all query terms the doc contains), so dedup keeps the max = the true score. */
+typedef struct { const orc_index* ix; const qterm_t* all; uint32_t n_all; heap_t* h; float max_list[ORC_MAX_TERMS]; } orctx;
+
+static void or_subsets(orctx* c) {
+    /* enumerate subsets in decreasing size; full-score semantics are obtained by scoring every doc that
+     * matches the AND of the subset with ALL query terms it contains (probe the others). To keep the
+     * restatement simple and exact we do: for subset masks ordered by Σ max_list desc, skip if bound <
+     * heap.min, else AND-enumerate the subset and score the doc fully. n_all <= 10 here. */
+    uint32_t n = c->n_all; uint32_t nm = 1u << n;
+    typedef struct { uint32_t mask; float bound; } sq;
+    sq* q = (sq*)malloc(nm * sizeof(sq)); uint32_t nq = 0;
+    for (uint32_t m = 1; m < nm; m++) {
+        float b = 0.0f; for (uint32_t t = 0; t < n; t++) if (m >> t & 1) b += c->max_list[t];
+        q[nq].mask = m; q[nq].bound = b; nq++;
+    }
+    /* sort by popcount desc then bound desc (AND of all first: union.rs:1328-1345) */
+    for (uint32_t i = 1; i < nq; i++) { sq x = q[i]; uint32_t j = i;
+        while (j > 0) { int pa = __builtin_popcount(q[j-1].mask), pb = __builtin_popcount(x.mask);
+            if (pa > pb || (pa == pb && q[j-1].bound >= x.bound)) break;
+            q[j] = q[j-1]; j--; }
+        q[j] = x; }
+    for (uint32_t i = 0; i < nq; i++) {
+        if (heap_full(c->h) && q[i].bound < heap_min(c->h)) continue;
+        qterm_t sub[ORC_MAX_TERMS]; uint32_t map[ORC_MAX_TERMS]; uint32_t ns = 0;
+        for (uint32_t t = 0; t < n; t++) if (q[i].mask >> t & 1) { sub[ns] = c->all[t]; map[ns] = t; ns++; }
+        /* docs matching exactly-this-subset-or-more get their FULL score: enumerate AND(sub) and add the
+         * remaining terms by probing */
+        const orc_index* ix = c->ix;
+        for (uint32_t li = 0; li < ix->n_levels; li++) {
+            const lvl_t* l = &ix->levels[li]; uint32_t tix[ORC_MAX_TERMS] = {0}; int ok = 1; float bb = 0.0f;
+            int64_t ent_all[ORC_MAX_TERMS];
+            for (uint32_t t = 0; t < n; t++) ent_all[t] = term_in_level(ix, &c->all[t], li);
+            for (uint32_t s = 0; s < ns; s++) { if (ent_all[map[s]] < 0) { ok = 0; break; }
+                tix[s] = ix->dict[ent_all[map[s]]].idx; bb += sub[s].idf * l->max_comp[tix[s]]; }
+            if (!ok) continue;
+            if (heap_full(c->h) && bb < heap_min(c->h)) continue; /* block-max skip for this sub-query */
+            uint32_t drv = 0, dn = 0xffffffffu;
+            for (uint32_t s = 0; s < ns; s++) { uint32_t cnt = l->posting_offsets[tix[s]+1]-l->posting_offsets[tix[s]];
+                if (cnt < dn) { dn = cnt; drv = s; } }
+            uint32_t pos[ORC_MAX_TERMS]; memset(pos, 0, sizeof(pos));
+            const uint16_t* da = l->doc_ids + l->posting_offsets[tix[drv]];
+            for (uint32_t j = 0; j < dn; j++) {
+                uint16_t d = da[j]; int all = 1;
+                for (uint32_t s = 0; s < ns && all; s++) { if (s == drv) continue;
+                    uint32_t off = l->posting_offsets[tix[s]], cnt = l->posting_offsets[tix[s]+1]-off;
+                    uint32_t p = gallop(l->doc_ids+off, pos[s], cnt, d); pos[s] = p;
+                    if (p >= cnt || l->doc_ids[off+p] != d) all = 0; }
+                if (!all) continue;
+                float comp = ix->cache[l->doc_len_bytes[d]]; float sc = 0.0f;
+                for (uint32_t t = 0; t < n; t++) {   /* full score, query order */
+                    if (ent_all[t] < 0) continue;
+                    uint32_t ti = ix->dict[ent_all[t]].idx;
+                    uint32_t off = l->posting_offsets[ti], cnt = l->posting_offsets[ti+1]-off;
+                    uint32_t p = gallop(l->doc_ids+off, 0, cnt, d);
+                    if (p < cnt && l->doc_ids[off+p] == d) sc += orc_bm25_term(c->all[t].idf, l->tfs[off+p], comp);
+                }
+                heap_add(c->h, ((uint64_t)l->level_id << 16) | d, sc, 1);
+            }
+        }
+    }
+    free(q);
+}
+
+int orc_search_lexical_pruned(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, uint32_t query_type,
+                              uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
+                              uint64_t* count_total) {
+    if (!ix || !ix->committed || n_terms > ORC_MAX_TERMS) return -1;
+    if (n_hits) *n_hits = 0;
+    if (count_total) *count_total = 0;
+    if (n_terms == 0) return 0;
+    qterm_t qt[ORC_MAX_TERMS]; resolve_terms(ix, keys, n_terms, qt);
+    qterm_t live[ORC_MAX_TERMS]; uint32_t nl = 0;
+    for (uint32_t t = 0; t < n_terms; t++) {
+        if (qt[t].df == 0) { if (query_type == ORC_QUERY_INTERSECTION) return 0; continue; }
+        live[nl++] = qt[t];
+    }
+    if (nl == 0) return 0;
+    uint32_t kk = k; if ((uint64_t)kk > ix->n_docs) kk = (uint32_t)ix->n_docs;
+    if (result_type == ORC_RESULT_COUNT) kk = 0;
+    heap_t h; h.e = (hent*)malloc(((size_t)kk ? kk : 1) * sizeof(hent)); h.n = 0; h.k = kk;
+    uint32_t order[ORC_MAX_TERMS]; for (uint32_t t = 0; t < nl; t++) order[t] = t;
+    uint64_t total = 0;
+    if (query_type == ORC_QUERY_INTERSECTION || nl == 1) {
+        if (nl == 1 && query_type != ORC_QUERY_INTERSECTION) {
+            total = live[0].df;                       /* single.rs:314-322 */
+            if (kk) single_pass(ix, &live[0], &h, 0);
+        } else {
+            total = and_pass(ix, live, order, nl, &h, result_type == ORC_RESULT_TOPK, 0);
+        }
+    } else if (nl == 2) {
+        /* union_docid_2 (union.rs:1168-1304) */
+        uint64_t both = and_pass(ix, live, order, 2, &h, result_type == ORC_RESULT_TOPK, 0);
+        total = (uint64_t)live[0].df + live[1].df;
+        total -= both; /* inaccurate under Topk, as in the reference (search.rs:196-198) */
+        if (kk) for (uint32_t t = 0; t < 2; t++) {
+            float mx = 0.0f;
+            for (uint64_t i = live[t].first; i < live[t].last; i++) {
+                float b = live[t].idf * ix->levels[ix->dict[i].level].max_comp[ix->dict[i].idx];
+                if (b > mx) mx = b;
+            }
+            if (!heap_full(&h) || mx >= heap_min(&h)) single_pass(ix, &live[t], &h, 1);
+        }
+    } else {
+        if (nl > 12) { free(h.e); return -2; }
+        orctx c; c.ix = ix; c.all = live; c.n_all = nl; c.h = &h;
+        for (uint32_t t = 0; t < nl; t++) { float mx = 0.0f;
+            for (uint64_t i = live[t].first; i < live[t].last; i++) {
+                float b = live[t].idf * ix->levels[ix->dict[i].level].max_comp[ix->dict[i].idx];
+                if (b > mx) mx = b; }
+            c.max_list[t] = mx; }
+        if (kk) or_subsets(&c);
+        if (result_type != ORC_RESULT_TOPK) total = union_count_all(ix, live, nl);
+    }
+    /* search.rs:3565-3596: take heap, sort by score desc (canonical: then doc id asc) */
+    topk_t tk = { hits, 0, kk };
+    for (uint32_t i = 0; i < h.n; i++) topk_push(&tk, h.e[i].d, h.e[i].s);
+    free(h.e);
+    if (n_hits) *n_hits = tk.n;
+    if (count_total) *count_total = total;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ vectors */
+void orc_normalize_f32(float* v, uint32_t n) {
+    /* vector_similarity.rs:70-74 */
+    float s = 0.0f; for (uint32_t i = 0; i < n; i++) s += v[i] * v[i];
+    float f = 1.0f / sqrtf(s);
+    for (uint32_t i = 0; i < n; i++) v[i] *= f;
+}
+
+float orc_dot_f32(const float* a, const float* b, uint32_t n) {
+    /* vector_similarity.rs:1006-1008: left-to-right sum of products */
+    float s = 0.0f; for (uint32_t i = 0; i < n; i++) s += a[i] * b[i];
+    return s;
+}
+
+float orc_dot_f32_lanes8(const float* q, const float* e, uint32_t n) {
+    /* vector_similarity.rs:1120-1142: 8 lanes of fused multiply-add, then in-order sum of the lanes */
+    float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        for (int j = 0; j < 8; j++) lane[j] = fmaf(q[i + j], e[i + j], lane[j]);
+    float s = 0.0f; for (int j = 0; j < 8; j++) s += lane[j];
+    for (; i < n; i++) s += q[i] * e[i];
+    return s;
+}
+
+float orc_euclidean_f32(const float* a, const float* b, uint32_t n) {
+    /* vector_similarity.rs:912-918 */
+    float s = 0.0f; for (uint32_t i = 0; i < n; i++) { float d = a[i] - b[i]; s += d * d; }
+    return s;
+}
+
+float orc_vector_score_postmap(float score, uint32_t sim) {
+    /* vector.rs:1489-1499, SIMILARITY_NORMALIZATION_64_I8 = 1/16129 (vector.rs:29) */
+    if (sim == ORC_SIM_EUCLIDEAN) return -score;
+    return ((score * (1.0f / 16129.0f)) + 1.0f) * 0.5f;
+}
+
+typedef struct {
+    const float* rows; const uint32_t* ids; uint64_t lo, hi; uint32_t dims, pitch, sim, lanes8;
+    const float* q; topk_t tk;
+} vjob;
+
+static void* vscan(void* p) {
+    vjob* j = (vjob*)p;
+    for (uint64_t r = j->lo; r < j->hi; r++) {
+        const float* e = j->rows + r * j->pitch; float s;
+        if (j->sim == ORC_SIM_EUCLIDEAN) s = -orc_euclidean_f32(j->q, e, j->dims);
+        else s = j->lanes8 ? orc_dot_f32_lanes8(j->q, e, j->dims) : orc_dot_f32(j->q, e, j->dims);
+        topk_push(&j->tk, j->ids ? j->ids[r] : r, s);
+    }
+    return NULL;
+}
+
+int orc_search_vector(const float* rows, const uint32_t* ids, uint64_t n_rows, uint32_t dims, uint32_t pitch,
+                      const float* query, uint32_t sim, uint32_t k, uint32_t lanes8, uint32_t n_threads,
+                      orc_hit* hits, uint32_t* n_hits) {
+    if (!rows || !query || !hits) return -1;
+    if (pitch == 0) pitch = dims;
+    if (n_threads == 0) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    vjob* jobs = (vjob*)calloc(n_threads, sizeof(vjob));
+    pthread_t* th = (pthread_t*)calloc(n_threads, sizeof(pthread_t));
+    for (uint32_t t = 0; t < n_threads; t++) {
+        vjob* j = &jobs[t];
+        j->rows = rows; j->ids = ids; j->dims = dims; j->pitch = pitch; j->sim = sim; j->lanes8 = lanes8; j->q = query;
+        j->lo = n_rows * t / n_threads; j->hi = n_rows * (t + 1) / n_threads;
+        j->tk.h = (orc_hit*)malloc(((size_t)k ? k : 1) * sizeof(orc_hit)); j->tk.n = 0; j->tk.k = k;
+        if (n_threads > 1) pthread_create(&th[t], NULL, vscan, j); else vscan(j);
+    }
+    topk_t out = { hits, 0, k };
+    for (uint32_t t = 0; t < n_threads; t++) {
+        if (n_threads > 1) pthread_join(th[t], NULL);
+        for (uint32_t i = 0; i < jobs[t].tk.n; i++) topk_push(&out, jobs[t].tk.h[i].doc_id, jobs[t].tk.h[i].score);
+        free(jobs[t].tk.h);
+    }
+    free(jobs); free(th);
+    if (n_hits) *n_hits = out.n;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ RRF: search.rs:1962-2035 */
+int orc_rrf(const orc_hit* lex, uint32_t n_lex, const orc_hit* vec, uint32_t n_vec, orc_hit* out, uint32_t* n_out) {
+    const float kf = 0.6f;
+    uint32_t n = 0;
+    /* inputs are already sorted score desc (canonical) — the reference re-sorts them (:1970, :1989) */
+    for (uint32_t i = 0; i < n_lex; i++) {
+        uint32_t j = 0; for (; j < n; j++) if (out[j].doc_id == lex[i].doc_id) break;
+        float s = 1.0f / (kf + (float)i);
+        if (j == n) { out[n].doc_id = lex[i].doc_id; out[n].score = s; out[n].pad = 0; n++; }
+        else out[j].score = s; /* HashMap::insert overwrites (:1975) */
+    }
+    for (uint32_t i = 0; i < n_vec; i++) {
+        uint32_t j = 0; for (; j < n; j++) if (out[j].doc_id == vec[i].doc_id) break;
+        float s = 1.0f / (kf + (float)i);
+        if (j == n) { out[n].doc_id = vec[i].doc_id; out[n].score = s; out[n].pad = 0; n++; }
+        else out[j].score += s;
+    }
+    /* :2097-2106 sort score desc; canonical tie: doc id asc */
+    for (uint32_t i = 1; i < n; i++) { orc_hit x = out[i]; uint32_t j = i;
+        while (j > 0 && better(x.score, x.doc_id, out[j-1].score, out[j-1].doc_id)) { out[j] = out[j-1]; j--; }
+        out[j] = x; }
+    if (n_out) *n_out = n;
+    return 0;
+}

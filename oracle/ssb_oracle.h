@@ -1,0 +1,106 @@
+/*
+ * ssb_oracle.h — CPU ORACLE for the seekstorm_b200 hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is a plain-C restatement of the reference's (SeekStorm 3.3.4) query-time arithmetic for
+ * BM25 AND/OR top-k, brute-force f32 vector top-k and RRF fusion.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may link or call it.
+ * The product path (seekstorm_b200/csrc, libseekstorm_b200.so) never does.
+ *
+ * PARITY PIN STATUS: the reference cannot be built here (Rust, no toolchain), and its own tests
+ * assert only result COUNTS (tests/test.rs:150-208, 693-745) plus aarch64-only kernel-vs-scalar
+ * checks (seekstorm/src/vector_similarity.rs:3008-3146).  Those fixtures are reproduced in
+ * tests/golden/.  BM25 scores / rank order / cosine scores / RRF scores are "parity unpinned" by
+ * the reference; they are pinned here by hand-computed known-answer vectors (tests/golden/).
+ *
+ * All file:line citations are relative to /root/reference/seekstorm/src/.
+ */
+#ifndef SSB_ORACLE_H
+#define SSB_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same values as include/seekstorm_b200.h */
+enum { ORC_QUERY_UNION = 0, ORC_QUERY_INTERSECTION = 1 };
+enum { ORC_RESULT_COUNT = 0, ORC_RESULT_TOPK = 1, ORC_RESULT_TOPKCOUNT = 2 };
+enum { ORC_SIM_DOT = 0, ORC_SIM_COSINE = 1, ORC_SIM_EUCLIDEAN = 2 };
+
+typedef struct { uint64_t doc_id; float score; uint32_t pad; } orc_hit;
+
+/* One committed level (= one 64K-doc block of one shard) in the neutral layout that
+ * include/seekstorm_b200.h's ssb_level_desc uses.  doc_ids ascending per term. */
+typedef struct {
+    uint32_t level_id;
+    uint32_t n_docs;
+    uint32_t n_terms;
+    uint32_t reserved;
+    const uint64_t* term_keys;        /* [n_terms]                         */
+    const uint32_t* posting_offsets;  /* [n_terms+1]                       */
+    const uint16_t* doc_ids;          /* [n_postings] local ids            */
+    const uint16_t* tfs;              /* [n_postings] positions_count      */
+    const uint8_t*  doc_len_bytes;    /* [n_docs] byte4 field length codes */
+} orc_level;
+
+typedef struct orc_index orc_index;
+
+/* ---- doc-length codec: index.rs:4237-4279 (Lucene SmallFloat byte4) ---- */
+uint8_t  orc_int_to_byte4(uint32_t i);
+uint32_t orc_byte4_to_int(uint8_t b);
+
+/* ---- BM25 statistics ---- */
+/* commit.rs:318-325: cache[b] = K*(1-B+B*DLC[b]/avgdl), avgdl = len_sum as f32 / n_docs as f32 */
+void  orc_bm25_cache(uint64_t n_docs, uint64_t len_sum_normalized, float cache[256]);
+/* search.rs:3225-3230: ln((N - df + 0.5)/(df + 0.5) + 1) in f32 */
+float orc_idf(uint64_t n_docs, uint32_t df);
+/* add_result.rs:1450-1452 single term contribution: idf*((tf*(K+1)/(tf+comp))+SIGMA) */
+float orc_bm25_term(float idf, uint32_t tf, float comp);
+
+/* ---- index ---- */
+orc_index* orc_index_new(void);
+void       orc_index_free(orc_index*);
+int        orc_index_add_level(orc_index*, const orc_level*);   /* copies everything */
+/* global statistics (1-shard semantics); finalises the dictionary */
+int        orc_index_commit(orc_index*, uint64_t n_docs, uint64_t len_sum_normalized);
+uint32_t   orc_index_df(const orc_index*, uint64_t term_key);
+
+/* Exhaustive BM25 search, canonical tie rule (score desc, doc id asc).
+ * Candidate semantics: AND intersection.rs:2023-2301, OR union.rs:1168-1479; score
+ * add_result.rs:1429-1482 summed in QUERY ORDER from 0.0; heap min_heap.rs:1193-1259. */
+int orc_search_lexical(const orc_index*, const uint64_t* term_keys, uint32_t n_terms,
+                       uint32_t query_type, uint32_t k, uint32_t result_type,
+                       orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
+
+/* Reference-shaped search: block-max ordered, heap-pruned, same control flow as
+ * single.rs:292-417, intersection.rs:2023-2301, union.rs:1168-1479.  Used as the timed CPU baseline
+ * ("port") and cross-checked against the exhaustive search in tests. */
+int orc_search_lexical_pruned(const orc_index*, const uint64_t* term_keys, uint32_t n_terms,
+                              uint32_t query_type, uint32_t k, uint32_t result_type,
+                              orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
+
+/* ---- vectors ---- */
+void  orc_normalize_f32(float* v, uint32_t n);                        /* vector_similarity.rs:70-74   */
+float orc_dot_f32(const float* a, const float* b, uint32_t n);        /* :1006-1008 scalar, in order  */
+float orc_dot_f32_lanes8(const float* q, const float* e, uint32_t n); /* :1120-1142 8-lane FMA order  */
+float orc_euclidean_f32(const float* a, const float* b, uint32_t n);  /* :912-918 Σ(x−y)²             */
+/* vector.rs:1489-1499: ((score * (1/16129)) + 1) * 0.5, or -score for Euclidean */
+float orc_vector_score_postmap(float score, uint32_t similarity);
+
+/* Exhaustive brute-force scan (vector.rs:1397-1467, AnnMode::All) + top-k (vector.rs:410-497),
+ * canonical tie rule.  rows are used as given (normalise beforehand for cosine, as the reference does at
+ * index time vector.rs:585-596); the query is used as given.  n_threads>1 splits rows (timing only). */
+int orc_search_vector(const float* rows, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims,
+                      uint32_t row_pitch_floats, const float* query, uint32_t similarity, uint32_t k,
+                      uint32_t use_lanes8, uint32_t n_threads, orc_hit* hits, uint32_t* n_hits);
+
+/* ---- hybrid: search.rs:1962-2035 RRF k=0.6, rank from 0; then sort score desc (:2097-2121).
+ * Tie order in the reference is hash-map iteration order; canonical here: doc id asc. */
+int orc_rrf(const orc_hit* lex, uint32_t n_lex, const orc_hit* vec, uint32_t n_vec,
+            orc_hit* out /* [n_lex+n_vec] */, uint32_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

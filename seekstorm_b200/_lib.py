@@ -1,0 +1,107 @@
+"""ctypes loader for libseekstorm_b200.so (the C-ABI in include/seekstorm_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or no B200 is visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libseekstorm_b200.so")
+
+SSB_OK = 0
+K_MAX = 32
+MAX_QUERY_TERMS = 16
+
+QUERY_UNION, QUERY_INTERSECTION = 0, 1
+RESULT_COUNT, RESULT_TOPK, RESULT_TOPKCOUNT = 0, 1, 2
+SIM_DOT, SIM_COSINE, SIM_EUCLIDEAN = 0, 1, 2
+
+
+class SsbHit(C.Structure):
+    _fields_ = [("doc_id", C.c_uint64), ("score", C.c_float), ("pad", C.c_uint32)]
+
+
+class SsbConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_batch", C.c_uint32), ("vector_dims", C.c_uint32),
+                ("vector_similarity", C.c_uint32), ("vector_kernel", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+class SsbLevelDesc(C.Structure):
+    _fields_ = [("level_id", C.c_uint32), ("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("reserved", C.c_uint32),
+                ("term_keys", C.c_void_p), ("posting_offsets", C.c_void_p), ("doc_ids", C.c_void_p),
+                ("tfs", C.c_void_p), ("doc_len_bytes", C.c_void_p)]
+
+
+class SsbLexBatch(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("query_type", C.c_uint32), ("term_offsets", C.c_void_p),
+                ("term_keys", C.c_void_p)]
+
+
+class SsbStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("postings_visited", C.c_uint64), ("reserved", C.c_uint64 * 3)]
+
+
+# every symbol include/seekstorm_b200.h declares
+EXPORTS = [
+    "ssb_abi_version", "ssb_last_error", "ssb_create", "ssb_destroy", "ssb_lexical_add_level",
+    "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
+    "ssb_vector_add_level", "ssb_vector_count", "ssb_search_lexical", "ssb_search_vector", "ssb_search_hybrid",
+    "ssb_rrf_fuse", "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
+    "ssb_stream", "ssb_last_stats",
+]
+
+_lib = None
+
+
+class SsbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the library (raises if it has not been built: run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SsbError(f"{LIB_PATH} not found — build it with __graft_entry__.build(); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+    L.ssb_abi_version.restype = u32
+    L.ssb_last_error.restype = C.c_char_p
+    sigs = {
+        "ssb_create": [C.POINTER(SsbConfig), C.POINTER(vp)],
+        "ssb_destroy": [vp],
+        "ssb_lexical_add_level": [vp, C.POINTER(SsbLevelDesc)],
+        "ssb_lexical_commit": [vp, u64, u64],
+        "ssb_lexical_dict_size": [vp, C.POINTER(u64)],
+        "ssb_lexical_dict_export": [vp, vp, vp, u64],
+        "ssb_lexical_set_global_df": [vp, vp, vp, u64],
+        "ssb_vector_add_level": [vp, u32, vp, u64, vp, u32, u32],
+        "ssb_vector_count": [vp, C.POINTER(u64)],
+        "ssb_search_lexical": [vp, C.POINTER(SsbLexBatch), u32, u32, vp, vp, vp],
+        "ssb_search_vector": [vp, vp, u32, u32, vp, vp],
+        "ssb_search_hybrid": [vp, C.POINTER(SsbLexBatch), vp, u32, vp, vp],
+        "ssb_rrf_fuse": [vp, u32, vp, u32, vp, C.POINTER(u32)],
+        "ssb_search_vector_keys": [vp, vp, u32, u32, vp],
+        "ssb_search_lexical_keys": [vp, C.POINTER(SsbLexBatch), u32, u32, vp, vp],
+        "ssb_merge_keys": [vp, vp, u32, u32, u32, vp, vp],
+        "ssb_sync": [vp],
+        "ssb_last_stats": [vp, C.POINTER(SsbStats)],
+    }
+    for name, args in sigs.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = i32
+    L.ssb_stream.argtypes = [vp]
+    L.ssb_stream.restype = vp
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != SSB_OK:
+        msg = lib().ssb_last_error().decode("utf-8", "replace")
+        raise SsbError(f"libseekstorm_b200 error {rc}: {msg}")

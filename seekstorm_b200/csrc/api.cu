@@ -1,0 +1,364 @@
+// api.cu — the extern "C" ABI of libseekstorm_b200.so (include/seekstorm_b200.h): handle, vector index
+// storage, search entry points, hybrid RRF, key decoding.  No torch types; CUDA runtime only.
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "bm25.h"
+#include "common.cuh"
+#include "vec_scan.h"
+
+namespace ssb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int32_t encode_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
+                           uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle128) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr; cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || !p || qr != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled unavailable"); return SSB_E_CUDA; }
+        fn = (EncodeTiledFn)p;
+    }
+    cuuint64_t gdim[2] = {inner_elems, rows};
+    cuuint64_t gstr[1] = {row_pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return SSB_E_CUDA; }
+    return SSB_OK;
+}
+
+static bool dev_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace ssb
+
+using namespace ssb;
+
+struct ssb_index {
+    ssb_config cfg;
+    int n_sms = 0;
+    cudaStream_t st = nullptr;
+    std::mutex mu;
+    LexIndex* lex = nullptr;
+    // vector index
+    uint32_t dims = 0, dpad = 0;
+    DevBuf<float> rows;
+    DevBuf<uint32_t> doc_ids;
+    uint64_t n_rows = 0;
+    // query workspace
+    DevBuf<float> qpad; DevBuf<float> qstage; DevBuf<uint64_t> scratch; DevBuf<uint64_t> keys_a, keys_b, counts;
+    std::vector<uint64_t> h_keys_a, h_keys_b, h_counts;
+    ssb_stats stats{};
+};
+
+namespace {
+
+int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, uint64_t* keys_out_dev /*[nq_pad][32] min*/) {
+    if (ix->dims == 0) { set_error("no vector index configured (vector_dims = 0)"); return SSB_E_STATE; }
+    if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
+    if (nq == 0) return SSB_OK;
+    const uint32_t nq_pad = (nq + vec::VEC_QT - 1) / vec::VEC_QT * vec::VEC_QT;
+    SSB_TRY(ix->qpad.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
+    const float* qsrc = queries;
+    if (!dev_ptr(queries)) {
+        SSB_TRY(ix->qstage.reserve((size_t)nq * ix->dims, 0, ix->st));
+        SSB_CUDA_TRY(cudaMemcpyAsync(ix->qstage.p, queries, (size_t)nq * ix->dims * 4, cudaMemcpyHostToDevice, ix->st));
+        ix->stats.h2d_bytes += (uint64_t)nq * ix->dims * 4;
+        qsrc = ix->qstage.p;
+    }
+    SSB_TRY(vec::launch_prep_queries(qsrc, nq, ix->dims, ix->dims, ix->qpad.p, nq_pad, ix->dpad,
+                                     ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->st));
+    ix->stats.kernel_launches += 1;
+    if (ix->n_rows == 0) { SSB_CUDA_TRY(cudaMemsetAsync(keys_out_dev, 0, (size_t)nq * LIST * 8, ix->st)); return SSB_OK; }
+    size_t sb = vec::scan_scratch_bytes(ix->n_sms, nq_pad);
+    SSB_TRY(ix->scratch.reserve(sb / 8 + (size_t)nq_pad * LIST, 0, ix->st));
+    vec::ScanArgs a{};
+    a.rows = ix->rows.p; a.doc_ids = ix->doc_ids.p; a.n_rows = ix->n_rows; a.dpad = ix->dpad; a.queries_padded = ix->qpad.p;
+    a.nq_pad = nq_pad; a.k = k; a.similarity = ix->cfg.vector_similarity; a.n_sms = ix->n_sms;
+    a.scratch = ix->scratch.p; a.scratch_bytes = sb;
+    uint64_t* merged = ix->scratch.p + sb / 8;   // [nq_pad][32]
+    a.keys_out = merged;
+    SSB_TRY(vec::launch_scan_ffma(a, ix->st));
+    SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, ix->st));
+    ix->stats.kernel_launches += 2;
+    ix->stats.algorithmic_bytes += (uint64_t)(nq_pad / vec::VEC_QT) * ix->n_rows * ix->dims * 4;
+    return SSB_OK;
+}
+
+void decode_keys(const uint64_t* keys, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+    for (uint32_t q = 0; q < nq; q++) {
+        uint32_t n = 0;
+        for (uint32_t j = 0; j < k && j < LIST; j++) {
+            uint64_t key = keys[(size_t)q * LIST + j];
+            if (!key) break;
+            hits[(size_t)q * k + n].doc_id = key_doc(key);
+            hits[(size_t)q * k + n].score = key_score(key);
+            hits[(size_t)q * k + n].pad = 0;
+            n++;
+        }
+        for (uint32_t j = n; j < k; j++) { hits[(size_t)q * k + j].doc_id = 0; hits[(size_t)q * k + j].score = 0.f; hits[(size_t)q * k + j].pad = 0; }
+        if (n_hits) n_hits[q] = n;
+    }
+}
+
+inline bool hit_better(const ssb_hit& a, const ssb_hit& b) { return a.score > b.score || (a.score == b.score && a.doc_id < b.doc_id); }
+
+}  // namespace
+
+extern "C" {
+
+uint32_t ssb_abi_version(void) { return SSB_ABI_VERSION; }
+const char* ssb_last_error(void) { return g_err; }
+
+int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
+    if (!cfg || !out) { set_error("ssb_create: null argument"); return SSB_E_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device visible: libseekstorm_b200 has no CPU fallback"); return SSB_E_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("device %d out of range (%d visible)", cfg->device, ndev); return SSB_E_INVALID; }
+    if (cfg->vector_similarity > SSB_SIM_EUCLIDEAN) { set_error("bad vector_similarity"); return SSB_E_INVALID; }
+    SSB_CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    SSB_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor); return SSB_E_UNSUPPORTED; }
+    ssb_index* ix = new (std::nothrow) ssb_index();
+    if (!ix) return SSB_E_NOMEM;
+    ix->cfg = *cfg;
+    if (ix->cfg.max_batch == 0) ix->cfg.max_batch = 4096;
+    ix->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking) != cudaSuccess) { delete ix; set_error("stream create failed"); return SSB_E_CUDA; }
+    ix->lex = new LexIndex(ix->st, ix->n_sms, ix->cfg.max_batch);
+    ix->dims = cfg->vector_dims;
+    ix->dpad = (cfg->vector_dims + 31) / 32 * 32;
+    *out = ix;
+    return SSB_OK;
+}
+
+int32_t ssb_destroy(ssb_index* ix) {
+    if (!ix) return SSB_OK;
+    cudaSetDevice(ix->cfg.device);
+    cudaStreamSynchronize(ix->st);
+    delete ix->lex;
+    ix->rows.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->scratch.release();
+    ix->keys_a.release(); ix->keys_b.release(); ix->counts.release();
+    cudaStreamDestroy(ix->st);
+    delete ix;
+    return SSB_OK;
+}
+
+int32_t ssb_lexical_add_level(ssb_index* ix, const ssb_level_desc* level) {
+    if (!ix) { set_error("null index"); return SSB_E_INVALID; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    return ix->lex->add_level(level);
+}
+
+int32_t ssb_lexical_commit(ssb_index* ix, uint64_t n_docs, uint64_t len_sum) {
+    if (!ix) { set_error("null index"); return SSB_E_INVALID; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    return ix->lex->commit(n_docs, len_sum);
+}
+
+int32_t ssb_lexical_dict_size(const ssb_index* ix, uint64_t* n) { if (!ix || !n) return SSB_E_INVALID; return ix->lex->dict_size(n); }
+int32_t ssb_lexical_dict_export(const ssb_index* ix, uint64_t* keys, uint32_t* dfs, uint64_t cap) { if (!ix) return SSB_E_INVALID; return ix->lex->dict_export(keys, dfs, cap); }
+int32_t ssb_lexical_set_global_df(ssb_index* ix, const uint64_t* keys, const uint32_t* dfs, uint64_t n) {
+    if (!ix || (n && (!keys || !dfs))) return SSB_E_INVALID;
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    return ix->lex->set_global_df(keys, dfs, n);
+}
+
+int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride, const uint16_t* local_ids,
+                             uint32_t n, uint32_t dims) {
+    if (!ix || (n && !rows)) { set_error("ssb_vector_add_level: null argument"); return SSB_E_INVALID; }
+    if (ix->dims == 0 || dims != ix->dims) { set_error("dims %u != configured vector_dims %u", dims, ix->dims); return SSB_E_INVALID; }
+    if (n > 65536) { set_error("a level holds at most 65536 vectors"); return SSB_E_INVALID; }
+    if (row_stride == 0) row_stride = dims;
+    if (row_stride < dims) { set_error("row stride < dims"); return SSB_E_INVALID; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    if (n == 0) return SSB_OK;
+    SSB_TRY(ix->rows.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, ix->st));
+    SSB_TRY(ix->doc_ids.reserve(ix->n_rows + n, ix->n_rows, ix->st));
+    float* dst = ix->rows.p + ix->n_rows * ix->dpad;
+    SSB_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ix->dpad * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, ix->st));
+    SSB_TRY(vec::launch_normalize_rows(dst, n, dims, ix->dpad, ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->st));
+    const uint16_t* lid = local_ids; uint16_t* tmp = nullptr;
+    if (local_ids && !dev_ptr(local_ids)) {
+        SSB_CUDA_TRY(cudaMalloc(&tmp, (size_t)n * 2));
+        SSB_CUDA_TRY(cudaMemcpyAsync(tmp, local_ids, (size_t)n * 2, cudaMemcpyHostToDevice, ix->st));
+        lid = tmp;
+    }
+    SSB_TRY(vec::launch_fill_doc_ids(ix->doc_ids.p + ix->n_rows, lid, level_id, n, ix->st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+    if (tmp) cudaFree(tmp);
+    ix->n_rows += n;
+    return SSB_OK;
+}
+
+int32_t ssb_vector_count(const ssb_index* ix, uint64_t* n) { if (!ix || !n) return SSB_E_INVALID; *n = ix->n_rows; return SSB_OK; }
+
+int32_t ssb_search_vector_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, uint64_t* keys_out_dev) {
+    if (!ix || (nq && (!queries || !keys_out_dev))) { set_error("ssb_search_vector_keys: null argument"); return SSB_E_INVALID; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    ix->stats = ssb_stats{};
+    return vec_keys(ix, queries, nq, k, keys_out_dev);
+}
+
+int32_t ssb_search_vector(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+    if (!ix || (nq && (!queries || !hits))) { set_error("ssb_search_vector: null argument"); return SSB_E_INVALID; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    ix->stats = ssb_stats{};
+    if (nq == 0) return SSB_OK;
+    SSB_TRY(ix->keys_a.reserve((size_t)nq * LIST, 0, ix->st));
+    SSB_TRY(vec_keys(ix, queries, nq, k, ix->keys_a.p));
+    ix->h_keys_a.resize((size_t)nq * LIST);
+    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+    ix->stats.d2h_bytes += (uint64_t)nq * LIST * 8;
+    decode_keys(ix->h_keys_a.data(), nq, k, hits, n_hits);
+    return SSB_OK;
+}
+
+int32_t ssb_search_lexical_keys(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, uint32_t result_type, uint64_t* keys_out_dev,
+                                uint64_t* count_dev) {
+    if (!ix || !q) { set_error("ssb_search_lexical_keys: null argument"); return SSB_E_INVALID; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    ix->stats = ssb_stats{};
+    return ix->lex->search_keys(q, k, result_type, keys_out_dev, count_dev, &ix->stats.kernel_launches);
+}
+
+int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, uint32_t result_type, ssb_hit* hits, uint32_t* n_hits,
+                           uint64_t* count_total) {
+    if (!ix || !q || (q->n_queries && k && result_type != SSB_RESULT_COUNT && !hits)) { set_error("ssb_search_lexical: null argument"); return SSB_E_INVALID; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    ix->stats = ssb_stats{};
+    const uint32_t nq = q->n_queries;
+    if (nq == 0) return SSB_OK;
+    SSB_TRY(ix->keys_a.reserve((size_t)nq * LIST, 0, ix->st));
+    SSB_TRY(ix->counts.reserve(nq, 0, ix->st));
+    SSB_TRY(ix->lex->search_keys(q, k, result_type, ix->keys_a.p, ix->counts.p, &ix->stats.kernel_launches));
+    ix->h_keys_a.resize((size_t)nq * LIST); ix->h_counts.resize(nq);
+    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
+    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_counts.data(), ix->counts.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+    ix->stats.d2h_bytes += (uint64_t)nq * (LIST * 8 + 8);
+    if (hits && k && result_type != SSB_RESULT_COUNT) decode_keys(ix->h_keys_a.data(), nq, k, hits, n_hits);
+    else if (n_hits) for (uint32_t i = 0; i < nq; i++) n_hits[i] = 0;
+    if (count_total) for (uint32_t i = 0; i < nq; i++) count_total[i] = ix->h_counts[i];
+    LexStats ls = ix->lex->last_stats();
+    ix->stats.postings_visited = ls.postings_visited;
+    ix->stats.algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 12 + ls.items_processed * 24;
+    ix->stats.reserved[0] = ls.probes; ix->stats.reserved[1] = ls.items_processed; ix->stats.reserved[2] = ls.items_skipped;
+    return SSB_OK;
+}
+
+int32_t ssb_rrf_fuse(const ssb_hit* lex, uint32_t n_lex, const ssb_hit* vec, uint32_t n_vec, ssb_hit* out, uint32_t* n_out) {
+    // search.rs:1962-2035: k = 0.6, rank from 0 over each list sorted by score desc; then :2097-2106 sort desc.
+    if ((n_lex && !lex) || (n_vec && !vec) || !out) { set_error("ssb_rrf_fuse: null argument"); return SSB_E_INVALID; }
+    const float kf = 0.6f;
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < n_lex; i++) {
+        volatile float denom = kf + (float)i; float s = 1.0f / denom;
+        uint32_t j = 0; for (; j < n; j++) if (out[j].doc_id == lex[i].doc_id) break;
+        if (j == n) { out[n].doc_id = lex[i].doc_id; out[n].score = s; out[n].pad = 0; n++; } else out[j].score = s;
+    }
+    for (uint32_t i = 0; i < n_vec; i++) {
+        volatile float denom = kf + (float)i; float s = 1.0f / denom;
+        uint32_t j = 0; for (; j < n; j++) if (out[j].doc_id == vec[i].doc_id) break;
+        if (j == n) { out[n].doc_id = vec[i].doc_id; out[n].score = s; out[n].pad = 0; n++; }
+        else { volatile float sum = out[j].score + s; out[j].score = sum; }
+    }
+    std::stable_sort(out, out + n, hit_better);
+    if (n_out) *n_out = n;
+    return SSB_OK;
+}
+
+int32_t ssb_search_hybrid(ssb_index* ix, const ssb_lex_batch* q, const float* queries, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+    if (!ix || !q || !queries || !hits) { set_error("ssb_search_hybrid: null argument"); return SSB_E_INVALID; }
+    if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    ix->stats = ssb_stats{};
+    const uint32_t nq = q->n_queries;
+    if (nq == 0) return SSB_OK;
+    SSB_TRY(ix->keys_a.reserve((size_t)nq * LIST, 0, ix->st));
+    SSB_TRY(ix->keys_b.reserve((size_t)nq * LIST, 0, ix->st));
+    SSB_TRY(ix->lex->search_keys(q, k, SSB_RESULT_TOPK, ix->keys_a.p, nullptr, &ix->stats.kernel_launches));
+    SSB_TRY(vec_keys(ix, queries, nq, k, ix->keys_b.p));
+    ix->h_keys_a.resize((size_t)nq * LIST); ix->h_keys_b.resize((size_t)nq * LIST);
+    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
+    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_b.data(), ix->keys_b.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+    ix->stats.d2h_bytes += (uint64_t)nq * LIST * 16;
+    std::vector<ssb_hit> a(k), b(k), f(2 * (size_t)k);
+    for (uint32_t i = 0; i < nq; i++) {
+        uint32_t na = 0, nb = 0, nf = 0;
+        decode_keys(ix->h_keys_a.data() + (size_t)i * LIST, 1, k, a.data(), &na);
+        decode_keys(ix->h_keys_b.data() + (size_t)i * LIST, 1, k, b.data(), &nb);
+        ssb_rrf_fuse(a.data(), na, b.data(), nb, f.data(), &nf);
+        uint32_t n = nf < k ? nf : k;     // search.rs:2117-2119 truncate(length)
+        for (uint32_t j = 0; j < k; j++) hits[(size_t)i * k + j] = j < n ? f[j] : ssb_hit{0, 0.f, 0};
+        if (n_hits) n_hits[i] = n;
+    }
+    return SSB_OK;
+}
+
+int32_t ssb_merge_keys(ssb_index* ix, const uint64_t* keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+    if (!ix || !keys_dev || !hits) { set_error("ssb_merge_keys: null argument"); return SSB_E_INVALID; }
+    if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    if (nq == 0) return SSB_OK;
+    SSB_TRY(ix->keys_b.reserve((size_t)nq * LIST, 0, ix->st));
+    SSB_TRY(vec::launch_merge_lists(keys_dev, n_lists, nq, ix->keys_b.p, ix->st));
+    ix->stats.kernel_launches += 1;
+    ix->h_keys_b.resize((size_t)nq * LIST);
+    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_b.data(), ix->keys_b.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+    decode_keys(ix->h_keys_b.data(), nq, k, hits, n_hits);
+    return SSB_OK;
+}
+
+int32_t ssb_sync(ssb_index* ix) {
+    if (!ix) return SSB_E_INVALID;
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+    return SSB_OK;
+}
+
+void* ssb_stream(ssb_index* ix) { return ix ? (void*)ix->st : nullptr; }
+
+int32_t ssb_last_stats(const ssb_index* ix, ssb_stats* out) {
+    if (!ix || !out) return SSB_E_INVALID;
+    *out = ix->stats;
+    return SSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// vec_scan.cu — brute-force f32 vector scan with fused top-k (sm_100a).
+//
+// Replaces the record loop of search_vector_shard (vector.rs:1397-1467): for every record,
+// similarity = dot_f32 / -euclidean_f32 (vector_similarity.rs:1006-1008, 912-918, 1120-1142) and
+// TopK::push (vector.rs:410-497), for a batch of queries per corpus pass.
+//
+// Layout: corpus = row-major f32 [n_rows, Dpad] (Dpad = dims rounded up to 32, zero padded), no AoS
+// header (the reference's 24-byte VectorHeader + embedding record, vector.rs:62-73, is split at load:
+// doc ids live in a separate u32 array).  HBM-bound: algorithmic bytes per pass = n_rows*dims*4.
+//
+// Kernel scan_ffma: persistent CTAs (one per SM), 8 consumer warps + 1 TMA producer warp.
+//   producer: cp.async.bulk.tensor.2d of a [256 rows x 32 floats] corpus box (SWIZZLE_128B) and the
+//             [16 queries x 32 floats] query box into a 5-stage mbarrier ring.
+//   consumers: warp w owns rows (w>>1)*64 + lane + {0,32} of the tile and queries (w&1)*8..+8;
+//             FP32 FFMA accumulation over the k-chunks (conflict-free swizzled LDS.128 for rows,
+//             broadcast LDS.128 for queries), then a warp-shuffle top-k insert per finished tile.
+//   per-warp lists -> scratch; merge_lists kernel reduces them to the final per-query top-k.
+#include "common.cuh"
+#include "vec_scan.h"
+
+namespace ssb {
+namespace vec {
+
+constexpr int KC = 32;                  // floats per k-chunk (128 B = one swizzle row)
+constexpr int TILE_ROWS = 256;
+constexpr int QT = VEC_QT;              // queries per pass (16)
+constexpr int STAGES = 5;
+constexpr int CWARPS = 8;
+constexpr int THREADS = (CWARPS + 1) * 32;
+constexpr int A_BYTES = TILE_ROWS * KC * 4;  // 32 KB
+constexpr int Q_BYTES = QT * KC * 4;         // 2 KB
+constexpr int STAGE_TX = A_BYTES + Q_BYTES;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + Q_BYTES) + 2 * STAGES * 8;
+
+template <int SIM>
+__global__ void __launch_bounds__(THREADS, 1)
+scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
+          uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
+          const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*CWARPS/2][QT][32]*/) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = base;                                  // [STAGES][A_BYTES], each 1024-aligned
+    uint8_t* sQ = base + STAGES * A_BYTES;               // [STAGES][Q_BYTES]
+    uint64_t* full = (uint64_t*)(sQ + STAGES * Q_BYTES); // [STAGES]
+    uint64_t* empty = full + STAGES;                     // [STAGES]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t group = blockIdx.y;                   // which block of QT queries
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CWARPS); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == CWARPS) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmQ);
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
+                    uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full[s], STAGE_TX);
+                    tma_load_2d(sA + s * A_BYTES, &tmA, (int)(kc * KC), (int)(tile * TILE_ROWS), &full[s]);
+                    tma_load_2d(sQ + s * Q_BYTES, &tmQ, (int)(kc * KC), (int)(group * QT), &full[s]);
+                }
+            }
+        }
+    } else {
+        // ===== consumers =====
+        const int rg = warp >> 1;            // row group 0..3 (64 rows each)
+        const int qh = (warp & 1) * 8;       // first query of this warp's half
+        const int r0 = rg * 64 + lane;       // rows r0 and r0+32; (r0+32)&7 == r0&7
+        const int sw = r0 & 7;
+        float acc[2][8];
+        uint64_t L[8];
+        uint32_t thr[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { L[q] = 0; thr[q] = 0; acc[0][q] = 0.f; acc[1][q] = 0.f; }
+
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
+                uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                const float4* A = (const float4*)(sA + s * A_BYTES);
+                const float4* Q = (const float4*)(sQ + s * Q_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    float4 a0 = A[r0 * 8 + (kk ^ sw)];
+                    float4 a1 = A[(r0 + 32) * 8 + (kk ^ sw)];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        float4 qv = Q[(qh + q) * 8 + kk];
+                        if (SIM == SSB_SIM_EUCLIDEAN) {
+                            float d;
+                            d = qv.x - a0.x; acc[0][q] = fmaf(d, d, acc[0][q]);
+                            d = qv.y - a0.y; acc[0][q] = fmaf(d, d, acc[0][q]);
+                            d = qv.z - a0.z; acc[0][q] = fmaf(d, d, acc[0][q]);
+                            d = qv.w - a0.w; acc[0][q] = fmaf(d, d, acc[0][q]);
+                            d = qv.x - a1.x; acc[1][q] = fmaf(d, d, acc[1][q]);
+                            d = qv.y - a1.y; acc[1][q] = fmaf(d, d, acc[1][q]);
+                            d = qv.z - a1.z; acc[1][q] = fmaf(d, d, acc[1][q]);
+                            d = qv.w - a1.w; acc[1][q] = fmaf(d, d, acc[1][q]);
+                        } else {
+                            acc[0][q] = fmaf(a0.x, qv.x, acc[0][q]);
+                            acc[0][q] = fmaf(a0.y, qv.y, acc[0][q]);
+                            acc[0][q] = fmaf(a0.z, qv.z, acc[0][q]);
+                            acc[0][q] = fmaf(a0.w, qv.w, acc[0][q]);
+                            acc[1][q] = fmaf(a1.x, qv.x, acc[1][q]);
+                            acc[1][q] = fmaf(a1.y, qv.y, acc[1][q]);
+                            acc[1][q] = fmaf(a1.z, qv.z, acc[1][q]);
+                            acc[1][q] = fmaf(a1.w, qv.w, acc[1][q]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+
+                if (kc + 1 == n_kchunks) {
+                    // ---- tile finished: fused top-k (TopK::push, vector.rs:410-497) ----
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        uint32_t row = tile * TILE_ROWS + (uint32_t)r0 + 32u * j;
+                        bool valid = row < n_rows;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            float sc = (SIM == SSB_SIM_EUCLIDEAN) ? -acc[j][q] : acc[j][q];
+                            acc[j][q] = 0.f;
+                            uint32_t so = ord_f32(sc);
+                            unsigned m = __ballot_sync(FULL, valid && so >= thr[q] && sc == sc);
+                            while (m) {
+                                int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                uint32_t so_s = __shfl_sync(FULL, so, src);
+                                uint32_t row_s = __shfl_sync(FULL, row, src);
+                                uint32_t doc = doc_ids ? __ldg(&doc_ids[row_s]) : row_s;
+                                uint64_t key = ((uint64_t)so_s << 32) | (uint64_t)(0xFFFFFFFFu - doc);
+                                wl_insert(L[q], key, lane);
+                            }
+                            thr[q] = (uint32_t)(shfl64(L[q], (int)k - 1) >> 32);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- publish the warp's lists: scratch[group][list][q][lane], list = (cta*4 + rg) ----
+        const uint32_t n_lists = gridDim.x * (CWARPS / 2);
+        uint64_t* out = scratch + ((size_t)group * n_lists + (size_t)blockIdx.x * (CWARPS / 2) + rg) * QT * LIST;
+#pragma unroll
+        for (int q = 0; q < 8; q++) out[(qh + q) * LIST + lane] = L[q];
+    }
+}
+
+// Merge `n_lists` descending 32-lists per query into one.  in: [n_groups][n_lists][qt][32] when
+// qt_major==0 ... generic form: list l of query q lives at in[(q / qt) * n_lists * qt * 32 + l * qt * 32 + (q % qt) * 32].
+__global__ void __launch_bounds__(256)
+merge_lists(const uint64_t* __restrict__ in, uint32_t n_lists, uint32_t qt, uint64_t* __restrict__ out /*[nq][32]*/) {
+    __shared__ uint64_t sm[8][LIST];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x;
+    const uint64_t* base = in + (size_t)(q / qt) * n_lists * qt * LIST + (size_t)(q % qt) * LIST;
+    uint64_t L = 0;
+    for (uint32_t l = warp; l < n_lists; l += 8) {
+        uint64_t B = __ldg(&base[(size_t)l * qt * LIST + lane]);
+        if (__any_sync(FULL, B != 0)) L = wl_merge(L, B, lane);
+    }
+    sm[warp][lane] = L;
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < 8; w++) L = wl_merge(L, sm[w][lane], lane);
+        out[(size_t)q * LIST + lane] = L;
+    }
+}
+
+// queries [nq][dims] (row stride qstride) -> padded [nq_pad][dpad], optionally L2-normalised
+// (normalize_f32, vector_similarity.rs:70-74; applied to the query at search.rs:1464-1475).
+__global__ void prep_queries(const float* __restrict__ q, uint32_t nq, uint32_t dims, uint64_t qstride,
+                             float* __restrict__ out, uint32_t nq_pad, uint32_t dpad, int normalize) {
+    const int lane = threadIdx.x & 31;
+    uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nq_pad) return;
+    float* o = out + (size_t)row * dpad;
+    if (row >= nq) { for (uint32_t i = lane; i < dpad; i += 32) o[i] = 0.f; return; }
+    const float* src = q + (size_t)row * qstride;
+    float f = 1.f;
+    if (normalize) {
+        float s = 0.f;
+        for (uint32_t i = lane; i < dims; i += 32) { float v = src[i]; s = fmaf(v, v, s); }
+        for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(FULL, s, m);
+        f = 1.0f / sqrtf(s);
+    }
+    for (uint32_t i = lane; i < dpad; i += 32) o[i] = i < dims ? src[i] * f : 0.f;
+}
+
+// corpus rows in place: [n][dpad]; normalise first `dims` entries (vector.rs:585-596), zero the padding
+__global__ void normalize_rows(float* __restrict__ rows, uint64_t n, uint32_t dims, uint32_t dpad, int normalize) {
+    const int lane = threadIdx.x & 31;
+    uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    float* r = rows + row * dpad;
+    float f = 1.f;
+    if (normalize) {
+        float s = 0.f;
+        for (uint32_t i = lane; i < dims; i += 32) { float v = r[i]; s = fmaf(v, v, s); }
+        for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(FULL, s, m);
+        f = 1.0f / sqrtf(s);
+    }
+    for (uint32_t i = lane; i < dpad; i += 32) r[i] = i < dims ? r[i] * f : 0.f;
+}
+
+__global__ void fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (level_id << 16) | (local_ids ? (uint32_t)local_ids[i] : i);
+}
+
+// ---------------------------------------------------------------- host side
+int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st) {
+    CUtensorMap tmA, tmQ;
+    uint32_t n_tiles = (uint32_t)((a.n_rows + TILE_ROWS - 1) / TILE_ROWS);
+    uint32_t n_groups = a.nq_pad / QT;
+    if (n_tiles == 0 || n_groups == 0) return SSB_OK;
+    SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, KC, TILE_ROWS, 1));
+    SSB_TRY(encode_tmap_2d_f32(&tmQ, a.queries_padded, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, KC, QT, 0));
+    uint32_t gx = n_tiles < (uint32_t)a.n_sms ? n_tiles : (uint32_t)a.n_sms;
+    dim3 grid(gx, n_groups);
+    uint32_t n_lists = gx * (CWARPS / 2);
+    if ((size_t)n_groups * n_lists * QT * LIST * 8 > a.scratch_bytes) {
+        set_error("vector scan scratch too small"); return SSB_E_STATE;
+    }
+    auto kern = a.similarity == SSB_SIM_EUCLIDEAN ? scan_ffma<SSB_SIM_EUCLIDEAN> : scan_ffma<SSB_SIM_DOT>;
+    static bool attr_set[2] = {false, false};
+    int ai = a.similarity == SSB_SIM_EUCLIDEAN;
+    if (!attr_set[ai]) {
+        SSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set[ai] = true;
+    }
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
+                                            a.scratch);
+    SSB_CUDA_TRY(cudaGetLastError());
+    merge_lists<<<a.nq_pad, 256, 0, st>>>(a.scratch, n_lists, QT, a.keys_out);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad) {
+    return (size_t)(nq_pad / QT) * (size_t)n_sms * (CWARPS / 2) * QT * LIST * 8;
+}
+
+int32_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, float* out,
+                            uint32_t nq_pad, uint32_t dpad, int normalize, cudaStream_t st) {
+    if (nq_pad == 0) return SSB_OK;
+    prep_queries<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, dims, qstride, out, nq_pad, dpad, normalize);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_normalize_rows(float* rows, uint64_t n, uint32_t dims, uint32_t dpad, int normalize, cudaStream_t st) {
+    if (n == 0) return SSB_OK;
+    normalize_rows<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rows, n, dims, dpad, normalize);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n, cudaStream_t st) {
+    if (n == 0) return SSB_OK;
+    fill_doc_ids<<<(n + 255) / 256, 256, 0, st>>>(out, local_ids, level_id, n);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_merge_lists(const uint64_t* in, uint32_t n_lists, uint32_t nq, uint64_t* out, cudaStream_t st) {
+    if (nq == 0) return SSB_OK;
+    // in: [n_lists][nq][32]  == generic form with qt = nq (single group)
+    merge_lists<<<nq, 256, 0, st>>>(in, n_lists, nq, out);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+}  // namespace vec
+}  // namespace ssb

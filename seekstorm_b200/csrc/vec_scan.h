@@ -1,0 +1,36 @@
+// vec_scan.h — host-visible launchers of the vector kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ssb {
+namespace vec {
+
+constexpr int VEC_QT = 16;  // queries per corpus pass of the FFMA kernel
+
+struct ScanArgs {
+    const float* rows;            // [n_rows][dpad]
+    const uint32_t* doc_ids;      // [n_rows] or nullptr
+    uint64_t n_rows;
+    uint32_t dpad;                // multiple of 32
+    const float* queries_padded;  // [nq_pad][dpad], nq_pad multiple of VEC_QT
+    uint32_t nq_pad;
+    uint32_t k;
+    uint32_t similarity;
+    int n_sms;
+    uint64_t* scratch;
+    size_t scratch_bytes;
+    uint64_t* keys_out;           // [nq_pad][32]
+};
+
+int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
+size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);
+int32_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, float* out,
+                            uint32_t nq_pad, uint32_t dpad, int normalize, cudaStream_t st);
+int32_t launch_normalize_rows(float* rows, uint64_t n, uint32_t dims, uint32_t dpad, int normalize, cudaStream_t st);
+int32_t launch_fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n, cudaStream_t st);
+// in: [n_lists][nq][32] descending lists -> out [nq][32]
+int32_t launch_merge_lists(const uint64_t* in, uint32_t n_lists, uint32_t nq, uint64_t* out, cudaStream_t st);
+
+}  // namespace vec
+}  // namespace ssb

@@ -1,0 +1,355 @@
+"""Host-side mirror of the reference's search interface for the hot path, on top of the C-ABI.
+
+Mirrors (names, argument meaning, error behaviour) of /root/reference/seekstorm/src/:
+  * `Search::search`                        search.rs:1134-1150 (impl 1153-2131)  -> Index.search
+  * `QueryType`, `ResultType`, `SearchMode`, `AnnMode`   search.rs:120-185, vector_similarity.rs:43-67
+  * `ResultObject` / `Result`               search.rs:186-213, min_heap.rs:17-40
+  * per-shard seams search_lexical_shard (search.rs:2427-2458) / search_vector_shard (vector.rs:1105-1115)
+    -> Index.search_lexical_batch / Index.search_vector_batch (batched: the GPU path amortises launches)
+
+The reference's `search` is infallible by type: failures yield an empty `ResultObject` (search.rs:1630-1631).
+The same holds here for "term not in dictionary"/empty queries; programming errors (k > 32, no GPU,
+library missing) raise `SsbError` — there is no CPU fallback.
+
+The tokenizer (tokenizer.rs) is out of scope: query strings are split on whitespace, a leading '+' marks a
+mandatory term (tokenizer.rs:546-563); terms are mapped to 64-bit keys by `term_key_fn`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import SsbConfig, SsbHit, SsbLevelDesc, SsbLexBatch, SsbStats, check, lib
+
+
+class QueryType(enum.IntEnum):
+    """search.rs `QueryType` (Phrase / Not are outside the hot-path scope)."""
+    Union = 0
+    Intersection = 1
+
+
+class ResultType(enum.IntEnum):
+    """search.rs:150-175."""
+    Count = 0
+    Topk = 1
+    TopkCount = 2
+
+
+class VectorSimilarity(enum.IntEnum):
+    """vector_similarity.rs:20-30."""
+    Dot = 0
+    Cosine = 1
+    Euclidean = 2
+
+
+class AnnMode(enum.Enum):
+    """vector_similarity.rs:43-67; only exhaustive search is in scope."""
+    All = "All"
+
+
+@dataclass
+class SearchMode:
+    """search.rs `SearchMode::{Lexical, Vector{..}, Hybrid{..}}`."""
+    kind: str = "Lexical"
+    similarity_threshold: Optional[float] = None
+    ann_mode: AnnMode = AnnMode.All
+
+    @staticmethod
+    def Lexical():
+        return SearchMode("Lexical")
+
+    @staticmethod
+    def Vector(similarity_threshold=None, ann_mode=AnnMode.All):
+        return SearchMode("Vector", similarity_threshold, ann_mode)
+
+    @staticmethod
+    def Hybrid(similarity_threshold=None, ann_mode=AnnMode.All):
+        return SearchMode("Hybrid", similarity_threshold, ann_mode)
+
+
+@dataclass
+class Result:
+    """min_heap.rs:17-40."""
+    doc_id: int
+    score: float
+
+
+@dataclass
+class ResultObject:
+    """search.rs:186-213 (facets / suggestions are outside the hot path)."""
+    original_query: str = ""
+    query: str = ""
+    query_terms: list = field(default_factory=list)
+    result_count: int = 0
+    result_count_total: int = 0
+    results: list = field(default_factory=list)
+    observed_vector_count: int = 0
+    observed_cluster_count: int = 0
+
+
+def fnv1a64(term: str) -> int:
+    h = 0xCBF29CE484222325
+    for b in term.encode("utf-8"):
+        h = ((h ^ b) * 0x100000001B3) & ((1 << 64) - 1)
+    return h & ~7
+
+
+def synthetic_term_key(term: str) -> int:
+    """Key of a synthetic term 't<id>' (synth.py) or FNV-1a of any other string; low 3 bits clear
+    (reserved for the n-gram type in the reference, index.rs:4165-4225)."""
+    from .synth import splitmix64
+    if len(term) > 1 and term[0] == "t" and term[1:].isdigit():
+        return splitmix64(int(term[1:])) & ~7
+    return fnv1a64(term)
+
+
+def _addr(x):
+    """Address of a numpy array / torch tensor (host or device) or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch.Tensor
+
+
+def _hits_array(n):
+    return np.zeros(n, dtype=np.dtype([("doc_id", "<u8"), ("score", "<f4"), ("pad", "<u4")]))
+
+
+class Index:
+    """One shard's GPU-resident mirror: committed lexical levels + vector levels on one B200."""
+
+    def __init__(self, device: int = 0, vector_dims: int = 0,
+                 vector_similarity: VectorSimilarity = VectorSimilarity.Cosine, max_batch: int = 4096,
+                 term_key_fn: Callable[[str], int] = synthetic_term_key):
+        self._h = C.c_void_p()
+        cfg = SsbConfig(device, max_batch, vector_dims, int(vector_similarity), 0, (C.c_uint32 * 3)(0, 0, 0))
+        check(lib().ssb_create(C.byref(cfg), C.byref(self._h)))
+        self.vector_dims = vector_dims
+        self.vector_similarity = VectorSimilarity(vector_similarity)
+        self.term_key_fn = term_key_fn
+        self.indexed_doc_count = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().ssb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ load
+    def add_lexical_level(self, level_id: int, n_docs: int, term_keys, posting_offsets, doc_ids, tfs, doc_len_bytes):
+        """One committed 64K-doc level in the neutral layout (arrays: numpy on host or torch on the device)."""
+        n_terms = int(term_keys.shape[0])
+        d = SsbLevelDesc(level_id, n_docs, n_terms, 0, _addr(term_keys), _addr(posting_offsets), _addr(doc_ids),
+                         _addr(tfs), _addr(doc_len_bytes))
+        check(lib().ssb_lexical_add_level(self._h, C.byref(d)))
+
+    def add_synth_level(self, lv):
+        """Convenience: a seekstorm_b200.synth.Level (tensors on CPU or on this index's device)."""
+        if lv.term_keys.is_cuda:
+            self.add_lexical_level(lv.level_id, lv.n_docs, lv.term_keys, lv.posting_offsets, lv.doc_ids, lv.tfs,
+                                   lv.doc_len_bytes)
+        else:
+            n = lv.to_numpy()
+            self.add_lexical_level(n["level_id"], n["n_docs"], n["term_keys"], n["posting_offsets"], n["doc_ids"],
+                                   n["tfs"], n["doc_len_bytes"])
+
+    def commit(self, n_docs: int, len_sum_normalized: int):
+        """Global statistics of the whole shard (commit.rs:318-319) + directory / block-max build."""
+        check(lib().ssb_lexical_commit(self._h, n_docs, len_sum_normalized))
+        self.indexed_doc_count = n_docs
+
+    def dict_export(self):
+        n = C.c_uint64(0)
+        check(lib().ssb_lexical_dict_size(self._h, C.byref(n)))
+        keys = np.zeros(n.value, dtype=np.uint64)
+        dfs = np.zeros(n.value, dtype=np.uint32)
+        check(lib().ssb_lexical_dict_export(self._h, keys.ctypes.data, dfs.ctypes.data, n.value))
+        return keys, dfs
+
+    def set_global_df(self, keys: np.ndarray, dfs: np.ndarray):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        dfs = np.ascontiguousarray(dfs, dtype=np.uint32)
+        check(lib().ssb_lexical_set_global_df(self._h, keys.ctypes.data, dfs.ctypes.data, len(keys)))
+
+    def add_vector_level(self, level_id: int, rows, local_ids=None):
+        """rows: [n, dims] f32 (numpy or torch, host or device), n <= 65536."""
+        n, dims = int(rows.shape[0]), int(rows.shape[1])
+        stride = rows.strides[0] // 4 if isinstance(rows, np.ndarray) else rows.stride(0)
+        check(lib().ssb_vector_add_level(self._h, level_id, _addr(rows), stride, _addr(local_ids), n, dims))
+
+    def add_vectors(self, rows, first_level: int = 0):
+        """Split a big [N, dims] matrix into 64K-row levels (doc_id = row index when first_level = 0)."""
+        n = int(rows.shape[0])
+        for s in range(0, n, 65536):
+            self.add_vector_level(first_level + s // 65536, rows[s:min(n, s + 65536)])
+
+    @property
+    def vector_count(self) -> int:
+        n = C.c_uint64(0)
+        check(lib().ssb_vector_count(self._h, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ batched shard-level search
+    def _lex_batch(self, queries_keys: Sequence[Sequence[int]], query_type: QueryType):
+        offs = np.zeros(len(queries_keys) + 1, dtype=np.uint32)
+        for i, q in enumerate(queries_keys):
+            if len(q) > _lib.MAX_QUERY_TERMS:
+                raise _lib.SsbError(f"query {i} has {len(q)} terms (> {_lib.MAX_QUERY_TERMS})")
+            offs[i + 1] = offs[i] + len(q)
+        keys = np.zeros(max(int(offs[-1]), 1), dtype=np.uint64)
+        p = 0
+        for q in queries_keys:
+            for t in q:
+                keys[p] = t
+                p += 1
+        b = SsbLexBatch(len(queries_keys), int(query_type), offs.ctypes.data, keys.ctypes.data)
+        return b, (offs, keys)
+
+    def search_lexical_batch(self, queries_keys, query_type: QueryType, k: int,
+                             result_type: ResultType = ResultType.TopkCount):
+        """Batched search_lexical_shard.  Returns (list of [(doc_id, score)...], counts ndarray)."""
+        nq = len(queries_keys)
+        b, keep = self._lex_batch(queries_keys, query_type)
+        hits = _hits_array(max(nq * max(k, 1), 1))
+        n_hits = np.zeros(max(nq, 1), dtype=np.uint32)
+        counts = np.zeros(max(nq, 1), dtype=np.uint64)
+        check(lib().ssb_search_lexical(self._h, C.byref(b), k, int(result_type), hits.ctypes.data, n_hits.ctypes.data,
+                                       counts.ctypes.data))
+        out = []
+        for i in range(nq):
+            h = hits[i * k: i * k + int(n_hits[i])]
+            out.append([(int(d), float(s)) for d, s in zip(h["doc_id"], h["score"])])
+        return out, counts[:nq]
+
+    def search_vector_batch(self, queries, k: int):
+        """Batched search_vector_shard (AnnMode::All).  queries: [nq, dims] f32 numpy/torch."""
+        nq = int(queries.shape[0])
+        if isinstance(queries, np.ndarray):
+            queries = np.ascontiguousarray(queries, dtype=np.float32)
+        hits = _hits_array(max(nq * k, 1))
+        n_hits = np.zeros(max(nq, 1), dtype=np.uint32)
+        check(lib().ssb_search_vector(self._h, _addr(queries), nq, k, hits.ctypes.data, n_hits.ctypes.data))
+        out = []
+        for i in range(nq):
+            h = hits[i * k: i * k + int(n_hits[i])]
+            out.append([(int(d), float(s)) for d, s in zip(h["doc_id"], h["score"])])
+        return out
+
+    def search_hybrid_batch(self, queries_keys, query_type: QueryType, queries, k: int):
+        nq = len(queries_keys)
+        b, keep = self._lex_batch(queries_keys, query_type)
+        if isinstance(queries, np.ndarray):
+            queries = np.ascontiguousarray(queries, dtype=np.float32)
+        hits = _hits_array(max(nq * k, 1))
+        n_hits = np.zeros(max(nq, 1), dtype=np.uint32)
+        check(lib().ssb_search_hybrid(self._h, C.byref(b), _addr(queries), k, hits.ctypes.data, n_hits.ctypes.data))
+        out = []
+        for i in range(nq):
+            h = hits[i * k: i * k + int(n_hits[i])]
+            out.append([(int(d), float(s)) for d, s in zip(h["doc_id"], h["score"])])
+        return out
+
+    def last_stats(self) -> dict:
+        s = SsbStats()
+        check(lib().ssb_last_stats(self._h, C.byref(s)))
+        return dict(kernel_launches=s.kernel_launches, algorithmic_bytes=s.algorithmic_bytes, h2d_bytes=s.h2d_bytes,
+                    d2h_bytes=s.d2h_bytes, postings_visited=s.postings_visited, probes=s.reserved[0],
+                    items_processed=s.reserved[1], items_skipped=s.reserved[2])
+
+    # ------------------------------------------------------------------ device-resident API (bench / multi-GPU)
+    def search_vector_keys(self, queries_dev, k: int, keys_out_dev):
+        check(lib().ssb_search_vector_keys(self._h, _addr(queries_dev), int(queries_dev.shape[0]), k, _addr(keys_out_dev)))
+
+    def search_lexical_keys(self, batch_struct, k: int, result_type: ResultType, keys_out_dev, counts_dev=None):
+        check(lib().ssb_search_lexical_keys(self._h, C.byref(batch_struct), k, int(result_type), _addr(keys_out_dev),
+                                            _addr(counts_dev)))
+
+    def merge_keys(self, keys_dev, n_lists: int, nq: int, k: int):
+        hits = _hits_array(max(nq * k, 1))
+        n_hits = np.zeros(max(nq, 1), dtype=np.uint32)
+        check(lib().ssb_merge_keys(self._h, _addr(keys_dev), n_lists, nq, k, hits.ctypes.data, n_hits.ctypes.data))
+        return [[(int(d), float(s)) for d, s in zip(hits[i * k: i * k + int(n_hits[i])]["doc_id"],
+                                                     hits[i * k: i * k + int(n_hits[i])]["score"])] for i in range(nq)]
+
+    def sync(self):
+        check(lib().ssb_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return lib().ssb_stream(self._h) or 0
+
+    # ------------------------------------------------------------------ the reference's public call
+    def search(self, query_string: str, query_vector=None, query_type_default: QueryType = QueryType.Union,
+               search_mode: SearchMode = None, enable_empty_query: bool = False, offset: int = 0, length: int = 10,
+               result_type: ResultType = ResultType.TopkCount, include_uncommitted: bool = False,
+               field_filter: Sequence[str] = (), query_facets: Sequence = (), facet_filter: Sequence = (),
+               result_sort: Sequence = (), query_rewriting=None) -> ResultObject:
+        """`Search::search` (search.rs:1134-1150) for committed data, 1-shard semantics.
+
+        Unsupported reference features (facets, filters, sort, uncommitted, rewriting, phrase) raise
+        NotImplementedError rather than being silently ignored."""
+        if field_filter or query_facets or facet_filter or result_sort or include_uncommitted:
+            raise NotImplementedError("facets / filters / sort / uncommitted search are outside the GPU hot path")
+        search_mode = search_mode or SearchMode.Lexical()
+        ro = ResultObject(original_query=query_string, query=query_string)
+        heap = offset + length                       # search.rs:1708 per-shard length = offset+length
+        # tokenizer stand-in: whitespace, '+' = mandatory (tokenizer.rs:546-563); unique terms (search.rs:3023-3039)
+        toks = query_string.split()
+        if any(t.startswith('"') or t.startswith("-") for t in toks):
+            raise NotImplementedError("phrase / NOT operators are outside the GPU hot path")
+        qt = query_type_default
+        if toks and all(t.startswith("+") for t in toks):
+            qt = QueryType.Intersection
+        terms = []
+        for t in toks:
+            t = t.lstrip("+")
+            if t and t not in terms:
+                terms.append(t)
+        ro.query_terms = list(terms)
+        keys = [self.term_key_fn(t) for t in terms]
+        lex, vec, total = [], [], 0
+        want_lex = search_mode.kind in ("Lexical", "Hybrid") and len(keys) > 0
+        want_vec = search_mode.kind in ("Vector", "Hybrid") and query_vector is not None
+        rt = ResultType(result_type)
+        if length == 0 and rt == ResultType.TopkCount:   # search.rs:2472-2478
+            rt = ResultType.Count
+        if want_lex:
+            res, counts = self.search_lexical_batch([keys], qt, heap if rt != ResultType.Count else 0, rt)
+            lex, total = res[0], int(counts[0])
+        if want_vec:
+            qv = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)
+            vec = self.search_vector_batch(qv, max(heap, 1))[0][:heap]
+            ro.observed_vector_count = self.vector_count
+        if search_mode.kind == "Lexical":
+            fused = lex
+            ro.result_count_total = total
+        elif search_mode.kind == "Vector":
+            fused = vec
+            ro.result_count_total = len(vec)       # vector.rs:1509 (scan-order dependent in the reference)
+        else:
+            a = _hits_array(max(len(lex), 1)); b = _hits_array(max(len(vec), 1)); o = _hits_array(len(lex) + len(vec) + 1)
+            for i, (d, s) in enumerate(lex):
+                a[i] = (d, s, 0)
+            for i, (d, s) in enumerate(vec):
+                b[i] = (d, s, 0)
+            n = C.c_uint32(0)
+            check(lib().ssb_rrf_fuse(a.ctypes.data, len(lex), b.ctypes.data, len(vec), o.ctypes.data, C.byref(n)))
+            fused = [(int(o[i]["doc_id"]), float(o[i]["score"])) for i in range(n.value)]
+            ro.result_count_total = total
+        # search.rs:2108-2121: drop offset, truncate length
+        fused = fused[offset:offset + length] if offset < len(fused) else []
+        ro.results = [Result(d, s) for d, s in fused]
+        ro.result_count = len(ro.results)
+        return ro

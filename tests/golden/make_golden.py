@@ -1,0 +1,162 @@
+"""Generates tests/golden/golden.json: known-answer vectors for the oracle and the CUDA path.
+
+Independent restatement in numpy float32 scalars (NOT calling oracle/ or the library) of the reference
+formulas, evaluated on tiny hand-checkable inputs:
+  * the reference's own fixtures: tests/test.rs:64-86 (4 docs, field `body`), :150-208 (AND '+body2 +test' -> 1/1/1,
+    Union Count 'test' -> total 2), :675-745 (3 x 128-d Euclidean, AnnMode::All -> 3 results)
+  * byte4 codec table (index.rs:4237-4279), idf edge cases (search.rs:3225-3230), bm25 cache (commit.rs:318-325),
+    BM25 scores (add_result.rs:1450-1452), RRF (search.rs:1962-2035), NEON-test vectors
+    (vector_similarity.rs:3011-3021 make_f32).
+Run:  python tests/golden/make_golden.py   (writes golden.json next to this file)
+"""
+import json
+import math
+import os
+
+import numpy as np
+
+f32 = np.float32
+
+
+def int_to_byte4(i):
+    if i < 24:
+        return i
+    ii = i - 24
+    nb = ii.bit_length()
+    if nb < 4:
+        return 24 + ii
+    sh = nb - 4
+    return 24 + (((ii >> sh) & 7) | ((sh + 1) << 3))
+
+
+def byte4_to_int(b):
+    if b < 24:
+        return b
+    i = b - 24
+    bits, sh = i & 7, i >> 3
+    return 24 + bits if sh == 0 else 24 + ((bits | 8) << (sh - 1))
+
+
+def cache(n_docs, len_sum):
+    K, B = f32(1.2), f32(0.75)
+    avgdl = f32(len_sum) / f32(n_docs)
+    return [K * (f32(1.0) - B + B * (f32(byte4_to_int(b)) / avgdl)) for b in range(256)]
+
+
+def idf(n, df):
+    return f32(math.log(float(((f32(n) - f32(df) + f32(0.5)) / (f32(df) + f32(0.5))) + f32(1.0))))  # double log, rounded
+
+
+def term(idf_, tf, comp):
+    tf = f32(tf)
+    return idf_ * ((tf * (f32(1.2) + f32(1.0)) / (tf + comp)) + f32(0.0))
+
+
+def main():
+    out = {}
+    out["byte4_to_int"] = [byte4_to_int(b) for b in range(256)]
+    out["int_to_byte4_samples"] = {str(i): int_to_byte4(i) for i in
+                                   [0, 1, 23, 24, 25, 31, 32, 39, 40, 41, 55, 56, 80, 96, 100, 255, 256, 1000, 2000, 65535, 1 << 20]}
+
+    # ---- the reference's 4-doc fixture, field body: "body1", "body1", "body2 test", "body3 test"
+    docs = [["body1"], ["body1"], ["body2", "test"], ["body3", "test"]]
+    lens = [len(d) for d in docs]
+    len_bytes = [int_to_byte4(l) for l in lens]
+    len_sum = sum(byte4_to_int(b) for b in len_bytes)
+    c = cache(4, len_sum)
+    postings = {}
+    for di, d in enumerate(docs):
+        for t in d:
+            postings.setdefault(t, {}).setdefault(di, 0)
+            postings[t][di] += 1
+    fx = {"docs": docs, "len_bytes": len_bytes, "len_sum": len_sum, "n_docs": 4,
+          "postings": {t: sorted(p.items()) for t, p in postings.items()}}
+    idf_body2, idf_test = idf(4, 1), idf(4, 2)
+    s_and = f32(0.0)
+    s_and = s_and + term(idf_body2, 1, c[len_bytes[2]])
+    s_and = s_and + term(idf_test, 1, c[len_bytes[2]])
+    fx["and_body2_test"] = {"results": [[2, float(s_and)]], "count_total": 1}
+    fx["union_count_test"] = {"count_total": 2}
+    # OR "body2 test": doc2 has both, doc3 only test
+    s3 = f32(0.0) + term(idf_test, 1, c[len_bytes[3]])
+    fx["or_body2_test"] = {"results": [[2, float(s_and)], [3, float(s3)]], "count_total": 2}
+    fx["idf"] = {"body2": float(idf_body2), "test": float(idf_test)}
+    fx["cache_at_len"] = {str(b): float(c[b]) for b in sorted(set(len_bytes))}
+    out["ref_fixture_lexical"] = fx
+
+    # ---- idf edge cases
+    out["idf_cases"] = [[n, df, float(idf(n, df))] for n, df in [(4, 1), (4, 2), (4, 4), (100000, 1), (100000, 50000), (100000, 100000), (10000000, 123)]]
+
+    # ---- a 6-doc hand corpus with varied tf / lengths
+    docs2 = ["a a a b", "a b b b b b b b", "b c", "a c c c c c c c c c c c c c c c c c c c c c c c c c c c c c",
+             "c", "a b c a b c a b c"]
+    docs2 = [d.split() for d in docs2]
+    lb2 = [int_to_byte4(len(d)) for d in docs2]
+    ls2 = sum(byte4_to_int(b) for b in lb2)
+    c2 = cache(6, ls2)
+    post2 = {}
+    for di, d in enumerate(docs2):
+        for t in d:
+            post2.setdefault(t, {}).setdefault(di, 0)
+            post2[t][di] += 1
+    df2 = {t: len(p) for t, p in post2.items()}
+    def score(di, terms):
+        s = f32(0.0)
+        for t in terms:
+            if di in post2[t]:
+                s = s + term(idf(6, df2[t]), post2[t][di], c2[lb2[di]])
+        return s
+    def rank(cands, terms, k):
+        sc = sorted(((-float(score(d, terms)), d) for d in cands))
+        return [[d, -s] for s, d in sc[:k]]
+    hand = {"docs": docs2, "len_bytes": lb2, "len_sum": ls2, "n_docs": 6,
+            "postings": {t: sorted(p.items()) for t, p in post2.items()}, "queries": []}
+    for terms, qt in [(["a", "b"], "and"), (["a", "b"], "or"), (["a", "b", "c"], "or"), (["c", "a"], "and"), (["b"], "or"), (["a", "zzz"], "and"), (["a", "zzz"], "or")]:
+        live = [t for t in terms if t in post2]
+        if qt == "and":
+            cands = [] if len(live) < len(terms) else [d for d in range(6) if all(d in post2[t] for t in live)]
+        else:
+            cands = [d for d in range(6) if any(d in post2[t] for t in live)]
+        hand["queries"].append({"terms": terms, "type": qt, "top3": rank(cands, live, 3), "count_total": len(cands)})
+    out["hand_corpus"] = hand
+
+    # ---- RRF: two 3-item lists, k = 0.6, rank from 0
+    lex = [[10, 9.0], [11, 5.0], [12, 1.0]]
+    vec = [[12, 0.9], [10, 0.8], [13, 0.7]]
+    r = {}
+    for i, (d, _) in enumerate(lex):
+        r[d] = f32(1.0) / (f32(0.6) + f32(i))
+    for i, (d, _) in enumerate(vec):
+        s = f32(1.0) / (f32(0.6) + f32(i))
+        r[d] = r[d] + s if d in r else s
+    fused = sorted(((-float(s), d) for d, s in r.items()))
+    out["rrf"] = {"lex": lex, "vec": vec, "fused": [[d, -s] for s, d in fused]}
+
+    # ---- vectors: the reference's NEON-parity generator (vector_similarity.rs:3011-3015)
+    def make_f32(n):
+        return [float(f32(math.sin(float(f32(i) * f32(0.137)))) * f32(0.5) + f32(math.cos(float(f32(i) * f32(0.013)))) * f32(0.5)) for i in range(n)]
+    a = np.array(make_f32(128), dtype=np.float32)
+    dot = f32(0.0)
+    for x in a:
+        dot = dot + x * x
+    out["neon_vec"] = {"make_f32_128": [float(x) for x in a], "dot_self_scalar": float(dot), "euclid_self": 0.0}
+
+    # ---- the reference's 3-vector Euclidean fixture (tests/test.rs:675-745): v_j[i] = 0.001*(128*j + i + 1)
+    vecs = [[(128 * j + i + 1) / 1000.0 for i in range(128)] for j in range(3)]
+    q = np.array(vecs[0], dtype=np.float32)
+    res = []
+    for j in range(3):
+        v = np.array(vecs[j], dtype=np.float32)
+        s = f32(0.0)
+        for x, y in zip(q, v):
+            d = x - y
+            s = s + d * d
+        res.append([j, -float(s)])
+    out["ref_fixture_vector"] = {"n": 3, "dims": 128, "results": res, "result_count": 3}
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,38 @@
+"""GPU, BASELINE.json full sizes: C2 (1M x 768 cosine top-10) checked against the oracle on a few queries and by
+size-independent properties (planted neighbours, batch-composition invariance, self-match)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from seekstorm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c2_full_size_vector():
+    from seekstorm_b200 import Index, VectorSimilarity
+    n, d = 1_000_000, 768
+    rows = synth.gen_vectors(n, d, 1002, "cuda")
+    ix = Index(0, vector_dims=d, vector_similarity=VectorSimilarity.Cosine)
+    ix.add_vectors(rows)
+    assert ix.vector_count == n
+    q = synth.gen_vectors(48, d, 2002, "cuda")
+    planted = torch.arange(0, 48, 3, device="cuda") * 20011 % n
+    q[::3] = rows[planted] + 0.05 * q[::3]
+    got = ix.search_vector_batch(q.cpu().numpy(), 10)
+    # property: planted neighbour is rank 1
+    for j, p in enumerate(planted.tolist()):
+        assert got[3 * j][0][0] == p
+    # property: results do not depend on batch composition / padding
+    again = ix.search_vector_batch(q[5:12].cpu().numpy(), 10)
+    assert again == got[5:12]
+    # oracle on 4 queries (multi-threaded exhaustive scan of the normalised corpus)
+    nrows = (rows / rows.norm(dim=1, keepdim=True)).cpu().numpy()
+    for i in (0, 1, 2, 7):
+        want = O.search_vector(nrows, O.normalize(q[i].cpu().numpy()), 10, O.SIM_COSINE, n_threads=16)
+        gs = np.array([s for _, s in got[i]]); ws = np.array([s for _, s in want])
+        assert np.allclose(gs, ws, rtol=1e-4, atol=1e-6)
+        for (gd, gsc), (wd, wsc) in zip(got[i], want):
+            assert gd == wd or abs(gsc - wsc) <= 1e-4 * abs(wsc)
+    ix.close()

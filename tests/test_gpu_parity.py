@@ -1,0 +1,222 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C-ABI vs the CPU oracle on the same seeded inputs.
+
+Bars: bit-exact doc ids / ranks / counts and bit-exact BM25 scores (every f32 op individually rounded on both
+sides); cosine / dot / Euclidean scores within 1e-4 relative (different reduction tree)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from seekstorm_b200 import synth
+from helpers import gpu_index, key_of, level_from_postings, oracle_index, query_keys, synth_levels
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # north_star tolerance for floating-point scores
+
+
+def _check_vec(got, want, strict_ids=True):
+    assert len(got) == len(want)
+    gs = np.array([s for _, s in got], dtype=np.float64)
+    ws = np.array([s for _, s in want], dtype=np.float64)
+    assert np.allclose(gs, ws, rtol=RTOL, atol=1e-6), (got, want)
+    if [d for d, _ in got] != [d for d, _ in want]:
+        # ids may only differ inside a near-tie group (scores closer than the tolerance)
+        for (gd, gsc), (wd, wsc) in zip(got, want):
+            if gd != wd:
+                assert abs(gsc - wsc) <= RTOL * max(abs(wsc), 1e-6), (got, want)
+
+
+@pytest.mark.parametrize("n,dims,sim", [
+    (1, 32, "cos"), (255, 128, "cos"), (257, 128, "dot"), (5000, 100, "cos"), (5000, 768, "cos"),
+    (70000, 64, "euc"), (3000, 960, "dot"), (1000, 33, "euc")])
+def test_vector_parity_small(n, dims, sim):
+    from seekstorm_b200 import Index, VectorSimilarity
+    simv = {"cos": VectorSimilarity.Cosine, "dot": VectorSimilarity.Dot, "euc": VectorSimilarity.Euclidean}[sim]
+    osim = {"cos": O.SIM_COSINE, "dot": O.SIM_DOT, "euc": O.SIM_EUCLIDEAN}[sim]
+    rows = synth.gen_vectors(n, dims, 1000 + n, "cpu").numpy()
+    qs = synth.gen_vectors(19, dims, 2000 + n, "cpu").numpy()      # 19: exercises query padding to 16
+    qs[3] = rows[n // 2] + 0.05 * qs[3]                            # planted neighbour
+    ix = Index(0, vector_dims=dims, vector_similarity=simv)
+    ix.add_vectors(rows)
+    assert ix.vector_count == n
+    for k in (1, 10, 32):
+        got = ix.search_vector_batch(qs, k)
+        ref_rows = np.stack([O.normalize(r) for r in rows]) if sim == "cos" else rows
+        for i in range(len(qs)):
+            q = O.normalize(qs[i]) if sim == "cos" else qs[i]
+            want = O.search_vector(ref_rows, q, k, osim)
+            _check_vec(got[i], want)
+    if sim == "cos":
+        assert got[3][0][0] == n // 2
+    ix.close()
+
+
+def test_vector_reference_fixture(golden):
+    """tests/test.rs:693-745 through the mirrored Search::search: 3 results / count 3 / total 3."""
+    from seekstorm_b200 import Index, QueryType, ResultType, SearchMode, VectorSimilarity
+    rows = np.array([[(128 * j + i + 1) / 1000.0 for i in range(128)] for j in range(3)], dtype=np.float32)
+    ix = Index(0, vector_dims=128, vector_similarity=VectorSimilarity.Euclidean)
+    ix.add_vectors(rows)
+    ro = ix.search("", list(rows[0]), QueryType.Union, SearchMode.Vector(None), False, 0, 10, ResultType.TopkCount)
+    assert len(ro.results) == 3 and ro.result_count == 3 and ro.result_count_total == 3
+    want = golden["ref_fixture_vector"]["results"]
+    assert [r.doc_id for r in ro.results] == [d for d, _ in want]
+    for r, (_, s) in zip(ro.results, want):
+        assert abs(r.score - s) <= 1e-5 * max(1.0, abs(s))
+    ix.close()
+
+
+def test_vector_doc_ids_and_levels():
+    """doc_id = level<<16 | local (vector.rs:1448) with explicit local ids and non-contiguous levels."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    rows = synth.gen_vectors(300, 64, 5, "cpu").numpy()
+    ix = Index(0, vector_dims=64, vector_similarity=VectorSimilarity.Dot)
+    ix.add_vector_level(2, rows[:100], np.arange(100, 200, dtype=np.uint16))
+    ix.add_vector_level(7, rows[100:], None)
+    ids = np.concatenate([(2 << 16) | np.arange(100, 200), (7 << 16) | np.arange(200)]).astype(np.uint32)
+    q = rows[150:151]
+    got = ix.search_vector_batch(q, 5)[0]
+    want = O.search_vector(rows, q[0], 5, O.SIM_DOT, doc_ids=ids)
+    _check_vec(got, want)
+    assert got[0][0] == (7 << 16) | 50
+    ix.close()
+
+
+def test_lexical_reference_fixture(golden):
+    """tests/test.rs:150-208 through the mirrored Search::search."""
+    from seekstorm_b200 import QueryType, ResultType, SearchMode
+    fx = golden["ref_fixture_lexical"]
+    post = {t: [(d, tf) for d, tf in p] for t, p in fx["postings"].items()}
+    ix = gpu_index([level_from_postings(0, fx["n_docs"], post, fx["len_bytes"])], fx["n_docs"], fx["len_sum"])
+    ro = ix.search("+body2 +test", None, QueryType.Intersection, SearchMode.Lexical(), False, 0, 10, ResultType.TopkCount)
+    assert len(ro.results) == 1 and ro.result_count == 1 and ro.result_count_total == 1
+    assert ro.results[0].doc_id == 2 and np.float32(ro.results[0].score) == np.float32(fx["and_body2_test"]["results"][0][1])
+    ro = ix.search("test", None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.Count)
+    assert len(ro.results) == 0 and ro.result_count == 0 and ro.result_count_total == 2
+    ro = ix.search("body2 test", None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.TopkCount)
+    assert [(r.doc_id, np.float32(r.score)) for r in ro.results] == [(d, np.float32(s)) for d, s in fx["or_body2_test"]["results"]]
+    assert ro.result_count_total == 2
+    # offset / length paging (search.rs:2108-2121)
+    ro = ix.search("body2 test", None, QueryType.Union, SearchMode.Lexical(), False, 1, 10, ResultType.TopkCount)
+    assert [r.doc_id for r in ro.results] == [3]
+    ix.close()
+
+
+def test_lexical_hand_corpus(golden):
+    from seekstorm_b200 import QueryType, ResultType
+    h = golden["hand_corpus"]
+    post = {t: [(d, tf) for d, tf in p] for t, p in h["postings"].items()}
+    ix = gpu_index([level_from_postings(0, h["n_docs"], post, h["len_bytes"])], h["n_docs"], h["len_sum"])
+    for q in h["queries"]:
+        qt = QueryType.Intersection if q["type"] == "and" else QueryType.Union
+        res, counts = ix.search_lexical_batch([[key_of(t) for t in q["terms"]]], qt, 3, ResultType.TopkCount)
+        assert int(counts[0]) == q["count_total"], q
+        assert [d for d, _ in res[0]] == [d for d, _ in q["top3"]], q
+        for (_, s), (_, w) in zip(res[0], q["top3"]):
+            assert abs(s - w) <= 2e-7 * abs(w), q
+    ix.close()
+
+
+def _compare_lexical(ix, orc, qkeys, qt, oqt, k, rt, ort):
+    got, counts = ix.search_lexical_batch(qkeys, qt, k, rt)
+    for i, kq in enumerate(qkeys):
+        want, tot = orc.search(kq, oqt, k, ort)
+        if ort != O.RESULT_COUNT:
+            assert got[i] == want, (i, kq, got[i], want)        # bit-exact ids, ranks, scores
+        else:
+            assert got[i] == []
+        if ort != O.RESULT_TOPK:
+            assert int(counts[i]) == tot, (i, counts[i], tot)
+
+
+def test_lexical_c1_and_parity():
+    """C1: 100k docs, 1000 2-term AND queries, TopkCount vs the exhaustive oracle."""
+    from seekstorm_b200 import QueryType, ResultType
+    lvs, ls = synth_levels(100000, 100000, 1001)
+    orc = oracle_index([l.to_numpy() for l in lvs], 100000, ls)
+    ix = gpu_index([l.to_numpy() for l in lvs], 100000, ls)
+    qk = query_keys(synth.gen_queries(1000, 2001, 20, 20000))
+    _compare_lexical(ix, orc, qk, QueryType.Intersection, O.QUERY_INTERSECTION, 10, ResultType.TopkCount, O.RESULT_TOPKCOUNT)
+    _compare_lexical(ix, orc, qk[:200], QueryType.Intersection, O.QUERY_INTERSECTION, 10, ResultType.Topk, O.RESULT_TOPK)
+    _compare_lexical(ix, orc, qk[:200], QueryType.Intersection, O.QUERY_INTERSECTION, 0, ResultType.Count, O.RESULT_COUNT)
+    ix.close()
+
+
+@pytest.mark.parametrize("seed,n_docs,vocab", [(3, 150000, 20000), (4, 66000, 500)])
+def test_lexical_or_parity(seed, n_docs, vocab):
+    """OR with block-max / MAXSCORE pruning == exhaustive oracle, 1-4 terms, dense and sparse lists, k in {1,10,32}."""
+    from seekstorm_b200 import QueryType, ResultType
+    lvs, ls = synth_levels(n_docs, vocab, seed)
+    orc = oracle_index([l.to_numpy() for l in lvs], n_docs, ls)
+    ix = gpu_index([l.to_numpy() for l in lvs], n_docs, ls)
+    qs = synth.gen_queries(300, 50 + seed, 1, min(vocab, 20000), (1, 2, 3, 4), (0.1, 0.4, 0.3, 0.2))
+    qk = query_keys(qs)
+    qk[5] = qk[5] + [key_of("missing-term")]          # OR drops unknown terms (search.rs:3295-3296)
+    for k in (1, 10, 32):
+        _compare_lexical(ix, orc, qk, QueryType.Union, O.QUERY_UNION, k, ResultType.Topk, O.RESULT_TOPK)
+    _compare_lexical(ix, orc, qk, QueryType.Union, O.QUERY_UNION, 10, ResultType.TopkCount, O.RESULT_TOPKCOUNT)
+    _compare_lexical(ix, orc, qk[:50], QueryType.Union, O.QUERY_UNION, 0, ResultType.Count, O.RESULT_COUNT)
+    qa = [q for q in qk if len(q) >= 2]
+    qa[3] = qa[3] + [key_of("missing-term")]          # AND with an unknown term -> empty (search.rs:3290-3294)
+    _compare_lexical(ix, orc, qa, QueryType.Intersection, O.QUERY_INTERSECTION, 10, ResultType.TopkCount, O.RESULT_TOPKCOUNT)
+    ix.close()
+
+
+def test_lexical_device_pointers_and_tf_overflow():
+    """Levels handed over as DEVICE pointers (torch tensors) + tf >= 255 exception path."""
+    from seekstorm_b200 import Index, QueryType, ResultType
+    post = {"big": [(0, 300), (5, 255), (9, 254), (70, 1000)], "x": [(5, 2), (9, 1), (11, 7)]}
+    lens = [synth.int_to_byte4(l) for l in ([400] * 100)]
+    lv = level_from_postings(0, 100, post, lens)
+    len_sum = sum(synth.byte4_to_int(b) for b in lens)
+    orc = oracle_index([lv], 100, len_sum)
+    ix = Index(0)
+    dev = {k: (torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else v.view(np.int32) if v.dtype == np.uint32
+                                else v.view(np.int16) if v.dtype == np.uint16 else v).cuda())
+           for k, v in lv.items() if isinstance(v, np.ndarray)}
+    ix.add_lexical_level(0, 100, dev["term_keys"], dev["posting_offsets"], dev["doc_ids"], dev["tfs"], dev["doc_len_bytes"])
+    ix.commit(100, len_sum)
+    qk = [[key_of("big")], [key_of("big"), key_of("x")], [key_of("x"), key_of("big")]]
+    for qt, oqt in ((QueryType.Union, O.QUERY_UNION), (QueryType.Intersection, O.QUERY_INTERSECTION)):
+        _compare_lexical(ix, orc, qk, qt, oqt, 10, ResultType.TopkCount, O.RESULT_TOPKCOUNT)
+    ix.close()
+
+
+def test_hybrid_parity():
+    """SearchMode::Hybrid: RRF (search.rs:1962-2035) of the two top-k lists vs the oracle's rrf on oracle lists."""
+    from seekstorm_b200 import Index, QueryType, VectorSimilarity
+    n = 70000
+    lvs, ls = synth_levels(n, 5000, 9)
+    orc = oracle_index([l.to_numpy() for l in lvs], n, ls)
+    rows = synth.gen_vectors(n, 96, 10, "cpu").numpy()
+    ix = Index(0, vector_dims=96, vector_similarity=VectorSimilarity.Cosine)
+    for l in lvs:
+        ix.add_synth_level(l)
+    ix.commit(n, ls)
+    ix.add_vectors(rows)
+    qs = synth.gen_queries(40, 77, 5, 4000, (2, 3), (0.5, 0.5))
+    qk = query_keys(qs)
+    qv = synth.gen_vectors(40, 96, 78, "cpu").numpy()
+    got = ix.search_hybrid_batch(qk, QueryType.Union, qv, 10)
+    nrows = np.stack([O.normalize(r) for r in rows])
+    for i in range(40):
+        lex, _ = orc.search(qk[i], O.QUERY_UNION, 10, O.RESULT_TOPK)
+        vec = O.search_vector(nrows, O.normalize(qv[i]), 10, O.SIM_COSINE)
+        want = O.rrf(lex, vec)[:10]
+        assert [d for d, _ in got[i]] == [d for d, _ in want], (i, got[i], want)
+        assert [np.float32(s) for _, s in got[i]] == [np.float32(s) for _, s in want]
+    ix.close()
+
+
+def test_errors_are_status_codes():
+    from seekstorm_b200 import Index, QueryType, ResultType, SsbError
+    ix = Index(0, vector_dims=32)
+    with pytest.raises(SsbError, match="commit"):
+        ix.search_lexical_batch([[1]], QueryType.Union, 10, ResultType.Topk)
+    with pytest.raises(SsbError, match="k"):
+        ix.search_vector_batch(np.zeros((1, 32), dtype=np.float32), 33)
+    with pytest.raises(SsbError, match="dims"):
+        ix.add_vector_level(0, np.zeros((4, 16), dtype=np.float32))
+    assert ix.search_vector_batch(np.ones((2, 32), dtype=np.float32), 5) == [[], []]   # empty index -> empty results
+    ix.close()

@@ -1,0 +1,129 @@
+"""CPU: the oracle against the golden vectors (tests/golden/golden.json) and the reference's own fixtures."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from seekstorm_b200 import synth
+from helpers import key_of, level_from_postings, oracle_index, query_keys, synth_levels
+
+
+def test_byte4_table(golden):
+    L = O.lib()
+    tab = golden["byte4_to_int"]
+    for b in range(256):
+        assert L.orc_byte4_to_int(b) == tab[b] == synth.byte4_to_int(b)
+    # index.rs:4232 NUM_FREE_VALUES: the first 24 lengths are exact
+    for i in range(24):
+        assert L.orc_int_to_byte4(i) == i
+    for s, v in golden["int_to_byte4_samples"].items():
+        assert L.orc_int_to_byte4(int(s)) == v == synth.int_to_byte4(int(s))
+    # round trip is the identity on codes and monotone, never over-estimates
+    prev = -1
+    for b in range(256):
+        v = L.orc_byte4_to_int(b)
+        assert L.orc_int_to_byte4(v) == b
+        assert v > prev
+        prev = v
+    for x in (24, 25, 100, 1000, 2000, 65535):
+        assert L.orc_byte4_to_int(L.orc_int_to_byte4(x)) <= x
+
+
+def test_idf_cases(golden):
+    for n, df, want in golden["idf_cases"]:
+        got = float(np.float32(O.lib().orc_idf(n, df)))
+        assert abs(got - want) <= abs(want) * 2e-7, (n, df, got, want)
+
+
+def _fixture_levels(fx):
+    post = {t: [(d, tf) for d, tf in p] for t, p in fx["postings"].items()}
+    return [level_from_postings(0, fx["n_docs"], post, fx["len_bytes"])]
+
+
+def test_reference_fixture_lexical(golden):
+    """tests/test.rs:150-208: AND '+body2 +test' -> 1/1/1; Union Count 'test' -> 0 results, total 2."""
+    fx = golden["ref_fixture_lexical"]
+    ix = oracle_index(_fixture_levels(fx), fx["n_docs"], fx["len_sum"])
+    cache = O.bm25_cache(fx["n_docs"], fx["len_sum"])
+    for b, v in fx["cache_at_len"].items():
+        assert cache[int(b)] == np.float32(v)
+    for pruned in (False, True):
+        hits, total = ix.search([key_of("body2"), key_of("test")], O.QUERY_INTERSECTION, 10, O.RESULT_TOPKCOUNT, pruned)
+        assert len(hits) == 1 and total == 1
+        assert hits[0][0] == 2 and hits[0][1] == np.float32(fx["and_body2_test"]["results"][0][1])
+        hits, total = ix.search([key_of("test")], O.QUERY_UNION, 10, O.RESULT_COUNT, pruned)
+        assert hits == [] and total == 2
+        hits, total = ix.search([key_of("body2"), key_of("test")], O.QUERY_UNION, 10, O.RESULT_TOPKCOUNT, pruned)
+        assert [(d, np.float32(s)) for d, s in fx["or_body2_test"]["results"]] == [(d, np.float32(s)) for d, s in hits]
+        assert total == 2
+
+
+def test_hand_corpus(golden):
+    h = golden["hand_corpus"]
+    post = {t: [(d, tf) for d, tf in p] for t, p in h["postings"].items()}
+    ix = oracle_index([level_from_postings(0, h["n_docs"], post, h["len_bytes"])], h["n_docs"], h["len_sum"])
+    for q in h["queries"]:
+        qt = O.QUERY_INTERSECTION if q["type"] == "and" else O.QUERY_UNION
+        for pruned in (False, True):
+            hits, total = ix.search([key_of(t) for t in q["terms"]], qt, 3, O.RESULT_TOPKCOUNT, pruned)
+            assert total == q["count_total"], q
+            assert [d for d, _ in hits] == [d for d, _ in q["top3"]], q
+            for (_, s), (_, w) in zip(hits, q["top3"]):
+                assert abs(s - w) <= 2e-7 * abs(w), q
+
+
+def test_rrf(golden):
+    r = golden["rrf"]
+    got = O.rrf([tuple(x) for x in r["lex"]], [tuple(x) for x in r["vec"]])
+    assert [d for d, _ in got] == [d for d, _ in r["fused"]]
+    for (_, s), (_, w) in zip(got, r["fused"]):
+        assert s == np.float32(w)
+
+
+def test_neon_parity_vectors(golden):
+    """vector_similarity.rs:3024-3062: SIMD kernel vs scalar within 1e-3."""
+    a = np.array(golden["neon_vec"]["make_f32_128"], dtype=np.float32)
+    L = O.lib()
+    s = L.orc_dot_f32(a.ctypes.data, a.ctypes.data, 128)
+    v = L.orc_dot_f32_lanes8(a.ctypes.data, a.ctypes.data, 128)
+    assert s == np.float32(golden["neon_vec"]["dot_self_scalar"])
+    assert abs(s - v) < 1e-3
+    assert L.orc_euclidean_f32(a.ctypes.data, a.ctypes.data, 128) == 0.0
+    n = O.normalize(a)
+    assert abs(float(np.dot(n.astype(np.float64), n.astype(np.float64))) - 1.0) < 1e-6
+
+
+def test_reference_fixture_vector(golden):
+    """tests/test.rs:693-745: 3 x 128-d f32 Euclidean, AnnMode::All, length 10 -> 3 results."""
+    fx = golden["ref_fixture_vector"]
+    rows = np.array([[(128 * j + i + 1) / 1000.0 for i in range(128)] for j in range(3)], dtype=np.float32)
+    hits = O.search_vector(rows, rows[0], 10, O.SIM_EUCLIDEAN)
+    assert len(hits) == fx["result_count"]
+    assert [d for d, _ in hits] == [0, 1, 2]
+    for (d, s), (wd, ws) in zip(hits, fx["results"]):
+        assert d == wd and abs(s - ws) <= 1e-6 * max(1.0, abs(ws))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_exhaustive_equals_pruned(seed):
+    """The reference-shaped block-max / MAXSCORE control flow returns the exhaustive top-k (canonical ties)."""
+    lvs, ls = synth_levels(70000, 3000, seed)
+    ix = oracle_index([l.to_numpy() for l in lvs], 70000, ls)
+    qs = synth.gen_queries(60, 100 + seed, 2, 2500, (1, 2, 3, 4), (0.1, 0.4, 0.3, 0.2))
+    for q, keys in zip(qs, query_keys(qs)):
+        for qt in (O.QUERY_UNION, O.QUERY_INTERSECTION):
+            for rt in (O.RESULT_TOPK, O.RESULT_TOPKCOUNT):
+                a = ix.search(keys, qt, 10, rt)
+                b = ix.search(keys, qt, 10, rt, pruned=True)
+                assert a[0] == b[0], (q, qt, rt)
+                if rt == O.RESULT_TOPKCOUNT:
+                    assert a[1] == b[1], (q, qt, rt)
+
+
+def test_vector_topk_canonical_ties():
+    rows = np.zeros((10, 8), dtype=np.float32)
+    rows[:, 0] = [1, 2, 2, 3, 3, 3, 0, 5, 5, 1]
+    q = np.zeros(8, dtype=np.float32); q[0] = 1
+    hits = O.search_vector(rows, q, 4, O.SIM_DOT)
+    assert hits == [(7, 5.0), (8, 5.0), (3, 3.0), (4, 3.0)]
+    hits_mt = O.search_vector(rows, q, 4, O.SIM_DOT, n_threads=3)
+    assert hits_mt == hits
