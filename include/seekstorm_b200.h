@@ -146,6 +146,10 @@ int32_t ssb_merge_keys(ssb_index* ix, const uint64_t* keys_dev, uint32_t n_lists
 int32_t ssb_sync(ssb_index* ix);
 /* the CUDA stream the index launches on (cudaStream_t as void*), for event timing */
 void*   ssb_stream(ssb_index* ix);
+/* run all further work of this index on a caller-owned stream (e.g. the stream NCCL collectives are enqueued
+ * on, so the per-GPU top-k -> all-gather -> merge chain needs no host synchronisation); NULL restores the
+ * index's own stream */
+int32_t ssb_set_stream(ssb_index* ix, void* cuda_stream);
 
 /* ---- statistics of the last search_* call (for roofline accounting) -------------------------------- */
 typedef struct {

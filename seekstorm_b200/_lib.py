@@ -50,7 +50,7 @@ EXPORTS = [
     "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
     "ssb_vector_add_level", "ssb_vector_count", "ssb_search_lexical", "ssb_search_vector", "ssb_search_hybrid",
     "ssb_rrf_fuse", "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
-    "ssb_stream", "ssb_last_stats",
+    "ssb_stream", "ssb_set_stream", "ssb_last_stats",
 ]
 
 _lib = None
@@ -89,6 +89,7 @@ def lib():
         "ssb_search_lexical_keys": [vp, C.POINTER(SsbLexBatch), u32, u32, vp, vp],
         "ssb_merge_keys": [vp, vp, u32, u32, u32, vp, vp],
         "ssb_sync": [vp],
+        "ssb_set_stream": [vp, vp],
         "ssb_last_stats": [vp, C.POINTER(SsbStats)],
     }
     for name, args in sigs.items():

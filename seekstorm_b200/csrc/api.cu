@@ -58,7 +58,8 @@ using namespace ssb;
 struct ssb_index {
     ssb_config cfg;
     int n_sms = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;       // stream in use
+    cudaStream_t own_st = nullptr;   // the index's own stream
     std::mutex mu;
     LexIndex* lex = nullptr;
     // vector index
@@ -148,6 +149,7 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     if (ix->cfg.max_batch == 0) ix->cfg.max_batch = 4096;
     ix->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking) != cudaSuccess) { delete ix; set_error("stream create failed"); return SSB_E_CUDA; }
+    ix->own_st = ix->st;
     ix->lex = new LexIndex(ix->st, ix->n_sms, ix->cfg.max_batch);
     ix->dims = cfg->vector_dims;
     ix->dpad = (cfg->vector_dims + 31) / 32 * 32;
@@ -162,7 +164,7 @@ int32_t ssb_destroy(ssb_index* ix) {
     delete ix->lex;
     ix->rows.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->scratch.release();
     ix->keys_a.release(); ix->keys_b.release(); ix->counts.release();
-    cudaStreamDestroy(ix->st);
+    cudaStreamDestroy(ix->own_st);
     delete ix;
     return SSB_OK;
 }
@@ -354,6 +356,16 @@ int32_t ssb_sync(ssb_index* ix) {
 }
 
 void* ssb_stream(ssb_index* ix) { return ix ? (void*)ix->st : nullptr; }
+
+int32_t ssb_set_stream(ssb_index* ix, void* stream) {
+    if (!ix) return SSB_E_INVALID;
+    std::lock_guard<std::mutex> g(ix->mu);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+    ix->st = stream ? (cudaStream_t)stream : ix->own_st;
+    ix->lex->set_stream(ix->st);
+    return SSB_OK;
+}
 
 int32_t ssb_last_stats(const ssb_index* ix, ssb_stats* out) {
     if (!ix || !out) return SSB_E_INVALID;

@@ -158,7 +158,7 @@ __global__ void compact_dense(const uint32_t* __restrict__ e_bitmap, uint32_t n,
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
                                                 uint32_t query_type, QueryPlan* plans, uint64_t* items, uint32_t* ctr,
                                                 uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2) {
-    extern __shared__ uint8_t sm_raw[];
+    extern __shared__ __align__(16) uint8_t sm_raw[];
     float* bound = (float*)sm_raw;                                     // [n_levels]
     uint32_t* cnt = (uint32_t*)(bound + v.n_levels);                   // [n_levels]
     uint64_t* skey = (uint64_t*)(((uintptr_t)(cnt + v.n_levels) + 7) & ~(uintptr_t)7);  // [n_pow2]
@@ -745,6 +745,7 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
     const bool off_dev = is_device_ptr(q->term_offsets);
     if (off_dev) SSB_CUDA_TRY(cudaMemcpy(&total_terms, q->term_offsets + nq, 4, cudaMemcpyDeviceToHost));
     else total_terms = q->term_offsets[nq];
+    if ((uint64_t)nq * (levels_.size() ? levels_.size() : 1) >= 0xFFFFFFFFull) { set_error("batch too large: n_queries * n_levels must be < 2^32"); return SSB_E_UNSUPPORTED; }
     SSB_TRY(ensure_workspace(nq, total_terms));
     SSB_CUDA_TRY(to_device(d_qoff_, q->term_offsets, ((size_t)nq + 1) * 4, st_));
     SSB_CUDA_TRY(to_device(d_qkeys_, q->term_keys, (size_t)total_terms * 8, st_));
@@ -764,6 +765,7 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
     // glist lives in keys_out_dev's shape: use a private list buffer = d_items_-adjacent? keep separate: reuse keys_out_dev
     // directly as the global list (32 u64 per query), then mask entries >= k in copy_out.
     uint64_t* glist = keys_out_dev;
+    if (plan_smem > 48 * 1024) SSB_CUDA_TRY(cudaFuncSetAttribute(lex_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
     lex_plan<<<nq, 128, plan_smem, st_>>>(v, d_qoff_, d_qkeys_, q->query_type, d_plans_, d_items_, d_ctr_, d_theta_, d_lock_, d_count_, glist, n_pow2);
     SSB_CUDA_TRY(cudaGetLastError());
     int grid = n_sms_ * 8;

@@ -86,6 +86,7 @@ public:
     int32_t search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t result_type, uint64_t* keys_out_dev,
                         uint64_t* count_dev, uint64_t* launches);
     bool committed() const { return committed_; }
+    void set_stream(cudaStream_t st) { st_ = st; }
     LexStats last_stats();
     uint64_t n_postings() const { return n_post_; }
 

@@ -290,6 +290,10 @@ class Index:
     def stream(self) -> int:
         return lib().ssb_stream(self._h) or 0
 
+    def set_stream(self, cuda_stream: int):
+        """Run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream."""
+        check(lib().ssb_set_stream(self._h, cuda_stream or None))
+
     # ------------------------------------------------------------------ the reference's public call
     def search(self, query_string: str, query_vector=None, query_type_default: QueryType = QueryType.Union,
                search_mode: SearchMode = None, enable_empty_query: bool = False, offset: int = 0, length: int = 10,
