@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the seekstorm_b200 hot path.
+
+Metric (BASELINE.json): queries/sec at top-10.  N=1 workload = configs[1]: brute-force cosine kNN over
+1M x 768 f32 (C2).  A "step" = one call of the hot path over one batch of synthetic queries (batch = --batch
+queries = batch/16 corpus passes).  `value` = device-resident QPS (queries already in HBM, packed keys left
+in HBM); `e2e` = the same through the reference-facing C-ABI call ssb_search_vector with HOST buffers (H2D of
+the queries and D2H of the results inside the timed region).  A second section ("bm25") measures C3
+(BM25 OR top-10 over a 10M-doc Zipfian index) the same way.
+
+N>1 (torchrun, one rank per GPU): the corpus is sharded by contiguous 64K-row level ranges (strong scaling);
+every rank scans its shard for the whole batch, then one NCCL all-gather of the packed top-k keys and a
+G*k -> k merge (seekstorm_b200/parallel.py).
+
+--impl reference: times the CPU restatement of the reference path (oracle/, kind "port": the Rust reference
+cannot be built here) on the host cores for the same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+C2_ROWS, C2_DIMS, TOPK = 1_000_000, 768, 10
+C3_DOCS, C3_VOCAB = 10_000_000, 1_000_000
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=256, help="vector queries per step")
+    p.add_argument("--rows", type=int, default=C2_ROWS)
+    p.add_argument("--dims", type=int, default=C2_DIMS)
+    p.add_argument("--sections", default="vector,bm25")
+    p.add_argument("--bm25-docs", type=int, default=C3_DOCS)
+    p.add_argument("--bm25-batch", type=int, default=4096, help="lexical queries per step")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
+    return p.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n):
+    if n <= 1:
+        return 0, 1
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", n))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl")
+    return rank, world
+
+
+def timed_steps(fn, steps, warmup, world):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, device time, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def vector_levels(rows, rank, world):
+    from seekstorm_b200.parallel import level_range
+    n_levels = (rows + 65535) // 65536
+    return n_levels, level_range(n_levels, rank, world)
+
+
+def gen_vector_level(level, rows, dims, device):
+    from seekstorm_b200 import synth
+    n = min(65536, rows - level * 65536)
+    return synth.gen_vectors(n, dims, 1002 * 1000 + level, device)
+
+
+def bench_vector(a, rank, world, out):
+    from seekstorm_b200 import Index, VectorSimilarity
+    from seekstorm_b200.parallel import ShardedSearcher
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ix = Index(dev.index, vector_dims=a.dims, vector_similarity=VectorSimilarity.Cosine, max_batch=max(a.batch, 16))
+    ix.set_stream(torch.cuda.current_stream().cuda_stream)
+    n_levels, mine = vector_levels(a.rows, rank, world)
+    local_rows = 0
+    for lv in mine:
+        r = gen_vector_level(lv, a.rows, a.dims, dev)
+        ix.add_vector_level(lv, r)
+        local_rows += r.shape[0]
+        del r
+    from seekstorm_b200 import synth
+    q_host = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").pin_memory()
+    q_dev = q_host.to(dev)
+    keys = torch.zeros((a.batch, 32), dtype=torch.int64, device=dev)
+    sh = ShardedSearcher(ix)
+
+    # ---- value: device-resident hot path (per rank scan + (N>1) NCCL all-gather + merge kernel) ----
+    if world == 1:
+        def step_dev():
+            ix.search_vector_keys(q_dev, TOPK, keys)
+    else:
+        def step_dev():
+            ix.search_vector_keys(q_dev, TOPK, keys)
+            sh.gather_keys(keys)
+    # roofline of the dominant kernel (scan_ffma), CUDA events recorded by the library around that launch
+    step_dev(); torch.cuda.synchronize()
+    kern_ns = []
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    ms = timed_steps(step_dev, a.steps, a.warmup, world)
+    clocks = sampler.stop() if sampler else None
+    for _ in range(5):
+        step_dev(); torch.cuda.synchronize()
+        kern_ns.append(ix.last_stats()["dominant_kernel_ns"])
+    launches_per_step = 3 + (1 if world > 1 else 0)
+    passes = (a.batch + 15) // 16
+    qps = a.batch * a.steps / (ms / 1e3)
+
+    # ---- e2e: the reference-facing call with HOST buffers (H2D queries, D2H hits inside the timed region) ----
+    q_np = q_host.numpy()
+    if world == 1:
+        def step_e2e():
+            ix.search_vector_batch(q_np, TOPK)
+    else:
+        import torch.distributed as dist
+        def step_e2e():
+            qd = q_host.to(dev, non_blocking=True) if rank == 0 else q_dev
+            dist.broadcast(qd, 0)
+            sh.search_vector(qd, TOPK)
+    ms_e2e = timed_steps(step_e2e, a.steps, a.warmup, world)
+    qps_e2e = a.batch * a.steps / (ms_e2e / 1e3)
+
+    peak, peak_kind = peaks()
+    kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
+    alg_bytes = float(local_rows) * a.dims * 4 * passes          # per launch (one launch = all passes of the batch)
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
+    out.update({
+        "metric": "queries/sec at top-10 (1M x 768 f32 cosine brute-force kNN)", "value": qps, "unit": "queries/s",
+        "ms_per_step": ms / a.steps, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2 brute-force cosine kNN: {a.rows} x {a.dims} f32, top-{TOPK}, batch {a.batch} queries/step "
+                               f"({passes} corpus passes of 16 queries)", "l2": "inputs larger than L2 (corpus %.2f GB per GPU)" % (local_rows * a.dims * 4 / 1e9),
+                   "parallelism": f"levels sharded over {world} GPU(s)", "kernel": "scan_ffma (TMA + FP32 FFMA + warp top-k)"},
+        "e2e": {"value": qps_e2e, "unit": "queries/s", "ms_per_step": ms_e2e / a.steps,
+                "h2d_bytes_per_step": a.batch * a.dims * 4, "d2h_bytes_per_step": a.batch * 32 * 8},
+        "gpu_launches": launches_per_step * a.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_kind": f"of {peak_kind}",
+                     "kernel": "scan_ffma", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
+        "clocks": clocks,
+    })
+    return ix, q_host
+
+
+def cpu_vector_baseline(a, seconds):
+    """The restated reference CPU path (oracle: exhaustive scan, 8-lane FMA dot as dot_f32_avx2, linear top-k), all
+    host threads, on a bounded sample of the C2 queries."""
+    from oracle import oracle as O
+    from seekstorm_b200 import synth
+    cores = os.cpu_count() or 1
+    rows = np.empty((a.rows, a.dims), dtype=np.float32)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    for lv in range((a.rows + 65535) // 65536):
+        r = gen_vector_level(lv, a.rows, a.dims, dev)
+        r = r / r.norm(dim=1, keepdim=True)
+        rows[lv * 65536: lv * 65536 + r.shape[0]] = r.cpu().numpy()
+    qs = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").numpy()
+    n_done, t0 = 0, time.perf_counter()
+    O.search_vector(rows, O.normalize(qs[0]), TOPK, O.SIM_COSINE, lanes8=True, n_threads=cores)  # warm
+    t0 = time.perf_counter()
+    while n_done < len(qs) and (time.perf_counter() - t0) < seconds:
+        O.search_vector(rows, O.normalize(qs[n_done]), TOPK, O.SIM_COSINE, lanes8=True, n_threads=cores)
+        n_done += 1
+    dt = time.perf_counter() - t0
+    return {"value": n_done / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{n_done} of the {a.batch} C2 queries, full {a.rows}x{a.dims} corpus, {cores} threads (row-split), {dt:.1f}s"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def build_bm25(a, rank, world, dev, want_host_copy):
+    from seekstorm_b200 import Index, synth
+    from seekstorm_b200.parallel import level_range, allreduce_global_df
+    ix = Index(dev.index if dev.type == "cuda" else 0, max_batch=a.bm25_batch)
+    ix.set_stream(torch.cuda.current_stream().cuda_stream)
+    n_levels = (a.bm25_docs + 65535) // 65536
+    mine = level_range(n_levels, rank, world)
+    len_sum = torch.zeros(1, dtype=torch.int64, device=dev)
+    host_levels = []
+    for lv in synth.gen_lexical_corpus(a.bm25_docs, C3_VOCAB, 1003, dev, level_ids=mine):
+        ix.add_synth_level(lv)
+        len_sum += lv.len_sum_normalized
+        if want_host_copy:
+            host_levels.append(lv.to_numpy())
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(len_sum)
+    ix.commit(a.bm25_docs, int(len_sum.item()))
+    if world > 1:
+        allreduce_global_df(ix)
+    return ix, host_levels, int(len_sum.item())
+
+
+def bm25_queries(n):
+    from seekstorm_b200 import synth
+    qs = synth.gen_queries(n, 2003, 20, 100000, (2, 3, 4), (0.4, 0.4, 0.2))
+    return [[int(k) for k in synth.term_keys_np(np.array(q, dtype=np.int64))] for q in qs]
+
+
+def bench_bm25(a, rank, world):
+    from seekstorm_b200 import QueryType, ResultType
+    from seekstorm_b200.parallel import ShardedSearcher
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t0 = time.perf_counter()
+    ix, _, _ = build_bm25(a, rank, world, dev, False)
+    build_s = time.perf_counter() - t0
+    qk = bm25_queries(a.bm25_batch)
+    b, keep = ix._lex_batch(qk, QueryType.Union)
+    offs_dev = torch.from_numpy(keep[0].view(np.int32)).to(dev)
+    keys_dev = torch.from_numpy(keep[1].view(np.int64)).to(dev)
+    from seekstorm_b200._lib import SsbLexBatch
+    b_dev = SsbLexBatch(len(qk), int(QueryType.Union), offs_dev.data_ptr(), keys_dev.data_ptr())
+    out_keys = torch.zeros((len(qk), 32), dtype=torch.int64, device=dev)
+    sh = ShardedSearcher(ix)
+
+    def step_dev():
+        ix.search_lexical_keys(b_dev, TOPK, ResultType.Topk, out_keys)
+        if world > 1:
+            sh.gather_keys(out_keys)
+    steps = max(3, a.steps // 2)
+    ms = timed_steps(step_dev, steps, a.warmup, world)
+    kern_ns = []
+    for _ in range(3):
+        step_dev(); torch.cuda.synchronize()
+        kern_ns.append(ix.last_stats()["dominant_kernel_ns"])
+
+    def step_e2e():
+        if world == 1:
+            ix.search_lexical_batch(qk, QueryType.Union, TOPK, ResultType.Topk)
+        else:
+            sh.search_lexical(b, len(qk), TOPK, ResultType.Topk, dev)
+    ms_e2e = timed_steps(step_e2e, steps, a.warmup, world)
+    st = ix.last_stats() if world == 1 else {}
+    peak, peak_kind = peaks()
+    kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
+    alg = st.get("algorithmic_bytes")
+    res = {
+        "metric": "queries/sec at top-10 (BM25 OR, block-max pruned, ResultType::Topk)", "value": len(qk) * steps / (ms / 1e3),
+        "unit": "queries/s", "ms_per_step": ms / steps, "steps": steps, "dtype": "f32 scores / u16 postings",
+        "config": {"workload": f"C3 BM25 OR top-{TOPK}: {a.bm25_docs} docs Zipf(1) V={C3_VOCAB}, {len(qk)} queries/step of 2-4 terms (40/40/20%), ranks log-uniform [20,1e5]",
+                   "index_build_s": build_s},
+        "e2e": {"value": len(qk) * steps / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(keep[0].nbytes + keep[1].nbytes), "d2h_bytes_per_step": len(qk) * (32 * 8 + 8)},
+        "gpu_launches": 3 * steps,
+        "roofline": {"bound": "hbm", "achieved": (alg / (kern_ms / 1e3) / 1e9) if (alg and kern_ms) else None, "peak": peak, "unit": "GB/s",
+                     "frac": (alg / (kern_ms / 1e3) / 1e9 / peak) if (alg and kern_ms) else None, "traffic": None,
+                     "peak_kind": f"of {peak_kind}", "kernel": "lex_score", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": alg, "postings_visited": st.get("postings_visited"), "probes": st.get("probes"),
+                     "items_processed": st.get("items_processed"), "items_skipped": st.get("items_skipped")},
+    }
+    ix.close()
+    return res
+
+
+def cpu_bm25_baseline(a, seconds):
+    """Reference-shaped CPU search (oracle pruned path: block-max ordered AND + MAXSCORE sub-queries) on the same index,
+    one worker thread per host core (the reference runs one task per shard, default shards = cores)."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    from seekstorm_b200 import synth
+    orc = O.OracleIndex()
+    len_sum = 0
+    for lv in synth.gen_lexical_corpus(a.bm25_docs, C3_VOCAB, 1003, dev):
+        orc.add_level(lv.to_numpy())
+        len_sum += lv.len_sum_normalized
+    orc.commit(a.bm25_docs, len_sum)
+    qk = bm25_queries(a.bm25_batch)
+    done = [0] * cores
+    stop = time.perf_counter() + seconds
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work(i):
+        while time.perf_counter() < stop:
+            with lock:
+                j = nxt[0]; nxt[0] += 1
+            if j >= len(qk):
+                return
+            orc.search(qk[j], O.QUERY_UNION, TOPK, O.RESULT_TOPK, pruned=True)
+            done[i] += 1
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]; [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    n = sum(done)
+    return {"value": n / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{n} of the {len(qk)} C3 queries on the full {a.bm25_docs}-doc index, {cores} threads (one query each), {dt:.1f}s"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    sections = [s for s in a.sections.split(",") if s]
+    if a.impl == "reference":
+        rank = int(os.environ.get("RANK", 0))
+        if rank != 0:
+            return 0
+        import __graft_entry__ as g
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+        base = cpu_vector_baseline(a, max(a.cpu_seconds, 2.0) * max(1, min(a.steps, 3)))
+        line = {"impl": "reference", "metric": "queries/sec at top-10 (1M x 768 f32 cosine brute-force kNN)", "value": base["value"],
+                "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C2 brute-force cosine kNN: {a.rows} x {a.dims} f32, top-{TOPK} (restated reference CPU path, {base['cores']} threads)"},
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if "bm25" in sections:
+            try:
+                line["bm25"] = {"cpu_baseline": cpu_bm25_baseline(a, a.cpu_seconds)}
+                line["bm25"]["value"] = line["bm25"]["cpu_baseline"]["value"]
+            except Exception as e:  # pragma: no cover
+                line["bm25"] = {"error": repr(e)}
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: bench.py measures the B200 path only (no CPU fallback)"}))
+        return 1
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB):
+        g.build()
+    rank, world = dist_setup(a.gpus)
+    out = {"n_gpus": world, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "impl": "b200"}
+    ix, _ = bench_vector(a, rank, world, out)
+    ix.close()
+    del ix
+    torch.cuda.empty_cache()
+    if "bm25" in sections:
+        try:
+            out["bm25"] = bench_bm25(a, rank, world)
+        except Exception as e:  # pragma: no cover
+            out["bm25"] = {"error": repr(e)}
+    if rank == 0 and world == 1 and a.cpu_seconds > 0:
+        torch.cuda.empty_cache()
+        try:
+            out["cpu_baseline"] = cpu_vector_baseline(a, a.cpu_seconds)
+        except Exception as e:  # pragma: no cover
+            out["cpu_baseline"] = {"error": repr(e)}
+        if "bm25" in sections and isinstance(out.get("bm25"), dict) and "error" not in out["bm25"]:
+            try:
+                out["bm25"]["cpu_baseline"] = cpu_bm25_baseline(a, a.cpu_seconds)
+            except Exception as e:  # pragma: no cover
+                out["bm25"]["cpu_baseline"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -156,7 +156,11 @@ typedef struct {
     uint64_t kernel_launches;     /* kernels launched by the last call                                   */
     uint64_t algorithmic_bytes;   /* SURVEY.md §8(d) bytes the call's kernels had to move                 */
     uint64_t h2d_bytes, d2h_bytes;
-    uint64_t postings_visited;    /* lexical: postings enumerated after pruning                           */
+    uint64_t postings_visited;    /* lexical: driver postings enumerated after pruning                    */
+    uint64_t probes;              /* lexical: membership probes into other lists                          */
+    uint64_t items_processed;     /* lexical: (query, block) work items executed                          */
+    uint64_t items_skipped;       /* lexical: work items pruned by block-max                              */
+    uint64_t dominant_kernel_ns;  /* CUDA-event duration of the call's dominant kernel (scan / scoring)   */
     uint64_t reserved[3];
 } ssb_stats;
 int32_t ssb_last_stats(const ssb_index* ix, ssb_stats* out);

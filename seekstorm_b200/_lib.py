@@ -41,7 +41,9 @@ class SsbLexBatch(C.Structure):
 
 class SsbStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("postings_visited", C.c_uint64), ("reserved", C.c_uint64 * 3)]
+                ("d2h_bytes", C.c_uint64), ("postings_visited", C.c_uint64), ("probes", C.c_uint64),
+                ("items_processed", C.c_uint64), ("items_skipped", C.c_uint64), ("dominant_kernel_ns", C.c_uint64),
+                ("reserved", C.c_uint64 * 3)]
 
 
 # every symbol include/seekstorm_b200.h declares

@@ -71,6 +71,7 @@ struct ssb_index {
     DevBuf<float> qpad; DevBuf<float> qstage; DevBuf<uint64_t> scratch; DevBuf<uint64_t> keys_a, keys_b, counts;
     std::vector<uint64_t> h_keys_a, h_keys_b, h_counts;
     ssb_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_used = false;
 };
 
 namespace {
@@ -99,7 +100,7 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     a.nq_pad = nq_pad; a.k = k; a.similarity = ix->cfg.vector_similarity; a.n_sms = ix->n_sms;
     a.scratch = ix->scratch.p; a.scratch_bytes = sb;
     uint64_t* merged = ix->scratch.p + sb / 8;   // [nq_pad][32]
-    a.keys_out = merged;
+    a.keys_out = merged; a.ev0 = ix->ev0; a.ev1 = ix->ev1; ix->ev_used = true;
     SSB_TRY(vec::launch_scan_ffma(a, ix->st));
     SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, ix->st));
     ix->stats.kernel_launches += 2;
@@ -150,7 +151,9 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     ix->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking) != cudaSuccess) { delete ix; set_error("stream create failed"); return SSB_E_CUDA; }
     ix->own_st = ix->st;
+    cudaEventCreate(&ix->ev0); cudaEventCreate(&ix->ev1);
     ix->lex = new LexIndex(ix->st, ix->n_sms, ix->cfg.max_batch);
+    ix->lex->set_events(ix->ev0, ix->ev1);
     ix->dims = cfg->vector_dims;
     ix->dpad = (cfg->vector_dims + 31) / 32 * 32;
     *out = ix;
@@ -164,6 +167,7 @@ int32_t ssb_destroy(ssb_index* ix) {
     delete ix->lex;
     ix->rows.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->scratch.release();
     ix->keys_a.release(); ix->keys_b.release(); ix->counts.release();
+    cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1);
     cudaStreamDestroy(ix->own_st);
     delete ix;
     return SSB_OK;
@@ -252,6 +256,7 @@ int32_t ssb_search_lexical_keys(ssb_index* ix, const ssb_lex_batch* q, uint32_t 
     std::lock_guard<std::mutex> g(ix->mu);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     ix->stats = ssb_stats{};
+    ix->ev_used = true;
     return ix->lex->search_keys(q, k, result_type, keys_out_dev, count_dev, &ix->stats.kernel_launches);
 }
 
@@ -277,7 +282,8 @@ int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, ui
     LexStats ls = ix->lex->last_stats();
     ix->stats.postings_visited = ls.postings_visited;
     ix->stats.algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 12 + ls.items_processed * 24;
-    ix->stats.reserved[0] = ls.probes; ix->stats.reserved[1] = ls.items_processed; ix->stats.reserved[2] = ls.items_skipped;
+    ix->stats.probes = ls.probes; ix->stats.items_processed = ls.items_processed; ix->stats.items_skipped = ls.items_skipped;
+    ix->ev_used = true;
     return SSB_OK;
 }
 
@@ -370,6 +376,13 @@ int32_t ssb_set_stream(ssb_index* ix, void* stream) {
 int32_t ssb_last_stats(const ssb_index* ix, ssb_stats* out) {
     if (!ix || !out) return SSB_E_INVALID;
     *out = ix->stats;
+    if (ix->ev_used) {
+        cudaSetDevice(ix->cfg.device);
+        float ms = 0.f;
+        if (cudaEventSynchronize(ix->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) == cudaSuccess)
+            out->dominant_kernel_ns = (uint64_t)((double)ms * 1e6);
+        else cudaGetLastError();
+    }
     return SSB_OK;
 }
 

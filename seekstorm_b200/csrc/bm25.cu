@@ -769,7 +769,9 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
     lex_plan<<<nq, 128, plan_smem, st_>>>(v, d_qoff_, d_qkeys_, q->query_type, d_plans_, d_items_, d_ctr_, d_theta_, d_lock_, d_count_, glist, n_pow2);
     SSB_CUDA_TRY(cudaGetLastError());
     int grid = n_sms_ * 8;
+    if (ev0_) cudaEventRecord(ev0_, st_);
     lex_score<<<grid, 256, 0, st_>>>(v, d_plans_, d_items_, nq, q->query_type, result_type, k ? k : 1, d_ctr_, d_theta_, d_lock_, d_count_, glist, d_stats_);
+    if (ev1_) cudaEventRecord(ev1_, st_);
     SSB_CUDA_TRY(cudaGetLastError());
     copy_out<<<(nq * LIST + 255) / 256, 256, 0, st_>>>(glist, d_count_, nq, result_type == SSB_RESULT_COUNT ? 0 : k, keys_out_dev, count_dev);
     SSB_CUDA_TRY(cudaGetLastError());

@@ -87,12 +87,14 @@ public:
                         uint64_t* count_dev, uint64_t* launches);
     bool committed() const { return committed_; }
     void set_stream(cudaStream_t st) { st_ = st; }
+    void set_events(cudaEvent_t a, cudaEvent_t b) { ev0_ = a; ev1_ = b; }
     LexStats last_stats();
     uint64_t n_postings() const { return n_post_; }
 
 private:
     int32_t ensure_workspace(uint32_t nq, uint32_t total_terms);
     cudaStream_t st_;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int n_sms_;
     uint32_t max_batch_;
     bool committed_ = false;

@@ -237,8 +237,10 @@ int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st) {
         SSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set[ai] = true;
     }
+    if (a.ev0) cudaEventRecord(a.ev0, st);
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
                                             a.scratch);
+    if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     merge_lists<<<a.nq_pad, 256, 0, st>>>(a.scratch, n_lists, QT, a.keys_out);
     SSB_CUDA_TRY(cudaGetLastError());

@@ -21,6 +21,7 @@ struct ScanArgs {
     uint64_t* scratch;
     size_t scratch_bytes;
     uint64_t* keys_out;           // [nq_pad][32]
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // recorded around the scan kernel when set
 };
 
 int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);

@@ -265,8 +265,9 @@ class Index:
         s = SsbStats()
         check(lib().ssb_last_stats(self._h, C.byref(s)))
         return dict(kernel_launches=s.kernel_launches, algorithmic_bytes=s.algorithmic_bytes, h2d_bytes=s.h2d_bytes,
-                    d2h_bytes=s.d2h_bytes, postings_visited=s.postings_visited, probes=s.reserved[0],
-                    items_processed=s.reserved[1], items_skipped=s.reserved[2])
+                    d2h_bytes=s.d2h_bytes, postings_visited=s.postings_visited, probes=s.probes,
+                    items_processed=s.items_processed, items_skipped=s.items_skipped,
+                    dominant_kernel_ns=s.dominant_kernel_ns)
 
     # ------------------------------------------------------------------ device-resident API (bench / multi-GPU)
     def search_vector_keys(self, queries_dev, k: int, keys_out_dev):
