@@ -68,7 +68,7 @@ struct ssb_index {
     DevBuf<uint32_t> doc_ids;
     uint64_t n_rows = 0;
     // query workspace
-    DevBuf<float> qpad; DevBuf<float> qstage; DevBuf<uint64_t> scratch; DevBuf<uint64_t> keys_a, keys_b, counts;
+    DevBuf<float> qpad; DevBuf<float> qstage; DevBuf<float> qhi, qlo; DevBuf<uint64_t> scratch; DevBuf<uint64_t> keys_a, keys_b, counts;
     std::vector<uint64_t> h_keys_a, h_keys_b, h_counts;
     ssb_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_used = false;
@@ -80,7 +80,9 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     if (ix->dims == 0) { set_error("no vector index configured (vector_dims = 0)"); return SSB_E_STATE; }
     if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
     if (nq == 0) return SSB_OK;
-    const uint32_t nq_pad = (nq + vec::VEC_QT - 1) / vec::VEC_QT * vec::VEC_QT;
+    const bool use_tc = ix->cfg.vector_kernel == SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN;
+    const uint32_t qt = use_tc ? vec::VEC_TC_NQ : vec::VEC_QT;
+    const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
     SSB_TRY(ix->qpad.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
     const float* qsrc = queries;
     if (!dev_ptr(queries)) {
@@ -93,7 +95,7 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
                                      ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->st));
     ix->stats.kernel_launches += 1;
     if (ix->n_rows == 0) { SSB_CUDA_TRY(cudaMemsetAsync(keys_out_dev, 0, (size_t)nq * LIST * 8, ix->st)); return SSB_OK; }
-    size_t sb = vec::scan_scratch_bytes(ix->n_sms, nq_pad);
+    size_t sb = use_tc ? vec::scan_tc_scratch_bytes(ix->n_sms, nq_pad) : vec::scan_scratch_bytes(ix->n_sms, nq_pad);
     SSB_TRY(ix->scratch.reserve(sb / 8 + (size_t)nq_pad * LIST, 0, ix->st));
     vec::ScanArgs a{};
     a.rows = ix->rows.p; a.doc_ids = ix->doc_ids.p; a.n_rows = ix->n_rows; a.dpad = ix->dpad; a.queries_padded = ix->qpad.p;
@@ -101,10 +103,18 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     a.scratch = ix->scratch.p; a.scratch_bytes = sb;
     uint64_t* merged = ix->scratch.p + sb / 8;   // [nq_pad][32]
     a.keys_out = merged; a.ev0 = ix->ev0; a.ev1 = ix->ev1; ix->ev_used = true;
-    SSB_TRY(vec::launch_scan_ffma(a, ix->st));
+    if (use_tc) {
+        SSB_TRY(ix->qhi.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
+        SSB_TRY(ix->qlo.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
+        a.q_hi = ix->qhi.p; a.q_lo = ix->qlo.p;
+        SSB_TRY(vec::launch_scan_tc(a, ix->st));
+        ix->stats.kernel_launches += 1;
+    } else {
+        SSB_TRY(vec::launch_scan_ffma(a, ix->st));
+    }
     SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, ix->st));
     ix->stats.kernel_launches += 2;
-    ix->stats.algorithmic_bytes += (uint64_t)(nq_pad / vec::VEC_QT) * ix->n_rows * ix->dims * 4;
+    ix->stats.algorithmic_bytes += (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * 4;
     return SSB_OK;
 }
 
@@ -165,7 +175,7 @@ int32_t ssb_destroy(ssb_index* ix) {
     cudaSetDevice(ix->cfg.device);
     cudaStreamSynchronize(ix->st);
     delete ix->lex;
-    ix->rows.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->scratch.release();
+    ix->rows.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->qhi.release(); ix->qlo.release(); ix->scratch.release();
     ix->keys_a.release(); ix->keys_b.release(); ix->counts.release();
     cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1);
     cudaStreamDestroy(ix->own_st);

@@ -247,6 +247,10 @@ int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st) {
     return SSB_OK;
 }
 
+void merge_lists_generic(const uint64_t* in, uint32_t n_lists, uint32_t qt, uint32_t nq, uint64_t* out, cudaStream_t st) {
+    merge_lists<<<nq, 256, 0, st>>>(in, n_lists, qt, out);
+}
+
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad) {
     return (size_t)(nq_pad / QT) * (size_t)n_sms * (CWARPS / 2) * QT * LIST * 8;
 }

@@ -6,7 +6,8 @@
 namespace ssb {
 namespace vec {
 
-constexpr int VEC_QT = 16;  // queries per corpus pass of the FFMA kernel
+constexpr int VEC_QT = 16;      // queries per corpus pass of the FFMA kernel
+constexpr int VEC_TC_NQ = 128;  // queries per corpus pass of the tcgen05 kernel (UMMA N)
 
 struct ScanArgs {
     const float* rows;            // [n_rows][dpad]
@@ -22,10 +23,15 @@ struct ScanArgs {
     size_t scratch_bytes;
     uint64_t* keys_out;           // [nq_pad][32]
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // recorded around the scan kernel when set
+    float* q_hi = nullptr; float* q_lo = nullptr;  // [nq_pad][dpad] tf32 split of the queries (tcgen05 kernel)
 };
 
 int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);
+int32_t launch_scan_tc(const ScanArgs& a, cudaStream_t st);
+size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad);
+// lists laid out [group][n_lists][qt][32] -> out [nq][32]
+void merge_lists_generic(const uint64_t* in, uint32_t n_lists, uint32_t qt, uint32_t nq, uint64_t* out, cudaStream_t st);
 int32_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, float* out,
                             uint32_t nq_pad, uint32_t dpad, int normalize, cudaStream_t st);
 int32_t launch_normalize_rows(float* rows, uint64_t n, uint32_t dims, uint32_t dpad, int normalize, cudaStream_t st);

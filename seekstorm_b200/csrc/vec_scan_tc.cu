@@ -1,0 +1,289 @@
+// vec_scan_tc.cu — tensor-core variant of the brute-force vector scan (sm_100a, tcgen05 + TMEM + TMA).
+//
+// Same contract as scan_ffma (vec_scan.cu): corpus [n_rows, Dpad] f32 x a block of NQ queries -> per-CTA
+// top-32 lists, but the query x corpus contraction runs on the 5th-gen tensor cores:
+//   D[128 corpus rows, NQ queries] (f32, TMEM) += A[128 x 8] . B[NQ x 8]^T      tcgen05.mma kind::tf32
+// f32 accuracy (north-star tolerance 1e-4 on cosine scores) is kept with the 3xTF32 split
+//   a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo,   x_hi = x & 0xFFFFE000 (exactly representable in tf32),
+//   x_lo = x - x_hi (exact in f32); the dropped a_lo.b_lo term is ~2^-22 relative.
+// B_hi / B_lo are prepared once per batch in global memory; A_hi / A_lo are produced per stage in shared
+// memory by 4 "splitter" warps (the corpus is stored once, as f32 — algorithmic bytes stay n_rows*dims*4).
+//
+// Warp roles (384 threads, 1 CTA/SM): w0 TMA producer | w1 TMEM alloc + MMA issuer | w4-7 epilogue (TMEM
+// lane quadrant = warp%4) | w8-11 splitters.  Pipelines: full/split/empty per smem stage, tfull/tempty per
+// TMEM accumulator buffer (double-buffered: the epilogue of tile t overlaps the MMAs of tile t+1).
+// Epilogue: tcgen05.ld 8 query columns at a time, filter against the per-query threshold, warp-aggregated
+// push into per-query buckets, per-query sorted lists (smem) updated by warp-shuffle insertion.
+#include "common.cuh"
+#include "vec_scan.h"
+
+namespace ssb {
+namespace vec {
+
+namespace tc {
+constexpr int KC = 32;                 // floats per k-chunk = one 128-byte swizzle row
+constexpr int TM = 128;                // corpus rows per tile = UMMA M
+constexpr int STAGES = 2;
+constexpr int A_BYTES = TM * KC * 4;   // 16 KB
+constexpr int THREADS = 384;
+constexpr int CHUNK = 8;               // query columns per epilogue step
+
+template <int NQ> struct Cfg {
+    static constexpr int B_BYTES = NQ * KC * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // A, A_lo, B_hi, B_lo
+    static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
+    static constexpr int LIST_BYTES = NQ * LIST * 8;
+    static constexpr int CAND_BYTES = CHUNK * TM * 8;
+    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + LIST_BYTES + CAND_BYTES + NQ * 4 + 256;
+    static constexpr int TMEM_COLS = 2 * NQ;                               // power of two for NQ in {64,128,256}
+};
+
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+    // K-major, SWIZZLE_128B canonical layout ((8,n),2):((8,SBO),1) in 16-byte units: LBO = 1, SBO = 1024 B
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int NQ>
+__global__ void __launch_bounds__(THREADS, 1)
+scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+        const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
+        const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x][NQ][32]*/) {
+    using C = Cfg<NQ>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage0 = base;
+    uint64_t* lists = (uint64_t*)(base + STAGES * C::STAGE_BYTES);            // [NQ][32]
+    uint64_t* cand = (uint64_t*)((uint8_t*)lists + C::LIST_BYTES);            // [CHUNK][TM]
+    float* thr_s = (float*)((uint8_t*)cand + C::CAND_BYTES);                  // [NQ]
+    uint64_t* bars = (uint64_t*)(thr_s + NQ);
+    uint64_t* full = bars;                 // [STAGES]
+    uint64_t* split = full + STAGES;       // [STAGES]
+    uint64_t* empty = split + STAGES;      // [STAGES]
+    uint64_t* tfull = empty + STAGES;      // [2]
+    uint64_t* tempty = tfull + 2;          // [2]
+    uint32_t* cand_cnt = (uint32_t*)(tempty + 2);   // [CHUNK]
+    uint32_t* tmem_slot = cand_cnt + CHUNK;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t group = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < NQ * LIST; i += THREADS) lists[i] = 0;
+    for (int i = threadIdx.x; i < NQ; i += THREADS) thr_s[i] = -INFINITY;
+    if (threadIdx.x < CHUNK) cand_cnt[threadIdx.x] = 0;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *(volatile uint32_t*)tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
+                    uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    uint8_t* st = stage0 + s * C::STAGE_BYTES;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full[s], C::TX_BYTES);
+                    tma_load_2d(st, &tmA, (int)(kc * KC), (int)(tile * TM), &full[s]);
+                    tma_load_2d(st + 2 * A_BYTES, &tmBh, (int)(kc * KC), (int)(group * NQ), &full[s]);
+                    tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmBl, (int)(kc * KC), (int)(group * NQ), &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            uint32_t it = 0, ti = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
+                mbar_wait(&tempty[buf], tph ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * NQ;
+                for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
+                    uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&full[s], ph);
+                    mbar_wait(&split[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage0 + s * C::STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_k128(sa), a_lo = umma_desc_k128(sa + A_BYTES);
+                    const uint64_t b_hi = umma_desc_k128(sa + 2 * A_BYTES), b_lo = umma_desc_k128(sa + 2 * A_BYTES + C::B_BYTES);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < 4; kk++) {        // 4 x K=8 (32 bytes) inside the 128-byte swizzle row
+                        const uint64_t o = (uint64_t)(kk * 2);  // +32 bytes in 16-byte units
+                        umma_tf32(d, a_hi + o, b_hi + o, idesc, (kc | kk) != 0);
+                        umma_tf32(d, a_lo + o, b_hi + o, idesc, 1);
+                        umma_tf32(d, a_hi + o, b_lo + o, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);                      // stage reusable once these MMAs retire
+                    if (kc + 1 == n_kchunks) umma_commit(&tfull[buf]);
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== splitters: A -> (A_hi in place, A_lo) =====================
+        const int t = threadIdx.x - 256;   // 0..127
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
+                uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                uint4* A = (uint4*)(stage0 + s * C::STAGE_BYTES);
+                uint4* Al = (uint4*)(stage0 + s * C::STAGE_BYTES + A_BYTES);
+#pragma unroll
+                for (int j = 0; j < (A_BYTES / 16) / 128; j++) {
+                    uint4 x = A[t + 128 * j], h, l;
+                    h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
+                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+                    A[t + 128 * j] = h;
+                    Al[t + 128 * j] = l;
+                }
+                fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> filter -> per-query top-k =====================
+        const int ew = warp - 4;                          // == warp % 4 == TMEM lane quadrant
+        const int et = threadIdx.x - 128;                 // 0..127 == row inside the tile
+        uint32_t ti = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
+            mbar_wait(&tfull[buf], tph);
+            tc_fence_after();
+            const uint32_t row = tile * TM + (uint32_t)et;
+            const bool valid = row < n_rows;
+            for (int c = 0; c < NQ / CHUNK; c++) {
+                uint32_t v[CHUNK];
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * NQ + c * CHUNK;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) {
+                    const float sc = __uint_as_float(v[j]);
+                    const bool pass = valid && sc >= thr_s[c * CHUNK + j];
+                    const unsigned m = __ballot_sync(FULL, pass);
+                    if (m) {
+                        uint32_t b0 = 0;
+                        if (lane == 0) b0 = atomicAdd(&cand_cnt[j], (uint32_t)__popc(m));
+                        b0 = __shfl_sync(FULL, b0, 0);
+                        if (pass) {
+                            const uint32_t doc = doc_ids ? __ldg(&doc_ids[row]) : row;
+                            cand[j * TM + b0 + __popc(m & ((1u << lane) - 1u))] = pack_key(sc, doc);
+                        }
+                    }
+                }
+                named_bar(1, 128);
+                // warp ew owns buckets 2*ew, 2*ew+1 of this chunk
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++) {
+                    const int j = ew * 2 + jj, q = c * CHUNK + j;
+                    const uint32_t n = cand_cnt[j];
+                    if (n) {
+                        uint64_t L = lists[q * LIST + lane];
+                        for (uint32_t i = 0; i < n; i++) wl_insert(L, cand[j * TM + i], lane);
+                        lists[q * LIST + lane] = L;
+                        const uint64_t kth = shfl64(L, (int)k - 1);
+                        if (lane == 0) { thr_s[q] = kth ? key_score(kth) : -INFINITY; cand_cnt[j] = 0; }
+                    }
+                }
+                named_bar(1, 128);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+        // publish this CTA's lists
+        uint64_t* out = scratch + ((size_t)group * gridDim.x + blockIdx.x) * NQ * LIST;
+        for (int i = et; i < NQ * LIST; i += 128) out[i] = lists[i];
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// [nq_pad][dpad] f32 -> hi / lo tf32 parts
+__global__ void split_queries(const float* __restrict__ q, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = __float_as_uint(q[i]), h = x & 0xFFFFE000u;
+    hi[i] = __uint_as_float(h);
+    lo[i] = __uint_as_float(x) - __uint_as_float(h);
+}
+
+}  // namespace tc
+
+template <int NQ>
+static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
+    using C = tc::Cfg<NQ>;
+    CUtensorMap tmA, tmBh, tmBl;
+    uint32_t n_tiles = (uint32_t)((a.n_rows + tc::TM - 1) / tc::TM);
+    uint32_t n_groups = a.nq_pad / NQ;
+    SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TM, 1));
+    SSB_TRY(encode_tmap_2d_f32(&tmBh, a.q_hi, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
+    SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
+    uint32_t gx = n_tiles < (uint32_t)a.n_sms ? n_tiles : (uint32_t)a.n_sms;
+    if ((size_t)n_groups * gx * NQ * LIST * 8 > a.scratch_bytes) { set_error("vector scan scratch too small"); return SSB_E_STATE; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    size_t nel = (size_t)a.nq_pad * a.dpad;
+    tc::split_queries<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, a.q_hi, a.q_lo, nel);
+    if (a.ev0) cudaEventRecord(a.ev0, st);
+    tc::scan_tc<NQ><<<dim3(gx, n_groups), tc::THREADS, C::SMEM, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, a.dpad / tc::KC, n_tiles,
+                                                                       a.k, a.doc_ids, a.scratch);
+    if (a.ev1) cudaEventRecord(a.ev1, st);
+    SSB_CUDA_TRY(cudaGetLastError());
+    // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ
+    merge_lists_generic(a.scratch, gx, NQ, a.nq_pad, a.keys_out, st);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_scan_tc(const ScanArgs& a, cudaStream_t st) {
+    if (a.n_rows == 0 || a.nq_pad == 0) return SSB_OK;
+    if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }
+    if (a.nq_pad % VEC_TC_NQ != 0) { set_error("tcgen05 scan: query count must be padded to %d", VEC_TC_NQ); return SSB_E_INVALID; }
+    return launch_tc_n<VEC_TC_NQ>(a, st);
+}
+
+size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)(nq_pad / VEC_TC_NQ) * (size_t)n_sms * VEC_TC_NQ * LIST * 8; }
+
+}  // namespace vec
+}  // namespace ssb

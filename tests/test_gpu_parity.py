@@ -220,3 +220,23 @@ def test_errors_are_status_codes():
         ix.add_vector_level(0, np.zeros((4, 16), dtype=np.float32))
     assert ix.search_vector_batch(np.ones((2, 32), dtype=np.float32), 5) == [[], []]   # empty index -> empty results
     ix.close()
+
+
+@pytest.mark.parametrize("n,dims,sim", [(300, 32, "dot"), (5000, 128, "cos"), (40000, 768, "cos"), (1000, 100, "dot")])
+def test_vector_tcgen05_parity(n, dims, sim):
+    """tcgen05 (3xTF32 split, TMEM accumulators) scan vs the oracle: same ids, scores within 1e-4 relative."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    simv = {"cos": VectorSimilarity.Cosine, "dot": VectorSimilarity.Dot}[sim]
+    osim = {"cos": O.SIM_COSINE, "dot": O.SIM_DOT}[sim]
+    rows = synth.gen_vectors(n, dims, 3000 + n, "cpu").numpy()
+    qs = synth.gen_vectors(150, dims, 4000 + n, "cpu").numpy()      # 150 -> padded to 256 = two query groups
+    qs[3] = rows[n // 2] + 0.05 * qs[3]
+    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_kernel=2)
+    ix.add_vectors(rows)
+    ref_rows = np.stack([O.normalize(r) for r in rows]) if sim == "cos" else rows
+    for k in (10, 32):
+        got = ix.search_vector_batch(qs, k)
+        for i in range(0, len(qs), 7):
+            q = O.normalize(qs[i]) if sim == "cos" else qs[i]
+            _check_vec(got[i], O.search_vector(ref_rows, q, k, osim))
+    ix.close()
