@@ -405,6 +405,9 @@ def main():
     if not os.path.exists(g.LIB):
         g.build()
     rank, world = dist_setup(a.gpus)
+    # one explicit (non-default) stream for everything: library kernels, torch CUDA events and NCCL collectives
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     out = {"n_gpus": world, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "impl": "b200"}
     ix, _ = bench_vector(a, rank, world, out)

@@ -147,8 +147,10 @@ int32_t ssb_sync(ssb_index* ix);
 /* the CUDA stream the index launches on (cudaStream_t as void*), for event timing */
 void*   ssb_stream(ssb_index* ix);
 /* run all further work of this index on a caller-owned stream (e.g. the stream NCCL collectives are enqueued
- * on, so the per-GPU top-k -> all-gather -> merge chain needs no host synchronisation); NULL restores the
- * index's own stream */
+ * on, so the per-GPU top-k -> all-gather -> merge chain needs no host synchronisation).  The value is used
+ * as a cudaStream_t as is (NULL = the CUDA legacy default stream); SSB_OWN_STREAM restores the index's own
+ * stream. */
+#define SSB_OWN_STREAM ((void*)(intptr_t)-1)
 int32_t ssb_set_stream(ssb_index* ix, void* cuda_stream);
 
 /* ---- statistics of the last search_* call (for roofline accounting) -------------------------------- */

@@ -378,7 +378,7 @@ int32_t ssb_set_stream(ssb_index* ix, void* stream) {
     std::lock_guard<std::mutex> g(ix->mu);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-    ix->st = stream ? (cudaStream_t)stream : ix->own_st;
+    ix->st = stream == SSB_OWN_STREAM ? ix->own_st : (cudaStream_t)stream;
     ix->lex->set_stream(ix->st);
     return SSB_OK;
 }

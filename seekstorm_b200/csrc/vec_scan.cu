@@ -9,11 +9,13 @@
 // doc ids live in a separate u32 array).  HBM-bound: algorithmic bytes per pass = n_rows*dims*4.
 //
 // Kernel scan_ffma: persistent CTAs (one per SM), 8 consumer warps + 1 TMA producer warp.
-//   producer: cp.async.bulk.tensor.2d of a [256 rows x 32 floats] corpus box (SWIZZLE_128B) and the
-//             [16 queries x 32 floats] query box into a 5-stage mbarrier ring.
-//   consumers: warp w owns rows (w>>1)*64 + lane + {0,32} of the tile and queries (w&1)*8..+8;
-//             FP32 FFMA accumulation over the k-chunks (conflict-free swizzled LDS.128 for rows,
-//             broadcast LDS.128 for queries), then a warp-shuffle top-k insert per finished tile.
+//   producer: cp.async.bulk.tensor.2d of two [256 rows x 32 floats] corpus boxes (SWIZZLE_128B, 64 KB) and
+//             the [16 queries x 32 floats] query box into a 3-stage mbarrier ring.
+//   consumers: warp w owns rows (w>>1)*128 + lane + 32*{0..3} of the tile and queries (w&1)*8..+8
+//             (4 x 8 register tile per lane): packed FP32x2 FFMA2 accumulation over the k-chunks
+//             (conflict-free swizzled LDS.128 for rows, broadcast LDS.128 for queries; the 4x8 tile
+//             keeps shared-memory wavefronts at ~55 % of the HBM-time budget), then a warp-shuffle
+//             top-k insert per finished tile.
 //   per-warp lists -> scratch; merge_lists kernel reduces them to the final per-query top-k.
 #include "common.cuh"
 #include "vec_scan.h"
@@ -22,25 +24,39 @@ namespace ssb {
 namespace vec {
 
 constexpr int KC = 32;                  // floats per k-chunk (128 B = one swizzle row)
-constexpr int TILE_ROWS = 256;
+constexpr int TILE_ROWS = 512;          // rows per pipeline stage (two 256-row TMA boxes)
+constexpr int BOX_ROWS = 256;
 constexpr int QT = VEC_QT;              // queries per pass (16)
-constexpr int STAGES = 5;
+constexpr int STAGES = 3;
 constexpr int CWARPS = 8;
 constexpr int THREADS = (CWARPS + 1) * 32;
-constexpr int A_BYTES = TILE_ROWS * KC * 4;  // 32 KB
+constexpr int A_BYTES = TILE_ROWS * KC * 4;  // 64 KB
 constexpr int Q_BYTES = QT * KC * 4;         // 2 KB
 constexpr int STAGE_TX = A_BYTES + Q_BYTES;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + Q_BYTES) + 2 * STAGES * 8;
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + Q_BYTES) + 2 * STAGES * 8;
+
+// packed FP32x2 math (Blackwell FFMA2 / FADD2): two FMAs per issued instruction
+__device__ __forceinline__ void ffma2(float2& c, float2 a, float2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(reinterpret_cast<unsigned long long&>(c))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    float2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return d;
+}
 
 template <int SIM>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __maxnreg__(224)
 scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
           uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
           const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*CWARPS/2][QT][32]*/) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = base;                                  // [STAGES][A_BYTES], each 1024-aligned
-    uint8_t* sQ = base + STAGES * A_BYTES;               // [STAGES][Q_BYTES]
+    // no static shared memory in this kernel: the dynamic segment starts at offset 0 of the CTA window, so the
+    // 1024-byte alignment SWIZZLE_128B needs holds and the pointers stay in the shared address space (LDS, not LD)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;                                  // [STAGES][A_BYTES]
+    uint8_t* sQ = smem + STAGES * A_BYTES;               // [STAGES][Q_BYTES]
     uint64_t* full = (uint64_t*)(sQ + STAGES * Q_BYTES); // [STAGES]
     uint64_t* empty = full + STAGES;                     // [STAGES]
 
@@ -64,21 +80,26 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&full[s], STAGE_TX);
                     tma_load_2d(sA + s * A_BYTES, &tmA, (int)(kc * KC), (int)(tile * TILE_ROWS), &full[s]);
+                    tma_load_2d(sA + s * A_BYTES + BOX_ROWS * KC * 4, &tmA, (int)(kc * KC), (int)(tile * TILE_ROWS + BOX_ROWS), &full[s]);
                     tma_load_2d(sQ + s * Q_BYTES, &tmQ, (int)(kc * KC), (int)(group * QT), &full[s]);
                 }
             }
         }
     } else {
-        // ===== consumers =====
-        const int rg = warp >> 1;            // row group 0..3 (64 rows each)
+        // ===== consumers: warp = (row group of 128 rows) x (query half); lane owns 4 rows x 8 queries =====
+        const int rg = warp >> 1;            // row group 0..3
         const int qh = (warp & 1) * 8;       // first query of this warp's half
-        const int r0 = rg * 64 + lane;       // rows r0 and r0+32; (r0+32)&7 == r0&7
+        const int r0 = rg * 128 + lane;      // rows r0 + 32*j, j = 0..3; all share (row & 7)
         const int sw = r0 & 7;
-        float acc[2][8];
+        float2 acc[4][8];                    // even-k / odd-k partial sums
         uint64_t L[8];
         uint32_t thr[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) { L[q] = 0; thr[q] = 0; acc[0][q] = 0.f; acc[1][q] = 0.f; }
+        for (int q = 0; q < 8; q++) {
+            L[q] = 0; thr[q] = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[j][q] = make_float2(0.f, 0.f);
+        }
 
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -89,30 +110,23 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const float4* Q = (const float4*)(sQ + s * Q_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < 8; kk++) {
-                    float4 a0 = A[r0 * 8 + (kk ^ sw)];
-                    float4 a1 = A[(r0 + 32) * 8 + (kk ^ sw)];
+                    float4 a[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) a[j] = A[(r0 + 32 * j) * 8 + (kk ^ sw)];
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
-                        float4 qv = Q[(qh + q) * 8 + kk];
-                        if (SIM == SSB_SIM_EUCLIDEAN) {
-                            float d;
-                            d = qv.x - a0.x; acc[0][q] = fmaf(d, d, acc[0][q]);
-                            d = qv.y - a0.y; acc[0][q] = fmaf(d, d, acc[0][q]);
-                            d = qv.z - a0.z; acc[0][q] = fmaf(d, d, acc[0][q]);
-                            d = qv.w - a0.w; acc[0][q] = fmaf(d, d, acc[0][q]);
-                            d = qv.x - a1.x; acc[1][q] = fmaf(d, d, acc[1][q]);
-                            d = qv.y - a1.y; acc[1][q] = fmaf(d, d, acc[1][q]);
-                            d = qv.z - a1.z; acc[1][q] = fmaf(d, d, acc[1][q]);
-                            d = qv.w - a1.w; acc[1][q] = fmaf(d, d, acc[1][q]);
-                        } else {
-                            acc[0][q] = fmaf(a0.x, qv.x, acc[0][q]);
-                            acc[0][q] = fmaf(a0.y, qv.y, acc[0][q]);
-                            acc[0][q] = fmaf(a0.z, qv.z, acc[0][q]);
-                            acc[0][q] = fmaf(a0.w, qv.w, acc[0][q]);
-                            acc[1][q] = fmaf(a1.x, qv.x, acc[1][q]);
-                            acc[1][q] = fmaf(a1.y, qv.y, acc[1][q]);
-                            acc[1][q] = fmaf(a1.z, qv.z, acc[1][q]);
-                            acc[1][q] = fmaf(a1.w, qv.w, acc[1][q]);
+                        const float4 qv = Q[(qh + q) * 8 + kk];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (SIM == SSB_SIM_EUCLIDEAN) {
+                                float2 d0 = fsub2(make_float2(qv.x, qv.y), make_float2(a[j].x, a[j].y));
+                                float2 d1 = fsub2(make_float2(qv.z, qv.w), make_float2(a[j].z, a[j].w));
+                                ffma2(acc[j][q], d0, d0);
+                                ffma2(acc[j][q], d1, d1);
+                            } else {
+                                ffma2(acc[j][q], make_float2(a[j].x, a[j].y), make_float2(qv.x, qv.y));
+                                ffma2(acc[j][q], make_float2(a[j].z, a[j].w), make_float2(qv.z, qv.w));
+                            }
                         }
                     }
                 }
@@ -122,13 +136,14 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (kc + 1 == n_kchunks) {
                     // ---- tile finished: fused top-k (TopK::push, vector.rs:410-497) ----
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
+                    for (int j = 0; j < 4; j++) {
                         uint32_t row = tile * TILE_ROWS + (uint32_t)r0 + 32u * j;
                         bool valid = row < n_rows;
 #pragma unroll
                         for (int q = 0; q < 8; q++) {
-                            float sc = (SIM == SSB_SIM_EUCLIDEAN) ? -acc[j][q] : acc[j][q];
-                            acc[j][q] = 0.f;
+                            float sum = acc[j][q].x + acc[j][q].y;
+                            float sc = (SIM == SSB_SIM_EUCLIDEAN) ? -sum : sum;
+                            acc[j][q] = make_float2(0.f, 0.f);
                             uint32_t so = ord_f32(sc);
                             unsigned m = __ballot_sync(FULL, valid && so >= thr[q] && sc == sc);
                             while (m) {
@@ -222,7 +237,7 @@ int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st) {
     uint32_t n_tiles = (uint32_t)((a.n_rows + TILE_ROWS - 1) / TILE_ROWS);
     uint32_t n_groups = a.nq_pad / QT;
     if (n_tiles == 0 || n_groups == 0) return SSB_OK;
-    SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, KC, TILE_ROWS, 1));
+    SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, KC, BOX_ROWS, 1));
     SSB_TRY(encode_tmap_2d_f32(&tmQ, a.queries_padded, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, KC, QT, 0));
     uint32_t gx = n_tiles < (uint32_t)a.n_sms ? n_tiles : (uint32_t)a.n_sms;
     dim3 grid(gx, n_groups);

@@ -292,9 +292,10 @@ class Index:
     def stream(self) -> int:
         return lib().ssb_stream(self._h) or 0
 
-    def set_stream(self, cuda_stream: int):
-        """Run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream."""
-        check(lib().ssb_set_stream(self._h, cuda_stream or None))
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned CUDA stream handle (e.g. torch.cuda.current_stream().cuda_stream; 0 = the CUDA legacy
+        default stream); None restores the index's own stream."""
+        check(lib().ssb_set_stream(self._h, C.c_void_p(-1 if cuda_stream is None else cuda_stream)))
 
     # ------------------------------------------------------------------ the reference's public call
     def search(self, query_string: str, query_vector=None, query_type_default: QueryType = QueryType.Union,
