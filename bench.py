@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--bm25-docs", type=int, default=C3_DOCS)
     p.add_argument("--bm25-batch", type=int, default=4096, help="lexical queries per step")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
+    p.add_argument("--vector-kernel", default="ffma", choices=["ffma", "tc"], help="FP32 FFMA2 scan or tcgen05 3xTF32 scan")
     return p.parse_args()
 
 
@@ -156,7 +157,9 @@ def bench_vector(a, rank, world, out):
     from seekstorm_b200 import Index, VectorSimilarity
     from seekstorm_b200.parallel import ShardedSearcher
     dev = torch.device("cuda", torch.cuda.current_device())
-    ix = Index(dev.index, vector_dims=a.dims, vector_similarity=VectorSimilarity.Cosine, max_batch=max(a.batch, 16))
+    ix = Index(dev.index, vector_dims=a.dims, vector_similarity=VectorSimilarity.Cosine, max_batch=max(a.batch, 16),
+               vector_kernel=2 if a.vector_kernel == "tc" else 1)
+    qt = 128 if a.vector_kernel == "tc" else 16
     ix.set_stream(torch.cuda.current_stream().cuda_stream)
     n_levels, mine = vector_levels(a.rows, rank, world)
     local_rows = 0
@@ -189,7 +192,7 @@ def bench_vector(a, rank, world, out):
         step_dev(); torch.cuda.synchronize()
         kern_ns.append(ix.last_stats()["dominant_kernel_ns"])
     launches_per_step = 3 + (1 if world > 1 else 0)
-    passes = (a.batch + 15) // 16
+    passes = (a.batch + qt - 1) // qt
     qps = a.batch * a.steps / (ms / 1e3)
 
     # ---- e2e: the reference-facing call with HOST buffers (H2D queries, D2H hits inside the timed region) ----
@@ -214,14 +217,14 @@ def bench_vector(a, rank, world, out):
         "metric": "queries/sec at top-10 (1M x 768 f32 cosine brute-force kNN)", "value": qps, "unit": "queries/s",
         "ms_per_step": ms / a.steps, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C2 brute-force cosine kNN: {a.rows} x {a.dims} f32, top-{TOPK}, batch {a.batch} queries/step "
-                               f"({passes} corpus passes of 16 queries)", "l2": "inputs larger than L2 (corpus %.2f GB per GPU)" % (local_rows * a.dims * 4 / 1e9),
-                   "parallelism": f"levels sharded over {world} GPU(s)", "kernel": "scan_ffma (TMA + FP32 FFMA + warp top-k)"},
+                               f"({passes} corpus passes of {qt} queries)", "l2": "inputs larger than L2 (corpus %.2f GB per GPU)" % (local_rows * a.dims * 4 / 1e9),
+                   "parallelism": f"levels sharded over {world} GPU(s)", "kernel": "scan_tc (TMA + tcgen05 3xTF32 + TMEM epilogue top-k)" if a.vector_kernel == "tc" else "scan_ffma (TMA + packed FP32 FFMA2 + warp top-k)"},
         "e2e": {"value": qps_e2e, "unit": "queries/s", "ms_per_step": ms_e2e / a.steps,
                 "h2d_bytes_per_step": a.batch * a.dims * 4, "d2h_bytes_per_step": a.batch * 32 * 8},
         "gpu_launches": launches_per_step * a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_kind": f"of {peak_kind}",
-                     "kernel": "scan_ffma", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
+                     "kernel": "scan_tc" if a.vector_kernel == "tc" else "scan_ffma", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
         "clocks": clocks,
     })
     return ix, q_host

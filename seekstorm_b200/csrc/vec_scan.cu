@@ -33,7 +33,8 @@ constexpr int THREADS = (CWARPS + 1) * 32;
 constexpr int A_BYTES = TILE_ROWS * KC * 4;  // 64 KB
 constexpr int Q_BYTES = QT * KC * 4;         // 2 KB
 constexpr int STAGE_TX = A_BYTES + Q_BYTES;
-constexpr int SMEM_BYTES = STAGES * (A_BYTES + Q_BYTES) + 2 * STAGES * 8;
+constexpr int LISTS_BYTES = CWARPS * 8 * LIST * 8;   // per-warp top-k lists (8 queries x 32 keys) live in smem
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + Q_BYTES) + LISTS_BYTES + 2 * STAGES * 8;
 
 // packed FP32x2 math (Blackwell FFMA2 / FADD2): two FMAs per issued instruction
 __device__ __forceinline__ void ffma2(float2& c, float2 a, float2 b) {
@@ -48,7 +49,7 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
 }
 
 template <int SIM>
-__global__ void __maxnreg__(224)
+__global__ void __launch_bounds__(THREADS, 1)
 scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
           uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
           const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*CWARPS/2][QT][32]*/) {
@@ -57,7 +58,8 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                  // [STAGES][A_BYTES]
     uint8_t* sQ = smem + STAGES * A_BYTES;               // [STAGES][Q_BYTES]
-    uint64_t* full = (uint64_t*)(sQ + STAGES * Q_BYTES); // [STAGES]
+    uint64_t* sL = (uint64_t*)(sQ + STAGES * Q_BYTES);   // [CWARPS][8][32] (9 warps -> one SMSP hosts 3: 168 regs/thread max)
+    uint64_t* full = sL + CWARPS * 8 * LIST;             // [STAGES]
     uint64_t* empty = full + STAGES;                     // [STAGES]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,11 +94,11 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int r0 = rg * 128 + lane;      // rows r0 + 32*j, j = 0..3; all share (row & 7)
         const int sw = r0 & 7;
         float2 acc[4][8];                    // even-k / odd-k partial sums
-        uint64_t L[8];
+        uint64_t* myL = sL + (size_t)warp * 8 * LIST + lane;   // myL[q * LIST]
         uint32_t thr[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            L[q] = 0; thr[q] = 0;
+            myL[q * LIST] = 0; thr[q] = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[j][q] = make_float2(0.f, 0.f);
         }
@@ -146,16 +148,20 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             acc[j][q] = make_float2(0.f, 0.f);
                             uint32_t so = ord_f32(sc);
                             unsigned m = __ballot_sync(FULL, valid && so >= thr[q] && sc == sc);
-                            while (m) {
-                                int src = __ffs(m) - 1;
-                                m &= m - 1;
-                                uint32_t so_s = __shfl_sync(FULL, so, src);
-                                uint32_t row_s = __shfl_sync(FULL, row, src);
-                                uint32_t doc = doc_ids ? __ldg(&doc_ids[row_s]) : row_s;
-                                uint64_t key = ((uint64_t)so_s << 32) | (uint64_t)(0xFFFFFFFFu - doc);
-                                wl_insert(L[q], key, lane);
+                            if (m) {                                   // rare after warm-up
+                                uint64_t Lq = myL[q * LIST];
+                                while (m) {
+                                    int src = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    uint32_t so_s = __shfl_sync(FULL, so, src);
+                                    uint32_t row_s = __shfl_sync(FULL, row, src);
+                                    uint32_t doc = doc_ids ? __ldg(&doc_ids[row_s]) : row_s;
+                                    uint64_t key = ((uint64_t)so_s << 32) | (uint64_t)(0xFFFFFFFFu - doc);
+                                    wl_insert(Lq, key, lane);
+                                }
+                                myL[q * LIST] = Lq;
+                                thr[q] = (uint32_t)(shfl64(Lq, (int)k - 1) >> 32);
                             }
-                            thr[q] = (uint32_t)(shfl64(L[q], (int)k - 1) >> 32);
                         }
                     }
                 }
@@ -165,7 +171,7 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t n_lists = gridDim.x * (CWARPS / 2);
         uint64_t* out = scratch + ((size_t)group * n_lists + (size_t)blockIdx.x * (CWARPS / 2) + rg) * QT * LIST;
 #pragma unroll
-        for (int q = 0; q < 8; q++) out[(qh + q) * LIST + lane] = L[q];
+        for (int q = 0; q < 8; q++) out[(qh + q) * LIST + lane] = myL[q * LIST];
     }
 }
 
