@@ -36,12 +36,12 @@
 namespace ssb {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr uint32_t DENSE_MIN = 4096;   // lists at least this long get a bitmap container
+constexpr uint32_t DENSE_MIN = 256;    // lists at least this long get a bitmap + rank index (O(1) probes)
 constexpr uint32_t MAX_LEVELS = 4096;  // per GPU (268M docs); plan kernel smem bound
 
 // ================================================================= build kernels
 __global__ void build_payload(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs,
-                              const uint8_t* __restrict__ len_bytes, uint16_t* __restrict__ pay, uint32_t n,
+                              const uint8_t* __restrict__ len_bytes, uint32_t* __restrict__ post, uint32_t n,
                               uint64_t post_base, uint64_t* exc_pos, uint32_t* exc_tf, uint32_t* exc_count,
                               uint32_t exc_cap) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,7 +53,7 @@ __global__ void build_payload(const uint16_t* __restrict__ ids, const uint16_t* 
         if (s < exc_cap) { exc_pos[s] = post_base + i; exc_tf[s] = tf; }
         tf = 255;
     }
-    pay[i] = (uint16_t)(tf | (len << 8));
+    post[i] = (uint32_t)ids[i] | ((tf | (len << 8)) << 16);   // id16 | tf8<<16 | len8<<24
 }
 
 __global__ void gather_dict(const uint64_t* __restrict__ term_keys, uint32_t n_terms, uint32_t level_idx,
@@ -95,7 +95,7 @@ __global__ void entry_maxcomp(LexView v, uint32_t n_entries, float* __restrict__
     int lane = threadIdx.x & 31;
     uint64_t off = v.e_off[e]; uint32_t cnt = v.e_count[e];
     float m = 0.f;
-    for (uint32_t i = lane; i < cnt; i += 32) m = fmaxf(m, comp_of(v, v.pay[off + i], off + i));
+    for (uint32_t i = lane; i < cnt; i += 32) m = fmaxf(m, comp_of(v, v.post[off + i] >> 16, off + i));
     for (int s = 16; s; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
     if (lane == 0) out[e] = m;
 }
@@ -111,7 +111,7 @@ __global__ void assign_bitmap(const uint32_t* __restrict__ e_count, const uint32
 // one CTA (256 threads) per dense entry
 __global__ void __launch_bounds__(256) build_bitmaps(const uint32_t* __restrict__ e_bitmap, const uint64_t* __restrict__ e_off,
                                                      const uint32_t* __restrict__ e_count, uint32_t n_entries,
-                                                     const uint16_t* __restrict__ ids, uint64_t* bm_words, uint16_t* bm_rank,
+                                                     const uint32_t* __restrict__ post, uint64_t* bm_words, uint16_t* bm_rank,
                                                      const uint32_t* __restrict__ dense_list) {
     __shared__ unsigned long long w[1024];
     __shared__ uint32_t pc[1024];
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) build_bitmaps(const uint32_t* __restrict_
     __syncthreads();
     uint64_t off = e_off[e]; uint32_t cnt = e_count[e];
     for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
-        uint32_t d = ids[off + i];
+        uint32_t d = post[off + i] & 0xFFFFu;
         atomicOr(&w[d >> 6], 1ull << (d & 63));
     }
     __syncthreads();
@@ -154,14 +154,19 @@ __global__ void compact_dense(const uint32_t* __restrict__ e_bitmap, uint32_t n,
 // ================================================================= plan kernel
 // One CTA per query.  Dictionary lookup (replaces decode_posting_list_object / segment.get, search.rs:2292-2423,
 // 3194-3217), live-term list in query order, per-level bound and presence count, blocks sorted by bound desc
-// (intersection.rs:2224-2225, single.rs:372).
+// (intersection.rs:2224-2225, single.rs:372).  For the first FAST_T live terms the entry index of every level is
+// recorded with the item so the scoring kernel needs no directory search.
+constexpr uint32_t FAST_T = 4;          // queries with <= 4 live terms take the register-resident fast path
+constexpr uint32_t ENT_NONE = 0xFFFFu;
+
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
-                                                uint32_t query_type, QueryPlan* plans, uint64_t* items, uint32_t* ctr,
+                                                uint32_t query_type, QueryPlan* plans, uint64_t* items, uint2* item_ent, uint32_t* ctr,
                                                 uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     float* bound = (float*)sm_raw;                                     // [n_levels]
     uint32_t* cnt = (uint32_t*)(bound + v.n_levels);                   // [n_levels]
-    uint64_t* skey = (uint64_t*)(((uintptr_t)(cnt + v.n_levels) + 7) & ~(uintptr_t)7);  // [n_pow2]
+    uint16_t* ent = (uint16_t*)(cnt + v.n_levels);                     // [FAST_T][n_levels] entry index relative to term.first
+    uint64_t* skey = (uint64_t*)(((uintptr_t)(ent + FAST_T * v.n_levels) + 7) & ~(uintptr_t)7);  // [n_pow2]
     __shared__ QTerm st[SSB_MAX_QUERY_TERMS];
     __shared__ QueryPlan pl;
     __shared__ uint32_t n_valid;
@@ -189,7 +194,10 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         if (query_type == SSB_QUERY_INTERSECTION && missing) nl = 0;
         pl.n_live = nl; pl.n_items = 0; pl.flags = 0; pl.pad = 0;
     }
-    for (uint32_t b = threadIdx.x; b < v.n_levels; b += blockDim.x) { bound[b] = 0.f; cnt[b] = 0; }
+    for (uint32_t b = threadIdx.x; b < v.n_levels; b += blockDim.x) {
+        bound[b] = 0.f; cnt[b] = 0;
+        for (uint32_t t = 0; t < FAST_T; t++) ent[t * v.n_levels + b] = (uint16_t)ENT_NONE;
+    }
     __syncthreads();
     const uint32_t nl = pl.n_live;
     for (uint32_t t = 0; t < nl; t++) {   // QUERY ORDER: the bound is summed exactly like a score would be
@@ -198,6 +206,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             uint32_t lv = v.e_level[qt.first + e];
             bound[lv] = __fadd_rn(bound[lv], __fmul_rn(qt.idf, v.e_maxcomp[qt.first + e]));
             cnt[lv] += 1;
+            if (t < FAST_T) ent[t * v.n_levels + lv] = (uint16_t)e;
         }
         __syncthreads();
     }
@@ -223,7 +232,17 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             __syncthreads();
         }
     }
-    for (uint32_t j = threadIdx.x; j < v.n_levels; j += blockDim.x) items[(size_t)q * v.n_levels + j] = skey[j];
+    for (uint32_t j = threadIdx.x; j < v.n_levels; j += blockDim.x) {
+        const uint64_t key = skey[j];
+        items[(size_t)q * v.n_levels + j] = key;
+        if (key) {
+            const uint32_t lv = 0xFFFFFFFFu - (uint32_t)key;
+            uint2 e;
+            e.x = (uint32_t)ent[lv] | ((uint32_t)ent[v.n_levels + lv] << 16);
+            e.y = (uint32_t)ent[2 * v.n_levels + lv] | ((uint32_t)ent[3 * v.n_levels + lv] << 16);
+            item_ent[(size_t)q * v.n_levels + j] = e;
+        }
+    }
     if (threadIdx.x == 0) {
         pl.n_items = n_valid;
         plans[q] = pl;
@@ -232,11 +251,11 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
 }
 
 // ================================================================= scoring kernel
-struct TermRegs {   // lane t holds query term t of the current item
+struct TermRegs {   // generic path: lane t holds query term t of the current item
     uint32_t cnt; uint64_t off; uint32_t bmi; float idf; float ub;
 };
 
-// membership + rank probe of doc d in the list described by (cnt, off, bmi)
+// membership + rank probe of doc d in the list described by (cnt, off, bmi); posting word returned in `pw`
 __device__ __forceinline__ bool probe(const LexView& v, uint32_t cnt, uint64_t off, uint32_t bmi, uint32_t d, uint32_t& rank) {
     if (bmi != NONE) {
         uint64_t w = __ldg(&v.bm_words[(size_t)bmi * 1024 + (d >> 6)]);
@@ -245,15 +264,15 @@ __device__ __forceinline__ bool probe(const LexView& v, uint32_t cnt, uint64_t o
         return true;
     }
     uint32_t lo = 0, hi = cnt;
-    const uint16_t* a = v.ids + off;
-    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((uint32_t)__ldg(&a[m]) < d) lo = m + 1; else hi = m; }
+    const uint32_t* a = v.post + off;
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((__ldg(&a[m]) & 0xFFFFu) < d) lo = m + 1; else hi = m; }
     rank = lo;
-    return lo < cnt && (uint32_t)__ldg(&a[lo]) == d;
+    return lo < cnt && (__ldg(&a[lo]) & 0xFFFFu) == d;
 }
 
 __device__ __forceinline__ float term_score(const LexView& v, float idf, uint64_t pos) {
     // idf * ((tf*(K+1)/(tf+comp)) + SIGMA), SIGMA = 0 (x + 0.0 == x)
-    return __fmul_rn(idf, comp_of(v, __ldg(&v.pay[pos]), pos));
+    return __fmul_rn(idf, comp_of(v, __ldg(&v.post[pos]) >> 16, pos));
 }
 
 __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bool cand, float score, uint32_t doc,
@@ -271,9 +290,277 @@ __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bo
     if (kth > thr) thr = kth;
 }
 
+struct ItemCtx {
+    uint32_t q, lv, n, k, docbase, bound_ord;
+    bool scoring, need_count, is_and;
+};
+
+// ---- fast path: n <= FAST_T live terms, per-term state in (warp-uniform) registers ----
+__device__ __forceinline__ void process_item_fast(const LexView& v, const QueryPlan* pl, const ItemCtx& c, uint2 ient, int lane,
+                                                  uint64_t& L, uint32_t& thr, bool& dirty, uint64_t& matches,
+                                                  uint64_t& st_visited, uint64_t& st_probes) {
+    uint32_t cnt[FAST_T], bmi[FAST_T]; uint64_t off[FAST_T]; float idf[FAST_T], ub[FAST_T];
+    const uint32_t n = c.n;
+#pragma unroll
+    for (uint32_t t = 0; t < FAST_T; t++) {
+        cnt[t] = 0; bmi[t] = NONE; off[t] = 0; idf[t] = 0.f; ub[t] = 0.f;
+        const uint32_t er = (t < 2 ? (ient.x >> (16 * t)) : (ient.y >> (16 * (t - 2)))) & 0xFFFFu;
+        if (t < n) {
+            const QTerm qt = pl->t[t];
+            idf[t] = qt.idf;
+            if (er != ENT_NONE) {
+                const uint32_t e = qt.first + er;
+                cnt[t] = __ldg(&v.e_count[e]); off[t] = __ldg(&v.e_off[e]); bmi[t] = __ldg(&v.e_bitmap[e]);
+                ub[t] = __fmul_rn(qt.idf, __ldg(&v.e_maxcomp[e]));
+            }
+        }
+    }
+    if (c.is_and) {
+        // ---------------- AND: drive with the shortest list (intersection.rs:258-273) ----------------
+        uint32_t drv = 0, best = cnt[0];
+#pragma unroll
+        for (uint32_t t = 1; t < FAST_T; t++) if (t < n && cnt[t] < best) { best = cnt[t]; drv = t; }
+        uint32_t dcnt = 0; uint64_t doff = 0;
+#pragma unroll
+        for (uint32_t t = 0; t < FAST_T; t++) if (t == drv) { dcnt = cnt[t]; doff = off[t]; }
+        st_visited += dcnt;
+        for (uint32_t base = 0; base < dcnt; base += 32) {
+            const uint32_t p = base + lane;
+            const bool active = p < dcnt;
+            const uint32_t pd = active ? __ldg(&v.post[doff + p]) : 0u;
+            const uint32_t d = pd & 0xFFFFu;
+            bool ok = active; float score = 0.f;
+#pragma unroll
+            for (uint32_t t = 0; t < FAST_T; t++) {          // query order
+                if (t >= n) continue;
+                if (t == drv) { if (ok && c.scoring) score = __fadd_rn(score, __fmul_rn(idf[t], comp_of(v, pd >> 16, doff + p))); continue; }
+                if (!ok) continue;
+                uint32_t rank; st_probes++;
+                if (!probe(v, cnt[t], off[t], bmi[t], d, rank)) { ok = false; continue; }
+                if (c.scoring) score = __fadd_rn(score, term_score(v, idf[t], off[t] + rank));
+            }
+            matches += __popc(__ballot_sync(FULL, ok));
+            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
+        }
+        return;
+    }
+    // ---------------- OR ----------------
+    if (c.scoring) {
+        // MAXSCORE: terms by block bound desc (present first); pos[t] = rank of term t, ord_t[p] = term at rank p
+        uint32_t pos[FAST_T];
+#pragma unroll
+        for (uint32_t t = 0; t < FAST_T; t++) {
+            uint32_t r = 0;
+#pragma unroll
+            for (uint32_t u = 0; u < FAST_T; u++) {
+                if (u == t || u >= n) continue;
+                const bool before = (cnt[u] > 0 && cnt[t] == 0) || ((cnt[u] > 0) == (cnt[t] > 0) && (ub[u] > ub[t] || (ub[u] == ub[t] && u < t)));
+                if (before) r++;
+            }
+            pos[t] = t < n ? r : 0xFFFFu;
+        }
+        for (uint32_t p = 0; p < n; p++) {
+            uint32_t drv = 0;
+#pragma unroll
+            for (uint32_t t = 0; t < FAST_T; t++) if (pos[t] == p) drv = t;
+            uint32_t dcnt = 0; uint64_t doff = 0; float didf = 0.f;
+#pragma unroll
+            for (uint32_t t = 0; t < FAST_T; t++) if (t == drv) { dcnt = cnt[t]; doff = off[t]; didf = idf[t]; }
+            if (dcnt == 0) break;                         // absent terms sort last
+            // a driver is essential while the in-query-order sum of the not-yet-driven bounds can reach theta
+            float S = 0.f;
+#pragma unroll
+            for (uint32_t t = 0; t < FAST_T; t++) if (t < n && pos[t] >= p) S = __fadd_rn(S, ub[t]);
+            if (ord_f32(S) < thr) break;
+            st_visited += dcnt;
+            for (uint32_t base = 0; base < dcnt; base += 32) {
+                const uint32_t pp = base + lane;
+                const bool active = pp < dcnt;
+                const uint32_t pd = active ? __ldg(&v.post[doff + pp]) : 0u;
+                const uint32_t d = pd & 0xFFFFu;
+                const float cd = __fmul_rn(didf, comp_of(v, pd >> 16, doff + pp));
+                // candidate bound: own contribution + bounds of the later-ranked terms, summed in query order
+                float Sc = 0.f;
+#pragma unroll
+                for (uint32_t t = 0; t < FAST_T; t++) {
+                    if (t >= n) continue;
+                    if (t == drv) Sc = __fadd_rn(Sc, cd);
+                    else if (pos[t] > p) Sc = __fadd_rn(Sc, ub[t]);
+                }
+                bool alive = active && ord_f32(Sc) >= thr;
+                float score = 0.f;
+#pragma unroll
+                for (uint32_t t = 0; t < FAST_T; t++) {      // query order
+                    if (t >= n) continue;
+                    if (t == drv) { score = __fadd_rn(score, cd); continue; }
+                    if (!alive || cnt[t] == 0) continue;
+                    uint32_t rank; st_probes++;
+                    if (probe(v, cnt[t], off[t], bmi[t], d, rank)) {
+                        if (pos[t] < p) alive = false;        // already emitted when that term was the driver
+                        else score = __fadd_rn(score, term_score(v, idf[t], off[t] + rank));
+                    }
+                }
+                insert_candidates(L, thr, alive && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
+            }
+        }
+    }
+    if (c.need_count) {
+        // exact |union| of this block: sum of counts - duplicates; enumerate all but the longest list, probe longer ones
+        uint32_t cpos[FAST_T];
+#pragma unroll
+        for (uint32_t t = 0; t < FAST_T; t++) {
+            uint32_t r = 0;
+#pragma unroll
+            for (uint32_t u = 0; u < FAST_T; u++) if (u != t && u < n && (cnt[u] > cnt[t] || (cnt[u] == cnt[t] && u < t))) r++;
+            cpos[t] = t < n ? r : 0xFFFFu;
+        }
+        for (uint32_t p = 0; p < n; p++) {
+            uint32_t dcnt = 0; uint64_t doff = 0;
+#pragma unroll
+            for (uint32_t t = 0; t < FAST_T; t++) if (cpos[t] == p) { dcnt = cnt[t]; doff = off[t]; }
+            if (dcnt == 0) break;
+            if (p == 0) { matches += dcnt; continue; }
+            st_visited += dcnt;
+            for (uint32_t base = 0; base < dcnt; base += 32) {
+                const uint32_t pp = base + lane;
+                const bool active = pp < dcnt;
+                const uint32_t d = active ? (__ldg(&v.post[doff + pp]) & 0xFFFFu) : 0u;
+                bool dup = false;
+#pragma unroll
+                for (uint32_t t = 0; t < FAST_T; t++) {
+                    if (t >= n || cpos[t] >= p || cnt[t] == 0 || !active || dup) continue;
+                    uint32_t rank; st_probes++;
+                    if (probe(v, cnt[t], off[t], bmi[t], d, rank)) dup = true;
+                }
+                matches += __popc(__ballot_sync(FULL, active && !dup));
+            }
+        }
+    }
+}
+
+// ---- generic path: up to SSB_MAX_QUERY_TERMS live terms, lane t holds term t, values broadcast by shuffles ----
+__device__ __noinline__ void process_item_generic(const LexView& v, const QueryPlan* pl, const ItemCtx& c, int lane,
+                                                  uint64_t& L, uint32_t& thr, bool& dirty, uint64_t& matches,
+                                                  uint64_t& st_visited, uint64_t& st_probes) {
+    const uint32_t n = c.n, lv = c.lv;
+    TermRegs tr; tr.cnt = 0; tr.off = 0; tr.bmi = NONE; tr.idf = 0.f; tr.ub = 0.f;
+    if ((uint32_t)lane < n) {
+        QTerm qt = pl->t[lane];
+        uint32_t lo = 0, hi = qt.n;
+        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (__ldg(&v.e_level[qt.first + m]) < lv) lo = m + 1; else hi = m; }
+        if (lo < qt.n && __ldg(&v.e_level[qt.first + lo]) == lv) {
+            uint32_t e = qt.first + lo;
+            tr.cnt = __ldg(&v.e_count[e]); tr.off = __ldg(&v.e_off[e]); tr.bmi = __ldg(&v.e_bitmap[e]);
+            tr.ub = __fmul_rn(qt.idf, __ldg(&v.e_maxcomp[e]));
+        }
+        tr.idf = qt.idf;
+    }
+    if (c.is_and) {
+        uint32_t cc = (uint32_t)lane < n ? tr.cnt : 0xFFFFFFFFu;
+        uint32_t key = cc; int drv = lane;
+        for (int s = 16; s; s >>= 1) {
+            uint32_t ok = __shfl_xor_sync(FULL, key, s); int od = __shfl_xor_sync(FULL, drv, s);
+            if (ok < key || (ok == key && od < drv)) { key = ok; drv = od; }
+        }
+        const uint32_t dcnt = __shfl_sync(FULL, tr.cnt, drv);
+        const uint64_t doff = shfl64(tr.off, drv);
+        st_visited += dcnt;
+        for (uint32_t base = 0; base < dcnt; base += 32) {
+            const uint32_t p = base + lane;
+            const bool active = p < dcnt;
+            const uint32_t d = active ? (__ldg(&v.post[doff + p]) & 0xFFFFu) : 0u;
+            bool ok = active; float score = 0.f;
+            for (uint32_t t = 0; t < n; t++) {          // query order
+                const uint32_t tc = __shfl_sync(FULL, tr.cnt, t); const uint64_t to = shfl64(tr.off, t);
+                const uint32_t tb = __shfl_sync(FULL, tr.bmi, t); const float ti = __shfl_sync(FULL, tr.idf, t);
+                uint32_t rank = p; bool found = true;
+                if ((int)t != drv) { found = ok && probe(v, tc, to, tb, d, rank); st_probes += ok ? 1 : 0; }
+                ok = ok && found;
+                if (ok && c.scoring) score = __fadd_rn(score, term_score(v, ti, to + rank));
+            }
+            matches += __popc(__ballot_sync(FULL, ok));
+            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
+        }
+        return;
+    }
+    if (c.scoring) {
+        uint32_t rk = 0;
+        for (uint32_t t = 0; t < n; t++) {
+            float ou = __shfl_sync(FULL, tr.ub, t); uint32_t oc = __shfl_sync(FULL, tr.cnt, t);
+            bool mine = (uint32_t)lane < n;
+            bool before = (oc > 0 && tr.cnt == 0) || ((oc > 0) == (tr.cnt > 0) && (ou > tr.ub || (ou == tr.ub && t < (uint32_t)lane)));
+            if (mine && before && t != (uint32_t)lane) rk++;
+        }
+        if ((uint32_t)lane >= n) rk = 0xFFFFu;
+        for (uint32_t p = 0; p < n; p++) {
+            const int drv = __ffs(__ballot_sync(FULL, rk == p)) - 1;
+            const uint32_t dcnt = __shfl_sync(FULL, tr.cnt, drv);
+            if (dcnt == 0) break;
+            float S = 0.f;
+            for (uint32_t t = 0; t < n; t++) {
+                float ou = __shfl_sync(FULL, tr.ub, t); uint32_t orr = __shfl_sync(FULL, rk, t);
+                if (orr >= p) S = __fadd_rn(S, ou);
+            }
+            if (ord_f32(S) < thr) break;
+            const uint64_t doff = shfl64(tr.off, drv);
+            const float didf = __shfl_sync(FULL, tr.idf, drv);
+            st_visited += dcnt;
+            for (uint32_t base = 0; base < dcnt; base += 32) {
+                const uint32_t pp = base + lane;
+                const bool active = pp < dcnt;
+                const uint32_t d = active ? (__ldg(&v.post[doff + pp]) & 0xFFFFu) : 0u;
+                bool dup = false; float score = 0.f;
+                for (uint32_t t = 0; t < n; t++) {      // query order
+                    const uint32_t tc = __shfl_sync(FULL, tr.cnt, t); const uint64_t to = shfl64(tr.off, t);
+                    const uint32_t tb = __shfl_sync(FULL, tr.bmi, t); const float ti = __shfl_sync(FULL, tr.idf, t);
+                    const uint32_t trk = __shfl_sync(FULL, rk, t);
+                    if ((int)t == drv) { if (active) score = __fadd_rn(score, term_score(v, didf, doff + pp)); continue; }
+                    if (tc == 0 || !active || dup) continue;
+                    uint32_t rank; st_probes++;
+                    if (probe(v, tc, to, tb, d, rank)) {
+                        if (trk < p) dup = true;
+                        else score = __fadd_rn(score, term_score(v, ti, to + rank));
+                    }
+                }
+                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
+            }
+        }
+    }
+    if (c.need_count) {
+        uint32_t crk = 0;
+        for (uint32_t t = 0; t < n; t++) {
+            uint32_t oc = __shfl_sync(FULL, tr.cnt, t);
+            if ((uint32_t)lane < n && t != (uint32_t)lane && (oc > tr.cnt || (oc == tr.cnt && t < (uint32_t)lane))) crk++;
+        }
+        if ((uint32_t)lane >= n) crk = 0xFFFFu;
+        for (uint32_t p = 0; p < n; p++) {
+            const int drv = __ffs(__ballot_sync(FULL, crk == p)) - 1;
+            const uint32_t dcnt = __shfl_sync(FULL, tr.cnt, drv);
+            if (dcnt == 0) break;
+            if (p == 0) { matches += dcnt; continue; }
+            const uint64_t doff = shfl64(tr.off, drv);
+            st_visited += dcnt;
+            for (uint32_t base = 0; base < dcnt; base += 32) {
+                const uint32_t pp = base + lane;
+                const bool active = pp < dcnt;
+                const uint32_t d = active ? (__ldg(&v.post[doff + pp]) & 0xFFFFu) : 0u;
+                bool dup = false;
+                for (uint32_t t = 0; t < n; t++) {
+                    const uint32_t tc = __shfl_sync(FULL, tr.cnt, t); const uint64_t to = shfl64(tr.off, t);
+                    const uint32_t tb = __shfl_sync(FULL, tr.bmi, t); const uint32_t trk = __shfl_sync(FULL, crk, t);
+                    if (trk >= p || tc == 0 || !active || dup) continue;
+                    uint32_t rank; st_probes++;
+                    if (probe(v, tc, to, tb, d, rank)) dup = true;
+                }
+                matches += __popc(__ballot_sync(FULL, active && !dup));
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) lex_score(LexView v, const QueryPlan* __restrict__ plans, const uint64_t* __restrict__ items,
-                                                 uint32_t nq, uint32_t query_type, uint32_t result_type, uint32_t k,
-                                                 uint32_t* ctr, uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist,
+                                                 const uint2* __restrict__ item_ent, uint32_t nq, uint32_t query_type, uint32_t result_type,
+                                                 uint32_t k, uint32_t* ctr, uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist,
                                                  LexStats* stats) {
     const int lane = threadIdx.x & 31;
     const uint32_t max_items = *(volatile uint32_t*)&ctr[1];
@@ -289,142 +576,21 @@ __global__ void __launch_bounds__(256) lex_score(LexView v, const QueryPlan* __r
         if ((uint64_t)i >= total) break;
         const uint32_t j = i / nq, q = i - j * nq;
         const QueryPlan* pl = &plans[q];
-        const uint32_t n = pl->n_live;
         if (j >= pl->n_items) continue;
         const uint64_t item = items[(size_t)q * v.n_levels + j];
-        const uint32_t lv = 0xFFFFFFFFu - (uint32_t)item;
-        const uint32_t bound_ord = (uint32_t)(item >> 32);
+        ItemCtx c;
+        c.q = q; c.n = pl->n_live; c.k = k; c.lv = 0xFFFFFFFFu - (uint32_t)item; c.bound_ord = (uint32_t)(item >> 32);
         uint32_t thr = (uint32_t)(__ldcg(&theta[q]) >> 32);
-        const bool scoring = want_topk && bound_ord >= thr;
-        if (!scoring && !need_count) { st_skipped++; continue; }
+        c.scoring = want_topk && c.bound_ord >= thr;
+        c.need_count = need_count; c.is_and = query_type == SSB_QUERY_INTERSECTION;
+        if (!c.scoring && !need_count) { st_skipped++; continue; }
         st_done++;
-
-        // ---- lane t: locate term t's entry for this level ----
-        TermRegs tr; tr.cnt = 0; tr.off = 0; tr.bmi = NONE; tr.idf = 0.f; tr.ub = 0.f;
-        if ((uint32_t)lane < n) {
-            QTerm qt = pl->t[lane];
-            uint32_t lo = 0, hi = qt.n;
-            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (__ldg(&v.e_level[qt.first + m]) < lv) lo = m + 1; else hi = m; }
-            if (lo < qt.n && __ldg(&v.e_level[qt.first + lo]) == lv) {
-                uint32_t e = qt.first + lo;
-                tr.cnt = __ldg(&v.e_count[e]); tr.off = __ldg(&v.e_off[e]); tr.bmi = __ldg(&v.e_bitmap[e]);
-                tr.ub = __fmul_rn(qt.idf, __ldg(&v.e_maxcomp[e]));
-            }
-            tr.idf = qt.idf;
-        }
-        const uint32_t docbase = __ldg(&v.level_ids[lv]) << 16;
+        c.docbase = __ldg(&v.level_ids[c.lv]) << 16;
         uint64_t L = 0; bool dirty = false; uint64_t matches = 0;
+        if (c.n <= FAST_T) process_item_fast(v, pl, c, item_ent[(size_t)q * v.n_levels + j], lane, L, thr, dirty, matches, st_visited, st_probes);
+        else process_item_generic(v, pl, c, lane, L, thr, dirty, matches, st_visited, st_probes);
 
-        if (query_type == SSB_QUERY_INTERSECTION) {
-            // ---------------- AND: drive with the shortest list (intersection.rs:258-273) ----------------
-            uint32_t c = (uint32_t)lane < n ? tr.cnt : 0xFFFFFFFFu;
-            uint32_t key = c; int drv = lane;
-            for (int s = 16; s; s >>= 1) {
-                uint32_t ok = __shfl_xor_sync(FULL, key, s); int od = __shfl_xor_sync(FULL, drv, s);
-                if (ok < key || (ok == key && od < drv)) { key = ok; drv = od; }
-            }
-            const uint32_t dcnt = __shfl_sync(FULL, tr.cnt, drv);
-            const uint64_t doff = shfl64(tr.off, drv);
-            st_visited += dcnt;
-            for (uint32_t base = 0; base < dcnt; base += 32) {
-                const uint32_t p = base + lane;
-                const bool active = p < dcnt;
-                const uint32_t d = active ? (uint32_t)__ldg(&v.ids[doff + p]) : 0u;
-                bool ok = active; float score = 0.f;
-                for (uint32_t t = 0; t < n; t++) {          // query order
-                    const uint32_t tc = __shfl_sync(FULL, tr.cnt, t); const uint64_t to = shfl64(tr.off, t);
-                    const uint32_t tb = __shfl_sync(FULL, tr.bmi, t); const float ti = __shfl_sync(FULL, tr.idf, t);
-                    uint32_t rank = p; bool found = true;
-                    if ((int)t != drv) { found = ok && probe(v, tc, to, tb, d, rank); st_probes += ok ? 1 : 0; }
-                    ok = ok && found;
-                    if (ok && scoring) score = __fadd_rn(score, term_score(v, ti, to + rank));
-                }
-                matches += __popc(__ballot_sync(FULL, ok));
-                if (scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, docbase | d, k, lane, dirty);
-            }
-        } else {
-            // ---------------- OR ----------------
-            if (scoring) {
-                // MAXSCORE: terms by block bound desc; a driver is essential while the in-query-order sum of the
-                // not-yet-driven terms' bounds can still reach θ (union.rs:1219-1301, 1371-1412 in spirit)
-                uint32_t rk = 0;
-                for (uint32_t t = 0; t < n; t++) {
-                    float ou = __shfl_sync(FULL, tr.ub, t); uint32_t oc = __shfl_sync(FULL, tr.cnt, t);
-                    bool mine = (uint32_t)lane < n;
-                    // present terms first, then by ub desc, then by index
-                    bool before = (oc > 0 && tr.cnt == 0) || ((oc > 0) == (tr.cnt > 0) && (ou > tr.ub || (ou == tr.ub && t < (uint32_t)lane)));
-                    if (mine && before && t != (uint32_t)lane) rk++;
-                }
-                if ((uint32_t)lane >= n) rk = 0xFFFFu;
-                for (uint32_t p = 0; p < n; p++) {
-                    const int drv = __ffs(__ballot_sync(FULL, rk == p)) - 1;
-                    const uint32_t dcnt = __shfl_sync(FULL, tr.cnt, drv);
-                    if (dcnt == 0) break;   // absent terms sort last
-                    float S = 0.f;
-                    for (uint32_t t = 0; t < n; t++) {
-                        float ou = __shfl_sync(FULL, tr.ub, t); uint32_t orr = __shfl_sync(FULL, rk, t);
-                        if (orr >= p) S = __fadd_rn(S, ou);
-                    }
-                    if (ord_f32(S) < thr) break;
-                    const uint64_t doff = shfl64(tr.off, drv);
-                    const float didf = __shfl_sync(FULL, tr.idf, drv);
-                    st_visited += dcnt;
-                    for (uint32_t base = 0; base < dcnt; base += 32) {
-                        const uint32_t pp = base + lane;
-                        const bool active = pp < dcnt;
-                        const uint32_t d = active ? (uint32_t)__ldg(&v.ids[doff + pp]) : 0u;
-                        bool dup = false; float score = 0.f;
-                        for (uint32_t t = 0; t < n; t++) {      // query order
-                            const uint32_t tc = __shfl_sync(FULL, tr.cnt, t); const uint64_t to = shfl64(tr.off, t);
-                            const uint32_t tb = __shfl_sync(FULL, tr.bmi, t); const float ti = __shfl_sync(FULL, tr.idf, t);
-                            const uint32_t trk = __shfl_sync(FULL, rk, t);
-                            if ((int)t == drv) { if (active) score = __fadd_rn(score, term_score(v, didf, doff + pp)); continue; }
-                            if (tc == 0 || !active || dup) continue;
-                            uint32_t rank; st_probes++;
-                            if (probe(v, tc, to, tb, d, rank)) {
-                                if (trk < p) dup = true;     // already emitted when that term was the driver
-                                else score = __fadd_rn(score, term_score(v, ti, to + rank));
-                            }
-                        }
-                        insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr, score, docbase | d, k, lane, dirty);
-                    }
-                }
-            }
-            if (need_count) {
-                // exact |union| of this block: Σ counts − duplicates, enumerating all but the longest list and
-                // probing only longer ones (union.rs:1236-1244 for 2 terms; union_count :807-1164 in general)
-                uint32_t crk = 0;
-                for (uint32_t t = 0; t < n; t++) {
-                    uint32_t oc = __shfl_sync(FULL, tr.cnt, t);
-                    if ((uint32_t)lane < n && t != (uint32_t)lane && (oc > tr.cnt || (oc == tr.cnt && t < (uint32_t)lane))) crk++;
-                }
-                if ((uint32_t)lane >= n) crk = 0xFFFFu;
-                for (uint32_t p = 0; p < n; p++) {
-                    const int drv = __ffs(__ballot_sync(FULL, crk == p)) - 1;
-                    const uint32_t dcnt = __shfl_sync(FULL, tr.cnt, drv);
-                    if (dcnt == 0) break;
-                    if (p == 0) { matches += dcnt; continue; }
-                    const uint64_t doff = shfl64(tr.off, drv);
-                    st_visited += dcnt;
-                    for (uint32_t base = 0; base < dcnt; base += 32) {
-                        const uint32_t pp = base + lane;
-                        const bool active = pp < dcnt;
-                        const uint32_t d = active ? (uint32_t)__ldg(&v.ids[doff + pp]) : 0u;
-                        bool dup = false;
-                        for (uint32_t t = 0; t < n; t++) {
-                            const uint32_t tc = __shfl_sync(FULL, tr.cnt, t); const uint64_t to = shfl64(tr.off, t);
-                            const uint32_t tb = __shfl_sync(FULL, tr.bmi, t); const uint32_t trk = __shfl_sync(FULL, crk, t);
-                            if (trk >= p || tc == 0 || !active || dup) continue;
-                            uint32_t rank; st_probes++;
-                            if (probe(v, tc, to, tb, d, rank)) dup = true;
-                        }
-                        matches += __popc(__ballot_sync(FULL, active && !dup));
-                    }
-                }
-            }
-        }
-
-        // ---- publish: merge the warp list into the query's global list, raise θ ----
+        // ---- publish: merge the warp list into the query's global list, raise theta ----
         if (dirty) {
             if (lane == 0) { while (atomicCAS(&lock[q], 0, 1) != 0) __nanosleep(40); }
             __syncwarp();
@@ -478,9 +644,9 @@ void LexIndex::free_committed() {
 }
 
 void LexIndex::free_workspace() {
-    cudaFree(d_plans_); cudaFree(d_items_); cudaFree(d_theta_); cudaFree(d_lock_); cudaFree(d_count_); cudaFree(d_ctr_);
+    cudaFree(d_plans_); cudaFree(d_items_); cudaFree(d_item_ent_); cudaFree(d_theta_); cudaFree(d_lock_); cudaFree(d_count_); cudaFree(d_ctr_);
     cudaFree(d_qoff_); cudaFree(d_qkeys_); cudaFree(d_stats_);
-    d_plans_ = nullptr; d_items_ = nullptr; d_theta_ = nullptr; d_lock_ = nullptr; d_count_ = nullptr; d_ctr_ = nullptr;
+    d_plans_ = nullptr; d_items_ = nullptr; d_item_ent_ = nullptr; d_theta_ = nullptr; d_lock_ = nullptr; d_count_ = nullptr; d_ctr_ = nullptr;
     d_qoff_ = nullptr; d_qkeys_ = nullptr; d_stats_ = nullptr; ws_nq_ = ws_terms_ = ws_levels_ = 0;
 }
 
@@ -513,12 +679,12 @@ int32_t LexIndex::add_level(const ssb_level_desc* d) {
     SSB_CUDA_TRY(to_device(l.d_term_keys, d->term_keys, (size_t)d->n_terms * 8, st_));
     if (d->n_terms) SSB_CUDA_TRY(to_device(l.d_posting_offsets, d->posting_offsets, ((size_t)d->n_terms + 1) * 4, st_));
     else SSB_CUDA_TRY(cudaMemsetAsync(l.d_posting_offsets, 0, 4, st_));
-    SSB_TRY(ids_.reserve(n_post_ + np + 8, n_post_, st_));
-    SSB_TRY(pay_.reserve(n_post_ + np + 8, n_post_, st_));
-    SSB_CUDA_TRY(to_device(ids_.p + n_post_, d->doc_ids, (size_t)np * 2, st_));
-    // payload = tf8 | len8<<8 (needs tfs + the level's length bytes on the device)
-    uint16_t* d_tfs = nullptr; uint8_t* d_len = nullptr; bool own_tfs = false, own_len = false;
+    SSB_TRY(post_.reserve(n_post_ + np + 8, n_post_, st_));
+    // posting word = id16 | tf8<<16 | len8<<24 (needs ids, tfs and the level's length bytes on the device)
+    uint16_t* d_ids = nullptr; uint16_t* d_tfs = nullptr; uint8_t* d_len = nullptr; bool own_ids = false, own_tfs = false, own_len = false;
     if (np) {
+        if (is_device_ptr(d->doc_ids)) d_ids = const_cast<uint16_t*>(d->doc_ids);
+        else { SSB_CUDA_TRY(cudaMalloc(&d_ids, (size_t)np * 2)); own_ids = true; SSB_CUDA_TRY(to_device(d_ids, d->doc_ids, (size_t)np * 2, st_)); }
         if (is_device_ptr(d->tfs)) d_tfs = const_cast<uint16_t*>(d->tfs);
         else { SSB_CUDA_TRY(cudaMalloc(&d_tfs, (size_t)np * 2)); own_tfs = true; SSB_CUDA_TRY(to_device(d_tfs, d->tfs, (size_t)np * 2, st_)); }
         if (is_device_ptr(d->doc_len_bytes)) d_len = const_cast<uint8_t*>(d->doc_len_bytes);
@@ -528,11 +694,12 @@ int32_t LexIndex::add_level(const ssb_level_desc* d) {
             SSB_CUDA_TRY(cudaMalloc(&d_exc_count_, 4)); SSB_CUDA_TRY(cudaMemsetAsync(d_exc_count_, 0, 4, st_));
             SSB_TRY(exc_pos_.reserve(exc_cap, 0, st_)); SSB_TRY(exc_tf_.reserve(exc_cap, 0, st_));
         }
-        build_payload<<<(np + 255) / 256, 256, 0, st_>>>(ids_.p + n_post_, d_tfs, d_len, pay_.p + n_post_, np, n_post_,
+        build_payload<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, d_len, post_.p + n_post_, np, n_post_,
                                                          exc_pos_.p, exc_tf_.p, d_exc_count_, exc_cap);
         SSB_CUDA_TRY(cudaGetLastError());
     }
     SSB_CUDA_TRY(cudaStreamSynchronize(st_));
+    if (own_ids) cudaFree(d_ids);
     if (own_tfs) cudaFree(d_tfs);
     if (own_len) cudaFree(d_len);
     n_post_ += np;
@@ -670,7 +837,7 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
             uint32_t* d_dense = nullptr;
             SSB_CUDA_TRY(cudaMalloc(&d_dense, (size_t)n_bitmaps_ * 4));
             compact_dense<<<(total + 255) / 256, 256, 0, st_>>>(d_e_bitmap_, total, d_dense);
-            build_bitmaps<<<n_bitmaps_, 256, 0, st_>>>(d_e_bitmap_, d_e_off_, d_e_count_, total, ids_.p, d_bm_words_, d_bm_rank_, d_dense);
+            build_bitmaps<<<n_bitmaps_, 256, 0, st_>>>(d_e_bitmap_, d_e_off_, d_e_count_, total, post_.p, d_bm_words_, d_bm_rank_, d_dense);
             SSB_CUDA_TRY(cudaGetLastError());
             SSB_CUDA_TRY(cudaStreamSynchronize(st_));
             cudaFree(d_dense);
@@ -682,7 +849,7 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     committed_ = true;   // view() is usable from here
     if (total) {
         LexView v{};
-        v.e_off = d_e_off_; v.e_count = d_e_count_; v.pay = pay_.p; v.cache = d_cache_; v.exc_pos = exc_pos_.p; v.exc_tf = exc_tf_.p;
+        v.e_off = d_e_off_; v.e_count = d_e_count_; v.post = post_.p; v.cache = d_cache_; v.exc_pos = exc_pos_.p; v.exc_tf = exc_tf_.p;
         v.n_exc = n_exc_; v.k1p = 1.2f + 1.0f;
         entry_maxcomp<<<(total + 7) / 8, 256, 0, st_>>>(v, total, d_e_maxcomp_);
         SSB_CUDA_TRY(cudaGetLastError());
@@ -723,6 +890,7 @@ int32_t LexIndex::ensure_workspace(uint32_t nq, uint32_t total_terms) {
     uint32_t ct = total_terms > cq * 4 ? total_terms : cq * 4;
     SSB_CUDA_TRY(cudaMalloc(&d_plans_, (size_t)cq * sizeof(QueryPlan)));
     SSB_CUDA_TRY(cudaMalloc(&d_items_, (size_t)cq * (nlv ? nlv : 1) * 8));
+    SSB_CUDA_TRY(cudaMalloc(&d_item_ent_, (size_t)cq * (nlv ? nlv : 1) * sizeof(uint2)));
     SSB_CUDA_TRY(cudaMalloc(&d_theta_, (size_t)cq * 8)); SSB_CUDA_TRY(cudaMalloc(&d_lock_, (size_t)cq * 4));
     SSB_CUDA_TRY(cudaMalloc(&d_count_, (size_t)cq * 8)); SSB_CUDA_TRY(cudaMalloc(&d_ctr_, 16));
     SSB_CUDA_TRY(cudaMalloc(&d_qoff_, ((size_t)cq + 1) * 4)); SSB_CUDA_TRY(cudaMalloc(&d_qkeys_, (size_t)ct * 8));
@@ -755,22 +923,22 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
     LexView v{};
     v.dict_keys = d_dict_keys_; v.n_terms = n_terms_; v.term_first = d_term_first_; v.term_idf = d_term_idf_; v.term_df = d_term_df_;
     v.e_level = d_e_level_; v.e_off = d_e_off_; v.e_count = d_e_count_; v.e_maxcomp = d_e_maxcomp_; v.e_bitmap = d_e_bitmap_;
-    v.ids = ids_.p; v.pay = pay_.p; v.bm_words = d_bm_words_; v.bm_rank = d_bm_rank_; v.level_ids = d_level_ids_;
+    v.post = post_.p; v.bm_words = d_bm_words_; v.bm_rank = d_bm_rank_; v.level_ids = d_level_ids_;
     v.n_levels = (uint32_t)levels_.size(); v.cache = d_cache_; v.exc_pos = exc_pos_.p; v.exc_tf = exc_tf_.p; v.n_exc = n_exc_;
     v.k1p = 1.2f + 1.0f;
 
     uint32_t n_pow2 = 1; while (n_pow2 < v.n_levels) n_pow2 <<= 1;
     if (n_pow2 < 2) n_pow2 = 2;
-    size_t plan_smem = (size_t)v.n_levels * 8 + 8 + (size_t)n_pow2 * 8;
+    size_t plan_smem = (size_t)v.n_levels * (8 + 2 * FAST_T) + 16 + (size_t)n_pow2 * 8;
     // glist lives in keys_out_dev's shape: use a private list buffer = d_items_-adjacent? keep separate: reuse keys_out_dev
     // directly as the global list (32 u64 per query), then mask entries >= k in copy_out.
     uint64_t* glist = keys_out_dev;
     if (plan_smem > 48 * 1024) SSB_CUDA_TRY(cudaFuncSetAttribute(lex_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
-    lex_plan<<<nq, 128, plan_smem, st_>>>(v, d_qoff_, d_qkeys_, q->query_type, d_plans_, d_items_, d_ctr_, d_theta_, d_lock_, d_count_, glist, n_pow2);
+    lex_plan<<<nq, 128, plan_smem, st_>>>(v, d_qoff_, d_qkeys_, q->query_type, d_plans_, d_items_, (uint2*)d_item_ent_, d_ctr_, d_theta_, d_lock_, d_count_, glist, n_pow2);
     SSB_CUDA_TRY(cudaGetLastError());
     int grid = n_sms_ * 8;
     if (ev0_) cudaEventRecord(ev0_, st_);
-    lex_score<<<grid, 256, 0, st_>>>(v, d_plans_, d_items_, nq, q->query_type, result_type, k ? k : 1, d_ctr_, d_theta_, d_lock_, d_count_, glist, d_stats_);
+    lex_score<<<grid, 256, 0, st_>>>(v, d_plans_, d_items_, (const uint2*)d_item_ent_, nq, q->query_type, result_type, k ? k : 1, d_ctr_, d_theta_, d_lock_, d_count_, glist, d_stats_);
     if (ev1_) cudaEventRecord(ev1_, st_);
     SSB_CUDA_TRY(cudaGetLastError());
     copy_out<<<(nq * LIST + 255) / 256, 256, 0, st_>>>(glist, d_count_, nq, result_type == SSB_RESULT_COUNT ? 0 : k, keys_out_dev, count_dev);

@@ -57,8 +57,7 @@ struct LexView {
     const uint32_t* e_count;
     const float* e_maxcomp;       // block-max basis: max tf*(K+1)/(tf+cache[len]) over the list
     const uint32_t* e_bitmap;     // index into bm_* or 0xFFFFFFFF
-    const uint16_t* ids;          // arena: local doc ids
-    const uint16_t* pay;          // arena: tf8 | len8<<8
+    const uint32_t* post;         // arena: id16 | tf8<<16 | len8<<24, one word per posting
     const uint64_t* bm_words;     // [n_bitmaps][1024]
     const uint16_t* bm_rank;      // [n_bitmaps][1024] postings before word w
     const uint32_t* level_ids;    // [n_levels]
@@ -99,7 +98,7 @@ private:
     uint32_t max_batch_;
     bool committed_ = false;
     std::vector<LexLevel> levels_;
-    DevBuf<uint16_t> ids_, pay_;
+    DevBuf<uint32_t> post_;
     uint64_t n_post_ = 0;
     DevBuf<uint64_t> exc_pos_; DevBuf<uint32_t> exc_tf_; uint32_t* d_exc_count_ = nullptr; uint32_t n_exc_ = 0;
     // committed structures
@@ -113,7 +112,7 @@ private:
     void free_committed();
     // workspace
     uint32_t ws_nq_ = 0, ws_terms_ = 0, ws_levels_ = 0;
-    QueryPlan* d_plans_ = nullptr; uint64_t* d_items_ = nullptr; uint64_t* d_theta_ = nullptr; int* d_lock_ = nullptr;
+    QueryPlan* d_plans_ = nullptr; uint64_t* d_items_ = nullptr; void* d_item_ent_ = nullptr; uint64_t* d_theta_ = nullptr; int* d_lock_ = nullptr;
     uint64_t* d_count_ = nullptr; uint32_t* d_ctr_ = nullptr; /* [0]=work counter [1]=max_items */
     uint32_t* d_qoff_ = nullptr; uint64_t* d_qkeys_ = nullptr; LexStats* d_stats_ = nullptr;
     void free_workspace();

@@ -34,7 +34,7 @@ template <int NQ> struct Cfg {
     static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
     static constexpr int LIST_BYTES = NQ * LIST * 8;
     static constexpr int CAND_BYTES = CHUNK * TM * 8;
-    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + LIST_BYTES + CAND_BYTES + NQ * 4 + 256;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + LIST_BYTES + CAND_BYTES + NQ * 4 + 256;
     static constexpr int TMEM_COLS = 2 * NQ;                               // power of two for NQ in {64,128,256}
 };
 
@@ -61,8 +61,9 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x][NQ][32]*/) {
     using C = Cfg<NQ>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for SWIZZLE_128B)
+    // and pointers derived from it stay in the shared address space (LDS/STS instead of generic LD/ST)
+    extern __shared__ __align__(1024) uint8_t base[];
     uint8_t* stage0 = base;
     uint64_t* lists = (uint64_t*)(base + STAGES * C::STAGE_BYTES);            // [NQ][32]
     uint64_t* cand = (uint64_t*)((uint8_t*)lists + C::LIST_BYTES);            // [CHUNK][TM]
