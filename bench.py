@@ -50,7 +50,7 @@ def parse():
     p.add_argument("--bm25-docs", type=int, default=C3_DOCS)
     p.add_argument("--bm25-batch", type=int, default=4096, help="lexical queries per step")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
-    p.add_argument("--vector-kernel", default="ffma", choices=["ffma", "tc"], help="FP32 FFMA2 scan or tcgen05 3xTF32 scan")
+    p.add_argument("--vector-kernel", default="ffma", choices=["ffma", "tc", "tc64"], help="FP32 FFMA2 scan or tcgen05 3xTF32 scan (128 / 64 queries per pass)")
     return p.parse_args()
 
 
@@ -71,10 +71,16 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def has_samples(self):
+        try:
+            return self.p is None or os.path.getsize(self.f.name) > 0
+        except OSError:
+            return True
 
     def stop(self):
         if self.p is None:
@@ -115,11 +121,17 @@ def dist_setup(n):
     return rank, world
 
 
-def timed_steps(fn, steps, warmup, world):
-    """W untimed + exactly K timed steps, barrier + synchronize on both sides, device time, max over ranks."""
+def timed_steps(fn, steps, warmup, world, sampler=None):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, device time, max over ranks.
+    With a clock sampler, extra untimed warm-up steps keep the GPU under load until nvidia-smi delivers its first sample."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    if sampler is not None:
+        t_end = time.perf_counter() + 3.0
+        while not sampler.has_samples() and time.perf_counter() < t_end:
+            fn()
+            torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -158,8 +170,8 @@ def bench_vector(a, rank, world, out):
     from seekstorm_b200.parallel import ShardedSearcher
     dev = torch.device("cuda", torch.cuda.current_device())
     ix = Index(dev.index, vector_dims=a.dims, vector_similarity=VectorSimilarity.Cosine, max_batch=max(a.batch, 16),
-               vector_kernel=2 if a.vector_kernel == "tc" else 1)
-    qt = 128 if a.vector_kernel == "tc" else 16
+               vector_kernel={"ffma": 1, "tc": 2, "tc64": 3}[a.vector_kernel])
+    qt = {"ffma": 16, "tc": 128, "tc64": 64}[a.vector_kernel]
     ix.set_stream(torch.cuda.current_stream().cuda_stream)
     n_levels, mine = vector_levels(a.rows, rank, world)
     local_rows = 0
@@ -186,7 +198,7 @@ def bench_vector(a, rank, world, out):
     step_dev(); torch.cuda.synchronize()
     kern_ns = []
     sampler = ClockSampler(dev.index) if rank == 0 else None
-    ms = timed_steps(step_dev, a.steps, a.warmup, world)
+    ms = timed_steps(step_dev, a.steps, a.warmup, world, sampler)
     clocks = sampler.stop() if sampler else None
     for _ in range(5):
         step_dev(); torch.cuda.synchronize()
@@ -197,9 +209,10 @@ def bench_vector(a, rank, world, out):
 
     # ---- e2e: the reference-facing call with HOST buffers (H2D queries, D2H hits inside the timed region) ----
     q_np = q_host.numpy()
+    hits_buf, nh_buf = ix.hits_buffer(a.batch * TOPK), np.zeros(a.batch, dtype=np.uint32)
     if world == 1:
         def step_e2e():
-            ix.search_vector_batch(q_np, TOPK)
+            ix.search_vector_raw(q_np, TOPK, hits_buf, nh_buf)     # ssb_search_vector: host queries in, host hits out
     else:
         import torch.distributed as dist
         def step_e2e():
@@ -218,13 +231,13 @@ def bench_vector(a, rank, world, out):
         "ms_per_step": ms / a.steps, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C2 brute-force cosine kNN: {a.rows} x {a.dims} f32, top-{TOPK}, batch {a.batch} queries/step "
                                f"({passes} corpus passes of {qt} queries)", "l2": "inputs larger than L2 (corpus %.2f GB per GPU)" % (local_rows * a.dims * 4 / 1e9),
-                   "parallelism": f"levels sharded over {world} GPU(s)", "kernel": "scan_tc (TMA + tcgen05 3xTF32 + TMEM epilogue top-k)" if a.vector_kernel == "tc" else "scan_ffma (TMA + packed FP32 FFMA2 + warp top-k)"},
+                   "parallelism": f"levels sharded over {world} GPU(s)", "kernel": "scan_tc (TMA + tcgen05 3xTF32 + TMEM epilogue top-k)" if a.vector_kernel != "ffma" else "scan_ffma (TMA + packed FP32 FFMA2 + warp top-k)"},
         "e2e": {"value": qps_e2e, "unit": "queries/s", "ms_per_step": ms_e2e / a.steps,
                 "h2d_bytes_per_step": a.batch * a.dims * 4, "d2h_bytes_per_step": a.batch * 32 * 8},
         "gpu_launches": launches_per_step * a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_kind": f"of {peak_kind}",
-                     "kernel": "scan_tc" if a.vector_kernel == "tc" else "scan_ffma", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
+                     "kernel": "scan_tc" if a.vector_kernel != "ffma" else "scan_ffma", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
         "clocks": clocks,
     })
     return ix, q_host
@@ -311,9 +324,11 @@ def bench_bm25(a, rank, world):
         step_dev(); torch.cuda.synchronize()
         kern_ns.append(ix.last_stats()["dominant_kernel_ns"])
 
+    hits_buf, nh_buf, cnt_buf = ix.hits_buffer(len(qk) * TOPK), np.zeros(len(qk), dtype=np.uint32), np.zeros(len(qk), dtype=np.uint64)
+
     def step_e2e():
         if world == 1:
-            ix.search_lexical_batch(qk, QueryType.Union, TOPK, ResultType.Topk)
+            ix.search_lexical_raw(b, TOPK, ResultType.Topk, hits_buf, nh_buf, cnt_buf)   # ssb_search_lexical, host buffers
         else:
             sh.search_lexical(b, len(qk), TOPK, ResultType.Topk, dev)
     ms_e2e = timed_steps(step_e2e, steps, a.warmup, world)

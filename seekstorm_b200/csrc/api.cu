@@ -80,8 +80,9 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     if (ix->dims == 0) { set_error("no vector index configured (vector_dims = 0)"); return SSB_E_STATE; }
     if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
     if (nq == 0) return SSB_OK;
-    const bool use_tc = ix->cfg.vector_kernel == SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN;
-    const uint32_t qt = use_tc ? vec::VEC_TC_NQ : vec::VEC_QT;
+    const bool use_tc = (ix->cfg.vector_kernel == SSB_VEC_KERNEL_TCGEN05 || ix->cfg.vector_kernel == SSB_VEC_KERNEL_TCGEN05_N64) &&
+                        ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN;
+    const uint32_t qt = !use_tc ? vec::VEC_QT : (ix->cfg.vector_kernel == SSB_VEC_KERNEL_TCGEN05_N64 ? 64u : 128u);
     const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
     SSB_TRY(ix->qpad.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
     const float* qsrc = queries;
@@ -107,7 +108,7 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
         SSB_TRY(ix->qhi.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         SSB_TRY(ix->qlo.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         a.q_hi = ix->qhi.p; a.q_lo = ix->qlo.p;
-        SSB_TRY(vec::launch_scan_tc(a, ix->st));
+        SSB_TRY(vec::launch_scan_tc(a, qt, ix->st));
         ix->stats.kernel_launches += 1;
     } else {
         SSB_TRY(vec::launch_scan_ffma(a, ix->st));

@@ -7,7 +7,6 @@ namespace ssb {
 namespace vec {
 
 constexpr int VEC_QT = 16;      // queries per corpus pass of the FFMA kernel
-constexpr int VEC_TC_NQ = 128;  // queries per corpus pass of the tcgen05 kernel (UMMA N)
 
 struct ScanArgs {
     const float* rows;            // [n_rows][dpad]
@@ -28,7 +27,7 @@ struct ScanArgs {
 
 int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);
-int32_t launch_scan_tc(const ScanArgs& a, cudaStream_t st);
+int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128*/, cudaStream_t st);
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad);
 // lists laid out [group][n_lists][qt][32] -> out [nq][32]
 void merge_lists_generic(const uint64_t* in, uint32_t n_lists, uint32_t qt, uint32_t nq, uint64_t* out, cudaStream_t st);

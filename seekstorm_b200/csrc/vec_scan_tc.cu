@@ -23,7 +23,6 @@ namespace vec {
 namespace tc {
 constexpr int KC = 32;                 // floats per k-chunk = one 128-byte swizzle row
 constexpr int TM = 128;                // corpus rows per tile = UMMA M
-constexpr int STAGES = 2;
 constexpr int A_BYTES = TM * KC * 4;   // 16 KB
 constexpr int THREADS = 384;
 constexpr int CHUNK = 8;               // query columns per epilogue step
@@ -31,10 +30,10 @@ constexpr int CHUNK = 8;               // query columns per epilogue step
 template <int NQ> struct Cfg {
     static constexpr int B_BYTES = NQ * KC * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // A, A_lo, B_hi, B_lo
+    static constexpr int STAGES = NQ <= 64 ? 4 : 3;                        // 4 x 48 KB or 3 x 64 KB
     static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
-    static constexpr int LIST_BYTES = NQ * LIST * 8;
     static constexpr int CAND_BYTES = CHUNK * TM * 8;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + LIST_BYTES + CAND_BYTES + NQ * 4 + 256;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + CAND_BYTES + NQ * 4 + 256;
     static constexpr int TMEM_COLS = 2 * NQ;                               // power of two for NQ in {64,128,256}
 };
 
@@ -61,12 +60,15 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x][NQ][32]*/) {
     using C = Cfg<NQ>;
+    constexpr int STAGES = C::STAGES;
     // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for SWIZZLE_128B)
     // and pointers derived from it stay in the shared address space (LDS/STS instead of generic LD/ST)
     extern __shared__ __align__(1024) uint8_t base[];
     uint8_t* stage0 = base;
-    uint64_t* lists = (uint64_t*)(base + STAGES * C::STAGE_BYTES);            // [NQ][32]
-    uint64_t* cand = (uint64_t*)((uint8_t*)lists + C::LIST_BYTES);            // [CHUNK][TM]
+    // per-query sorted lists live directly in this CTA's slice of the output scratch (global, L2-resident): they are
+    // touched only on the rare candidate insert, and each query is always owned by the same warp
+    uint64_t* lists = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NQ * LIST;   // [NQ][32]
+    uint64_t* cand = (uint64_t*)(base + STAGES * C::STAGE_BYTES);             // [CHUNK][TM]
     float* thr_s = (float*)((uint8_t*)cand + C::CAND_BYTES);                  // [NQ]
     uint64_t* bars = (uint64_t*)(thr_s + NQ);
     uint64_t* full = bars;                 // [STAGES]
@@ -224,9 +226,6 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
         }
-        // publish this CTA's lists
-        uint64_t* out = scratch + ((size_t)group * gridDim.x + blockIdx.x) * NQ * LIST;
-        for (int i = et; i < NQ * LIST; i += 128) out[i] = lists[i];
     }
 
     tc_fence_before();
@@ -277,14 +276,14 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     return SSB_OK;
 }
 
-int32_t launch_scan_tc(const ScanArgs& a, cudaStream_t st) {
+int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, cudaStream_t st) {
     if (a.n_rows == 0 || a.nq_pad == 0) return SSB_OK;
     if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }
-    if (a.nq_pad % VEC_TC_NQ != 0) { set_error("tcgen05 scan: query count must be padded to %d", VEC_TC_NQ); return SSB_E_INVALID; }
-    return launch_tc_n<VEC_TC_NQ>(a, st);
+    if ((nq_tile != 64 && nq_tile != 128) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 scan: query count must be padded to the 64/128 query tile"); return SSB_E_INVALID; }
+    return nq_tile == 64 ? launch_tc_n<64>(a, st) : launch_tc_n<128>(a, st);
 }
 
-size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)(nq_pad / VEC_TC_NQ) * (size_t)n_sms * VEC_TC_NQ * LIST * 8; }
+size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)nq_pad * (size_t)n_sms * LIST * 8; }
 
 }  // namespace vec
 }  // namespace ssb

@@ -248,6 +248,24 @@ class Index:
             out.append([(int(d), float(s)) for d, s in zip(h["doc_id"], h["score"])])
         return out
 
+    # ---- raw C-ABI calls with caller-owned numpy buffers (no per-hit Python objects; what a Rust shim would do) ----
+    def make_lex_batch(self, queries_keys, query_type: QueryType):
+        """Build the host-side ssb_lex_batch once; returns (struct, keepalive)."""
+        return self._lex_batch(queries_keys, query_type)
+
+    def search_lexical_raw(self, batch_struct, k: int, result_type: ResultType, hits, n_hits, counts):
+        """ssb_search_lexical with preallocated outputs: hits = structured array [nq*k] (doc_id u8, score f4, pad u4)."""
+        check(lib().ssb_search_lexical(self._h, C.byref(batch_struct), k, int(result_type), hits.ctypes.data,
+                                       n_hits.ctypes.data, counts.ctypes.data if counts is not None else None))
+
+    def search_vector_raw(self, queries, k: int, hits, n_hits):
+        """ssb_search_vector with preallocated outputs; queries: host or device [nq, dims] f32."""
+        check(lib().ssb_search_vector(self._h, _addr(queries), int(queries.shape[0]), k, hits.ctypes.data, n_hits.ctypes.data))
+
+    @staticmethod
+    def hits_buffer(n):
+        return _hits_array(n)
+
     def search_hybrid_batch(self, queries_keys, query_type: QueryType, queries, k: int):
         nq = len(queries_keys)
         b, keep = self._lex_batch(queries_keys, query_type)
