@@ -89,28 +89,15 @@ __device__ __forceinline__ float comp_of(const LexView& v, uint32_t payload, uin
 }
 
 // one warp per entry: block-max basis (get_max_score, index.rs:2938-3049 — here exact over the list)
-// also writes the max of every 32-posting chunk (posting-level block-max: lets the scoring kernel skip chunks of an
-// essential list whose best posting cannot reach theta — the role BMW-style blocks play on a CPU)
-__global__ void entry_maxcomp(LexView v, uint32_t n_entries, float* __restrict__ out, const uint32_t* __restrict__ cm_off,
-                              float* __restrict__ chunkmax) {
+__global__ void entry_maxcomp(LexView v, uint32_t n_entries, float* __restrict__ out) {
     uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= n_entries) return;
     int lane = threadIdx.x & 31;
     uint64_t off = v.e_off[e]; uint32_t cnt = v.e_count[e];
-    const uint32_t co = cm_off[e];
     float m = 0.f;
-    for (uint32_t base = 0; base < cnt; base += 32) {
-        uint32_t i = base + lane;
-        float c = i < cnt ? comp_of(v, v.post[off + i] >> 16, off + i) : 0.f;
-        for (int s = 16; s; s >>= 1) c = fmaxf(c, __shfl_xor_sync(FULL, c, s));
-        if (lane == 0) chunkmax[co + (base >> 5)] = c;
-        m = fmaxf(m, c);
-    }
+    for (uint32_t i = lane; i < cnt; i += 32) m = fmaxf(m, comp_of(v, v.post[off + i] >> 16, off + i));
+    for (int s = 16; s; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
     if (lane == 0) out[e] = m;
-}
-__global__ void chunk_counts(const uint32_t* __restrict__ e_count, uint32_t n, uint32_t* out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (e_count[i] + 31) >> 5;
 }
 
 __global__ void mark_dense(const uint32_t* __restrict__ e_count, uint32_t n, uint32_t* flags) {
@@ -312,11 +299,11 @@ struct ItemCtx {
 __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryPlan* pl, const ItemCtx& c, uint2 ient, int lane,
                                                   uint64_t& L, uint32_t& thr, bool& dirty, uint64_t& matches,
                                                   uint64_t& st_visited, uint64_t& st_probes) {
-    uint32_t cnt[FAST_T], bmi[FAST_T], cmo[FAST_T]; uint64_t off[FAST_T]; float idf[FAST_T], ub[FAST_T];
+    uint32_t cnt[FAST_T], bmi[FAST_T]; uint64_t off[FAST_T]; float idf[FAST_T], ub[FAST_T];
     const uint32_t n = c.n;
 #pragma unroll
     for (uint32_t t = 0; t < FAST_T; t++) {
-        cnt[t] = 0; bmi[t] = NONE; off[t] = 0; idf[t] = 0.f; ub[t] = 0.f; cmo[t] = 0;
+        cnt[t] = 0; bmi[t] = NONE; off[t] = 0; idf[t] = 0.f; ub[t] = 0.f;
         const uint32_t er = (t < 2 ? (ient.x >> (16 * t)) : (ient.y >> (16 * (t - 2)))) & 0xFFFFu;
         if (t < n) {
             const QTerm qt = pl->t[t];
@@ -324,7 +311,7 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
             if (er != ENT_NONE) {
                 const uint32_t e = qt.first + er;
                 cnt[t] = __ldg(&v.e_count[e]); off[t] = __ldg(&v.e_off[e]); bmi[t] = __ldg(&v.e_bitmap[e]);
-                ub[t] = __fmul_rn(qt.idf, __ldg(&v.e_maxcomp[e])); cmo[t] = __ldg(&v.e_cmoff[e]);
+                ub[t] = __fmul_rn(qt.idf, __ldg(&v.e_maxcomp[e]));
             }
         }
     }
@@ -376,37 +363,31 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
             uint32_t drv = 0;
 #pragma unroll
             for (uint32_t t = 0; t < FAST_T; t++) if (pos[t] == p) drv = t;
-            uint32_t dcnt = 0, dcmo = 0; uint64_t doff = 0; float didf = 0.f;
+            uint32_t dcnt = 0; uint64_t doff = 0; float didf = 0.f;
 #pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) if (t == drv) { dcnt = cnt[t]; doff = off[t]; didf = idf[t]; dcmo = cmo[t]; }
+            for (uint32_t t = 0; t < FAST_T; t++) if (t == drv) { dcnt = cnt[t]; doff = off[t]; didf = idf[t]; }
             if (dcnt == 0) break;                         // absent terms sort last
             // a driver is essential while the in-query-order sum of the not-yet-driven bounds can reach theta
             float S = 0.f;
 #pragma unroll
             for (uint32_t t = 0; t < FAST_T; t++) if (t < n && pos[t] >= p) S = __fadd_rn(S, ub[t]);
             if (ord_f32(S) < thr) break;
-            const uint32_t n_chunks = (dcnt + 31) >> 5;
-            for (uint32_t cg = 0; cg < n_chunks; cg += 32) {
-                // posting-level block-max: lane l tests chunk cg+l (32 postings) with its precomputed maximum
-                const uint32_t ch = cg + lane;
-                float Sm = 0.f;
-                {
-                    const float cmx = ch < n_chunks ? __fmul_rn(didf, __ldg(&v.chunkmax[dcmo + ch])) : 0.f;
+            st_visited += dcnt;
+            for (uint32_t base = 0; base < dcnt; base += 128) {
+                // 4 chunks of 32 postings per iteration: the 4 streaming loads are issued back to back (memory-level
+                // parallelism; the per-chunk work below is mostly a bound check that rarely survives)
+                uint32_t pdv[4];
 #pragma unroll
-                    for (uint32_t t = 0; t < FAST_T; t++) {
-                        if (t >= n) continue;
-                        if (t == drv) Sm = __fadd_rn(Sm, cmx);
-                        else if (pos[t] > p) Sm = __fadd_rn(Sm, ub[t]);
-                    }
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t pp = base + 32u * u + lane;
+                    pdv[u] = pp < dcnt ? __ldg(&v.post[doff + pp]) : 0u;
                 }
-                unsigned cmask = __ballot_sync(FULL, ch < n_chunks && ord_f32(Sm) >= thr);
-                while (cmask) {
-                    const uint32_t cb = cg + (uint32_t)(__ffs(cmask) - 1);
-                    cmask &= cmask - 1;
-                    st_visited += 32;
-                    const uint32_t pp = cb * 32 + lane;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (base + 32u * u >= dcnt) break;
+                    const uint32_t pp = base + 32u * u + lane;
                     const bool active = pp < dcnt;
-                    const uint32_t pd = active ? __ldg(&v.post[doff + pp]) : 0u;
+                    const uint32_t pd = pdv[u];
                     const uint32_t d = pd & 0xFFFFu;
                     const float cd = __fmul_rn(didf, comp_of(v, pd >> 16, doff + pp));
                     // candidate bound: own contribution + bounds of the later-ranked terms, summed in query order
@@ -418,6 +399,7 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
                         else if (pos[t] > p) Sc = __fadd_rn(Sc, ub[t]);
                     }
                     bool alive = active && ord_f32(Sc) >= thr;
+                    if (!__any_sync(FULL, alive)) continue;
                     float score = 0.f;
 #pragma unroll
                     for (uint32_t t = 0; t < FAST_T; t++) {      // query order
@@ -667,8 +649,7 @@ LexIndex::~LexIndex() {
 void LexIndex::free_committed() {
     cudaFree(d_dict_keys_); cudaFree(d_term_first_); cudaFree(d_term_idf_); cudaFree(d_term_df_);
     cudaFree(d_e_level_); cudaFree(d_e_off_); cudaFree(d_e_count_); cudaFree(d_e_maxcomp_); cudaFree(d_e_bitmap_);
-    cudaFree(d_bm_words_); cudaFree(d_bm_rank_); cudaFree(d_level_ids_); cudaFree(d_cache_); cudaFree(d_e_cmoff_); cudaFree(d_chunkmax_);
-    d_e_cmoff_ = nullptr; d_chunkmax_ = nullptr;
+    cudaFree(d_bm_words_); cudaFree(d_bm_rank_); cudaFree(d_level_ids_); cudaFree(d_cache_);
     d_dict_keys_ = nullptr; d_term_first_ = nullptr; d_term_idf_ = nullptr; d_term_df_ = nullptr;
     d_e_level_ = nullptr; d_e_off_ = nullptr; d_e_count_ = nullptr; d_e_maxcomp_ = nullptr; d_e_bitmap_ = nullptr;
     d_bm_words_ = nullptr; d_bm_rank_ = nullptr; d_level_ids_ = nullptr; d_cache_ = nullptr;
@@ -883,16 +864,7 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
         LexView v{};
         v.e_off = d_e_off_; v.e_count = d_e_count_; v.post = post_.p; v.cache = d_cache_; v.exc_pos = exc_pos_.p; v.exc_tf = exc_tf_.p;
         v.n_exc = n_exc_; v.k1p = 1.2f + 1.0f;
-        SSB_CUDA_TRY(cudaMalloc(&d_e_cmoff_, (size_t)total * 4));
-        chunk_counts<<<(total + 255) / 256, 256, 0, st_>>>(d_e_count_, total, d_e_cmoff_);
-        uint32_t last_cnt = 0, last_off = 0;
-        SSB_CUDA_TRY(cudaMemcpyAsync(&last_cnt, d_e_cmoff_ + total - 1, 4, cudaMemcpyDeviceToHost, st_));
-        thrust::exclusive_scan(pol, thrust::device_ptr<uint32_t>(d_e_cmoff_), thrust::device_ptr<uint32_t>(d_e_cmoff_ + total), thrust::device_ptr<uint32_t>(d_e_cmoff_));
-        SSB_CUDA_TRY(cudaMemcpyAsync(&last_off, d_e_cmoff_ + total - 1, 4, cudaMemcpyDeviceToHost, st_));
-        SSB_CUDA_TRY(cudaStreamSynchronize(st_));
-        n_chunks_ = (uint64_t)last_cnt + last_off;
-        SSB_CUDA_TRY(cudaMalloc(&d_chunkmax_, (n_chunks_ ? n_chunks_ : 1) * 4));
-        entry_maxcomp<<<(total + 7) / 8, 256, 0, st_>>>(v, total, d_e_maxcomp_, d_e_cmoff_, d_chunkmax_);
+        entry_maxcomp<<<(total + 7) / 8, 256, 0, st_>>>(v, total, d_e_maxcomp_);
         SSB_CUDA_TRY(cudaGetLastError());
     }
     SSB_CUDA_TRY(cudaStreamSynchronize(st_));
@@ -964,7 +936,6 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
     LexView v{};
     v.dict_keys = d_dict_keys_; v.n_terms = n_terms_; v.term_first = d_term_first_; v.term_idf = d_term_idf_; v.term_df = d_term_df_;
     v.e_level = d_e_level_; v.e_off = d_e_off_; v.e_count = d_e_count_; v.e_maxcomp = d_e_maxcomp_; v.e_bitmap = d_e_bitmap_;
-    v.e_cmoff = d_e_cmoff_; v.chunkmax = d_chunkmax_;
     v.post = post_.p; v.bm_words = d_bm_words_; v.bm_rank = d_bm_rank_; v.level_ids = d_level_ids_;
     v.n_levels = (uint32_t)levels_.size(); v.cache = d_cache_; v.exc_pos = exc_pos_.p; v.exc_tf = exc_tf_.p; v.n_exc = n_exc_;
     v.k1p = 1.2f + 1.0f;

@@ -57,8 +57,6 @@ struct LexView {
     const uint32_t* e_count;
     const float* e_maxcomp;       // block-max basis: max tf*(K+1)/(tf+cache[len]) over the list
     const uint32_t* e_bitmap;     // index into bm_* or 0xFFFFFFFF
-    const uint32_t* e_cmoff;      // first chunk-max slot of the entry
-    const float* chunkmax;        // max comp of every 32-posting chunk (posting-level block-max)
     const uint32_t* post;         // arena: id16 | tf8<<16 | len8<<24, one word per posting
     const uint64_t* bm_words;     // [n_bitmaps][1024]
     const uint16_t* bm_rank;      // [n_bitmaps][1024] postings before word w
@@ -108,7 +106,7 @@ private:
     uint32_t n_terms_ = 0, n_entries_ = 0, n_bitmaps_ = 0;
     uint64_t* d_dict_keys_ = nullptr; uint32_t* d_term_first_ = nullptr; float* d_term_idf_ = nullptr; uint32_t* d_term_df_ = nullptr;
     uint32_t* d_e_level_ = nullptr; uint64_t* d_e_off_ = nullptr; uint32_t* d_e_count_ = nullptr; float* d_e_maxcomp_ = nullptr; uint32_t* d_e_bitmap_ = nullptr;
-    uint64_t* d_bm_words_ = nullptr; uint16_t* d_bm_rank_ = nullptr; uint32_t* d_e_cmoff_ = nullptr; float* d_chunkmax_ = nullptr; uint64_t n_chunks_ = 0;
+    uint64_t* d_bm_words_ = nullptr; uint16_t* d_bm_rank_ = nullptr;
     uint32_t* d_level_ids_ = nullptr; float* d_cache_ = nullptr;
     std::vector<uint64_t> h_dict_keys_; std::vector<uint32_t> h_term_df_;
     void free_committed();

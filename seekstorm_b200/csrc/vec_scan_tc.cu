@@ -3,6 +3,8 @@
 // Same contract as scan_ffma (vec_scan.cu): corpus [n_rows, Dpad] f32 x a block of NQ queries -> per-CTA
 // top-32 lists, but the query x corpus contraction runs on the 5th-gen tensor cores:
 //   D[128 corpus rows, NQ queries] (f32, TMEM) += A[128 x 8] . B[NQ x 8]^T      tcgen05.mma kind::tf32
+// Each smem stage holds MT=2 corpus tiles (256 rows) against ONE query chunk, so the query operand, which is
+// re-fetched from L2 for every stage, costs half the L2->SM bandwidth (the measured limiter of the 1-tile version).
 // f32 accuracy (north-star tolerance 1e-4 on cosine scores) is kept with the 3xTF32 split
 //   a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo,   x_hi = x & 0xFFFFE000 (exactly representable in tf32),
 //   x_lo = x - x_hi (exact in f32); the dropped a_lo.b_lo term is ~2^-22 relative.
@@ -22,19 +24,22 @@ namespace vec {
 
 namespace tc {
 constexpr int KC = 32;                 // floats per k-chunk = one 128-byte swizzle row
-constexpr int TM = 128;                // corpus rows per tile = UMMA M
-constexpr int A_BYTES = TM * KC * 4;   // 16 KB
+constexpr int TM = 128;                // UMMA M
+constexpr int MT = 2;                  // M-tiles per stage: the B (query) chunk is fetched once per MT*128 corpus rows
+constexpr int TROWS = TM * MT;         // corpus rows per stage
+constexpr int A1_BYTES = TM * KC * 4;  // one 128-row swizzled tile, 16 KB
+constexpr int A_BYTES = MT * A1_BYTES; // 32 KB
 constexpr int THREADS = 384;
 constexpr int CHUNK = 8;               // query columns per epilogue step
 
 template <int NQ> struct Cfg {
     static constexpr int B_BYTES = NQ * KC * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // A, A_lo, B_hi, B_lo
-    static constexpr int STAGES = NQ <= 64 ? 4 : 3;                        // 4 x 48 KB or 3 x 64 KB
+    static constexpr int STAGES = 2;                                       // 2 x (64 KB A/A_lo + 2*B) 
     static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
     static constexpr int CAND_BYTES = CHUNK * TM * 8;
     static constexpr int SMEM = STAGES * STAGE_BYTES + CAND_BYTES + NQ * 4 + 256;
-    static constexpr int TMEM_COLS = 2 * NQ;                               // power of two for NQ in {64,128,256}
+    static constexpr int TMEM_COLS = 2 * MT * NQ;                          // double-buffered MT accumulators (256 / 512 columns)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
@@ -110,7 +115,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     uint8_t* st = stage0 + s * C::STAGE_BYTES;
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&full[s], C::TX_BYTES);
-                    tma_load_2d(st, &tmA, (int)(kc * KC), (int)(tile * TM), &full[s]);
+                    tma_load_2d(st, &tmA, (int)(kc * KC), (int)(tile * TROWS), &full[s]);   // 256-row box = MT swizzled tiles
                     tma_load_2d(st + 2 * A_BYTES, &tmBh, (int)(kc * KC), (int)(group * NQ), &full[s]);
                     tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmBl, (int)(kc * KC), (int)(group * NQ), &full[s]);
                 }
@@ -126,7 +131,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
                 mbar_wait(&tempty[buf], tph ^ 1u);
                 tc_fence_after();
-                const uint32_t d = tmem_base + buf * NQ;
+                const uint32_t d = tmem_base + buf * (MT * NQ);
                 for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
                     uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&full[s], ph);
@@ -136,11 +141,15 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     const uint64_t a_hi = umma_desc_k128(sa), a_lo = umma_desc_k128(sa + A_BYTES);
                     const uint64_t b_hi = umma_desc_k128(sa + 2 * A_BYTES), b_lo = umma_desc_k128(sa + 2 * A_BYTES + C::B_BYTES);
 #pragma unroll
-                    for (uint32_t kk = 0; kk < 4; kk++) {        // 4 x K=8 (32 bytes) inside the 128-byte swizzle row
-                        const uint64_t o = (uint64_t)(kk * 2);  // +32 bytes in 16-byte units
-                        umma_tf32(d, a_hi + o, b_hi + o, idesc, (kc | kk) != 0);
-                        umma_tf32(d, a_lo + o, b_hi + o, idesc, 1);
-                        umma_tf32(d, a_hi + o, b_lo + o, idesc, 1);
+                    for (uint32_t m = 0; m < MT; m++) {
+                        const uint64_t am = (uint64_t)((m * A1_BYTES) >> 4);   // next 128-row tile of the stage
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; kk++) {        // 4 x K=8 (32 bytes) inside the 128-byte swizzle row
+                            const uint64_t o = (uint64_t)(kk * 2);  // +32 bytes in 16-byte units
+                            umma_tf32(d + m * NQ, a_hi + am + o, b_hi + o, idesc, (kc | kk) != 0);
+                            umma_tf32(d + m * NQ, a_lo + am + o, b_hi + o, idesc, 1);
+                            umma_tf32(d + m * NQ, a_hi + am + o, b_lo + o, idesc, 1);
+                        }
                     }
                     umma_commit(&empty[s]);                      // stage reusable once these MMAs retire
                     if (kc + 1 == n_kchunks) umma_commit(&tfull[buf]);
@@ -174,7 +183,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: TMEM -> filter -> per-query top-k =====================
+        // ===================== epilogue: TMEM -> filter -> per-query top-k (MT accumulators per buffer) =====================
         const int ew = warp - 4;                          // == warp % 4 == TMEM lane quadrant
         const int et = threadIdx.x - 128;                 // 0..127 == row inside the tile
         uint32_t ti = 0;
@@ -182,11 +191,12 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
             mbar_wait(&tfull[buf], tph);
             tc_fence_after();
-            const uint32_t row = tile * TM + (uint32_t)et;
-            const bool valid = row < n_rows;
-            for (int c = 0; c < NQ / CHUNK; c++) {
+            for (int mc = 0; mc < MT * (NQ / CHUNK); mc++) {
+                const int m = mc / (NQ / CHUNK), c = mc % (NQ / CHUNK);
+                const uint32_t row = tile * TROWS + (uint32_t)(m * TM) + (uint32_t)et;
+                const bool valid = row < n_rows;
                 uint32_t v[CHUNK];
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * NQ + c * CHUNK;
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (MT * NQ) + m * NQ + c * CHUNK;
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                              : "r"(taddr) : "memory");
@@ -251,9 +261,9 @@ template <int NQ>
 static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     using C = tc::Cfg<NQ>;
     CUtensorMap tmA, tmBh, tmBl;
-    uint32_t n_tiles = (uint32_t)((a.n_rows + tc::TM - 1) / tc::TM);
+    uint32_t n_tiles = (uint32_t)((a.n_rows + tc::TROWS - 1) / tc::TROWS);
     uint32_t n_groups = a.nq_pad / NQ;
-    SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TM, 1));
+    SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TROWS, 1));
     SSB_TRY(encode_tmap_2d_f32(&tmBh, a.q_hi, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
     SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
     uint32_t gx = n_tiles < (uint32_t)a.n_sms ? n_tiles : (uint32_t)a.n_sms;
