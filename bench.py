@@ -256,15 +256,28 @@ def cpu_vector_baseline(a, seconds):
         r = r / r.norm(dim=1, keepdim=True)
         rows[lv * 65536: lv * 65536 + r.shape[0]] = r.cpu().numpy()
     qs = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").numpy()
-    n_done, t0 = 0, time.perf_counter()
-    O.search_vector(rows, O.normalize(qs[0]), TOPK, O.SIM_COSINE, lanes8=True, n_threads=cores)  # warm
+    qn = [O.normalize(q) for q in qs]
+    O.search_vector(rows, qn[0], TOPK, O.SIM_COSINE, lanes8=True, n_threads=cores)  # warm (page in the corpus)
+    # one worker per core, each answering whole queries single-threaded (8-lane FMA dot, linear top-k): the
+    # throughput-optimal arrangement of the reference's per-shard scan on this host
+    done = [0] * cores
+    stop = time.perf_counter() + seconds
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work(i):
+        while time.perf_counter() < stop:
+            with lock:
+                j = nxt[0]; nxt[0] += 1
+            O.search_vector(rows, qn[j % len(qn)], TOPK, O.SIM_COSINE, lanes8=True, n_threads=1)
+            done[i] += 1
     t0 = time.perf_counter()
-    while n_done < len(qs) and (time.perf_counter() - t0) < seconds:
-        O.search_vector(rows, O.normalize(qs[n_done]), TOPK, O.SIM_COSINE, lanes8=True, n_threads=cores)
-        n_done += 1
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]; [t.join() for t in th]
     dt = time.perf_counter() - t0
+    n_done = sum(done)
     return {"value": n_done / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-            "sample": f"{n_done} of the {a.batch} C2 queries, full {a.rows}x{a.dims} corpus, {cores} threads (row-split), {dt:.1f}s"}
+            "sample": f"{n_done} queries (cycling the {a.batch} C2 queries), full {a.rows}x{a.dims} corpus, {cores} threads (one query each), {dt:.1f}s"}
 
 
 # ----------------------------------------------------------------------------------------------------------------

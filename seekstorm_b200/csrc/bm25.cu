@@ -156,6 +156,9 @@ __global__ void compact_dense(const uint32_t* __restrict__ e_bitmap, uint32_t n,
 // 3194-3217), live-term list in query order, per-level bound and presence count, blocks sorted by bound desc
 // (intersection.rs:2224-2225, single.rs:372).  For the first FAST_T live terms the entry index of every level is
 // recorded with the item so the scoring kernel needs no directory search.
+#ifndef SSB_LEX_U
+#define SSB_LEX_U 1   // 32-posting chunks fetched per iteration (measured: batching 2-4 chunks is SLOWER — code size / I-cache)
+#endif
 constexpr uint32_t FAST_T = 4;          // queries with <= 4 live terms take the register-resident fast path
 constexpr uint32_t ENT_NONE = 0xFFFFu;
 
@@ -373,17 +376,17 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
             for (uint32_t t = 0; t < FAST_T; t++) if (t < n && pos[t] >= p) S = __fadd_rn(S, ub[t]);
             if (ord_f32(S) < thr) break;
             st_visited += dcnt;
-            for (uint32_t base = 0; base < dcnt; base += 128) {
+            for (uint32_t base = 0; base < dcnt; base += 32u * SSB_LEX_U) {
                 // 4 chunks of 32 postings per iteration: the 4 streaming loads are issued back to back (memory-level
                 // parallelism; the per-chunk work below is mostly a bound check that rarely survives)
-                uint32_t pdv[4];
+                uint32_t pdv[SSB_LEX_U];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < SSB_LEX_U; u++) {
                     const uint32_t pp = base + 32u * u + lane;
                     pdv[u] = pp < dcnt ? __ldg(&v.post[doff + pp]) : 0u;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < SSB_LEX_U; u++) {
                     if (base + 32u * u >= dcnt) break;
                     const uint32_t pp = base + 32u * u + lane;
                     const bool active = pp < dcnt;
@@ -571,7 +574,10 @@ __device__ __noinline__ void process_item_generic(const LexView& v, const QueryP
     }
 }
 
-__global__ void __launch_bounds__(256) lex_score(LexView v, const QueryPlan* __restrict__ plans, const uint64_t* __restrict__ items,
+#ifndef SSB_LEX_MINB
+#define SSB_LEX_MINB 5
+#endif
+__global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const QueryPlan* __restrict__ plans, const uint64_t* __restrict__ items,
                                                  const uint2* __restrict__ item_ent, uint32_t nq, uint32_t query_type, uint32_t result_type,
                                                  uint32_t k, uint32_t* ctr, uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist,
                                                  LexStats* stats) {
@@ -949,7 +955,7 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
     if (plan_smem > 48 * 1024) SSB_CUDA_TRY(cudaFuncSetAttribute(lex_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
     lex_plan<<<nq, 128, plan_smem, st_>>>(v, d_qoff_, d_qkeys_, q->query_type, d_plans_, d_items_, (uint2*)d_item_ent_, d_ctr_, d_theta_, d_lock_, d_count_, glist, n_pow2);
     SSB_CUDA_TRY(cudaGetLastError());
-    int grid = n_sms_ * 8;
+    int grid = n_sms_ * SSB_LEX_MINB;
     if (ev0_) cudaEventRecord(ev0_, st_);
     lex_score<<<grid, 256, 0, st_>>>(v, d_plans_, d_items_, (const uint2*)d_item_ent_, nq, q->query_type, result_type, k ? k : 1, d_ctr_, d_theta_, d_lock_, d_count_, glist, d_stats_);
     if (ev1_) cudaEventRecord(ev1_, st_);
