@@ -261,10 +261,11 @@ struct TermRegs {   // generic path: lane t holds query term t of the current it
 // membership + rank probe of doc d in the list described by (cnt, off, bmi); posting word returned in `pw`
 __device__ __forceinline__ bool probe(const LexView& v, uint32_t cnt, uint64_t off, uint32_t bmi, uint32_t d, uint32_t& rank) {
     if (bmi != NONE) {
-        uint64_t w = __ldg(&v.bm_words[(size_t)bmi * 1024 + (d >> 6)]);
-        if (!((w >> (d & 63)) & 1ull)) return false;
-        rank = (uint32_t)__ldg(&v.bm_rank[(size_t)bmi * 1024 + (d >> 6)]) + (uint32_t)__popcll(w & ((1ull << (d & 63)) - 1ull));
-        return true;
+        // both loads depend only on d: issue them together (one memory latency instead of two)
+        const uint64_t w = __ldg(&v.bm_words[(size_t)bmi * 1024 + (d >> 6)]);
+        const uint32_t r0 = (uint32_t)__ldg(&v.bm_rank[(size_t)bmi * 1024 + (d >> 6)]);
+        rank = r0 + (uint32_t)__popcll(w & ((1ull << (d & 63)) - 1ull));
+        return ((w >> (d & 63)) & 1ull) != 0;
     }
     uint32_t lo = 0, hi = cnt;
     const uint32_t* a = v.post + off;
@@ -376,12 +377,14 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
             for (uint32_t t = 0; t < FAST_T; t++) if (t < n && pos[t] >= p) S = __fadd_rn(S, ub[t]);
             if (ord_f32(S) < thr) break;
             st_visited += dcnt;
+            uint32_t pd_next = (uint32_t)lane < dcnt ? __ldg(&v.post[doff + lane]) : 0u;
             for (uint32_t base = 0; base < dcnt; base += 32u * SSB_LEX_U) {
-                // 4 chunks of 32 postings per iteration: the 4 streaming loads are issued back to back (memory-level
-                // parallelism; the per-chunk work below is mostly a bound check that rarely survives)
+                // software pipelining: the next chunk's postings are requested before this chunk is processed
                 uint32_t pdv[SSB_LEX_U];
+                pdv[0] = pd_next;
+                { const uint32_t pn = base + 32u * SSB_LEX_U + lane; pd_next = pn < dcnt ? __ldg(&v.post[doff + pn]) : 0u; }
 #pragma unroll
-                for (int u = 0; u < SSB_LEX_U; u++) {
+                for (int u = 1; u < SSB_LEX_U; u++) {
                     const uint32_t pp = base + 32u * u + lane;
                     pdv[u] = pp < dcnt ? __ldg(&v.post[doff + pp]) : 0u;
                 }

@@ -80,6 +80,19 @@ __device__ __forceinline__ void wl_insert(uint64_t& L, uint64_t cand, int lane) 
     if (lane == pos) L = cand;
     else if (lane > pos) L = up;
 }
+// Sort 32 keys (one per lane) descending with a shuffle bitonic network (15 compare-exchange steps).
+__device__ __forceinline__ uint64_t wl_sort_desc(uint64_t v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t p = shfl64_xor(v, j);
+            const bool keep_max = ((lane & k) == 0) == ((lane & j) == 0);
+            v = keep_max ? (v > p ? v : p) : (v < p ? v : p);
+        }
+    }
+    return v;
+}
 // Merge two descending lists -> the 32 largest of their union, descending.
 __device__ __forceinline__ uint64_t wl_merge(uint64_t A, uint64_t B, int lane) {
     uint64_t Br = shfl64(B, 31 - lane);

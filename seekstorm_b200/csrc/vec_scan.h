@@ -23,13 +23,19 @@ struct ScanArgs {
     uint64_t* keys_out;           // [nq_pad][32]
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // recorded around the scan kernel when set
     float* q_hi = nullptr; float* q_lo = nullptr;  // [nq_pad][dpad] tf32 split of the queries (tcgen05 kernel)
+    uint32_t* thr_buf = nullptr;                   // [nq_pad] scratch for the pre-sampled per-query thresholds
+    const uint32_t* thr_init = nullptr;            // internal: initial thresholds (ordered-uint scores) or null
 };
+
+constexpr uint64_t VEC_PRESAMPLE_ROWS = 32768;   // rows scanned first to seed the per-query top-k thresholds
 
 int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);
 int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128*/, cudaStream_t st);
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad);
 // lists laid out [group][n_lists][qt][32] -> out [nq][32]
+// thr[q] = ordered-uint score of the k-th entry of keys[q][32] (0 if the list is shorter)
+void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_t* thr, cudaStream_t st);
 void merge_lists_generic(const uint64_t* in, uint32_t n_lists, uint32_t qt, uint32_t nq, uint64_t* out, cudaStream_t st);
 int32_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, float* out,
                             uint32_t nq_pad, uint32_t dpad, int normalize, cudaStream_t st);

@@ -37,8 +37,7 @@ template <int NQ> struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // A, A_lo, B_hi, B_lo
     static constexpr int STAGES = 2;                                       // 2 x (64 KB A/A_lo + 2*B) 
     static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
-    static constexpr int CAND_BYTES = CHUNK * TM * 8;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + CAND_BYTES + NQ * 4 + 256;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + NQ * 4 + 256;
     static constexpr int TMEM_COLS = 2 * MT * NQ;                          // double-buffered MT accumulators (256 / 512 columns)
 };
 
@@ -63,7 +62,8 @@ template <int NQ>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
         const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
-        const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x][NQ][32]*/) {
+        const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*4][NQ][32]*/,
+        const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/) {
     using C = Cfg<NQ>;
     constexpr int STAGES = C::STAGES;
     // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for SWIZZLE_128B)
@@ -72,17 +72,15 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     uint8_t* stage0 = base;
     // per-query sorted lists live directly in this CTA's slice of the output scratch (global, L2-resident): they are
     // touched only on the rare candidate insert, and each query is always owned by the same warp
-    uint64_t* lists = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NQ * LIST;   // [NQ][32]
-    uint64_t* cand = (uint64_t*)(base + STAGES * C::STAGE_BYTES);             // [CHUNK][TM]
-    float* thr_s = (float*)((uint8_t*)cand + C::CAND_BYTES);                  // [NQ]
+    uint64_t* lists = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 * NQ * LIST;   // [4 epilogue warps][NQ][32]
+    float* thr_s = (float*)(base + STAGES * C::STAGE_BYTES);                  // [NQ] (used as ordered-uint thresholds)
     uint64_t* bars = (uint64_t*)(thr_s + NQ);
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* split = full + STAGES;       // [STAGES]
     uint64_t* empty = split + STAGES;      // [STAGES]
     uint64_t* tfull = empty + STAGES;      // [2]
     uint64_t* tempty = tfull + 2;          // [2]
-    uint32_t* cand_cnt = (uint32_t*)(tempty + 2);   // [CHUNK]
-    uint32_t* tmem_slot = cand_cnt + CHUNK;
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t group = blockIdx.y;
@@ -92,9 +90,8 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < NQ * LIST; i += THREADS) lists[i] = 0;
-    for (int i = threadIdx.x; i < NQ; i += THREADS) thr_s[i] = -INFINITY;
-    if (threadIdx.x < CHUNK) cand_cnt[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < NQ; i += THREADS)   // ordered-uint thresholds, seeded by the pre-sample pass when present
+        reinterpret_cast<uint32_t*>(thr_s)[i] = thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -114,10 +111,20 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     uint8_t* st = stage0 + s * C::STAGE_BYTES;
                     mbar_wait(&empty[s], ph ^ 1u);
+#ifdef TC_DBG_NOB
+                    mbar_arrive_expect_tx(&full[s], it < (uint32_t)STAGES ? C::TX_BYTES : A_BYTES);
+#else
                     mbar_arrive_expect_tx(&full[s], C::TX_BYTES);
+#endif
                     tma_load_2d(st, &tmA, (int)(kc * KC), (int)(tile * TROWS), &full[s]);   // 256-row box = MT swizzled tiles
+#ifdef TC_DBG_NOB
+                    if (it < (uint32_t)STAGES) {
+#endif
                     tma_load_2d(st + 2 * A_BYTES, &tmBh, (int)(kc * KC), (int)(group * NQ), &full[s]);
                     tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmBl, (int)(kc * KC), (int)(group * NQ), &full[s]);
+#ifdef TC_DBG_NOB
+                    }
+#endif
                 }
             }
         }
@@ -147,8 +154,10 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                         for (uint32_t kk = 0; kk < 4; kk++) {        // 4 x K=8 (32 bytes) inside the 128-byte swizzle row
                             const uint64_t o = (uint64_t)(kk * 2);  // +32 bytes in 16-byte units
                             umma_tf32(d + m * NQ, a_hi + am + o, b_hi + o, idesc, (kc | kk) != 0);
+#ifndef TC_DBG_1MMA
                             umma_tf32(d + m * NQ, a_lo + am + o, b_hi + o, idesc, 1);
                             umma_tf32(d + m * NQ, a_hi + am + o, b_lo + o, idesc, 1);
+#endif
                         }
                     }
                     umma_commit(&empty[s]);                      // stage reusable once these MMAs retire
@@ -166,6 +175,9 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 mbar_wait(&full[s], ph);
                 uint4* A = (uint4*)(stage0 + s * C::STAGE_BYTES);
                 uint4* Al = (uint4*)(stage0 + s * C::STAGE_BYTES + A_BYTES);
+#ifdef TC_DBG_NOSPLIT
+                if (false)
+#endif
 #pragma unroll
                 for (int j = 0; j < (A_BYTES / 16) / 128; j++) {
                     uint4 x = A[t + 128 * j], h, l;
@@ -183,9 +195,17 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: TMEM -> filter -> per-query top-k (MT accumulators per buffer) =====================
+        // ===================== epilogue: TMEM -> filter -> per-warp per-query top-k (no CTA-level barriers) =====================
+        // Each epilogue warp owns the 32 TMEM lanes (= corpus rows) of its quadrant and keeps its own sorted list per
+        // query in this CTA's slice of the output scratch.  The per-query threshold (ordered-uint score of the best
+        // k-th entry any warp of the CTA has seen) is shared through smem with atomicMax: monotone, so stale reads only
+        // cost an extra insert.  (An earlier version synchronised the 4 warps with two named barriers per 8-query chunk;
+        // measured cost ~800 cycles per barrier — 40 % of the kernel.)
         const int ew = warp - 4;                          // == warp % 4 == TMEM lane quadrant
-        const int et = threadIdx.x - 128;                 // 0..127 == row inside the tile
+        uint32_t* thr_u = reinterpret_cast<uint32_t*>(thr_s);
+        uint64_t* mylists = lists + (size_t)ew * NQ * LIST;
+        for (int i = lane; i < NQ * LIST; i += 32) mylists[i] = 0;
+        __syncwarp();
         uint32_t ti = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
             const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
@@ -193,7 +213,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             tc_fence_after();
             for (int mc = 0; mc < MT * (NQ / CHUNK); mc++) {
                 const int m = mc / (NQ / CHUNK), c = mc % (NQ / CHUNK);
-                const uint32_t row = tile * TROWS + (uint32_t)(m * TM) + (uint32_t)et;
+                const uint32_t row = tile * TROWS + (uint32_t)(m * TM) + (uint32_t)(ew * 32 + lane);
                 const bool valid = row < n_rows;
                 uint32_t v[CHUNK];
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (MT * NQ) + m * NQ + c * CHUNK;
@@ -203,34 +223,26 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < CHUNK; j++) {
+                    const int q = c * CHUNK + j;
                     const float sc = __uint_as_float(v[j]);
-                    const bool pass = valid && sc >= thr_s[c * CHUNK + j];
-                    const unsigned m = __ballot_sync(FULL, pass);
-                    if (m) {
-                        uint32_t b0 = 0;
-                        if (lane == 0) b0 = atomicAdd(&cand_cnt[j], (uint32_t)__popc(m));
-                        b0 = __shfl_sync(FULL, b0, 0);
-                        if (pass) {
-                            const uint32_t doc = doc_ids ? __ldg(&doc_ids[row]) : row;
-                            cand[j * TM + b0 + __popc(m & ((1u << lane) - 1u))] = pack_key(sc, doc);
+                    const uint32_t so = ord_f32(sc);
+                    const bool pass = valid && sc == sc && so >= thr_u[q];
+                    unsigned pm = __ballot_sync(FULL, pass);
+                    if (pm) {                                           // rare after warm-up
+                        uint64_t key = 0;
+                        if (pass) key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
+                        uint64_t L = mylists[q * LIST + lane];
+                        if (__popc(pm) > 3) {
+                            // bulk (warm-up tiles: every row passes): sort the 32 keys, bitonic-merge into the list
+                            L = wl_merge(L, wl_sort_desc(key, lane), lane);
+                        } else {
+                            while (pm) { const int src = __ffs(pm) - 1; pm &= pm - 1; wl_insert(L, shfl64(key, src), lane); }
                         }
+                        mylists[q * LIST + lane] = L;
+                        const uint32_t kth = (uint32_t)(shfl64(L, (int)k - 1) >> 32);
+                        if (lane == 0 && kth > thr_u[q]) atomicMax(&thr_u[q], kth);
                     }
                 }
-                named_bar(1, 128);
-                // warp ew owns buckets 2*ew, 2*ew+1 of this chunk
-#pragma unroll
-                for (int jj = 0; jj < 2; jj++) {
-                    const int j = ew * 2 + jj, q = c * CHUNK + j;
-                    const uint32_t n = cand_cnt[j];
-                    if (n) {
-                        uint64_t L = lists[q * LIST + lane];
-                        for (uint32_t i = 0; i < n; i++) wl_insert(L, cand[j * TM + i], lane);
-                        lists[q * LIST + lane] = L;
-                        const uint64_t kth = shfl64(L, (int)k - 1);
-                        if (lane == 0) { thr_s[q] = kth ? key_score(kth) : -INFINITY; cand_cnt[j] = 0; }
-                    }
-                }
-                named_bar(1, 128);
             }
             tc_fence_before();
             __syncwarp();
@@ -267,7 +279,7 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     SSB_TRY(encode_tmap_2d_f32(&tmBh, a.q_hi, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
     SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
     uint32_t gx = n_tiles < (uint32_t)a.n_sms ? n_tiles : (uint32_t)a.n_sms;
-    if ((size_t)n_groups * gx * NQ * LIST * 8 > a.scratch_bytes) { set_error("vector scan scratch too small"); return SSB_E_STATE; }
+    if ((size_t)n_groups * gx * 4 * NQ * LIST * 8 > a.scratch_bytes) { set_error("vector scan scratch too small"); return SSB_E_STATE; }
     static bool attr_set = false;
     if (!attr_set) {
         SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -277,23 +289,37 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     tc::split_queries<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, a.q_hi, a.q_lo, nel);
     if (a.ev0) cudaEventRecord(a.ev0, st);
     tc::scan_tc<NQ><<<dim3(gx, n_groups), tc::THREADS, C::SMEM, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, a.dpad / tc::KC, n_tiles,
-                                                                       a.k, a.doc_ids, a.scratch);
+                                                                       a.k, a.doc_ids, a.scratch, a.thr_init);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ
-    merge_lists_generic(a.scratch, gx, NQ, a.nq_pad, a.keys_out, st);
+    merge_lists_generic(a.scratch, gx * 4, NQ, a.nq_pad, a.keys_out, st);
     SSB_CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }
 
+static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, cudaStream_t st);
+
 int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, cudaStream_t st) {
+    // threshold pre-sampling (see vec_scan.cu): scan the first rows, seed the thresholds, then the full scan
+    if (a.thr_init || !a.thr_buf || a.n_rows < 4 * VEC_PRESAMPLE_ROWS) return launch_scan_tc_impl(a, nq_tile, st);
+    ScanArgs pre = a;
+    pre.n_rows = VEC_PRESAMPLE_ROWS; pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
+    SSB_TRY(launch_scan_tc_impl(pre, nq_tile, st));
+    launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
+    ScanArgs full = a;
+    full.thr_init = a.thr_buf;
+    return launch_scan_tc_impl(full, nq_tile, st);
+}
+
+static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, cudaStream_t st) {
     if (a.n_rows == 0 || a.nq_pad == 0) return SSB_OK;
     if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }
     if ((nq_tile != 64 && nq_tile != 128) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 scan: query count must be padded to the 64/128 query tile"); return SSB_E_INVALID; }
     return nq_tile == 64 ? launch_tc_n<64>(a, st) : launch_tc_n<128>(a, st);
 }
 
-size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)nq_pad * (size_t)n_sms * LIST * 8; }
+size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)nq_pad * (size_t)n_sms * 4 * LIST * 8; }
 
 }  // namespace vec
 }  // namespace ssb
