@@ -50,7 +50,8 @@ def parse():
     p.add_argument("--bm25-docs", type=int, default=C3_DOCS)
     p.add_argument("--bm25-batch", type=int, default=4096, help="lexical queries per step")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
-    p.add_argument("--vector-kernel", default="ffma", choices=["ffma", "tc", "tc64"], help="FP32 FFMA2 scan or tcgen05 3xTF32 scan (128 / 64 queries per pass)")
+    p.add_argument("--vector-kernel", default="both", choices=["both", "ffma", "tc", "tc64"],
+                   help="FP32 FFMA2 scan, tcgen05 3xTF32 scan (128 / 64 queries per pass) or both (headline = the faster)")
     return p.parse_args()
 
 
@@ -165,28 +166,18 @@ def gen_vector_level(level, rows, dims, device):
     return synth.gen_vectors(n, dims, 1002 * 1000 + level, device)
 
 
-def bench_vector(a, rank, world, out):
-    from seekstorm_b200 import Index, VectorSimilarity
-    from seekstorm_b200.parallel import ShardedSearcher
-    dev = torch.device("cuda", torch.cuda.current_device())
-    ix = Index(dev.index, vector_dims=a.dims, vector_similarity=VectorSimilarity.Cosine, max_batch=max(a.batch, 16),
-               vector_kernel={"ffma": 1, "tc": 2, "tc64": 3}[a.vector_kernel])
-    qt = {"ffma": 16, "tc": 128, "tc64": 64}[a.vector_kernel]
-    ix.set_stream(torch.cuda.current_stream().cuda_stream)
-    n_levels, mine = vector_levels(a.rows, rank, world)
-    local_rows = 0
-    for lv in mine:
-        r = gen_vector_level(lv, a.rows, a.dims, dev)
-        ix.add_vector_level(lv, r)
-        local_rows += r.shape[0]
-        del r
-    from seekstorm_b200 import synth
-    q_host = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").pin_memory()
-    q_dev = q_host.to(dev)
-    keys = torch.zeros((a.batch, 32), dtype=torch.int64, device=dev)
-    sh = ShardedSearcher(ix)
+KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + warp top-k)"),
+           "tc": (2, 128, "scan_tc", "scan_tc (TMA + tcgen05 3xTF32 split, TMEM accumulators, TMEM-epilogue top-k)"),
+           "tc64": (3, 64, "scan_tc", "scan_tc<64> (tcgen05 3xTF32, 64 queries per pass)")}
+# traffic (dram__bytes_read+write per launch) and tensor-pipe utilisation from the committed ncu captures (profiles/)
+NCU = {"scan_ffma": {"traffic": 3.08e9, "source": "profiles/r01_scan_ffma_v3.summary.txt"},
+       "scan_tc": {"traffic": 3.08e9, "source": "profiles/r01_scan_tc_v3.summary.txt"}}
 
-    # ---- value: device-resident hot path (per rank scan + (N>1) NCCL all-gather + merge kernel) ----
+
+def measure_vector_kernel(a, ix, sh, kname, q_host, q_dev, keys, local_rows, rank, world, dev, want_clocks):
+    kid, qt, kshort, klong = KERNELS[kname]
+    ix.set_vector_kernel(kid)
+    # ---- value: device-resident hot path (per rank scan + (N>1) NCCL all-gather of the packed keys) ----
     if world == 1:
         def step_dev():
             ix.search_vector_keys(q_dev, TOPK, keys)
@@ -194,19 +185,16 @@ def bench_vector(a, rank, world, out):
         def step_dev():
             ix.search_vector_keys(q_dev, TOPK, keys)
             sh.gather_keys(keys)
-    # roofline of the dominant kernel (scan_ffma), CUDA events recorded by the library around that launch
     step_dev(); torch.cuda.synchronize()
-    kern_ns = []
-    sampler = ClockSampler(dev.index) if rank == 0 else None
+    sampler = ClockSampler(dev.index) if want_clocks else None
     ms = timed_steps(step_dev, a.steps, a.warmup, world, sampler)
     clocks = sampler.stop() if sampler else None
-    for _ in range(5):
+    kern_ns = []
+    for _ in range(5):       # duration of the dominant kernel: CUDA events the library records around that launch
         step_dev(); torch.cuda.synchronize()
         kern_ns.append(ix.last_stats()["dominant_kernel_ns"])
-    launches_per_step = 3 + (1 if world > 1 else 0)
+    launches = ix.last_stats()["kernel_launches"] + (1 if world > 1 else 0)
     passes = (a.batch + qt - 1) // qt
-    qps = a.batch * a.steps / (ms / 1e3)
-
     # ---- e2e: the reference-facing call with HOST buffers (H2D queries, D2H hits inside the timed region) ----
     q_np = q_host.numpy()
     hits_buf, nh_buf = ix.hits_buffer(a.batch * TOPK), np.zeros(a.batch, dtype=np.uint32)
@@ -215,30 +203,61 @@ def bench_vector(a, rank, world, out):
             ix.search_vector_raw(q_np, TOPK, hits_buf, nh_buf)     # ssb_search_vector: host queries in, host hits out
     else:
         import torch.distributed as dist
+
         def step_e2e():
             qd = q_host.to(dev, non_blocking=True) if rank == 0 else q_dev
             dist.broadcast(qd, 0)
             sh.search_vector(qd, TOPK)
     ms_e2e = timed_steps(step_e2e, a.steps, a.warmup, world)
-    qps_e2e = a.batch * a.steps / (ms_e2e / 1e3)
-
     peak, peak_kind = peaks()
     kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
     alg_bytes = float(local_rows) * a.dims * 4 * passes          # per launch (one launch = all passes of the batch)
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
-    out.update({
-        "metric": "queries/sec at top-10 (1M x 768 f32 cosine brute-force kNN)", "value": qps, "unit": "queries/s",
-        "ms_per_step": ms / a.steps, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2 brute-force cosine kNN: {a.rows} x {a.dims} f32, top-{TOPK}, batch {a.batch} queries/step "
-                               f"({passes} corpus passes of {qt} queries)", "l2": "inputs larger than L2 (corpus %.2f GB per GPU)" % (local_rows * a.dims * 4 / 1e9),
-                   "parallelism": f"levels sharded over {world} GPU(s)", "kernel": "scan_tc (TMA + tcgen05 3xTF32 + TMEM epilogue top-k)" if a.vector_kernel != "ffma" else "scan_ffma (TMA + packed FP32 FFMA2 + warp top-k)"},
-        "e2e": {"value": qps_e2e, "unit": "queries/s", "ms_per_step": ms_e2e / a.steps,
+    ncu = NCU.get(kshort, {})
+    return {
+        "value": a.batch * a.steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / a.steps,
+        "e2e": {"value": a.batch * a.steps / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / a.steps,
                 "h2d_bytes_per_step": a.batch * a.dims * 4, "d2h_bytes_per_step": a.batch * 32 * 8},
-        "gpu_launches": launches_per_step * a.steps,
+        "gpu_launches": int(launches) * a.steps, "queries_per_pass": qt, "passes_per_step": passes, "kernel_desc": klong,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_kind": f"of {peak_kind}",
-                     "kernel": "scan_tc" if a.vector_kernel != "ffma" else "scan_ffma", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes},
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": (ncu.get("traffic") * passes * local_rows / 1e6) if (ncu.get("traffic") and a.dims == C2_DIMS) else None,
+                     "traffic_source": ncu.get("source"), "peak_kind": f"of {peak_kind}", "kernel": kshort, "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes},
         "clocks": clocks,
+    }
+
+
+def bench_vector(a, rank, world, out):
+    from seekstorm_b200 import Index, VectorSimilarity, synth
+    from seekstorm_b200.parallel import ShardedSearcher
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ix = Index(dev.index, vector_dims=a.dims, vector_similarity=VectorSimilarity.Cosine, max_batch=max(a.batch, 16))
+    ix.set_stream(torch.cuda.current_stream().cuda_stream)
+    n_levels, mine = vector_levels(a.rows, rank, world)
+    local_rows = 0
+    for lv in mine:
+        r = gen_vector_level(lv, a.rows, a.dims, dev)
+        ix.add_vector_level(lv, r)
+        local_rows += r.shape[0]
+        del r
+    q_host = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").pin_memory()
+    q_dev = q_host.to(dev)
+    keys = torch.zeros((a.batch, 32), dtype=torch.int64, device=dev)
+    sh = ShardedSearcher(ix)
+    names = ["ffma", "tc"] if a.vector_kernel == "both" else [a.vector_kernel]
+    res = {k: measure_vector_kernel(a, ix, sh, k, q_host, q_dev, keys, local_rows, rank, world, dev, rank == 0) for k in names}
+    best = max(names, key=lambda k: res[k]["value"])      # headline = what SSB_VEC_KERNEL_AUTO picks for this batch size
+    r = res[best]
+    out.update({
+        "metric": "queries/sec at top-10 (1M x 768 f32 cosine brute-force kNN)", "value": r["value"], "unit": "queries/s",
+        "ms_per_step": r["ms_per_step"], "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2 brute-force cosine kNN: {a.rows} x {a.dims} f32, top-{TOPK}, batch {a.batch} queries/step "
+                               f"({r['passes_per_step']} corpus passes of {r['queries_per_pass']} queries)",
+                   "l2": "inputs larger than L2 (corpus %.2f GB per GPU)" % (local_rows * a.dims * 4 / 1e9),
+                   "parallelism": f"64K-row levels sharded over {world} GPU(s)", "kernel": r["kernel_desc"]},
+        "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "clocks": r["clocks"],
+        "kernels": {KERNELS[k][2] + ("" if k != "tc64" else "_n64"): {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
     })
     return ix, q_host
 

@@ -50,7 +50,7 @@ class SsbStats(C.Structure):
 EXPORTS = [
     "ssb_abi_version", "ssb_last_error", "ssb_create", "ssb_destroy", "ssb_lexical_add_level",
     "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
-    "ssb_vector_add_level", "ssb_vector_count", "ssb_search_lexical", "ssb_search_vector", "ssb_search_hybrid",
+    "ssb_vector_add_level", "ssb_vector_count", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_hybrid",
     "ssb_rrf_fuse", "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
     "ssb_stream", "ssb_set_stream", "ssb_last_stats",
 ]
@@ -83,6 +83,7 @@ def lib():
         "ssb_lexical_set_global_df": [vp, vp, vp, u64],
         "ssb_vector_add_level": [vp, u32, vp, u64, vp, u32, u32],
         "ssb_vector_count": [vp, C.POINTER(u64)],
+        "ssb_set_vector_kernel": [vp, u32],
         "ssb_search_lexical": [vp, C.POINTER(SsbLexBatch), u32, u32, vp, vp, vp],
         "ssb_search_vector": [vp, vp, u32, u32, vp, vp],
         "ssb_search_hybrid": [vp, C.POINTER(SsbLexBatch), vp, u32, vp, vp],

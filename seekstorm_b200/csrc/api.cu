@@ -240,6 +240,13 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
     return SSB_OK;
 }
 
+int32_t ssb_set_vector_kernel(ssb_index* ix, uint32_t kernel) {
+    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_N64) { set_error("bad vector kernel"); return SSB_E_INVALID; }
+    std::lock_guard<std::mutex> g(ix->mu);
+    ix->cfg.vector_kernel = kernel;
+    return SSB_OK;
+}
+
 int32_t ssb_vector_count(const ssb_index* ix, uint64_t* n) { if (!ix || !n) return SSB_E_INVALID; *n = ix->n_rows; return SSB_OK; }
 
 int32_t ssb_search_vector_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, uint64_t* keys_out_dev) {

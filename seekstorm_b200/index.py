@@ -196,6 +196,10 @@ class Index:
         for s in range(0, n, 65536):
             self.add_vector_level(first_level + s // 65536, rows[s:min(n, s + 65536)])
 
+    def set_vector_kernel(self, kernel: int):
+        """0 = auto, 1 = FP32 FFMA2 scan, 2 = tcgen05 scan (128 queries/pass), 3 = tcgen05 (64 queries/pass)."""
+        check(lib().ssb_set_vector_kernel(self._h, kernel))
+
     @property
     def vector_count(self) -> int:
         n = C.c_uint64(0)
