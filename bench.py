@@ -169,9 +169,11 @@ def gen_vector_level(level, rows, dims, device):
 KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + warp top-k)"),
            "tc": (2, 128, "scan_tc", "scan_tc (TMA + tcgen05 3xTF32 split, TMEM accumulators, TMEM-epilogue top-k)"),
            "tc64": (3, 64, "scan_tc", "scan_tc<64> (tcgen05 3xTF32, 64 queries per pass)")}
-# traffic (dram__bytes_read+write per launch) and tensor-pipe utilisation from the committed ncu captures (profiles/)
-NCU = {"scan_ffma": {"traffic": 3.08e9, "source": "profiles/r01_scan_ffma_v3.summary.txt"},
-       "scan_tc": {"traffic": 3.08e9, "source": "profiles/r01_scan_tc_v3.summary.txt"}}
+# DRAM traffic per corpus pass (dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture, divided by
+# the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
+# (3.072 GB), i.e. no re-reads.
+NCU = {"scan_ffma": {"traffic_per_pass": 24.608e9 / 8, "source": "profiles/r01_scan_ffma_v3.summary.txt"},
+       "scan_tc": {"traffic_per_pass": 3.0815e9, "source": "profiles/r01_scan_tc.summary.txt"}}
 
 
 def measure_vector_kernel(a, ix, sh, kname, q_host, q_dev, keys, local_rows, rank, world, dev, want_clocks):
@@ -221,7 +223,7 @@ def measure_vector_kernel(a, ix, sh, kname, q_host, q_dev, keys, local_rows, ran
         "gpu_launches": int(launches) * a.steps, "queries_per_pass": qt, "passes_per_step": passes, "kernel_desc": klong,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     "traffic": (ncu.get("traffic") * passes * local_rows / 1e6) if (ncu.get("traffic") and a.dims == C2_DIMS) else None,
+                     "traffic": (ncu["traffic_per_pass"] * passes * local_rows / 1e6) if (ncu and a.dims == C2_DIMS) else None,
                      "traffic_source": ncu.get("source"), "peak_kind": f"of {peak_kind}", "kernel": kshort, "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": alg_bytes},
         "clocks": clocks,
@@ -409,9 +411,7 @@ def cpu_bm25_baseline(a, seconds):
         while time.perf_counter() < stop:
             with lock:
                 j = nxt[0]; nxt[0] += 1
-            if j >= len(qk):
-                return
-            orc.search(qk[j], O.QUERY_UNION, TOPK, O.RESULT_TOPK, pruned=True)
+            orc.search(qk[j % len(qk)], O.QUERY_UNION, TOPK, O.RESULT_TOPK, pruned=True)
             done[i] += 1
     t0 = time.perf_counter()
     th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
@@ -419,7 +419,7 @@ def cpu_bm25_baseline(a, seconds):
     dt = time.perf_counter() - t0
     n = sum(done)
     return {"value": n / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-            "sample": f"{n} of the {len(qk)} C3 queries on the full {a.bm25_docs}-doc index, {cores} threads (one query each), {dt:.1f}s"}
+            "sample": f"{n} queries (cycling the {len(qk)} C3 queries) on the full {a.bm25_docs}-doc index, {cores} threads (one query each), {dt:.1f}s"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
