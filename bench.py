@@ -118,7 +118,8 @@ def dist_setup(n):
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", n))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    dist.init_process_group("nccl")
+    import datetime
+    dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=180))
     return rank, world
 
 
@@ -128,11 +129,17 @@ def timed_steps(fn, steps, warmup, world, sampler=None):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    if sampler is not None:
+    if sampler is not None and world == 1:
         t_end = time.perf_counter() + 3.0
         while not sampler.has_samples() and time.perf_counter() < t_end:
             fn()
             torch.cuda.synchronize()
+    elif world > 1:
+        # every rank must issue the same number of collectives: a FIXED number of extra untimed steps keeps the GPUs under
+        # load while rank 0's nvidia-smi sampler starts (a rank-dependent loop here deadlocks the all-gather)
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
