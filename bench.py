@@ -115,6 +115,7 @@ class ClockSampler:
 def dist_setup(n):
     if n <= 1:
         return 0, 1
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", n))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -137,7 +138,7 @@ def timed_steps(fn, steps, warmup, world, sampler=None):
     elif world > 1:
         # every rank must issue the same number of collectives: a FIXED number of extra untimed steps keeps the GPUs under
         # load while rank 0's nvidia-smi sampler starts (a rank-dependent loop here deadlocks the all-gather)
-        for _ in range(20):
+        for _ in range(100):
             fn()
         torch.cuda.synchronize()
     if world > 1:
@@ -216,7 +217,7 @@ def measure_vector_kernel(a, ix, sh, kname, q_host, q_dev, keys, local_rows, ran
         def step_e2e():
             qd = q_host.to(dev, non_blocking=True) if rank == 0 else q_dev
             dist.broadcast(qd, 0)
-            sh.search_vector(qd, TOPK)
+            sh.search_vector(qd, TOPK, raw_out=(hits_buf, nh_buf))
     ms_e2e = timed_steps(step_e2e, a.steps, a.warmup, world)
     peak, peak_kind = peaks()
     kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
@@ -371,7 +372,7 @@ def bench_bm25(a, rank, world):
         if world == 1:
             ix.search_lexical_raw(b, TOPK, ResultType.Topk, hits_buf, nh_buf, cnt_buf)   # ssb_search_lexical, host buffers
         else:
-            sh.search_lexical(b, len(qk), TOPK, ResultType.Topk, dev)
+            sh.search_lexical(b, len(qk), TOPK, ResultType.Topk, dev, raw_out=(hits_buf, nh_buf))
     ms_e2e = timed_steps(step_e2e, steps, a.warmup, world)
     st = ix.last_stats() if world == 1 else {}
     peak, peak_kind = peaks()

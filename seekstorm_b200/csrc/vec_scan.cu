@@ -248,14 +248,14 @@ void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_
     if (nq) kth_threshold<<<(nq + 127) / 128, 128, 0, st>>>(keys, nq, k, thr);
 }
 
-// Threshold pre-sampling: scan the first VEC_PRESAMPLE_ROWS rows, take each query's k-th best score there as the initial
+// Threshold pre-sampling: scan the first vec_presample_rows() rows (1/16 of the shard, 4K..32K), take each query's k-th best score there as the initial
 // threshold of the full scan.  It is the k-th best of a subset, hence a valid lower bound of the final k-th best: results
 // are unchanged, but the expected number of list insertions per query drops from ~k*ln(rows/k) PER LIST to ~k*N/S in total.
 template <class F>
 static int32_t with_presample(const ScanArgs& a, cudaStream_t st, F launch) {
-    if (a.thr_init || !a.thr_buf || a.n_rows < 4 * VEC_PRESAMPLE_ROWS) return launch(a);
+    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows) == 0) return launch(a);
     ScanArgs pre = a;
-    pre.n_rows = VEC_PRESAMPLE_ROWS; pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
+    pre.n_rows = vec_presample_rows(a.n_rows); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
     SSB_TRY(launch(pre));
     launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
     ScanArgs full = a;

@@ -27,7 +27,13 @@ struct ScanArgs {
     const uint32_t* thr_init = nullptr;            // internal: initial thresholds (ordered-uint scores) or null
 };
 
-constexpr uint64_t VEC_PRESAMPLE_ROWS = 32768;   // rows scanned first to seed the per-query top-k thresholds
+// rows scanned first to seed the per-query top-k thresholds: ~1/16 of the shard, between 4K and 32K rows (0 = too small)
+inline uint64_t vec_presample_rows(uint64_t n_rows) {
+    if (n_rows < 65536) return 0;
+    uint64_t s = n_rows / 16;
+    s = s < 4096 ? 4096 : (s > 32768 ? 32768 : s);
+    return s / 512 * 512;
+}
 
 int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);

@@ -307,6 +307,10 @@ class Index:
         return [[(int(d), float(s)) for d, s in zip(hits[i * k: i * k + int(n_hits[i])]["doc_id"],
                                                      hits[i * k: i * k + int(n_hits[i])]["score"])] for i in range(nq)]
 
+    def merge_keys_raw(self, keys_dev, n_lists: int, nq: int, k: int, hits, n_hits):
+        """ssb_merge_keys into caller-owned numpy buffers (no per-hit Python objects)."""
+        check(lib().ssb_merge_keys(self._h, _addr(keys_dev), n_lists, nq, k, hits.ctypes.data, n_hits.ctypes.data))
+
     def sync(self):
         check(lib().ssb_sync(self._h))
 

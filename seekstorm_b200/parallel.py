@@ -74,18 +74,23 @@ class ShardedSearcher:
         dist.all_gather_into_tensor(out.view(-1, keys_local.shape[-1]), keys_local.contiguous(), group=self.group)
         return out
 
-    def search_vector(self, queries_dev: torch.Tensor, k: int):
+    def search_vector(self, queries_dev: torch.Tensor, k: int, raw_out=None):
+        """raw_out = (hits structured array [nq*k], n_hits u32 [nq]) writes results there instead of building Python lists."""
         nq = int(queries_dev.shape[0])
         keys = self._buf("vec", (nq, 32), queries_dev.device)
         self.index.search_vector_keys(queries_dev, k, keys)
         allk = self.gather_keys(keys)
+        if raw_out is not None:
+            return self.index.merge_keys_raw(allk, self.world, nq, k, raw_out[0], raw_out[1])
         return self.merge_fn(allk, self.world, nq, k)
 
-    def search_lexical(self, batch_struct, nq: int, k: int, result_type, device="cuda"):
+    def search_lexical(self, batch_struct, nq: int, k: int, result_type, device="cuda", raw_out=None):
         keys = self._buf("lex", (nq, 32), device)
         counts = self._buf("cnt", (nq,), device)
         self.index.search_lexical_keys(batch_struct, k, result_type, keys, counts)
         allk = self.gather_keys(keys)
         if self.world > 1:
             dist.all_reduce(counts, group=self.group)   # result_count_total = Σ shards (search.rs:1875-1940)
+        if raw_out is not None:
+            return self.index.merge_keys_raw(allk, self.world, nq, k, raw_out[0], raw_out[1]), counts
         return self.merge_fn(allk, self.world, nq, k), counts
