@@ -375,6 +375,18 @@ def bench_bm25(a, rank, world):
             sh.search_lexical(b, len(qk), TOPK, ResultType.Topk, dev, raw_out=(hits_buf, nh_buf))
     ms_e2e = timed_steps(step_e2e, steps, a.warmup, world)
     st = ix.last_stats() if world == 1 else {}
+    # secondary modes on the same index / queries (device-resident, same timing rules): exact counts and AND
+    variants = {}
+    if world == 1:
+        for name, qt_, rt_ in (("or_topkcount", QueryType.Union, ResultType.TopkCount), ("and_topkcount", QueryType.Intersection, ResultType.TopkCount),
+                               ("and_topk", QueryType.Intersection, ResultType.Topk)):
+            bv = SsbLexBatch(len(qk), int(qt_), offs_dev.data_ptr(), keys_dev.data_ptr())
+            cnt_dev = torch.zeros(len(qk), dtype=torch.int64, device=dev)
+
+            def step_v():
+                ix.search_lexical_keys(bv, TOPK, rt_, out_keys, cnt_dev)
+            msv = timed_steps(step_v, max(2, steps // 2), 2, world)
+            variants[name] = {"value": len(qk) * max(2, steps // 2) / (msv / 1e3), "unit": "queries/s"}
     peak, peak_kind = peaks()
     kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
     alg = st.get("algorithmic_bytes")
@@ -385,7 +397,7 @@ def bench_bm25(a, rank, world):
                    "index_build_s": build_s},
         "e2e": {"value": len(qk) * steps / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(keep[0].nbytes + keep[1].nbytes), "d2h_bytes_per_step": len(qk) * (32 * 8 + 8)},
-        "gpu_launches": 3 * steps,
+        "gpu_launches": 3 * steps, "variants": variants,
         "roofline": {"bound": "hbm", "achieved": (alg / (kern_ms / 1e3) / 1e9) if (alg and kern_ms) else None, "peak": peak, "unit": "GB/s",
                      "frac": (alg / (kern_ms / 1e3) / 1e9 / peak) if (alg and kern_ms) else None, "traffic": None,
                      "peak_kind": f"of {peak_kind}", "kernel": "lex_score", "kernel_ms": kern_ms,
