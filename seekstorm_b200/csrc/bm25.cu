@@ -6,14 +6,14 @@
 //   add_result_multiterm_singlefield + get_bm25f_multiterm_singlefield  add_result.rs:3418-3706, 1429-1482
 //   MinHeap::add_topk  min_heap.rs:1193-1259
 //
-// HBM layout (built once at load, SoA):
-//   ids[]  u16 local doc ids, pay[] u16 = tf8 | doclen_byte<<8 — one entry per posting, all levels
-//          concatenated (level-major, term-major inside a level).  The doc-length byte is co-located
-//          with the posting so scoring needs no random access into the 64 KB per-level length array
-//          (the reference does that gather per candidate, add_result.rs:1437-1442).
+// HBM layout (built once at load):
+//   post[] u32 = id16 | tf8<<16 | doclen_byte<<24 — one word per posting, all levels concatenated (level-major,
+//          term-major inside a level).  The doc-length byte is co-located with the posting so scoring needs no
+//          random access into the 64 KB per-level length array (the reference does that gather per candidate,
+//          add_result.rs:1437-1442), and one load delivers id and payload.
 //   directory: sorted dict_keys -> per-term list of (level, offset, count, block-max, bitmap) entries;
-//          lists with >= 4096 postings additionally get an 8 KB bitmap + 2 KB rank index (the
-//          reference's Bitmap container threshold, compress_postinglist.rs:256-332) for O(1) probes.
+//          lists with >= 256 postings additionally get an 8 KB bitmap + 2 KB rank index for O(1) probes (the
+//          reference's Bitmap container starts at 4096, compress_postinglist.rs:256-332).
 //
 // Execution: one batch = plan kernel (per query: dictionary lookup, per-block bound = Σ idf·block-max in
 // query order, blocks sorted by bound) + a persistent scoring kernel whose warps pull (query, block) items
