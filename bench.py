@@ -257,6 +257,21 @@ def bench_vector(a, rank, world, out):
     sh = ShardedSearcher(ix)
     names = ["ffma", "tc"] if a.vector_kernel == "both" else [a.vector_kernel]
     res = {k: measure_vector_kernel(a, ix, sh, k, q_host, q_dev, keys, local_rows, rank, world, dev, rank == 0) for k in names}
+    # batch-size sweep through the reference-facing call (host buffers, AUTO kernel choice): latency at batch 1 .. 256
+    sweep = {}
+    if world == 1:
+        ix.set_vector_kernel(0)
+        for bs in (1, 8, 64, 256):
+            if bs > a.batch:
+                continue
+            qn = q_host.numpy()[:bs].copy()
+            hb, nb = ix.hits_buffer(bs * TOPK), np.zeros(bs, dtype=np.uint32)
+
+            def step_b():
+                ix.search_vector_raw(qn, TOPK, hb, nb)
+            msb = timed_steps(step_b, max(5, a.steps // 2), 2, world)
+            per = msb / max(5, a.steps // 2)
+            sweep[str(bs)] = {"ms_per_call": per, "queries_per_s": bs / (per / 1e3)}
     best = max(names, key=lambda k: res[k]["value"])      # headline = what SSB_VEC_KERNEL_AUTO picks for this batch size
     r = res[best]
     out.update({
@@ -267,6 +282,7 @@ def bench_vector(a, rank, world, out):
                    "l2": "inputs larger than L2 (corpus %.2f GB per GPU)" % (local_rows * a.dims * 4 / 1e9),
                    "parallelism": f"64K-row levels sharded over {world} GPU(s)", "kernel": r["kernel_desc"]},
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "clocks": r["clocks"],
+        "batch_sweep_e2e": sweep,
         "kernels": {KERNELS[k][2] + ("" if k != "tc64" else "_n64"): {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
     })
     return ix, q_host

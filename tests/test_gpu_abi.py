@@ -1,0 +1,149 @@
+"""GPU: the C-ABI surface beyond plain search — stats, caller-owned streams, device pointers, raw buffers,
+kernel selection, the mirrored Search::search in Vector / Hybrid mode, re-commit after adding levels."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from seekstorm_b200 import synth
+from helpers import gpu_index, oracle_index, query_keys, synth_levels
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stats_and_kernel_selection():
+    from seekstorm_b200 import Index, VectorSimilarity
+    rows = synth.gen_vectors(70000, 64, 1, "cpu").numpy()
+    q = synth.gen_vectors(50, 64, 2, "cpu").numpy()
+    ix = Index(0, vector_dims=64, vector_similarity=VectorSimilarity.Dot)
+    ix.add_vectors(rows)
+    outs = {}
+    for kern in (1, 2, 3, 0):
+        ix.set_vector_kernel(kern)
+        outs[kern] = ix.search_vector_batch(q, 10)
+        st = ix.last_stats()
+        assert st["kernel_launches"] >= 3 and st["dominant_kernel_ns"] > 0
+        assert st["h2d_bytes"] == 50 * 64 * 4 and st["d2h_bytes"] == 50 * 32 * 8
+        passes = {1: 4, 2: 1, 3: 1, 0: 1}[kern]           # 50 queries: 4 x 16, 1 x 128, 1 x 64, AUTO -> tcgen05
+        assert st["algorithmic_bytes"] == passes * 70000 * 64 * 4
+    for kern in (2, 3, 0):                                  # all kernels agree on the ids (scores within tolerance)
+        for a, b in zip(outs[1], outs[kern]):
+            assert [d for d, _ in a] == [d for d, _ in b]
+            assert np.allclose([s for _, s in a], [s for _, s in b], rtol=1e-4, atol=1e-6)
+    with pytest.raises(Exception):
+        ix.set_vector_kernel(9)
+    ix.close()
+
+
+def test_caller_stream_and_device_queries():
+    """ssb_set_stream: library work ordered on a torch stream; queries and key outputs as device pointers."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    rows = synth.gen_vectors(20000, 96, 3, "cuda")
+    q = synth.gen_vectors(24, 96, 4, "cuda")
+    ix = Index(0, vector_dims=96, vector_similarity=VectorSimilarity.Cosine)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        ix.set_stream(st.cuda_stream)
+        ix.add_vectors(rows)
+        keys = torch.zeros((24, 32), dtype=torch.int64, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ix.search_vector_keys(q, 10, keys)
+        e1.record()
+        st.synchronize()
+        assert e0.elapsed_time(e1) > 0
+        got = ix.merge_keys(keys.unsqueeze(0).contiguous(), 1, 24, 10)
+    ix.set_stream(None)
+    want = ix.search_vector_batch(q.cpu().numpy(), 10)
+    assert got == want
+    hits, nh = ix.hits_buffer(24 * 10), np.zeros(24, dtype=np.uint32)
+    ix.search_vector_raw(q, 10, hits, nh)                                   # device queries, host outputs
+    assert (nh == 10).all() and [int(d) for d in hits["doc_id"][:10]] == [d for d, _ in want[0]]
+    ix.close()
+
+
+def test_search_mirror_vector_hybrid_and_paging():
+    """Index.search (Search::search signature): Vector and Hybrid modes, offset/length, unsupported args raise."""
+    from seekstorm_b200 import Index, QueryType, ResultType, SearchMode, VectorSimilarity
+    n = 66000
+    lvs, ls = synth_levels(n, 3000, 21)
+    orc = oracle_index([l.to_numpy() for l in lvs], n, ls)
+    rows = synth.gen_vectors(n, 48, 22, "cpu").numpy()
+    ix = Index(0, vector_dims=48, vector_similarity=VectorSimilarity.Cosine)
+    for l in lvs:
+        ix.add_synth_level(l)
+    ix.commit(n, ls)
+    ix.add_vectors(rows)
+    qv = synth.gen_vectors(1, 48, 23, "cpu").numpy()[0]
+    terms = [30, 700]
+    qk = query_keys([terms])[0]
+    qs = " ".join(f"t{t}" for t in terms)
+    nrows = np.stack([O.normalize(r) for r in rows])
+    vec = O.search_vector(nrows, O.normalize(qv), 12, O.SIM_COSINE)
+    lex, tot = orc.search(qk, O.QUERY_UNION, 12, O.RESULT_TOPKCOUNT)
+    ro = ix.search(qs, list(qv), QueryType.Union, SearchMode.Vector(), False, 2, 10, ResultType.TopkCount)
+    assert [r.doc_id for r in ro.results] == [d for d, _ in vec[2:12]] and ro.result_count == 10
+    assert ro.observed_vector_count == n
+    ro = ix.search(qs, None, QueryType.Union, SearchMode.Lexical(), False, 2, 10, ResultType.TopkCount)
+    assert [(r.doc_id, np.float32(r.score)) for r in ro.results] == [(d, np.float32(s)) for d, s in lex[2:12]]
+    assert ro.result_count_total == tot
+    ro = ix.search(qs, list(qv), QueryType.Union, SearchMode.Hybrid(), False, 0, 10, ResultType.Topk)
+    lex10, _ = orc.search(qk, O.QUERY_UNION, 10, O.RESULT_TOPK)
+    want = O.rrf(lex10, vec[:10])[:10]
+    assert [r.doc_id for r in ro.results] == [d for d, _ in want]
+    ro = ix.search("+t30 +t700", None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.TopkCount)
+    a, ta = orc.search(qk, O.QUERY_INTERSECTION, 10, O.RESULT_TOPKCOUNT)           # '+' on every term -> Intersection
+    assert [r.doc_id for r in ro.results] == [d for d, _ in a] and ro.result_count_total == ta
+    ro = ix.search("t30", None, QueryType.Union, SearchMode.Lexical(), False, 0, 0, ResultType.TopkCount)
+    assert ro.results == [] and ro.result_count_total == orc.search(qk[:1], O.QUERY_UNION, 0, O.RESULT_COUNT)[1]   # length 0 -> Count
+    ro = ix.search("unknownterm", None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.TopkCount)
+    assert ro.results == [] and ro.result_count_total == 0                          # infallible: empty ResultObject
+    with pytest.raises(NotImplementedError):
+        ix.search(qs, None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.Topk, field_filter=["body"])
+    with pytest.raises(NotImplementedError):
+        ix.search('"t30 t700"', None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.Topk)
+    ix.close()
+
+
+def test_incremental_levels_recommit():
+    """Levels are immutable; adding one and committing again (new N / avgdl) must equal a fresh build."""
+    from seekstorm_b200 import QueryType, ResultType
+    lvs, ls = synth_levels(140000, 4000, 31)          # 3 levels
+    part = lvs[:2]
+    n_part = sum(l.n_docs for l in part)
+    ls_part = sum(l.len_sum_normalized for l in part)
+    ix = gpu_index([l.to_numpy() for l in part], n_part, ls_part)
+    qk = query_keys(synth.gen_queries(40, 32, 3, 3000, (2, 3), (0.5, 0.5)))
+    o1 = oracle_index([l.to_numpy() for l in part], n_part, ls_part)
+    got, cnt = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
+    for i, k in enumerate(qk):
+        assert (got[i], int(cnt[i])) == o1.search(k, O.QUERY_UNION, 10, O.RESULT_TOPKCOUNT)
+    ix.add_synth_level(lvs[2])
+    ix.commit(140000, ls)
+    o2 = oracle_index([l.to_numpy() for l in lvs], 140000, ls)
+    got, cnt = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
+    for i, k in enumerate(qk):
+        assert (got[i], int(cnt[i])) == o2.search(k, O.QUERY_UNION, 10, O.RESULT_TOPKCOUNT)
+    ix.close()
+
+
+def test_many_term_queries_generic_path():
+    """> 4 live terms take the shuffle-broadcast generic path (up to SSB_MAX_QUERY_TERMS = 16)."""
+    from seekstorm_b200 import QueryType, ResultType, SsbError
+    lvs, ls = synth_levels(80000, 2000, 41)
+    orc = oracle_index([l.to_numpy() for l in lvs], 80000, ls)
+    ix = gpu_index([l.to_numpy() for l in lvs], 80000, ls)
+    qs = synth.gen_queries(30, 42, 2, 1800, (5, 8, 12), (0.4, 0.4, 0.2))
+    qk = query_keys(qs)
+    got, cnt = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
+    for i, k in enumerate(qk):
+        want, tot = orc.search(k, O.QUERY_UNION, 10, O.RESULT_TOPKCOUNT)
+        assert [d for d, _ in got[i]] == [d for d, _ in want] and int(cnt[i]) == tot
+        assert np.allclose([s for _, s in got[i]], [s for _, s in want], rtol=1e-6)     # same query-order sums
+    got, cnt = ix.search_lexical_batch(qk[:10], QueryType.Intersection, 10, ResultType.TopkCount)
+    for i, k in enumerate(qk[:10]):
+        want, tot = orc.search(k, O.QUERY_INTERSECTION, 10, O.RESULT_TOPKCOUNT)
+        assert got[i] == want and int(cnt[i]) == tot
+    with pytest.raises(SsbError):
+        ix.search_lexical_batch([list(range(17))], QueryType.Union, 10, ResultType.Topk)
+    ix.close()
