@@ -50,7 +50,7 @@ def parse():
     p.add_argument("--bm25-docs", type=int, default=C3_DOCS)
     p.add_argument("--bm25-batch", type=int, default=4096, help="lexical queries per step")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
-    p.add_argument("--vector-kernel", default="both", choices=["both", "ffma", "tc", "tc64"],
+    p.add_argument("--vector-kernel", default="both", choices=["both", "ffma", "tc", "tc64", "tcb", "tcb64"],
                    help="FP32 FFMA2 scan, tcgen05 3xTF32 scan (128 / 64 queries per pass) or both (headline = the faster)")
     return p.parse_args()
 
@@ -176,7 +176,9 @@ def gen_vector_level(level, rows, dims, device):
 
 KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + warp top-k)"),
            "tc": (2, 128, "scan_tc", "scan_tc (TMA + tcgen05 3xTF32 split, TMEM accumulators, TMEM-epilogue top-k)"),
-           "tc64": (3, 64, "scan_tc", "scan_tc<64> (tcgen05 3xTF32, 64 queries per pass)")}
+           "tc64": (3, 64, "scan_tc", "scan_tc<64> (tcgen05 3xTF32, 64 queries per pass)"),
+           "tcb": (4, 128, "scan_tc", "scan_tc (TMA + tcgen05 3xBF16 split, TMEM accumulators, TMEM-epilogue top-k)"),
+           "tcb64": (5, 64, "scan_tc", "scan_tc<64> (tcgen05 3xBF16, 64 queries per pass)")}
 # DRAM traffic per corpus pass (dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture, divided by
 # the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
 # (3.072 GB), i.e. no re-reads.
@@ -255,7 +257,7 @@ def bench_vector(a, rank, world, out):
     q_dev = q_host.to(dev)
     keys = torch.zeros((a.batch, 32), dtype=torch.int64, device=dev)
     sh = ShardedSearcher(ix)
-    names = ["ffma", "tc"] if a.vector_kernel == "both" else [a.vector_kernel]
+    names = ["ffma", "tcb"] if a.vector_kernel == "both" else [a.vector_kernel]
     res = {k: measure_vector_kernel(a, ix, sh, k, q_host, q_dev, keys, local_rows, rank, world, dev, rank == 0) for k in names}
     # batch-size sweep through the reference-facing call (host buffers, AUTO kernel choice): latency at batch 1 .. 256
     sweep = {}
@@ -283,7 +285,8 @@ def bench_vector(a, rank, world, out):
                    "parallelism": f"64K-row levels sharded over {world} GPU(s)", "kernel": r["kernel_desc"]},
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "clocks": r["clocks"],
         "batch_sweep_e2e": sweep,
-        "kernels": {KERNELS[k][2] + ("" if k != "tc64" else "_n64"): {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
+        "kernels": {{"ffma": "scan_ffma", "tc": "scan_tc_tf32", "tc64": "scan_tc_tf32_n64", "tcb": "scan_tc_bf16", "tcb64": "scan_tc_bf16_n64"}[k]:
+                    {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
     })
     return ix, q_host
 

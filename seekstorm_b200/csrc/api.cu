@@ -27,6 +27,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 int32_t encode_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
                            uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle128) {
+    return encode_tmap_2d(out, base, 4, inner_elems, rows, row_pitch_bytes, box_inner, box_rows, swizzle128 ? 128 : 0);
+}
+
+int32_t encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner_elems, uint64_t rows,
+                       uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr; cudaDriverEntryPointQueryResult qr;
@@ -38,8 +43,9 @@ int32_t encode_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner_el
     cuuint64_t gstr[1] = {row_pitch_bytes};
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return SSB_E_CUDA; }
     return SSB_OK;
@@ -83,10 +89,10 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     // AUTO: the tensor-core scan (128 queries per corpus pass) wins from ~48 queries up; below that the FP32 scan
     // (16 queries per pass, HBM-bound) is faster.  Euclidean always takes the FP32 scan.
     uint32_t kern = ix->cfg.vector_kernel;
-    if (kern == SSB_VEC_KERNEL_AUTO) kern = nq >= 48 ? SSB_VEC_KERNEL_TCGEN05 : SSB_VEC_KERNEL_FFMA;
-    const bool use_tc = (kern == SSB_VEC_KERNEL_TCGEN05 || kern == SSB_VEC_KERNEL_TCGEN05_N64) &&
-                        ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN;
-    const uint32_t qt = !use_tc ? vec::VEC_QT : (kern == SSB_VEC_KERNEL_TCGEN05_N64 ? 64u : 128u);
+    if (kern == SSB_VEC_KERNEL_AUTO) kern = nq >= 48 ? SSB_VEC_KERNEL_TCGEN05_BF16 : SSB_VEC_KERNEL_FFMA;
+    const bool use_tc = kern >= SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN;
+    const bool tc_bf16 = kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64;
+    const uint32_t qt = !use_tc ? vec::VEC_QT : ((kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : 128u);
     const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
     SSB_TRY(ix->qpad.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
     const float* qsrc = queries;
@@ -113,7 +119,7 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
         SSB_TRY(ix->qhi.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         SSB_TRY(ix->qlo.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         a.q_hi = ix->qhi.p; a.q_lo = ix->qlo.p;
-        SSB_TRY(vec::launch_scan_tc(a, qt, ix->st));
+        SSB_TRY(vec::launch_scan_tc(a, qt, tc_bf16 ? 1 : 0, ix->st));
         ix->stats.kernel_launches += 1;
     } else {
         SSB_TRY(vec::launch_scan_ffma(a, ix->st));
@@ -241,7 +247,7 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
 }
 
 int32_t ssb_set_vector_kernel(ssb_index* ix, uint32_t kernel) {
-    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_N64) { set_error("bad vector kernel"); return SSB_E_INVALID; }
+    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_BF16_N64) { set_error("bad vector kernel"); return SSB_E_INVALID; }
     std::lock_guard<std::mutex> g(ix->mu);
     ix->cfg.vector_kernel = kernel;
     return SSB_OK;

@@ -151,6 +151,9 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 #endif  // __CUDACC__
 
 // host: encode a 2-D row-major f32 tensor map (cuTensorMapEncodeTiled resolved at runtime, no libcuda link)
+// generic 2-D row-major tensor map: elem_bytes 4 (f32) or 2 (bf16); swizzle_bytes 0 / 64 / 128
+int32_t encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner_elems, uint64_t rows,
+                       uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
 int32_t encode_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
                            uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle128);
 

@@ -37,7 +37,7 @@ inline uint64_t vec_presample_rows(uint64_t n_rows) {
 
 int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);
-int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128*/, cudaStream_t st);
+int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128*/, int bf16 /*0: 3xTF32, 1: 3xBF16*/, cudaStream_t st);
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad);
 // lists laid out [group][n_lists][qt][32] -> out [nq][32]
 // thr[q] = ordered-uint score of the k-th entry of keys[q][32] (0 if the list is shorter)

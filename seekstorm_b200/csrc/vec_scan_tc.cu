@@ -1,21 +1,28 @@
 // vec_scan_tc.cu — tensor-core variant of the brute-force vector scan (sm_100a, tcgen05 + TMEM + TMA).
 //
-// Same contract as scan_ffma (vec_scan.cu): corpus [n_rows, Dpad] f32 x a block of NQ queries -> per-CTA
+// Same contract as scan_ffma (vec_scan.cu): corpus [n_rows, Dpad] f32 x a block of NQ queries -> per-warp
 // top-32 lists, but the query x corpus contraction runs on the 5th-gen tensor cores:
-//   D[128 corpus rows, NQ queries] (f32, TMEM) += A[128 x 8] . B[NQ x 8]^T      tcgen05.mma kind::tf32
-// Each smem stage holds MT=2 corpus tiles (256 rows) against ONE query chunk, so the query operand, which is
-// re-fetched from L2 for every stage, costs half the L2->SM bandwidth (the measured limiter of the 1-tile version).
-// f32 accuracy (north-star tolerance 1e-4 on cosine scores) is kept with the 3xTF32 split
-//   a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo,   x_hi = x & 0xFFFFE000 (exactly representable in tf32),
-//   x_lo = x - x_hi (exact in f32); the dropped a_lo.b_lo term is ~2^-22 relative.
-// B_hi / B_lo are prepared once per batch in global memory; A_hi / A_lo are produced per stage in shared
+//   D[128 corpus rows, NQ queries] (f32, TMEM) += A[128 x K] . B[NQ x K]^T          tcgen05.mma.cta_group::1
+// f32-level accuracy (north-star tolerance 1e-4 on cosine scores) comes from a 3-product split
+//   a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo                (the dropped a_lo.b_lo term is second order)
+// in one of two operand precisions (template PREC):
+//   PREC_TF32 : kind::tf32, x_hi = x & 0xFFFFE000 (exactly representable in tf32, so the result does not depend on
+//               whether the tensor core truncates or rounds), x_lo = x - x_hi (exact); error ~2^-22 per product.
+//   PREC_BF16 : kind::f16 (bf16 operands, f32 accumulate), x_hi = bf16_rn(x), x_lo = bf16_rn(x - x_hi);
+//               error ~3*2^-17 per product (random sign) -> ~1e-5 relative on a 768-d score.  Operand bytes per
+//               MAC are half of tf32, and this kernel is bound by shared-memory operand traffic (measured), so the
+//               bf16 split is the faster one.
+// The query parts are prepared once per batch in global memory; the corpus parts are produced per stage in shared
 // memory by 4 "splitter" warps (the corpus is stored once, as f32 — algorithmic bytes stay n_rows*dims*4).
+// Each smem stage holds MT=2 corpus tiles (256 rows) against ONE query chunk.
 //
-// Warp roles (384 threads, 1 CTA/SM): w0 TMA producer | w1 TMEM alloc + MMA issuer | w4-7 epilogue (TMEM
-// lane quadrant = warp%4) | w8-11 splitters.  Pipelines: full/split/empty per smem stage, tfull/tempty per
+// Warp roles (512 threads, 1 CTA/SM): w0 TMA producer | w1 TMEM alloc + MMA issuer | w4-7 epilogue (TMEM
+// lane quadrant = warp%4) | w8-15 splitters (8 warps: with 4 the conversion chain of one warp per SMSP was the limiter).  Pipelines: full/split/empty per smem stage, tfull/tempty per
 // TMEM accumulator buffer (double-buffered: the epilogue of tile t overlaps the MMAs of tile t+1).
-// Epilogue: tcgen05.ld 8 query columns at a time, filter against the per-query threshold, warp-aggregated
-// push into per-query buckets, per-query sorted lists (smem) updated by warp-shuffle insertion.
+// Epilogue: tcgen05.ld 8 query columns at a time, ballot-filter against the per-query threshold (seeded by the
+// pre-sample pass, vec_scan.cu), per-warp sorted lists in the CTA's slice of the output scratch (no CTA barriers).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "vec_scan.h"
 
@@ -23,58 +30,81 @@ namespace ssb {
 namespace vec {
 
 namespace tc {
-constexpr int KC = 32;                 // floats per k-chunk = one 128-byte swizzle row
+constexpr int KC = 32;                 // floats per k-chunk = one 128-byte swizzle row of the f32 corpus tile
 constexpr int TM = 128;                // UMMA M
-constexpr int MT = 2;                  // M-tiles per stage: the B (query) chunk is fetched once per MT*128 corpus rows
+constexpr int MT = 2;                  // M-tiles per stage: the query chunk is fetched once per MT*128 corpus rows
 constexpr int TROWS = TM * MT;         // corpus rows per stage
-constexpr int A1_BYTES = TM * KC * 4;  // one 128-row swizzled tile, 16 KB
+constexpr int A1_BYTES = TM * KC * 4;  // one 128-row f32 tile, 16 KB
 constexpr int A_BYTES = MT * A1_BYTES; // 32 KB
-constexpr int THREADS = 384;
+constexpr int THREADS = 512;            // 16 warps: TMA, MMA, 2 idle, 4 epilogue, 8 splitters
+constexpr int SPLIT_THREADS = 256;
 constexpr int CHUNK = 8;               // query columns per epilogue step
+constexpr int STAGES = 2;
+enum { PREC_TF32 = 0, PREC_BF16 = 1 };
 
-template <int NQ> struct Cfg {
-    static constexpr int B_BYTES = NQ * KC * 4;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // A, A_lo, B_hi, B_lo
-    static constexpr int STAGES = 2;                                       // 2 x (64 KB A/A_lo + 2*B) 
+template <int NQ, int PREC> struct Cfg {
+    // TF32: [A (-> A_hi in place) | A_lo | B_hi | B_lo], all f32 SWIZZLE_128B tiles
+    // BF16: [A f32 | A1 bf16 | A2 bf16 | B1 bf16 | B2 bf16], bf16 tiles are 64-byte rows, SWIZZLE_64B
+    static constexpr int B_BYTES = PREC == PREC_TF32 ? NQ * KC * 4 : NQ * KC * 2;
+    static constexpr int ALO_OFF = A_BYTES;                                    // TF32: A_lo   | BF16: A1
+    static constexpr int A2_OFF = A_BYTES + A_BYTES / 2;                       // BF16: A2
+    static constexpr int B_OFF = 2 * A_BYTES;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + NQ * 4 + 256;
-    static constexpr int TMEM_COLS = 2 * MT * NQ;                          // double-buffered MT accumulators (256 / 512 columns)
+    static constexpr int TMEM_COLS = 2 * MT * NQ;                              // double-buffered MT accumulators
 };
 
+// K-major SWIZZLE_128B canonical layout ((8,n),2):((8,SBO),1) in 16-byte units: LBO = 1, SBO = 1024 B
 __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
-    // K-major, SWIZZLE_128B canonical layout ((8,n),2):((8,SBO),1) in 16-byte units: LBO = 1, SBO = 1024 B
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+// K-major SWIZZLE_64B: 64-byte rows, 8-row atom = 512 B -> SBO = 512 B, layout type 4
+__device__ __forceinline__ uint64_t umma_desc_k64(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+template <int PREC>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if (PREC == PREC_TF32)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int NQ>
+__device__ __forceinline__ uint32_t bf16x2_hi(float x, float y, float& rx, float& ry) {
+    // hi = bf16_rn(x); the residual x - hi is exact in f32
+    __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    rx = x - __low2float(h); ry = y - __high2float(h);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t bf16x2(float x, float y) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int NQ, int PREC>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
         const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*4][NQ][32]*/,
         const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/) {
-    using C = Cfg<NQ>;
-    constexpr int STAGES = C::STAGES;
-    // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for SWIZZLE_128B)
-    // and pointers derived from it stay in the shared address space (LDS/STS instead of generic LD/ST)
+    using C = Cfg<NQ, PREC>;
+    // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for the swizzled
+    // tiles) and pointers derived from it stay in the shared address space (LDS/STS instead of generic LD/ST)
     extern __shared__ __align__(1024) uint8_t base[];
     uint8_t* stage0 = base;
     // per-query sorted lists live directly in this CTA's slice of the output scratch (global, L2-resident): they are
-    // touched only on the rare candidate insert, and each query is always owned by the same warp
+    // touched only on the rare candidate insert, and each (warp, query) list is always owned by the same warp
     uint64_t* lists = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 * NQ * LIST;   // [4 epilogue warps][NQ][32]
-    float* thr_s = (float*)(base + STAGES * C::STAGE_BYTES);                  // [NQ] (used as ordered-uint thresholds)
-    uint64_t* bars = (uint64_t*)(thr_s + NQ);
+    uint32_t* thr_u = (uint32_t*)(base + STAGES * C::STAGE_BYTES);            // [NQ] ordered-uint score thresholds
+    uint64_t* bars = (uint64_t*)(thr_u + NQ);
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* split = full + STAGES;       // [STAGES]
     uint64_t* empty = split + STAGES;      // [STAGES]
@@ -86,12 +116,12 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     const uint32_t group = blockIdx.y;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&split[s], SPLIT_THREADS / 32); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < NQ; i += THREADS)   // ordered-uint thresholds, seeded by the pre-sample pass when present
-        reinterpret_cast<uint32_t*>(thr_s)[i] = thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u;
+    for (int i = threadIdx.x; i < NQ; i += THREADS)   // seeded by the pre-sample pass when present
+        thr_u[i] = thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -111,28 +141,20 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     uint8_t* st = stage0 + s * C::STAGE_BYTES;
                     mbar_wait(&empty[s], ph ^ 1u);
-#ifdef TC_DBG_NOB
-                    mbar_arrive_expect_tx(&full[s], it < (uint32_t)STAGES ? C::TX_BYTES : A_BYTES);
-#else
                     mbar_arrive_expect_tx(&full[s], C::TX_BYTES);
-#endif
                     tma_load_2d(st, &tmA, (int)(kc * KC), (int)(tile * TROWS), &full[s]);   // 256-row box = MT swizzled tiles
-#ifdef TC_DBG_NOB
-                    if (it < (uint32_t)STAGES) {
-#endif
-                    tma_load_2d(st + 2 * A_BYTES, &tmBh, (int)(kc * KC), (int)(group * NQ), &full[s]);
-                    tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmBl, (int)(kc * KC), (int)(group * NQ), &full[s]);
-#ifdef TC_DBG_NOB
-                    }
-#endif
+                    tma_load_2d(st + C::B_OFF, &tmBh, (int)(kc * KC), (int)(group * NQ), &full[s]);
+                    tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmBl, (int)(kc * KC), (int)(group * NQ), &full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (tf32 = 2, bf16 = 1), both K-major,
+            // N>>3 at bit 17, M>>4 at bit 24
+            constexpr uint32_t fmt = PREC == PREC_TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t it = 0, ti = 0;
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
                 const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
@@ -145,19 +167,33 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     mbar_wait(&split[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stage0 + s * C::STAGE_BYTES);
-                    const uint64_t a_hi = umma_desc_k128(sa), a_lo = umma_desc_k128(sa + A_BYTES);
-                    const uint64_t b_hi = umma_desc_k128(sa + 2 * A_BYTES), b_lo = umma_desc_k128(sa + 2 * A_BYTES + C::B_BYTES);
+                    if (PREC == PREC_TF32) {
+                        const uint64_t a_hi = umma_desc_k128(sa), a_lo = umma_desc_k128(sa + C::ALO_OFF);
+                        const uint64_t b_hi = umma_desc_k128(sa + C::B_OFF), b_lo = umma_desc_k128(sa + C::B_OFF + C::B_BYTES);
 #pragma unroll
-                    for (uint32_t m = 0; m < MT; m++) {
-                        const uint64_t am = (uint64_t)((m * A1_BYTES) >> 4);   // next 128-row tile of the stage
+                        for (uint32_t m = 0; m < MT; m++) {
+                            const uint64_t am = (uint64_t)((m * A1_BYTES) >> 4);   // next 128-row tile of the stage
 #pragma unroll
-                        for (uint32_t kk = 0; kk < 4; kk++) {        // 4 x K=8 (32 bytes) inside the 128-byte swizzle row
-                            const uint64_t o = (uint64_t)(kk * 2);  // +32 bytes in 16-byte units
-                            umma_tf32(d + m * NQ, a_hi + am + o, b_hi + o, idesc, (kc | kk) != 0);
-#ifndef TC_DBG_1MMA
-                            umma_tf32(d + m * NQ, a_lo + am + o, b_hi + o, idesc, 1);
-                            umma_tf32(d + m * NQ, a_hi + am + o, b_lo + o, idesc, 1);
-#endif
+                            for (uint32_t kk = 0; kk < 4; kk++) {        // 4 x K=8 (32 bytes) inside the 128-byte swizzle row
+                                const uint64_t o = (uint64_t)(kk * 2);  // +32 bytes in 16-byte units
+                                umma<PREC>(d + m * NQ, a_hi + am + o, b_hi + o, idesc, (kc | kk) != 0);
+                                umma<PREC>(d + m * NQ, a_lo + am + o, b_hi + o, idesc, 1);
+                                umma<PREC>(d + m * NQ, a_hi + am + o, b_lo + o, idesc, 1);
+                            }
+                        }
+                    } else {
+                        const uint64_t a1 = umma_desc_k64(sa + C::ALO_OFF), a2 = umma_desc_k64(sa + C::A2_OFF);
+                        const uint64_t b1 = umma_desc_k64(sa + C::B_OFF), b2 = umma_desc_k64(sa + C::B_OFF + C::B_BYTES);
+#pragma unroll
+                        for (uint32_t m = 0; m < MT; m++) {
+                            const uint64_t am = (uint64_t)((m * (A1_BYTES / 2)) >> 4);   // bf16 tile = 8 KB
+#pragma unroll
+                            for (uint32_t kk = 0; kk < 2; kk++) {        // 2 x K=16 bf16 (32 bytes) inside the 64-byte swizzle row
+                                const uint64_t o = (uint64_t)(kk * 2);
+                                umma<PREC>(d + m * NQ, a1 + am + o, b1 + o, idesc, (kc | kk) != 0);
+                                umma<PREC>(d + m * NQ, a2 + am + o, b1 + o, idesc, 1);
+                                umma<PREC>(d + m * NQ, a1 + am + o, b2 + o, idesc, 1);
+                            }
                         }
                     }
                     umma_commit(&empty[s]);                      // stage reusable once these MMAs retire
@@ -166,28 +202,48 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             }
         }
     } else if (warp >= 8) {
-        // ===================== splitters: A -> (A_hi in place, A_lo) =====================
-        const int t = threadIdx.x - 256;   // 0..127
+        // ===================== splitters: f32 corpus tile -> (hi, lo) operand tiles =====================
+        const int t = threadIdx.x - 256;   // 0..SPLIT_THREADS-1
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
                 uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&full[s], ph);
-                uint4* A = (uint4*)(stage0 + s * C::STAGE_BYTES);
-                uint4* Al = (uint4*)(stage0 + s * C::STAGE_BYTES + A_BYTES);
-#ifdef TC_DBG_NOSPLIT
-                if (false)
-#endif
+                uint8_t* st = stage0 + s * C::STAGE_BYTES;
+                if (PREC == PREC_TF32) {
+                    uint4* A = (uint4*)st;
+                    uint4* Al = (uint4*)(st + C::ALO_OFF);
 #pragma unroll
-                for (int j = 0; j < (A_BYTES / 16) / 128; j++) {
-                    uint4 x = A[t + 128 * j], h, l;
-                    h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
-                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
-                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
-                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
-                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
-                    A[t + 128 * j] = h;
-                    Al[t + 128 * j] = l;
+                    for (int j = 0; j < (A_BYTES / 16) / SPLIT_THREADS; j++) {
+                        uint4 x = A[t + SPLIT_THREADS * j], h, l;
+                        h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
+                        l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+                        l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+                        l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+                        l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+                        A[t + SPLIT_THREADS * j] = h;
+                        Al[t + SPLIT_THREADS * j] = l;
+                    }
+                } else {
+                    // unit u = (row r, 8-element group j): two float4 of the SWIZZLE_128B f32 tile -> one 16-byte chunk of
+                    // each SWIZZLE_64B bf16 tile (chunk j of row r lives at physical chunk j ^ ((r >> 1) & 3))
+                    const float4* A = (const float4*)st;
+                    uint4* A1 = (uint4*)(st + C::ALO_OFF);
+                    uint4* A2 = (uint4*)(st + C::A2_OFF);
+#pragma unroll
+                    for (int i = 0; i < (TROWS * 4) / SPLIT_THREADS; i++) {
+                        const int u = t + SPLIT_THREADS * i, r = u >> 2, j = u & 3;
+                        const float4 x = A[r * 8 + ((2 * j) ^ (r & 7))];
+                        const float4 y = A[r * 8 + ((2 * j + 1) ^ (r & 7))];
+                        float r0, r1, r2, r3, r4, r5, r6, r7;
+                        uint4 h, l;
+                        h.x = bf16x2_hi(x.x, x.y, r0, r1); h.y = bf16x2_hi(x.z, x.w, r2, r3);
+                        h.z = bf16x2_hi(y.x, y.y, r4, r5); h.w = bf16x2_hi(y.z, y.w, r6, r7);
+                        l.x = bf16x2(r0, r1); l.y = bf16x2(r2, r3); l.z = bf16x2(r4, r5); l.w = bf16x2(r6, r7);
+                        const int dst = r * 4 + (j ^ ((r >> 1) & 3));
+                        A1[dst] = h;
+                        A2[dst] = l;
+                    }
                 }
                 fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -197,12 +253,12 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     } else if (warp >= 4) {
         // ===================== epilogue: TMEM -> filter -> per-warp per-query top-k (no CTA-level barriers) =====================
         // Each epilogue warp owns the 32 TMEM lanes (= corpus rows) of its quadrant and keeps its own sorted list per
-        // query in this CTA's slice of the output scratch.  The per-query threshold (ordered-uint score of the best
-        // k-th entry any warp of the CTA has seen) is shared through smem with atomicMax: monotone, so stale reads only
-        // cost an extra insert.  (An earlier version synchronised the 4 warps with two named barriers per 8-query chunk;
-        // measured cost ~800 cycles per barrier — 40 % of the kernel.)
+        // query.  The per-query threshold (ordered-uint score of the best k-th entry any warp of the CTA has seen, seeded
+        // by the pre-sample pass) is shared through smem with atomicMax: monotone, so stale reads only cost an extra
+        // insert.  (An earlier version pushed candidates into per-query buckets with two CTA-wide named barriers per
+        // 8-query chunk and inserted them one by one: the dependent-shuffle insert chain made the epilogue, not the
+        // tensor pipe, the limiter.)
         const int ew = warp - 4;                          // == warp % 4 == TMEM lane quadrant
-        uint32_t* thr_u = reinterpret_cast<uint32_t*>(thr_s);
         uint64_t* mylists = lists + (size_t)ew * NQ * LIST;
         for (int i = lane; i < NQ * LIST; i += 32) mylists[i] = 0;
         __syncwarp();
@@ -233,7 +289,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                         if (pass) key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
                         uint64_t L = mylists[q * LIST + lane];
                         if (__popc(pm) > 3) {
-                            // bulk (warm-up tiles: every row passes): sort the 32 keys, bitonic-merge into the list
+                            // bulk (warm-up tiles: many rows pass): sort the 32 keys, bitonic-merge into the list
                             L = wl_merge(L, wl_sort_desc(key, lane), lane);
                         } else {
                             while (pm) { const int src = __ffs(pm) - 1; pm &= pm - 1; wl_insert(L, shfl64(key, src), lane); }
@@ -258,38 +314,53 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     }
 }
 
-// [nq_pad][dpad] f32 -> hi / lo tf32 parts
-__global__ void split_queries(const float* __restrict__ q, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+// [nq_pad][dpad] f32 -> hi / lo parts: tf32 (f32 containers) or bf16
+__global__ void split_queries_tf32(const float* __restrict__ q, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t x = __float_as_uint(q[i]), h = x & 0xFFFFE000u;
     hi[i] = __uint_as_float(h);
     lo[i] = __uint_as_float(x) - __uint_as_float(h);
 }
+__global__ void split_queries_bf16(const float* __restrict__ q, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = q[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
 
 }  // namespace tc
 
-template <int NQ>
+template <int NQ, int PREC>
 static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
-    using C = tc::Cfg<NQ>;
+    using C = tc::Cfg<NQ, PREC>;
     CUtensorMap tmA, tmBh, tmBl;
     uint32_t n_tiles = (uint32_t)((a.n_rows + tc::TROWS - 1) / tc::TROWS);
     uint32_t n_groups = a.nq_pad / NQ;
+    size_t nel = (size_t)a.nq_pad * a.dpad;
     SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TROWS, 1));
-    SSB_TRY(encode_tmap_2d_f32(&tmBh, a.q_hi, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
-    SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
+    if (PREC == tc::PREC_TF32) {
+        SSB_TRY(encode_tmap_2d_f32(&tmBh, a.q_hi, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
+        SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
+        tc::split_queries_tf32<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, a.q_hi, a.q_lo, nel);
+    } else {
+        // the two bf16 parts live in the q_hi / q_lo buffers (half of each is used)
+        SSB_TRY(encode_tmap_2d(&tmBh, a.q_hi, 2 /*bf16*/, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, tc::KC, NQ, 64));
+        SSB_TRY(encode_tmap_2d(&tmBl, a.q_lo, 2 /*bf16*/, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, tc::KC, NQ, 64));
+        tc::split_queries_bf16<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, (__nv_bfloat16*)a.q_hi, (__nv_bfloat16*)a.q_lo, nel);
+    }
     uint32_t gx = n_tiles < (uint32_t)a.n_sms ? n_tiles : (uint32_t)a.n_sms;
     if ((size_t)n_groups * gx * 4 * NQ * LIST * 8 > a.scratch_bytes) { set_error("vector scan scratch too small"); return SSB_E_STATE; }
     static bool attr_set = false;
     if (!attr_set) {
-        SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    size_t nel = (size_t)a.nq_pad * a.dpad;
-    tc::split_queries<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, a.q_hi, a.q_lo, nel);
     if (a.ev0) cudaEventRecord(a.ev0, st);
-    tc::scan_tc<NQ><<<dim3(gx, n_groups), tc::THREADS, C::SMEM, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, a.dpad / tc::KC, n_tiles,
-                                                                       a.k, a.doc_ids, a.scratch, a.thr_init);
+    tc::scan_tc<NQ, PREC><<<dim3(gx, n_groups), tc::THREADS, C::SMEM, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, a.dpad / tc::KC, n_tiles,
+                                                                             a.k, a.doc_ids, a.scratch, a.thr_init);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ
@@ -298,25 +369,24 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     return SSB_OK;
 }
 
-static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, cudaStream_t st);
-
-int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, cudaStream_t st) {
-    // threshold pre-sampling (see vec_scan.cu): scan the first rows, seed the thresholds, then the full scan
-    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows) == 0) return launch_scan_tc_impl(a, nq_tile, st);
-    ScanArgs pre = a;
-    pre.n_rows = vec_presample_rows(a.n_rows); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
-    SSB_TRY(launch_scan_tc_impl(pre, nq_tile, st));
-    launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
-    ScanArgs full = a;
-    full.thr_init = a.thr_buf;
-    return launch_scan_tc_impl(full, nq_tile, st);
-}
-
-static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, cudaStream_t st) {
+static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream_t st) {
     if (a.n_rows == 0 || a.nq_pad == 0) return SSB_OK;
     if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }
     if ((nq_tile != 64 && nq_tile != 128) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 scan: query count must be padded to the 64/128 query tile"); return SSB_E_INVALID; }
-    return nq_tile == 64 ? launch_tc_n<64>(a, st) : launch_tc_n<128>(a, st);
+    if (bf16) return nq_tile == 64 ? launch_tc_n<64, tc::PREC_BF16>(a, st) : launch_tc_n<128, tc::PREC_BF16>(a, st);
+    return nq_tile == 64 ? launch_tc_n<64, tc::PREC_TF32>(a, st) : launch_tc_n<128, tc::PREC_TF32>(a, st);
+}
+
+int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream_t st) {
+    // threshold pre-sampling (see vec_scan.cu): scan the first rows, seed the thresholds, then the full scan
+    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows) == 0) return launch_scan_tc_impl(a, nq_tile, bf16, st);
+    ScanArgs pre = a;
+    pre.n_rows = vec_presample_rows(a.n_rows); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
+    SSB_TRY(launch_scan_tc_impl(pre, nq_tile, bf16, st));
+    launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
+    ScanArgs full = a;
+    full.thr_init = a.thr_buf;
+    return launch_scan_tc_impl(full, nq_tile, bf16, st);
 }
 
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)nq_pad * (size_t)n_sms * 4 * LIST * 8; }

@@ -18,15 +18,15 @@ def test_stats_and_kernel_selection():
     ix = Index(0, vector_dims=64, vector_similarity=VectorSimilarity.Dot)
     ix.add_vectors(rows)
     outs = {}
-    for kern in (1, 2, 3, 0):
+    for kern in (1, 2, 3, 4, 5, 0):
         ix.set_vector_kernel(kern)
         outs[kern] = ix.search_vector_batch(q, 10)
         st = ix.last_stats()
         assert st["kernel_launches"] >= 3 and st["dominant_kernel_ns"] > 0
         assert st["h2d_bytes"] == 50 * 64 * 4 and st["d2h_bytes"] == 50 * 32 * 8
-        passes = {1: 4, 2: 1, 3: 1, 0: 1}[kern]           # 50 queries: 4 x 16, 1 x 128, 1 x 64, AUTO -> tcgen05
+        passes = {1: 4, 2: 1, 3: 1, 4: 1, 5: 1, 0: 1}[kern]   # 50 queries: 4 x 16, 1 x 128, 1 x 64, AUTO -> tcgen05
         assert st["algorithmic_bytes"] == passes * 70000 * 64 * 4
-    for kern in (2, 3, 0):                                  # all kernels agree on the ids (scores within tolerance)
+    for kern in (2, 3, 4, 5, 0):                            # all kernels agree on the ids (scores within tolerance)
         for a, b in zip(outs[1], outs[kern]):
             assert [d for d, _ in a] == [d for d, _ in b]
             assert np.allclose([s for _, s in a], [s for _, s in b], rtol=1e-4, atol=1e-6)
