@@ -183,7 +183,7 @@ KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + wa
 # the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
 # (3.072 GB), i.e. no re-reads.
 NCU = {"scan_ffma": {"traffic_per_pass": 24.608e9 / 8, "source": "profiles/r01_scan_ffma_v3.summary.txt"},
-       "scan_tc": {"traffic_per_pass": 3.0815e9, "source": "profiles/r01_scan_tc.summary.txt"}}
+       "scan_tc": {"traffic_per_pass": 3.1149e9, "source": "profiles/r01_scan_tc_bf16.summary.txt"}}
 
 
 def measure_vector_kernel(a, ix, sh, kname, q_host, q_dev, keys, local_rows, rank, world, dev, want_clocks):
