@@ -49,7 +49,7 @@ enum { SSB_SIM_DOT = 0, SSB_SIM_COSINE = 1, SSB_SIM_EUCLIDEAN = 2 };
 /* which vector scan kernel to use */
 /* FFMA: packed-FP32 scan, 16 queries per corpus pass (HBM-bound).  TCGEN05[_N64]: tensor-core scan with the 3xTF32
  * split, 128 (or 64) queries per corpus pass.  TCGEN05_BF16[_N64]: tensor-core scan with the 3xBF16 split (half the
- * operand bytes; score error ~1e-5 relative, inside the 1e-4 tolerance).  AUTO: TCGEN05_BF16 for batches of >= 48
+ * operand bytes; score error ~1e-5 relative, inside the 1e-4 tolerance).  AUTO: TCGEN05_BF16 for batches of > 16
  * Dot/Cosine queries, else FFMA; Euclidean always FFMA. */
 enum { SSB_VEC_KERNEL_AUTO = 0, SSB_VEC_KERNEL_FFMA = 1, SSB_VEC_KERNEL_TCGEN05 = 2, SSB_VEC_KERNEL_TCGEN05_N64 = 3,
        SSB_VEC_KERNEL_TCGEN05_BF16 = 4, SSB_VEC_KERNEL_TCGEN05_BF16_N64 = 5 };

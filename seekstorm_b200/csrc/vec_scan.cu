@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
           uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
           const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*CWARPS/2][QT][32]*/,
-          const uint32_t* __restrict__ thr_init /*[gridDim.y*QT] or null*/) {
+          const uint32_t* __restrict__ thr_init /*[gridDim.y*QT] or null*/, uint32_t nq_valid) {
     // no static shared memory in this kernel: the dynamic segment starts at offset 0 of the CTA window, so the
     // 1024-byte alignment SWIZZLE_128B needs holds and the pointers stay in the shared address space (LDS, not LD)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -99,7 +99,9 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         uint32_t thr[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            myL[q * LIST] = 0; thr[q] = thr_init ? __ldg(&thr_init[group * QT + qh + q]) : 0u;
+            myL[q * LIST] = 0;
+            // zero-padded query slots score 0 on every row: give them an unreachable threshold so they never insert
+            thr[q] = group * QT + qh + q >= nq_valid ? 0xFFFFFFFFu : (thr_init ? __ldg(&thr_init[group * QT + qh + q]) : 0u);
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[j][q] = make_float2(0.f, 0.f);
         }
@@ -285,7 +287,7 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
     }
     if (a.ev0) cudaEventRecord(a.ev0, st);
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
-                                            a.scratch, a.thr_init);
+                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     merge_lists<<<a.nq_pad, 256, 0, st>>>(a.scratch, n_lists, QT, a.keys_out);

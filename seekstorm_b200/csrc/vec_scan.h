@@ -15,6 +15,7 @@ struct ScanArgs {
     uint32_t dpad;                // multiple of 32
     const float* queries_padded;  // [nq_pad][dpad], nq_pad multiple of VEC_QT
     uint32_t nq_pad;
+    uint32_t nq_valid = 0;         // real queries; rows >= nq_valid are zero padding and must never collect candidates
     uint32_t k;
     uint32_t similarity;
     int n_sms;

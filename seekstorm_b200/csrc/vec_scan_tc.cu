@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
         const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*4][NQ][32]*/,
-        const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/) {
+        const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/, uint32_t nq_valid) {
     using C = Cfg<NQ, PREC>;
     // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for the swizzled
     // tiles) and pointers derived from it stay in the shared address space (LDS/STS instead of generic LD/ST)
@@ -121,7 +121,8 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < NQ; i += THREADS)   // seeded by the pre-sample pass when present
-        thr_u[i] = thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u;
+        thr_u[i] = blockIdx.y * NQ + i >= nq_valid ? 0xFFFFFFFFu   // zero-padded query slot: unreachable threshold
+                                                   : (thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -360,7 +361,7 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     }
     if (a.ev0) cudaEventRecord(a.ev0, st);
     tc::scan_tc<NQ, PREC><<<dim3(gx, n_groups), tc::THREADS, C::SMEM, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, a.dpad / tc::KC, n_tiles,
-                                                                             a.k, a.doc_ids, a.scratch, a.thr_init);
+                                                                             a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ
