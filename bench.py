@@ -46,9 +46,10 @@ def parse():
     p.add_argument("--batch", type=int, default=256, help="vector queries per step")
     p.add_argument("--rows", type=int, default=C2_ROWS)
     p.add_argument("--dims", type=int, default=C2_DIMS)
-    p.add_argument("--sections", default="vector,bm25")
+    p.add_argument("--sections", default="vector,bm25,hybrid")
     p.add_argument("--bm25-docs", type=int, default=C3_DOCS)
     p.add_argument("--bm25-batch", type=int, default=4096, help="lexical queries per step")
+    p.add_argument("--hybrid-docs", type=int, default=5_000_000)
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
     p.add_argument("--vector-kernel", default="both", choices=["both", "ffma", "tc", "tc64", "tcb", "tcb64"],
                    help="FP32 FFMA2 scan, tcgen05 3xTF32 scan (128 / 64 queries per pass) or both (headline = the faster)")
@@ -418,13 +419,52 @@ def bench_bm25(a, rank, world):
                 "h2d_bytes_per_step": int(keep[0].nbytes + keep[1].nbytes), "d2h_bytes_per_step": len(qk) * (32 * 8 + 8)},
         "gpu_launches": 3 * steps, "variants": variants,
         "roofline": {"bound": "hbm", "achieved": (alg / (kern_ms / 1e3) / 1e9) if (alg and kern_ms) else None, "peak": peak, "unit": "GB/s",
-                     "frac": (alg / (kern_ms / 1e3) / 1e9 / peak) if (alg and kern_ms) else None, "traffic": None,
+                     "frac": (alg / (kern_ms / 1e3) / 1e9 / peak) if (alg and kern_ms) else None,
+                     # dram__bytes_read+write of one ncu --set full capture of this launch shape (profiles/r01_lex_score_v2): 2.3x the
+                     # algorithmic bytes — 4-byte probes cost 32-byte sectors
+                     "traffic": 8.668e9 if (a.bm25_docs == C3_DOCS and len(qk) == 4096 and world == 1) else None,
+                     "traffic_source": "profiles/r01_lex_score_v2.summary.txt",
                      "peak_kind": f"of {peak_kind}", "kernel": "lex_score", "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": alg, "postings_visited": st.get("postings_visited"), "probes": st.get("probes"),
                      "items_processed": st.get("items_processed"), "items_skipped": st.get("items_skipped")},
     }
     ix.close()
     return res
+
+
+def bench_hybrid(a, rank, world):
+    """C4: SearchMode::Hybrid (BM25 OR top-10 + 768-d cosine top-10, RRF k=0.6) over 5M docs, 1 GPU, through
+    ssb_search_hybrid with host buffers (the RRF join runs on the host inside the library, search.rs:1962-2035)."""
+    from seekstorm_b200 import Index, QueryType, VectorSimilarity, synth
+    from seekstorm_b200._lib import check, lib
+    import ctypes as C
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_docs = a.hybrid_docs
+    ix = Index(dev.index, vector_dims=C2_DIMS, vector_similarity=VectorSimilarity.Cosine, max_batch=1024)
+    ix.set_stream(torch.cuda.current_stream().cuda_stream)
+    len_sum = 0
+    for lv in synth.gen_lexical_corpus(n_docs, C3_VOCAB, 1004, dev):
+        ix.add_synth_level(lv)
+        len_sum += lv.len_sum_normalized
+    ix.commit(n_docs, len_sum)
+    for lv in range((n_docs + 65535) // 65536):
+        ix.add_vector_level(lv, synth.gen_vectors(min(65536, n_docs - lv * 65536), C2_DIMS, 1005 * 1000 + lv, dev))
+    nq = 1000
+    qs = synth.gen_queries(nq, 2004, 20, 100000, (2, 3, 4), (0.4, 0.4, 0.2))
+    qk = [[int(k) for k in synth.term_keys_np(np.array(q, dtype=np.int64))] for q in qs]
+    b, keep = ix.make_lex_batch(qk, QueryType.Union)
+    qv = synth.gen_vectors(nq, C2_DIMS, 2005, "cpu").numpy()
+    hits, nh = ix.hits_buffer(nq * TOPK), np.zeros(nq, dtype=np.uint32)
+
+    def step():
+        check(lib().ssb_search_hybrid(ix._h, C.byref(b), qv.ctypes.data, TOPK, hits.ctypes.data, nh.ctypes.data))
+    steps = max(3, a.steps // 4)
+    ms = timed_steps(step, steps, 2, world)
+    ix.close()
+    return {"metric": "queries/sec at top-10 (hybrid: BM25 OR + 768-d cosine, RRF)", "value": nq * steps / (ms / 1e3), "unit": "queries/s",
+            "ms_per_step": ms / steps, "steps": steps,
+            "config": {"workload": f"C4 hybrid: {n_docs} docs (Zipf lexical index + {n_docs} x {C2_DIMS} f32 vectors), {nq} queries/step, e2e through ssb_search_hybrid (host buffers)"},
+            "h2d_bytes_per_step": int(qv.nbytes + keep[0].nbytes + keep[1].nbytes), "d2h_bytes_per_step": nq * 32 * 16}
 
 
 def cpu_bm25_baseline(a, seconds):
@@ -508,6 +548,12 @@ def main():
             out["bm25"] = bench_bm25(a, rank, world)
         except Exception as e:  # pragma: no cover
             out["bm25"] = {"error": repr(e)}
+    if "hybrid" in sections and world == 1:
+        torch.cuda.empty_cache()
+        try:
+            out["hybrid"] = bench_hybrid(a, rank, world)
+        except Exception as e:  # pragma: no cover
+            out["hybrid"] = {"error": repr(e)}
     if rank == 0 and world == 1 and a.cpu_seconds > 0:
         torch.cuda.empty_cache()
         try:
