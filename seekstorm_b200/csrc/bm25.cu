@@ -40,6 +40,18 @@ constexpr uint32_t DENSE_MIN = 256;    // lists at least this long get a bitmap 
 constexpr uint32_t MAX_LEVELS = 4096;  // per GPU (268M docs); plan kernel smem bound
 
 // ================================================================= build kernels
+// posting i belongs to the term whose offset range contains it (binary search over posting_offsets)
+__global__ void validate_level(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs, const uint32_t* __restrict__ offs,
+                               uint32_t n_terms, uint32_t n, uint32_t n_docs, uint32_t* bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t lo = 0, hi = n_terms;                     // term t with offs[t] <= i < offs[t+1]
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (offs[m + 1] <= i) lo = m + 1; else hi = m; }
+    bool ok = lo < n_terms && ids[i] < n_docs && tfs[i] >= 1;
+    if (ok && i > offs[lo] && ids[i] <= ids[i - 1]) ok = false;
+    if (!ok) atomicAdd(bad, 1u);
+}
+
 __global__ void build_payload(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs,
                               const uint8_t* __restrict__ len_bytes, uint32_t* __restrict__ post, uint32_t n,
                               uint64_t post_base, uint64_t* exc_pos, uint32_t* exc_tf, uint32_t* exc_count,
@@ -703,14 +715,20 @@ int32_t LexIndex::add_level(const ssb_level_desc* d) {
     else SSB_CUDA_TRY(cudaMemsetAsync(l.d_posting_offsets, 0, 4, st_));
     SSB_TRY(post_.reserve(n_post_ + np + 8, n_post_, st_));
     // posting word = id16 | tf8<<16 | len8<<24 (needs ids, tfs and the level's length bytes on the device)
-    uint16_t* d_ids = nullptr; uint16_t* d_tfs = nullptr; uint8_t* d_len = nullptr; bool own_ids = false, own_tfs = false, own_len = false;
+    uint16_t* d_ids = nullptr; uint16_t* d_tfs = nullptr; uint8_t* d_len = nullptr;
+    DevTmp<uint16_t> t_ids, t_tfs; DevTmp<uint8_t> t_len; DevTmp<uint32_t> t_bad;
     if (np) {
         if (is_device_ptr(d->doc_ids)) d_ids = const_cast<uint16_t*>(d->doc_ids);
-        else { SSB_CUDA_TRY(cudaMalloc(&d_ids, (size_t)np * 2)); own_ids = true; SSB_CUDA_TRY(to_device(d_ids, d->doc_ids, (size_t)np * 2, st_)); }
+        else { SSB_CUDA_TRY(t_ids.alloc(np)); d_ids = t_ids.p; SSB_CUDA_TRY(to_device(d_ids, d->doc_ids, (size_t)np * 2, st_)); }
         if (is_device_ptr(d->tfs)) d_tfs = const_cast<uint16_t*>(d->tfs);
-        else { SSB_CUDA_TRY(cudaMalloc(&d_tfs, (size_t)np * 2)); own_tfs = true; SSB_CUDA_TRY(to_device(d_tfs, d->tfs, (size_t)np * 2, st_)); }
+        else { SSB_CUDA_TRY(t_tfs.alloc(np)); d_tfs = t_tfs.p; SSB_CUDA_TRY(to_device(d_tfs, d->tfs, (size_t)np * 2, st_)); }
         if (is_device_ptr(d->doc_len_bytes)) d_len = const_cast<uint8_t*>(d->doc_len_bytes);
-        else { SSB_CUDA_TRY(cudaMalloc(&d_len, d->n_docs)); own_len = true; SSB_CUDA_TRY(to_device(d_len, d->doc_len_bytes, d->n_docs, st_)); }
+        else { SSB_CUDA_TRY(t_len.alloc(d->n_docs)); d_len = t_len.p; SSB_CUDA_TRY(to_device(d_len, d->doc_len_bytes, d->n_docs, st_)); }
+        // input contract: ids ascending and unique inside a term, < n_docs, tf >= 1 (a violated contract would make the
+        // scoring kernel read out of bounds or mis-rank silently)
+        SSB_CUDA_TRY(t_bad.alloc(1)); SSB_CUDA_TRY(cudaMemsetAsync(t_bad.p, 0, 4, st_));
+        validate_level<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, l.d_posting_offsets, d->n_terms, np, d->n_docs, t_bad.p);
+        SSB_CUDA_TRY(cudaGetLastError());
         const uint32_t exc_cap = 1u << 20;
         if (!d_exc_count_) {
             SSB_CUDA_TRY(cudaMalloc(&d_exc_count_, 4)); SSB_CUDA_TRY(cudaMemsetAsync(d_exc_count_, 0, 4, st_));
@@ -721,9 +739,15 @@ int32_t LexIndex::add_level(const ssb_level_desc* d) {
         SSB_CUDA_TRY(cudaGetLastError());
     }
     SSB_CUDA_TRY(cudaStreamSynchronize(st_));
-    if (own_ids) cudaFree(d_ids);
-    if (own_tfs) cudaFree(d_tfs);
-    if (own_len) cudaFree(d_len);
+    if (np) {
+        uint32_t bad = 0;
+        SSB_CUDA_TRY(cudaMemcpy(&bad, t_bad.p, 4, cudaMemcpyDeviceToHost));
+        if (bad) {
+            cudaFree(l.d_term_keys); cudaFree(l.d_posting_offsets);
+            set_error("add_level %u: malformed postings (%u violations: ids must ascend strictly inside a term and be < n_docs, tf >= 1)", d->level_id, bad);
+            return SSB_E_INVALID;
+        }
+    }
     n_post_ += np;
     levels_.push_back(l);
     committed_ = false;
@@ -788,9 +812,10 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     }
 
     size_t alloc_n = total ? total : 1;
-    uint64_t *d_keys = nullptr, *d_vals = nullptr, *d_lbase = nullptr; const uint32_t** d_loffs = nullptr;
-    SSB_CUDA_TRY(cudaMalloc(&d_keys, alloc_n * 8)); SSB_CUDA_TRY(cudaMalloc(&d_vals, alloc_n * 8));
-    SSB_CUDA_TRY(cudaMalloc(&d_lbase, lbase.size() * 8)); SSB_CUDA_TRY(cudaMalloc(&d_loffs, loffs.size() * sizeof(void*)));
+    DevTmp<uint64_t> t_keys, t_vals, t_lbase, t_ukeys; DevTmp<const uint32_t*> t_loffs; DevTmp<uint32_t> t_epc, t_df;
+    SSB_CUDA_TRY(t_keys.alloc(alloc_n)); SSB_CUDA_TRY(t_vals.alloc(alloc_n));
+    SSB_CUDA_TRY(t_lbase.alloc(lbase.size())); SSB_CUDA_TRY(t_loffs.alloc(loffs.size()));
+    uint64_t *d_keys = t_keys.p, *d_vals = t_vals.p, *d_lbase = t_lbase.p; const uint32_t** d_loffs = t_loffs.p;
     SSB_CUDA_TRY(cudaMemcpyAsync(d_lbase, lbase.data(), lbase.size() * 8, cudaMemcpyHostToDevice, st_));
     SSB_CUDA_TRY(cudaMemcpyAsync(d_loffs, loffs.data(), loffs.size() * sizeof(void*), cudaMemcpyHostToDevice, st_));
     uint32_t pos = 0;
@@ -809,8 +834,8 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     SSB_CUDA_TRY(cudaGetLastError());
 
     // dictionary: unique keys, entries per term, df per term
-    uint64_t* d_ukeys = nullptr; uint32_t *d_epc = nullptr, *d_df = nullptr;
-    SSB_CUDA_TRY(cudaMalloc(&d_ukeys, alloc_n * 8)); SSB_CUDA_TRY(cudaMalloc(&d_epc, (alloc_n + 1) * 4)); SSB_CUDA_TRY(cudaMalloc(&d_df, alloc_n * 4));
+    SSB_CUDA_TRY(t_ukeys.alloc(alloc_n)); SSB_CUDA_TRY(t_epc.alloc(alloc_n + 1)); SSB_CUDA_TRY(t_df.alloc(alloc_n));
+    uint64_t* d_ukeys = t_ukeys.p; uint32_t *d_epc = t_epc.p, *d_df = t_df.p;
     uint32_t nt = 0;
     if (total) {
         auto e1 = thrust::reduce_by_key(pol, thrust::device_ptr<uint64_t>(d_keys), thrust::device_ptr<uint64_t>(d_keys + total),
@@ -831,7 +856,6 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     SSB_CUDA_TRY(cudaMemcpyAsync(h_dict_keys_.data(), d_dict_keys_, (size_t)nt * 8, cudaMemcpyDeviceToHost, st_));
     SSB_CUDA_TRY(cudaMemcpyAsync(h_term_df_.data(), d_term_df_, (size_t)nt * 4, cudaMemcpyDeviceToHost, st_));
     SSB_CUDA_TRY(cudaStreamSynchronize(st_));
-    cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_lbase); cudaFree(d_loffs); cudaFree(d_ukeys); cudaFree(d_epc); cudaFree(d_df);
     {   // idf on the host (same libm as the oracle)
         std::vector<float> idf(nt_alloc);
         for (uint32_t t = 0; t < nt; t++) idf[t] = host_idf(n_docs, h_term_df_[t]);
@@ -842,8 +866,9 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     // bitmaps for dense lists
     n_bitmaps_ = 0;
     if (total) {
-        uint32_t *d_flags = nullptr, *d_scan = nullptr;
-        SSB_CUDA_TRY(cudaMalloc(&d_flags, alloc_n * 4)); SSB_CUDA_TRY(cudaMalloc(&d_scan, alloc_n * 4));
+        DevTmp<uint32_t> t_flags, t_scan, t_dense;
+        SSB_CUDA_TRY(t_flags.alloc(alloc_n)); SSB_CUDA_TRY(t_scan.alloc(alloc_n));
+        uint32_t *d_flags = t_flags.p, *d_scan = t_scan.p;
         mark_dense<<<(total + 255) / 256, 256, 0, st_>>>(d_e_count_, total, d_flags);
         thrust::exclusive_scan(pol, thrust::device_ptr<uint32_t>(d_flags), thrust::device_ptr<uint32_t>(d_flags + total), thrust::device_ptr<uint32_t>(d_scan));
         uint32_t last_flag = 0, last_scan = 0;
@@ -856,16 +881,14 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
         if (n_bitmaps_) {
             SSB_CUDA_TRY(cudaMalloc(&d_bm_words_, (size_t)n_bitmaps_ * 1024 * 8));
             SSB_CUDA_TRY(cudaMalloc(&d_bm_rank_, (size_t)n_bitmaps_ * 1024 * 2));
-            uint32_t* d_dense = nullptr;
-            SSB_CUDA_TRY(cudaMalloc(&d_dense, (size_t)n_bitmaps_ * 4));
+            SSB_CUDA_TRY(t_dense.alloc(n_bitmaps_));
+            uint32_t* d_dense = t_dense.p;
             compact_dense<<<(total + 255) / 256, 256, 0, st_>>>(d_e_bitmap_, total, d_dense);
             build_bitmaps<<<n_bitmaps_, 256, 0, st_>>>(d_e_bitmap_, d_e_off_, d_e_count_, total, post_.p, d_bm_words_, d_bm_rank_, d_dense);
             SSB_CUDA_TRY(cudaGetLastError());
             SSB_CUDA_TRY(cudaStreamSynchronize(st_));
-            cudaFree(d_dense);
         }
         SSB_CUDA_TRY(cudaStreamSynchronize(st_));
-        cudaFree(d_flags); cudaFree(d_scan);
     }
 
     committed_ = true;   // view() is usable from here

@@ -38,6 +38,17 @@ struct DevBuf {
     }
 };
 
+// scoped device temporary (freed on every exit path, including SSB_CUDA_TRY early returns)
+template <typename T>
+struct DevTmp {
+    T* p = nullptr;
+    DevTmp() = default;
+    DevTmp(const DevTmp&) = delete;
+    DevTmp& operator=(const DevTmp&) = delete;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+};
+
 struct LexLevel {
     uint32_t level_id, n_docs, n_terms;
     uint64_t post_base;            // offset of this level's postings in the arenas

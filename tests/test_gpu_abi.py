@@ -147,3 +147,21 @@ def test_many_term_queries_generic_path():
     with pytest.raises(SsbError):
         ix.search_lexical_batch([list(range(17))], QueryType.Union, 10, ResultType.Topk)
     ix.close()
+
+
+def test_add_level_rejects_malformed_postings():
+    """Input contract of ssb_lexical_add_level is validated on the device (status code, not UB)."""
+    from seekstorm_b200 import Index, SsbError
+    from helpers import level_from_postings
+    ix = Index(0)
+    good = level_from_postings(0, 50, {"a": [(1, 1), (5, 2), (9, 1)], "b": [(5, 3)]}, [10] * 50)
+    for bad_post in ({"a": [(5, 1), (1, 2)]},            # ids not ascending
+                     {"a": [(3, 1), (3, 1)]},            # duplicate id
+                     {"a": [(60, 1)]},                   # id >= n_docs
+                     {"a": [(2, 0)]}):                   # tf = 0
+        lv = level_from_postings(0, 50, bad_post, [10] * 50)
+        with pytest.raises(SsbError, match="malformed"):
+            ix.add_lexical_level(lv["level_id"], lv["n_docs"], lv["term_keys"], lv["posting_offsets"], lv["doc_ids"], lv["tfs"], lv["doc_len_bytes"])
+    ix.add_lexical_level(good["level_id"], good["n_docs"], good["term_keys"], good["posting_offsets"], good["doc_ids"], good["tfs"], good["doc_len_bytes"])
+    ix.commit(50, 500)
+    ix.close()
