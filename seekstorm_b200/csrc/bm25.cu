@@ -389,49 +389,42 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
             for (uint32_t t = 0; t < FAST_T; t++) if (t < n && pos[t] >= p) S = __fadd_rn(S, ub[t]);
             if (ord_f32(S) < thr) break;
             st_visited += dcnt;
+            // R = in-query-order sum of the bounds of the later-ranked (not yet driven) terms.  The per-posting filter is
+            // (approx(cd) + R) * (1 + 2e-6) >= theta: cheap (no IEEE divide, no per-term loop) and still a strict upper bound
+            // of the exact in-order score — the inflation covers the approximate reciprocal (<= 2 ulp) and the different
+            // association of <= 4 additions (<= 3 ulp).  Survivors are re-scored exactly below.
+            float R = 0.f;
+#pragma unroll
+            for (uint32_t t = 0; t < FAST_T; t++) if (t < n && t != drv && pos[t] > p) R = __fadd_rn(R, ub[t]);
+            const float didf_k = didf * v.k1p;
             uint32_t pd_next = (uint32_t)lane < dcnt ? __ldg(&v.post[doff + lane]) : 0u;
-            for (uint32_t base = 0; base < dcnt; base += 32u * SSB_LEX_U) {
+            for (uint32_t base = 0; base < dcnt; base += 32u) {
                 // software pipelining: the next chunk's postings are requested before this chunk is processed
-                uint32_t pdv[SSB_LEX_U];
-                pdv[0] = pd_next;
-                { const uint32_t pn = base + 32u * SSB_LEX_U + lane; pd_next = pn < dcnt ? __ldg(&v.post[doff + pn]) : 0u; }
+                const uint32_t pd = pd_next;
+                { const uint32_t pn = base + 32u + lane; pd_next = pn < dcnt ? __ldg(&v.post[doff + pn]) : 0u; }
+                const uint32_t pp = base + lane;
+                const bool active = pp < dcnt;
+                const uint32_t d = pd & 0xFFFFu;
+                const uint32_t tf8 = (pd >> 16) & 255u;
+                const float tfb = tf8 == 255u ? 65535.f : (float)tf8;                 // overflowed tf: bound with the u16 maximum
+                const float cdb = didf_k * __fdividef(tfb, tfb + __ldg(&v.cache[pd >> 24]));
+                bool alive = active && ord_f32((cdb + R) * 1.000002f) >= thr;
+                if (!__any_sync(FULL, alive)) continue;
+                // ---- survivors: exact contribution, probes, exact in-order score ----
+                const float cd = alive ? __fmul_rn(didf, comp_of(v, pd >> 16, doff + pp)) : 0.f;
+                float score = 0.f;
 #pragma unroll
-                for (int u = 1; u < SSB_LEX_U; u++) {
-                    const uint32_t pp = base + 32u * u + lane;
-                    pdv[u] = pp < dcnt ? __ldg(&v.post[doff + pp]) : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < SSB_LEX_U; u++) {
-                    if (base + 32u * u >= dcnt) break;
-                    const uint32_t pp = base + 32u * u + lane;
-                    const bool active = pp < dcnt;
-                    const uint32_t pd = pdv[u];
-                    const uint32_t d = pd & 0xFFFFu;
-                    const float cd = __fmul_rn(didf, comp_of(v, pd >> 16, doff + pp));
-                    // candidate bound: own contribution + bounds of the later-ranked terms, summed in query order
-                    float Sc = 0.f;
-#pragma unroll
-                    for (uint32_t t = 0; t < FAST_T; t++) {
-                        if (t >= n) continue;
-                        if (t == drv) Sc = __fadd_rn(Sc, cd);
-                        else if (pos[t] > p) Sc = __fadd_rn(Sc, ub[t]);
+                for (uint32_t t = 0; t < FAST_T; t++) {      // query order
+                    if (t >= n) continue;
+                    if (t == drv) { score = __fadd_rn(score, cd); continue; }
+                    if (!alive || cnt[t] == 0) continue;
+                    uint32_t rank; st_probes++;
+                    if (probe(v, cnt[t], off[t], bmi[t], d, rank)) {
+                        if (pos[t] < p) alive = false;        // already emitted when that term was the driver
+                        else score = __fadd_rn(score, term_score(v, idf[t], off[t] + rank));
                     }
-                    bool alive = active && ord_f32(Sc) >= thr;
-                    if (!__any_sync(FULL, alive)) continue;
-                    float score = 0.f;
-#pragma unroll
-                    for (uint32_t t = 0; t < FAST_T; t++) {      // query order
-                        if (t >= n) continue;
-                        if (t == drv) { score = __fadd_rn(score, cd); continue; }
-                        if (!alive || cnt[t] == 0) continue;
-                        uint32_t rank; st_probes++;
-                        if (probe(v, cnt[t], off[t], bmi[t], d, rank)) {
-                            if (pos[t] < p) alive = false;        // already emitted when that term was the driver
-                            else score = __fadd_rn(score, term_score(v, idf[t], off[t] + rank));
-                        }
-                    }
-                    insert_candidates(L, thr, alive && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
                 }
+                insert_candidates(L, thr, alive && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
             }
         }
     }
