@@ -34,7 +34,8 @@ extern "C" {
 #endif
 
 #define SSB_ABI_VERSION 1
-#define SSB_K_MAX 32u            /* top-k capacity of the fused kernels (lane-distributed lists)        */
+#define SSB_K_MAX 32u            /* top-k capacity of one kernel pass (lane-distributed lists); *_keys calls */
+#define SSB_K_LIMIT 1024u        /* ssb_search_lexical / ssb_search_vector page beyond 32 internally         */
 #define SSB_MAX_QUERY_TERMS 16u  /* unique terms per lexical query                                        */
 
 enum { SSB_OK = 0, SSB_E_INVALID = -1, SSB_E_CUDA = -2, SSB_E_NOMEM = -3, SSB_E_STATE = -4,

@@ -74,7 +74,8 @@ struct ssb_index {
     DevBuf<uint32_t> doc_ids;
     uint64_t n_rows = 0;
     // query workspace
-    DevBuf<float> qpad; DevBuf<float> qstage; DevBuf<float> qhi, qlo; DevBuf<uint64_t> scratch; DevBuf<uint64_t> keys_a, keys_b, counts;
+    DevBuf<float> qpad; DevBuf<float> qstage; DevBuf<float> qhi, qlo; DevBuf<uint64_t> ceil;
+    std::vector<uint64_t> h_ceil; DevBuf<uint64_t> scratch; DevBuf<uint64_t> keys_a, keys_b, counts;
     std::vector<uint64_t> h_keys_a, h_keys_b, h_counts;
     ssb_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_used = false;
@@ -82,7 +83,8 @@ struct ssb_index {
 
 namespace {
 
-int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, uint64_t* keys_out_dev /*[nq_pad][32] min*/) {
+int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, uint64_t* keys_out_dev /*[nq_pad][32] min*/,
+                 const uint64_t* ceil_dev = nullptr /*[>= nq_pad] paging ceilings*/) {
     if (ix->dims == 0) { set_error("no vector index configured (vector_dims = 0)"); return SSB_E_STATE; }
     if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
     if (nq == 0) return SSB_OK;
@@ -115,6 +117,7 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     uint64_t* merged = ix->scratch.p + sb / 8;   // [nq_pad][32]
     a.keys_out = merged; a.ev0 = ix->ev0; a.ev1 = ix->ev1; ix->ev_used = true;
     a.thr_buf = reinterpret_cast<uint32_t*>(merged + (size_t)nq_pad * LIST);
+    a.ceil_keys = ceil_dev;
     if (use_tc) {
         SSB_TRY(ix->qhi.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         SSB_TRY(ix->qlo.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
@@ -145,6 +148,45 @@ void decode_keys(const uint64_t* keys, uint32_t nq, uint32_t k, ssb_hit* hits, u
         if (n_hits) n_hits[q] = n;
     }
 }
+
+// Paging state of the host-facing search calls (k > SSB_K_MAX).
+struct PageState {
+    ssb_index* ix; uint32_t nq, k; ssb_hit* hits; uint32_t* n_hits; std::vector<uint32_t> cnt;
+    PageState(ssb_index* ix_, uint32_t nq_, uint32_t k_, ssb_hit* h, uint32_t* n) : ix(ix_), nq(nq_), k(k_), hits(h), n_hits(n), cnt(nq_, 0) {
+        ix->h_ceil.assign((size_t)nq_ + 256, 0);
+    }
+    // append up to kk keys per query from a [nq][32] page; returns true if any query may have more results
+    bool append(const uint64_t* keys, uint32_t done, uint32_t kk) {
+        bool more = false;
+        for (uint32_t q = 0; q < nq; q++) {
+            if (cnt[q] < done) { ix->h_ceil[q] = 0; continue; }         // exhausted on an earlier page
+            uint32_t n = 0; uint64_t last = 0;
+            for (uint32_t j = 0; j < kk; j++) {
+                const uint64_t key = keys[(size_t)q * LIST + j];
+                if (!key) break;
+                ssb_hit& h = hits[(size_t)q * k + cnt[q] + n];
+                h.doc_id = key_doc(key); h.score = key_score(key); h.pad = 0;
+                last = key; n++;
+            }
+            cnt[q] += n;
+            ix->h_ceil[q] = n == kk ? last : 0;                           // 0 = nothing left below
+            more = more || n == kk;
+        }
+        return more;
+    }
+    int32_t upload_ceilings() {
+        SSB_TRY(ix->ceil.reserve((size_t)nq + 256, 0, ix->st));
+        SSB_CUDA_TRY(cudaMemcpyAsync(ix->ceil.p, ix->h_ceil.data(), ((size_t)nq + 256) * 8, cudaMemcpyHostToDevice, ix->st));
+        ix->stats.h2d_bytes += (uint64_t)nq * 8;
+        return SSB_OK;
+    }
+    void finish() {
+        for (uint32_t q = 0; q < nq; q++) {
+            for (uint32_t j = cnt[q]; j < k; j++) { ssb_hit& h = hits[(size_t)q * k + j]; h.doc_id = 0; h.score = 0.f; h.pad = 0; }
+            if (n_hits) n_hits[q] = cnt[q];
+        }
+    }
+};
 
 inline bool hit_better(const ssb_hit& a, const ssb_hit& b) { return a.score > b.score || (a.score == b.score && a.doc_id < b.doc_id); }
 
@@ -187,7 +229,7 @@ int32_t ssb_destroy(ssb_index* ix) {
     cudaSetDevice(ix->cfg.device);
     cudaStreamSynchronize(ix->st);
     delete ix->lex;
-    ix->rows.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->qhi.release(); ix->qlo.release(); ix->scratch.release();
+    ix->rows.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->qhi.release(); ix->qlo.release(); ix->ceil.release(); ix->scratch.release();
     ix->keys_a.release(); ix->keys_b.release(); ix->counts.release();
     cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1);
     cudaStreamDestroy(ix->own_st);
@@ -269,13 +311,22 @@ int32_t ssb_search_vector(ssb_index* ix, const float* queries, uint32_t nq, uint
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     ix->stats = ssb_stats{};
     if (nq == 0) return SSB_OK;
+    if (k == 0 || k > SSB_K_LIMIT) { set_error("k must be in 1..%u", SSB_K_LIMIT); return SSB_E_UNSUPPORTED; }
     SSB_TRY(ix->keys_a.reserve((size_t)nq * LIST, 0, ix->st));
-    SSB_TRY(vec_keys(ix, queries, nq, k, ix->keys_a.p));
     ix->h_keys_a.resize((size_t)nq * LIST);
-    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
-    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-    ix->stats.d2h_bytes += (uint64_t)nq * LIST * 8;
-    decode_keys(ix->h_keys_a.data(), nq, k, hits, n_hits);
+    PageState ps(ix, nq, k, hits, n_hits);
+    // the fused kernels keep 32 results per query; longer result lists are produced page by page, each page restricted to
+    // keys strictly below the last key of the previous one (keys are a total order on (score desc, doc id asc))
+    for (uint32_t done = 0; done < k; done += SSB_K_MAX) {
+        const uint32_t kk = k - done < SSB_K_MAX ? k - done : SSB_K_MAX;
+        SSB_TRY(vec_keys(ix, queries, nq, kk, ix->keys_a.p, done ? ix->ceil.p : nullptr));
+        SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
+        SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+        ix->stats.d2h_bytes += (uint64_t)nq * LIST * 8;
+        if (!ps.append(ix->h_keys_a.data(), done, kk) || done + kk >= k) break;
+        SSB_TRY(ps.upload_ceilings());
+    }
+    ps.finish();
     return SSB_OK;
 }
 
@@ -297,16 +348,32 @@ int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, ui
     ix->stats = ssb_stats{};
     const uint32_t nq = q->n_queries;
     if (nq == 0) return SSB_OK;
+    if (k > SSB_K_LIMIT) { set_error("k=%u exceeds SSB_K_LIMIT=%u", k, SSB_K_LIMIT); return SSB_E_UNSUPPORTED; }
     SSB_TRY(ix->keys_a.reserve((size_t)nq * LIST, 0, ix->st));
     SSB_TRY(ix->counts.reserve(nq, 0, ix->st));
-    SSB_TRY(ix->lex->search_keys(q, k, result_type, ix->keys_a.p, ix->counts.p, &ix->stats.kernel_launches));
     ix->h_keys_a.resize((size_t)nq * LIST); ix->h_counts.resize(nq);
+    const bool want_hits = hits && k && result_type != SSB_RESULT_COUNT;
+    const uint32_t k1 = k < SSB_K_MAX ? k : SSB_K_MAX;
+    SSB_TRY(ix->lex->search_keys(q, k1, result_type, ix->keys_a.p, ix->counts.p, &ix->stats.kernel_launches));
     SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
     SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_counts.data(), ix->counts.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->st));
     SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
     ix->stats.d2h_bytes += (uint64_t)nq * (LIST * 8 + 8);
-    if (hits && k && result_type != SSB_RESULT_COUNT) decode_keys(ix->h_keys_a.data(), nq, k, hits, n_hits);
-    else if (n_hits) for (uint32_t i = 0; i < nq; i++) n_hits[i] = 0;
+    if (want_hits) {
+        PageState ps(ix, nq, k, hits, n_hits);
+        bool more = ps.append(ix->h_keys_a.data(), 0, k1);
+        // pages beyond the first 32 results: Topk search restricted to keys below the previous page's last key
+        for (uint32_t done = k1; more && done < k; done += SSB_K_MAX) {
+            const uint32_t kk = k - done < SSB_K_MAX ? k - done : SSB_K_MAX;
+            SSB_TRY(ps.upload_ceilings());
+            SSB_TRY(ix->lex->search_keys(q, kk, SSB_RESULT_TOPK, ix->keys_a.p, nullptr, &ix->stats.kernel_launches, ix->ceil.p));
+            SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
+            SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+            ix->stats.d2h_bytes += (uint64_t)nq * LIST * 8;
+            more = ps.append(ix->h_keys_a.data(), done, kk);
+        }
+        ps.finish();
+    } else if (n_hits) for (uint32_t i = 0; i < nq; i++) n_hits[i] = 0;
     if (count_total) for (uint32_t i = 0; i < nq; i++) count_total[i] = ix->h_counts[i];
     LexStats ls = ix->lex->last_stats();
     ix->stats.postings_visited = ls.postings_visited;

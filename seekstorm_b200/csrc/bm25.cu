@@ -292,14 +292,14 @@ __device__ __forceinline__ float term_score(const LexView& v, float idf, uint64_
 }
 
 __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bool cand, float score, uint32_t doc,
-                                                  uint32_t k, int lane, bool& dirty) {
-    unsigned m = __ballot_sync(FULL, cand);
+                                                  uint32_t k, int lane, bool& dirty, uint64_t ceil) {
+    // `ceil`: exclusive upper bound on keys (paging beyond 32 results: everything >= ceil was returned by an earlier page)
+    const uint64_t key = pack_key(score, doc);
+    unsigned m = __ballot_sync(FULL, cand && key < ceil);
     if (!m) return;
-    uint32_t so = ord_f32(score);
     while (m) {
         int src = __ffs(m) - 1; m &= m - 1;
-        uint32_t s = __shfl_sync(FULL, so, src), dd = __shfl_sync(FULL, doc, src);
-        wl_insert(L, ((uint64_t)s << 32) | (uint64_t)(0xFFFFFFFFu - dd), lane);
+        wl_insert(L, shfl64(key, src), lane);
     }
     dirty = true;
     uint32_t kth = (uint32_t)(shfl64(L, (int)k - 1) >> 32);
@@ -308,6 +308,7 @@ __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bo
 
 struct ItemCtx {
     uint32_t q, lv, n, k, docbase, bound_ord;
+    uint64_t ceil;
     bool scoring, need_count, is_and;
 };
 
@@ -356,7 +357,7 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
                 if (c.scoring) score = __fadd_rn(score, term_score(v, idf[t], off[t] + rank));
             }
             matches += __popc(__ballot_sync(FULL, ok));
-            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
+            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
         }
         return;
     }
@@ -424,7 +425,7 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
                         else score = __fadd_rn(score, term_score(v, idf[t], off[t] + rank));
                     }
                 }
-                insert_candidates(L, thr, alive && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
+                insert_candidates(L, thr, alive && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
             }
         }
     }
@@ -503,7 +504,7 @@ __device__ __noinline__ void process_item_generic(const LexView& v, const QueryP
                 if (ok && c.scoring) score = __fadd_rn(score, term_score(v, ti, to + rank));
             }
             matches += __popc(__ballot_sync(FULL, ok));
-            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
+            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
         }
         return;
     }
@@ -546,7 +547,7 @@ __device__ __noinline__ void process_item_generic(const LexView& v, const QueryP
                         else score = __fadd_rn(score, term_score(v, ti, to + rank));
                     }
                 }
-                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty);
+                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
             }
         }
     }
@@ -588,7 +589,7 @@ __device__ __noinline__ void process_item_generic(const LexView& v, const QueryP
 __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const QueryPlan* __restrict__ plans, const uint64_t* __restrict__ items,
                                                  const uint2* __restrict__ item_ent, uint32_t nq, uint32_t query_type, uint32_t result_type,
                                                  uint32_t k, uint32_t* ctr, uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist,
-                                                 LexStats* stats) {
+                                                 LexStats* stats, const uint64_t* __restrict__ ceil_keys) {
     const int lane = threadIdx.x & 31;
     const uint32_t max_items = *(volatile uint32_t*)&ctr[1];
     const uint64_t total = (uint64_t)max_items * nq;
@@ -606,6 +607,8 @@ __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const 
         if (j >= pl->n_items) continue;
         const uint64_t item = items[(size_t)q * v.n_levels + j];
         ItemCtx c;
+        c.ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
+        if (c.ceil == 0) continue;                       // this query's result list is already exhausted
         c.q = q; c.n = pl->n_live; c.k = k; c.lv = 0xFFFFFFFFu - (uint32_t)item; c.bound_ord = (uint32_t)(item >> 32);
         uint32_t thr = (uint32_t)(__ldcg(&theta[q]) >> 32);
         c.scoring = want_topk && c.bound_ord >= thr;
@@ -939,7 +942,7 @@ int32_t LexIndex::ensure_workspace(uint32_t nq, uint32_t total_terms) {
 }
 
 int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t result_type, uint64_t* keys_out_dev,
-                              uint64_t* count_dev, uint64_t* launches) {
+                              uint64_t* count_dev, uint64_t* launches, const uint64_t* ceil_dev) {
     if (!committed_) { set_error("search before ssb_lexical_commit"); return SSB_E_STATE; }
     if (!q || (q->n_queries && (!q->term_offsets || !keys_out_dev))) { set_error("search_lexical: null argument"); return SSB_E_INVALID; }
     if (k > SSB_K_MAX) { set_error("k=%u exceeds SSB_K_MAX=%u", k, SSB_K_MAX); return SSB_E_UNSUPPORTED; }
@@ -976,7 +979,7 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
     SSB_CUDA_TRY(cudaGetLastError());
     int grid = n_sms_ * SSB_LEX_MINB;
     if (ev0_) cudaEventRecord(ev0_, st_);
-    lex_score<<<grid, 256, 0, st_>>>(v, d_plans_, d_items_, (const uint2*)d_item_ent_, nq, q->query_type, result_type, k ? k : 1, d_ctr_, d_theta_, d_lock_, d_count_, glist, d_stats_);
+    lex_score<<<grid, 256, 0, st_>>>(v, d_plans_, d_items_, (const uint2*)d_item_ent_, nq, q->query_type, result_type, k ? k : 1, d_ctr_, d_theta_, d_lock_, d_count_, glist, d_stats_, ceil_dev);
     if (ev1_) cudaEventRecord(ev1_, st_);
     SSB_CUDA_TRY(cudaGetLastError());
     copy_out<<<(nq * LIST + 255) / 256, 256, 0, st_>>>(glist, d_count_, nq, result_type == SSB_RESULT_COUNT ? 0 : k, keys_out_dev, count_dev);

@@ -93,8 +93,9 @@ public:
     int32_t dict_export(uint64_t* keys, uint32_t* dfs, uint64_t cap) const;
     int32_t set_global_df(const uint64_t* keys, const uint32_t* dfs, uint64_t n);
     // keys_out_dev: [n_queries][32]; count_dev: [n_queries] or null. Asynchronous on the stream.
+    // ceil_dev: optional [n_queries] exclusive key ceilings (paging: only hits ranked after that key; 0 = none left)
     int32_t search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t result_type, uint64_t* keys_out_dev,
-                        uint64_t* count_dev, uint64_t* launches);
+                        uint64_t* count_dev, uint64_t* launches, const uint64_t* ceil_dev = nullptr);
     bool committed() const { return committed_; }
     void set_stream(cudaStream_t st) { st_ = st; }
     void set_events(cudaEvent_t a, cudaEvent_t b) { ev0_ = a; ev1_ = b; }

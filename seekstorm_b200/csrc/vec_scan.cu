@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
           uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
           const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*CWARPS/2][QT][32]*/,
-          const uint32_t* __restrict__ thr_init /*[gridDim.y*QT] or null*/, uint32_t nq_valid) {
+          const uint32_t* __restrict__ thr_init /*[gridDim.y*QT] or null*/, uint32_t nq_valid,
+          const uint64_t* __restrict__ ceil_keys /*[gridDim.y*QT] or null*/) {
     // no static shared memory in this kernel: the dynamic segment starts at offset 0 of the CTA window, so the
     // 1024-byte alignment SWIZZLE_128B needs holds and the pointers stay in the shared address space (LDS, not LD)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -152,6 +153,8 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             uint32_t so = ord_f32(sc);
                             unsigned m = __ballot_sync(FULL, valid && so >= thr[q] && sc == sc);
                             if (m) {                                   // rare after warm-up
+                                // paging: keys >= ceil were returned by an earlier page (0 = this query is exhausted)
+                                const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[group * QT + qh + q]) : ~0ull;
                                 uint64_t Lq = myL[q * LIST];
                                 while (m) {
                                     int src = __ffs(m) - 1;
@@ -160,7 +163,7 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                     uint32_t row_s = __shfl_sync(FULL, row, src);
                                     uint32_t doc = doc_ids ? __ldg(&doc_ids[row_s]) : row_s;
                                     uint64_t key = ((uint64_t)so_s << 32) | (uint64_t)(0xFFFFFFFFu - doc);
-                                    wl_insert(Lq, key, lane);
+                                    if (key < ceil) wl_insert(Lq, key, lane);
                                 }
                                 myL[q * LIST] = Lq;
                                 const uint32_t kth = (uint32_t)(shfl64(Lq, (int)k - 1) >> 32);
@@ -287,7 +290,7 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
     }
     if (a.ev0) cudaEventRecord(a.ev0, st);
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
-                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad);
+                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     merge_lists<<<a.nq_pad, 256, 0, st>>>(a.scratch, n_lists, QT, a.keys_out);

@@ -26,6 +26,7 @@ struct ScanArgs {
     float* q_hi = nullptr; float* q_lo = nullptr;  // [nq_pad][dpad] tf32 split of the queries (tcgen05 kernel)
     uint32_t* thr_buf = nullptr;                   // [nq_pad] scratch for the pre-sampled per-query thresholds
     const uint32_t* thr_init = nullptr;            // internal: initial thresholds (ordered-uint scores) or null
+    const uint64_t* ceil_keys = nullptr;           // [nq_pad] exclusive key ceilings for paging beyond 32 results, or null
 };
 
 // rows scanned first to seed the per-query top-k thresholds: ~1/16 of the shard, between 4K and 32K rows (0 = too small)

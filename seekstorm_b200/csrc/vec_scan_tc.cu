@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
         const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*4][NQ][32]*/,
-        const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/, uint32_t nq_valid) {
+        const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/, uint32_t nq_valid,
+        const uint64_t* __restrict__ ceil_keys /*[gridDim.y*NQ] or null*/) {
     using C = Cfg<NQ, PREC>;
     // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for the swizzled
     // tiles) and pointers derived from it stay in the shared address space (LDS/STS instead of generic LD/ST)
@@ -288,6 +289,12 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     if (pm) {                                           // rare after warm-up
                         uint64_t key = 0;
                         if (pass) key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
+                        if (ceil_keys) {   // paging: keys >= ceil were returned by an earlier page (0 = exhausted)
+                            const uint64_t ceil = __ldg(&ceil_keys[blockIdx.y * NQ + q]);
+                            if (key >= ceil) key = 0;
+                            pm = __ballot_sync(FULL, key != 0);
+                            if (!pm) continue;
+                        }
                         uint64_t L = mylists[q * LIST + lane];
                         if (__popc(pm) > 3) {
                             // bulk (warm-up tiles: many rows pass): sort the 32 keys, bitonic-merge into the list
@@ -361,7 +368,7 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     }
     if (a.ev0) cudaEventRecord(a.ev0, st);
     tc::scan_tc<NQ, PREC><<<dim3(gx, n_groups), tc::THREADS, C::SMEM, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, a.dpad / tc::KC, n_tiles,
-                                                                             a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad);
+                                                                             a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ

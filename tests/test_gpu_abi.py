@@ -165,3 +165,50 @@ def test_add_level_rejects_malformed_postings():
     ix.add_lexical_level(good["level_id"], good["n_docs"], good["term_keys"], good["posting_offsets"], good["doc_ids"], good["tfs"], good["doc_len_bytes"])
     ix.commit(50, 500)
     ix.close()
+
+
+@pytest.mark.parametrize("kern", [1, 2, 4])
+def test_vector_paging_beyond_32(kern):
+    """offset+length > 32 (the reference's heap is min(offset+length, N), search.rs:2527-2531): the host-facing call pages
+    internally with an exclusive key ceiling; results must equal the oracle's top-k for k = 100 and k = N."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    rows = synth.gen_vectors(70000, 64, 51, "cpu").numpy()
+    q = synth.gen_vectors(20, 64, 52, "cpu").numpy()
+    rows[7] = rows[3]                                       # exact duplicate rows: tie broken by doc id across pages
+    ix = Index(0, vector_dims=64, vector_similarity=VectorSimilarity.Dot, vector_kernel=kern)
+    ix.add_vectors(rows)
+    got = ix.search_vector_batch(q, 100)
+    for i in (0, 7, 19):
+        want = O.search_vector(rows, q[i], 100, O.SIM_DOT)
+        assert len(got[i]) == 100
+        assert [d for d, _ in got[i]] == [d for d, _ in want]
+        assert np.allclose([s for _, s in got[i]], [s for _, s in want], rtol=1e-4, atol=1e-5)
+    small = Index(0, vector_dims=64, vector_similarity=VectorSimilarity.Dot, vector_kernel=kern)
+    small.add_vectors(rows[:50])
+    got = small.search_vector_batch(q[:3], 80)              # fewer rows than k: every row, best first, then stop
+    for i in range(3):
+        want = O.search_vector(rows[:50], q[i], 80, O.SIM_DOT)
+        assert [d for d, _ in got[i]] == [d for d, _ in want] and len(got[i]) == 50
+    ix.close(); small.close()
+
+
+def test_lexical_paging_beyond_32():
+    from seekstorm_b200 import QueryType, ResultType, SearchMode
+    lvs, ls = synth_levels(90000, 1500, 61)
+    orc = oracle_index([l.to_numpy() for l in lvs], 90000, ls)
+    ix = gpu_index([l.to_numpy() for l in lvs], 90000, ls)
+    qs = synth.gen_queries(25, 62, 2, 1400, (1, 2, 3), (0.2, 0.5, 0.3))
+    qk = query_keys(qs)
+    for qt, oqt in ((QueryType.Union, O.QUERY_UNION), (QueryType.Intersection, O.QUERY_INTERSECTION)):
+        got, cnt = ix.search_lexical_batch(qk, qt, 77, ResultType.TopkCount)
+        for i, k in enumerate(qk):
+            want, tot = orc.search(k, oqt, 77, O.RESULT_TOPKCOUNT)
+            assert got[i] == want, (qt, i)                 # bit-exact across page boundaries (ties by doc id)
+            assert int(cnt[i]) == tot
+    # the mirrored Search::search with offset paging past 32
+    terms = qs[0]
+    ro = ix.search(" ".join(f"t{t}" for t in terms), None, QueryType.Union, SearchMode.Lexical(), False, 40, 10, ResultType.TopkCount)
+    want, tot = orc.search(qk[0], O.QUERY_UNION, 50, O.RESULT_TOPKCOUNT)
+    assert [(r.doc_id, np.float32(r.score)) for r in ro.results] == [(d, np.float32(s)) for d, s in want[40:50]]
+    assert ro.result_count_total == tot
+    ix.close()

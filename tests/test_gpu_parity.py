@@ -215,7 +215,7 @@ def test_errors_are_status_codes():
     with pytest.raises(SsbError, match="commit"):
         ix.search_lexical_batch([[1]], QueryType.Union, 10, ResultType.Topk)
     with pytest.raises(SsbError, match="k"):
-        ix.search_vector_batch(np.zeros((1, 32), dtype=np.float32), 33)
+        ix.search_vector_batch(np.zeros((1, 32), dtype=np.float32), 1025)      # SSB_K_LIMIT = 1024 (paged beyond 32)
     with pytest.raises(SsbError, match="dims"):
         ix.add_vector_level(0, np.zeros((4, 16), dtype=np.float32))
     assert ix.search_vector_batch(np.ones((2, 32), dtype=np.float32), 5) == [[], []]   # empty index -> empty results
