@@ -118,17 +118,16 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     a.keys_out = merged; a.ev0 = ix->ev0; a.ev1 = ix->ev1; ix->ev_used = true;
     a.thr_buf = reinterpret_cast<uint32_t*>(merged + (size_t)nq_pad * LIST);
     a.ceil_keys = ceil_dev;
+    a.launches = &ix->stats.kernel_launches;
     if (use_tc) {
         SSB_TRY(ix->qhi.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         SSB_TRY(ix->qlo.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         a.q_hi = ix->qhi.p; a.q_lo = ix->qlo.p;
         SSB_TRY(vec::launch_scan_tc(a, qt, tc_bf16 ? 1 : 0, ix->st));
-        ix->stats.kernel_launches += 1;
     } else {
         SSB_TRY(vec::launch_scan_ffma(a, ix->st));
     }
     SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, ix->st));
-    ix->stats.kernel_launches += 2;
     ix->stats.algorithmic_bytes += (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * 4;
     return SSB_OK;
 }

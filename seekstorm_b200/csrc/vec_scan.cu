@@ -263,6 +263,7 @@ static int32_t with_presample(const ScanArgs& a, cudaStream_t st, F launch) {
     pre.n_rows = vec_presample_rows(a.n_rows); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
     SSB_TRY(launch(pre));
     launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
+    if (a.launches) *a.launches += 1;
     ScanArgs full = a;
     full.thr_init = a.thr_buf;
     return launch(full);
@@ -295,6 +296,7 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
     SSB_CUDA_TRY(cudaGetLastError());
     merge_lists<<<a.nq_pad, 256, 0, st>>>(a.scratch, n_lists, QT, a.keys_out);
     SSB_CUDA_TRY(cudaGetLastError());
+    if (a.launches) *a.launches += 2;   // scan + merge
     return SSB_OK;
 }
 

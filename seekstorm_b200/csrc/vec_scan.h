@@ -27,6 +27,7 @@ struct ScanArgs {
     uint32_t* thr_buf = nullptr;                   // [nq_pad] scratch for the pre-sampled per-query thresholds
     const uint32_t* thr_init = nullptr;            // internal: initial thresholds (ordered-uint scores) or null
     const uint64_t* ceil_keys = nullptr;           // [nq_pad] exclusive key ceilings for paging beyond 32 results, or null
+    uint64_t* launches = nullptr;                  // incremented once per kernel launched (ssb_stats.kernel_launches)
 };
 
 // rows scanned first to seed the per-query top-k thresholds: ~1/16 of the shard, between 4K and 32K rows (0 = too small)

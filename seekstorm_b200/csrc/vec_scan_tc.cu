@@ -374,6 +374,7 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ
     merge_lists_generic(a.scratch, gx * 4, NQ, a.nq_pad, a.keys_out, st);
     SSB_CUDA_TRY(cudaGetLastError());
+    if (a.launches) *a.launches += 3;   // query split + scan + merge
     return SSB_OK;
 }
 
@@ -392,6 +393,7 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream
     pre.n_rows = vec_presample_rows(a.n_rows); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
     SSB_TRY(launch_scan_tc_impl(pre, nq_tile, bf16, st));
     launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
+    if (a.launches) *a.launches += 1;
     ScanArgs full = a;
     full.thr_init = a.thr_buf;
     return launch_scan_tc_impl(full, nq_tile, bf16, st);
