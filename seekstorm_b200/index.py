@@ -364,6 +364,12 @@ class Index:
         if want_vec:
             qv = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)
             vec = self.search_vector_batch(qv, max(heap, 1))[0][:heap]
+            if search_mode.similarity_threshold is not None:
+                # TopK::new (vector.rs:388-399): threshold pre-map (2t-1)*16129 for Dot/Cosine, -t for Euclidean; hits below
+                # it are rejected in TopK::push (:421).  Filtering the top-k afterwards is equivalent (scores are sorted).
+                t = float(search_mode.similarity_threshold)
+                cut = -t if self.vector_similarity == VectorSimilarity.Euclidean else ((t * 2.0) - 1.0) * 16129.0
+                vec = [(d, s) for d, s in vec if s >= cut]
             ro.observed_vector_count = self.vector_count
         if search_mode.kind == "Lexical":
             fused = lex
