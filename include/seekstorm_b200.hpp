@@ -1,0 +1,184 @@
+// seekstorm_b200.hpp — header-only C++17 host mirror of the reference's search interface, on top of the C-ABI
+// (include/seekstorm_b200.h).  The reference is a Rust crate; no Rust toolchain exists in this build environment, so the
+// compiled-language host side a SeekStorm maintainer would write in Rust is mirrored here in C++ with
+// the same names, argument meaning and error behaviour:
+//
+//   ssb::Index::search(...)            <- Search::search              seekstorm/src/search.rs:1134-1150 (impl 1153-2131)
+//   ssb::QueryType / ResultType        <- search.rs `QueryType`, `ResultType` (:150-175)
+//   ssb::SearchMode / AnnMode          <- search.rs `SearchMode::{Lexical,Vector,Hybrid}`, vector_similarity.rs:43-67
+//   ssb::Result / ResultObject         <- min_heap.rs:17-40, search.rs:186-213
+//
+// Like the reference, `search` is infallible by type for data-dependent failures (unknown terms, empty index -> empty
+// ResultObject, search.rs:1630-1631); programming errors (k too large, no GPU, unsupported arguments) throw ssb::Error.
+// Facets / filters / sort / uncommitted search / query rewriting / phrase queries are outside the GPU hot path and throw.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <optional>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "seekstorm_b200.h"
+
+namespace ssb {
+
+struct Error : std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int32_t rc) {
+    if (rc != SSB_OK) throw Error(rc, std::string("libseekstorm_b200 error ") + std::to_string(rc) + ": " + ssb_last_error());
+}
+
+enum class QueryType : uint32_t { Union = SSB_QUERY_UNION, Intersection = SSB_QUERY_INTERSECTION };
+enum class ResultType : uint32_t { Count = SSB_RESULT_COUNT, Topk = SSB_RESULT_TOPK, TopkCount = SSB_RESULT_TOPKCOUNT };
+enum class VectorSimilarity : uint32_t { Dot = SSB_SIM_DOT, Cosine = SSB_SIM_COSINE, Euclidean = SSB_SIM_EUCLIDEAN };
+enum class AnnMode { All };   // exhaustive search only
+
+struct SearchMode {
+    enum Kind { Lexical, Vector, Hybrid } kind = Lexical;
+    std::optional<float> similarity_threshold;
+    AnnMode ann_mode = AnnMode::All;
+    static SearchMode lexical() { return {Lexical, std::nullopt, AnnMode::All}; }
+    static SearchMode vector(std::optional<float> t = std::nullopt) { return {Vector, t, AnnMode::All}; }
+    static SearchMode hybrid(std::optional<float> t = std::nullopt) { return {Hybrid, t, AnnMode::All}; }
+};
+
+struct Result { uint64_t doc_id; float score; };
+
+struct ResultObject {
+    std::string original_query, query;
+    std::vector<std::string> query_terms;
+    size_t result_count = 0, result_count_total = 0;
+    std::vector<Result> results;
+    size_t observed_vector_count = 0;
+};
+
+// 64-bit FNV-1a with the low 3 bits cleared (the reference reserves them for the n-gram type, index.rs:4165-4225; its
+// real key is an ahash of the term string — any stable 64-bit key function works as long as index and queries agree)
+inline uint64_t fnv1a64(const std::string& term) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    for (unsigned char c : term) h = (h ^ c) * 0x100000001B3ull;
+    return h & ~7ull;
+}
+
+class Index {
+public:
+    using TermKeyFn = std::function<uint64_t(const std::string&)>;
+
+    explicit Index(int device = 0, uint32_t vector_dims = 0, VectorSimilarity sim = VectorSimilarity::Cosine,
+                   uint32_t max_batch = 4096, TermKeyFn key_fn = fnv1a64)
+        : key_fn_(std::move(key_fn)), sim_(sim) {
+        ssb_config cfg{};
+        cfg.device = device; cfg.max_batch = max_batch; cfg.vector_dims = vector_dims;
+        cfg.vector_similarity = static_cast<uint32_t>(sim); cfg.vector_kernel = SSB_VEC_KERNEL_AUTO;
+        check(ssb_create(&cfg, &h_));
+    }
+    ~Index() { if (h_) ssb_destroy(h_); }
+    Index(const Index&) = delete;
+    Index& operator=(const Index&) = delete;
+
+    ssb_index* handle() const { return h_; }
+
+    // ---- load (what the Rust level loader of INTEGRATION.md §2 would call) ----
+    void add_lexical_level(const ssb_level_desc& level) { check(ssb_lexical_add_level(h_, &level)); }
+    void commit(uint64_t indexed_doc_count, uint64_t positions_sum_normalized) {
+        check(ssb_lexical_commit(h_, indexed_doc_count, positions_sum_normalized));
+        indexed_doc_count_ = indexed_doc_count;
+    }
+    void add_vector_level(uint32_t level_id, const float* rows, uint32_t n, uint32_t dims, uint64_t row_stride = 0,
+                          const uint16_t* local_ids = nullptr) {
+        check(ssb_vector_add_level(h_, level_id, rows, row_stride, local_ids, n, dims));
+    }
+    uint64_t indexed_doc_count() const { return indexed_doc_count_; }
+    uint64_t vector_count() const { uint64_t n = 0; check(ssb_vector_count(h_, &n)); return n; }
+
+    // ---- Search::search (search.rs:1134-1150), 1-shard semantics, committed data ----
+    ResultObject search(const std::string& query_string, const std::optional<std::vector<float>>& query_vector,
+                        QueryType query_type_default, const SearchMode& search_mode, bool enable_empty_query, size_t offset,
+                        size_t length, ResultType result_type, bool include_uncommitted = false,
+                        const std::vector<std::string>& field_filter = {}, size_t n_query_facets = 0, size_t n_facet_filter = 0,
+                        size_t n_result_sort = 0) const {
+        (void)enable_empty_query;
+        if (include_uncommitted || !field_filter.empty() || n_query_facets || n_facet_filter || n_result_sort)
+            throw Error(SSB_E_UNSUPPORTED, "facets / filters / sort / uncommitted search are outside the GPU hot path");
+        ResultObject ro;
+        ro.original_query = ro.query = query_string;
+        const size_t heap = offset + length;                                   // search.rs:1708: per-shard length = offset+length
+        // tokenizer stand-in (tokenizer.rs is out of scope): whitespace split, leading '+' = mandatory, unique terms
+        QueryType qt = query_type_default;
+        std::vector<std::string> terms;
+        {
+            std::istringstream is(query_string);
+            std::string tok; bool all_plus = true, any = false;
+            while (is >> tok) {
+                if (tok[0] == '"' || tok[0] == '-') throw Error(SSB_E_UNSUPPORTED, "phrase / NOT operators are outside the GPU hot path");
+                any = true;
+                if (tok[0] == '+') tok.erase(0, 1); else all_plus = false;
+                if (tok.empty()) continue;
+                bool dup = false;
+                for (auto& t : terms) dup = dup || t == tok;
+                if (!dup) terms.push_back(tok);
+            }
+            if (any && all_plus) qt = QueryType::Intersection;
+        }
+        ro.query_terms = terms;
+        ResultType rt = result_type;
+        if (length == 0 && rt == ResultType::TopkCount) rt = ResultType::Count;   // search.rs:2472-2478
+        std::vector<ssb_hit> lex, vec;
+        uint64_t total = 0;
+        const bool want_lex = (search_mode.kind != SearchMode::Vector) && !terms.empty();
+        const bool want_vec = (search_mode.kind != SearchMode::Lexical) && query_vector.has_value();
+        if (want_lex) {
+            std::vector<uint64_t> keys;
+            for (auto& t : terms) keys.push_back(key_fn_(t));
+            uint32_t offs[2] = {0, static_cast<uint32_t>(keys.size())};
+            ssb_lex_batch b{1, static_cast<uint32_t>(qt), offs, keys.data()};
+            const uint32_t k = rt == ResultType::Count ? 0u : static_cast<uint32_t>(heap);
+            lex.resize(k ? k : 1);
+            uint32_t n = 0;
+            check(ssb_search_lexical(h_, &b, k, static_cast<uint32_t>(rt), lex.data(), &n, &total));
+            lex.resize(n);
+        }
+        if (want_vec) {
+            const uint32_t k = static_cast<uint32_t>(heap ? heap : 1);
+            vec.resize(k);
+            uint32_t n = 0;
+            check(ssb_search_vector(h_, query_vector->data(), 1, k, vec.data(), &n));
+            vec.resize(n < heap ? n : heap);
+            if (search_mode.similarity_threshold) {
+                // TopK::new threshold pre-map (vector.rs:388-399): (2t-1)*16129 for Dot/Cosine, -t for Euclidean
+                const float t = *search_mode.similarity_threshold;
+                const float cut = sim_ == VectorSimilarity::Euclidean ? -t : ((t * 2.0f) - 1.0f) * 16129.0f;
+                std::vector<ssb_hit> kept;
+                for (auto& h : vec) if (h.score >= cut) kept.push_back(h);
+                vec.swap(kept);
+            }
+            ro.observed_vector_count = vector_count();
+        }
+        std::vector<ssb_hit> fused;
+        if (search_mode.kind == SearchMode::Lexical) { fused = lex; ro.result_count_total = total; }
+        else if (search_mode.kind == SearchMode::Vector) { fused = vec; ro.result_count_total = vec.size(); }
+        else {
+            fused.resize(lex.size() + vec.size() + 1);
+            uint32_t n = 0;
+            check(ssb_rrf_fuse(lex.data(), static_cast<uint32_t>(lex.size()), vec.data(), static_cast<uint32_t>(vec.size()), fused.data(), &n));
+            fused.resize(n);
+            ro.result_count_total = total;
+        }
+        // search.rs:2108-2121: drop `offset`, truncate to `length`
+        for (size_t i = offset; i < fused.size() && ro.results.size() < length; i++) ro.results.push_back({fused[i].doc_id, fused[i].score});
+        ro.result_count = ro.results.size();
+        return ro;
+    }
+
+private:
+    ssb_index* h_ = nullptr;
+    TermKeyFn key_fn_;
+    VectorSimilarity sim_;
+    uint64_t indexed_doc_count_ = 0;
+};
+
+}  // namespace ssb
