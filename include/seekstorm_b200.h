@@ -87,7 +87,8 @@ typedef struct {
 } ssb_level_desc;
 
 /* A batch of lexical queries, already tokenised by the host (tokenizer.rs is out of scope): unique terms
- * per query as 64-bit keys, CSR layout. */
+ * per query as 64-bit keys, CSR layout; at most SSB_MAX_QUERY_TERMS per query (checked for host arrays; with device
+ * arrays extra terms are ignored).  Repeated keys inside a query count once, as in the reference's unique_terms. */
 typedef struct {
     uint32_t n_queries;
     uint32_t query_type;              /* SSB_QUERY_* (applies to the whole batch)                         */

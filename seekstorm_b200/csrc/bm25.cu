@@ -204,7 +204,12 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t nl = 0; bool missing = false;
-        for (uint32_t t = 0; t < nt; t++) { if (st[t].n) pl.t[nl++] = st[t]; else missing = true; }
+        for (uint32_t t = 0; t < nt; t++) {
+            if (!st[t].n) { missing = true; continue; }
+            bool dup = false;                       // the reference scores unique_terms (search.rs:3023-3039): drop repeated keys
+            for (uint32_t u = 0; u < nl; u++) dup = dup || pl.t[u].first == st[t].first;
+            if (!dup) pl.t[nl++] = st[t];
+        }
         // search.rs:3290-3296: AND with an unknown term -> empty result; OR drops the term
         if (query_type == SSB_QUERY_INTERSECTION && missing) nl = 0;
         pl.n_live = nl; pl.n_items = 0; pl.flags = 0; pl.pad = 0;
@@ -953,7 +958,14 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
     uint32_t total_terms = 0;
     const bool off_dev = is_device_ptr(q->term_offsets);
     if (off_dev) SSB_CUDA_TRY(cudaMemcpy(&total_terms, q->term_offsets + nq, 4, cudaMemcpyDeviceToHost));
-    else total_terms = q->term_offsets[nq];
+    else {
+        total_terms = q->term_offsets[nq];
+        for (uint32_t i = 0; i < nq; i++)
+            if (q->term_offsets[i + 1] < q->term_offsets[i] || q->term_offsets[i + 1] - q->term_offsets[i] > SSB_MAX_QUERY_TERMS) {
+                set_error("query %u has %u terms (max %u unique terms per query)", i, q->term_offsets[i + 1] - q->term_offsets[i], SSB_MAX_QUERY_TERMS);
+                return SSB_E_UNSUPPORTED;
+            }
+    }
     if ((uint64_t)nq * (levels_.size() ? levels_.size() : 1) >= 0xFFFFFFFFull) { set_error("batch too large: n_queries * n_levels must be < 2^32"); return SSB_E_UNSUPPORTED; }
     SSB_TRY(ensure_workspace(nq, total_terms));
     SSB_CUDA_TRY(to_device(d_qoff_, q->term_offsets, ((size_t)nq + 1) * 4, st_));
