@@ -258,9 +258,9 @@ void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_
 // are unchanged, but the expected number of list insertions per query drops from ~k*ln(rows/k) PER LIST to ~k*N/S in total.
 template <class F>
 static int32_t with_presample(const ScanArgs& a, cudaStream_t st, F launch) {
-    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows) == 0) return launch(a);
+    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, false) == 0) return launch(a);
     ScanArgs pre = a;
-    pre.n_rows = vec_presample_rows(a.n_rows); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
+    pre.n_rows = vec_presample_rows(a.n_rows, false); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
     SSB_TRY(launch(pre));
     launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
     if (a.launches) *a.launches += 1;

@@ -388,9 +388,9 @@ static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int bf16
 
 int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream_t st) {
     // threshold pre-sampling (see vec_scan.cu): scan the first rows, seed the thresholds, then the full scan
-    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows) == 0) return launch_scan_tc_impl(a, nq_tile, bf16, st);
+    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, bf16, st);
     ScanArgs pre = a;
-    pre.n_rows = vec_presample_rows(a.n_rows); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
+    pre.n_rows = vec_presample_rows(a.n_rows, true); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
     SSB_TRY(launch_scan_tc_impl(pre, nq_tile, bf16, st));
     launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
     if (a.launches) *a.launches += 1;
