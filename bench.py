@@ -46,7 +46,8 @@ def parse():
     p.add_argument("--batch", type=int, default=256, help="vector queries per step")
     p.add_argument("--rows", type=int, default=C2_ROWS)
     p.add_argument("--dims", type=int, default=C2_DIMS)
-    p.add_argument("--sections", default="vector,bm25,hybrid")
+    p.add_argument("--sections", default="vector,int8,bm25,hybrid")
+    p.add_argument("--int8-batch", type=int, default=1024, help="queries per step of the int8 (ScalarQuantizationI8) section")
     p.add_argument("--bm25-docs", type=int, default=C3_DOCS)
     p.add_argument("--bm25-batch", type=int, default=4096, help="lexical queries per step")
     p.add_argument("--hybrid-docs", type=int, default=5_000_000)
@@ -290,6 +291,119 @@ def bench_vector(a, rank, world, out):
                     {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
     })
     return ix, q_host
+
+
+def bench_vector_int8(a, rank, world):
+    """C2 corpus with Cosine + ScalarQuantizationI8 (SURVEY §8f row 2): int8 corpus, tcgen05 kind::i8 scan, exact scores."""
+    from seekstorm_b200 import Index, VectorSimilarity, synth
+    from seekstorm_b200.parallel import ShardedSearcher
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nb = a.int8_batch
+    ix = Index(dev.index, vector_dims=a.dims, vector_similarity=VectorSimilarity.Cosine, max_batch=max(nb, 16), vector_quantization=1)
+    ix.set_stream(torch.cuda.current_stream().cuda_stream)
+    n_levels, mine = vector_levels(a.rows, rank, world)
+    local_rows = 0
+    for lv in mine:
+        r = gen_vector_level(lv, a.rows, a.dims, dev)
+        ix.add_vector_level(lv, r)
+        local_rows += r.shape[0]
+        del r
+    q_host = synth.gen_vectors(nb, a.dims, 2002, "cpu").pin_memory()
+    q_dev = q_host.to(dev)
+    keys = torch.zeros((nb, 32), dtype=torch.int64, device=dev)
+    sh = ShardedSearcher(ix)
+
+    def step_dev():
+        ix.search_vector_keys(q_dev, TOPK, keys)
+        if world > 1:
+            sh.gather_keys(keys)
+    step_dev(); torch.cuda.synchronize()
+    ms = timed_steps(step_dev, a.steps, a.warmup, world)
+    kern_ns = []
+    for _ in range(5):
+        step_dev(); torch.cuda.synchronize()
+        kern_ns.append(ix.last_stats()["dominant_kernel_ns"])
+    launches = ix.last_stats()["kernel_launches"] + (1 if world > 1 else 0)
+    q_np = q_host.numpy()
+    hits_buf, nh_buf = ix.hits_buffer(nb * TOPK), np.zeros(nb, dtype=np.uint32)
+    if world == 1:
+        def step_e2e():
+            ix.search_vector_raw(q_np, TOPK, hits_buf, nh_buf)
+    else:
+        import torch.distributed as dist
+
+        def step_e2e():
+            qd = q_host.to(dev, non_blocking=True) if rank == 0 else q_dev
+            dist.broadcast(qd, 0)
+            sh.search_vector(qd, TOPK, raw_out=(hits_buf, nh_buf))
+    ms_e2e = timed_steps(step_e2e, a.steps, a.warmup, world)
+    sweep = {}
+    if world == 1:
+        for bs in (1, 128, 256):
+            qn = q_np[:bs].copy()
+            hb, nbuf = ix.hits_buffer(bs * TOPK), np.zeros(bs, dtype=np.uint32)
+
+            def step_b():
+                ix.search_vector_raw(qn, TOPK, hb, nbuf)
+            n_it = max(5, a.steps // 2)
+            per = timed_steps(step_b, n_it, 2, world) / n_it
+            sweep[str(bs)] = {"ms_per_call": per, "queries_per_s": bs / (per / 1e3)}
+    peak, peak_kind = peaks()
+    passes = (nb + 127) // 128
+    kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
+    alg_bytes = float(local_rows) * a.dims * 1 * passes
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
+    ix.close()
+    return {
+        "metric": "queries/sec at top-10 (1M x 768 cosine, ScalarQuantizationI8 brute-force kNN)",
+        "value": nb * a.steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / a.steps, "dtype": "i8 (int32 accumulate, exact)",
+        "config": {"workload": f"C2 corpus quantised to int8 (Cosine + ScalarQuantizationI8): {a.rows} x {a.dims}, top-{TOPK}, "
+                               f"batch {nb} queries/step ({passes} corpus passes of 128 queries)",
+                   "kernel": "scan_tc<128, i8> (tcgen05 kind::i8, TMEM s32 accumulators)"},
+        "e2e": {"value": nb * a.steps / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / a.steps,
+                "h2d_bytes_per_step": nb * a.dims * 4, "d2h_bytes_per_step": nb * 32 * 8},
+        "gpu_launches": int(launches) * a.steps, "batch_sweep_e2e": sweep,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "peak_kind": f"of {peak_kind}", "kernel": "scan_tc_i8", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes},
+    }
+
+
+def cpu_vector_int8_baseline(a, seconds):
+    """Restated reference CPU path for Cosine + SQ-I8 (dot_i8 over the int8 corpus, linear top-k), one query per thread."""
+    from oracle import oracle as O
+    from seekstorm_b200 import synth
+    cores = os.cpu_count() or 1
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    rows = np.empty((a.rows, a.dims), dtype=np.int8)
+    sl = 65536
+
+    def quant(lv):
+        r = gen_vector_level(lv, a.rows, a.dims, dev).cpu().numpy()
+        rows[lv * sl: lv * sl + r.shape[0]] = O.quantize_rows_i8(r)
+    for lv in range((a.rows + sl - 1) // sl):
+        quant(lv)
+    qs = synth.gen_vectors(64, a.dims, 2002, "cpu").numpy()
+    q8 = O.quantize_rows_i8(qs)
+    O.search_vector_i8(rows, q8[0], TOPK)
+    done = [0] * cores
+    stop = time.perf_counter() + seconds
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work(i):
+        while time.perf_counter() < stop:
+            with lock:
+                j = nxt[0]; nxt[0] += 1
+            O.search_vector_i8(rows, q8[j % len(q8)], TOPK)
+            done[i] += 1
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]; [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    n_done = sum(done)
+    return {"value": n_done / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{n_done} queries, full {a.rows}x{a.dims} int8 corpus, {cores} threads (one query each), {dt:.1f}s"}
 
 
 def cpu_vector_baseline(a, seconds):
@@ -553,6 +667,12 @@ def main():
     ix.close()
     del ix
     torch.cuda.empty_cache()
+    if "int8" in sections:
+        try:
+            out["int8"] = bench_vector_int8(a, rank, world)
+        except Exception as e:  # pragma: no cover
+            out["int8"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
     if "bm25" in sections:
         try:
             out["bm25"] = bench_bm25(a, rank, world)
@@ -570,6 +690,11 @@ def main():
             out["cpu_baseline"] = cpu_vector_baseline(a, a.cpu_seconds)
         except Exception as e:  # pragma: no cover
             out["cpu_baseline"] = {"error": repr(e)}
+        if "int8" in sections and isinstance(out.get("int8"), dict) and "error" not in out["int8"]:
+            try:
+                out["int8"]["cpu_baseline"] = cpu_vector_int8_baseline(a, min(a.cpu_seconds, 8.0))
+            except Exception as e:  # pragma: no cover
+                out["int8"]["cpu_baseline"] = {"error": repr(e)}
         if "bm25" in sections and isinstance(out.get("bm25"), dict) and "error" not in out["bm25"]:
             try:
                 out["bm25"]["cpu_baseline"] = cpu_bm25_baseline(a, a.cpu_seconds)

@@ -47,6 +47,10 @@ enum { SSB_QUERY_UNION = 0, SSB_QUERY_INTERSECTION = 1 };
 enum { SSB_RESULT_COUNT = 0, SSB_RESULT_TOPK = 1, SSB_RESULT_TOPKCOUNT = 2 };
 /* VectorSimilarity (vector_similarity.rs:20-30) */
 enum { SSB_SIM_DOT = 0, SSB_SIM_COSINE = 1, SSB_SIM_EUCLIDEAN = 2 };
+/* Quantization (vector_similarity.rs `Quantization`): SCALAR_I8 = ScalarQuantizationI8 with Cosine similarity —
+ * rows and queries are normalised, then quantised round(v*127) clamped to [-127,127] (vector_similarity.rs:1226-1232,
+ * vector.rs:585-640); score = the exact int32 dot product as f32 (vector_similarity.rs:193-206, 1011-1016). */
+enum { SSB_QUANT_NONE = 0, SSB_QUANT_SCALAR_I8 = 1 };
 /* which vector scan kernel to use */
 /* FFMA: packed-FP32 scan, 16 queries per corpus pass (HBM-bound).  TCGEN05[_N64]: tensor-core scan with the 3xTF32
  * split, 128 (or 64) queries per corpus pass.  TCGEN05_BF16[_N64]: tensor-core scan with the 3xBF16 split (half the
@@ -66,7 +70,8 @@ typedef struct {
     uint32_t vector_dims;        /* 0 = no vector index                                                   */
     uint32_t vector_similarity;  /* SSB_SIM_*  (meta.inference similarity)                               */
     uint32_t vector_kernel;      /* SSB_VEC_KERNEL_*                                                      */
-    uint32_t reserved[3];
+    uint32_t vector_quantization;/* SSB_QUANT_* (0 = f32 corpus)                                           */
+    uint32_t reserved[2];
 } ssb_config;
 
 /* One committed level = one 64K-doc block of the shard, in a neutral (decoded) layout.

@@ -71,6 +71,12 @@ def lib():
         L.orc_search_vector.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                         C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_void_p, C.POINTER(C.c_uint32)]
+        L.orc_quantize_f32_to_i8.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_quantize_rows_i8.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.orc_dot_i8.restype = C.c_int32
+        L.orc_dot_i8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_search_vector_i8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
+                                           C.c_void_p, C.POINTER(C.c_uint32)]
         L.orc_rrf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                               C.POINTER(C.c_uint32)]
         _lib = L
@@ -150,6 +156,33 @@ def normalize(v: np.ndarray) -> np.ndarray:
     v = np.ascontiguousarray(v, dtype=np.float32).copy()
     lib().orc_normalize_f32(_ptr(v), v.size)
     return v
+
+
+def quantize_i8(v: np.ndarray) -> np.ndarray:
+    """normalize_f32 (scalar order) then quantize_f32_to_i8, as the reference does at index / query time for Cosine + SQ-I8."""
+    vn = normalize(v)
+    out = np.zeros(vn.size, dtype=np.int8)
+    lib().orc_quantize_f32_to_i8(_ptr(vn), vn.size, _ptr(out))
+    return out
+
+
+def quantize_rows_i8(rows: np.ndarray) -> np.ndarray:
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    out = np.zeros(rows.shape, dtype=np.int8)
+    lib().orc_quantize_rows_i8(_ptr(rows), rows.shape[0], rows.shape[1], rows.shape[1], _ptr(out), rows.shape[1])
+    return out
+
+
+def search_vector_i8(rows_i8: np.ndarray, query_i8: np.ndarray, k: int, doc_ids=None):
+    rows_i8 = np.ascontiguousarray(rows_i8, dtype=np.int8)
+    q = np.ascontiguousarray(query_i8, dtype=np.int8)
+    ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint32)
+    buf = (OrcHit * max(k, 1))()
+    n = C.c_uint32(0)
+    rc = lib().orc_search_vector_i8(_ptr(rows_i8), None if ids is None else _ptr(ids), rows_i8.shape[0], rows_i8.shape[1],
+                                    rows_i8.strides[0], _ptr(q), k, buf, C.byref(n))
+    assert rc == 0
+    return _hits_to_list(buf, n.value)
 
 
 def rrf(lex, vec):

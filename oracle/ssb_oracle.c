@@ -647,6 +647,45 @@ int orc_search_vector(const float* rows, const uint32_t* ids, uint64_t n_rows, u
     return 0;
 }
 
+/* ------------------------------------------------------------------ int8 scalar quantisation */
+void orc_quantize_f32_to_i8(const float* v, uint32_t n, int8_t* out) {
+    /* vector_similarity.rs:1226-1232 */
+    for (uint32_t i = 0; i < n; i++) {
+        float r = roundf(v[i] * 127.0f);
+        if (r < -127.0f) r = -127.0f;
+        if (r > 127.0f) r = 127.0f;
+        out[i] = r == r ? (int8_t)r : (int8_t)0;   /* NaN as i8 = 0 (Rust saturating cast) */
+    }
+}
+
+void orc_quantize_rows_i8(const float* rows, uint64_t n_rows, uint32_t dims, uint64_t pitch, int8_t* out, uint64_t out_pitch) {
+    float* tmp = (float*)malloc((size_t)dims * sizeof(float));
+    for (uint64_t r = 0; r < n_rows; r++) {
+        memcpy(tmp, rows + r * pitch, (size_t)dims * sizeof(float));
+        orc_normalize_f32(tmp, dims);
+        orc_quantize_f32_to_i8(tmp, dims, out + r * out_pitch);
+    }
+    free(tmp);
+}
+
+int32_t orc_dot_i8(const int8_t* a, const int8_t* b, uint32_t n) {
+    /* vector_similarity.rs:1011-1016 */
+    int32_t s = 0;
+    for (uint32_t i = 0; i < n; i++) s += (int32_t)a[i] * (int32_t)b[i];
+    return s;
+}
+
+int orc_search_vector_i8(const int8_t* rows, const uint32_t* ids, uint64_t n_rows, uint32_t dims, uint32_t pitch,
+                         const int8_t* query, uint32_t k, orc_hit* hits, uint32_t* n_hits) {
+    if (!rows || !query || !hits) return -1;
+    if (pitch == 0) pitch = dims;
+    topk_t tk = { hits, 0, k };
+    for (uint64_t r = 0; r < n_rows; r++)
+        topk_push(&tk, ids ? ids[r] : r, (float)orc_dot_i8(query, rows + r * pitch, dims));   /* dot_i8(a, b) as f32 */
+    if (n_hits) *n_hits = tk.n;
+    return 0;
+}
+
 /* ------------------------------------------------------------------ RRF: search.rs:1962-2035 */
 int orc_rrf(const orc_hit* lex, uint32_t n_lex, const orc_hit* vec, uint32_t n_vec, orc_hit* out, uint32_t* n_out) {
     const float kf = 0.6f;

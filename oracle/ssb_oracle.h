@@ -95,6 +95,17 @@ int orc_search_vector(const float* rows, const uint32_t* doc_ids, uint64_t n_row
                       uint32_t row_pitch_floats, const float* query, uint32_t similarity, uint32_t k,
                       uint32_t use_lanes8, uint32_t n_threads, orc_hit* hits, uint32_t* n_hits);
 
+/* ---- int8 scalar quantisation (Cosine + Quantization::ScalarQuantizationI8) ----
+ * index time (vector.rs:585-640): normalize_f32 then quantize_f32_to_i8 = round(v*127) clamped to [-127,127]
+ * (vector_similarity.rs:1226-1232; Rust f32::round = half away from zero = roundf); scale = 1.
+ * query time: same normalise + quantise; similarity = dot_i8 as f32 (vector_similarity.rs:1011-1016, 193-206). */
+void  orc_quantize_f32_to_i8(const float* v, uint32_t n, int8_t* out);
+/* normalize_f32 + quantize_f32_to_i8 of every row (what index time does for Cosine + SQ-I8, vector.rs:585-640) */
+void  orc_quantize_rows_i8(const float* rows, uint64_t n_rows, uint32_t dims, uint64_t row_pitch_floats, int8_t* out, uint64_t out_pitch);
+int32_t orc_dot_i8(const int8_t* a, const int8_t* b, uint32_t n);
+int orc_search_vector_i8(const int8_t* rows, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims, uint32_t row_pitch,
+                         const int8_t* query, uint32_t k, orc_hit* hits, uint32_t* n_hits);
+
 /* ---- hybrid: search.rs:1962-2035 RRF k=0.6, rank from 0; then sort score desc (:2097-2121).
  * Tie order in the reference is hash-map iteration order; canonical here: doc id asc. */
 int orc_rrf(const orc_hit* lex, uint32_t n_lex, const orc_hit* vec, uint32_t n_vec,

@@ -25,7 +25,8 @@ class SsbHit(C.Structure):
 
 class SsbConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_batch", C.c_uint32), ("vector_dims", C.c_uint32),
-                ("vector_similarity", C.c_uint32), ("vector_kernel", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("vector_similarity", C.c_uint32), ("vector_kernel", C.c_uint32), ("vector_quantization", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
 
 
 class SsbLevelDesc(C.Structure):

@@ -44,7 +44,7 @@ int32_t encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint6
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
-    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = fn(out, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return SSB_E_CUDA; }
@@ -69,8 +69,10 @@ struct ssb_index {
     std::mutex mu;
     LexIndex* lex = nullptr;
     // vector index
-    uint32_t dims = 0, dpad = 0;
+    uint32_t dims = 0, dpad = 0, dpad8 = 0;
+    bool quant_i8 = false;            // Cosine + ScalarQuantizationI8: int8 corpus, exact int32 dot products
     DevBuf<float> rows;
+    DevBuf<int8_t> rows_i8, q_i8;
     DevBuf<uint32_t> doc_ids;
     uint64_t n_rows = 0;
     // query workspace
@@ -91,12 +93,13 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     // AUTO (measured, 1M x 768): one FP32 pass of 16 queries takes 0.53 ms, one tensor-core pass of up to 128 queries
     // 0.81 ms -> FP32 scan for <= 16 queries, tensor-core scan above.  Euclidean always takes the FP32 scan.
     uint32_t kern = ix->cfg.vector_kernel;
+    if (ix->quant_i8) kern = SSB_VEC_KERNEL_TCGEN05;   // one kernel for the int8 corpus: tcgen05 kind::i8, 128-query tile
     if (kern == SSB_VEC_KERNEL_AUTO) kern = nq > 16 ? SSB_VEC_KERNEL_TCGEN05_BF16 : SSB_VEC_KERNEL_FFMA;
     const bool use_tc = kern >= SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN;
     const bool tc_bf16 = kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64;
     const uint32_t qt = !use_tc ? vec::VEC_QT : ((kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : 128u);
     const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
-    SSB_TRY(ix->qpad.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
+    if (!ix->quant_i8) SSB_TRY(ix->qpad.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
     const float* qsrc = queries;
     if (!dev_ptr(queries)) {
         SSB_TRY(ix->qstage.reserve((size_t)nq * ix->dims, 0, ix->st));
@@ -104,6 +107,11 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
         ix->stats.h2d_bytes += (uint64_t)nq * ix->dims * 4;
         qsrc = ix->qstage.p;
     }
+    if (ix->quant_i8) {
+        // the query is normalised and quantised exactly like the corpus (search.rs:1464-1475, vector_similarity.rs:1226-1232)
+        SSB_TRY(ix->q_i8.reserve((size_t)nq_pad * ix->dpad8, 0, ix->st));
+        SSB_TRY(vec::launch_quantize_rows_i8(qsrc, ix->dims, nq, nq_pad, ix->dims, ix->q_i8.p, ix->dpad8, ix->st));
+    } else
     SSB_TRY(vec::launch_prep_queries(qsrc, nq, ix->dims, ix->dims, ix->qpad.p, nq_pad, ix->dpad,
                                      ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->st));
     ix->stats.kernel_launches += 1;
@@ -119,7 +127,10 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     a.thr_buf = reinterpret_cast<uint32_t*>(merged + (size_t)nq_pad * LIST);
     a.ceil_keys = ceil_dev;
     a.launches = &ix->stats.kernel_launches;
-    if (use_tc) {
+    if (ix->quant_i8) {
+        a.rows_i8 = ix->rows_i8.p; a.queries_i8 = ix->q_i8.p; a.dpad8 = ix->dpad8;
+        SSB_TRY(vec::launch_scan_tc(a, 128, 2, ix->st));
+    } else if (use_tc) {
         SSB_TRY(ix->qhi.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         SSB_TRY(ix->qlo.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
         a.q_hi = ix->qhi.p; a.q_lo = ix->qlo.p;
@@ -128,7 +139,7 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
         SSB_TRY(vec::launch_scan_ffma(a, ix->st));
     }
     SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, ix->st));
-    ix->stats.algorithmic_bytes += (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * 4;
+    ix->stats.algorithmic_bytes += (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * (ix->quant_i8 ? 1 : 4);
     return SSB_OK;
 }
 
@@ -203,6 +214,11 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device visible: libseekstorm_b200 has no CPU fallback"); return SSB_E_NO_DEVICE; }
     if (cfg->device < 0 || cfg->device >= ndev) { set_error("device %d out of range (%d visible)", cfg->device, ndev); return SSB_E_INVALID; }
     if (cfg->vector_similarity > SSB_SIM_EUCLIDEAN) { set_error("bad vector_similarity"); return SSB_E_INVALID; }
+    if (cfg->vector_quantization > SSB_QUANT_SCALAR_I8) { set_error("bad vector_quantization"); return SSB_E_INVALID; }
+    if (cfg->vector_quantization == SSB_QUANT_SCALAR_I8 && cfg->vector_similarity != SSB_SIM_COSINE) {
+        // Dot / Euclidean + SQ carry per-vector scale / zero point (vector.rs:597-660): not built
+        set_error("ScalarQuantizationI8 is built for Cosine similarity only"); return SSB_E_UNSUPPORTED;
+    }
     SSB_CUDA_TRY(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
     SSB_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
@@ -219,6 +235,8 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     ix->lex->set_events(ix->ev0, ix->ev1);
     ix->dims = cfg->vector_dims;
     ix->dpad = (cfg->vector_dims + 31) / 32 * 32;
+    ix->dpad8 = (cfg->vector_dims + 127) / 128 * 128;
+    ix->quant_i8 = cfg->vector_quantization == SSB_QUANT_SCALAR_I8;
     *out = ix;
     return SSB_OK;
 }
@@ -228,7 +246,7 @@ int32_t ssb_destroy(ssb_index* ix) {
     cudaSetDevice(ix->cfg.device);
     cudaStreamSynchronize(ix->st);
     delete ix->lex;
-    ix->rows.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->qhi.release(); ix->qlo.release(); ix->ceil.release(); ix->scratch.release();
+    ix->rows.release(); ix->rows_i8.release(); ix->q_i8.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->qhi.release(); ix->qlo.release(); ix->ceil.release(); ix->scratch.release();
     ix->keys_a.release(); ix->keys_b.release(); ix->counts.release();
     cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1);
     cudaStreamDestroy(ix->own_st);
@@ -269,11 +287,19 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
     std::lock_guard<std::mutex> g(ix->mu);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     if (n == 0) return SSB_OK;
-    SSB_TRY(ix->rows.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, ix->st));
     SSB_TRY(ix->doc_ids.reserve(ix->n_rows + n, ix->n_rows, ix->st));
-    float* dst = ix->rows.p + ix->n_rows * ix->dpad;
-    SSB_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ix->dpad * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, ix->st));
-    SSB_TRY(vec::launch_normalize_rows(dst, n, dims, ix->dpad, ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->st));
+    if (ix->quant_i8) {
+        // index-time normalise + quantise (vector.rs:585-640); the f32 rows are only staged
+        SSB_TRY(ix->rows_i8.reserve((ix->n_rows + n) * ix->dpad8, ix->n_rows * ix->dpad8, ix->st));
+        SSB_TRY(ix->qstage.reserve((size_t)n * dims, 0, ix->st));
+        SSB_CUDA_TRY(cudaMemcpy2DAsync(ix->qstage.p, (size_t)dims * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, ix->st));
+        SSB_TRY(vec::launch_quantize_rows_i8(ix->qstage.p, dims, n, n, dims, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8, ix->st));
+    } else {
+        SSB_TRY(ix->rows.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, ix->st));
+        float* dst = ix->rows.p + ix->n_rows * ix->dpad;
+        SSB_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ix->dpad * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, ix->st));
+        SSB_TRY(vec::launch_normalize_rows(dst, n, dims, ix->dpad, ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->st));
+    }
     const uint16_t* lid = local_ids; uint16_t* tmp = nullptr;
     if (local_ids && !dev_ptr(local_ids)) {
         SSB_CUDA_TRY(cudaMalloc(&tmp, (size_t)n * 2));

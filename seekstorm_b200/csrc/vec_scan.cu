@@ -239,6 +239,38 @@ __global__ void normalize_rows(float* __restrict__ rows, uint64_t n, uint32_t di
     for (uint32_t i = lane; i < dpad; i += 32) r[i] = i < dims ? r[i] * f : 0.f;
 }
 
+// Cosine + ScalarQuantizationI8: normalize_f32 (vector_similarity.rs:70-74) then quantize_f32_to_i8 (:1226-1232), done
+// at index time for the corpus (vector.rs:585-640) and per query.  One warp per row.  The squared norm is accumulated
+// strictly left to right with individually rounded multiplies / adds (the reference's scalar `.map(|x| x*x).sum()`), so
+// the int8 codes — and with them every int32 dot product — are bit-identical to the CPU's: the sequential chain runs
+// redundantly in all lanes over shuffled products.
+__global__ void quantize_rows_i8(const float* __restrict__ src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims,
+                                 int8_t* __restrict__ dst, uint32_t dpad8) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_out) return;
+    int8_t* o = dst + row * dpad8;
+    if (row >= n) { for (uint32_t i = lane; i < dpad8; i += 32) o[i] = 0; return; }
+    const float* r = src + row * src_stride;
+    float s = 0.0f;
+    for (uint32_t base = 0; base < dims; base += 32) {
+        const float v = base + lane < dims ? r[base + lane] : 0.0f;
+        const float p = __fmul_rn(v, v);
+#pragma unroll
+        for (int l = 0; l < 32; l++) s = __fadd_rn(s, __shfl_sync(FULL, p, l));   // out-of-range products are +0: exact no-ops
+    }
+    const float f = __fdiv_rn(1.0f, __fsqrt_rn(s));
+    for (uint32_t i = lane; i < dpad8; i += 32) {
+        int8_t q = 0;
+        if (i < dims) {
+            float x = roundf(__fmul_rn(__fmul_rn(r[i], f), 127.0f));    // Rust f32::round: half away from zero
+            x = fminf(fmaxf(x, -127.0f), 127.0f);
+            q = x == x ? (int8_t)x : (int8_t)0;                          // NaN (all-zero vector) `as i8` = 0
+        }
+        o[i] = q;
+    }
+}
+
 __global__ void fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (level_id << 16) | (local_ids ? (uint32_t)local_ids[i] : i);
@@ -316,6 +348,14 @@ int32_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dims, uint64_t
                             uint32_t nq_pad, uint32_t dpad, int normalize, cudaStream_t st) {
     if (nq_pad == 0) return SSB_OK;
     prep_queries<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, dims, qstride, out, nq_pad, dpad, normalize);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_quantize_rows_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, int8_t* dst,
+                                uint32_t dpad8, cudaStream_t st) {
+    if (n_out == 0) return SSB_OK;
+    quantize_rows_i8<<<(unsigned)((n_out + 7) / 8), 256, 0, st>>>(src, src_stride, n, n_out, dims, dst, dpad8);
     SSB_CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

@@ -28,6 +28,10 @@ struct ScanArgs {
     const uint32_t* thr_init = nullptr;            // internal: initial thresholds (ordered-uint scores) or null
     const uint64_t* ceil_keys = nullptr;           // [nq_pad] exclusive key ceilings for paging beyond 32 results, or null
     uint64_t* launches = nullptr;                  // incremented once per kernel launched (ssb_stats.kernel_launches)
+    const int8_t* rows_i8 = nullptr;               // int8 path: [n_rows][dpad8] quantised corpus
+    const int8_t* queries_i8 = nullptr;            //            [nq_pad][dpad8] quantised queries
+    uint32_t dpad8 = 0;                            //            multiple of 128
+    bool sample_groupmax = false;                  // internal (int8): threshold-seeding pass, writes thr_buf instead of lists
 };
 
 // rows scanned first to seed the per-query top-k thresholds (0 = shard too small to bother).  With S sample rows the full
@@ -44,7 +48,7 @@ inline uint64_t vec_presample_rows(uint64_t n_rows, bool tensor_core) {
 
 int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);
-int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128*/, int bf16 /*0: 3xTF32, 1: 3xBF16*/, cudaStream_t st);
+int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128*/, int prec /*0: 3xTF32, 1: 3xBF16, 2: int8 (exact)*/, cudaStream_t st);
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad);
 // lists laid out [group][n_lists][qt][32] -> out [nq][32]
 // thr[q] = ordered-uint score of the k-th entry of keys[q][32] (0 if the list is shorter)
@@ -52,6 +56,9 @@ void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_
 void merge_lists_generic(const uint64_t* in, uint32_t n_lists, uint32_t qt, uint32_t nq, uint64_t* out, cudaStream_t st);
 int32_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, float* out,
                             uint32_t nq_pad, uint32_t dpad, int normalize, cudaStream_t st);
+// f32 rows -> normalize_f32 + quantize_f32_to_i8 (bit-identical to the reference's scalar arithmetic); rows >= n are zero
+int32_t launch_quantize_rows_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, int8_t* dst,
+                                uint32_t dpad8, cudaStream_t st);
 int32_t launch_normalize_rows(float* rows, uint64_t n, uint32_t dims, uint32_t dpad, int normalize, cudaStream_t st);
 int32_t launch_fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n, cudaStream_t st);
 // in: [n_lists][nq][32] descending lists -> out [nq][32]

@@ -39,18 +39,24 @@ constexpr int A_BYTES = MT * A1_BYTES; // 32 KB
 constexpr int THREADS = 512;            // 16 warps: TMA, MMA, 2 idle, 4 epilogue, 8 splitters
 constexpr int SPLIT_THREADS = 256;
 constexpr int CHUNK = 8;               // query columns per epilogue step
-constexpr int STAGES = 2;
-enum { PREC_TF32 = 0, PREC_BF16 = 1 };
+enum { PREC_TF32 = 0, PREC_BF16 = 1, PREC_I8 = 2 };
 
-template <int NQ, int PREC> struct Cfg {
+constexpr int MAX_STAGES = 6;
+template <int NQ, int PREC, bool BRES = false> struct Cfg {
     // TF32: [A (-> A_hi in place) | A_lo | B_hi | B_lo], all f32 SWIZZLE_128B tiles
     // BF16: [A f32 | A1 bf16 | A2 bf16 | B1 bf16 | B2 bf16], bf16 tiles are 64-byte rows, SWIZZLE_64B
-    static constexpr int B_BYTES = PREC == PREC_TF32 ? NQ * KC * 4 : NQ * KC * 2;
+    // I8  : [A i8 | B i8]: the int8 corpus (quantised at load time) is the MMA operand as TMA delivers it — no splitter
+    //       pass, 128 dims per 128-byte swizzle row, 4 smem stages
+    static constexpr int STAGES = PREC == PREC_I8 ? 4 : 2;
+    static constexpr int KCE = PREC == PREC_I8 ? 128 : KC;                     // elements per k-chunk (128 bytes either way)
+    static constexpr int B_BYTES = PREC == PREC_BF16 ? NQ * KC * 2 : NQ * KC * 4;
     static constexpr int ALO_OFF = A_BYTES;                                    // TF32: A_lo   | BF16: A1
     static constexpr int A2_OFF = A_BYTES + A_BYTES / 2;                       // BF16: A2
-    static constexpr int B_OFF = 2 * A_BYTES;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TX_BYTES = A_BYTES + 2 * B_BYTES;
+    static constexpr int B_OFF = PREC == PREC_I8 ? A_BYTES : 2 * A_BYTES;
+    // BRES (int8 only): the whole quantised query block [n_kchunks][NQ x 128 B] stays resident in smem behind the A stages,
+    // so the per-stage L2->SM traffic is the corpus tile alone (stage count chosen at launch from what is left of 227 KB)
+    static constexpr int STAGE_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : 2 * A_BYTES + 2 * B_BYTES);
+    static constexpr int TX_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : A_BYTES + 2 * B_BYTES);
     static constexpr int SMEM = STAGES * STAGE_BYTES + NQ * 4 + 256;
     static constexpr int TMEM_COLS = 2 * MT * NQ;                              // double-buffered MT accumulators
 };
@@ -67,6 +73,9 @@ template <int PREC>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     if (PREC == PREC_TF32)
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    else if (PREC == PREC_I8)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
                      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
     else
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
@@ -89,14 +98,21 @@ __device__ __forceinline__ uint32_t bf16x2(float x, float y) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int NQ, int PREC>
+// int8 path: thresholds are kept as int32 dot products (scores are integer valued, so ord_f32((float)d) is monotone in d)
+__device__ __forceinline__ int ord_to_int(uint32_t o) {
+    return o == 0u ? INT_MIN : (o == 0xFFFFFFFFu ? INT_MAX : (int)unord_f32(o));
+}
+
+template <int NQ, int PREC, bool BRES>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
         const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*4][NQ][32]*/,
         const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/, uint32_t nq_valid,
-        const uint64_t* __restrict__ ceil_keys /*[gridDim.y*NQ] or null*/) {
-    using C = Cfg<NQ, PREC>;
+        const uint64_t* __restrict__ ceil_keys /*[gridDim.y*NQ] or null*/, uint32_t nst_rt,
+        uint32_t sample_mode /*int8 only: write per-(32-row group, query) score maxima instead of lists*/) {
+    using C = Cfg<NQ, PREC, BRES>;
+    const uint32_t STAGES = BRES ? nst_rt : (uint32_t)C::STAGES;
     // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for the swizzled
     // tiles) and pointers derived from it stay in the shared address space (LDS/STS instead of generic LD/ST)
     extern __shared__ __align__(1024) uint8_t base[];
@@ -104,26 +120,32 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     // per-query sorted lists live directly in this CTA's slice of the output scratch (global, L2-resident): they are
     // touched only on the rare candidate insert, and each (warp, query) list is always owned by the same warp
     uint64_t* lists = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 * NQ * LIST;   // [4 epilogue warps][NQ][32]
-    uint32_t* thr_u = (uint32_t*)(base + STAGES * C::STAGE_BYTES);            // [NQ] ordered-uint score thresholds
+    uint8_t* bres = base + STAGES * C::STAGE_BYTES;                           // BRES: resident query block
+    uint32_t* thr_u = (uint32_t*)(bres + (BRES ? n_kchunks * C::B_BYTES : 0)); // [NQ] ordered-uint score thresholds
     uint64_t* bars = (uint64_t*)(thr_u + NQ);
-    uint64_t* full = bars;                 // [STAGES]
-    uint64_t* split = full + STAGES;       // [STAGES]
-    uint64_t* empty = split + STAGES;      // [STAGES]
-    uint64_t* tfull = empty + STAGES;      // [2]
-    uint64_t* tempty = tfull + 2;          // [2]
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint64_t* full = bars;                     // [STAGES]
+    uint64_t* split = full + MAX_STAGES;       // [STAGES]
+    uint64_t* empty = split + MAX_STAGES;      // [STAGES]
+    uint64_t* tfull = empty + MAX_STAGES;      // [2]
+    uint64_t* tempty = tfull + 2;              // [2]
+    uint64_t* bfull = tempty + 2;              // BRES: query block landed
+    uint32_t* tmem_slot = (uint32_t*)(bfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t group = blockIdx.y;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&split[s], SPLIT_THREADS / 32); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        mbar_init(bfull, 1);
+        for (uint32_t s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&split[s], SPLIT_THREADS / 32); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PREC == PREC_I8 ? 12 : 4); }
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < NQ; i += THREADS)   // seeded by the pre-sample pass when present
-        thr_u[i] = blockIdx.y * NQ + i >= nq_valid ? 0xFFFFFFFFu   // zero-padded query slot: unreachable threshold
-                                                   : (thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u);
+    for (int i = threadIdx.x; i < NQ; i += THREADS) {  // seeded by the pre-sample pass when present
+        uint32_t t = blockIdx.y * NQ + i >= nq_valid ? 0xFFFFFFFFu   // zero-padded query slot: unreachable threshold
+                                                     : (thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u);
+        if (PREC == PREC_I8) t = (uint32_t)ord_to_int(t);            // int8 path compares the raw int32 dot products
+        thr_u[i] = t;
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -138,15 +160,20 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         if (lane == 0) {
             tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
             uint32_t it = 0;
+            if (BRES) {
+                mbar_arrive_expect_tx(bfull, n_kchunks * C::B_BYTES);
+                for (uint32_t kc = 0; kc < n_kchunks; ++kc)
+                    tma_load_2d(bres + kc * C::B_BYTES, &tmBh, (int)(kc * C::KCE), (int)(group * NQ), bfull);
+            }
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
                     uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     uint8_t* st = stage0 + s * C::STAGE_BYTES;
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&full[s], C::TX_BYTES);
-                    tma_load_2d(st, &tmA, (int)(kc * KC), (int)(tile * TROWS), &full[s]);   // 256-row box = MT swizzled tiles
-                    tma_load_2d(st + C::B_OFF, &tmBh, (int)(kc * KC), (int)(group * NQ), &full[s]);
-                    tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmBl, (int)(kc * KC), (int)(group * NQ), &full[s]);
+                    tma_load_2d(st, &tmA, (int)(kc * C::KCE), (int)(tile * TROWS), &full[s]);   // 256-row box = MT swizzled tiles
+                    if (!BRES) tma_load_2d(st + C::B_OFF, &tmBh, (int)(kc * C::KCE), (int)(group * NQ), &full[s]);
+                    if (PREC != PREC_I8) tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmBl, (int)(kc * C::KCE), (int)(group * NQ), &full[s]);
                 }
             }
         }
@@ -155,9 +182,12 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         if (lane == 0) {
             // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (tf32 = 2, bf16 = 1), both K-major,
             // N>>3 at bit 17, M>>4 at bit 24
+            // (kind::i8: D = s32 (2 at bit 4), A/B format 1 = signed int8)
             constexpr uint32_t fmt = PREC == PREC_TF32 ? 2u : 1u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            constexpr uint32_t cfmt = PREC == PREC_I8 ? 2u : 1u;
+            const uint32_t idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t it = 0, ti = 0;
+            if (BRES) mbar_wait(bfull, 0);
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
                 const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
                 mbar_wait(&tempty[buf], tph ^ 1u);
@@ -166,10 +196,19 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
                     uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&full[s], ph);
-                    mbar_wait(&split[s], ph);
+                    if (PREC != PREC_I8) mbar_wait(&split[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stage0 + s * C::STAGE_BYTES);
-                    if (PREC == PREC_TF32) {
+                    if (PREC == PREC_I8) {
+                        const uint64_t a = umma_desc_k128(sa), b = umma_desc_k128(BRES ? smem_u32(bres + kc * C::B_BYTES) : sa + C::B_OFF);
+#pragma unroll
+                        for (uint32_t m = 0; m < MT; m++) {
+                            const uint64_t am = (uint64_t)((m * A1_BYTES) >> 4);
+#pragma unroll
+                            for (uint32_t kk = 0; kk < 4; kk++)          // 4 x K=32 int8 (32 bytes) inside the 128-byte swizzle row
+                                umma<PREC>(d + m * NQ, a + am + (uint64_t)(kk * 2), b + (uint64_t)(kk * 2), idesc, (kc | kk) != 0);
+                        }
+                    } else if (PREC == PREC_TF32) {
                         const uint64_t a_hi = umma_desc_k128(sa), a_lo = umma_desc_k128(sa + C::ALO_OFF);
                         const uint64_t b_hi = umma_desc_k128(sa + C::B_OFF), b_lo = umma_desc_k128(sa + C::B_OFF + C::B_BYTES);
 #pragma unroll
@@ -203,7 +242,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && PREC != PREC_I8) {
         // ===================== splitters: f32 corpus tile -> (hi, lo) operand tiles =====================
         const int t = threadIdx.x - 256;   // 0..SPLIT_THREADS-1
         uint32_t it = 0;
@@ -252,7 +291,90 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 if (lane == 0) mbar_arrive(&split[s]);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && PREC == PREC_I8) {
+        // ===================== int8 epilogue: 12 warps = 4 TMEM lane quadrants x 3 query-column groups =====================
+        // With the int8 operands the MMA + smem side of a 128-query pass costs a fraction of the HBM time, so the epilogue
+        // (one compare + ballot per (row, query) pair) is what has to keep up: the 8 warps that are splitters in the f32
+        // variants join in.  Warp (quadrant ew, group g) owns the 16-query column chunks c = g, g+3, ... for both M tiles,
+        // and with them the lists (ew, q) of those queries — the scratch layout is the same as in the 4-warp epilogue.
+        const int ew = warp & 3, g = (warp - 4) >> 2;
+        int* thr_i = (int*)thr_u;
+        uint64_t* mylists = lists + (size_t)ew * NQ * LIST;
+        if (!sample_mode)
+            for (int c = g; c < NQ / 16; c += 3)
+                for (int i = lane; i < 16 * LIST; i += 32) mylists[c * 16 * LIST + i] = 0;
+        __syncwarp();
+        // sample mode (threshold seeding): no lists.  Every (tile, m, quadrant) is a group of 32 rows; per query the group's
+        // best score goes to gmax[query][group].  The k-th largest group maximum is a valid lower bound of the k-th best score
+        // (k groups each hold a row at least that good) and, for k << #groups, nearly as tight as an exact k-th of the sample.
+        int* gmax = (int*)scratch;                       // [gridDim.y * NQ][n_tiles * 8]
+        const uint32_t n_rg = n_tiles * (MT * 4);
+        uint32_t ti = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
+            mbar_wait(&tfull[buf], tph);
+            tc_fence_after();
+            for (int m = 0; m < MT; m++) {
+                const uint32_t row = tile * TROWS + (uint32_t)(m * TM) + (uint32_t)(ew * 32 + lane);
+                const bool valid = row < n_rows;
+                for (int c = g; c < NQ / 16; c += 3) {
+                    uint32_t v[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * (MT * NQ) + m * NQ + c * 16;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                 : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (sample_mode) {
+                        int keep = INT_MIN;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            int d = valid ? (int)v[j] : INT_MIN;
+                            if (ceil_keys && valid) {   // paging: rows already returned by an earlier page do not count
+                                const uint64_t key = ((uint64_t)ord_f32((float)d) << 32) | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
+                                if (key >= __ldg(&ceil_keys[blockIdx.y * NQ + c * 16 + j])) d = INT_MIN;
+                            }
+                            const int mx = __reduce_max_sync(FULL, d);
+                            if (lane == j) keep = mx;
+                        }
+                        if (lane < 16)
+                            gmax[(size_t)(blockIdx.y * NQ + c * 16 + lane) * n_rg + (tile * (MT * 4) + m * 4 + ew)] = keep;
+                        continue;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int q = c * 16 + j;
+                        const int d = (int)v[j];
+                        const bool pass = valid && d >= thr_i[q];
+                        unsigned pm = __ballot_sync(FULL, pass);
+                        if (pm) {                                           // rare after warm-up
+                            uint64_t key = 0;
+                            if (pass) key = ((uint64_t)ord_f32((float)d) << 32)   // dot_i8 as f32: exact below 2^24
+                                            | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
+                            if (ceil_keys) {
+                                const uint64_t ceil = __ldg(&ceil_keys[blockIdx.y * NQ + q]);
+                                if (key >= ceil) key = 0;
+                                pm = __ballot_sync(FULL, key != 0);
+                                if (!pm) continue;
+                            }
+                            uint64_t L = mylists[q * LIST + lane];
+                            if (__popc(pm) > 3) {
+                                L = wl_merge(L, wl_sort_desc(key, lane), lane);
+                            } else {
+                                while (pm) { const int src = __ffs(pm) - 1; pm &= pm - 1; wl_insert(L, shfl64(key, src), lane); }
+                            }
+                            mylists[q * LIST + lane] = L;
+                            const uint32_t kth = (uint32_t)(shfl64(L, (int)k - 1) >> 32);
+                            if (lane == 0 && kth) atomicMax(&thr_i[q], ord_to_int(kth));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    } else if (warp >= 4 && warp < 8) {
         // ===================== epilogue: TMEM -> filter -> per-warp per-query top-k (no CTA-level barriers) =====================
         // Each epilogue warp owns the 32 TMEM lanes (= corpus rows) of its quadrant and keeps its own sorted list per
         // query.  The per-query threshold (ordered-uint score of the best k-th entry any warp of the CTA has seen, seeded
@@ -282,7 +404,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 #pragma unroll
                 for (int j = 0; j < CHUNK; j++) {
                     const int q = c * CHUNK + j;
-                    const float sc = __uint_as_float(v[j]);
+                    const float sc = PREC == PREC_I8 ? (float)(int32_t)v[j] /* dot_i8 as f32, exact below 2^24 */ : __uint_as_float(v[j]);
                     const uint32_t so = ord_f32(sc);
                     const bool pass = valid && sc == sc && so >= thr_u[q];
                     unsigned pm = __ballot_sync(FULL, pass);
@@ -339,47 +461,96 @@ __global__ void split_queries_bf16(const float* __restrict__ q, __nv_bfloat16* _
     lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
+// thr[q] = ordered-uint of the k-th largest of gmax[q][0..n_rg) as an f32 score (0 = no threshold when fewer than k groups
+// hold an eligible row).  One warp per query, lane-distributed sorted list, chunks that cannot enter the list are skipped.
+__global__ void kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, uint32_t nq, uint32_t k, uint32_t* __restrict__ thr) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int* g = gmax + (size_t)q * n_rg;
+    uint64_t L = 0;
+    for (uint32_t base = 0; base < n_rg; base += 32) {
+        const uint32_t i = base + lane;
+        const int v = i < n_rg ? g[i] : INT_MIN;
+        // key: biased value in the high word (> 0 for every eligible row), group index below it keeps keys distinct
+        const uint64_t key = v == INT_MIN ? 0ull : (((uint64_t)((uint32_t)v ^ 0x80000000u)) << 32) | (uint64_t)(0xFFFFFFFFu - i);
+        const uint64_t kth = shfl64(L, (int)k - 1);
+        if (__any_sync(FULL, key > kth)) L = wl_merge(L, wl_sort_desc(key, lane), lane);
+    }
+    const uint64_t kth = shfl64(L, (int)k - 1);
+    if (lane == 0) thr[q] = kth ? ord_f32((float)(int)((uint32_t)(kth >> 32) ^ 0x80000000u)) : 0u;
+}
+
 }  // namespace tc
 
-template <int NQ, int PREC>
+template <int NQ, int PREC, bool BRES = false>
 static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
-    using C = tc::Cfg<NQ, PREC>;
+    using C = tc::Cfg<NQ, PREC, BRES>;
     CUtensorMap tmA, tmBh, tmBl;
     uint32_t n_tiles = (uint32_t)((a.n_rows + tc::TROWS - 1) / tc::TROWS);
     uint32_t n_groups = a.nq_pad / NQ;
     size_t nel = (size_t)a.nq_pad * a.dpad;
-    SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TROWS, 1));
-    if (PREC == tc::PREC_TF32) {
+    uint32_t n_kchunks = a.dpad / tc::KC;
+    if constexpr (PREC == tc::PREC_I8) {
+        // int8 corpus / queries (quantised by the caller): 128 dims per 128-byte swizzle row
+        SSB_TRY(encode_tmap_2d(&tmA, a.rows_i8, 1, a.dpad8, a.n_rows, a.dpad8, 128, tc::TROWS, 128));
+        SSB_TRY(encode_tmap_2d(&tmBh, a.queries_i8, 1, a.dpad8, a.nq_pad, a.dpad8, 128, NQ, 128));
+        tmBl = tmBh;
+        n_kchunks = a.dpad8 / 128;
+    } else if constexpr (PREC == tc::PREC_TF32) {
+        SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TROWS, 1));
         SSB_TRY(encode_tmap_2d_f32(&tmBh, a.q_hi, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
         SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
         tc::split_queries_tf32<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, a.q_hi, a.q_lo, nel);
     } else {
         // the two bf16 parts live in the q_hi / q_lo buffers (half of each is used)
+        SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TROWS, 1));
         SSB_TRY(encode_tmap_2d(&tmBh, a.q_hi, 2 /*bf16*/, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, tc::KC, NQ, 64));
         SSB_TRY(encode_tmap_2d(&tmBl, a.q_lo, 2 /*bf16*/, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, tc::KC, NQ, 64));
         tc::split_queries_bf16<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, (__nv_bfloat16*)a.q_hi, (__nv_bfloat16*)a.q_lo, nel);
     }
     uint32_t gx = n_tiles < (uint32_t)a.n_sms ? n_tiles : (uint32_t)a.n_sms;
     if ((size_t)n_groups * gx * 4 * NQ * LIST * 8 > a.scratch_bytes) { set_error("vector scan scratch too small"); return SSB_E_STATE; }
+    constexpr int SMEM_MAX = 232448;   // 227 KB opt-in limit per CTA
+    uint32_t nst = C::STAGES;
+    int smem = C::SMEM;
+    if (BRES) {   // resident query block + as many corpus stages as fit (launch_scan_tc_impl guarantees >= 3)
+        const int fixed = (int)n_kchunks * C::B_BYTES + NQ * 4 + 256;
+        nst = (uint32_t)((SMEM_MAX - fixed) / C::STAGE_BYTES);
+        if (nst > (uint32_t)tc::MAX_STAGES) nst = tc::MAX_STAGES;
+        smem = fixed + (int)nst * C::STAGE_BYTES;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ, PREC, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRES ? SMEM_MAX : C::SMEM));
         attr_set = true;
     }
     if (a.ev0) cudaEventRecord(a.ev0, st);
-    tc::scan_tc<NQ, PREC><<<dim3(gx, n_groups), tc::THREADS, C::SMEM, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, a.dpad / tc::KC, n_tiles,
-                                                                             a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys);
+    tc::scan_tc<NQ, PREC, BRES><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
+                                                                             a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, nst,
+                                                                             a.sample_groupmax ? 1u : 0u);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
+    if (a.sample_groupmax) {   // threshold seeding pass: scratch holds gmax[nq_pad][n_tiles * 8]
+        tc::kth_from_groupmax<<<(a.nq_pad + 7) / 8, 256, 0, st>>>((const int*)a.scratch, n_tiles * (tc::MT * 4), a.nq_pad, a.k, a.thr_buf);
+        SSB_CUDA_TRY(cudaGetLastError());
+        if (a.launches) *a.launches += 2;
+        return SSB_OK;
+    }
     // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ
     merge_lists_generic(a.scratch, gx * 4, NQ, a.nq_pad, a.keys_out, st);
     SSB_CUDA_TRY(cudaGetLastError());
-    if (a.launches) *a.launches += 3;   // query split + scan + merge
+    if (a.launches) *a.launches += PREC == tc::PREC_I8 ? 2 : 3;   // (query split +) scan + merge
     return SSB_OK;
 }
 
 static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream_t st) {
     if (a.n_rows == 0 || a.nq_pad == 0) return SSB_OK;
+    if (bf16 == 2) {
+        if (nq_tile != 128 || a.nq_pad % 128 != 0 || !a.rows_i8 || !a.queries_i8 || a.dpad8 % 128) { set_error("int8 scan: bad arguments"); return SSB_E_INVALID; }
+        // query block resident in smem when it leaves room for >= 3 corpus stages (dims <= 1024), else streamed per stage
+        return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true>(a, st) : launch_tc_n<128, tc::PREC_I8, false>(a, st);
+    }
     if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }
     if ((nq_tile != 64 && nq_tile != 128) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 scan: query count must be padded to the 64/128 query tile"); return SSB_E_INVALID; }
     if (bf16) return nq_tile == 64 ? launch_tc_n<64, tc::PREC_BF16>(a, st) : launch_tc_n<128, tc::PREC_BF16>(a, st);
@@ -391,6 +562,20 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream
     if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, bf16, st);
     ScanArgs pre = a;
     pre.n_rows = vec_presample_rows(a.n_rows, true); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
+    if (bf16 == 2) {
+        // int8: the sample pass is latency-bound on its insert storms, one 256-row tile per CTA costs the same for 30 CTAs
+        // as for all of them — sample one tile per SM (ncu: the full scan's epilogue warps otherwise spend a third of their
+        // time waiting on list loads for candidates a better seed rejects)
+        uint64_t s = (uint64_t)a.n_sms * tc::TROWS;
+        if (s > a.n_rows / 4) s = a.n_rows / 4 / tc::TROWS * tc::TROWS;
+        if (s > pre.n_rows) pre.n_rows = s;
+        // group-maxima sample mode: no lists, no insert storm; writes the thresholds straight into thr_buf
+        pre.sample_groupmax = true; pre.thr_buf = a.thr_buf;
+        SSB_TRY(launch_scan_tc_impl(pre, nq_tile, bf16, st));
+        ScanArgs full = a;
+        full.thr_init = a.thr_buf;
+        return launch_scan_tc_impl(full, nq_tile, bf16, st);
+    }
     SSB_TRY(launch_scan_tc_impl(pre, nq_tile, bf16, st));
     launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
     if (a.launches) *a.launches += 1;

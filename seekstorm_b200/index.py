@@ -126,10 +126,12 @@ class Index:
 
     def __init__(self, device: int = 0, vector_dims: int = 0,
                  vector_similarity: VectorSimilarity = VectorSimilarity.Cosine, max_batch: int = 4096,
-                 term_key_fn: Callable[[str], int] = synthetic_term_key, vector_kernel: int = 0):
+                 term_key_fn: Callable[[str], int] = synthetic_term_key, vector_kernel: int = 0,
+                 vector_quantization: int = 0):
         """vector_kernel: 0 = auto, 1 = FP32 FFMA scan, 2 = tcgen05 (3xTF32) scan."""
         self._h = C.c_void_p()
-        cfg = SsbConfig(device, max_batch, vector_dims, int(vector_similarity), vector_kernel, (C.c_uint32 * 3)(0, 0, 0))
+        cfg = SsbConfig(device, max_batch, vector_dims, int(vector_similarity), vector_kernel, int(vector_quantization),
+                        (C.c_uint32 * 2)(0, 0))
         check(lib().ssb_create(C.byref(cfg), C.byref(self._h)))
         self.vector_dims = vector_dims
         self.vector_similarity = VectorSimilarity(vector_similarity)

@@ -45,3 +45,37 @@ def test_c2_full_size_vector():
         for (gd, gsc), (wd, wsc) in zip(got[i], want):
             assert gd == wd or abs(gsc - wsc) <= 1e-4 * abs(wsc)
     ix.close()
+
+
+def test_c2_full_size_vector_int8():
+    """C2 corpus with Cosine + ScalarQuantizationI8: bit-exact ids and integer scores against the oracle's quantiser +
+    an exact CPU scoring (f32 BLAS over int8 values: every partial sum is an integer below 2^24)."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    n, d = 1_000_000, 768
+    rows = synth.gen_vectors(n, d, 1002, "cuda")
+    ix = Index(0, vector_dims=d, vector_similarity=VectorSimilarity.Cosine, vector_quantization=1)
+    ix.add_vectors(rows)
+    assert ix.vector_count == n
+    q = synth.gen_vectors(200, d, 2002, "cuda")
+    planted = torch.arange(0, 200, 3, device="cuda") * 20011 % n
+    q[::3] = rows[planted] + 0.05 * q[::3]
+    qh = q.cpu().numpy()
+    got = ix.search_vector_batch(qh, 10)
+    for j, p in enumerate(planted.tolist()):
+        assert got[3 * j][0][0] == p
+    assert ix.search_vector_batch(qh[5:12], 10) == got[5:12]        # batch-composition invariance, bit-exact
+    rows_h = rows.cpu().numpy()
+    r8 = O.quantize_rows_i8(rows_h)
+    q8 = O.quantize_rows_i8(qh)
+    sel = [0, 1, 2, 7, 100, 199]
+    qf = q8[sel].astype(np.float32)
+    best = [[] for _ in sel]
+    for s in range(0, n, 100_000):
+        sc = r8[s:s + 100_000].astype(np.float32) @ qf.T
+        for j in range(len(sel)):
+            idx = np.argpartition(-sc[:, j], 64)[:64]
+            best[j] += [(-float(sc[i, j]), s + int(i)) for i in idx]
+    for j, qi in enumerate(sel):
+        want = [(doc, -negs) for negs, doc in sorted(best[j])[:10]]
+        assert got[qi] == want, (qi, got[qi][:3], want[:3])
+    ix.close()

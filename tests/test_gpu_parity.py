@@ -241,3 +241,52 @@ def test_vector_tcgen05_parity(n, dims, sim, kernel):
             q = O.normalize(qs[i]) if sim == "cos" else qs[i]
             _check_vec(got[i], O.search_vector(ref_rows, q, k, osim))
     ix.close()
+
+
+def _i8_want(r8, q8, k):
+    """exact int32 scores via f32 BLAS (every partial sum is an integer < 2^24), canonical tie rule"""
+    sc = r8.astype(np.float32) @ q8.astype(np.float32).T            # [n, nq]
+    out = []
+    for j in range(sc.shape[1]):
+        order = np.lexsort((np.arange(sc.shape[0]), -sc[:, j]))[:k]
+        out.append([(int(i), float(sc[i, j])) for i in order])
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dims", [(1, 32), (300, 100), (5000, 128), (5000, 768), (70000, 200), (140000, 64), (3000, 1100)])
+def test_vector_int8_parity(n, dims):
+    """Cosine + ScalarQuantizationI8 (SURVEY §8f row 2): tcgen05 kind::i8 scan, BIT-EXACT ids and scores vs the oracle."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    rows = synth.gen_vectors(n, dims, 5000 + n, "cpu").numpy()
+    qs = synth.gen_vectors(150, dims, 6000 + n, "cpu").numpy()      # 150 -> padded to 256 = two query groups
+    qs[3] = rows[n // 2] + 0.05 * qs[3]
+    ix = Index(0, vector_dims=dims, vector_similarity=VectorSimilarity.Cosine, vector_quantization=1)
+    ix.add_vectors(rows)
+    assert ix.vector_count == n
+    r8 = O.quantize_rows_i8(rows)
+    q8 = O.quantize_rows_i8(qs)
+    for k in (1, 10, 32, 100):
+        got = ix.search_vector_batch(qs, k)
+        want = _i8_want(r8, q8, k)
+        for i in range(len(qs)):
+            assert got[i] == want[i], (i, k, got[i][:3], want[i][:3])
+    # and against the C oracle's own scan for a few queries
+    got = ix.search_vector_batch(qs[:5], 10)
+    for i in range(5):
+        assert got[i] == O.search_vector_i8(r8, q8[i], 10)
+    assert got[3][0][0] == n // 2
+    # single query (padding slots must stay empty), device-resident queries
+    one = ix.search_vector_batch(torch.from_numpy(qs[7:8]).cuda(), 10)
+    assert one[0] == _i8_want(r8, q8[7:8], 10)[0]
+    ix.close()
+
+
+@pytest.mark.gpu
+def test_vector_int8_config_errors():
+    from seekstorm_b200 import Index, VectorSimilarity
+    from seekstorm_b200._lib import SsbError
+    with pytest.raises(SsbError):
+        Index(0, vector_dims=64, vector_similarity=VectorSimilarity.Dot, vector_quantization=1)
+    with pytest.raises(SsbError):
+        Index(0, vector_dims=64, vector_quantization=7)

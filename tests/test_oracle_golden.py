@@ -127,3 +127,35 @@ def test_vector_topk_canonical_ties():
     assert hits == [(7, 5.0), (8, 5.0), (3, 3.0), (4, 3.0)]
     hits_mt = O.search_vector(rows, q, 4, O.SIM_DOT, n_threads=3)
     assert hits_mt == hits
+
+
+def test_int8_quantisation_known_answers():
+    """quantize_f32_to_i8 (vector_similarity.rs:1226-1232): round half AWAY from zero, clamp to [-127, 127]; dot_i8 exact."""
+    v = np.array([0.5 / 127, -0.5 / 127, 1.5 / 127, 2.5 / 127, 2.0, -3.0, 0.4999 / 127, 1e-9], dtype=np.float32)
+    out = np.zeros(8, dtype=np.int8)
+    O.lib().orc_quantize_f32_to_i8(v.ctypes.data, 8, out.ctypes.data)
+    assert out.tolist() == [1, -1, 2, 3, 127, -127, 0, 0]
+    # unit vector along one axis -> 127 on that axis; [3,4]/5 -> round(76.2), round(101.6)
+    assert O.quantize_i8(np.array([0, 0, 9.0, 0], dtype=np.float32)).tolist() == [0, 0, 127, 0]
+    assert O.quantize_i8(np.array([3.0, 4.0], dtype=np.float32)).tolist() == [76, 102]
+    assert O.quantize_i8(np.zeros(4, dtype=np.float32)).tolist() == [0, 0, 0, 0]          # NaN as i8 = 0
+    rng = np.random.default_rng(5)
+    a = rng.integers(-127, 128, 300).astype(np.int8)
+    b = rng.integers(-127, 128, 300).astype(np.int8)
+    assert O.lib().orc_dot_i8(a.ctypes.data, b.ctypes.data, 300) == int(a.astype(np.int64) @ b.astype(np.int64))
+    # worst case fits f32 exactly: 768 * 127 * 127 < 2^24
+    assert 768 * 127 * 127 < 2 ** 24
+
+
+def test_int8_search_matches_numpy():
+    rng = np.random.default_rng(6)
+    rows = rng.normal(size=(500, 96)).astype(np.float32)
+    r8 = O.quantize_rows_i8(rows)
+    assert (r8 == np.stack([O.quantize_i8(r) for r in rows])).all()
+    q8 = O.quantize_i8(rows[17] + 0.1 * rng.normal(size=96).astype(np.float32))
+    sc = r8.astype(np.int64) @ q8.astype(np.int64)
+    order = np.lexsort((np.arange(500), -sc))[:10]
+    got = O.search_vector_i8(r8, q8, 10)
+    assert [d for d, _ in got] == order.tolist()
+    assert [s for _, s in got] == [float(sc[i]) for i in order]
+    assert got[0][0] == 17
