@@ -341,6 +341,16 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                             gmax[(size_t)(blockIdx.y * NQ + c * 16 + lane) * n_rg + (tile * (MT * 4) + m * 4 + ew)] = keep;
                         continue;
                     }
+                    {   // common case, branch-free: does ANY of the 32 x 16 scores reach its query's threshold?  (ncu: with a
+                        // ballot + branch per column this loop, not HBM, set the tile period)
+                        const int4* t4 = reinterpret_cast<const int4*>(thr_i + c * 16);
+                        const int4 t0 = t4[0], t1 = t4[1], t2 = t4[2], t3 = t4[3];
+                        bool any = ((int)v[0] >= t0.x) | ((int)v[1] >= t0.y) | ((int)v[2] >= t0.z) | ((int)v[3] >= t0.w) |
+                                   ((int)v[4] >= t1.x) | ((int)v[5] >= t1.y) | ((int)v[6] >= t1.z) | ((int)v[7] >= t1.w) |
+                                   ((int)v[8] >= t2.x) | ((int)v[9] >= t2.y) | ((int)v[10] >= t2.z) | ((int)v[11] >= t2.w) |
+                                   ((int)v[12] >= t3.x) | ((int)v[13] >= t3.y) | ((int)v[14] >= t3.z) | ((int)v[15] >= t3.w);
+                        if (!__any_sync(FULL, any && valid)) continue;
+                    }
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int q = c * 16 + j;
@@ -384,8 +394,10 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         // tensor pipe, the limiter.)
         const int ew = warp - 4;                          // == warp % 4 == TMEM lane quadrant
         uint64_t* mylists = lists + (size_t)ew * NQ * LIST;
-        for (int i = lane; i < NQ * LIST; i += 32) mylists[i] = 0;
+        if (!sample_mode) for (int i = lane; i < NQ * LIST; i += 32) mylists[i] = 0;
         __syncwarp();
+        uint32_t* gmaxu = (uint32_t*)scratch;            // sample mode (see the int8 epilogue): ordered-uint group maxima
+        const uint32_t n_rg = n_tiles * (MT * 4);
         uint32_t ti = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
             const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
@@ -401,10 +413,27 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                              : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (sample_mode) {
+                    uint32_t keep = 0;
+#pragma unroll
+                    for (int j = 0; j < CHUNK; j++) {
+                        const float sc = __uint_as_float(v[j]);
+                        uint32_t so = (valid && sc == sc) ? ord_f32(sc) : 0u;
+                        if (ceil_keys && so) {
+                            const uint64_t key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
+                            if (key >= __ldg(&ceil_keys[blockIdx.y * NQ + c * CHUNK + j])) so = 0u;
+                        }
+                        const uint32_t mx = __reduce_max_sync(FULL, so);
+                        if (lane == j) keep = mx;
+                    }
+                    if (lane < CHUNK)
+                        gmaxu[(size_t)(blockIdx.y * NQ + c * CHUNK + lane) * n_rg + (tile * (MT * 4) + m * 4 + ew)] = keep;
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < CHUNK; j++) {
                     const int q = c * CHUNK + j;
-                    const float sc = PREC == PREC_I8 ? (float)(int32_t)v[j] /* dot_i8 as f32, exact below 2^24 */ : __uint_as_float(v[j]);
+                    const float sc = __uint_as_float(v[j]);
                     const uint32_t so = ord_f32(sc);
                     const bool pass = valid && sc == sc && so >= thr_u[q];
                     unsigned pm = __ballot_sync(FULL, pass);
@@ -463,7 +492,8 @@ __global__ void split_queries_bf16(const float* __restrict__ q, __nv_bfloat16* _
 
 // thr[q] = ordered-uint of the k-th largest of gmax[q][0..n_rg) as an f32 score (0 = no threshold when fewer than k groups
 // hold an eligible row).  One warp per query, lane-distributed sorted list, chunks that cannot enter the list are skipped.
-__global__ void kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, uint32_t nq, uint32_t k, uint32_t* __restrict__ thr) {
+__global__ void kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, uint32_t nq, uint32_t k, uint32_t* __restrict__ thr,
+                                  int is_int /*1: int32 dot products (INT_MIN = none), 0: ordered-uint f32 scores (0 = none)*/) {
     const int lane = threadIdx.x & 31;
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -471,14 +501,14 @@ __global__ void kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, u
     uint64_t L = 0;
     for (uint32_t base = 0; base < n_rg; base += 32) {
         const uint32_t i = base + lane;
-        const int v = i < n_rg ? g[i] : INT_MIN;
-        // key: biased value in the high word (> 0 for every eligible row), group index below it keeps keys distinct
-        const uint64_t key = v == INT_MIN ? 0ull : (((uint64_t)((uint32_t)v ^ 0x80000000u)) << 32) | (uint64_t)(0xFFFFFFFFu - i);
+        // key: order-preserving unsigned value in the high word (> 0 for every eligible row), group index below it keeps keys distinct
+        const uint32_t u = i < n_rg ? ((uint32_t)g[i] ^ (is_int ? 0x80000000u : 0u)) : 0u;
+        const uint64_t key = u == 0u ? 0ull : ((uint64_t)u << 32) | (uint64_t)(0xFFFFFFFFu - i);
         const uint64_t kth = shfl64(L, (int)k - 1);
         if (__any_sync(FULL, key > kth)) L = wl_merge(L, wl_sort_desc(key, lane), lane);
     }
     const uint64_t kth = shfl64(L, (int)k - 1);
-    if (lane == 0) thr[q] = kth ? ord_f32((float)(int)((uint32_t)(kth >> 32) ^ 0x80000000u)) : 0u;
+    if (lane == 0) thr[q] = !kth ? 0u : (is_int ? ord_f32((float)(int)((uint32_t)(kth >> 32) ^ 0x80000000u)) : (uint32_t)(kth >> 32));
 }
 
 }  // namespace tc
@@ -532,9 +562,10 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     if (a.sample_groupmax) {   // threshold seeding pass: scratch holds gmax[nq_pad][n_tiles * 8]
-        tc::kth_from_groupmax<<<(a.nq_pad + 7) / 8, 256, 0, st>>>((const int*)a.scratch, n_tiles * (tc::MT * 4), a.nq_pad, a.k, a.thr_buf);
+        tc::kth_from_groupmax<<<(a.nq_pad + 7) / 8, 256, 0, st>>>((const int*)a.scratch, n_tiles * (tc::MT * 4), a.nq_pad, a.k, a.thr_buf,
+                                                                      PREC == tc::PREC_I8 ? 1 : 0);
         SSB_CUDA_TRY(cudaGetLastError());
-        if (a.launches) *a.launches += 2;
+        if (a.launches) *a.launches += PREC == tc::PREC_I8 ? 2 : 3;   // (query split +) scan + kth
         return SSB_OK;
     }
     // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ
@@ -561,24 +592,15 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream
     // threshold pre-sampling (see vec_scan.cu): scan the first rows, seed the thresholds, then the full scan
     if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, bf16, st);
     ScanArgs pre = a;
-    pre.n_rows = vec_presample_rows(a.n_rows, true); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
-    if (bf16 == 2) {
-        // int8: the sample pass is latency-bound on its insert storms, one 256-row tile per CTA costs the same for 30 CTAs
-        // as for all of them — sample one tile per SM (ncu: the full scan's epilogue warps otherwise spend a third of their
-        // time waiting on list loads for candidates a better seed rejects)
-        uint64_t s = (uint64_t)a.n_sms * tc::TROWS;
-        if (s > a.n_rows / 4) s = a.n_rows / 4 / tc::TROWS * tc::TROWS;
-        if (s > pre.n_rows) pre.n_rows = s;
-        // group-maxima sample mode: no lists, no insert storm; writes the thresholds straight into thr_buf
-        pre.sample_groupmax = true; pre.thr_buf = a.thr_buf;
-        SSB_TRY(launch_scan_tc_impl(pre, nq_tile, bf16, st));
-        ScanArgs full = a;
-        full.thr_init = a.thr_buf;
-        return launch_scan_tc_impl(full, nq_tile, bf16, st);
-    }
+    // The sample pass writes per-(32-row group, query) score maxima instead of lists (no insert storm) and costs the same for one
+    // 256-row tile per CTA as for a handful of tiles: sample one tile per SM.  (An earlier version ran the normal list epilogue
+    // over N/128 rows: ~90 us per pass, and ncu showed the full scan's epilogue warps waiting on list loads for candidates that
+    // a better seed rejects.)
+    uint64_t s = (uint64_t)a.n_sms * tc::TROWS;
+    if (s > a.n_rows / 4) s = a.n_rows / 4 / tc::TROWS * tc::TROWS;
+    pre.n_rows = s; pre.ev0 = nullptr; pre.ev1 = nullptr;
+    pre.sample_groupmax = true;                          // writes the thresholds straight into thr_buf
     SSB_TRY(launch_scan_tc_impl(pre, nq_tile, bf16, st));
-    launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
-    if (a.launches) *a.launches += 1;
     ScanArgs full = a;
     full.thr_init = a.thr_buf;
     return launch_scan_tc_impl(full, nq_tile, bf16, st);
