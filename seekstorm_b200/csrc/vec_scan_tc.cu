@@ -430,6 +430,16 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                         gmaxu[(size_t)(blockIdx.y * NQ + c * CHUNK + lane) * n_rg + (tile * (MT * 4) + m * 4 + ew)] = keep;
                     continue;
                 }
+                {   // common case, branch-free: one vote per 8-query chunk instead of one per column (a NaN score maps above every
+                    // threshold here and is rejected by the per-column test below)
+                    const uint4* t4 = reinterpret_cast<const uint4*>(thr_u + c * CHUNK);
+                    const uint4 t0 = t4[0], t1 = t4[1];
+                    const bool any = (ord_f32(__uint_as_float(v[0])) >= t0.x) | (ord_f32(__uint_as_float(v[1])) >= t0.y) |
+                                     (ord_f32(__uint_as_float(v[2])) >= t0.z) | (ord_f32(__uint_as_float(v[3])) >= t0.w) |
+                                     (ord_f32(__uint_as_float(v[4])) >= t1.x) | (ord_f32(__uint_as_float(v[5])) >= t1.y) |
+                                     (ord_f32(__uint_as_float(v[6])) >= t1.z) | (ord_f32(__uint_as_float(v[7])) >= t1.w);
+                    if (!__any_sync(FULL, any && valid)) continue;
+                }
 #pragma unroll
                 for (int j = 0; j < CHUNK; j++) {
                     const int q = c * CHUNK + j;
