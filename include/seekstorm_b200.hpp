@@ -35,6 +35,7 @@ inline void check(int32_t rc) {
 enum class QueryType : uint32_t { Union = SSB_QUERY_UNION, Intersection = SSB_QUERY_INTERSECTION };
 enum class ResultType : uint32_t { Count = SSB_RESULT_COUNT, Topk = SSB_RESULT_TOPK, TopkCount = SSB_RESULT_TOPKCOUNT };
 enum class VectorSimilarity : uint32_t { Dot = SSB_SIM_DOT, Cosine = SSB_SIM_COSINE, Euclidean = SSB_SIM_EUCLIDEAN };
+enum class Quantization : uint32_t { None = SSB_QUANT_NONE, ScalarQuantizationI8 = SSB_QUANT_SCALAR_I8 };   // vector.rs:230-240
 enum class AnnMode { All };   // exhaustive search only
 
 struct SearchMode {
@@ -69,11 +70,12 @@ public:
     using TermKeyFn = std::function<uint64_t(const std::string&)>;
 
     explicit Index(int device = 0, uint32_t vector_dims = 0, VectorSimilarity sim = VectorSimilarity::Cosine,
-                   uint32_t max_batch = 4096, TermKeyFn key_fn = fnv1a64)
+                   uint32_t max_batch = 4096, TermKeyFn key_fn = fnv1a64, Quantization quantization = Quantization::None)
         : key_fn_(std::move(key_fn)), sim_(sim) {
         ssb_config cfg{};
         cfg.device = device; cfg.max_batch = max_batch; cfg.vector_dims = vector_dims;
         cfg.vector_similarity = static_cast<uint32_t>(sim); cfg.vector_kernel = SSB_VEC_KERNEL_AUTO;
+        cfg.vector_quantization = static_cast<uint32_t>(quantization);
         check(ssb_create(&cfg, &h_));
     }
     ~Index() { if (h_) ssb_destroy(h_); }

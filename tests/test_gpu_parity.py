@@ -290,3 +290,29 @@ def test_vector_int8_config_errors():
         Index(0, vector_dims=64, vector_similarity=VectorSimilarity.Dot, vector_quantization=1)
     with pytest.raises(SsbError):
         Index(0, vector_dims=64, vector_quantization=7)
+
+
+@pytest.mark.gpu
+def test_hybrid_with_int8_vectors():
+    """Hybrid RRF over BM25 + the int8 vector path: fused list equals RRF of the two oracle lists."""
+    from seekstorm_b200 import Index, QueryType, VectorSimilarity
+    n, dims = 30000, 96
+    levels, ls = synth_levels(n, 3000, 21)
+    ix = gpu_index([lv.to_numpy() for lv in levels], n, ls, vector_dims=dims, vector_similarity=VectorSimilarity.Cosine,
+                   vector_quantization=1)
+    orc = oracle_index([lv.to_numpy() for lv in levels], n, ls)
+    rows = synth.gen_vectors(n, dims, 22, "cpu").numpy()
+    ix.add_vectors(rows)
+    r8 = O.quantize_rows_i8(rows)
+    queries = synth.gen_queries(6, 23, 5, 1500, (2, 3), (0.5, 0.5))
+    qkeys = query_keys(queries)
+    qv = synth.gen_vectors(6, dims, 24, "cpu").numpy()
+    q8 = O.quantize_rows_i8(qv)
+    got = ix.search_hybrid_batch(qkeys, QueryType.Union, qv, 10)
+    for i in range(6):
+        lex, _ = orc.search(qkeys[i], O.QUERY_UNION, 10, O.RESULT_TOPK)
+        vec = O.search_vector_i8(r8, q8[i], 10)
+        want = O.rrf(lex, vec)[:10]
+        assert [d for d, _ in got[i]] == [d for d, _ in want], (i, got[i], want)
+        assert np.allclose([s for _, s in got[i]], [s for _, s in want], rtol=1e-6)
+    ix.close()
