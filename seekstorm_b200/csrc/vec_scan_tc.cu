@@ -44,18 +44,21 @@ enum { PREC_TF32 = 0, PREC_BF16 = 1, PREC_I8 = 2 };
 constexpr int MAX_STAGES = 6;
 template <int NQ, int PREC, bool BRES = false> struct Cfg {
     // TF32: [A (-> A_hi in place) | A_lo | B_hi | B_lo], all f32 SWIZZLE_128B tiles
-    // BF16: [A f32 | A1 bf16 | A2 bf16 | B1 bf16 | B2 bf16], bf16 tiles are 64-byte rows, SWIZZLE_64B
+    // BF16: [A f32 -> (A1 bf16 | A2 bf16) IN PLACE | B1 bf16 | B2 bf16], bf16 tiles are 64-byte rows, SWIZZLE_64B.  The two
+    //       bf16 tiles together are exactly as large as the f32 tile they come from; the splitters read the whole f32 tile
+    //       into registers, meet at a named barrier, then overwrite it.  48 KB per stage -> 4 stages instead of the 2 that an
+    //       out-of-place split (80 KB) allowed: with 2 stages the TMA latency, not the tensor pipe, set the stage period.
     // I8  : [A i8 | B i8]: the int8 corpus (quantised at load time) is the MMA operand as TMA delivers it — no splitter
     //       pass, 128 dims per 128-byte swizzle row, 4 smem stages
-    static constexpr int STAGES = PREC == PREC_I8 ? 4 : 2;
+    static constexpr int STAGES = PREC == PREC_TF32 ? 2 : 4;
     static constexpr int KCE = PREC == PREC_I8 ? 128 : KC;                     // elements per k-chunk (128 bytes either way)
     static constexpr int B_BYTES = PREC == PREC_BF16 ? NQ * KC * 2 : NQ * KC * 4;
-    static constexpr int ALO_OFF = A_BYTES;                                    // TF32: A_lo   | BF16: A1
-    static constexpr int A2_OFF = A_BYTES + A_BYTES / 2;                       // BF16: A2
-    static constexpr int B_OFF = PREC == PREC_I8 ? A_BYTES : 2 * A_BYTES;
+    static constexpr int ALO_OFF = PREC == PREC_BF16 ? 0 : A_BYTES;            // TF32: A_lo   | BF16: A1 (in place)
+    static constexpr int A2_OFF = A_BYTES / 2;                                 // BF16: A2 (in place)
+    static constexpr int B_OFF = PREC == PREC_TF32 ? 2 * A_BYTES : A_BYTES;
     // BRES (int8 only): the whole quantised query block [n_kchunks][NQ x 128 B] stays resident in smem behind the A stages,
     // so the per-stage L2->SM traffic is the corpus tile alone (stage count chosen at launch from what is left of 227 KB)
-    static constexpr int STAGE_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : 2 * A_BYTES + 2 * B_BYTES);
+    static constexpr int STAGE_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : (PREC == PREC_BF16 ? A_BYTES + 2 * B_BYTES : 2 * A_BYTES + 2 * B_BYTES));
     static constexpr int TX_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : A_BYTES + 2 * B_BYTES);
     static constexpr int SMEM = STAGES * STAGE_BYTES + NQ * 4 + 256;
     static constexpr int TMEM_COLS = 2 * MT * NQ;                              // double-buffered MT accumulators
@@ -271,11 +274,19 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     const float4* A = (const float4*)st;
                     uint4* A1 = (uint4*)(st + C::ALO_OFF);
                     uint4* A2 = (uint4*)(st + C::A2_OFF);
+                    constexpr int UNITS = (TROWS * 4) / SPLIT_THREADS;
+                    float4 xs[UNITS], ys[UNITS];
 #pragma unroll
-                    for (int i = 0; i < (TROWS * 4) / SPLIT_THREADS; i++) {
+                    for (int i = 0; i < UNITS; i++) {
                         const int u = t + SPLIT_THREADS * i, r = u >> 2, j = u & 3;
-                        const float4 x = A[r * 8 + ((2 * j) ^ (r & 7))];
-                        const float4 y = A[r * 8 + ((2 * j + 1) ^ (r & 7))];
+                        xs[i] = A[r * 8 + ((2 * j) ^ (r & 7))];
+                        ys[i] = A[r * 8 + ((2 * j + 1) ^ (r & 7))];
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(SPLIT_THREADS) : "memory");   // every f32 value is in a register: overwrite
+#pragma unroll
+                    for (int i = 0; i < UNITS; i++) {
+                        const int u = t + SPLIT_THREADS * i, r = u >> 2, j = u & 3;
+                        const float4 x = xs[i], y = ys[i];
                         float r0, r1, r2, r3, r4, r5, r6, r7;
                         uint4 h, l;
                         h.x = bf16x2_hi(x.x, x.y, r0, r1); h.y = bf16x2_hi(x.z, x.w, r2, r3);
