@@ -666,8 +666,26 @@ def cpu_bm25_baseline(a, seconds):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of this run, written straight to the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    # stdout carries exactly one JSON line: everything else any library writes to fd 1 (NCCL prints its version banner
+    # there whenever NCCL_DEBUG >= VERSION) is sent to stderr instead
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sections = [s for s in a.sections.split(",") if s]
     if a.impl == "reference":
         rank = int(os.environ.get("RANK", 0))
@@ -688,11 +706,11 @@ def main():
                 line["bm25"]["value"] = line["bm25"]["cpu_baseline"]["value"]
             except Exception as e:  # pragma: no cover
                 line["bm25"] = {"error": repr(e)}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: bench.py measures the B200 path only (no CPU fallback)"}))
+        emit({"error": "no CUDA device: bench.py measures the B200 path only (no CPU fallback)"})
         return 1
     import __graft_entry__ as g
     if not os.path.exists(g.LIB):
@@ -741,7 +759,7 @@ def main():
             except Exception as e:  # pragma: no cover
                 out["bm25"]["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
