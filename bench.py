@@ -225,7 +225,9 @@ KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + wa
 # the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
 # (3.072 GB), i.e. no re-reads.
 NCU = {"scan_ffma": {"traffic_per_pass": 24.608e9 / 8, "source": "profiles/r01_scan_ffma_v3.summary.txt"},
-       "scan_tc": {"traffic_per_pass": 3.1149e9, "source": "profiles/r01_scan_tc_bf16.summary.txt"}}
+       "scan_tc": {"traffic_per_pass": 3.1149e9, "source": "profiles/r01_scan_tc_bf16.summary.txt"},
+       # int8 full scan of 1M x 768: dram read 777.6 MB + write 29.3 MB (per-warp list scratch)
+       "scan_tc_i8": {"traffic_per_pass": 0.8069e9, "source": "profiles/r01_scan_tc_i8_v1.summary.txt"}}
 
 
 def measure_vector_kernel(a, ix, sh, kname, q_host, q_dev, keys, local_rows, rank, world, dev, want_clocks):
@@ -404,7 +406,9 @@ def bench_vector_int8(a, rank, world):
                 "h2d_bytes_per_step": nb * a.dims * 4, "d2h_bytes_per_step": nb * 32 * 8},
         "gpu_launches": int(launches) * a.steps, "batch_sweep_e2e": sweep,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "peak_kind": f"of {peak_kind}", "kernel": "scan_tc_i8", "kernel_ms": kern_ms,
+                     "traffic": (NCU["scan_tc_i8"]["traffic_per_pass"] * passes * local_rows / 1e6) if a.dims == C2_DIMS else None,
+                     "traffic_source": NCU["scan_tc_i8"]["source"],
+                     "peak_kind": f"of {peak_kind}", "kernel": "scan_tc_i8", "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": alg_bytes},
     }
 
