@@ -320,6 +320,8 @@ struct ItemCtx {
     bool scoring, need_count, is_and;
 };
 
+struct FTerm { uint64_t off; uint32_t cnt, bmi; float idf, ub; uint32_t pos, cpos; };   // 32 B, one per (warp, query term)
+
 // ---- fast path: n <= FAST_T live terms, per-term state in (warp-uniform) registers ----
 __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryPlan* pl, const ItemCtx& c, uint2 ient, int lane,
                                                   uint64_t& L, uint32_t& thr, bool& dirty, uint64_t& matches,
@@ -370,10 +372,16 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
         return;
     }
     // ---------------- OR ----------------
+    // Per-term state moves from registers to a per-warp shared-memory record here.  With 6 four-entry register arrays live
+    // across the posting loop and a 48-register budget (5 CTAs/SM), the compiler re-evaluated the "t == drv" select chains
+    // in every chunk iteration: ncu attributed 33 % of the kernel's instructions to the three per-driver setup lines.  Values
+    // are warp-uniform, so every access below is one broadcast LDS with a dynamic index.
     __shared__ uint2 cbuf[8][64];                             // per-warp survivor queue (posting index, posting word)
+    __shared__ FTerm fts[8][FAST_T];
     uint2* mybuf = cbuf[(threadIdx.x >> 5) & 7];
-    if (c.scoring) {
-        // MAXSCORE: terms by block bound desc (present first); pos[t] = rank of term t, ord_t[p] = term at rank p
+    FTerm* ft = fts[(threadIdx.x >> 5) & 7];
+    {
+        // MAXSCORE order: terms by block bound desc (present first); pos = rank of the term
         uint32_t pos[FAST_T];
 #pragma unroll
         for (uint32_t t = 0; t < FAST_T; t++) {
@@ -386,18 +394,25 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
             }
             pos[t] = t < n ? r : 0xFFFFu;
         }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (uint32_t t = 0; t < FAST_T; t++) {
+                FTerm f; f.off = off[t]; f.cnt = cnt[t]; f.bmi = bmi[t]; f.idf = idf[t]; f.ub = ub[t]; f.pos = pos[t]; f.cpos = 0xFFFFu;
+                ft[t] = f;
+            }
+        }
+        __syncwarp();
+    }
+    if (c.scoring) {
         for (uint32_t p = 0; p < n; p++) {
             uint32_t drv = 0;
-#pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) if (pos[t] == p) drv = t;
-            uint32_t dcnt = 0; uint64_t doff = 0; float didf = 0.f;
-#pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) if (t == drv) { dcnt = cnt[t]; doff = off[t]; didf = idf[t]; }
+            for (uint32_t t = 0; t < n; t++) if (ft[t].pos == p) drv = t;
+            const uint32_t dcnt = ft[drv].cnt; const uint64_t doff = ft[drv].off; const float didf = ft[drv].idf;
             if (dcnt == 0) break;                         // absent terms sort last
             // a driver is essential while the in-query-order sum of the not-yet-driven bounds can reach theta
             float S = 0.f;
-#pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) if (t < n && pos[t] >= p) S = __fadd_rn(S, ub[t]);
+            for (uint32_t t = 0; t < n; t++) if (ft[t].pos >= p) S = __fadd_rn(S, ft[t].ub);
             if (ord_f32(S) < thr) break;
             st_visited += dcnt;
             // R = in-query-order sum of the bounds of the later-ranked (not yet driven) terms.  The per-posting filter is
@@ -405,23 +420,22 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
             // of the exact in-order score — the inflation covers the approximate reciprocal (<= 2 ulp) and the different
             // association of <= 4 additions (<= 3 ulp).  Survivors are re-scored exactly below.
             float R = 0.f;
-#pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) if (t < n && t != drv && pos[t] > p) R = __fadd_rn(R, ub[t]);
+            for (uint32_t t = 0; t < n; t++) if (t != drv && ft[t].pos > p) R = __fadd_rn(R, ft[t].ub);
             const float didf_k = didf * v.k1p;
             // exact contribution, probes, exact in-order score of one queued survivor per lane
             auto rescore = [&](uint32_t pp, uint32_t pd, bool alive) {
                 const uint32_t d = pd & 0xFFFFu;
                 const float cd = alive ? __fmul_rn(didf, comp_of(v, pd >> 16, doff + pp)) : 0.f;
                 float score = 0.f;
-#pragma unroll
-                for (uint32_t t = 0; t < FAST_T; t++) {      // query order
-                    if (t >= n) continue;
+                for (uint32_t t = 0; t < n; t++) {           // query order
                     if (t == drv) { score = __fadd_rn(score, cd); continue; }
-                    if (!alive || cnt[t] == 0) continue;
+                    const uint32_t tc = ft[t].cnt;
+                    if (!alive || tc == 0) continue;
                     uint32_t rank; st_probes++;
-                    if (probe(v, cnt[t], off[t], bmi[t], d, rank)) {
-                        if (pos[t] < p) alive = false;        // already emitted when that term was the driver
-                        else score = __fadd_rn(score, term_score(v, idf[t], off[t] + rank));
+                    const uint64_t toff = ft[t].off;
+                    if (probe(v, tc, toff, ft[t].bmi, d, rank)) {
+                        if (ft[t].pos < p) alive = false;     // already emitted when that term was the driver
+                        else score = __fadd_rn(score, term_score(v, ft[t].idf, toff + rank));
                     }
                 }
                 insert_candidates(L, thr, alive && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
@@ -446,17 +460,17 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
                 // the doc is not in contributes nothing.  No exact divide, no rank / payload load for postings that die here
                 // (measured before this filter: 0.75 probes per enumerated posting, 0.10 after).  Lists without a bitmap count as
                 // "maybe".
-                if (alive) {
+                {
                     float B = cdb; bool dead = false;
-#pragma unroll
-                    for (uint32_t t = 0; t < FAST_T; t++) {
-                        if (t >= n || t == drv || cnt[t] == 0) continue;
-                        if (bmi[t] != NONE) {
-                            const uint64_t w = __ldg(&v.bm_words[(size_t)bmi[t] * 1024 + (d >> 6)]);
-                            if ((w >> (d & 63)) & 1ull) { if (pos[t] < p) dead = true; else B += ub[t]; }
-                        } else if (pos[t] > p) B += ub[t];
+                    for (uint32_t t = 0; t < n; t++) {
+                        if (t == drv || ft[t].cnt == 0) continue;
+                        const uint32_t tb = ft[t].bmi, tp = ft[t].pos;
+                        if (tb != NONE) {
+                            const uint64_t w = alive ? __ldg(&v.bm_words[(size_t)tb * 1024 + (d >> 6)]) : 0ull;
+                            if ((w >> (d & 63)) & 1ull) { if (tp < p) dead = true; else B += ft[t].ub; }
+                        } else if (tp > p) B += ft[t].ub;
                     }
-                    alive = !dead && ord_f32(B * 1.000002f) >= thr;
+                    alive = alive && !dead && ord_f32(B * 1.000002f) >= thr;
                 }
 #endif
                 // ---- compaction: the exact re-score is ~10x the cost of the filters and only a few lanes of a chunk survive them
@@ -489,18 +503,17 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
     }
     if (c.need_count) {
         // exact |union| of this block: sum of counts - duplicates; enumerate all but the longest list, probe longer ones
-        uint32_t cpos[FAST_T];
-#pragma unroll
-        for (uint32_t t = 0; t < FAST_T; t++) {
-            uint32_t r = 0;
-#pragma unroll
-            for (uint32_t u = 0; u < FAST_T; u++) if (u != t && u < n && (cnt[u] > cnt[t] || (cnt[u] == cnt[t] && u < t))) r++;
-            cpos[t] = t < n ? r : 0xFFFFu;
+        if (lane == 0) {
+            for (uint32_t t = 0; t < n; t++) {
+                uint32_t r = 0;
+                for (uint32_t u = 0; u < n; u++) if (u != t && (ft[u].cnt > ft[t].cnt || (ft[u].cnt == ft[t].cnt && u < t))) r++;
+                ft[t].cpos = r;
+            }
         }
+        __syncwarp();
         for (uint32_t p = 0; p < n; p++) {
             uint32_t dcnt = 0; uint64_t doff = 0;
-#pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) if (cpos[t] == p) { dcnt = cnt[t]; doff = off[t]; }
+            for (uint32_t t = 0; t < n; t++) if (ft[t].cpos == p) { dcnt = ft[t].cnt; doff = ft[t].off; }
             if (dcnt == 0) break;
             if (p == 0) { matches += dcnt; continue; }
             st_visited += dcnt;
@@ -509,15 +522,16 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
                 const bool active = pp < dcnt;
                 const uint32_t d = active ? (__ldg(&v.post[doff + pp]) & 0xFFFFu) : 0u;
                 bool dup = false;
-#pragma unroll
-                for (uint32_t t = 0; t < FAST_T; t++) {
-                    if (t >= n || cpos[t] >= p || cnt[t] == 0 || !active || dup) continue;
+                for (uint32_t t = 0; t < n; t++) {
+                    const uint32_t tc = ft[t].cnt;
+                    if (ft[t].cpos >= p || tc == 0 || !active || dup) continue;
                     uint32_t rank; st_probes++;
-                    if (probe(v, cnt[t], off[t], bmi[t], d, rank)) dup = true;
+                    if (probe(v, tc, ft[t].off, ft[t].bmi, d, rank)) dup = true;
                 }
                 matches += __popc(__ballot_sync(FULL, active && !dup));
             }
         }
+        __syncwarp();
     }
 }
 
