@@ -588,10 +588,11 @@ def bench_bm25(a, rank, world):
         "gpu_launches": 3 * steps, "variants": variants,
         "roofline": {"bound": "hbm", "achieved": (alg / (kern_ms / 1e3) / 1e9) if (alg and kern_ms) else None, "peak": peak, "unit": "GB/s",
                      "frac": (alg / (kern_ms / 1e3) / 1e9 / peak) if (alg and kern_ms) else None,
-                     # dram__bytes_read+write of one ncu --set full capture of this launch shape (profiles/r01_lex_score_v2): 2.3x the
-                     # algorithmic bytes — 4-byte probes cost 32-byte sectors
-                     "traffic": 8.668e9 if (a.bm25_docs == C3_DOCS and len(qk) == 4096 and world == 1) else None,
-                     "traffic_source": "profiles/r01_lex_score_v2.summary.txt",
+                     # dram__bytes_read+write of one ncu --set full capture of this launch shape (profiles/r01_lex_score_v3: 8.39 GB
+                     # read + 1.74 GB written): several times the algorithmic bytes — 4- and 8-byte probes cost 32-byte sectors,
+                     # and the write side is per-thread stack traffic of the register-array paths (open item)
+                     "traffic": 10.13e9 if (a.bm25_docs == C3_DOCS and len(qk) == 4096 and world == 1) else None,
+                     "traffic_source": "profiles/r01_lex_score_v3.summary.txt",
                      "peak_kind": f"of {peak_kind}", "kernel": "lex_score", "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": alg, "postings_visited": st.get("postings_visited"), "probes": st.get("probes"),
                      "items_processed": st.get("items_processed"), "items_skipped": st.get("items_skipped")},
