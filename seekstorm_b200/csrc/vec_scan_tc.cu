@@ -5,22 +5,30 @@
 //   D[128 corpus rows, NQ queries] (f32, TMEM) += A[128 x K] . B[NQ x K]^T          tcgen05.mma.cta_group::1
 // f32-level accuracy (north-star tolerance 1e-4 on cosine scores) comes from a 3-product split
 //   a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo                (the dropped a_lo.b_lo term is second order)
-// in one of two operand precisions (template PREC):
+// in one of two operand precisions, or exactly on int8 codes (template PREC):
 //   PREC_TF32 : kind::tf32, x_hi = x & 0xFFFFE000 (exactly representable in tf32, so the result does not depend on
 //               whether the tensor core truncates or rounds), x_lo = x - x_hi (exact); error ~2^-22 per product.
 //   PREC_BF16 : kind::f16 (bf16 operands, f32 accumulate), x_hi = bf16_rn(x), x_lo = bf16_rn(x - x_hi);
-//               error ~3*2^-17 per product (random sign) -> ~1e-5 relative on a 768-d score.  Operand bytes per
-//               MAC are half of tf32, and this kernel is bound by shared-memory operand traffic (measured), so the
-//               bf16 split is the faster one.
+//               error ~3*2^-17 per product (random sign) -> ~1e-5 relative on a 768-d score.  Twice the MACs per MMA
+//               instruction and half the operand bytes per MAC of tf32: the faster split (measured), now within a few
+//               percent of the tensor-pipe floor of 12 MMAs per 256-row stage.
+//   PREC_I8   : kind::i8 over an int8 corpus (Cosine + ScalarQuantizationI8, quantised at load time): ONE exact product, s32
+//               accumulators; the TMA'd tile is the MMA operand (no splitters), the 128-query block stays resident in smem
+//               (template BRES) and 12 warps run the epilogue.  See DESIGN.md §3.2b.
 // The query parts are prepared once per batch in global memory; the corpus parts are produced per stage in shared
-// memory by 4 "splitter" warps (the corpus is stored once, as f32 — algorithmic bytes stay n_rows*dims*4).
+// memory by 8 "splitter" warps (the corpus is stored once, as f32 — algorithmic bytes stay n_rows*dims*4).  The bf16 split
+// overwrites the f32 tile IN PLACE (both bf16 tiles together are as large as the f32 tile; read everything into registers,
+// named barrier, write), which makes a stage 48 KB and allows 4 stages; the tf32 split is out of place (2 stages).
 // Each smem stage holds MT=2 corpus tiles (256 rows) against ONE query chunk.
 //
-// Warp roles (512 threads, 1 CTA/SM): w0 TMA producer | w1 TMEM alloc + MMA issuer | w4-7 epilogue (TMEM
-// lane quadrant = warp%4) | w8-15 splitters (8 warps: with 4 the conversion chain of one warp per SMSP was the limiter).  Pipelines: full/split/empty per smem stage, tfull/tempty per
-// TMEM accumulator buffer (double-buffered: the epilogue of tile t overlaps the MMAs of tile t+1).
-// Epilogue: tcgen05.ld 8 query columns at a time, ballot-filter against the per-query threshold (seeded by the
-// pre-sample pass, vec_scan.cu), per-warp sorted lists in the CTA's slice of the output scratch (no CTA barriers).
+// Warp roles (512 threads, 1 CTA/SM): w0 TMA producer | w1 TMEM alloc + MMA issuer | w4-7 epilogue (TMEM lane quadrant =
+// warp%4) | w8-15 splitters (f32 variants) or additional epilogue warps (int8).  Pipelines: full/split/empty per smem stage,
+// tfull/tempty per TMEM accumulator buffer (double-buffered: the epilogue of tile t overlaps the MMAs of tile t+1).
+// Epilogue: tcgen05.ld 8 (int8: 16) query columns at a time; the whole chunk is tested against the per-query thresholds
+// branch-free with ONE vote, and only chunks with a candidate take the per-column path (ballot, per-warp sorted lists in the
+// CTA's slice of the output scratch, no CTA barriers).
+// Threshold seeding: the same kernel runs first in sample mode over one tile per SM and writes per-(32-row group, query)
+// score maxima; kth_from_groupmax turns them into valid lower bounds of the k-th best score.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -596,22 +604,22 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     return SSB_OK;
 }
 
-static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream_t st) {
+static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec /*0 tf32, 1 bf16, 2 int8*/, cudaStream_t st) {
     if (a.n_rows == 0 || a.nq_pad == 0) return SSB_OK;
-    if (bf16 == 2) {
+    if (prec == 2) {
         if (nq_tile != 128 || a.nq_pad % 128 != 0 || !a.rows_i8 || !a.queries_i8 || a.dpad8 % 128) { set_error("int8 scan: bad arguments"); return SSB_E_INVALID; }
         // query block resident in smem when it leaves room for >= 3 corpus stages (dims <= 1024), else streamed per stage
         return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true>(a, st) : launch_tc_n<128, tc::PREC_I8, false>(a, st);
     }
     if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }
     if ((nq_tile != 64 && nq_tile != 128) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 scan: query count must be padded to the 64/128 query tile"); return SSB_E_INVALID; }
-    if (bf16) return nq_tile == 64 ? launch_tc_n<64, tc::PREC_BF16>(a, st) : launch_tc_n<128, tc::PREC_BF16>(a, st);
+    if (prec == 1) return nq_tile == 64 ? launch_tc_n<64, tc::PREC_BF16>(a, st) : launch_tc_n<128, tc::PREC_BF16>(a, st);
     return nq_tile == 64 ? launch_tc_n<64, tc::PREC_TF32>(a, st) : launch_tc_n<128, tc::PREC_TF32>(a, st);
 }
 
-int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream_t st) {
+int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int prec, cudaStream_t st) {
     // threshold pre-sampling (see vec_scan.cu): scan the first rows, seed the thresholds, then the full scan
-    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, bf16, st);
+    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, prec, st);
     ScanArgs pre = a;
     // The sample pass writes per-(32-row group, query) score maxima instead of lists (no insert storm) and costs the same for one
     // 256-row tile per CTA as for a handful of tiles: sample one tile per SM.  (An earlier version ran the normal list epilogue
@@ -621,10 +629,10 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int bf16, cudaStream
     if (s > a.n_rows / 4) s = a.n_rows / 4 / tc::TROWS * tc::TROWS;
     pre.n_rows = s; pre.ev0 = nullptr; pre.ev1 = nullptr;
     pre.sample_groupmax = true;                          // writes the thresholds straight into thr_buf
-    SSB_TRY(launch_scan_tc_impl(pre, nq_tile, bf16, st));
+    SSB_TRY(launch_scan_tc_impl(pre, nq_tile, prec, st));
     ScanArgs full = a;
     full.thr_init = a.thr_buf;
-    return launch_scan_tc_impl(full, nq_tile, bf16, st);
+    return launch_scan_tc_impl(full, nq_tile, prec, st);
 }
 
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)nq_pad * (size_t)n_sms * 4 * LIST * 8; }
