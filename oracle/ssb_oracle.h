@@ -2,7 +2,7 @@
  * ssb_oracle.h — CPU ORACLE for the seekstorm_b200 hot path.  TEST INFRASTRUCTURE ONLY.
  *
  * This is a plain-C restatement of the reference's (SeekStorm 3.3.4) query-time arithmetic for
- * BM25 AND/OR top-k, brute-force f32 vector top-k and RRF fusion.  Only tests/,
+ * BM25 AND/OR top-k, brute-force f32 vector top-k, Cosine + ScalarQuantizationI8 int8 vector top-k and RRF fusion.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may link or call it.
  * The product path (seekstorm_b200/csrc, libseekstorm_b200.so) never does.
  *

@@ -141,6 +141,23 @@ def main():
         dot = dot + x * x
     out["neon_vec"] = {"make_f32_128": [float(x) for x in a], "dot_self_scalar": float(dot), "euclid_self": 0.0}
 
+    # ---- int8: the reference's make_i8 generator and its dot_i8 self-product (vector_similarity.rs:3018-3047), and the
+    # Cosine + ScalarQuantizationI8 codes of make_f32(128): normalize_f32 (:70-74, sequential f32 sum) then
+    # quantize_f32_to_i8 (:1226-1232, round half away from zero, clamp) — restated here with numpy scalars / python ints
+    mi8 = [((i * 17 + 5) % 251) - 125 for i in range(128)]
+    assert all(-128 <= x <= 127 for x in mi8)
+    norm2 = f32(0.0)
+    for x in a:
+        norm2 = norm2 + x * x
+    fac = f32(1.0) / f32(math.sqrt(float(norm2)))          # f32 sqrt: sqrt in f64 of an f32, rounded once = correctly rounded
+    codes = []
+    for x in a:
+        y = float(f32(f32(x * fac) * f32(127.0)))           # two individually rounded f32 multiplies
+        r = math.floor(abs(y) + 0.5) * (1 if y >= 0 else -1)  # exact in f64: half away from zero
+        codes.append(int(max(-127, min(127, r))))
+    out["int8"] = {"make_i8_128": mi8, "dot_i8_self": sum(x * x for x in mi8),
+                   "quant_of_make_f32_128": codes, "dot_codes_self": sum(c * c for c in codes)}
+
     # ---- the reference's 3-vector Euclidean fixture (tests/test.rs:675-745): v_j[i] = 0.001*(128*j + i + 1)
     vecs = [[(128 * j + i + 1) / 1000.0 for i in range(128)] for j in range(3)]
     q = np.array(vecs[0], dtype=np.float32)

@@ -159,3 +159,17 @@ def test_int8_search_matches_numpy():
     assert [d for d, _ in got] == order.tolist()
     assert [s for _, s in got] == [float(sc[i]) for i in order]
     assert got[0][0] == 17
+
+
+def test_int8_reference_generators(golden):
+    """The reference's own int8 test vector (make_i8, vector_similarity.rs:3018-3047: dot_i8 of it with itself) and the
+    Cosine + ScalarQuantizationI8 codes of its make_f32(128) vector, against an independent numpy/python restatement."""
+    g = golden["int8"]
+    a = np.array(g["make_i8_128"], dtype=np.int8)
+    assert O.lib().orc_dot_i8(a.ctypes.data, a.ctypes.data, 128) == g["dot_i8_self"]
+    f = np.array(golden["neon_vec"]["make_f32_128"], dtype=np.float32)
+    codes = O.quantize_i8(f)
+    assert codes.tolist() == g["quant_of_make_f32_128"]
+    assert O.lib().orc_dot_i8(codes.ctypes.data, codes.ctypes.data, 128) == g["dot_codes_self"]
+    # a unit vector quantises to a self-product close to 127^2
+    assert abs(g["dot_codes_self"] - 127 * 127) < 200
