@@ -171,6 +171,9 @@ __global__ void compact_dense(const uint32_t* __restrict__ e_bitmap, uint32_t n,
 #ifndef SSB_LEX_PRESENCE
 #define SSB_LEX_PRESENCE 1   // OR fast path: per-doc bitmap membership filter before the exact re-score
 #endif
+#ifndef SSB_LEX_AND_SMEM
+#define SSB_LEX_AND_SMEM 0   // AND fast path with per-term state in shared memory (unmeasured experiment, see process_item_fast)
+#endif
 #ifndef SSB_LEX_U
 #define SSB_LEX_U 1   // 32-posting chunks fetched per iteration (measured: batching 2-4 chunks is SLOWER — code size / I-cache)
 #endif
@@ -342,6 +345,46 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
             }
         }
     }
+#if SSB_LEX_AND_SMEM
+    if (c.is_and) {
+        // ---------------- AND, per-term state in shared memory (EXPERIMENT, default off: written after the round's GPU budget
+        // was spent, never run; same transformation that took the OR path from 4.7 to 3.5 ms) ----------------
+        __shared__ FTerm afts[8][FAST_T];
+        FTerm* at = afts[(threadIdx.x >> 5) & 7];
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (uint32_t t = 0; t < FAST_T; t++) {
+                FTerm f; f.off = off[t]; f.cnt = cnt[t]; f.bmi = bmi[t]; f.idf = idf[t]; f.ub = ub[t]; f.pos = 0; f.cpos = 0;
+                at[t] = f;
+            }
+        }
+        __syncwarp();
+        uint32_t drv = 0, best = at[0].cnt;
+        for (uint32_t t = 1; t < n; t++) { const uint32_t ct = at[t].cnt; if (ct < best) { best = ct; drv = t; } }
+        const uint32_t dcnt = best; const uint64_t doff = at[drv].off; const float didf = at[drv].idf;
+        st_visited += dcnt;
+        for (uint32_t base = 0; base < dcnt; base += 32) {
+            const uint32_t p = base + lane;
+            const bool active = p < dcnt;
+            const uint32_t pd = active ? __ldg(&v.post[doff + p]) : 0u;
+            const uint32_t d = pd & 0xFFFFu;
+            bool ok = active; float score = 0.f;
+            for (uint32_t t = 0; t < n; t++) {               // query order
+                if (t == drv) { if (ok && c.scoring) score = __fadd_rn(score, __fmul_rn(didf, comp_of(v, pd >> 16, doff + p))); continue; }
+                if (!ok) continue;
+                uint32_t rank; st_probes++;
+                const uint64_t toff = at[t].off;
+                if (!probe(v, at[t].cnt, toff, at[t].bmi, d, rank)) { ok = false; continue; }
+                if (c.scoring) score = __fadd_rn(score, term_score(v, at[t].idf, toff + rank));
+            }
+            matches += __popc(__ballot_sync(FULL, ok));
+            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
+        }
+        __syncwarp();
+        return;
+    }
+#else
     if (c.is_and) {
         // ---------------- AND: drive with the shortest list (intersection.rs:258-273) ----------------
         uint32_t drv = 0, best = cnt[0];
@@ -371,6 +414,7 @@ __device__ __forceinline__ void process_item_fast(const LexView& v, const QueryP
         }
         return;
     }
+#endif
     // ---------------- OR ----------------
     // Per-term state moves from registers to a per-warp shared-memory record here.  With 6 four-entry register arrays live
     // across the posting loop and a 48-register budget (5 CTAs/SM), the compiler re-evaluated the "t == drv" select chains
