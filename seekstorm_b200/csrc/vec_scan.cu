@@ -48,13 +48,22 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
     return d;
 }
 
+#ifndef SSB_FFMA_GROUPMAX
+#define SSB_FFMA_GROUPMAX 0   // EXPERIMENT (default off, compile-checked only, never run): group-maximum threshold sampling as in
+                                // vec_scan_tc.cu instead of the list-based sample pass — DESIGN.md §7 item 3
+#endif
+
 template <int SIM>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
           uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
           const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*CWARPS/2][QT][32]*/,
           const uint32_t* __restrict__ thr_init /*[gridDim.y*QT] or null*/, uint32_t nq_valid,
-          const uint64_t* __restrict__ ceil_keys /*[gridDim.y*QT] or null*/) {
+          const uint64_t* __restrict__ ceil_keys /*[gridDim.y*QT] or null*/
+#if SSB_FFMA_GROUPMAX
+          , uint32_t sample_mode
+#endif
+          ) {
     // no static shared memory in this kernel: the dynamic segment starts at offset 0 of the CTA window, so the
     // 1024-byte alignment SWIZZLE_128B needs holds and the pointers stay in the shared address space (LDS, not LD)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -139,6 +148,33 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
 
+#if SSB_FFMA_GROUPMAX
+                if (kc + 1 == n_kchunks && sample_mode) {
+                    // sample mode: lane (j*8 + q) keeps the best ordered-uint score of row group j (32 rows) for query q
+                    uint32_t keep = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t row = tile * TILE_ROWS + (uint32_t)r0 + 32u * j;
+                        const bool valid = row < n_rows;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float sum = acc[j][q].x + acc[j][q].y;
+                            const float sc = (SIM == SSB_SIM_EUCLIDEAN) ? -sum : sum;
+                            acc[j][q] = make_float2(0.f, 0.f);
+                            uint32_t so = (valid && sc == sc) ? ord_f32(sc) : 0u;
+                            if (ceil_keys && so) {
+                                const uint64_t key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
+                                if (key >= __ldg(&ceil_keys[group * QT + qh + q])) so = 0u;
+                            }
+                            const uint32_t mx = __reduce_max_sync(FULL, so);
+                            if (lane == j * 8 + q) keep = mx;
+                        }
+                    }
+                    uint32_t* gmax = (uint32_t*)scratch;               // [gridDim.y * QT][n_tiles * 16]
+                    gmax[(size_t)(group * QT + qh + (lane & 7)) * (n_tiles * 16) + (tile * 16 + rg * 4 + (lane >> 3))] = keep;
+                    continue;
+                }
+#endif
                 if (kc + 1 == n_kchunks) {
                     // ---- tile finished: fused top-k (TopK::push, vector.rs:410-497) ----
 #pragma unroll
@@ -175,6 +211,9 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
         // ---- publish the warp's lists: scratch[group][list][q][lane], list = (cta*4 + rg) ----
+#if SSB_FFMA_GROUPMAX
+        if (sample_mode) return;                          // scratch holds the group maxima, not lists
+#endif
         const uint32_t n_lists = gridDim.x * (CWARPS / 2);
         uint64_t* out = scratch + ((size_t)group * n_lists + (size_t)blockIdx.x * (CWARPS / 2) + rg) * QT * LIST;
 #pragma unroll
@@ -293,9 +332,14 @@ static int32_t with_presample(const ScanArgs& a, cudaStream_t st, F launch) {
     if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, false) == 0) return launch(a);
     ScanArgs pre = a;
     pre.n_rows = vec_presample_rows(a.n_rows, false); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
+#if SSB_FFMA_GROUPMAX
+    pre.sample_groupmax = true; pre.thr_buf = a.thr_buf;     // the sample launch writes the thresholds itself
+    SSB_TRY(launch(pre));
+#else
     SSB_TRY(launch(pre));
     launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
     if (a.launches) *a.launches += 1;
+#endif
     ScanArgs full = a;
     full.thr_init = a.thr_buf;
     return launch(full);
@@ -322,8 +366,19 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
         attr_set[ai] = true;
     }
     if (a.ev0) cudaEventRecord(a.ev0, st);
+#if SSB_FFMA_GROUPMAX
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
+                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, a.sample_groupmax ? 1u : 0u);
+    if (a.sample_groupmax) {
+        SSB_CUDA_TRY(cudaGetLastError());
+        launch_kth_from_groupmax(a.scratch, n_tiles * 16, a.nq_pad, a.k, a.thr_buf, 0, st);
+        if (a.launches) *a.launches += 2;   // scan + kth
+        return SSB_OK;
+    }
+#else
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
                                             a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys);
+#endif
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     merge_lists<<<a.nq_pad, 256, 0, st>>>(a.scratch, n_lists, QT, a.keys_out);

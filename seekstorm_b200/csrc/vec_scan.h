@@ -53,6 +53,8 @@ size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad);
 // lists laid out [group][n_lists][qt][32] -> out [nq][32]
 // thr[q] = ordered-uint score of the k-th entry of keys[q][32] (0 if the list is shorter)
 void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_t* thr, cudaStream_t st);
+// thr[q] = k-th largest group maximum (sample mode of the scans; is_int: int32 dot products instead of ordered-uint scores)
+void launch_kth_from_groupmax(const void* gmax, uint32_t n_groups, uint32_t nq, uint32_t k, uint32_t* thr, int is_int, cudaStream_t st);
 void merge_lists_generic(const uint64_t* in, uint32_t n_lists, uint32_t qt, uint32_t nq, uint64_t* out, cudaStream_t st);
 int32_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, float* out,
                             uint32_t nq_pad, uint32_t dpad, int normalize, cudaStream_t st);

@@ -635,6 +635,10 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int prec, cudaStream
     return launch_scan_tc_impl(full, nq_tile, prec, st);
 }
 
+void launch_kth_from_groupmax(const void* gmax, uint32_t n_groups, uint32_t nq, uint32_t k, uint32_t* thr, int is_int, cudaStream_t st) {
+    if (nq) tc::kth_from_groupmax<<<(nq + 7) / 8, 256, 0, st>>>((const int*)gmax, n_groups, nq, k, thr, is_int);
+}
+
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)nq_pad * (size_t)n_sms * 4 * LIST * 8; }
 
 }  // namespace vec
