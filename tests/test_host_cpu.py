@@ -61,3 +61,64 @@ def test_packed_key_order_is_canonical():
     # -0.0 and 0.0 compare equal as floats but order by sign bit in the key; exclude that pair from the check
     strip = lambda l: [x for x in l if x[0] != 0.0]
     assert strip(keyed) == strip(canon)
+
+
+def test_lex_bound_inflation_covers_rounding():
+    """The OR fast path of lex_score (bm25.cu) filters postings with the bound
+        (approx(cd) + sum of upper bounds of the other present terms) * (1 + 2e-6) >= theta
+    where approx(cd) = (idf*(K+1)) * fdividef(tf, tf + cache) uses an approximate reciprocal (<= 2 ulp) and a different
+    association than the exact score idf * ((tf*(K+1)) / (tf + cache)), and the exact score is summed in QUERY order while
+    the bound adds driver first.  Property: with the tightest admissible term bounds (ub == the term's exact contribution)
+    and the approximate quotient pushed 2 ulp DOWN, the inflated bound still dominates the exact in-order f32 score."""
+    f32 = np.float32
+    rng = np.random.default_rng(11)
+    k1p = f32(1.2) + f32(1.0)
+
+    def down(x, n):
+        for _ in range(n):
+            x = np.nextafter(f32(x), f32(-np.inf))
+        return f32(x)
+
+    worst = 0.0
+    for _ in range(20000):
+        n = int(rng.integers(1, 5))
+        idf = [f32(rng.uniform(0.05, 14.0)) for _ in range(n)]
+        tf = [f32(rng.integers(1, 256)) for _ in range(n)]
+        cache = [f32(rng.uniform(0.3, 4.0)) for _ in range(n)]
+        present = [True] + [bool(rng.integers(0, 2)) for _ in range(n - 1)]
+        drv = int(rng.integers(0, n))
+        present[drv] = True
+        contrib = [f32(idf[t] * f32(f32(tf[t] * k1p) / f32(tf[t] + cache[t]))) for t in range(n)]   # comp_of + term_score
+        score = f32(0.0)
+        for t in range(n):                                   # exact score: query order, from 0.0
+            if present[t]:
+                score = f32(score + contrib[t])
+        didf_k = f32(idf[drv] * k1p)
+        quot = down(f32(tf[drv] / f32(tf[drv] + cache[drv])), 2)      # fdividef: up to 2 ulp below the rounded quotient
+        B = f32(didf_k * quot)
+        for t in range(n):                                   # bound: driver first, then the other present terms
+            if t != drv and present[t]:
+                B = f32(B + contrib[t])
+        assert f32(B * f32(1.000002)) >= score, (n, drv, float(B), float(score))
+        worst = max(worst, float(score) / float(B) - 1.0)
+    assert worst < 2e-6                                      # the slack actually needed stays well inside the inflation
+
+
+def test_group_maximum_threshold_is_a_valid_lower_bound():
+    """Threshold seeding of the tcgen05 scans (vec_scan_tc.cu, sample mode): the k-th largest of the per-32-row-group maxima is
+    never above the true k-th best score (k disjoint groups each hold a row at least that good), and for k << #groups it is
+    close to the exact k-th of the sample."""
+    rng = np.random.default_rng(12)
+    for n_groups, k in ((1184, 10), (1184, 32), (64, 10), (16, 10), (8, 10)):
+        scores = rng.normal(size=(n_groups, 32)).astype(np.float32)
+        gmax = np.sort(scores.max(axis=1))[::-1]
+        exact = np.sort(scores.ravel())[::-1]
+        if n_groups >= k:
+            seed = gmax[k - 1]
+            assert seed <= exact[k - 1]
+            # rank of the seed inside the sample: what the full scan pays for the looser bound
+            rank = int((exact > seed).sum())
+            assert rank >= k - 1
+            if n_groups >= 64 * k // 10:
+                assert rank <= 2 * k + 4
+        # fewer groups than k: kth_from_groupmax returns "no threshold" (0), nothing to check
