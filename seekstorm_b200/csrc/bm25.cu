@@ -174,9 +174,8 @@ __global__ void compact_dense(const uint32_t* __restrict__ e_bitmap, uint32_t n,
 #ifndef SSB_LEX_AND_SMEM
 #define SSB_LEX_AND_SMEM 0   // AND fast path with per-term state in shared memory (unmeasured experiment, see process_item_fast)
 #endif
-#ifndef SSB_LEX_U
-#define SSB_LEX_U 1   // 32-posting chunks fetched per iteration (measured: batching 2-4 chunks is SLOWER — code size / I-cache)
-#endif
+// (measured earlier in the round: fetching 2-4 posting chunks per loop iteration was SLOWER at every occupancy — the loop body
+// then still contained the whole exact re-score; worth re-measuring now that it does not)
 constexpr uint32_t FAST_T = 4;          // queries with <= 4 live terms take the register-resident fast path
 constexpr uint32_t ENT_NONE = 0xFFFFu;
 
