@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libseekstorm_b200.so")
+# SSB_LIB: A/B experiments with an alternative in-tree build of the same sources (e.g. a compile-time switch); never a fallback
+LIB_PATH = os.environ.get("SSB_LIB") or os.path.join(_HERE, "libseekstorm_b200.so")
 
 SSB_OK = 0
 K_MAX = 32

@@ -359,12 +359,8 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
         set_error("vector scan scratch too small"); return SSB_E_STATE;
     }
     auto kern = a.similarity == SSB_SIM_EUCLIDEAN ? scan_ffma<SSB_SIM_EUCLIDEAN> : scan_ffma<SSB_SIM_DOT>;
-    static bool attr_set[2] = {false, false};
-    int ai = a.similarity == SSB_SIM_EUCLIDEAN;
-    if (!attr_set[ai]) {
-        SSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set[ai] = true;
-    }
+    // per launch: the attribute belongs to the current device's context (several devices per process are allowed)
+    SSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     if (a.ev0) cudaEventRecord(a.ev0, st);
 #if SSB_FFMA_GROUPMAX
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,

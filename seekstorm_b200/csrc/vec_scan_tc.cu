@@ -579,11 +579,9 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
         if (nst > (uint32_t)tc::MAX_STAGES) nst = tc::MAX_STAGES;
         smem = fixed + (int)nst * C::STAGE_BYTES;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ, PREC, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRES ? SMEM_MAX : C::SMEM));
-        attr_set = true;
-    }
+    // per launch, not once per process: the opt-in applies to the CURRENT device's context only (ssb_config.device allows
+    // several indexes on different GPUs in one process); the call is a cheap host-side attribute write
+    SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ, PREC, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRES ? SMEM_MAX : C::SMEM));
     if (a.ev0) cudaEventRecord(a.ev0, st);
     tc::scan_tc<NQ, PREC, BRES><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
                                                                              a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, nst,

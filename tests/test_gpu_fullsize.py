@@ -79,3 +79,113 @@ def test_c2_full_size_vector_int8():
         want = [(doc, -negs) for negs, doc in sorted(best[j])[:10]]
         assert got[qi] == want, (qi, got[qi][:3], want[:3])
     ix.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C3 (BM25, 10 M docs) and C4 (hybrid, 5 M docs) at BASELINE.json's full sizes: top-k identity against the exhaustive
+# oracle (ids, ranks, scores `==`; counts `==`).  The corpus is generated on the GPU (same seeded law as bench.py),
+# handed to the library as device pointers and copied to the host once for the oracle.
+def _build_full_lexical(n_docs, seed, want_oracle=True, **index_kw):
+    from seekstorm_b200 import Index
+    ix = Index(0, max_batch=256, **index_kw)
+    orc = O.OracleIndex() if want_oracle else None
+    ls = 0
+    for lv in synth.gen_lexical_corpus(n_docs, 1_000_000, seed, "cuda"):
+        ix.add_synth_level(lv)
+        if orc is not None:
+            orc.add_level(lv.to_numpy())
+        ls += lv.len_sum_normalized
+    ix.commit(n_docs, ls)
+    if orc is not None:
+        orc.commit(n_docs, ls)
+    return ix, orc
+
+
+@pytest.fixture(scope="module")
+def c3_index():
+    ix, orc = _build_full_lexical(10_000_000, 1003)
+    yield ix, orc
+    ix.close()
+
+
+def _c3_queries(n, seed):
+    from helpers import query_keys
+    return query_keys(synth.gen_queries(n, seed, 20, 100000, (2, 3, 4), (0.4, 0.4, 0.2)))
+
+
+def test_c3_full_size_or_top10_identity(c3_index):
+    """C3: 10 M docs, 64 OR queries of the bench's own law — ids / ranks / scores == exhaustive oracle; TopkCount counts ==."""
+    from seekstorm_b200 import QueryType, ResultType
+    ix, orc = c3_index
+    qk = _c3_queries(64, 2003)                       # the first 64 of the queries bench.py times
+    got, _ = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.Topk)
+    got_c, counts = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
+    for i, kq in enumerate(qk):
+        want, tot = orc.search(kq, O.QUERY_UNION, 10, O.RESULT_TOPKCOUNT)
+        assert len(want) == 10
+        assert got[i] == want, (i, kq, got[i], want)          # bit-exact ids, ranks, scores (pruned Topk path)
+        assert got_c[i] == want, (i, kq, got_c[i], want)      # and with exact counting switched on
+        assert int(counts[i]) == tot, (i, counts[i], tot)
+
+
+def test_c3_full_size_and_top10_identity(c3_index):
+    """C3 corpus, 64 AND queries: ids / ranks / scores / match counts == exhaustive oracle."""
+    from seekstorm_b200 import QueryType, ResultType
+    ix, orc = c3_index
+    qk = _c3_queries(64, 2013)
+    got, counts = ix.search_lexical_batch(qk, QueryType.Intersection, 10, ResultType.TopkCount)
+    got_t, _ = ix.search_lexical_batch(qk, QueryType.Intersection, 10, ResultType.Topk)
+    n_nonempty = 0
+    for i, kq in enumerate(qk):
+        want, tot = orc.search(kq, O.QUERY_INTERSECTION, 10, O.RESULT_TOPKCOUNT)
+        assert got[i] == want, (i, kq, got[i], want)
+        assert got_t[i] == want, (i, kq, got_t[i], want)
+        assert int(counts[i]) == tot, (i, counts[i], tot)
+        n_nonempty += 1 if want else 0
+    assert n_nonempty >= 32                                  # the query law produces real intersections at 10 M docs
+
+
+def test_c3_full_size_batch_invariance_and_paging(c3_index):
+    """Size-independent properties at 10 M docs: results do not depend on batch composition; k=100 (paged) extends k=10."""
+    from seekstorm_b200 import QueryType, ResultType
+    ix, orc = c3_index
+    qk = _c3_queries(200, 2023)
+    full, _ = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.Topk)
+    part, _ = ix.search_lexical_batch(qk[37:53], QueryType.Union, 10, ResultType.Topk)
+    assert part == full[37:53]
+    deep, _ = ix.search_lexical_batch(qk[:8], QueryType.Union, 100, ResultType.Topk)
+    for i in range(8):
+        assert deep[i][:10] == full[i]
+        sc = [s for _, s in deep[i]]
+        assert sc == sorted(sc, reverse=True) and len({d for d, _ in deep[i]}) == len(deep[i])
+        want, _ = orc.search(qk[i], O.QUERY_UNION, 100, O.RESULT_TOPK)
+        assert deep[i] == want
+
+
+def test_c4_full_size_hybrid_identity():
+    """C4: 5 M docs + 5 M x 768 f32 vectors, 16 hybrid queries: fused ids / RRF scores == O.rrf of the two oracle lists
+    (lexical list bit-exact; the vector list is checked to 1e-4 and must agree on ids for the RRF ranks to agree)."""
+    from seekstorm_b200 import QueryType, VectorSimilarity
+    n, d = 5_000_000, 768
+    ix, orc = _build_full_lexical(n, 1004, vector_dims=d, vector_similarity=VectorSimilarity.Cosine)
+    host_rows = np.empty((n, d), dtype=np.float32)
+    for lv in range((n + 65535) // 65536):
+        r = synth.gen_vectors(min(65536, n - lv * 65536), d, 1005 * 1000 + lv, "cuda")
+        ix.add_vector_level(lv, r)
+        host_rows[lv * 65536: lv * 65536 + r.shape[0]] = (r / r.norm(dim=1, keepdim=True)).cpu().numpy()
+        del r
+    qk = _c3_queries(16, 2004)
+    qv = synth.gen_vectors(16, d, 2005, "cpu").numpy()
+    got = ix.search_hybrid_batch(qk, QueryType.Union, qv, 10)
+    lex_got, _ = ix.search_lexical_batch(qk, QueryType.Union, 10)
+    vec_got = ix.search_vector_batch(qv, 10)
+    for i in range(16):
+        lex, _ = orc.search(qk[i], O.QUERY_UNION, 10, O.RESULT_TOPK)
+        vec = O.search_vector(host_rows, O.normalize(qv[i]), 10, O.SIM_COSINE, n_threads=32)
+        assert lex_got[i] == lex, (i, lex_got[i], lex)
+        assert [x for x, _ in vec_got[i]] == [x for x, _ in vec], (i, vec_got[i], vec)
+        assert np.allclose([s for _, s in vec_got[i]], [s for _, s in vec], rtol=1e-4, atol=1e-6)
+        want = O.rrf(lex, vec)[:10]
+        assert [x for x, _ in got[i]] == [x for x, _ in want], (i, got[i], want)
+        assert [np.float32(s) for _, s in got[i]] == [np.float32(s) for _, s in want]
+    ix.close()
