@@ -19,8 +19,10 @@
  * INTEGRATION.md shows the Rust `extern "C"` block + shim a maintainer would add.
  *
  * Conventions: every call returns int32_t status (0 = OK, <0 = SSB_E_*), never unwinds, never aborts.
- * Outputs are caller-allocated.  search_* calls on one handle are serialised internally (one stream);
- * index mutation must be externally serialised against searches (mirrors the reference's RwLock).
+ * Outputs are caller-allocated.  search_* calls on one handle may run CONCURRENTLY from many threads: each takes a
+ * search context (CUDA stream + workspaces) from an internal pool, the committed index data is immutable and shared.
+ * Index mutation (add_level / commit / set_global_df / set_stream) takes the handle exclusively, like the reference's
+ * RwLock around a shard (commit.rs:142, index.rs:5508).
  * Doc ids on the ABI are the reference's shard-local ids: (level << 16) | local (vector.rs:1448,
  * add_result.rs docid = block_id<<16 | local), widened to u64.
  */
@@ -33,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 #define SSB_K_MAX 32u            /* top-k capacity of one kernel pass (lane-distributed lists); *_keys calls */
 #define SSB_K_LIMIT 1024u        /* ssb_search_lexical / ssb_search_vector page beyond 32 internally         */
 #define SSB_MAX_QUERY_TERMS 16u  /* unique terms per lexical query                                        */
@@ -63,6 +65,14 @@ typedef struct ssb_index ssb_index;
 
 /* min_heap.rs:17-40 `Result` {doc_id, score}; 16 bytes */
 typedef struct { uint64_t doc_id; float score; uint32_t pad; } ssb_hit;
+/* the `vb`-feature fields of `Result` (min_heap.rs:21-39), parallel to an ssb_hit array; 48 bytes.
+ * source: ResultSource (Lexical / Vector / Hybrid). */
+enum { SSB_SOURCE_LEXICAL = 0, SSB_SOURCE_VECTOR = 1, SSB_SOURCE_HYBRID = 2 };
+typedef struct {
+    uint32_t field_id, chunk_id, level_id, shard_id, cluster_id;
+    float cluster_score, vector_score, lexical_score;
+    uint32_t source; uint32_t pad[3];
+} ssb_hit_ext;
 
 typedef struct {
     int32_t  device;             /* CUDA device ordinal                                                  */
@@ -137,6 +147,23 @@ int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, ui
  * (Dot/Cosine) or -Σ(q-x)² (Euclidean) exactly as Result.score in vector.rs:1489. */
 int32_t ssb_search_vector(ssb_index* ix, const float* queries, uint32_t n_queries, uint32_t k,
                           ssb_hit* hits, uint32_t* n_hits);
+/* search_vector_shard with all of its arguments (vector.rs:1105-1115): `similarity_threshold: Option<f32>` (pre-mapped as in
+ * TopK::new, vector.rs:388-399: (2t-1)*16129 for Dot/Cosine, -t for Euclidean; hits scoring below it are dropped), queries as
+ * f32 or — ScalarQuantizationI8 indexes only — as the int8 codes the reference's server holds after quantize_f32_to_i8
+ * (search.rs:1477-1490).  ext: [n_queries * k] or NULL (vb fields: level_id, vector_score post-map vector.rs:1495-1499, source);
+ * observed: [n_queries] or NULL (observed_vector_count: every record under AnnMode::All).  Rows that share a doc id (one vector
+ * per chunk) are collapsed to the best-scoring one, as TopK::push does (vector.rs:436-470). */
+enum { SSB_QFMT_F32 = 0, SSB_QFMT_I8 = 1 };
+typedef struct {
+    const void* queries;          /* [n_queries, dims] f32 or i8, host or device                              */
+    uint32_t n_queries, k;
+    uint32_t query_format;        /* SSB_QFMT_*                                                               */
+    uint32_t has_threshold;       /* 0 = None                                                                 */
+    float    similarity_threshold;
+    uint32_t reserved[3];
+} ssb_vec_query;
+int32_t ssb_search_vector_ex(ssb_index* ix, const ssb_vec_query* q, ssb_hit* hits, uint32_t* n_hits, ssb_hit_ext* ext,
+                             uint64_t* observed);
 /* SearchMode::Hybrid: both searches with length k, RRF (k=0.6, rank from 0), sort, truncate to k.
  * hits: [n_queries * k]. */
 int32_t ssb_search_hybrid(ssb_index* ix, const ssb_lex_batch* q, const float* queries, uint32_t k,

@@ -30,6 +30,17 @@ class SsbConfig(C.Structure):
                 ("reserved", C.c_uint32 * 2)]
 
 
+class SsbHitExt(C.Structure):
+    _fields_ = [("field_id", C.c_uint32), ("chunk_id", C.c_uint32), ("level_id", C.c_uint32), ("shard_id", C.c_uint32),
+                ("cluster_id", C.c_uint32), ("cluster_score", C.c_float), ("vector_score", C.c_float),
+                ("lexical_score", C.c_float), ("source", C.c_uint32), ("pad", C.c_uint32 * 3)]
+
+
+class SsbVecQuery(C.Structure):
+    _fields_ = [("queries", C.c_void_p), ("n_queries", C.c_uint32), ("k", C.c_uint32), ("query_format", C.c_uint32),
+                ("has_threshold", C.c_uint32), ("similarity_threshold", C.c_float), ("reserved", C.c_uint32 * 3)]
+
+
 class SsbLevelDesc(C.Structure):
     _fields_ = [("level_id", C.c_uint32), ("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("reserved", C.c_uint32),
                 ("term_keys", C.c_void_p), ("posting_offsets", C.c_void_p), ("doc_ids", C.c_void_p),
@@ -52,7 +63,7 @@ class SsbStats(C.Structure):
 EXPORTS = [
     "ssb_abi_version", "ssb_last_error", "ssb_create", "ssb_destroy", "ssb_lexical_add_level",
     "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
-    "ssb_vector_add_level", "ssb_vector_count", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_hybrid",
+    "ssb_vector_add_level", "ssb_vector_count", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_vector_ex", "ssb_search_hybrid",
     "ssb_rrf_fuse", "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
     "ssb_stream", "ssb_set_stream", "ssb_last_stats",
 ]
@@ -88,6 +99,7 @@ def lib():
         "ssb_set_vector_kernel": [vp, u32],
         "ssb_search_lexical": [vp, C.POINTER(SsbLexBatch), u32, u32, vp, vp, vp],
         "ssb_search_vector": [vp, vp, u32, u32, vp, vp],
+        "ssb_search_vector_ex": [vp, C.POINTER(SsbVecQuery), vp, vp, vp, vp],
         "ssb_search_hybrid": [vp, C.POINTER(SsbLexBatch), vp, u32, vp, vp],
         "ssb_rrf_fuse": [vp, u32, vp, u32, vp, C.POINTER(u32)],
         "ssb_search_vector_keys": [vp, vp, u32, u32, vp],

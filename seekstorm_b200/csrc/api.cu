@@ -3,8 +3,12 @@
 #include <stdarg.h>
 #include <string.h>
 #include <algorithm>
+#include <condition_variable>
+#include <exception>
+#include <memory>
 #include <mutex>
 #include <new>
+#include <shared_mutex>
 #include <vector>
 
 #include "bm25.h"
@@ -61,37 +65,104 @@ static bool dev_ptr(const void* p) {
 
 using namespace ssb;
 
+// One search context = one CUDA stream + every per-call workspace.  Concurrent ssb_search_* calls on one handle each take a
+// context from the pool ("handles are thread-safe for concurrent search_* calls — a stream/workspace pool");
+// the committed index data is immutable and shared.
+struct SearchCtx {
+    cudaStream_t st = nullptr;       // stream this context launches on (its own, or the caller's after ssb_set_stream)
+    cudaStream_t own_st = nullptr;
+    LexWorkspace lex;
+    DevBuf<float> qpad, qstage, qhi, qlo; DevBuf<int8_t> q_i8;
+    DevBuf<uint64_t> ceil, scratch, keys_a, keys_b, counts;
+    std::vector<uint64_t> h_ceil, h_keys_a, h_keys_b, h_counts;
+    ssb_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_used = false, last_lex = false;
+    ~SearchCtx() {
+        if (own_st) cudaStreamSynchronize(own_st);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (own_st) cudaStreamDestroy(own_st);
+    }
+};
+
+constexpr size_t SSB_MAX_CTX = 16;
+
 struct ssb_index {
     ssb_config cfg;
     int n_sms = 0;
-    cudaStream_t st = nullptr;       // stream in use
-    cudaStream_t own_st = nullptr;   // the index's own stream
-    std::mutex mu;
+    cudaStream_t load_st = nullptr;   // load-time stream (add_level / commit)
+    // searches hold `rw` shared, index mutation exclusive (mirrors the reference's RwLock around the shard, commit.rs:142)
+    std::shared_mutex rw;
+    std::mutex pool_mu; std::condition_variable pool_cv;
+    std::vector<std::unique_ptr<SearchCtx>> pool; std::vector<SearchCtx*> free_ctx;
+    bool ext_stream_set = false; cudaStream_t ext_stream = nullptr;   // ssb_set_stream: every search runs on the caller's stream (one context)
+    std::mutex stats_mu; SearchCtx* last_ctx = nullptr; ssb_stats last_stats{};
     LexIndex* lex = nullptr;
     // vector index
     uint32_t dims = 0, dpad = 0, dpad8 = 0;
     bool quant_i8 = false;            // Cosine + ScalarQuantizationI8: int8 corpus, exact int32 dot products
+    bool dup_docs = false;            // some doc id occurs on more than one vector row (multi-chunk documents): results are de-duplicated
     DevBuf<float> rows;
-    DevBuf<int8_t> rows_i8, q_i8;
+    DevBuf<int8_t> rows_i8;
     DevBuf<uint32_t> doc_ids;
     uint64_t n_rows = 0;
-    // query workspace
-    DevBuf<float> qpad; DevBuf<float> qstage; DevBuf<float> qhi, qlo; DevBuf<uint64_t> ceil;
-    std::vector<uint64_t> h_ceil; DevBuf<uint64_t> scratch; DevBuf<uint64_t> keys_a, keys_b, counts;
-    std::vector<uint64_t> h_keys_a, h_keys_b, h_counts;
-    ssb_stats stats{};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_used = false;
 };
 
 namespace {
 
-int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, uint64_t* keys_out_dev /*[nq_pad][32] min*/,
+// RAII lease of a search context
+struct CtxLease {
+    ssb_index* ix; SearchCtx* c = nullptr;
+    explicit CtxLease(ssb_index* i) : ix(i) {}
+    // block = false: give up (c stays null, SSB_OK) instead of waiting when every context is busy
+    int32_t acquire(bool block = true) {
+        std::unique_lock<std::mutex> g(ix->pool_mu);
+        const size_t cap = ix->ext_stream_set ? 1 : SSB_MAX_CTX;
+        for (;;) {
+            if (!ix->free_ctx.empty()) { c = ix->free_ctx.back(); ix->free_ctx.pop_back(); break; }
+            if (ix->pool.size() < cap) {
+                std::unique_ptr<SearchCtx> n(new (std::nothrow) SearchCtx());
+                if (!n) { set_error("out of host memory"); return SSB_E_NOMEM; }
+                if (cudaStreamCreateWithFlags(&n->own_st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); set_error("stream create failed"); return SSB_E_CUDA; }
+                cudaEventCreate(&n->ev0); cudaEventCreate(&n->ev1);
+                n->lex.ev0 = n->ev0; n->lex.ev1 = n->ev1;
+                c = n.get(); ix->pool.push_back(std::move(n));
+                break;
+            }
+            if (!block) return SSB_OK;
+            ix->pool_cv.wait(g);
+        }
+        c->st = ix->ext_stream_set ? ix->ext_stream : c->own_st;
+        c->stats = ssb_stats{}; c->ev_used = false; c->last_lex = false;
+        return SSB_OK;
+    }
+    ~CtxLease() {
+        if (!c) return;
+        { std::lock_guard<std::mutex> g(ix->stats_mu); ix->last_ctx = c; ix->last_stats = c->stats; }
+        { std::lock_guard<std::mutex> g(ix->pool_mu); ix->free_ctx.push_back(c); }
+        ix->pool_cv.notify_one();
+    }
+};
+
+// every extern "C" body runs inside this guard: no exception (thrust::system_error, std::bad_alloc, ...) crosses the C boundary
+#define SSB_API_BEGIN try {
+#define SSB_API_END                                                                                              \
+    } catch (const std::bad_alloc&) { cudaGetLastError(); set_error("out of memory (host or device)"); return SSB_E_NOMEM; \
+    } catch (const std::exception& e) { cudaGetLastError(); set_error("internal error: %s", e.what()); return SSB_E_CUDA;   \
+    } catch (...) { cudaGetLastError(); set_error("internal error: unknown exception"); return SSB_E_CUDA; }
+
+}  // namespace
+
+namespace {
+
+int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_i8, uint32_t nq, uint32_t k, uint64_t* keys_out_dev /*[nq][32]*/,
                  const uint64_t* ceil_dev = nullptr /*[>= nq_pad] paging ceilings*/) {
     if (ix->dims == 0) { set_error("no vector index configured (vector_dims = 0)"); return SSB_E_STATE; }
     if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
+    if (queries_i8 && !ix->quant_i8) { set_error("int8 queries need a ScalarQuantizationI8 index"); return SSB_E_INVALID; }
     if (nq == 0) return SSB_OK;
-    // AUTO (measured, 1M x 768): one FP32 pass of 16 queries takes 0.53 ms, one tensor-core pass of up to 128 queries
-    // 0.81 ms -> FP32 scan for <= 16 queries, tensor-core scan above.  Euclidean always takes the FP32 scan.
+    // AUTO (measured, 1M x 768): one FP32 pass of 16 queries takes ~0.5 ms, one tensor-core pass of up to 128 queries
+    // ~0.6 ms -> FP32 scan for <= 16 queries, tensor-core scan above.  Euclidean always takes the FP32 scan.
     uint32_t kern = ix->cfg.vector_kernel;
     if (ix->quant_i8) kern = SSB_VEC_KERNEL_TCGEN05;   // one kernel for the int8 corpus: tcgen05 kind::i8, 128-query tile
     if (kern == SSB_VEC_KERNEL_AUTO) kern = nq > 16 ? SSB_VEC_KERNEL_TCGEN05_BF16 : SSB_VEC_KERNEL_FFMA;
@@ -99,95 +170,124 @@ int32_t vec_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, u
     const bool tc_bf16 = kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64;
     const uint32_t qt = !use_tc ? vec::VEC_QT : ((kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : 128u);
     const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
-    if (!ix->quant_i8) SSB_TRY(ix->qpad.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
-    const float* qsrc = queries;
+    cudaStream_t st = c.st;
+    if (!ix->quant_i8) SSB_TRY(c.qpad.reserve((size_t)nq_pad * ix->dpad, 0, st));
+    const size_t qbytes = (size_t)nq * ix->dims * (queries_i8 ? 1 : 4);
+    const void* qsrc = queries;
     if (!dev_ptr(queries)) {
-        SSB_TRY(ix->qstage.reserve((size_t)nq * ix->dims, 0, ix->st));
-        SSB_CUDA_TRY(cudaMemcpyAsync(ix->qstage.p, queries, (size_t)nq * ix->dims * 4, cudaMemcpyHostToDevice, ix->st));
-        ix->stats.h2d_bytes += (uint64_t)nq * ix->dims * 4;
-        qsrc = ix->qstage.p;
+        SSB_TRY(c.qstage.reserve(((size_t)nq * ix->dims + 3) / (queries_i8 ? 4 : 1) + 1, 0, st));
+        SSB_CUDA_TRY(cudaMemcpyAsync(c.qstage.p, queries, qbytes, cudaMemcpyHostToDevice, st));
+        c.stats.h2d_bytes += qbytes;
+        qsrc = c.qstage.p;
     }
     if (ix->quant_i8) {
-        // the query is normalised and quantised exactly like the corpus (search.rs:1464-1475, vector_similarity.rs:1226-1232)
-        SSB_TRY(ix->q_i8.reserve((size_t)nq_pad * ix->dpad8, 0, ix->st));
-        SSB_TRY(vec::launch_quantize_rows_i8(qsrc, ix->dims, nq, nq_pad, ix->dims, ix->q_i8.p, ix->dpad8, ix->st));
+        SSB_TRY(c.q_i8.reserve((size_t)nq_pad * ix->dpad8, 0, st));
+        if (queries_i8) {
+            // the caller already ran normalize + quantize_f32_to_i8 (what the reference's server holds after search.rs:1477-1490): pad only
+            SSB_CUDA_TRY(cudaMemsetAsync(c.q_i8.p, 0, (size_t)nq_pad * ix->dpad8, st));
+            SSB_CUDA_TRY(cudaMemcpy2DAsync(c.q_i8.p, ix->dpad8, qsrc, ix->dims, ix->dims, nq, cudaMemcpyDeviceToDevice, st));
+        } else {
+            // the query is normalised and quantised exactly like the corpus (search.rs:1464-1475, vector_similarity.rs:1226-1232)
+            SSB_TRY(vec::launch_quantize_rows_i8((const float*)qsrc, ix->dims, nq, nq_pad, ix->dims, c.q_i8.p, ix->dpad8, st));
+        }
     } else
-    SSB_TRY(vec::launch_prep_queries(qsrc, nq, ix->dims, ix->dims, ix->qpad.p, nq_pad, ix->dpad,
-                                     ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->st));
-    ix->stats.kernel_launches += 1;
-    if (ix->n_rows == 0) { SSB_CUDA_TRY(cudaMemsetAsync(keys_out_dev, 0, (size_t)nq * LIST * 8, ix->st)); return SSB_OK; }
+    SSB_TRY(vec::launch_prep_queries((const float*)qsrc, nq, ix->dims, ix->dims, c.qpad.p, nq_pad, ix->dpad,
+                                     ix->cfg.vector_similarity == SSB_SIM_COSINE, st));
+    c.stats.kernel_launches += 1;
+    if (ix->n_rows == 0) { SSB_CUDA_TRY(cudaMemsetAsync(keys_out_dev, 0, (size_t)nq * LIST * 8, st)); return SSB_OK; }
     size_t sb = use_tc ? vec::scan_tc_scratch_bytes(ix->n_sms, nq_pad) : vec::scan_scratch_bytes(ix->n_sms, nq_pad);
-    SSB_TRY(ix->scratch.reserve(sb / 8 + (size_t)nq_pad * LIST + (nq_pad + 1) / 2, 0, ix->st));
+    SSB_TRY(c.scratch.reserve(sb / 8 + (size_t)nq_pad * LIST + (nq_pad + 1) / 2, 0, st));
     vec::ScanArgs a{};
-    a.rows = ix->rows.p; a.doc_ids = ix->doc_ids.p; a.n_rows = ix->n_rows; a.dpad = ix->dpad; a.queries_padded = ix->qpad.p;
+    a.rows = ix->rows.p; a.doc_ids = ix->doc_ids.p; a.n_rows = ix->n_rows; a.dpad = ix->dpad; a.queries_padded = c.qpad.p;
     a.nq_pad = nq_pad; a.nq_valid = nq; a.k = k; a.similarity = ix->cfg.vector_similarity; a.n_sms = ix->n_sms;
-    a.scratch = ix->scratch.p; a.scratch_bytes = sb;
-    uint64_t* merged = ix->scratch.p + sb / 8;   // [nq_pad][32]
-    a.keys_out = merged; a.ev0 = ix->ev0; a.ev1 = ix->ev1; ix->ev_used = true;
+    a.scratch = c.scratch.p; a.scratch_bytes = sb;
+    uint64_t* merged = c.scratch.p + sb / 8;   // [nq_pad][32]
+    a.keys_out = merged; a.ev0 = c.ev0; a.ev1 = c.ev1; c.ev_used = true;
     a.thr_buf = reinterpret_cast<uint32_t*>(merged + (size_t)nq_pad * LIST);
     a.ceil_keys = ceil_dev;
-    a.launches = &ix->stats.kernel_launches;
+    a.launches = &c.stats.kernel_launches;
     if (ix->quant_i8) {
-        a.rows_i8 = ix->rows_i8.p; a.queries_i8 = ix->q_i8.p; a.dpad8 = ix->dpad8;
-        SSB_TRY(vec::launch_scan_tc(a, 128, 2, ix->st));
+        a.rows_i8 = ix->rows_i8.p; a.queries_i8 = c.q_i8.p; a.dpad8 = ix->dpad8;
+        SSB_TRY(vec::launch_scan_tc(a, 128, 2, st));
     } else if (use_tc) {
-        SSB_TRY(ix->qhi.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
-        SSB_TRY(ix->qlo.reserve((size_t)nq_pad * ix->dpad, 0, ix->st));
-        a.q_hi = ix->qhi.p; a.q_lo = ix->qlo.p;
-        SSB_TRY(vec::launch_scan_tc(a, qt, tc_bf16 ? 1 : 0, ix->st));
+        SSB_TRY(c.qhi.reserve((size_t)nq_pad * ix->dpad, 0, st));
+        SSB_TRY(c.qlo.reserve((size_t)nq_pad * ix->dpad, 0, st));
+        a.q_hi = c.qhi.p; a.q_lo = c.qlo.p;
+        SSB_TRY(vec::launch_scan_tc(a, qt, tc_bf16 ? 1 : 0, st));
     } else {
-        SSB_TRY(vec::launch_scan_ffma(a, ix->st));
+        SSB_TRY(vec::launch_scan_ffma(a, st));
     }
-    SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, ix->st));
-    ix->stats.algorithmic_bytes += (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * (ix->quant_i8 ? 1 : 4);
+    SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, st));
+    c.stats.algorithmic_bytes += (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * (ix->quant_i8 ? 1 : 4);
     return SSB_OK;
 }
 
-void decode_keys(const uint64_t* keys, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+// keys of one query -> hits; `dedup`: keep only the best-scoring row of a doc id (TopK::push, vector.rs:436-470)
+uint32_t decode_list(const uint64_t* keys, uint32_t k, ssb_hit* hits, bool dedup) {
+    uint32_t n = 0;
+    for (uint32_t j = 0; j < LIST && n < k; j++) {
+        const uint64_t key = keys[j];
+        if (!key) break;
+        const uint64_t doc = key_doc(key);
+        if (dedup) { bool seen = false; for (uint32_t i = 0; i < n; i++) seen = seen || hits[i].doc_id == doc; if (seen) continue; }
+        hits[n].doc_id = doc; hits[n].score = key_score(key); hits[n].pad = 0;
+        n++;
+    }
+    return n;
+}
+
+void decode_keys(const uint64_t* keys, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits, bool dedup = false) {
     for (uint32_t q = 0; q < nq; q++) {
-        uint32_t n = 0;
-        for (uint32_t j = 0; j < k && j < LIST; j++) {
-            uint64_t key = keys[(size_t)q * LIST + j];
-            if (!key) break;
-            hits[(size_t)q * k + n].doc_id = key_doc(key);
-            hits[(size_t)q * k + n].score = key_score(key);
-            hits[(size_t)q * k + n].pad = 0;
-            n++;
-        }
+        const uint32_t n = decode_list(keys + (size_t)q * LIST, k, hits + (size_t)q * k, dedup);
         for (uint32_t j = n; j < k; j++) { hits[(size_t)q * k + j].doc_id = 0; hits[(size_t)q * k + j].score = 0.f; hits[(size_t)q * k + j].pad = 0; }
         if (n_hits) n_hits[q] = n;
     }
 }
 
-// Paging state of the host-facing search calls (k > SSB_K_MAX).
+// Paging state of the host-facing search calls (k > SSB_K_MAX, or de-duplication of multi-chunk documents).
 struct PageState {
-    ssb_index* ix; uint32_t nq, k; ssb_hit* hits; uint32_t* n_hits; std::vector<uint32_t> cnt;
-    PageState(ssb_index* ix_, uint32_t nq_, uint32_t k_, ssb_hit* h, uint32_t* n) : ix(ix_), nq(nq_), k(k_), hits(h), n_hits(n), cnt(nq_, 0) {
-        ix->h_ceil.assign((size_t)nq_ + 256, 0);
+    SearchCtx& c; uint32_t nq, k; ssb_hit* hits; uint32_t* n_hits; std::vector<uint32_t> cnt; std::vector<uint8_t> open; bool dedup;
+    PageState(SearchCtx& c_, uint32_t nq_, uint32_t k_, ssb_hit* h, uint32_t* n, bool dedup_ = false)
+        : c(c_), nq(nq_), k(k_), hits(h), n_hits(n), cnt(nq_, 0), open(nq_, 1), dedup(dedup_) {
+        c.h_ceil.assign((size_t)nq_ + 256, 0);
     }
-    // append up to kk keys per query from a [nq][32] page; returns true if any query may have more results
-    bool append(const uint64_t* keys, uint32_t done, uint32_t kk) {
+    // consume one [nq][32] page that was fetched with `kk` results per query; returns true if any query wants another page
+    bool append(const uint64_t* keys, uint32_t kk) {
         bool more = false;
         for (uint32_t q = 0; q < nq; q++) {
-            if (cnt[q] < done) { ix->h_ceil[q] = 0; continue; }         // exhausted on an earlier page
-            uint32_t n = 0; uint64_t last = 0;
-            for (uint32_t j = 0; j < kk; j++) {
+            if (!open[q]) { c.h_ceil[q] = 0; continue; }                    // exhausted or complete on an earlier page
+            uint32_t seen = 0; uint64_t last = 0;
+            for (uint32_t j = 0; j < kk && cnt[q] < k; j++) {
                 const uint64_t key = keys[(size_t)q * LIST + j];
                 if (!key) break;
-                ssb_hit& h = hits[(size_t)q * k + cnt[q] + n];
-                h.doc_id = key_doc(key); h.score = key_score(key); h.pad = 0;
-                last = key; n++;
+                seen++; last = key;
+                const uint64_t doc = key_doc(key);
+                if (dedup) {
+                    bool dup = false;
+                    for (uint32_t i = 0; i < cnt[q]; i++) dup = dup || hits[(size_t)q * k + i].doc_id == doc;
+                    if (dup) continue;
+                }
+                ssb_hit& h = hits[(size_t)q * k + cnt[q]];
+                h.doc_id = doc; h.score = key_score(key); h.pad = 0;
+                cnt[q]++;
             }
-            cnt[q] += n;
-            ix->h_ceil[q] = n == kk ? last : 0;                           // 0 = nothing left below
-            more = more || n == kk;
+            // another page only if this one was full (else the list is exhausted) and the query still lacks results
+            open[q] = seen == kk && cnt[q] < k;
+            c.h_ceil[q] = open[q] ? last : 0;                                // 0 = nothing left below
+            more = more || open[q];
         }
         return more;
     }
+    uint32_t next_page_k() const {   // results to fetch per query on the next page
+        if (dedup) return SSB_K_MAX;
+        uint32_t need = 0;
+        for (uint32_t q = 0; q < nq; q++) if (open[q]) need = std::max(need, k - cnt[q]);
+        return need < SSB_K_MAX ? need : SSB_K_MAX;
+    }
     int32_t upload_ceilings() {
-        SSB_TRY(ix->ceil.reserve((size_t)nq + 256, 0, ix->st));
-        SSB_CUDA_TRY(cudaMemcpyAsync(ix->ceil.p, ix->h_ceil.data(), ((size_t)nq + 256) * 8, cudaMemcpyHostToDevice, ix->st));
-        ix->stats.h2d_bytes += (uint64_t)nq * 8;
+        SSB_TRY(c.ceil.reserve((size_t)nq + 256, 0, c.st));
+        SSB_CUDA_TRY(cudaMemcpyAsync(c.ceil.p, c.h_ceil.data(), ((size_t)nq + 256) * 8, cudaMemcpyHostToDevice, c.st));
+        c.stats.h2d_bytes += (uint64_t)nq * 8;
         return SSB_OK;
     }
     void finish() {
@@ -200,6 +300,36 @@ struct PageState {
 
 inline bool hit_better(const ssb_hit& a, const ssb_hit& b) { return a.score > b.score || (a.score == b.score && a.doc_id < b.doc_id); }
 
+void finish_stats(ssb_index* ix, SearchCtx& c) {
+    if (c.ev_used) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(c.ev1) == cudaSuccess && cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess)
+            c.stats.dominant_kernel_ns = (uint64_t)((double)ms * 1e6);
+        else cudaGetLastError();
+    }
+}
+
+// host-facing vector search: paging beyond 32 results, de-duplication, optional threshold
+int32_t search_vector_host(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_i8, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+    SSB_TRY(c.keys_a.reserve((size_t)nq * LIST, 0, c.st));
+    c.h_keys_a.resize((size_t)nq * LIST);
+    PageState ps(c, nq, k, hits, n_hits, ix->dup_docs);
+    // the fused kernels keep 32 results per query; longer result lists are produced page by page, each page restricted to
+    // keys strictly below the last key of the previous one (keys are a total order on (score desc, doc id asc))
+    uint32_t kk = ix->dup_docs ? SSB_K_MAX : (k < SSB_K_MAX ? k : SSB_K_MAX);
+    for (uint32_t page = 0; page < 4096; page++) {
+        SSB_TRY(vec_keys(ix, c, queries, queries_i8, nq, kk, c.keys_a.p, page ? c.ceil.p : nullptr));
+        SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
+        SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
+        c.stats.d2h_bytes += (uint64_t)nq * LIST * 8;
+        if (!ps.append(c.h_keys_a.data(), kk)) break;
+        kk = ps.next_page_k();
+        SSB_TRY(ps.upload_ceilings());
+    }
+    ps.finish();
+    return SSB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -208,6 +338,7 @@ uint32_t ssb_abi_version(void) { return SSB_ABI_VERSION; }
 const char* ssb_last_error(void) { return g_err; }
 
 int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
+    SSB_API_BEGIN
     if (!cfg || !out) { set_error("ssb_create: null argument"); return SSB_E_INVALID; }
     *out = nullptr;
     int ndev = 0;
@@ -223,192 +354,261 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     cudaDeviceProp prop;
     SSB_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor); return SSB_E_UNSUPPORTED; }
-    ssb_index* ix = new (std::nothrow) ssb_index();
-    if (!ix) return SSB_E_NOMEM;
+    std::unique_ptr<ssb_index> ix(new (std::nothrow) ssb_index());
+    if (!ix) { set_error("out of host memory"); return SSB_E_NOMEM; }
     ix->cfg = *cfg;
     if (ix->cfg.max_batch == 0) ix->cfg.max_batch = 4096;
     ix->n_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking) != cudaSuccess) { delete ix; set_error("stream create failed"); return SSB_E_CUDA; }
-    ix->own_st = ix->st;
-    cudaEventCreate(&ix->ev0); cudaEventCreate(&ix->ev1);
-    ix->lex = new LexIndex(ix->st, ix->n_sms, ix->cfg.max_batch);
-    ix->lex->set_events(ix->ev0, ix->ev1);
+    if (cudaStreamCreateWithFlags(&ix->load_st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); set_error("stream create failed"); return SSB_E_CUDA; }
+    ix->lex = new (std::nothrow) LexIndex(ix->load_st, ix->n_sms, ix->cfg.max_batch);
+    if (!ix->lex) { cudaStreamDestroy(ix->load_st); set_error("out of host memory"); return SSB_E_NOMEM; }
     ix->dims = cfg->vector_dims;
     ix->dpad = (cfg->vector_dims + 31) / 32 * 32;
     ix->dpad8 = (cfg->vector_dims + 127) / 128 * 128;
     ix->quant_i8 = cfg->vector_quantization == SSB_QUANT_SCALAR_I8;
-    *out = ix;
+    *out = ix.release();
     return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_destroy(ssb_index* ix) {
+    SSB_API_BEGIN
     if (!ix) return SSB_OK;
     cudaSetDevice(ix->cfg.device);
-    cudaStreamSynchronize(ix->st);
-    delete ix->lex;
-    ix->rows.release(); ix->rows_i8.release(); ix->q_i8.release(); ix->doc_ids.release(); ix->qpad.release(); ix->qstage.release(); ix->qhi.release(); ix->qlo.release(); ix->ceil.release(); ix->scratch.release();
-    ix->keys_a.release(); ix->keys_b.release(); ix->counts.release();
-    cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1);
-    cudaStreamDestroy(ix->own_st);
+    {
+        std::unique_lock<std::shared_mutex> g(ix->rw);    // waits for searches in flight
+        cudaStreamSynchronize(ix->load_st);
+        ix->pool.clear();                                  // ~SearchCtx synchronises its stream
+        delete ix->lex; ix->lex = nullptr;
+        ix->rows.release(); ix->rows_i8.release(); ix->doc_ids.release();
+        cudaStreamDestroy(ix->load_st);
+    }
     delete ix;
     return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_lexical_add_level(ssb_index* ix, const ssb_level_desc* level) {
+    SSB_API_BEGIN
     if (!ix) { set_error("null index"); return SSB_E_INVALID; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::unique_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     return ix->lex->add_level(level);
+    SSB_API_END
 }
 
 int32_t ssb_lexical_commit(ssb_index* ix, uint64_t n_docs, uint64_t len_sum) {
+    SSB_API_BEGIN
     if (!ix) { set_error("null index"); return SSB_E_INVALID; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::unique_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     return ix->lex->commit(n_docs, len_sum);
+    SSB_API_END
 }
 
 int32_t ssb_lexical_dict_size(const ssb_index* ix, uint64_t* n) { if (!ix || !n) return SSB_E_INVALID; return ix->lex->dict_size(n); }
 int32_t ssb_lexical_dict_export(const ssb_index* ix, uint64_t* keys, uint32_t* dfs, uint64_t cap) { if (!ix) return SSB_E_INVALID; return ix->lex->dict_export(keys, dfs, cap); }
 int32_t ssb_lexical_set_global_df(ssb_index* ix, const uint64_t* keys, const uint32_t* dfs, uint64_t n) {
+    SSB_API_BEGIN
     if (!ix || (n && (!keys || !dfs))) return SSB_E_INVALID;
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::unique_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     return ix->lex->set_global_df(keys, dfs, n);
+    SSB_API_END
 }
 
 int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride, const uint16_t* local_ids,
                              uint32_t n, uint32_t dims) {
+    SSB_API_BEGIN
     if (!ix || (n && !rows)) { set_error("ssb_vector_add_level: null argument"); return SSB_E_INVALID; }
     if (ix->dims == 0 || dims != ix->dims) { set_error("dims %u != configured vector_dims %u", dims, ix->dims); return SSB_E_INVALID; }
     if (n > 65536) { set_error("a level holds at most 65536 vectors"); return SSB_E_INVALID; }
+    if (level_id >= 65536) { set_error("level_id must be < 65536 (doc id = level_id << 16 | local)"); return SSB_E_INVALID; }
     if (row_stride == 0) row_stride = dims;
     if (row_stride < dims) { set_error("row stride < dims"); return SSB_E_INVALID; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::unique_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     if (n == 0) return SSB_OK;
-    SSB_TRY(ix->doc_ids.reserve(ix->n_rows + n, ix->n_rows, ix->st));
+    cudaStream_t st = ix->load_st;
+    // multi-chunk documents: several rows may share a local id (one vector per chunk, vector.rs:62-73); the reference's TopK keeps
+    // the best chunk per doc id (vector.rs:436-470) — remember that this index needs the de-duplicating result path
+    std::vector<uint16_t> h_ids;
+    if (local_ids) {
+        h_ids.resize(n);
+        SSB_CUDA_TRY(cudaMemcpy(h_ids.data(), local_ids, (size_t)n * 2, cudaMemcpyDefault));
+        std::vector<bool> seen(65536, false);
+        for (uint32_t i = 0; i < n; i++) { if (seen[h_ids[i]]) ix->dup_docs = true; seen[h_ids[i]] = true; }
+    }
+    SSB_TRY(ix->doc_ids.reserve(ix->n_rows + n, ix->n_rows, st));
+    DevTmp<float> stage;
     if (ix->quant_i8) {
         // index-time normalise + quantise (vector.rs:585-640); the f32 rows are only staged
-        SSB_TRY(ix->rows_i8.reserve((ix->n_rows + n) * ix->dpad8, ix->n_rows * ix->dpad8, ix->st));
-        SSB_TRY(ix->qstage.reserve((size_t)n * dims, 0, ix->st));
-        SSB_CUDA_TRY(cudaMemcpy2DAsync(ix->qstage.p, (size_t)dims * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, ix->st));
-        SSB_TRY(vec::launch_quantize_rows_i8(ix->qstage.p, dims, n, n, dims, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8, ix->st));
+        SSB_TRY(ix->rows_i8.reserve((ix->n_rows + n) * ix->dpad8, ix->n_rows * ix->dpad8, st));
+        SSB_CUDA_TRY(stage.alloc((size_t)n * dims));
+        SSB_CUDA_TRY(cudaMemcpy2DAsync(stage.p, (size_t)dims * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, st));
+        SSB_TRY(vec::launch_quantize_rows_i8(stage.p, dims, n, n, dims, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8, st));
     } else {
-        SSB_TRY(ix->rows.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, ix->st));
+        SSB_TRY(ix->rows.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, st));
         float* dst = ix->rows.p + ix->n_rows * ix->dpad;
-        SSB_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ix->dpad * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, ix->st));
-        SSB_TRY(vec::launch_normalize_rows(dst, n, dims, ix->dpad, ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->st));
+        SSB_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ix->dpad * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, st));
+        SSB_TRY(vec::launch_normalize_rows(dst, n, dims, ix->dpad, ix->cfg.vector_similarity == SSB_SIM_COSINE, st));
     }
-    const uint16_t* lid = local_ids; uint16_t* tmp = nullptr;
+    DevTmp<uint16_t> tmp;
+    const uint16_t* lid = local_ids;
     if (local_ids && !dev_ptr(local_ids)) {
-        SSB_CUDA_TRY(cudaMalloc(&tmp, (size_t)n * 2));
-        SSB_CUDA_TRY(cudaMemcpyAsync(tmp, local_ids, (size_t)n * 2, cudaMemcpyHostToDevice, ix->st));
-        lid = tmp;
+        SSB_CUDA_TRY(tmp.alloc(n));
+        SSB_CUDA_TRY(cudaMemcpyAsync(tmp.p, h_ids.data(), (size_t)n * 2, cudaMemcpyHostToDevice, st));
+        lid = tmp.p;
     }
-    SSB_TRY(vec::launch_fill_doc_ids(ix->doc_ids.p + ix->n_rows, lid, level_id, n, ix->st));
-    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-    if (tmp) cudaFree(tmp);
+    SSB_TRY(vec::launch_fill_doc_ids(ix->doc_ids.p + ix->n_rows, lid, level_id, n, st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(st));
     ix->n_rows += n;
     return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_set_vector_kernel(ssb_index* ix, uint32_t kernel) {
+    SSB_API_BEGIN
     if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_BF16_N64) { set_error("bad vector kernel"); return SSB_E_INVALID; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::unique_lock<std::shared_mutex> g(ix->rw);
     ix->cfg.vector_kernel = kernel;
     return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_vector_count(const ssb_index* ix, uint64_t* n) { if (!ix || !n) return SSB_E_INVALID; *n = ix->n_rows; return SSB_OK; }
 
 int32_t ssb_search_vector_keys(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, uint64_t* keys_out_dev) {
+    SSB_API_BEGIN
     if (!ix || (nq && (!queries || !keys_out_dev))) { set_error("ssb_search_vector_keys: null argument"); return SSB_E_INVALID; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::shared_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
-    ix->stats = ssb_stats{};
-    return vec_keys(ix, queries, nq, k, keys_out_dev);
+    CtxLease l(ix); SSB_TRY(l.acquire());
+    return vec_keys(ix, *l.c, queries, false, nq, k, keys_out_dev);
+    SSB_API_END
 }
 
 int32_t ssb_search_vector(ssb_index* ix, const float* queries, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+    SSB_API_BEGIN
     if (!ix || (nq && (!queries || !hits))) { set_error("ssb_search_vector: null argument"); return SSB_E_INVALID; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::shared_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
-    ix->stats = ssb_stats{};
     if (nq == 0) return SSB_OK;
     if (k == 0 || k > SSB_K_LIMIT) { set_error("k must be in 1..%u", SSB_K_LIMIT); return SSB_E_UNSUPPORTED; }
-    SSB_TRY(ix->keys_a.reserve((size_t)nq * LIST, 0, ix->st));
-    ix->h_keys_a.resize((size_t)nq * LIST);
-    PageState ps(ix, nq, k, hits, n_hits);
-    // the fused kernels keep 32 results per query; longer result lists are produced page by page, each page restricted to
-    // keys strictly below the last key of the previous one (keys are a total order on (score desc, doc id asc))
-    for (uint32_t done = 0; done < k; done += SSB_K_MAX) {
-        const uint32_t kk = k - done < SSB_K_MAX ? k - done : SSB_K_MAX;
-        SSB_TRY(vec_keys(ix, queries, nq, kk, ix->keys_a.p, done ? ix->ceil.p : nullptr));
-        SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
-        SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-        ix->stats.d2h_bytes += (uint64_t)nq * LIST * 8;
-        if (!ps.append(ix->h_keys_a.data(), done, kk) || done + kk >= k) break;
-        SSB_TRY(ps.upload_ceilings());
-    }
-    ps.finish();
+    CtxLease l(ix); SSB_TRY(l.acquire());
+    SSB_TRY(search_vector_host(ix, *l.c, queries, false, nq, k, hits, n_hits));
+    finish_stats(ix, *l.c);
     return SSB_OK;
+    SSB_API_END
+}
+
+int32_t ssb_search_vector_ex(ssb_index* ix, const ssb_vec_query* vq, ssb_hit* hits, uint32_t* n_hits, ssb_hit_ext* ext, uint64_t* observed) {
+    SSB_API_BEGIN
+    if (!ix || !vq || (vq->n_queries && (!vq->queries || !hits))) { set_error("ssb_search_vector_ex: null argument"); return SSB_E_INVALID; }
+    if (vq->query_format > SSB_QFMT_I8) { set_error("bad query_format"); return SSB_E_INVALID; }
+    std::shared_lock<std::shared_mutex> g(ix->rw);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    const uint32_t nq = vq->n_queries, k = vq->k;
+    if (nq == 0) return SSB_OK;
+    if (k == 0 || k > SSB_K_LIMIT) { set_error("k must be in 1..%u", SSB_K_LIMIT); return SSB_E_UNSUPPORTED; }
+    CtxLease l(ix); SSB_TRY(l.acquire());
+    std::vector<uint32_t> nh(nq, 0);
+    SSB_TRY(search_vector_host(ix, *l.c, vq->queries, vq->query_format == SSB_QFMT_I8, nq, k, hits, nh.data()));
+    finish_stats(ix, *l.c);
+    const bool euclid = ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN;
+    // TopK::new (vector.rs:388-399): threshold pre-map (2t-1)*16129 for Dot/Cosine, -t for Euclidean; TopK::push (:421) rejects
+    // score < threshold.  The hits are sorted by score, so dropping the tail is the same filter.
+    volatile float t2 = vq->similarity_threshold * 2.0f; volatile float t21 = t2 - 1.0f;
+    const float cut = euclid ? -vq->similarity_threshold : t21 / (1.0f / 16129.0f);
+    for (uint32_t q = 0; q < nq; q++) {
+        uint32_t n = nh[q];
+        if (vq->has_threshold) {
+            uint32_t m = 0;
+            while (m < n && !(hits[(size_t)q * k + m].score < cut)) m++;
+            for (uint32_t j = m; j < n; j++) hits[(size_t)q * k + j] = ssb_hit{0, 0.f, 0};
+            n = m;
+        }
+        if (n_hits) n_hits[q] = n;
+        if (observed) observed[q] = ix->n_rows;              // AnnMode::All scores every record (observed_vector_count, vector.rs:420)
+        if (ext) for (uint32_t j = 0; j < k; j++) {
+            ssb_hit_ext& e = ext[(size_t)q * k + j];
+            memset(&e, 0, sizeof(e));
+            if (j >= n) continue;
+            const ssb_hit& h = hits[(size_t)q * k + j];
+            e.level_id = (uint32_t)(h.doc_id >> 16);           // vector.rs:1448 doc id = level << 16 | local
+            volatile float sn = h.score * (1.0f / 16129.0f); volatile float s1 = sn + 1.0f;
+            e.vector_score = euclid ? -h.score : s1 * 0.5f;     // vector.rs:1495-1499 (SIMILARITY_NORMALIZATION_64_I8 regardless of precision)
+            e.cluster_score = euclid ? 0.f : 0.5f;              // no clustering (AnnMode::All, Clustering::None): cluster_score = 0 -> post-map 0.5 / -0
+            e.source = SSB_SOURCE_VECTOR;
+        }
+    }
+    return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_search_lexical_keys(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, uint32_t result_type, uint64_t* keys_out_dev,
                                 uint64_t* count_dev) {
+    SSB_API_BEGIN
     if (!ix || !q) { set_error("ssb_search_lexical_keys: null argument"); return SSB_E_INVALID; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::shared_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
-    ix->stats = ssb_stats{};
-    ix->ev_used = true;
-    return ix->lex->search_keys(q, k, result_type, keys_out_dev, count_dev, &ix->stats.kernel_launches);
+    CtxLease l(ix); SSB_TRY(l.acquire());
+    l.c->ev_used = true; l.c->last_lex = true;
+    return ix->lex->search_keys(l.c->lex, l.c->st, q, k, result_type, keys_out_dev, count_dev, &l.c->stats.kernel_launches);
+    SSB_API_END
 }
 
 int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, uint32_t result_type, ssb_hit* hits, uint32_t* n_hits,
                            uint64_t* count_total) {
+    SSB_API_BEGIN
     if (!ix || !q || (q->n_queries && k && result_type != SSB_RESULT_COUNT && !hits)) { set_error("ssb_search_lexical: null argument"); return SSB_E_INVALID; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::shared_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
-    ix->stats = ssb_stats{};
     const uint32_t nq = q->n_queries;
     if (nq == 0) return SSB_OK;
     if (k > SSB_K_LIMIT) { set_error("k=%u exceeds SSB_K_LIMIT=%u", k, SSB_K_LIMIT); return SSB_E_UNSUPPORTED; }
-    SSB_TRY(ix->keys_a.reserve((size_t)nq * LIST, 0, ix->st));
-    SSB_TRY(ix->counts.reserve(nq, 0, ix->st));
-    ix->h_keys_a.resize((size_t)nq * LIST); ix->h_counts.resize(nq);
+    CtxLease l(ix); SSB_TRY(l.acquire());
+    SearchCtx& c = *l.c;
+    SSB_TRY(c.keys_a.reserve((size_t)nq * LIST, 0, c.st));
+    SSB_TRY(c.counts.reserve(nq, 0, c.st));
+    c.h_keys_a.resize((size_t)nq * LIST); c.h_counts.resize(nq);
     const bool want_hits = hits && k && result_type != SSB_RESULT_COUNT;
     const uint32_t k1 = k < SSB_K_MAX ? k : SSB_K_MAX;
-    SSB_TRY(ix->lex->search_keys(q, k1, result_type, ix->keys_a.p, ix->counts.p, &ix->stats.kernel_launches));
-    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
-    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_counts.data(), ix->counts.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, ix->st));
-    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-    ix->stats.d2h_bytes += (uint64_t)nq * (LIST * 8 + 8);
+    SSB_TRY(ix->lex->search_keys(c.lex, c.st, q, k1, result_type, c.keys_a.p, c.counts.p, &c.stats.kernel_launches));
+    SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
+    SSB_CUDA_TRY(cudaMemcpyAsync(c.h_counts.data(), c.counts.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, c.st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
+    c.stats.d2h_bytes += (uint64_t)nq * (LIST * 8 + 8);
+    c.ev_used = true;
+    finish_stats(ix, c);                                        // the first page's scoring kernel is the one reported
+    const LexStats ls = LexIndex::read_stats(c.lex, c.st);
     if (want_hits) {
-        PageState ps(ix, nq, k, hits, n_hits);
-        bool more = ps.append(ix->h_keys_a.data(), 0, k1);
+        PageState ps(c, nq, k, hits, n_hits);
+        bool more = ps.append(c.h_keys_a.data(), k1);
         // pages beyond the first 32 results: Topk search restricted to keys below the previous page's last key
-        for (uint32_t done = k1; more && done < k; done += SSB_K_MAX) {
-            const uint32_t kk = k - done < SSB_K_MAX ? k - done : SSB_K_MAX;
+        while (more) {
+            const uint32_t kk = ps.next_page_k();
             SSB_TRY(ps.upload_ceilings());
-            SSB_TRY(ix->lex->search_keys(q, kk, SSB_RESULT_TOPK, ix->keys_a.p, nullptr, &ix->stats.kernel_launches, ix->ceil.p));
-            SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
-            SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-            ix->stats.d2h_bytes += (uint64_t)nq * LIST * 8;
-            more = ps.append(ix->h_keys_a.data(), done, kk);
+            SSB_TRY(ix->lex->search_keys(c.lex, c.st, q, kk, SSB_RESULT_TOPK, c.keys_a.p, nullptr, &c.stats.kernel_launches, c.ceil.p));
+            SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
+            SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
+            c.stats.d2h_bytes += (uint64_t)nq * LIST * 8;
+            more = ps.append(c.h_keys_a.data(), kk);
         }
         ps.finish();
     } else if (n_hits) for (uint32_t i = 0; i < nq; i++) n_hits[i] = 0;
-    if (count_total) for (uint32_t i = 0; i < nq; i++) count_total[i] = ix->h_counts[i];
-    LexStats ls = ix->lex->last_stats();
-    ix->stats.postings_visited = ls.postings_visited;
-    ix->stats.algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 12 + ls.items_processed * 24;
-    ix->stats.probes = ls.probes; ix->stats.items_processed = ls.items_processed; ix->stats.items_skipped = ls.items_skipped;
-    ix->ev_used = true;
+    if (count_total) for (uint32_t i = 0; i < nq; i++) count_total[i] = c.h_counts[i];
+    c.stats.postings_visited = ls.postings_visited;
+    // SURVEY.md §8(d) accounting with this layout's sizes: 4 B per streamed posting word, 14 B per exact probe (8 B bitmap word + 2 B
+    // rank + 4 B payload), 128 B per (query, level) record read, 8 B per bitmap word of the dense count paths
+    c.stats.algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 14 + ls.recs_processed * 128 + ls.dense_words * 8;
+    c.stats.probes = ls.probes; c.stats.items_processed = ls.items_processed; c.stats.items_skipped = ls.items_skipped;
     return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_rrf_fuse(const ssb_hit* lex, uint32_t n_lex, const ssb_hit* vec, uint32_t n_vec, ssb_hit* out, uint32_t* n_out) {
+    SSB_API_BEGIN
     // search.rs:1962-2035: k = 0.6, rank from 0 over each list sorted by score desc; then :2097-2106 sort desc.
     if ((n_lex && !lex) || (n_vec && !vec) || !out) { set_error("ssb_rrf_fuse: null argument"); return SSB_E_INVALID; }
     const float kf = 0.6f;
@@ -427,84 +627,131 @@ int32_t ssb_rrf_fuse(const ssb_hit* lex, uint32_t n_lex, const ssb_hit* vec, uin
     std::stable_sort(out, out + n, hit_better);
     if (n_out) *n_out = n;
     return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_search_hybrid(ssb_index* ix, const ssb_lex_batch* q, const float* queries, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+    SSB_API_BEGIN
     if (!ix || !q || !queries || !hits) { set_error("ssb_search_hybrid: null argument"); return SSB_E_INVALID; }
     if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::shared_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
-    ix->stats = ssb_stats{};
     const uint32_t nq = q->n_queries;
     if (nq == 0) return SSB_OK;
-    SSB_TRY(ix->keys_a.reserve((size_t)nq * LIST, 0, ix->st));
-    SSB_TRY(ix->keys_b.reserve((size_t)nq * LIST, 0, ix->st));
-    SSB_TRY(ix->lex->search_keys(q, k, SSB_RESULT_TOPK, ix->keys_a.p, nullptr, &ix->stats.kernel_launches));
-    SSB_TRY(vec_keys(ix, queries, nq, k, ix->keys_b.p));
-    ix->h_keys_a.resize((size_t)nq * LIST); ix->h_keys_b.resize((size_t)nq * LIST);
-    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_a.data(), ix->keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
-    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_b.data(), ix->keys_b.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
-    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-    ix->stats.d2h_bytes += (uint64_t)nq * LIST * 16;
+    // the two per-shard searches are independent until the fusion: the lexical one runs on this context's stream, the vector one
+    // on a second context's stream, so lex_score and the scan share the GPU instead of running back to back
+    CtxLease l(ix); SSB_TRY(l.acquire());
+    SearchCtx& c = *l.c;
+    CtxLease l2(ix);
+    SearchCtx* cv = &c;
+    if (!ix->ext_stream_set) { SSB_TRY(l2.acquire(false)); if (l2.c) cv = l2.c; }   // never wait for a second context (no hold-and-wait)
+    SSB_TRY(c.keys_a.reserve((size_t)nq * LIST, 0, c.st));
+    SSB_TRY(cv->keys_b.reserve((size_t)nq * LIST, 0, cv->st));
+    c.h_keys_a.resize((size_t)nq * LIST); cv->h_keys_b.resize((size_t)nq * LIST);
+    SSB_TRY(ix->lex->search_keys(c.lex, c.st, q, k, SSB_RESULT_TOPK, c.keys_a.p, nullptr, &c.stats.kernel_launches));
+    SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
+    // multi-chunk documents: fetch the full 32-list so that k distinct docs survive the per-doc de-duplication
+    SSB_TRY(vec_keys(ix, *cv, queries, false, nq, ix->dup_docs ? SSB_K_MAX : k, cv->keys_b.p));
+    SSB_CUDA_TRY(cudaMemcpyAsync(cv->h_keys_b.data(), cv->keys_b.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, cv->st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
+    if (cv != &c) SSB_CUDA_TRY(cudaStreamSynchronize(cv->st));
+    c.stats.kernel_launches += cv != &c ? cv->stats.kernel_launches : 0;
+    c.stats.h2d_bytes += cv != &c ? cv->stats.h2d_bytes : 0;
+    c.stats.d2h_bytes += (uint64_t)nq * LIST * 16;
     std::vector<ssb_hit> a(k), b(k), f(2 * (size_t)k);
     for (uint32_t i = 0; i < nq; i++) {
-        uint32_t na = 0, nb = 0, nf = 0;
-        decode_keys(ix->h_keys_a.data() + (size_t)i * LIST, 1, k, a.data(), &na);
-        decode_keys(ix->h_keys_b.data() + (size_t)i * LIST, 1, k, b.data(), &nb);
+        uint32_t nf = 0;
+        const uint32_t na = decode_list(c.h_keys_a.data() + (size_t)i * LIST, k, a.data(), false);
+        const uint32_t nb = decode_list(cv->h_keys_b.data() + (size_t)i * LIST, k, b.data(), ix->dup_docs);
         ssb_rrf_fuse(a.data(), na, b.data(), nb, f.data(), &nf);
         uint32_t n = nf < k ? nf : k;     // search.rs:2117-2119 truncate(length)
         for (uint32_t j = 0; j < k; j++) hits[(size_t)i * k + j] = j < n ? f[j] : ssb_hit{0, 0.f, 0};
         if (n_hits) n_hits[i] = n;
     }
     return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_merge_keys(ssb_index* ix, const uint64_t* keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+    SSB_API_BEGIN
     if (!ix || !keys_dev || !hits) { set_error("ssb_merge_keys: null argument"); return SSB_E_INVALID; }
     if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::shared_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     if (nq == 0) return SSB_OK;
-    SSB_TRY(ix->keys_b.reserve((size_t)nq * LIST, 0, ix->st));
-    SSB_TRY(vec::launch_merge_lists(keys_dev, n_lists, nq, ix->keys_b.p, ix->st));
-    ix->stats.kernel_launches += 1;
-    ix->h_keys_b.resize((size_t)nq * LIST);
-    SSB_CUDA_TRY(cudaMemcpyAsync(ix->h_keys_b.data(), ix->keys_b.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, ix->st));
-    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-    decode_keys(ix->h_keys_b.data(), nq, k, hits, n_hits);
+    CtxLease l(ix); SSB_TRY(l.acquire());
+    SearchCtx& c = *l.c;
+    SSB_TRY(c.keys_b.reserve((size_t)nq * LIST, 0, c.st));
+    SSB_TRY(vec::launch_merge_lists(keys_dev, n_lists, nq, c.keys_b.p, c.st));
+    c.stats.kernel_launches += 1;
+    c.h_keys_b.resize((size_t)nq * LIST);
+    SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_b.data(), c.keys_b.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
+    decode_keys(c.h_keys_b.data(), nq, k, hits, n_hits, ix->dup_docs);
     return SSB_OK;
+    SSB_API_END
 }
 
 int32_t ssb_sync(ssb_index* ix) {
+    SSB_API_BEGIN
     if (!ix) return SSB_E_INVALID;
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
-    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
+    std::vector<cudaStream_t> sts;
+    {
+        std::lock_guard<std::mutex> g(ix->pool_mu);
+        for (auto& c : ix->pool) sts.push_back(ix->ext_stream_set ? ix->ext_stream : c->own_st);
+    }
+    for (cudaStream_t s : sts) SSB_CUDA_TRY(cudaStreamSynchronize(s));
     return SSB_OK;
+    SSB_API_END
 }
 
-void* ssb_stream(ssb_index* ix) { return ix ? (void*)ix->st : nullptr; }
+void* ssb_stream(ssb_index* ix) {
+    if (!ix) return nullptr;
+    if (ix->ext_stream_set) return (void*)ix->ext_stream;
+    std::lock_guard<std::mutex> g(ix->pool_mu);
+    return ix->pool.empty() ? (void*)ix->load_st : (void*)ix->pool[0]->own_st;
+}
 
 int32_t ssb_set_stream(ssb_index* ix, void* stream) {
+    SSB_API_BEGIN
     if (!ix) return SSB_E_INVALID;
-    std::lock_guard<std::mutex> g(ix->mu);
+    std::unique_lock<std::shared_mutex> g(ix->rw);       // no search in flight
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
-    SSB_CUDA_TRY(cudaStreamSynchronize(ix->st));
-    ix->st = stream == SSB_OWN_STREAM ? ix->own_st : (cudaStream_t)stream;
-    ix->lex->set_stream(ix->st);
-    return SSB_OK;
-}
-
-int32_t ssb_last_stats(const ssb_index* ix, ssb_stats* out) {
-    if (!ix || !out) return SSB_E_INVALID;
-    *out = ix->stats;
-    if (ix->ev_used) {
-        cudaSetDevice(ix->cfg.device);
-        float ms = 0.f;
-        if (cudaEventSynchronize(ix->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) == cudaSuccess)
-            out->dominant_kernel_ns = (uint64_t)((double)ms * 1e6);
-        else cudaGetLastError();
+    {
+        std::lock_guard<std::mutex> g2(ix->pool_mu);
+        for (auto& c : ix->pool) SSB_CUDA_TRY(cudaStreamSynchronize(ix->ext_stream_set ? ix->ext_stream : c->own_st));
+        if (stream == SSB_OWN_STREAM) { ix->ext_stream_set = false; ix->ext_stream = nullptr; }
+        else { ix->ext_stream_set = true; ix->ext_stream = (cudaStream_t)stream; }
+        // with a caller-owned stream every search runs on that one stream: keep a single context
+        if (ix->ext_stream_set && ix->pool.size() > 1) {
+            ix->pool.resize(1); ix->free_ctx.clear(); ix->free_ctx.push_back(ix->pool[0].get()); ix->last_ctx = nullptr;
+        }
     }
     return SSB_OK;
+    SSB_API_END
+}
+
+int32_t ssb_last_stats(const ssb_index* cix, ssb_stats* out) {
+    SSB_API_BEGIN
+    if (!cix || !out) return SSB_E_INVALID;
+    ssb_index* ix = const_cast<ssb_index*>(cix);
+    SearchCtx* c = nullptr;
+    { std::lock_guard<std::mutex> g(ix->stats_mu); *out = ix->last_stats; c = ix->last_ctx; }
+    if (c && c->ev_used && out->dominant_kernel_ns == 0) {   // asynchronous *_keys call: wait for its kernel's events now
+        cudaSetDevice(ix->cfg.device);
+        float ms = 0.f;
+        if (cudaEventSynchronize(c->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+            out->dominant_kernel_ns = (uint64_t)((double)ms * 1e6);
+        else cudaGetLastError();
+        if (c->last_lex && out->postings_visited == 0 && c->lex.stats) {
+            const LexStats ls = LexIndex::read_stats(c->lex, ix->ext_stream_set ? ix->ext_stream : c->own_st);
+            out->postings_visited = ls.postings_visited; out->probes = ls.probes; out->items_processed = ls.items_processed; out->items_skipped = ls.items_skipped;
+            if (ls.postings_visited) out->algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 14 + ls.recs_processed * 128 + ls.dense_words * 8;
+        }
+    }
+    return SSB_OK;
+    SSB_API_END
 }
 
 }  // extern "C"

@@ -2,27 +2,39 @@
 //
 // Replaces, for committed data without facets/filters/phrases (all paths /root/reference/seekstorm/src/):
 //   intersection_blockid / intersection_docid   intersection.rs:2023-2301 / 112-2013   (AND)
+//   intersection_bitmap_2                       intersection.rs:33-108                 (dense x dense: bitmap-word AND + popcount)
 //   union_docid_2 / union_docid_3 / single_blockid  union.rs:1168-1479, single.rs:292-417 (OR + block-max)
+//   union_count                                 union.rs:807-1164                      (exact |union|: bitmap-word OR + popcount)
 //   add_result_multiterm_singlefield + get_bm25f_multiterm_singlefield  add_result.rs:3418-3706, 1429-1482
 //   MinHeap::add_topk  min_heap.rs:1193-1259
 //
-// HBM layout (built once at load):
-//   post[] u32 = id16 | tf8<<16 | doclen_byte<<24 — one word per posting, all levels concatenated (level-major,
-//          term-major inside a level).  The doc-length byte is co-located with the posting so scoring needs no
-//          random access into the 64 KB per-level length array (the reference does that gather per candidate,
-//          add_result.rs:1437-1442), and one load delivers id and payload.
+// HBM layout (built once at load; the reference's per-level byte arrays are decoded by the caller / loader):
+//   post[] u32 = id16 | bound16<<16 — the STREAM arena, one word per posting, all levels concatenated (level-major,
+//          term-major inside a level).  bound16 = fp16 bits of the posting's query-independent score component
+//          tf*(K+1)/(tf+cache[len]) rounded UP (filled at commit, when avgdl is known): the per-posting upper bound
+//          idf*bound + R is three instructions (cvt, ffma, compare) and needs no table lookup, so a warp filters 128
+//          postings per 16-byte-per-lane load.
+//   pay[]  u32 = tf16 | doclen_byte<<16 — the PAYLOAD arena (same index): read only for the few postings whose exact
+//          score is computed.  The doc-length byte is co-located with the posting, so scoring never gathers from the
+//          64 KB per-level length array the way add_result.rs:1437-1442 does.
 //   directory: sorted dict_keys -> per-term list of (level, offset, count, block-max, bitmap) entries;
 //          lists with >= 256 postings additionally get an 8 KB bitmap + 2 KB rank index for O(1) probes (the
 //          reference's Bitmap container starts at 4096, compress_postinglist.rs:256-332).
 //
-// Execution: one batch = plan kernel (per query: dictionary lookup, per-block bound = Σ idf·block-max in
-// query order, blocks sorted by bound) + a persistent scoring kernel whose warps pull (query, block) items
-// ordered wave-by-wave (all queries' best block first).  A per-query global threshold θ (the k-th best key so
-// far) gives block-max pruning across blocks and MAXSCORE-style essential-list pruning inside a block.
-// Scores are bit-exact w.r.t. the CPU oracle: every f32 op individually rounded (__fmul_rn/__fdiv_rn/__fadd_rn),
-// summed in query order from 0.0 (add_result.rs:1450-1452), idf and the 256-entry cache computed on the host.
+// Execution: one batch = lex_plan (per query: dictionary lookup, per-level bound = Σ idf·block-max in query order,
+// levels sorted by bound, one fully resolved 128-byte RECORD per (query, level) with the MAXSCORE order and the
+// in-order suffix bounds precomputed by one thread, records grouped into work ITEMS of <= 8 levels) + one persistent
+// lex_score launch whose warps pull items wave by wave (every query's best levels first).  Inside an item the warp keeps
+// its top-k list and threshold in registers across levels, streams the essential lists, pushes the postings that pass the
+// bound filter into a per-warp shared-memory queue and runs the expensive stages (bitmap presence filter, exact in-order
+// re-score) on 32 queued survivors at a time — lanes of one batch may belong to different levels and drivers.
+// A per-query global threshold θ (k-th best key so far, merged under a per-query lock once per dirty item) gives
+// block-max pruning across items.  Scores are bit-exact w.r.t. the CPU oracle: every f32 op individually rounded
+// (__fmul_rn/__fdiv_rn/__fadd_rn), summed in query order from 0.0 (add_result.rs:1450-1452), idf and the 256-entry
+// cache computed on the host.
 #include "bm25.h"
 
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 #include <thrust/device_ptr.h>
@@ -36,10 +48,26 @@
 namespace ssb {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr uint32_t DENSE_MIN = 256;    // lists at least this long get a bitmap + rank index (O(1) probes)
-constexpr uint32_t MAX_LEVELS = 4096;  // per GPU (268M docs); plan kernel smem bound
+constexpr uint32_t DENSE_MIN = 256;     // lists at least this long get a bitmap + rank index (O(1) probes)
+constexpr uint32_t COUNT_DENSE = 512;   // lists at least this long are counted by bitmap-word algebra (8 KB stream < 512 sector probes)
+constexpr uint32_t MAX_LEVELS = 4096;   // per GPU (268M docs); plan kernel smem bound
+constexpr uint32_t FAST_T = 4;          // queries with <= 4 live terms take the record path
+constexpr uint32_t ENT_NONE = 0xFFFFu;
+constexpr uint32_t GMAX = 8;            // records (levels) per work item
+constexpr uint32_t ITEM_W = 4096;       // target size of an item: postings of its top-ranked lists (+64 per record)
+constexpr uint32_t QCAP = 192;          // survivor queue slots per warp: < 32 pending + 4 x 32 pushed per iteration
+constexpr float INFL = 1.000002f;       // bound inflation covering the fp16 round-up + different association of <= 4 additions
 
 // ================================================================= build kernels
+__global__ void validate_offsets(const uint32_t* __restrict__ offs, uint32_t n_terms, uint32_t* bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && offs[0] != 0) atomicAdd(bad, 1u);
+    if (i < n_terms && offs[i + 1] < offs[i]) atomicAdd(bad, 1u);
+}
+__global__ void validate_keys_sorted_unique(const uint64_t* __restrict__ sorted_keys, uint32_t n, uint32_t* bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && sorted_keys[i] == sorted_keys[i + 1]) atomicAdd(bad, 1u);
+}
 // posting i belongs to the term whose offset range contains it (binary search over posting_offsets)
 __global__ void validate_level(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs, const uint32_t* __restrict__ offs,
                                uint32_t n_terms, uint32_t n, uint32_t n_docs, uint32_t* bad) {
@@ -52,20 +80,26 @@ __global__ void validate_level(const uint16_t* __restrict__ ids, const uint16_t*
     if (!ok) atomicAdd(bad, 1u);
 }
 
-__global__ void build_payload(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs,
-                              const uint8_t* __restrict__ len_bytes, uint32_t* __restrict__ post, uint32_t n,
-                              uint64_t post_base, uint64_t* exc_pos, uint32_t* exc_tf, uint32_t* exc_count,
-                              uint32_t exc_cap) {
+__global__ void build_postings(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs, const uint8_t* __restrict__ len_bytes,
+                               uint32_t* __restrict__ post, uint32_t* __restrict__ pay, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t tf = tfs[i];
-    uint32_t len = len_bytes[ids[i]];
-    if (tf >= 255) {
-        uint32_t s = atomicAdd(exc_count, 1u);
-        if (s < exc_cap) { exc_pos[s] = post_base + i; exc_tf[s] = tf; }
-        tf = 255;
-    }
-    post[i] = (uint32_t)ids[i] | ((tf | (len << 8)) << 16);   // id16 | tf8<<16 | len8<<24
+    const uint32_t id = ids[i];
+    post[i] = id;                                                 // bound16 is filled by fill_bounds at commit
+    pay[i] = (uint32_t)tfs[i] | ((uint32_t)len_bytes[id] << 16);  // tf16 | len8<<16
+}
+
+// query-independent posting score component: tf*(K+1)/(tf+cache[len])   (add_result.rs:1450)
+__device__ __forceinline__ float comp_of(const LexView& v, uint32_t payload) {
+    const float tf = (float)(payload & 0xFFFFu);
+    return __fdiv_rn(__fmul_rn(tf, v.k1p), __fadd_rn(tf, __ldg(&v.cache[(payload >> 16) & 255u])));
+}
+
+__global__ void fill_bounds(LexView v, uint32_t* __restrict__ post, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const __half h = __float2half_ru(comp_of(v, v.pay[i]));       // rounded UP: idf*h >= idf*comp
+    post[i] = (post[i] & 0xFFFFu) | ((uint32_t)__half_as_ushort(h) << 16);
 }
 
 __global__ void gather_dict(const uint64_t* __restrict__ term_keys, uint32_t n_terms, uint32_t level_idx,
@@ -86,20 +120,6 @@ __global__ void build_entries(const uint64_t* __restrict__ vals, uint32_t n, con
     e_level[i] = lv; e_off[i] = lvl_base[lv] + a; e_count[i] = b - a;
 }
 
-__device__ __forceinline__ uint32_t exc_lookup(const LexView& v, uint64_t pos) {
-    uint32_t lo = 0, hi = v.n_exc;
-    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (v.exc_pos[m] < pos) lo = m + 1; else hi = m; }
-    return (lo < v.n_exc && v.exc_pos[lo] == pos) ? v.exc_tf[lo] : 255u;
-}
-
-// query-independent posting score component: tf*(K+1)/(tf+cache[len])   (add_result.rs:1450)
-__device__ __forceinline__ float comp_of(const LexView& v, uint32_t payload, uint64_t pos) {
-    uint32_t tfu = payload & 255u;
-    if (tfu == 255u) tfu = exc_lookup(v, pos);
-    float tf = (float)tfu;
-    return __fdiv_rn(__fmul_rn(tf, v.k1p), __fadd_rn(tf, v.cache[payload >> 8]));
-}
-
 // one warp per entry: block-max basis (get_max_score, index.rs:2938-3049 — here exact over the list)
 __global__ void entry_maxcomp(LexView v, uint32_t n_entries, float* __restrict__ out) {
     uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -107,7 +127,7 @@ __global__ void entry_maxcomp(LexView v, uint32_t n_entries, float* __restrict__
     int lane = threadIdx.x & 31;
     uint64_t off = v.e_off[e]; uint32_t cnt = v.e_count[e];
     float m = 0.f;
-    for (uint32_t i = lane; i < cnt; i += 32) m = fmaxf(m, comp_of(v, v.post[off + i] >> 16, off + i));
+    for (uint32_t i = lane; i < cnt; i += 32) m = fmaxf(m, comp_of(v, v.pay[off + i]));
     for (int s = 16; s; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
     if (lane == 0) out[e] = m;
 }
@@ -163,28 +183,28 @@ __global__ void compact_dense(const uint32_t* __restrict__ e_bitmap, uint32_t n,
     if (i < n && e_bitmap[i] != NONE) dense_list[e_bitmap[i]] = i;
 }
 
+// ================================================================= record helpers (host + device)
+__device__ __forceinline__ uint32_t slot_cnt(const LvSlot& s) { return s.offhi_cnt & 0xFFFFFu; }
+__device__ __forceinline__ uint64_t slot_off(const LvSlot& s) { return ((uint64_t)(s.offhi_cnt >> 20) << 32) | s.off_lo; }
+__device__ __forceinline__ uint32_t meta_npres(uint32_t m) { return m & 7u; }
+__device__ __forceinline__ uint32_t meta_perm(uint32_t m, uint32_t p) { return (m >> (3 + 2 * p)) & 3u; }
+__device__ __forceinline__ uint32_t meta_rank(uint32_t m, uint32_t s) { return (m >> (11 + 2 * s)) & 3u; }
+__device__ __forceinline__ uint32_t meta_anddrv(uint32_t m) { return (m >> 19) & 3u; }
+__device__ __forceinline__ uint32_t meta_cperm(uint32_t m, uint32_t c) { return (m >> (21 + 2 * c)) & 3u; }
+
 // ================================================================= plan kernel
 // One CTA per query.  Dictionary lookup (replaces decode_posting_list_object / segment.get, search.rs:2292-2423,
-// 3194-3217), live-term list in query order, per-level bound and presence count, blocks sorted by bound desc
-// (intersection.rs:2224-2225, single.rs:372).  For the first FAST_T live terms the entry index of every level is
-// recorded with the item so the scoring kernel needs no directory search.
-#ifndef SSB_LEX_PRESENCE
-#define SSB_LEX_PRESENCE 1   // OR fast path: per-doc bitmap membership filter before the exact re-score
-#endif
-#ifndef SSB_LEX_AND_SMEM
-#define SSB_LEX_AND_SMEM 0   // AND fast path with per-term state in shared memory (unmeasured experiment, see process_item_fast)
-#endif
-// (measured earlier in the round: fetching 2-4 posting chunks per loop iteration was SLOWER at every occupancy — the loop body
-// then still contained the whole exact re-score; worth re-measuring now that it does not)
-constexpr uint32_t FAST_T = 4;          // queries with <= 4 live terms take the register-resident fast path
-constexpr uint32_t ENT_NONE = 0xFFFFu;
-
+// 3194-3217), live-term list in query order, per-level bound and presence count, levels sorted by bound desc
+// (intersection.rs:2224-2225, single.rs:372).  Then one THREAD per (query, level) resolves everything the scoring warp
+// would otherwise derive per item with warp-uniform code: directory entries of every term, MAXSCORE order (terms by
+// block bound), the in-query-order suffix sums S[p] / R[p], the count order, the AND driver — and writes them as one
+// 128-byte record.  Thread 0 finally cuts the sorted record list into work items.
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
-                                                uint32_t query_type, QueryPlan* plans, uint64_t* items, uint2* item_ent, uint32_t* ctr,
+                                                uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
                                                 uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     float* bound = (float*)sm_raw;                                     // [n_levels]
-    uint32_t* cnt = (uint32_t*)(bound + v.n_levels);                   // [n_levels]
+    uint32_t* cnt = (uint32_t*)(bound + v.n_levels);                   // [n_levels]; after the sort: item weights by sorted position
     uint16_t* ent = (uint16_t*)(cnt + v.n_levels);                     // [FAST_T][n_levels] entry index relative to term.first
     uint64_t* skey = (uint64_t*)(((uintptr_t)(ent + FAST_T * v.n_levels) + 7) & ~(uintptr_t)7);  // [n_pow2]
     __shared__ QTerm st[SSB_MAX_QUERY_TERMS];
@@ -192,6 +212,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
     __shared__ uint32_t n_valid;
 
     const uint32_t q = blockIdx.x;
+    const uint32_t nlv = v.n_levels;
     const uint32_t t0 = q_off[q], nt_raw = q_off[q + 1] - t0;
     const uint32_t nt = nt_raw > SSB_MAX_QUERY_TERMS ? SSB_MAX_QUERY_TERMS : nt_raw;
     if (threadIdx.x < 32) glist[(size_t)q * LIST + threadIdx.x] = 0;
@@ -217,11 +238,11 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         }
         // search.rs:3290-3296: AND with an unknown term -> empty result; OR drops the term
         if (query_type == SSB_QUERY_INTERSECTION && missing) nl = 0;
-        pl.n_live = nl; pl.n_items = 0; pl.flags = 0; pl.pad = 0;
+        pl.n_live = nl; pl.n_items = 0; pl.n_recs = 0; pl.pad = 0;
     }
-    for (uint32_t b = threadIdx.x; b < v.n_levels; b += blockDim.x) {
+    for (uint32_t b = threadIdx.x; b < nlv; b += blockDim.x) {
         bound[b] = 0.f; cnt[b] = 0;
-        for (uint32_t t = 0; t < FAST_T; t++) ent[t * v.n_levels + b] = (uint16_t)ENT_NONE;
+        for (uint32_t t = 0; t < FAST_T; t++) ent[t * nlv + b] = (uint16_t)ENT_NONE;
     }
     __syncthreads();
     const uint32_t nl = pl.n_live;
@@ -231,13 +252,13 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             uint32_t lv = v.e_level[qt.first + e];
             bound[lv] = __fadd_rn(bound[lv], __fmul_rn(qt.idf, v.e_maxcomp[qt.first + e]));
             cnt[lv] += 1;
-            if (t < FAST_T) ent[t * v.n_levels + lv] = (uint16_t)e;
+            if (t < FAST_T) ent[t * nlv + lv] = (uint16_t)e;
         }
         __syncthreads();
     }
     for (uint32_t b = threadIdx.x; b < n_pow2; b += blockDim.x) {
         uint64_t key = 0;
-        if (b < v.n_levels) {
+        if (b < nlv) {
             bool ok = query_type == SSB_QUERY_INTERSECTION ? (nl > 0 && cnt[b] == nl) : (cnt[b] > 0);
             if (ok) { key = ((uint64_t)ord_f32(bound[b]) << 32) | (uint64_t)(0xFFFFFFFFu - b); atomicAdd(&n_valid, 1u); }
         }
@@ -257,21 +278,101 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             __syncthreads();
         }
     }
-    for (uint32_t j = threadIdx.x; j < v.n_levels; j += blockDim.x) {
-        const uint64_t key = skey[j];
-        items[(size_t)q * v.n_levels + j] = key;
-        if (key) {
-            const uint32_t lv = 0xFFFFFFFFu - (uint32_t)key;
-            uint2 e;
-            e.x = (uint32_t)ent[lv] | ((uint32_t)ent[v.n_levels + lv] << 16);
-            e.y = (uint32_t)ent[2 * v.n_levels + lv] | ((uint32_t)ent[3 * v.n_levels + lv] << 16);
-            item_ent[(size_t)q * v.n_levels + j] = e;
+    // ---- one thread per sorted position: the resolved record ----
+    const uint32_t nv = n_valid;
+    const bool is_and = query_type == SSB_QUERY_INTERSECTION;
+    for (uint32_t j = threadIdx.x; j < nv; j += blockDim.x) {
+        const uint32_t lv = 0xFFFFFFFFu - (uint32_t)skey[j];
+        LvRec r;
+        r.docbase = v.level_ids[lv] << 16; r.bound = bound[lv]; r.lv = lv;
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0; float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+        uint32_t weight = ITEM_W;
+        uint32_t meta = 0;
+#pragma unroll
+        for (uint32_t s = 0; s < FAST_T; s++) {
+            LvSlot sl; sl.off_lo = 0; sl.offhi_cnt = 0; sl.bmi = NONE; sl.ub = 0.f;
+            float idf = 0.f;
+            if (s < nl && nl <= FAST_T) {
+                const QTerm qt = pl.t[s];
+                idf = qt.idf;
+                const uint32_t er = ent[s * nlv + lv];
+                if (er != ENT_NONE) {
+                    const uint32_t e = qt.first + er;
+                    const uint64_t off = v.e_off[e]; const uint32_t c = v.e_count[e];
+                    sl.off_lo = (uint32_t)off; sl.offhi_cnt = ((uint32_t)(off >> 32) << 20) | c; sl.bmi = v.e_bitmap[e];
+                    sl.ub = __fmul_rn(qt.idf, v.e_maxcomp[e]);
+                    if (s == 0) { c0 = c; u0 = sl.ub; } else if (s == 1) { c1 = c; u1 = sl.ub; } else if (s == 2) { c2 = c; u2 = sl.ub; } else { c3 = c; u3 = sl.ub; }
+                }
+            }
+            r.t[s] = sl; r.idf[s] = idf;
         }
+        if (nl <= FAST_T) {
+            const uint32_t cs[4] = {c0, c1, c2, c3}; const float us[4] = {u0, u1, u2, u3};
+            uint32_t np = 0, rank[4], crank[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) np += cs[s] ? 1u : 0u;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                uint32_t rk = 0, ck = 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (u == s || !cs[u]) continue;
+                    if (us[u] > us[s] || (us[u] == us[s] && u < s)) rk++;
+                    if (cs[u] > cs[s] || (cs[u] == cs[s] && u < s)) ck++;
+                }
+                rank[s] = cs[s] ? rk : 3u; crank[s] = cs[s] ? ck : 3u;
+            }
+            uint32_t perm = 0, cperm = 0, rankbits = 0, and_drv = 0;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                if (!cs[s]) continue;
+                perm |= (uint32_t)s << (2 * rank[s]); cperm |= (uint32_t)s << (2 * crank[s]); rankbits |= rank[s] << (2 * s);
+                if (crank[s] == np - 1) and_drv = s;            // the shortest list drives an intersection (intersection.rs:258-273)
+            }
+            meta = np | (perm << 3) | (rankbits << 11) | (and_drv << 19) | (cperm << 21) | (nl << 29);
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                float S = 0.f, R = 0.f;
+#pragma unroll
+                for (int s = 0; s < 4; s++) {   // query order
+                    if (!cs[s]) continue;
+                    if (is_and) { if (p == 0) { S = __fadd_rn(S, us[s]); if ((uint32_t)s != and_drv) R = __fadd_rn(R, us[s]); } }
+                    else { if (rank[s] >= (uint32_t)p) S = __fadd_rn(S, us[s]); if (rank[s] > (uint32_t)p) R = __fadd_rn(R, us[s]); }
+                }
+                r.S[p] = S; r.R[p] = R;
+            }
+            uint32_t wsl = is_and ? and_drv : (perm & 3u);
+            weight = cs[wsl];
+        } else {
+            meta = nl << 29;
+#pragma unroll
+            for (int p = 0; p < 4; p++) { r.S[p] = 0.f; r.R[p] = 0.f; }
+        }
+        r.meta = meta;
+        const uint4* src = reinterpret_cast<const uint4*>(&r);
+        uint4* dst = reinterpret_cast<uint4*>(recs + (size_t)q * nlv + j);
+#pragma unroll
+        for (int i = 0; i < 8; i++) dst[i] = src[i];
+        cnt[j] = weight;                                        // (cnt[] by level is dead after the key build above)
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        pl.n_items = n_valid;
+        // items: consecutive records of the bound-sorted list, <= GMAX levels and ~ITEM_W postings of their top lists each.
+        // The first item stays small so that the query's threshold is published early.
+        uint16_t* is = item_start + (size_t)q * (nlv + 1);
+        uint32_t ni = 0, acc = 0, nin = 0;
+        is[0] = 0;
+        for (uint32_t j = 0; j < nv; j++) {
+            const uint32_t lim = ni == 0 ? 2u : GMAX;
+            const uint32_t w = cnt[j] + 64u;
+            if (nin > 0 && (nin >= lim || acc + w > ITEM_W)) { ni++; is[ni] = (uint16_t)j; acc = 0; nin = 0; }
+            acc += w; nin++;
+        }
+        if (nv) { ni++; is[ni] = (uint16_t)nv; }
+        pl.n_items = ni; pl.n_recs = nv;
         plans[q] = pl;
-        atomicMax(&ctr[1], n_valid);
+        atomicMax(&ctr[1], ni);
+        if (pl.n_live > FAST_T) atomicOr(&ctr[4], 1u);
     }
 }
 
@@ -280,7 +381,7 @@ struct TermRegs {   // generic path: lane t holds query term t of the current it
     uint32_t cnt; uint64_t off; uint32_t bmi; float idf; float ub;
 };
 
-// membership + rank probe of doc d in the list described by (cnt, off, bmi); posting word returned in `pw`
+// membership + rank probe of doc d in the list described by (cnt, off, bmi)
 __device__ __forceinline__ bool probe(const LexView& v, uint32_t cnt, uint64_t off, uint32_t bmi, uint32_t d, uint32_t& rank) {
     if (bmi != NONE) {
         // both loads depend only on d: issue them together (one memory latency instead of two)
@@ -295,11 +396,21 @@ __device__ __forceinline__ bool probe(const LexView& v, uint32_t cnt, uint64_t o
     rank = lo;
     return lo < cnt && (__ldg(&a[lo]) & 0xFFFFu) == d;
 }
+// membership only
+__device__ __forceinline__ bool present_in(const LexView& v, uint32_t cnt, uint64_t off, uint32_t bmi, uint32_t d) {
+    if (bmi != NONE) return ((__ldg(&v.bm_words[(size_t)bmi * 1024 + (d >> 6)]) >> (d & 63)) & 1ull) != 0;
+    uint32_t lo = 0, hi = cnt;
+    const uint32_t* a = v.post + off;
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((__ldg(&a[m]) & 0xFFFFu) < d) lo = m + 1; else hi = m; }
+    return lo < cnt && (__ldg(&a[lo]) & 0xFFFFu) == d;
+}
 
 __device__ __forceinline__ float term_score(const LexView& v, float idf, uint64_t pos) {
     // idf * ((tf*(K+1)/(tf+comp)) + SIGMA), SIGMA = 0 (x + 0.0 == x)
-    return __fmul_rn(idf, comp_of(v, __ldg(&v.post[pos]) >> 16, pos));
+    return __fmul_rn(idf, comp_of(v, __ldg(&v.pay[pos])));
 }
+
+__device__ __forceinline__ float bound_of_word(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bool cand, float score, uint32_t doc,
                                                   uint32_t k, int lane, bool& dirty, uint64_t ceil) {
@@ -322,267 +433,254 @@ struct ItemCtx {
     bool scoring, need_count, is_and;
 };
 
-struct FTerm { uint64_t off; uint32_t cnt, bmi; float idf, ub; uint32_t pos, cpos; };   // 32 B, one per (warp, query term)
+struct WarpSm { LvRec recs[GMAX]; uint2 queue[QCAP]; };   // 1024 + 1536 B per warp
 
-// ---- fast path: n <= FAST_T live terms, per-term state in (warp-uniform) registers ----
-__device__ __forceinline__ void process_item_fast(const LexView& v, const QueryPlan* pl, const ItemCtx& c, uint2 ient, int lane,
-                                                  uint64_t& L, uint32_t& thr, bool& dirty, uint64_t& matches,
-                                                  uint64_t& st_visited, uint64_t& st_probes) {
-    uint32_t cnt[FAST_T], bmi[FAST_T]; uint64_t off[FAST_T]; float idf[FAST_T], ub[FAST_T];
-    const uint32_t n = c.n;
+// thresholds derived from the ordered-uint k-th score `thr` (0 = list not full yet): BM25 scores are non-negative, so
+// the per-posting tests are plain float compares against thr_lo = thr_f / INFL (rounded down).
+struct Thr {
+    uint32_t u; float lo;
+    __device__ __forceinline__ void set(uint32_t t) { u = t; lo = t ? __fdiv_rd(unord_f32(t), INFL) : -1.0f; }
+};
+
+// ---- stages 2 + 3 on up to 32 queued survivors (one per lane; lanes may belong to different records / drivers) ----
+template <bool IS_AND>
+__device__ __forceinline__ void process_queued(const LexView& v, const WarpSm& w, uint2 e, bool active, int lane, uint32_t k, uint64_t ceil,
+                                               uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
+    const uint32_t pos = e.x & 0x1FFFFu, ri = (e.x >> 17) & 7u, p = (e.x >> 20) & 3u;
+    const uint32_t d = e.y & 0xFFFFu;
+    const LvRec& rec = w.recs[ri];
+    const uint32_t meta = rec.meta;
+    const uint32_t drv = IS_AND ? meta_anddrv(meta) : meta_perm(meta, p);
+    const float didf = rec.idf[drv];
+    // ---- stage 2: replace the level-wide bound by what the bitmaps say about THIS doc.  One 8-byte load per bitmap-backed
+    // term gives membership: (OR) a doc that is in an earlier-ranked list was already emitted there, and a term the doc is
+    // not in contributes nothing; (AND) a doc missing from any list is dead.  Lists without a bitmap count as "maybe".
+    uint64_t bw[FAST_T];
+    uint32_t bmi[FAST_T], cnts[FAST_T];
 #pragma unroll
-    for (uint32_t t = 0; t < FAST_T; t++) {
-        cnt[t] = 0; bmi[t] = NONE; off[t] = 0; idf[t] = 0.f; ub[t] = 0.f;
-        const uint32_t er = (t < 2 ? (ient.x >> (16 * t)) : (ient.y >> (16 * (t - 2)))) & 0xFFFFu;
-        if (t < n) {
-            const QTerm qt = pl->t[t];
-            idf[t] = qt.idf;
-            if (er != ENT_NONE) {
-                const uint32_t e = qt.first + er;
-                cnt[t] = __ldg(&v.e_count[e]); off[t] = __ldg(&v.e_off[e]); bmi[t] = __ldg(&v.e_bitmap[e]);
-                ub[t] = __fmul_rn(qt.idf, __ldg(&v.e_maxcomp[e]));
-            }
+    for (uint32_t s = 0; s < FAST_T; s++) {
+        cnts[s] = slot_cnt(rec.t[s]); bmi[s] = rec.t[s].bmi;
+        const bool need = active && s != drv && cnts[s] != 0 && bmi[s] != NONE;
+        bw[s] = need ? __ldg(&v.bm_words[(size_t)bmi[s] * 1024 + (d >> 6)]) : 0ull;
+    }
+    float B = didf * bound_of_word(e.y);
+    bool dead = !active;
+#pragma unroll
+    for (uint32_t s = 0; s < FAST_T; s++) {
+        if (s == drv || cnts[s] == 0) continue;
+        const uint32_t rk = meta_rank(meta, s);
+        const float ub = rec.t[s].ub;
+        if (bmi[s] != NONE) {
+            const bool pres = ((bw[s] >> (d & 63)) & 1ull) != 0;
+            if (IS_AND) { if (!pres) dead = true; else B += ub; }
+            else if (pres) { if (rk < p) dead = true; else B += ub; }
+        } else if (IS_AND || rk > p) B += ub;
+    }
+    bool alive = !dead && B >= thr.lo;
+    if (!__any_sync(FULL, alive)) return;
+    // ---- stage 3: exact in-query-order score (add_result.rs:1450-1452) of the survivors ----
+    float score = 0.f;
+    if (alive) {
+        const uint64_t doff = slot_off(rec.t[drv]);
+#pragma unroll
+        for (uint32_t s = 0; s < FAST_T; s++) {
+            if (cnts[s] == 0 || !alive) continue;
+            if (s == drv) { score = __fadd_rn(score, __fmul_rn(didf, comp_of(v, __ldg(&v.pay[doff + pos])))); continue; }
+            const uint64_t soff = slot_off(rec.t[s]);
+            bool pres; uint32_t rank;
+            st_probes++;
+            if (bmi[s] != NONE) {
+                pres = ((bw[s] >> (d & 63)) & 1ull) != 0;
+                if (pres) rank = (uint32_t)__ldg(&v.bm_rank[(size_t)bmi[s] * 1024 + (d >> 6)]) + (uint32_t)__popcll(bw[s] & ((1ull << (d & 63)) - 1ull));
+            } else pres = probe(v, cnts[s], soff, NONE, d, rank);
+            if (pres) {
+                if (!IS_AND && meta_rank(meta, s) < p) alive = false;   // already emitted when that term was the driver
+                else score = __fadd_rn(score, __fmul_rn(rec.idf[s], comp_of(v, __ldg(&v.pay[soff + rank]))));
+            } else if (IS_AND) alive = false;
         }
     }
-#if SSB_LEX_AND_SMEM
-    if (c.is_and) {
-        // ---------------- AND, per-term state in shared memory (EXPERIMENT, default off: written after the round's GPU budget
-        // was spent, never run; same transformation that took the OR path from 4.7 to 3.5 ms) ----------------
-        __shared__ FTerm afts[8][FAST_T];
-        FTerm* at = afts[(threadIdx.x >> 5) & 7];
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) {
-                FTerm f; f.off = off[t]; f.cnt = cnt[t]; f.bmi = bmi[t]; f.idf = idf[t]; f.ub = ub[t]; f.pos = 0; f.cpos = 0;
-                at[t] = f;
-            }
-        }
-        __syncwarp();
-        uint32_t drv = 0, best = at[0].cnt;
-        for (uint32_t t = 1; t < n; t++) { const uint32_t ct = at[t].cnt; if (ct < best) { best = ct; drv = t; } }
-        const uint32_t dcnt = best; const uint64_t doff = at[drv].off; const float didf = at[drv].idf;
-        st_visited += dcnt;
-        for (uint32_t base = 0; base < dcnt; base += 32) {
-            const uint32_t p = base + lane;
-            const bool active = p < dcnt;
-            const uint32_t pd = active ? __ldg(&v.post[doff + p]) : 0u;
-            const uint32_t d = pd & 0xFFFFu;
-            bool ok = active; float score = 0.f;
-            for (uint32_t t = 0; t < n; t++) {               // query order
-                if (t == drv) { if (ok && c.scoring) score = __fadd_rn(score, __fmul_rn(didf, comp_of(v, pd >> 16, doff + p))); continue; }
-                if (!ok) continue;
-                uint32_t rank; st_probes++;
-                const uint64_t toff = at[t].off;
-                if (!probe(v, at[t].cnt, toff, at[t].bmi, d, rank)) { ok = false; continue; }
-                if (c.scoring) score = __fadd_rn(score, term_score(v, at[t].idf, toff + rank));
-            }
-            matches += __popc(__ballot_sync(FULL, ok));
-            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
-        }
-        __syncwarp();
-        return;
+    uint32_t t = thr.u;
+    insert_candidates(L, t, alive && ord_f32(score) >= thr.u, score, rec.docbase | d, k, lane, dirty, ceil);
+    if (t != thr.u) thr.set(t);
+}
+
+// drain full batches of the survivor queue; keeps < 32 entries at the front
+template <bool IS_AND>
+__device__ __forceinline__ void drain_queue(const LexView& v, WarpSm& w, uint32_t& nq_in, bool flush, int lane, uint32_t k, uint64_t ceil,
+                                            uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
+    uint32_t head = 0;
+    while (nq_in - head >= 32u || (flush && nq_in > head)) {
+        const bool act = head + (uint32_t)lane < nq_in;
+        const uint2 e = act ? w.queue[head + lane] : make_uint2(0u, 0u);
+        process_queued<IS_AND>(v, w, e, act, lane, k, ceil, L, thr, dirty, st_probes);
+        head += 32u;
+        if (head > nq_in) head = nq_in;
     }
-#else
-    if (c.is_and) {
-        // ---------------- AND: drive with the shortest list (intersection.rs:258-273) ----------------
-        uint32_t drv = 0, best = cnt[0];
-#pragma unroll
-        for (uint32_t t = 1; t < FAST_T; t++) if (t < n && cnt[t] < best) { best = cnt[t]; drv = t; }
-        uint32_t dcnt = 0; uint64_t doff = 0;
-#pragma unroll
-        for (uint32_t t = 0; t < FAST_T; t++) if (t == drv) { dcnt = cnt[t]; doff = off[t]; }
-        st_visited += dcnt;
-        for (uint32_t base = 0; base < dcnt; base += 32) {
-            const uint32_t p = base + lane;
-            const bool active = p < dcnt;
-            const uint32_t pd = active ? __ldg(&v.post[doff + p]) : 0u;
-            const uint32_t d = pd & 0xFFFFu;
-            bool ok = active; float score = 0.f;
-#pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) {          // query order
-                if (t >= n) continue;
-                if (t == drv) { if (ok && c.scoring) score = __fadd_rn(score, __fmul_rn(idf[t], comp_of(v, pd >> 16, doff + p))); continue; }
-                if (!ok) continue;
-                uint32_t rank; st_probes++;
-                if (!probe(v, cnt[t], off[t], bmi[t], d, rank)) { ok = false; continue; }
-                if (c.scoring) score = __fadd_rn(score, term_score(v, idf[t], off[t] + rank));
-            }
-            matches += __popc(__ballot_sync(FULL, ok));
-            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
-        }
-        return;
-    }
-#endif
-    // ---------------- OR ----------------
-    // Per-term state moves from registers to a per-warp shared-memory record here.  With 6 four-entry register arrays live
-    // across the posting loop and a 48-register budget (5 CTAs/SM), the compiler re-evaluated the "t == drv" select chains
-    // in every chunk iteration: ncu attributed 33 % of the kernel's instructions to the three per-driver setup lines.  Values
-    // are warp-uniform, so every access below is one broadcast LDS with a dynamic index.
-    __shared__ uint2 cbuf[8][64];                             // per-warp survivor queue (posting index, posting word)
-    __shared__ FTerm fts[8][FAST_T];
-    uint2* mybuf = cbuf[(threadIdx.x >> 5) & 7];
-    FTerm* ft = fts[(threadIdx.x >> 5) & 7];
-    {
-        // MAXSCORE order: terms by block bound desc (present first); pos = rank of the term
-        uint32_t pos[FAST_T];
-#pragma unroll
-        for (uint32_t t = 0; t < FAST_T; t++) {
-            uint32_t r = 0;
-#pragma unroll
-            for (uint32_t u = 0; u < FAST_T; u++) {
-                if (u == t || u >= n) continue;
-                const bool before = (cnt[u] > 0 && cnt[t] == 0) || ((cnt[u] > 0) == (cnt[t] > 0) && (ub[u] > ub[t] || (ub[u] == ub[t] && u < t)));
-                if (before) r++;
-            }
-            pos[t] = t < n ? r : 0xFFFFu;
-        }
+    if (head) {
+        const uint32_t rem = nq_in - head;
+        uint2 tmp = make_uint2(0u, 0u);
+        if ((uint32_t)lane < rem) tmp = w.queue[head + lane];
         __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-            for (uint32_t t = 0; t < FAST_T; t++) {
-                FTerm f; f.off = off[t]; f.cnt = cnt[t]; f.bmi = bmi[t]; f.idf = idf[t]; f.ub = ub[t]; f.pos = pos[t]; f.cpos = 0xFFFFu;
-                ft[t] = f;
-            }
-        }
+        if ((uint32_t)lane < rem) w.queue[lane] = tmp;
         __syncwarp();
-    }
-    if (c.scoring) {
-        for (uint32_t p = 0; p < n; p++) {
-            uint32_t drv = 0;
-            for (uint32_t t = 0; t < n; t++) if (ft[t].pos == p) drv = t;
-            const uint32_t dcnt = ft[drv].cnt; const uint64_t doff = ft[drv].off; const float didf = ft[drv].idf;
-            if (dcnt == 0) break;                         // absent terms sort last
-            // a driver is essential while the in-query-order sum of the not-yet-driven bounds can reach theta
-            float S = 0.f;
-            for (uint32_t t = 0; t < n; t++) if (ft[t].pos >= p) S = __fadd_rn(S, ft[t].ub);
-            if (ord_f32(S) < thr) break;
-            st_visited += dcnt;
-            // R = in-query-order sum of the bounds of the later-ranked (not yet driven) terms.  The per-posting filter is
-            // (approx(cd) + R) * (1 + 2e-6) >= theta: cheap (no IEEE divide, no per-term loop) and still a strict upper bound
-            // of the exact in-order score — the inflation covers the approximate reciprocal (<= 2 ulp) and the different
-            // association of <= 4 additions (<= 3 ulp).  Survivors are re-scored exactly below.
-            float R = 0.f;
-            for (uint32_t t = 0; t < n; t++) if (t != drv && ft[t].pos > p) R = __fadd_rn(R, ft[t].ub);
-            const float didf_k = didf * v.k1p;
-            // exact contribution, probes, exact in-order score of one queued survivor per lane
-            auto rescore = [&](uint32_t pp, uint32_t pd, bool alive) {
-                const uint32_t d = pd & 0xFFFFu;
-                const float cd = alive ? __fmul_rn(didf, comp_of(v, pd >> 16, doff + pp)) : 0.f;
-                float score = 0.f;
-                for (uint32_t t = 0; t < n; t++) {           // query order
-                    if (t == drv) { score = __fadd_rn(score, cd); continue; }
-                    const uint32_t tc = ft[t].cnt;
-                    if (!alive || tc == 0) continue;
-                    uint32_t rank; st_probes++;
-                    const uint64_t toff = ft[t].off;
-                    if (probe(v, tc, toff, ft[t].bmi, d, rank)) {
-                        if (ft[t].pos < p) alive = false;     // already emitted when that term was the driver
-                        else score = __fadd_rn(score, term_score(v, ft[t].idf, toff + rank));
-                    }
-                }
-                insert_candidates(L, thr, alive && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
-            };
-            uint32_t nbuf = 0;                            // queued survivors of this warp (warp-uniform, < 32 between chunks)
-            uint32_t pd_next = (uint32_t)lane < dcnt ? __ldg(&v.post[doff + lane]) : 0u;
-            for (uint32_t base = 0; base < dcnt; base += 32u) {
-                // software pipelining: the next chunk's postings are requested before this chunk is processed
-                const uint32_t pd = pd_next;
-                { const uint32_t pn = base + 32u + lane; pd_next = pn < dcnt ? __ldg(&v.post[doff + pn]) : 0u; }
-                const uint32_t pp = base + lane;
-                const bool active = pp < dcnt;
-                const uint32_t d = pd & 0xFFFFu;
-                const uint32_t tf8 = (pd >> 16) & 255u;
-                const float tfb = tf8 == 255u ? 65535.f : (float)tf8;                 // overflowed tf: bound with the u16 maximum
-                const float cdb = didf_k * __fdividef(tfb, tfb + __ldg(&v.cache[pd >> 24]));
-                bool alive = active && ord_f32((cdb + R) * 1.000002f) >= thr;
-                if (!__any_sync(FULL, alive)) continue;
-#if SSB_LEX_PRESENCE
-                // ---- second filter: replace the level-wide bound R by what the bitmaps say about THIS doc.  One 8-byte load per
-                // bitmap-backed term gives membership; a doc that is in an earlier-ranked list was already emitted there, and a term
-                // the doc is not in contributes nothing.  No exact divide, no rank / payload load for postings that die here
-                // (measured before this filter: 0.75 probes per enumerated posting, 0.10 after).  Lists without a bitmap count as
-                // "maybe".
-                {
-                    float B = cdb; bool dead = false;
-                    for (uint32_t t = 0; t < n; t++) {
-                        if (t == drv || ft[t].cnt == 0) continue;
-                        const uint32_t tb = ft[t].bmi, tp = ft[t].pos;
-                        if (tb != NONE) {
-                            const uint64_t w = alive ? __ldg(&v.bm_words[(size_t)tb * 1024 + (d >> 6)]) : 0ull;
-                            if ((w >> (d & 63)) & 1ull) { if (tp < p) dead = true; else B += ft[t].ub; }
-                        } else if (tp > p) B += ft[t].ub;
-                    }
-                    alive = alive && !dead && ord_f32(B * 1.000002f) >= thr;
-                }
-#endif
-                // ---- compaction: the exact re-score is ~10x the cost of the filters and only a few lanes of a chunk survive them
-                // (but most chunks have at least one survivor).  Survivors are queued per warp and re-scored 32 at a time, so the
-                // expensive path runs with full lanes.  Order does not matter: keys are a total order, the top-k is a set.
-                const unsigned am = __ballot_sync(FULL, alive);
-                if (!am) continue;
-                if (alive) mybuf[nbuf + __popc(am & ((1u << lane) - 1u))] = make_uint2(pp, pd);
-                nbuf += __popc(am);
-                __syncwarp();
-                if (nbuf >= 32u) {
-                    const uint2 e = mybuf[lane];
-                    rescore(e.x, e.y, true);
-                    const uint32_t rem = nbuf - 32u;
-                    uint2 tmp = make_uint2(0u, 0u);
-                    if ((uint32_t)lane < rem) tmp = mybuf[32 + lane];
-                    __syncwarp();
-                    if ((uint32_t)lane < rem) mybuf[lane] = tmp;
-                    __syncwarp();
-                    nbuf = rem;
-                }
-            }
-            if (nbuf) {
-                const bool act = (uint32_t)lane < nbuf;
-                const uint2 e = act ? mybuf[lane] : make_uint2(0u, 0u);
-                rescore(e.x, e.y, act);
-                __syncwarp();
-            }
-        }
-    }
-    if (c.need_count) {
-        // exact |union| of this block: sum of counts - duplicates; enumerate all but the longest list, probe longer ones
-        if (lane == 0) {
-            for (uint32_t t = 0; t < n; t++) {
-                uint32_t r = 0;
-                for (uint32_t u = 0; u < n; u++) if (u != t && (ft[u].cnt > ft[t].cnt || (ft[u].cnt == ft[t].cnt && u < t))) r++;
-                ft[t].cpos = r;
-            }
-        }
-        __syncwarp();
-        for (uint32_t p = 0; p < n; p++) {
-            uint32_t dcnt = 0; uint64_t doff = 0;
-            for (uint32_t t = 0; t < n; t++) if (ft[t].cpos == p) { dcnt = ft[t].cnt; doff = ft[t].off; }
-            if (dcnt == 0) break;
-            if (p == 0) { matches += dcnt; continue; }
-            st_visited += dcnt;
-            for (uint32_t base = 0; base < dcnt; base += 32) {
-                const uint32_t pp = base + lane;
-                const bool active = pp < dcnt;
-                const uint32_t d = active ? (__ldg(&v.post[doff + pp]) & 0xFFFFu) : 0u;
-                bool dup = false;
-                for (uint32_t t = 0; t < n; t++) {
-                    const uint32_t tc = ft[t].cnt;
-                    if (ft[t].cpos >= p || tc == 0 || !active || dup) continue;
-                    uint32_t rank; st_probes++;
-                    if (probe(v, tc, ft[t].off, ft[t].bmi, d, rank)) dup = true;
-                }
-                matches += __popc(__ballot_sync(FULL, active && !dup));
-            }
-        }
-        __syncwarp();
+        nq_in = rem;
     }
 }
 
+// stream one list 128 postings per iteration (one 16-byte load per lane) and queue the postings whose bound reaches θ
+template <bool IS_AND>
+__device__ __forceinline__ void stream_driver(const LexView& v, WarpSm& w, uint32_t tag /* ri<<17 | p<<20 */, uint64_t doff, uint32_t dcnt,
+                                              float didf, float R, uint32_t& nq_in, int lane, uint32_t k, uint64_t ceil,
+                                              uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
+    // 32-bit indices relative to the 16-byte aligned start: the list occupies [r0, r1) of the words fetched
+    const uint32_t r0 = (uint32_t)doff & 3u, r1 = r0 + dcnt;
+    const uint32_t n_it = (r1 + 127u) >> 7;
+    const uint4* src = reinterpret_cast<const uint4*>(v.post + (doff - r0)) + lane;
+    uint32_t rel = 4u * lane;                                   // first word of this lane's vector
+    uint4 nxt = rel < r1 ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t it = 0; it < n_it; it++, rel += 128u) {
+        const uint4 cur = nxt;
+        // software pipelining: the next 128 postings are requested before these are filtered
+        src += 32;
+        nxt = rel + 128u < r1 ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
+        const bool a0 = rel      >= r0 && rel      < r1 && fmaf(didf, bound_of_word(cur.x), R) >= thr.lo;
+        const bool a1 = rel + 1u >= r0 && rel + 1u < r1 && fmaf(didf, bound_of_word(cur.y), R) >= thr.lo;
+        const bool a2 = rel + 2u >= r0 && rel + 2u < r1 && fmaf(didf, bound_of_word(cur.z), R) >= thr.lo;
+        const bool a3 = rel + 3u >= r0 && rel + 3u < r1 && fmaf(didf, bound_of_word(cur.w), R) >= thr.lo;
+        if (!__any_sync(FULL, a0 | a1 | a2 | a3)) continue;
+        const uint32_t lt = (1u << lane) - 1u;
+        unsigned m;
+        m = __ballot_sync(FULL, a0); if (a0) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel      - r0) | tag, cur.x); nq_in += __popc(m);
+        m = __ballot_sync(FULL, a1); if (a1) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 1u - r0) | tag, cur.y); nq_in += __popc(m);
+        m = __ballot_sync(FULL, a2); if (a2) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 2u - r0) | tag, cur.z); nq_in += __popc(m);
+        m = __ballot_sync(FULL, a3); if (a3) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 3u - r0) | tag, cur.w); nq_in += __popc(m);
+        __syncwarp();
+        if (nq_in >= 32u) drain_queue<IS_AND>(v, w, nq_in, false, lane, k, ceil, L, thr, dirty, st_probes);
+    }
+}
+
+// enumerate a whole list 128 postings per iteration: f(doc id, valid) is called 4x per lane per iteration (warp-converged)
+template <class F>
+__device__ __forceinline__ void for_each_posting(const LexView& v, uint64_t doff, uint32_t dcnt, int lane, F f) {
+    const uint32_t r0 = (uint32_t)doff & 3u, r1 = r0 + dcnt;
+    const uint4* src = reinterpret_cast<const uint4*>(v.post + (doff - r0)) + lane;
+    for (uint32_t rel = 4u * lane; rel - 4u * lane < r1; rel += 128u, src += 32) {
+        const uint4 cur = rel < r1 ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
+        f(cur.x & 0xFFFFu, rel      >= r0 && rel      < r1);
+        f(cur.y & 0xFFFFu, rel + 1u >= r0 && rel + 1u < r1);
+        f(cur.z & 0xFFFFu, rel + 2u >= r0 && rel + 2u < r1);
+        f(cur.w & 0xFFFFu, rel + 3u >= r0 && rel + 3u < r1);
+    }
+}
+
+// ---- exact match counts of one record (TopkCount / Count) ----
+// OR: |union| = (dense lists: popcount of the OR of their bitmap words, union_count union.rs:807-1164) + for every sparse list the
+// postings that are in no longer list (2 terms: df0 + df1 - |AND|, union.rs:1236-1244).  AND: popcount of the AND of the bitmap
+// words when every list is dense (intersection_bitmap_2, intersection.rs:33-108), else the shortest list probes the others.
+__device__ __forceinline__ uint32_t count_record(const LexView& v, const LvRec& rec, bool is_and, int lane, uint32_t& st_visited,
+                                                 uint32_t& st_probes, uint32_t& st_words) {
+    const uint32_t meta = rec.meta, np = meta_npres(meta);
+    uint32_t acc = 0;
+    if (np == 0) return 0;
+    if (is_and) {
+        const uint32_t drv = meta_anddrv(meta);
+        const uint32_t dcnt = slot_cnt(rec.t[drv]);
+        if (np == 1) return lane == 0 ? dcnt : 0u;
+        if (dcnt >= COUNT_DENSE) {
+            for (uint32_t wi = lane; wi < 1024u; wi += 32u) {
+                uint64_t a = ~0ull;
+                for (uint32_t c = 0; c < np; c++) a &= __ldg(&v.bm_words[(size_t)rec.t[meta_cperm(meta, c)].bmi * 1024 + wi]);
+                acc += (uint32_t)__popcll(a);
+            }
+            st_words += np * 32u;
+            return acc;
+        }
+        st_visited += dcnt;
+        for_each_posting(v, slot_off(rec.t[drv]), dcnt, lane, [&](uint32_t d, bool valid) {
+            bool ok = valid;
+            for (uint32_t c = 0; c < np; c++) {
+                const uint32_t s = meta_cperm(meta, c);
+                if (s == drv || !ok) continue;
+                st_probes++;
+                ok = present_in(v, slot_cnt(rec.t[s]), slot_off(rec.t[s]), rec.t[s].bmi, d);
+            }
+            acc += ok ? 1u : 0u;
+        });
+        return acc;
+    }
+    uint32_t n_dense = 0;
+    for (uint32_t c = 0; c < np; c++) n_dense += slot_cnt(rec.t[meta_cperm(meta, c)]) >= COUNT_DENSE ? 1u : 0u;   // cperm: cnt descending
+    uint32_t first_sparse = n_dense;
+    if (n_dense >= 2) {
+        for (uint32_t wi = lane; wi < 1024u; wi += 32u) {
+            uint64_t a = 0ull;
+            for (uint32_t c = 0; c < n_dense; c++) a |= __ldg(&v.bm_words[(size_t)rec.t[meta_cperm(meta, c)].bmi * 1024 + wi]);
+            acc += (uint32_t)__popcll(a);
+        }
+        st_words += n_dense * 32u;
+    } else {
+        if (lane == 0) acc += slot_cnt(rec.t[meta_cperm(meta, 0)]);     // the longest list counts in full
+        first_sparse = 1;
+    }
+    for (uint32_t c = first_sparse; c < np; c++) {
+        const uint32_t s = meta_cperm(meta, c);
+        const uint32_t dcnt = slot_cnt(rec.t[s]);
+        st_visited += dcnt;
+        for_each_posting(v, slot_off(rec.t[s]), dcnt, lane, [&](uint32_t d, bool valid) {
+            bool fresh = valid;
+            for (uint32_t c2 = 0; c2 < c; c2++) {                          // longer lists
+                if (!fresh) continue;
+                const uint32_t s2 = meta_cperm(meta, c2);
+                st_probes++;
+                if (present_in(v, slot_cnt(rec.t[s2]), slot_off(rec.t[s2]), rec.t[s2].bmi, d)) fresh = false;
+            }
+            acc += fresh ? 1u : 0u;
+        });
+    }
+    return acc;
+}
+
+// ---- record path (n <= FAST_T live terms), scoring of one item ----
+template <bool IS_AND>
+__device__ __forceinline__ void score_records(const LexView& v, WarpSm& w, uint32_t nrec, uint32_t q, uint32_t k, uint64_t ceil,
+                                              const uint64_t* theta, int lane, uint64_t& L, Thr& thr, bool& dirty,
+                                              uint32_t& st_visited, uint32_t& st_probes, uint32_t& st_recs, uint32_t& st_skipped) {
+    uint32_t nq_in = 0;
+    for (uint32_t ri = 0; ri < nrec; ri++) {
+        const LvRec& rec = w.recs[ri];
+        const uint32_t meta = rec.meta;
+        if (ri) { const uint32_t t2 = (uint32_t)(__ldcg(&theta[q]) >> 32); if (t2 > thr.u) thr.set(t2); }   // other warps' progress
+        // block-max: records are sorted by bound, so the first one below θ ends the scoring of this item
+        // (only strictly smaller bounds prune: intersection.rs:2227-2233, single.rs:386-394)
+        if (ord_f32(rec.bound) < thr.u) { st_skipped += nrec - ri; break; }
+        st_recs++;
+        if (IS_AND) {
+            const uint32_t drv = meta_anddrv(meta);
+            const uint32_t dcnt = slot_cnt(rec.t[drv]);
+            st_visited += dcnt;
+            stream_driver<true>(v, w, ri << 17, slot_off(rec.t[drv]), dcnt, rec.idf[drv], rec.R[0], nq_in, lane, k, ceil, L, thr, dirty, st_probes);
+        } else {
+            const uint32_t np = meta_npres(meta);
+            for (uint32_t p = 0; p < np; p++) {
+                // MAXSCORE: a list is essential while the in-query-order sum of the not-yet-driven bounds can reach θ (the role
+                // of union_docid_2/3's "single pass only if max_list_score > heap.min", union.rs:1259-1301, 1371-1412)
+                if (ord_f32(rec.S[p]) < thr.u) break;
+                const uint32_t drv = meta_perm(meta, p);
+                const uint32_t dcnt = slot_cnt(rec.t[drv]);
+                st_visited += dcnt;
+                stream_driver<false>(v, w, (ri << 17) | (p << 20), slot_off(rec.t[drv]), dcnt, rec.idf[drv], rec.R[p], nq_in, lane, k, ceil, L, thr, dirty, st_probes);
+            }
+        }
+    }
+    if (nq_in) drain_queue<IS_AND>(v, w, nq_in, true, lane, k, ceil, L, thr, dirty, st_probes);
+}
+
 // ---- generic path: up to SSB_MAX_QUERY_TERMS live terms, lane t holds term t, values broadcast by shuffles ----
-__device__ __noinline__ void process_item_generic(const LexView& v, const QueryPlan* pl, const ItemCtx& c, int lane,
-                                                  uint64_t& L, uint32_t& thr, bool& dirty, uint64_t& matches,
-                                                  uint64_t& st_visited, uint64_t& st_probes) {
+__device__ __forceinline__ void process_item_generic(const LexView& v, const QueryPlan* pl, const ItemCtx& c, int lane,
+                                                  uint64_t& L, uint32_t& thr, bool& dirty, uint32_t& matches_out,
+                                                  uint32_t& st_visited, uint32_t& st_probes) {
     const uint32_t n = c.n, lv = c.lv;
+    uint32_t matches = 0;
     TermRegs tr; tr.cnt = 0; tr.off = 0; tr.bmi = NONE; tr.idf = 0.f; tr.ub = 0.f;
     if ((uint32_t)lane < n) {
         QTerm qt = pl->t[lane];
@@ -621,6 +719,7 @@ __device__ __noinline__ void process_item_generic(const LexView& v, const QueryP
             matches += __popc(__ballot_sync(FULL, ok));
             if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
         }
+        if (lane == 0) matches_out += matches;
         return;
     }
     if (c.scoring) {
@@ -696,72 +795,165 @@ __device__ __noinline__ void process_item_generic(const LexView& v, const QueryP
             }
         }
     }
+    if (lane == 0) matches_out += matches;
 }
 
 #ifndef SSB_LEX_MINB
-#define SSB_LEX_MINB 5
+#define SSB_LEX_MINB 3
 #endif
-__global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const QueryPlan* __restrict__ plans, const uint64_t* __restrict__ items,
-                                                 const uint2* __restrict__ item_ent, uint32_t nq, uint32_t query_type, uint32_t result_type,
-                                                 uint32_t k, uint32_t* ctr, uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist,
-                                                 LexStats* stats, const uint64_t* __restrict__ ceil_keys) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t max_items = *(volatile uint32_t*)&ctr[1];
-    const uint64_t total = (uint64_t)max_items * nq;
-    uint64_t st_visited = 0, st_probes = 0, st_done = 0, st_skipped = 0;
-    const bool want_topk = result_type != SSB_RESULT_COUNT && k > 0;
-    const bool need_count = result_type != SSB_RESULT_TOPK;
 
-    for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(&ctr[0], 1u);
-        i = __shfl_sync(FULL, i, 0);
-        if ((uint64_t)i >= total) break;
-        const uint32_t j = i / nq, q = i - j * nq;
-        const QueryPlan* pl = &plans[q];
-        if (j >= pl->n_items) continue;
-        const uint64_t item = items[(size_t)q * v.n_levels + j];
-        ItemCtx c;
-        c.ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
-        if (c.ceil == 0) continue;                       // this query's result list is already exhausted
-        c.q = q; c.n = pl->n_live; c.k = k; c.lv = 0xFFFFFFFFu - (uint32_t)item; c.bound_ord = (uint32_t)(item >> 32);
-        uint32_t thr = (uint32_t)(__ldcg(&theta[q]) >> 32);
-        c.scoring = want_topk && c.bound_ord >= thr;
-        c.need_count = need_count; c.is_and = query_type == SSB_QUERY_INTERSECTION;
-        if (!c.scoring && !need_count) { st_skipped++; continue; }
-        st_done++;
-        c.docbase = __ldg(&v.level_ids[c.lv]) << 16;
-        uint64_t L = 0; bool dirty = false; uint64_t matches = 0;
-        if (c.n <= FAST_T) process_item_fast(v, pl, c, item_ent[(size_t)q * v.n_levels + j], lane, L, thr, dirty, matches, st_visited, st_probes);
-        else process_item_generic(v, pl, c, lane, L, thr, dirty, matches, st_visited, st_probes);
-
-        // ---- publish: merge the warp list into the query's global list, raise theta ----
-        if (dirty) {
-            if (lane == 0) { while (atomicCAS(&lock[q], 0, 1) != 0) __nanosleep(40); }
-            __syncwarp();
-            __threadfence();
-            uint64_t G = __ldcg(&glist[(size_t)q * LIST + lane]);
-            uint64_t M = wl_merge(L, G, lane);
-            __stcg(&glist[(size_t)q * LIST + lane], M);
-            uint64_t nth = shfl64(M, (int)k - 1);
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                if (nth > __ldcg(&theta[q])) __stcg(&theta[q], nth);
-                __threadfence();
-                atomicExch(&lock[q], 0);
-            }
-        }
-        if (need_count && lane == 0 && matches) atomicAdd((unsigned long long*)&count[q], (unsigned long long)matches);
-    }
+// claim the next work item: wave order — item i -> (j = i / nq, q = i % nq) = the j-th item of query q, so every query's best
+// levels are scored first and its θ is published before most of its other items start
+__device__ __forceinline__ bool next_item(uint32_t* counter, uint64_t total, uint32_t nq, int lane, uint32_t& j, uint32_t& q) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(counter, 1u);
+    i = __shfl_sync(FULL, i, 0);
+    if ((uint64_t)i >= total) return false;
+    j = i / nq; q = i - j * nq;
+    return true;
+}
+// stage the item's records in shared memory: 128 B per record, one coalesced word per lane
+__device__ __forceinline__ uint32_t stage_item(WarpSm& w, const LvRec* __restrict__ recs, const uint16_t* __restrict__ item_start,
+                                               uint32_t nlv, uint32_t q, uint32_t j, int lane) {
+    const uint16_t* is = item_start + (size_t)q * (nlv + 1);
+    const uint32_t r0 = __ldg(&is[j]), r1 = __ldg(&is[j + 1]);
+    const uint32_t nrec = r1 - r0;
+    __syncwarp();
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(recs + (size_t)q * nlv + r0);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(w.recs);
+    for (uint32_t r = 0; r < nrec; r++) dst[r * 32 + lane] = __ldg(src + r * 32 + lane);
+    __syncwarp();
+    return nrec;
+}
+// merge the warp's list into the query's global list under the per-query lock, raise θ
+__device__ __forceinline__ void publish(uint64_t L, uint32_t q, uint32_t k, int lane, uint64_t* theta, int* lock, uint64_t* glist) {
+    if (lane == 0) { while (atomicCAS(&lock[q], 0, 1) != 0) __nanosleep(40); }
+    __syncwarp();
+    __threadfence();
+    uint64_t G = __ldcg(&glist[(size_t)q * LIST + lane]);
+    uint64_t M = wl_merge(L, G, lane);
+    __stcg(&glist[(size_t)q * LIST + lane], M);
+    uint64_t nth = shfl64(M, (int)k - 1);
+    __threadfence();
+    __syncwarp();
     if (lane == 0) {
-        atomicAdd((unsigned long long*)&stats->postings_visited, (unsigned long long)st_visited);
+        if (nth > __ldcg(&theta[q])) __stcg(&theta[q], nth);
+        __threadfence();
+        atomicExch(&lock[q], 0);
+    }
+}
+
+// ---- scoring, queries with <= 4 live terms (ResultType Topk / TopkCount) ----
+template <bool IS_AND>
+__global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const QueryPlan* __restrict__ plans, const LvRec* __restrict__ recs,
+                                                 const uint16_t* __restrict__ item_start, uint32_t nq, uint32_t k, uint32_t* ctr, uint64_t* theta,
+                                                 int* lock, uint64_t* glist, LexStats* stats, const uint64_t* __restrict__ ceil_keys) {
+    __shared__ __align__(16) WarpSm wsm[8];
+    WarpSm& w = wsm[(threadIdx.x >> 5) & 7];
+    const int lane = threadIdx.x & 31;
+    const uint64_t total = (uint64_t)(*(volatile uint32_t*)&ctr[1]) * nq;
+    uint32_t st_visited = 0, st_probes = 0, st_done = 0, st_skipped = 0, st_recs = 0;
+    uint64_t acc_visited = 0, acc_probes = 0;
+    uint32_t j, q;
+    while (next_item(&ctr[0], total, nq, lane, j, q)) {
+        const QueryPlan* pl = &plans[q];
+        if (j >= __ldg(&pl->n_items) || __ldg(&pl->n_live) > FAST_T) continue;
+        const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
+        if (ceil == 0) continue;                         // this query's result list is already exhausted
+        const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
+        Thr thr; thr.set((uint32_t)(__ldcg(&theta[q]) >> 32));
+        if (ord_f32(w.recs[0].bound) < thr.u) { st_skipped += nrec; continue; }   // whole item below θ
+        uint64_t L = 0; bool dirty = false;
+        st_done++;
+        score_records<IS_AND>(v, w, nrec, q, k, ceil, theta, lane, L, thr, dirty, st_visited, st_probes, st_recs, st_skipped);
+        if (dirty) publish(L, q, k, lane, theta, lock, glist);
+        acc_visited += st_visited; acc_probes += st_probes; st_visited = 0; st_probes = 0;
+    }
+    // per-lane counters (probes) are summed over the warp; warp-uniform ones are taken from lane 0
+    for (int s = 16; s; s >>= 1) acc_probes += __shfl_xor_sync(FULL, acc_probes, s);
+    if (lane == 0) {
+        atomicAdd((unsigned long long*)&stats->postings_visited, (unsigned long long)acc_visited);
+        atomicAdd((unsigned long long*)&stats->probes, (unsigned long long)acc_probes);
         atomicAdd((unsigned long long*)&stats->items_processed, (unsigned long long)st_done);
         atomicAdd((unsigned long long*)&stats->items_skipped, (unsigned long long)st_skipped);
+        atomicAdd((unsigned long long*)&stats->recs_processed, (unsigned long long)st_recs);
+    }
+}
+
+// ---- exact match counts, queries with <= 4 live terms (ResultType Count / TopkCount): independent of θ, own kernel ----
+__global__ void __launch_bounds__(256, 4) lex_count(LexView v, const QueryPlan* __restrict__ plans, const LvRec* __restrict__ recs,
+                                                const uint16_t* __restrict__ item_start, uint32_t nq, uint32_t query_type, uint32_t* ctr,
+                                                uint64_t* count, LexStats* stats) {
+    __shared__ __align__(16) WarpSm wsm[8];
+    WarpSm& w = wsm[(threadIdx.x >> 5) & 7];
+    const int lane = threadIdx.x & 31;
+    const uint64_t total = (uint64_t)(*(volatile uint32_t*)&ctr[1]) * nq;
+    const bool is_and = query_type == SSB_QUERY_INTERSECTION;
+    uint64_t acc_visited = 0, acc_probes = 0, acc_words = 0; uint32_t st_recs = 0;
+    uint32_t j, q;
+    while (next_item(&ctr[2], total, nq, lane, j, q)) {
+        const QueryPlan* pl = &plans[q];
+        if (j >= __ldg(&pl->n_items) || __ldg(&pl->n_live) > FAST_T) continue;
+        const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
+        uint32_t matches = 0, st_visited = 0, st_probes = 0, st_words = 0;
+        for (uint32_t ri = 0; ri < nrec; ri++) matches += count_record(v, w.recs[ri], is_and, lane, st_visited, st_probes, st_words);
+        st_recs += nrec;
+        for (int s = 16; s; s >>= 1) matches += __shfl_xor_sync(FULL, matches, s);
+        if (lane == 0 && matches) atomicAdd((unsigned long long*)&count[q], (unsigned long long)matches);
+        acc_visited += st_visited; acc_probes += st_probes; acc_words += st_words;
+    }
+    for (int s = 16; s; s >>= 1) acc_probes += __shfl_xor_sync(FULL, acc_probes, s);
+    if (lane == 0) {
+        atomicAdd((unsigned long long*)&stats->postings_visited, (unsigned long long)acc_visited);
+        atomicAdd((unsigned long long*)&stats->probes, (unsigned long long)acc_probes);
+        atomicAdd((unsigned long long*)&stats->dense_words, (unsigned long long)acc_words);
+        atomicAdd((unsigned long long*)&stats->recs_processed, (unsigned long long)st_recs);
+    }
+}
+
+// ---- queries with 5..16 live terms: one level per item, per-term state in lanes (scoring and counting) ----
+__global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* __restrict__ plans, const LvRec* __restrict__ recs,
+                                                  const uint16_t* __restrict__ item_start, uint32_t nq, uint32_t query_type, uint32_t result_type,
+                                                  uint32_t k, uint32_t* ctr, uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist,
+                                                  LexStats* stats, const uint64_t* __restrict__ ceil_keys) {
+    if (*(volatile uint32_t*)&ctr[4] == 0) return;       // no query of this batch has more than FAST_T live terms
+    __shared__ __align__(16) WarpSm wsm[8];
+    WarpSm& w = wsm[(threadIdx.x >> 5) & 7];
+    const int lane = threadIdx.x & 31;
+    const uint64_t total = (uint64_t)(*(volatile uint32_t*)&ctr[1]) * nq;
+    const bool want_topk = result_type != SSB_RESULT_COUNT && k > 0;
+    const bool need_count = result_type != SSB_RESULT_TOPK;
+    uint32_t st_visited = 0, st_probes = 0, st_done = 0, st_skipped = 0;
+    uint32_t j, q;
+    while (next_item(&ctr[3], total, nq, lane, j, q)) {
+        const QueryPlan* pl = &plans[q];
+        const uint32_t n_live = __ldg(&pl->n_live);
+        if (j >= __ldg(&pl->n_items) || n_live <= FAST_T) continue;
+        const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
+        if (ceil == 0) continue;
+        const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
+        uint32_t thr = (uint32_t)(__ldcg(&theta[q]) >> 32);
+        uint64_t L = 0; bool dirty = false; uint32_t matches = 0;
+        for (uint32_t ri = 0; ri < nrec; ri++) {
+            ItemCtx c;
+            c.ceil = ceil; c.q = q; c.n = n_live; c.k = k; c.lv = w.recs[ri].lv; c.bound_ord = ord_f32(w.recs[ri].bound);
+            c.scoring = want_topk && c.bound_ord >= thr;
+            c.need_count = need_count; c.is_and = query_type == SSB_QUERY_INTERSECTION; c.docbase = w.recs[ri].docbase;
+            if (!c.scoring && !need_count) { st_skipped++; continue; }
+            st_done++;
+            process_item_generic(v, pl, c, lane, L, thr, dirty, matches, st_visited, st_probes);
+        }
+        if (dirty) publish(L, q, k, lane, theta, lock, glist);
+        if (need_count && lane == 0 && matches) atomicAdd((unsigned long long*)&count[q], (unsigned long long)matches);
     }
     unsigned long long pr = st_probes;
     for (int s = 16; s; s >>= 1) pr += __shfl_xor_sync(FULL, pr, s);
-    if (lane == 0) atomicAdd((unsigned long long*)&stats->probes, pr);
+    if (lane == 0) {
+        atomicAdd((unsigned long long*)&stats->postings_visited, (unsigned long long)st_visited);
+        atomicAdd((unsigned long long*)&stats->probes, pr);
+        atomicAdd((unsigned long long*)&stats->items_processed, (unsigned long long)st_done);
+        atomicAdd((unsigned long long*)&stats->items_skipped, (unsigned long long)st_skipped);
+    }
 }
 
 __global__ void copy_out(const uint64_t* __restrict__ glist, const uint64_t* __restrict__ count, uint32_t nq, uint32_t k,
@@ -774,8 +966,7 @@ __global__ void copy_out(const uint64_t* __restrict__ glist, const uint64_t* __r
 // ================================================================= host side
 LexIndex::~LexIndex() {
     for (auto& l : levels_) { cudaFree(l.d_term_keys); cudaFree(l.d_posting_offsets); }
-    free_committed(); free_workspace();
-    if (d_exc_count_) cudaFree(d_exc_count_);
+    free_committed();
 }
 
 void LexIndex::free_committed() {
@@ -788,11 +979,11 @@ void LexIndex::free_committed() {
     committed_ = false;
 }
 
-void LexIndex::free_workspace() {
-    cudaFree(d_plans_); cudaFree(d_items_); cudaFree(d_item_ent_); cudaFree(d_theta_); cudaFree(d_lock_); cudaFree(d_count_); cudaFree(d_ctr_);
-    cudaFree(d_qoff_); cudaFree(d_qkeys_); cudaFree(d_stats_);
-    d_plans_ = nullptr; d_items_ = nullptr; d_item_ent_ = nullptr; d_theta_ = nullptr; d_lock_ = nullptr; d_count_ = nullptr; d_ctr_ = nullptr;
-    d_qoff_ = nullptr; d_qkeys_ = nullptr; d_stats_ = nullptr; ws_nq_ = ws_terms_ = ws_levels_ = 0;
+void LexWorkspace::release() {
+    cudaFree(plans); cudaFree(recs); cudaFree(item_start); cudaFree(theta); cudaFree(lock); cudaFree(count); cudaFree(ctr);
+    cudaFree(qoff); cudaFree(qkeys); cudaFree(stats);
+    plans = nullptr; recs = nullptr; item_start = nullptr; theta = nullptr; lock = nullptr; count = nullptr; ctr = nullptr;
+    qoff = nullptr; qkeys = nullptr; stats = nullptr; cap_q = cap_terms = cap_levels = 0;
 }
 
 static bool is_device_ptr(const void* p) {
@@ -809,56 +1000,65 @@ static cudaError_t to_device(void* dst, const void* src, size_t n, cudaStream_t 
 
 int32_t LexIndex::add_level(const ssb_level_desc* d) {
     if (!d || d->n_docs == 0 || d->n_docs > 65536) { set_error("add_level: n_docs must be in 1..65536"); return SSB_E_INVALID; }
+    if (d->level_id >= 65536) { set_error("add_level: level_id must be < 65536 (doc id = level_id << 16 | local)"); return SSB_E_INVALID; }
+    if (d->n_terms && (!d->term_keys || !d->posting_offsets)) { set_error("add_level: null term_keys / posting_offsets"); return SSB_E_INVALID; }
     if (levels_.size() >= MAX_LEVELS) { set_error("add_level: more than %u levels per GPU unsupported", MAX_LEVELS); return SSB_E_UNSUPPORTED; }
     for (auto& l : levels_) if (l.level_id == d->level_id) { set_error("add_level: duplicate level_id %u", d->level_id); return SSB_E_INVALID; }
     if (!levels_.empty() && d->level_id < levels_.back().level_id) { set_error("add_level: levels must be added in ascending level_id order"); return SSB_E_INVALID; }
-    uint32_t np = 0;
+    // ---- the whole input contract is checked BEFORE anything is appended to the arenas (a violated contract would make the
+    // scoring kernel read out of bounds or mis-rank silently): offsets start at 0 and ascend, term keys are unique inside
+    // the level, ids ascend strictly inside a term and are < n_docs, tf >= 1
+    DevTmp<uint64_t> t_keys, t_sorted; DevTmp<uint32_t> t_offs, t_bad;
+    SSB_CUDA_TRY(t_keys.alloc(d->n_terms)); SSB_CUDA_TRY(t_offs.alloc((size_t)d->n_terms + 1)); SSB_CUDA_TRY(t_bad.alloc(1));
+    SSB_CUDA_TRY(cudaMemsetAsync(t_bad.p, 0, 4, st_));
+    SSB_CUDA_TRY(to_device(t_keys.p, d->term_keys, (size_t)d->n_terms * 8, st_));
+    if (d->n_terms) SSB_CUDA_TRY(to_device(t_offs.p, d->posting_offsets, ((size_t)d->n_terms + 1) * 4, st_));
+    else SSB_CUDA_TRY(cudaMemsetAsync(t_offs.p, 0, 4, st_));
+    uint32_t np = 0, bad = 0;
     if (d->n_terms) {
-        if (is_device_ptr(d->posting_offsets)) SSB_CUDA_TRY(cudaMemcpy(&np, d->posting_offsets + d->n_terms, 4, cudaMemcpyDeviceToHost));
-        else np = d->posting_offsets[d->n_terms];
-    }
-    LexLevel l{};
-    l.level_id = d->level_id; l.n_docs = d->n_docs; l.n_terms = d->n_terms; l.post_base = n_post_; l.n_post = np;
-    SSB_CUDA_TRY(cudaMalloc(&l.d_term_keys, (size_t)(d->n_terms ? d->n_terms : 1) * 8));
-    SSB_CUDA_TRY(cudaMalloc(&l.d_posting_offsets, ((size_t)d->n_terms + 1) * 4));
-    SSB_CUDA_TRY(to_device(l.d_term_keys, d->term_keys, (size_t)d->n_terms * 8, st_));
-    if (d->n_terms) SSB_CUDA_TRY(to_device(l.d_posting_offsets, d->posting_offsets, ((size_t)d->n_terms + 1) * 4, st_));
-    else SSB_CUDA_TRY(cudaMemsetAsync(l.d_posting_offsets, 0, 4, st_));
-    SSB_TRY(post_.reserve(n_post_ + np + 8, n_post_, st_));
-    // posting word = id16 | tf8<<16 | len8<<24 (needs ids, tfs and the level's length bytes on the device)
-    uint16_t* d_ids = nullptr; uint16_t* d_tfs = nullptr; uint8_t* d_len = nullptr;
-    DevTmp<uint16_t> t_ids, t_tfs; DevTmp<uint8_t> t_len; DevTmp<uint32_t> t_bad;
-    if (np) {
-        if (is_device_ptr(d->doc_ids)) d_ids = const_cast<uint16_t*>(d->doc_ids);
-        else { SSB_CUDA_TRY(t_ids.alloc(np)); d_ids = t_ids.p; SSB_CUDA_TRY(to_device(d_ids, d->doc_ids, (size_t)np * 2, st_)); }
-        if (is_device_ptr(d->tfs)) d_tfs = const_cast<uint16_t*>(d->tfs);
-        else { SSB_CUDA_TRY(t_tfs.alloc(np)); d_tfs = t_tfs.p; SSB_CUDA_TRY(to_device(d_tfs, d->tfs, (size_t)np * 2, st_)); }
-        if (is_device_ptr(d->doc_len_bytes)) d_len = const_cast<uint8_t*>(d->doc_len_bytes);
-        else { SSB_CUDA_TRY(t_len.alloc(d->n_docs)); d_len = t_len.p; SSB_CUDA_TRY(to_device(d_len, d->doc_len_bytes, d->n_docs, st_)); }
-        // input contract: ids ascending and unique inside a term, < n_docs, tf >= 1 (a violated contract would make the
-        // scoring kernel read out of bounds or mis-rank silently)
-        SSB_CUDA_TRY(t_bad.alloc(1)); SSB_CUDA_TRY(cudaMemsetAsync(t_bad.p, 0, 4, st_));
-        validate_level<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, l.d_posting_offsets, d->n_terms, np, d->n_docs, t_bad.p);
+        validate_offsets<<<(d->n_terms + 255) / 256, 256, 0, st_>>>(t_offs.p, d->n_terms, t_bad.p);
         SSB_CUDA_TRY(cudaGetLastError());
-        const uint32_t exc_cap = 1u << 20;
-        if (!d_exc_count_) {
-            SSB_CUDA_TRY(cudaMalloc(&d_exc_count_, 4)); SSB_CUDA_TRY(cudaMemsetAsync(d_exc_count_, 0, 4, st_));
-            SSB_TRY(exc_pos_.reserve(exc_cap, 0, st_)); SSB_TRY(exc_tf_.reserve(exc_cap, 0, st_));
-        }
-        build_payload<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, d_len, post_.p + n_post_, np, n_post_,
-                                                         exc_pos_.p, exc_tf_.p, d_exc_count_, exc_cap);
+        SSB_CUDA_TRY(t_sorted.alloc(d->n_terms));
+        SSB_CUDA_TRY(cudaMemcpyAsync(t_sorted.p, t_keys.p, (size_t)d->n_terms * 8, cudaMemcpyDeviceToDevice, st_));
+        thrust::sort(thrust::cuda::par.on(st_), thrust::device_ptr<uint64_t>(t_sorted.p), thrust::device_ptr<uint64_t>(t_sorted.p + d->n_terms));
+        validate_keys_sorted_unique<<<(d->n_terms + 255) / 256, 256, 0, st_>>>(t_sorted.p, d->n_terms, t_bad.p);
         SSB_CUDA_TRY(cudaGetLastError());
+        SSB_CUDA_TRY(cudaMemcpyAsync(&np, t_offs.p + d->n_terms, 4, cudaMemcpyDeviceToHost, st_));
+        SSB_CUDA_TRY(cudaMemcpyAsync(&bad, t_bad.p, 4, cudaMemcpyDeviceToHost, st_));
+        SSB_CUDA_TRY(cudaStreamSynchronize(st_));
+        if (bad) { set_error("add_level %u: malformed directory (%u violations: posting_offsets must start at 0 and ascend, term_keys must be unique)", d->level_id, bad); return SSB_E_INVALID; }
     }
-    SSB_CUDA_TRY(cudaStreamSynchronize(st_));
+    if (np && (!d->doc_ids || !d->tfs || !d->doc_len_bytes)) { set_error("add_level: null doc_ids / tfs / doc_len_bytes"); return SSB_E_INVALID; }
+    const uint16_t* d_ids = nullptr; const uint16_t* d_tfs = nullptr; const uint8_t* d_len = nullptr;
+    DevTmp<uint16_t> t_ids, t_tfs; DevTmp<uint8_t> t_len;
     if (np) {
-        uint32_t bad = 0;
-        SSB_CUDA_TRY(cudaMemcpy(&bad, t_bad.p, 4, cudaMemcpyDeviceToHost));
+        if (is_device_ptr(d->doc_ids)) d_ids = d->doc_ids;
+        else { SSB_CUDA_TRY(t_ids.alloc(np)); d_ids = t_ids.p; SSB_CUDA_TRY(to_device(t_ids.p, d->doc_ids, (size_t)np * 2, st_)); }
+        if (is_device_ptr(d->tfs)) d_tfs = d->tfs;
+        else { SSB_CUDA_TRY(t_tfs.alloc(np)); d_tfs = t_tfs.p; SSB_CUDA_TRY(to_device(t_tfs.p, d->tfs, (size_t)np * 2, st_)); }
+        if (is_device_ptr(d->doc_len_bytes)) d_len = d->doc_len_bytes;
+        else { SSB_CUDA_TRY(t_len.alloc(d->n_docs)); d_len = t_len.p; SSB_CUDA_TRY(to_device(t_len.p, d->doc_len_bytes, d->n_docs, st_)); }
+        validate_level<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, t_offs.p, d->n_terms, np, d->n_docs, t_bad.p);
+        SSB_CUDA_TRY(cudaGetLastError());
+        SSB_CUDA_TRY(cudaMemcpyAsync(&bad, t_bad.p, 4, cudaMemcpyDeviceToHost, st_));
+        SSB_CUDA_TRY(cudaStreamSynchronize(st_));
         if (bad) {
-            cudaFree(l.d_term_keys); cudaFree(l.d_posting_offsets);
             set_error("add_level %u: malformed postings (%u violations: ids must ascend strictly inside a term and be < n_docs, tf >= 1)", d->level_id, bad);
             return SSB_E_INVALID;
         }
+        // validated: append (n_post_ advances only after the kernels were enqueued without error)
+        SSB_TRY(post_.reserve(n_post_ + np + 160, n_post_, st_));     // +160: the 16-byte vector loads of the stream may run past the end
+        SSB_TRY(pay_.reserve(n_post_ + np + 160, n_post_, st_));
+        build_postings<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, d_len, post_.p + n_post_, pay_.p + n_post_, np);
+        SSB_CUDA_TRY(cudaGetLastError());
+        SSB_CUDA_TRY(cudaStreamSynchronize(st_));
+    } else {
+        SSB_TRY(post_.reserve(n_post_ + 160, n_post_, st_));
+        SSB_TRY(pay_.reserve(n_post_ + 160, n_post_, st_));
     }
+    LexLevel l{};
+    l.level_id = d->level_id; l.n_docs = d->n_docs; l.n_terms = d->n_terms; l.post_base = n_post_; l.n_post = np;
+    l.d_term_keys = t_keys.release(); l.d_posting_offsets = t_offs.release();
     n_post_ += np;
     levels_.push_back(l);
     committed_ = false;
@@ -892,6 +1092,16 @@ static float host_idf(uint64_t n_docs, uint32_t df) {
     return logf(r1);
 }
 
+LexView LexIndex::view() const {
+    LexView v{};
+    v.dict_keys = d_dict_keys_; v.n_terms = n_terms_; v.term_first = d_term_first_; v.term_idf = d_term_idf_; v.term_df = d_term_df_;
+    v.e_level = d_e_level_; v.e_off = d_e_off_; v.e_count = d_e_count_; v.e_maxcomp = d_e_maxcomp_; v.e_bitmap = d_e_bitmap_;
+    v.post = post_.p; v.pay = pay_.p; v.bm_words = d_bm_words_; v.bm_rank = d_bm_rank_; v.level_ids = d_level_ids_;
+    v.n_levels = (uint32_t)levels_.size(); v.cache = d_cache_;
+    v.k1p = 1.2f + 1.0f;
+    return v;
+}
+
 int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     if (n_docs == 0) { set_error("commit: n_docs must be > 0"); return SSB_E_INVALID; }
     free_committed();
@@ -900,6 +1110,7 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     uint64_t total64 = 0;
     for (auto& l : levels_) total64 += l.n_terms;
     if (total64 >= 0xFFFFFFFFull) { set_error("commit: too many (term, level) entries"); return SSB_E_UNSUPPORTED; }
+    if (n_post_ >= (1ull << 44)) { set_error("commit: more than 2^44 postings per GPU unsupported"); return SSB_E_UNSUPPORTED; }
     const uint32_t total = (uint32_t)total64;
     n_entries_ = total;
     auto pol = thrust::cuda::par.on(st_);
@@ -913,14 +1124,14 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     SSB_CUDA_TRY(cudaMalloc(&d_level_ids_, lids.size() * 4));
     SSB_CUDA_TRY(cudaMemcpyAsync(d_level_ids_, lids.data(), lids.size() * 4, cudaMemcpyHostToDevice, st_));
 
-    // exceptions sorted by posting position
-    if (d_exc_count_) {
-        SSB_CUDA_TRY(cudaMemcpyAsync(&n_exc_, d_exc_count_, 4, cudaMemcpyDeviceToHost, st_));
-        SSB_CUDA_TRY(cudaStreamSynchronize(st_));
-        if (n_exc_ > (1u << 20)) { set_error("commit: more than 2^20 postings with tf >= 255"); return SSB_E_UNSUPPORTED; }
-        if (n_exc_) thrust::sort_by_key(pol, thrust::device_ptr<uint64_t>(exc_pos_.p), thrust::device_ptr<uint64_t>(exc_pos_.p + n_exc_),
-                                        thrust::device_ptr<uint32_t>(exc_tf_.p));
+    // per-posting fp16 upper bounds of the score component (needs the cache, i.e. avgdl)
+    if (n_post_) {
+        LexView v{};
+        v.pay = pay_.p; v.cache = d_cache_; v.k1p = 1.2f + 1.0f;
+        fill_bounds<<<(unsigned)((n_post_ + 255) / 256), 256, 0, st_>>>(v, post_.p, n_post_);
+        SSB_CUDA_TRY(cudaGetLastError());
     }
+    if (post_.p) SSB_CUDA_TRY(cudaMemsetAsync(post_.p + n_post_, 0, 160 * 4, st_));   // tail read by the vector loads
 
     size_t alloc_n = total ? total : 1;
     DevTmp<uint64_t> t_keys, t_vals, t_lbase, t_ukeys; DevTmp<const uint32_t*> t_loffs; DevTmp<uint32_t> t_epc, t_df;
@@ -1002,16 +1213,13 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
         SSB_CUDA_TRY(cudaStreamSynchronize(st_));
     }
 
-    committed_ = true;   // view() is usable from here
     if (total) {
-        LexView v{};
-        v.e_off = d_e_off_; v.e_count = d_e_count_; v.post = post_.p; v.cache = d_cache_; v.exc_pos = exc_pos_.p; v.exc_tf = exc_tf_.p;
-        v.n_exc = n_exc_; v.k1p = 1.2f + 1.0f;
+        LexView v = view();
         entry_maxcomp<<<(total + 7) / 8, 256, 0, st_>>>(v, total, d_e_maxcomp_);
         SSB_CUDA_TRY(cudaGetLastError());
     }
     SSB_CUDA_TRY(cudaStreamSynchronize(st_));
-    free_workspace();
+    committed_ = true;
     return SSB_OK;
 }
 
@@ -1038,26 +1246,26 @@ int32_t LexIndex::set_global_df(const uint64_t* keys, const uint32_t* dfs, uint6
     return SSB_OK;
 }
 
-int32_t LexIndex::ensure_workspace(uint32_t nq, uint32_t total_terms) {
+int32_t LexIndex::ensure_workspace(LexWorkspace& ws, uint32_t nq, uint32_t total_terms) const {
     const uint32_t nlv = (uint32_t)levels_.size();
-    if (nq <= ws_nq_ && total_terms <= ws_terms_ && nlv == ws_levels_) return SSB_OK;
-    free_workspace();
+    if (nq <= ws.cap_q && total_terms <= ws.cap_terms && nlv == ws.cap_levels) return SSB_OK;
+    ws.release();
     uint32_t cq = nq > max_batch_ ? nq : max_batch_;
     uint32_t ct = total_terms > cq * 4 ? total_terms : cq * 4;
-    SSB_CUDA_TRY(cudaMalloc(&d_plans_, (size_t)cq * sizeof(QueryPlan)));
-    SSB_CUDA_TRY(cudaMalloc(&d_items_, (size_t)cq * (nlv ? nlv : 1) * 8));
-    SSB_CUDA_TRY(cudaMalloc(&d_item_ent_, (size_t)cq * (nlv ? nlv : 1) * sizeof(uint2)));
-    SSB_CUDA_TRY(cudaMalloc(&d_theta_, (size_t)cq * 8)); SSB_CUDA_TRY(cudaMalloc(&d_lock_, (size_t)cq * 4));
-    SSB_CUDA_TRY(cudaMalloc(&d_count_, (size_t)cq * 8)); SSB_CUDA_TRY(cudaMalloc(&d_ctr_, 16));
-    SSB_CUDA_TRY(cudaMalloc(&d_qoff_, ((size_t)cq + 1) * 4)); SSB_CUDA_TRY(cudaMalloc(&d_qkeys_, (size_t)ct * 8));
-    SSB_CUDA_TRY(cudaMalloc(&d_stats_, sizeof(LexStats)));
-    SSB_CUDA_TRY(cudaMemsetAsync(d_stats_, 0, sizeof(LexStats), st_));
-    ws_nq_ = cq; ws_terms_ = ct; ws_levels_ = nlv;
+    const size_t nl1 = nlv ? nlv : 1;
+    SSB_CUDA_TRY(cudaMalloc(&ws.plans, (size_t)cq * sizeof(QueryPlan)));
+    SSB_CUDA_TRY(cudaMalloc(&ws.recs, (size_t)cq * nl1 * sizeof(LvRec)));
+    SSB_CUDA_TRY(cudaMalloc(&ws.item_start, (size_t)cq * (nl1 + 1) * sizeof(uint16_t)));
+    SSB_CUDA_TRY(cudaMalloc(&ws.theta, (size_t)cq * 8)); SSB_CUDA_TRY(cudaMalloc(&ws.lock, (size_t)cq * 4));
+    SSB_CUDA_TRY(cudaMalloc(&ws.count, (size_t)cq * 8)); SSB_CUDA_TRY(cudaMalloc(&ws.ctr, 32));
+    SSB_CUDA_TRY(cudaMalloc(&ws.qoff, ((size_t)cq + 1) * 4)); SSB_CUDA_TRY(cudaMalloc(&ws.qkeys, (size_t)ct * 8));
+    SSB_CUDA_TRY(cudaMalloc(&ws.stats, sizeof(LexStats)));
+    ws.cap_q = cq; ws.cap_terms = ct; ws.cap_levels = nlv;
     return SSB_OK;
 }
 
-int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t result_type, uint64_t* keys_out_dev,
-                              uint64_t* count_dev, uint64_t* launches, const uint64_t* ceil_dev) {
+int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_batch* q, uint32_t k, uint32_t result_type,
+                              uint64_t* keys_out_dev, uint64_t* count_dev, uint64_t* launches, const uint64_t* ceil_dev) const {
     if (!committed_) { set_error("search before ssb_lexical_commit"); return SSB_E_STATE; }
     if (!q || (q->n_queries && (!q->term_offsets || !keys_out_dev))) { set_error("search_lexical: null argument"); return SSB_E_INVALID; }
     if (k > SSB_K_MAX) { set_error("k=%u exceeds SSB_K_MAX=%u", k, SSB_K_MAX); return SSB_E_UNSUPPORTED; }
@@ -1076,43 +1284,53 @@ int32_t LexIndex::search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t resul
                 return SSB_E_UNSUPPORTED;
             }
     }
+    if (total_terms && !q->term_keys) { set_error("search_lexical: null term_keys"); return SSB_E_INVALID; }
     if ((uint64_t)nq * (levels_.size() ? levels_.size() : 1) >= 0xFFFFFFFFull) { set_error("batch too large: n_queries * n_levels must be < 2^32"); return SSB_E_UNSUPPORTED; }
-    SSB_TRY(ensure_workspace(nq, total_terms));
-    SSB_CUDA_TRY(to_device(d_qoff_, q->term_offsets, ((size_t)nq + 1) * 4, st_));
-    SSB_CUDA_TRY(to_device(d_qkeys_, q->term_keys, (size_t)total_terms * 8, st_));
-    SSB_CUDA_TRY(cudaMemsetAsync(d_ctr_, 0, 16, st_));
-    SSB_CUDA_TRY(cudaMemsetAsync(d_stats_, 0, sizeof(LexStats), st_));
+    SSB_TRY(ensure_workspace(ws, nq, total_terms));
+    SSB_CUDA_TRY(to_device(ws.qoff, q->term_offsets, ((size_t)nq + 1) * 4, st));
+    SSB_CUDA_TRY(to_device(ws.qkeys, q->term_keys, (size_t)total_terms * 8, st));
+    SSB_CUDA_TRY(cudaMemsetAsync(ws.ctr, 0, 32, st));
+    SSB_CUDA_TRY(cudaMemsetAsync(ws.stats, 0, sizeof(LexStats), st));
 
-    LexView v{};
-    v.dict_keys = d_dict_keys_; v.n_terms = n_terms_; v.term_first = d_term_first_; v.term_idf = d_term_idf_; v.term_df = d_term_df_;
-    v.e_level = d_e_level_; v.e_off = d_e_off_; v.e_count = d_e_count_; v.e_maxcomp = d_e_maxcomp_; v.e_bitmap = d_e_bitmap_;
-    v.post = post_.p; v.bm_words = d_bm_words_; v.bm_rank = d_bm_rank_; v.level_ids = d_level_ids_;
-    v.n_levels = (uint32_t)levels_.size(); v.cache = d_cache_; v.exc_pos = exc_pos_.p; v.exc_tf = exc_tf_.p; v.n_exc = n_exc_;
-    v.k1p = 1.2f + 1.0f;
-
+    const LexView v = view();
     uint32_t n_pow2 = 1; while (n_pow2 < v.n_levels) n_pow2 <<= 1;
     if (n_pow2 < 2) n_pow2 = 2;
     size_t plan_smem = (size_t)v.n_levels * (8 + 2 * FAST_T) + 16 + (size_t)n_pow2 * 8;
-    // glist lives in keys_out_dev's shape: use a private list buffer = d_items_-adjacent? keep separate: reuse keys_out_dev
-    // directly as the global list (32 u64 per query), then mask entries >= k in copy_out.
+    // keys_out_dev doubles as the per-query global list (32 u64 per query); copy_out masks the entries >= k afterwards
     uint64_t* glist = keys_out_dev;
     if (plan_smem > 48 * 1024) SSB_CUDA_TRY(cudaFuncSetAttribute(lex_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
-    lex_plan<<<nq, 128, plan_smem, st_>>>(v, d_qoff_, d_qkeys_, q->query_type, d_plans_, d_items_, (uint2*)d_item_ent_, d_ctr_, d_theta_, d_lock_, d_count_, glist, n_pow2);
+    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2);
     SSB_CUDA_TRY(cudaGetLastError());
-    int grid = n_sms_ * SSB_LEX_MINB;
-    if (ev0_) cudaEventRecord(ev0_, st_);
-    lex_score<<<grid, 256, 0, st_>>>(v, d_plans_, d_items_, (const uint2*)d_item_ent_, nq, q->query_type, result_type, k ? k : 1, d_ctr_, d_theta_, d_lock_, d_count_, glist, d_stats_, ceil_dev);
-    if (ev1_) cudaEventRecord(ev1_, st_);
+    const bool is_and = q->query_type == SSB_QUERY_INTERSECTION;
+    const bool want_topk = result_type != SSB_RESULT_COUNT && k > 0;
+    const bool need_count = result_type != SSB_RESULT_TOPK;
+    const uint32_t kk = k ? k : 1;
+    if (ws.ev0) cudaEventRecord(ws.ev0, st);
+    if (want_topk) {
+        const int grid = n_sms_ * SSB_LEX_MINB;
+        if (is_and) lex_score<true><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev);
+        else lex_score<false><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev);
+        SSB_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
+    if (need_count) {
+        lex_count<<<n_sms_ * 4, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, q->query_type, ws.ctr, ws.count, ws.stats);
+        SSB_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
+    // queries with 5..16 live terms (the kernel returns at once when the batch has none)
+    lex_generic<<<n_sms_ * 2, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, q->query_type, result_type, kk, ws.ctr, ws.theta, ws.lock, ws.count, glist, ws.stats, ceil_dev);
     SSB_CUDA_TRY(cudaGetLastError());
-    copy_out<<<(nq * LIST + 255) / 256, 256, 0, st_>>>(glist, d_count_, nq, result_type == SSB_RESULT_COUNT ? 0 : k, keys_out_dev, count_dev);
+    if (ws.ev1) cudaEventRecord(ws.ev1, st);
+    copy_out<<<(nq * LIST + 255) / 256, 256, 0, st>>>(glist, ws.count, nq, result_type == SSB_RESULT_COUNT ? 0 : k, keys_out_dev, count_dev);
     SSB_CUDA_TRY(cudaGetLastError());
-    if (launches) *launches += 3;
+    if (launches) *launches += 3;   // plan + generic + copy_out
     return SSB_OK;
 }
 
-LexStats LexIndex::last_stats() {
+LexStats LexIndex::read_stats(const LexWorkspace& ws, cudaStream_t st) {
     LexStats s{};
-    if (d_stats_) { cudaMemcpyAsync(&s, d_stats_, sizeof(s), cudaMemcpyDeviceToHost, st_); cudaStreamSynchronize(st_); }
+    if (ws.stats) { cudaMemcpyAsync(&s, ws.stats, sizeof(s), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }
     return s;
 }
 

@@ -13,6 +13,9 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;   // elements
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     int32_t reserve(size_t n, size_t used, cudaStream_t st) {
@@ -22,17 +25,17 @@ struct DevBuf {
         T* q = nullptr;
         cudaError_t e = cudaMalloc(&q, nc * sizeof(T));
         if (e != cudaSuccess) {
-            // fall back to the exact size
-            nc = n;
+            cudaGetLastError();
+            nc = n;   // fall back to the exact size
             e = cudaMalloc(&q, nc * sizeof(T));
-            if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", nc * sizeof(T), cudaGetErrorString(e)); return SSB_E_NOMEM; }
+            if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu bytes) failed: %s", nc * sizeof(T), cudaGetErrorString(e)); return SSB_E_NOMEM; }
         }
         if (used && p) {
             e = cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { cudaFree(q); set_error("DevBuf grow copy failed: %s", cudaGetErrorString(e)); return SSB_E_CUDA; }
         }
-        if (p) cudaFree(p);
+        if (p) { cudaStreamSynchronize(st); cudaFree(p); }
         p = q; cap = nc;
         return SSB_OK;
     }
@@ -47,6 +50,7 @@ struct DevTmp {
     DevTmp& operator=(const DevTmp&) = delete;
     ~DevTmp() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+    T* release() { T* q = p; p = nullptr; return q; }
 };
 
 struct LexLevel {
@@ -68,20 +72,57 @@ struct LexView {
     const uint32_t* e_count;
     const float* e_maxcomp;       // block-max basis: max tf*(K+1)/(tf+cache[len]) over the list
     const uint32_t* e_bitmap;     // index into bm_* or 0xFFFFFFFF
-    const uint32_t* post;         // arena: id16 | tf8<<16 | len8<<24, one word per posting
+    const uint32_t* post;         // stream arena: id16 | bound16<<16 (fp16 bits of the posting's score component, rounded UP)
+    const uint32_t* pay;          // payload arena, same index: tf16 | doclen_byte<<16 (read for exact scores only)
     const uint64_t* bm_words;     // [n_bitmaps][1024]
     const uint16_t* bm_rank;      // [n_bitmaps][1024] postings before word w
     const uint32_t* level_ids;    // [n_levels]
     uint32_t n_levels;
     const float* cache;           // [256] bm25_component_cache
-    const uint64_t* exc_pos; const uint32_t* exc_tf; uint32_t n_exc;  // tf >= 255 exceptions, sorted by pos
     float k1p;                    // K + 1
 };
 
 struct QTerm { uint32_t first, n; float idf; uint32_t df; };
-struct QueryPlan { QTerm t[SSB_MAX_QUERY_TERMS]; uint32_t n_live, n_items, flags, pad; };
+struct QueryPlan { QTerm t[SSB_MAX_QUERY_TERMS]; uint32_t n_live, n_items, n_recs, pad; };
 
-struct LexStats { uint64_t postings_visited, probes, items_processed, items_skipped; };
+// One (query, level) record, built by lex_plan for queries with <= 4 live terms; 128 bytes = one cache line.
+// Slots are in QUERY order (scores are summed in query order, add_result.rs:1450-1452); cnt == 0 marks a term
+// that has no postings in this level.
+struct LvSlot { uint32_t off_lo; uint32_t offhi_cnt /* (off >> 32) << 20 | cnt */; uint32_t bmi; float ub; };
+struct LvRec {
+    uint32_t docbase;   // level_id << 16
+    uint32_t meta;      // see REC_* below
+    float bound;        // in-query-order sum of the present terms' block-max contributions
+    uint32_t lv;        // local level index (generic path: directory lookups)
+    LvSlot t[4];
+    float S[4];         // OR: S[p] = in-order sum of ub over slots with MAXSCORE rank >= p.      AND: S[0] = bound
+    float R[4];         // OR: R[p] = in-order sum of ub over slots with MAXSCORE rank >  p.      AND: R[0] = sum over slots != driver
+    float idf[4];
+};
+static_assert(sizeof(LvRec) == 128, "LvRec must be one 128-byte line");
+// meta bit fields
+//   [0:3)   n_pres   number of present slots
+//   [3:11)  perm     MAXSCORE order: 2 bits per rank p -> slot        (ub desc, slot asc; present slots only)
+//   [11:19) rank     2 bits per slot -> MAXSCORE rank
+//   [19:21) and_drv  AND: slot of the shortest list
+//   [21:29) cperm    count order: 2 bits per count-rank -> slot      (cnt desc, slot asc; present slots only)
+//   [29:32) n_live   live terms of the query (== n_pres for AND records)
+
+struct LexStats { uint64_t postings_visited, probes, items_processed, items_skipped, recs_processed, dense_words; };
+
+// Per-call scratch of one search context (api.cu keeps a pool of them: concurrent searches on one index do not share any).
+struct LexWorkspace {
+    uint32_t cap_q = 0, cap_terms = 0, cap_levels = 0;
+    QueryPlan* plans = nullptr; uint64_t* items = nullptr; LvRec* recs = nullptr; uint16_t* item_start = nullptr;
+    uint64_t* theta = nullptr; int* lock = nullptr; uint64_t* count = nullptr; uint32_t* ctr = nullptr; /* [0] score / [2] count / [3] generic work counters, [1] max_items, [4] any query with > 4 live terms */
+    uint32_t* qoff = nullptr; uint64_t* qkeys = nullptr; LexStats* stats = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // recorded around lex_score when set
+    void release();
+    ~LexWorkspace() { release(); }
+    LexWorkspace() = default;
+    LexWorkspace(const LexWorkspace&) = delete;
+    LexWorkspace& operator=(const LexWorkspace&) = delete;
+};
 
 class LexIndex {
 public:
@@ -92,27 +133,26 @@ public:
     int32_t dict_size(uint64_t* n) const { *n = n_terms_; return SSB_OK; }
     int32_t dict_export(uint64_t* keys, uint32_t* dfs, uint64_t cap) const;
     int32_t set_global_df(const uint64_t* keys, const uint32_t* dfs, uint64_t n);
-    // keys_out_dev: [n_queries][32]; count_dev: [n_queries] or null. Asynchronous on the stream.
+    // keys_out_dev: [n_queries][32]; count_dev: [n_queries] or null.  Asynchronous on `st`; thread-safe for concurrent
+    // calls with distinct workspaces (the committed index is immutable).
     // ceil_dev: optional [n_queries] exclusive key ceilings (paging: only hits ranked after that key; 0 = none left)
-    int32_t search_keys(const ssb_lex_batch* q, uint32_t k, uint32_t result_type, uint64_t* keys_out_dev,
-                        uint64_t* count_dev, uint64_t* launches, const uint64_t* ceil_dev = nullptr);
+    int32_t search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_batch* q, uint32_t k, uint32_t result_type,
+                        uint64_t* keys_out_dev, uint64_t* count_dev, uint64_t* launches, const uint64_t* ceil_dev = nullptr) const;
     bool committed() const { return committed_; }
-    void set_stream(cudaStream_t st) { st_ = st; }
-    void set_events(cudaEvent_t a, cudaEvent_t b) { ev0_ = a; ev1_ = b; }
-    LexStats last_stats();
+    void set_stream(cudaStream_t st) { st_ = st; }   // load-time stream (add_level / commit)
+    static LexStats read_stats(const LexWorkspace& ws, cudaStream_t st);
     uint64_t n_postings() const { return n_post_; }
+    uint32_t n_levels() const { return (uint32_t)levels_.size(); }
 
 private:
-    int32_t ensure_workspace(uint32_t nq, uint32_t total_terms);
+    int32_t ensure_workspace(LexWorkspace& ws, uint32_t nq, uint32_t total_terms) const;
     cudaStream_t st_;
-    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int n_sms_;
     uint32_t max_batch_;
     bool committed_ = false;
     std::vector<LexLevel> levels_;
-    DevBuf<uint32_t> post_;
+    DevBuf<uint32_t> post_, pay_;
     uint64_t n_post_ = 0;
-    DevBuf<uint64_t> exc_pos_; DevBuf<uint32_t> exc_tf_; uint32_t* d_exc_count_ = nullptr; uint32_t n_exc_ = 0;
     // committed structures
     uint64_t n_docs_ = 0, len_sum_ = 0;
     uint32_t n_terms_ = 0, n_entries_ = 0, n_bitmaps_ = 0;
@@ -122,12 +162,7 @@ private:
     uint32_t* d_level_ids_ = nullptr; float* d_cache_ = nullptr;
     std::vector<uint64_t> h_dict_keys_; std::vector<uint32_t> h_term_df_;
     void free_committed();
-    // workspace
-    uint32_t ws_nq_ = 0, ws_terms_ = 0, ws_levels_ = 0;
-    QueryPlan* d_plans_ = nullptr; uint64_t* d_items_ = nullptr; void* d_item_ent_ = nullptr; uint64_t* d_theta_ = nullptr; int* d_lock_ = nullptr;
-    uint64_t* d_count_ = nullptr; uint32_t* d_ctr_ = nullptr; /* [0]=work counter [1]=max_items */
-    uint32_t* d_qoff_ = nullptr; uint64_t* d_qkeys_ = nullptr; LexStats* d_stats_ = nullptr;
-    void free_workspace();
+    LexView view() const;
 };
 
 }  // namespace ssb

@@ -1,16 +1,24 @@
 #!/bin/bash
-# GPU call 1 (round 2): full gpu test-suite incl. the new C3/C4 full-size identity tests on the round-1 kernels,
-# plus the A/B of the never-run SSB_FFMA_GROUPMAX switch.
+# GPU call (round 2): new BM25 engine (records + multi-level items + vectorised stream) — memcheck on small shapes first,
+# then the full gpu suite incl. the C3/C4 full-size identity tests, then a bm25-only bench.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/c1_gpu.txt 2>&1
 free -g > gpurun_out/c1_host.txt; nproc >> gpurun_out/c1_host.txt
-timeout 1500 python -m pytest tests -m gpu -q -x --durations=15 > gpurun_out/c1_pytest.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/c1_pytest.log
-tail -5 gpurun_out/c1_pytest.log
-# FFMA group-max seeding A/B: parity tests + batch sweep with the variant library
-SSB_LIB=$PWD/seekstorm_b200/libseekstorm_b200_gm.so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_abi.py -m gpu -q -x -k "vector_parity_small or vector_doc_ids or vector_paging" > gpurun_out/c1_gm_pytest.log 2>&1
-echo "gm pytest rc=$?" >> gpurun_out/c1_gm_pytest.log
-tail -3 gpurun_out/c1_gm_pytest.log
-timeout 300 python bench.py --sections "" --vector-kernel ffma --cpu-seconds 0 --batch 16 --steps 20 > gpurun_out/c1_ffma_base.json 2> gpurun_out/c1_ffma_base.err
-SSB_LIB=$PWD/seekstorm_b200/libseekstorm_b200_gm.so timeout 300 python bench.py --sections "" --vector-kernel ffma --cpu-seconds 0 --batch 16 --steps 20 > gpurun_out/c1_ffma_gm.json 2> gpurun_out/c1_ffma_gm.err
-echo done
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "lexical_hand_corpus or lexical_reference_fixture or device_pointers" > gpurun_out/c1_memcheck_lex.log 2>&1
+echo "memcheck rc=$?" | tee -a gpurun_out/c1_memcheck_lex.log
+tail -4 gpurun_out/c1_memcheck_lex.log
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_abi.py -m gpu -q -x --durations=10 > gpurun_out/c1_pytest_small.log 2>&1
+echo "pytest small rc=$?" | tee -a gpurun_out/c1_pytest_small.log
+tail -15 gpurun_out/c1_pytest_small.log
+timeout 1500 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_multi.py -m gpu -q -x --durations=10 > gpurun_out/c1_pytest_full.log 2>&1
+echo "pytest full rc=$?" | tee -a gpurun_out/c1_pytest_full.log
+tail -15 gpurun_out/c1_pytest_full.log
+timeout 600 python bench.py --sections bm25 --rows 65536 --cpu-seconds 0 --steps 10 > gpurun_out/c1_bench_bm25.json 2> gpurun_out/c1_bench_bm25.err
+echo "bench rc=$?"
+python - <<'PY'
+import json
+try:
+    d=json.load(open('gpurun_out/c1_bench_bm25.json'))
+    b=d['bm25']; print('bm25', b.get('value'), b.get('e2e'), b.get('variants'), b.get('roofline'))
+except Exception as e: print('bench parse', e)
+PY
