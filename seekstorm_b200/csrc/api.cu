@@ -103,6 +103,7 @@ struct ssb_index {
     bool quant_i8 = false;            // Cosine + ScalarQuantizationI8: int8 corpus, exact int32 dot products
     bool dup_docs = false;            // some doc id occurs on more than one vector row (multi-chunk documents): results are de-duplicated
     DevBuf<float> rows;
+    DevBuf<uint16_t> rows_hi, rows_lo;   // bf16 planes of `rows` (hi = bf16_rn(x), lo = bf16_rn(x - hi)): what the tcgen05 bf16 scan streams
     DevBuf<int8_t> rows_i8;
     DevBuf<uint32_t> doc_ids;
     uint64_t n_rows = 0;
@@ -190,6 +191,12 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
             // the query is normalised and quantised exactly like the corpus (search.rs:1464-1475, vector_similarity.rs:1226-1232)
             SSB_TRY(vec::launch_quantize_rows_i8((const float*)qsrc, ix->dims, nq, nq_pad, ix->dims, c.q_i8.p, ix->dpad8, st));
         }
+    } else if (use_tc && tc_bf16) {
+        // one launch: pad + normalise + bf16 hi/lo split (the scan reads only the split parts)
+        SSB_TRY(c.qhi.reserve((size_t)nq_pad * ix->dpad, 0, st));
+        SSB_TRY(c.qlo.reserve((size_t)nq_pad * ix->dpad, 0, st));
+        SSB_TRY(vec::launch_prep_split_queries_bf16((const float*)qsrc, nq, ix->dims, ix->dims, c.qhi.p, c.qlo.p, nq_pad, ix->dpad,
+                                                    ix->cfg.vector_similarity == SSB_SIM_COSINE, st));
     } else
     SSB_TRY(vec::launch_prep_queries((const float*)qsrc, nq, ix->dims, ix->dims, c.qpad.p, nq_pad, ix->dpad,
                                      ix->cfg.vector_similarity == SSB_SIM_COSINE, st));
@@ -198,7 +205,7 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     size_t sb = use_tc ? vec::scan_tc_scratch_bytes(ix->n_sms, nq_pad) : vec::scan_scratch_bytes(ix->n_sms, nq_pad);
     SSB_TRY(c.scratch.reserve(sb / 8 + (size_t)nq_pad * LIST + (nq_pad + 1) / 2, 0, st));
     vec::ScanArgs a{};
-    a.rows = ix->rows.p; a.doc_ids = ix->doc_ids.p; a.n_rows = ix->n_rows; a.dpad = ix->dpad; a.queries_padded = c.qpad.p;
+    a.rows = ix->rows.p; a.rows_hi = ix->rows_hi.p; a.rows_lo = ix->rows_lo.p; a.doc_ids = ix->doc_ids.p; a.n_rows = ix->n_rows; a.dpad = ix->dpad; a.queries_padded = c.qpad.p;
     a.nq_pad = nq_pad; a.nq_valid = nq; a.k = k; a.similarity = ix->cfg.vector_similarity; a.n_sms = ix->n_sms;
     a.scratch = c.scratch.p; a.scratch_bytes = sb;
     uint64_t* merged = c.scratch.p + sb / 8;   // [nq_pad][32]
@@ -380,7 +387,7 @@ int32_t ssb_destroy(ssb_index* ix) {
         cudaStreamSynchronize(ix->load_st);
         ix->pool.clear();                                  // ~SearchCtx synchronises its stream
         delete ix->lex; ix->lex = nullptr;
-        ix->rows.release(); ix->rows_i8.release(); ix->doc_ids.release();
+        ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->doc_ids.release();
         cudaStreamDestroy(ix->load_st);
     }
     delete ix;
@@ -452,6 +459,13 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
         float* dst = ix->rows.p + ix->n_rows * ix->dpad;
         SSB_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ix->dpad * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, st));
         SSB_TRY(vec::launch_normalize_rows(dst, n, dims, ix->dpad, ix->cfg.vector_similarity == SSB_SIM_COSINE, st));
+        if (ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN) {
+            // the tensor-core scan reads the corpus as two bf16 planes (same 4 bytes per element as the f32 rows, which stay for
+            // the FP32 scan): split once here instead of per stage in shared memory
+            SSB_TRY(ix->rows_hi.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, st));
+            SSB_TRY(ix->rows_lo.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, st));
+            SSB_TRY(vec::launch_split_rows_bf16(dst, ix->rows_hi.p + ix->n_rows * ix->dpad, ix->rows_lo.p + ix->n_rows * ix->dpad, (size_t)n * ix->dpad, st));
+        }
     }
     DevTmp<uint16_t> tmp;
     const uint16_t* lid = local_ids;

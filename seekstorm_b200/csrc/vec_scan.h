@@ -10,6 +10,7 @@ constexpr int VEC_QT = 16;      // queries per corpus pass of the FFMA kernel
 
 struct ScanArgs {
     const float* rows;            // [n_rows][dpad]
+    const void* rows_hi = nullptr; const void* rows_lo = nullptr;   // bf16 planes [n_rows][dpad] of the same rows (tcgen05 bf16 scan)
     const uint32_t* doc_ids;      // [n_rows] or nullptr
     uint64_t n_rows;
     uint32_t dpad;                // multiple of 32
@@ -50,6 +51,11 @@ int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);
 int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128*/, int prec /*0: 3xTF32, 1: 3xBF16, 2: int8 (exact)*/, cudaStream_t st);
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad);
+// fused query preparation of the bf16 tensor-core scan: pad + (Cosine) normalise + hi/lo split in one launch
+int32_t launch_prep_split_queries_bf16(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, void* hi, void* lo, uint32_t nq_pad,
+                                       uint32_t dpad, int normalize, cudaStream_t st);
+// load time: f32 rows (already normalised) -> bf16 hi / lo planes
+int32_t launch_split_rows_bf16(const float* rows, void* hi, void* lo, size_t n_elems, cudaStream_t st);
 // lists laid out [group][n_lists][qt][32] -> out [nq][32]
 // thr[q] = ordered-uint score of the k-th entry of keys[q][32] (0 if the list is shorter)
 void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_t* thr, cudaStream_t st);

@@ -15,14 +15,16 @@
 //   PREC_I8   : kind::i8 over an int8 corpus (Cosine + ScalarQuantizationI8, quantised at load time): ONE exact product, s32
 //               accumulators; the TMA'd tile is the MMA operand (no splitters), the 128-query block stays resident in smem
 //               (template BRES) and 12 warps run the epilogue.  See DESIGN.md §3.2b.
-// The query parts are prepared once per batch in global memory; the corpus parts are produced per stage in shared
-// memory by 8 "splitter" warps (the corpus is stored once, as f32 — algorithmic bytes stay n_rows*dims*4).  The bf16 split
-// overwrites the f32 tile IN PLACE (both bf16 tiles together are as large as the f32 tile; read everything into registers,
-// named barrier, write), which makes a stage 48 KB and allows 4 stages; the tf32 split is out of place (2 stages).
-// Each smem stage holds MT=2 corpus tiles (256 rows) against ONE query chunk.
+// The query parts are prepared once per batch in global memory.  PREC_BF16: the corpus parts are prepared ONCE AT LOAD TIME as
+// two bf16 planes (hi, lo) — together 4 bytes per element, so the algorithmic bytes of a pass stay n_rows*dims*4 — and TMA
+// delivers them straight into the MMA-ready SWIZZLE_64B tiles: no splitter warps, no generic-proxy pass over the tile, half the
+// shared-memory traffic per stage (round 1 split the f32 tile in shared memory per stage: ncu showed LSU wavefronts at 47 % of
+// peak with 49.5 M bank conflicts competing with the tensor core's operand reads for the 128 B/clk of the SM's shared memory,
+// and the pass ran at 1.35x the HBM floor).  48 KB per stage, 4 stages.  PREC_TF32 keeps the f32 corpus and the 8 splitter
+// warps (out of place, 2 stages).  Each smem stage holds MT=2 corpus tiles (256 rows) against ONE query chunk.
 //
 // Warp roles (512 threads, 1 CTA/SM): w0 TMA producer | w1 TMEM alloc + MMA issuer | w4-7 epilogue (TMEM lane quadrant =
-// warp%4) | w8-15 splitters (f32 variants) or additional epilogue warps (int8).  Pipelines: full/split/empty per smem stage,
+// warp%4) | w8-15 splitters (tf32) / additional epilogue warps (int8) / idle (bf16).  Pipelines: full/split/empty per smem stage,
 // tfull/tempty per TMEM accumulator buffer (double-buffered: the epilogue of tile t overlaps the MMAs of tile t+1).
 // Epilogue: tcgen05.ld 8 (int8: 16) query columns at a time; the whole chunk is tested against the per-query thresholds
 // branch-free with ONE vote, and only chunks with a candidate take the per-column path (ballot, per-warp sorted lists in the
@@ -52,10 +54,8 @@ enum { PREC_TF32 = 0, PREC_BF16 = 1, PREC_I8 = 2 };
 constexpr int MAX_STAGES = 6;
 template <int NQ, int PREC, bool BRES = false> struct Cfg {
     // TF32: [A (-> A_hi in place) | A_lo | B_hi | B_lo], all f32 SWIZZLE_128B tiles
-    // BF16: [A f32 -> (A1 bf16 | A2 bf16) IN PLACE | B1 bf16 | B2 bf16], bf16 tiles are 64-byte rows, SWIZZLE_64B.  The two
-    //       bf16 tiles together are exactly as large as the f32 tile they come from; the splitters read the whole f32 tile
-    //       into registers, meet at a named barrier, then overwrite it.  48 KB per stage -> 4 stages instead of the 2 that an
-    //       out-of-place split (80 KB) allowed: with 2 stages the TMA latency, not the tensor pipe, set the stage period.
+    // BF16: [A1 bf16 (hi plane) | A2 bf16 (lo plane) | B1 bf16 | B2 bf16], 64-byte rows, SWIZZLE_64B, all four delivered by TMA.
+    //       48 KB per stage -> 4 stages.
     // I8  : [A i8 | B i8]: the int8 corpus (quantised at load time) is the MMA operand as TMA delivers it — no splitter
     //       pass, 128 dims per 128-byte swizzle row, 4 smem stages
     static constexpr int STAGES = PREC == PREC_TF32 ? 2 : 4;
@@ -116,8 +116,8 @@ __device__ __forceinline__ int ord_to_int(uint32_t o) {
 
 template <int NQ, int PREC, bool BRES>
 __global__ void __launch_bounds__(THREADS, 1)
-scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-        const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
+scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2 /*bf16: lo plane*/,
+        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*4][NQ][32]*/,
         const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/, uint32_t nq_valid,
         const uint64_t* __restrict__ ceil_keys /*[gridDim.y*NQ] or null*/, uint32_t nst_rt,
@@ -169,7 +169,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
             uint32_t it = 0;
             if (BRES) {
                 mbar_arrive_expect_tx(bfull, n_kchunks * C::B_BYTES);
@@ -183,6 +183,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&full[s], C::TX_BYTES);
                     tma_load_2d(st, &tmA, (int)(kc * C::KCE), (int)(tile * TROWS), &full[s]);   // 256-row box = MT swizzled tiles
+                    if (PREC == PREC_BF16) tma_load_2d(st + C::A2_OFF, &tmA2, (int)(kc * C::KCE), (int)(tile * TROWS), &full[s]);   // lo plane
                     if (!BRES) tma_load_2d(st + C::B_OFF, &tmBh, (int)(kc * C::KCE), (int)(group * NQ), &full[s]);
                     if (PREC != PREC_I8) tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmBl, (int)(kc * C::KCE), (int)(group * NQ), &full[s]);
                 }
@@ -207,7 +208,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
                     uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&full[s], ph);
-                    if (PREC != PREC_I8) mbar_wait(&split[s], ph);
+                    if (PREC == PREC_TF32) mbar_wait(&split[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stage0 + s * C::STAGE_BYTES);
                     if (PREC == PREC_I8) {
@@ -253,8 +254,8 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 }
             }
         }
-    } else if (warp >= 8 && PREC != PREC_I8) {
-        // ===================== splitters: f32 corpus tile -> (hi, lo) operand tiles =====================
+    } else if (warp >= 8 && PREC == PREC_TF32) {
+        // ===================== splitters (tf32 only): f32 corpus tile -> (hi, lo) operand tiles =====================
         const int t = threadIdx.x - 256;   // 0..SPLIT_THREADS-1
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -275,34 +276,6 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                         l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
                         A[t + SPLIT_THREADS * j] = h;
                         Al[t + SPLIT_THREADS * j] = l;
-                    }
-                } else {
-                    // unit u = (row r, 8-element group j): two float4 of the SWIZZLE_128B f32 tile -> one 16-byte chunk of
-                    // each SWIZZLE_64B bf16 tile (chunk j of row r lives at physical chunk j ^ ((r >> 1) & 3))
-                    const float4* A = (const float4*)st;
-                    uint4* A1 = (uint4*)(st + C::ALO_OFF);
-                    uint4* A2 = (uint4*)(st + C::A2_OFF);
-                    constexpr int UNITS = (TROWS * 4) / SPLIT_THREADS;
-                    float4 xs[UNITS], ys[UNITS];
-#pragma unroll
-                    for (int i = 0; i < UNITS; i++) {
-                        const int u = t + SPLIT_THREADS * i, r = u >> 2, j = u & 3;
-                        xs[i] = A[r * 8 + ((2 * j) ^ (r & 7))];
-                        ys[i] = A[r * 8 + ((2 * j + 1) ^ (r & 7))];
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(SPLIT_THREADS) : "memory");   // every f32 value is in a register: overwrite
-#pragma unroll
-                    for (int i = 0; i < UNITS; i++) {
-                        const int u = t + SPLIT_THREADS * i, r = u >> 2, j = u & 3;
-                        const float4 x = xs[i], y = ys[i];
-                        float r0, r1, r2, r3, r4, r5, r6, r7;
-                        uint4 h, l;
-                        h.x = bf16x2_hi(x.x, x.y, r0, r1); h.y = bf16x2_hi(x.z, x.w, r2, r3);
-                        h.z = bf16x2_hi(y.x, y.y, r4, r5); h.w = bf16x2_hi(y.z, y.w, r6, r7);
-                        l.x = bf16x2(r0, r1); l.y = bf16x2(r2, r3); l.z = bf16x2(r4, r5); l.w = bf16x2(r6, r7);
-                        const int dst = r * 4 + (j ^ ((r >> 1) & 3));
-                        A1[dst] = h;
-                        A2[dst] = l;
                     }
                 }
                 fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -510,13 +483,39 @@ __global__ void split_queries_tf32(const float* __restrict__ q, float* __restric
     hi[i] = __uint_as_float(h);
     lo[i] = __uint_as_float(x) - __uint_as_float(h);
 }
-__global__ void split_queries_bf16(const float* __restrict__ q, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
+// queries [nq][dims] f32 -> padded, (Cosine:) L2-normalised exactly like prep_queries (vec_scan.cu), split into bf16 hi / lo parts:
+// one launch instead of prep_queries + split (the per-batch launch chain is what limits small shards, SCALE_r01)
+__global__ void prep_split_queries_bf16(const float* __restrict__ q, uint32_t nq, uint32_t dims, uint64_t qstride,
+                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, uint32_t nq_pad, uint32_t dpad, int normalize) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nq_pad) return;
+    __nv_bfloat16* oh = hi + (size_t)row * dpad;
+    __nv_bfloat16* ol = lo + (size_t)row * dpad;
+    if (row >= nq) { for (uint32_t i = lane; i < dpad; i += 32) { oh[i] = __float2bfloat16_rn(0.f); ol[i] = __float2bfloat16_rn(0.f); } return; }
+    const float* src = q + (size_t)row * qstride;
+    float f = 1.f;
+    if (normalize) {
+        float s = 0.f;
+        for (uint32_t i = lane; i < dims; i += 32) { float v = src[i]; s = fmaf(v, v, s); }
+        for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(FULL, s, m);
+        f = 1.0f / sqrtf(s);
+    }
+    for (uint32_t i = lane; i < dpad; i += 32) {
+        const float x = i < dims ? src[i] * f : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        oh[i] = h;
+        ol[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+// load time: (normalised) f32 corpus rows -> the two bf16 planes the tensor-core scan streams (hi = bf16_rn(x), lo = bf16_rn(x - hi))
+__global__ void split_rows_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float x = q[i];
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
     hi[i] = h;
-    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
 // thr[q] = ordered-uint of the k-th largest of gmax[q][0..n_rg) as an f32 score (0 = no threshold when fewer than k groups
@@ -545,7 +544,7 @@ __global__ void kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, u
 template <int NQ, int PREC, bool BRES = false>
 static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     using C = tc::Cfg<NQ, PREC, BRES>;
-    CUtensorMap tmA, tmBh, tmBl;
+    CUtensorMap tmA, tmA2, tmBh, tmBl;
     uint32_t n_tiles = (uint32_t)((a.n_rows + tc::TROWS - 1) / tc::TROWS);
     uint32_t n_groups = a.nq_pad / NQ;
     size_t nel = (size_t)a.nq_pad * a.dpad;
@@ -554,19 +553,22 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
         // int8 corpus / queries (quantised by the caller): 128 dims per 128-byte swizzle row
         SSB_TRY(encode_tmap_2d(&tmA, a.rows_i8, 1, a.dpad8, a.n_rows, a.dpad8, 128, tc::TROWS, 128));
         SSB_TRY(encode_tmap_2d(&tmBh, a.queries_i8, 1, a.dpad8, a.nq_pad, a.dpad8, 128, NQ, 128));
-        tmBl = tmBh;
+        tmBl = tmBh; tmA2 = tmA;
         n_kchunks = a.dpad8 / 128;
     } else if constexpr (PREC == tc::PREC_TF32) {
         SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TROWS, 1));
         SSB_TRY(encode_tmap_2d_f32(&tmBh, a.q_hi, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
         SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
-        tc::split_queries_tf32<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, a.q_hi, a.q_lo, nel);
+        tmA2 = tmA;
+        if (!a.thr_init) tc::split_queries_tf32<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, a.q_hi, a.q_lo, nel);
     } else {
-        // the two bf16 parts live in the q_hi / q_lo buffers (half of each is used)
-        SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TROWS, 1));
+        // corpus: the two bf16 planes written at load time; queries: the two bf16 parts live in the q_hi / q_lo buffers (half of
+        // each is used) and were written by prep_split_queries_bf16 (launch_prep_split_queries_bf16)
+        if (!a.rows_hi || !a.rows_lo) { set_error("tcgen05 bf16 scan: the index holds no bf16 planes"); return SSB_E_STATE; }
+        SSB_TRY(encode_tmap_2d(&tmA, a.rows_hi, 2 /*bf16*/, a.dpad, a.n_rows, (uint64_t)a.dpad * 2, tc::KC, tc::TROWS, 64));
+        SSB_TRY(encode_tmap_2d(&tmA2, a.rows_lo, 2 /*bf16*/, a.dpad, a.n_rows, (uint64_t)a.dpad * 2, tc::KC, tc::TROWS, 64));
         SSB_TRY(encode_tmap_2d(&tmBh, a.q_hi, 2 /*bf16*/, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, tc::KC, NQ, 64));
         SSB_TRY(encode_tmap_2d(&tmBl, a.q_lo, 2 /*bf16*/, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, tc::KC, NQ, 64));
-        tc::split_queries_bf16<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, (__nv_bfloat16*)a.q_hi, (__nv_bfloat16*)a.q_lo, nel);
     }
     uint32_t gx = n_tiles < (uint32_t)a.n_sms ? n_tiles : (uint32_t)a.n_sms;
     if ((size_t)n_groups * gx * 4 * NQ * LIST * 8 > a.scratch_bytes) { set_error("vector scan scratch too small"); return SSB_E_STATE; }
@@ -583,7 +585,7 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     // several indexes on different GPUs in one process); the call is a cheap host-side attribute write
     SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ, PREC, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRES ? SMEM_MAX : C::SMEM));
     if (a.ev0) cudaEventRecord(a.ev0, st);
-    tc::scan_tc<NQ, PREC, BRES><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
+    tc::scan_tc<NQ, PREC, BRES><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmA2, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
                                                                              a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, nst,
                                                                              a.sample_groupmax ? 1u : 0u);
     if (a.ev1) cudaEventRecord(a.ev1, st);
@@ -592,13 +594,13 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
         tc::kth_from_groupmax<<<(a.nq_pad + 7) / 8, 256, 0, st>>>((const int*)a.scratch, n_tiles * (tc::MT * 4), a.nq_pad, a.k, a.thr_buf,
                                                                       PREC == tc::PREC_I8 ? 1 : 0);
         SSB_CUDA_TRY(cudaGetLastError());
-        if (a.launches) *a.launches += PREC == tc::PREC_I8 ? 2 : 3;   // (query split +) scan + kth
+        if (a.launches) *a.launches += PREC == tc::PREC_TF32 ? 3 : 2;   // (tf32 query split +) scan + kth
         return SSB_OK;
     }
     // scratch layout [group][list][q in NQ][32] -> generic merge with qt = NQ
     merge_lists_generic(a.scratch, gx * 4, NQ, a.nq_pad, a.keys_out, st);
     SSB_CUDA_TRY(cudaGetLastError());
-    if (a.launches) *a.launches += PREC == tc::PREC_I8 ? 2 : 3;   // (query split +) scan + merge
+    if (a.launches) *a.launches += 2;   // scan + merge (the tf32 query split is counted with the sample pass)
     return SSB_OK;
 }
 
@@ -635,6 +637,21 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int prec, cudaStream
 
 void launch_kth_from_groupmax(const void* gmax, uint32_t n_groups, uint32_t nq, uint32_t k, uint32_t* thr, int is_int, cudaStream_t st) {
     if (nq) tc::kth_from_groupmax<<<(nq + 7) / 8, 256, 0, st>>>((const int*)gmax, n_groups, nq, k, thr, is_int);
+}
+
+int32_t launch_prep_split_queries_bf16(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, void* hi, void* lo, uint32_t nq_pad,
+                                       uint32_t dpad, int normalize, cudaStream_t st) {
+    if (nq_pad == 0) return SSB_OK;
+    tc::prep_split_queries_bf16<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, dims, qstride, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, nq_pad, dpad, normalize);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_split_rows_bf16(const float* rows, void* hi, void* lo, size_t n_elems, cudaStream_t st) {
+    if (n_elems == 0) return SSB_OK;
+    tc::split_rows_bf16<<<(unsigned)((n_elems + 255) / 256), 256, 0, st>>>(rows, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n_elems);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
 }
 
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad) { return (size_t)nq_pad * (size_t)n_sms * 4 * LIST * 8; }
