@@ -184,6 +184,22 @@ int32_t ssb_search_lexical_keys(ssb_index* ix, const ssb_lex_batch* q, uint32_t 
 /* merge `n_lists` key lists per query ([n_lists][n_queries][32], device) into hits (host) */
 int32_t ssb_merge_keys(ssb_index* ix, const uint64_t* keys_dev, uint32_t n_lists, uint32_t n_queries,
                        uint32_t k, ssb_hit* hits, uint32_t* n_hits);
+/* ---- sharded index over several GPUs: one process per GPU, each handle holds a contiguous range of levels ---- */
+/* The reference fans a query out over its shards and concatenates + sorts their results (search.rs:1637-1743, 1875-1928, 2097-2106).
+ * Here every rank calls the same ssb_search_* with the same queries; once a communicator is set the library itself enqueues the
+ * exchange on the search stream — ncclAllGather of the packed top-k keys + the G*k -> k merge, ncclAllReduce of the match
+ * counts; hybrid: both lists are merged over the shards first and fused (RRF) afterwards — and every rank returns the GLOBAL
+ * result.  Searches on a handle with a communicator are serialised (collectives must be issued in the same order everywhere).
+ * NCCL is resolved at run time (the copy already loaded in the process, libnccl.so.2, or $SSB_NCCL_LIB). */
+#define SSB_COMM_ID_BYTES 128
+int32_t ssb_comm_unique_id(uint8_t* id128);                       /* ncclGetUniqueId; rank 0 calls it and ships the bytes to the others */
+int32_t ssb_comm_init(ssb_index* ix, const uint8_t* id128, uint32_t rank, uint32_t world);   /* collective: ncclCommInitRank      */
+int32_t ssb_comm_attach(ssb_index* ix, void* nccl_comm, uint32_t rank, uint32_t world);      /* borrow the caller's ncclComm_t      */
+int32_t ssb_comm_destroy(ssb_index* ix);
+/* collective: install the index-wide document frequencies (idf uses the df of the whole index, search.rs:3225-3230; the commit
+ * already received the global N and length sum).  After it, scores equal those of an unsharded index bit for bit. */
+int32_t ssb_lexical_sync_df(ssb_index* ix);
+
 int32_t ssb_sync(ssb_index* ix);
 /* the CUDA stream the index launches on (cudaStream_t as void*), for event timing */
 void*   ssb_stream(ssb_index* ix);

@@ -442,70 +442,77 @@ static uint64_t union_count_all(const orc_index* ix, const qterm_t* terms, uint3
     return total;
 }
 
-/* OR over a term subset: MAXSCORE-style sub-query enumeration in the spirit of union_docid_2/3
- * (union.rs:1168-1479): AND of all terms first, then every (n-1)-subset whose Σ max_list_score can still
- * beat heap.min, recursively, down to single terms. Scores of docs found by a sub-query are FULL scores
- * (all query terms the doc contains), so dedup keeps the max = the true score. */
+/* OR over 3+ terms: block-max ordered levels + MAXSCORE inside a level — the work union_docid_3's sub-query queue does
+ * (union.rs:1308-1479: sub-queries ordered by their summed max scores, each skipped once it cannot beat heap.min), restated
+ * as the textbook document-at-a-time loop so that the timed CPU baseline is not a strawman: levels by Σ block-max bound
+ * descending, stop at the first level whose bound < heap.min (only strictly smaller bounds prune, intersection.rs:2227-2233);
+ * inside a level the lists are driven in block-max order while the in-query-order sum of the not-yet-driven bounds can
+ * reach heap.min; a posting is scored fully (galloping probes into the other lists, monotone cursors) unless its own
+ * contribution + the later bounds cannot reach heap.min; docs found in an earlier-driven list are duplicates. */
 typedef struct { const orc_index* ix; const qterm_t* all; uint32_t n_all; heap_t* h; float max_list[ORC_MAX_TERMS]; } orctx;
+typedef struct { uint32_t level; float bound; } lvb_t;
+static int cmp_lvb_desc(const void* a, const void* b) {
+    float x = ((const lvb_t*)a)->bound, y = ((const lvb_t*)b)->bound;
+    if (x != y) return x > y ? -1 : 1;
+    uint32_t la = ((const lvb_t*)a)->level, lb = ((const lvb_t*)b)->level;
+    return la < lb ? -1 : (la > lb);
+}
 
-static void or_subsets(orctx* c) {
-    /* enumerate subsets in decreasing size; full-score semantics are obtained by scoring every doc that
-     * matches the AND of the subset with ALL query terms it contains (probe the others). To keep the
-     * restatement simple and exact we do: for subset masks ordered by Σ max_list desc, skip if bound <
-     * heap.min, else AND-enumerate the subset and score the doc fully. n_all <= 10 here. */
-    uint32_t n = c->n_all; uint32_t nm = 1u << n;
-    typedef struct { uint32_t mask; float bound; } sq;
-    sq* q = (sq*)malloc(nm * sizeof(sq)); uint32_t nq = 0;
-    for (uint32_t m = 1; m < nm; m++) {
-        float b = 0.0f; for (uint32_t t = 0; t < n; t++) if (m >> t & 1) b += c->max_list[t];
-        q[nq].mask = m; q[nq].bound = b; nq++;
-    }
-    /* sort by popcount desc then bound desc (AND of all first: union.rs:1328-1345) */
-    for (uint32_t i = 1; i < nq; i++) { sq x = q[i]; uint32_t j = i;
-        while (j > 0) { int pa = __builtin_popcount(q[j-1].mask), pb = __builtin_popcount(x.mask);
-            if (pa > pb || (pa == pb && q[j-1].bound >= x.bound)) break;
-            q[j] = q[j-1]; j--; }
-        q[j] = x; }
-    for (uint32_t i = 0; i < nq; i++) {
-        if (heap_full(c->h) && q[i].bound < heap_min(c->h)) continue;
-        qterm_t sub[ORC_MAX_TERMS]; uint32_t map[ORC_MAX_TERMS]; uint32_t ns = 0;
-        for (uint32_t t = 0; t < n; t++) if (q[i].mask >> t & 1) { sub[ns] = c->all[t]; map[ns] = t; ns++; }
-        /* docs matching exactly-this-subset-or-more get their FULL score: enumerate AND(sub) and add the
-         * remaining terms by probing */
-        const orc_index* ix = c->ix;
-        for (uint32_t li = 0; li < ix->n_levels; li++) {
-            const lvl_t* l = &ix->levels[li]; uint32_t tix[ORC_MAX_TERMS] = {0}; int ok = 1; float bb = 0.0f;
-            int64_t ent_all[ORC_MAX_TERMS];
-            for (uint32_t t = 0; t < n; t++) ent_all[t] = term_in_level(ix, &c->all[t], li);
-            for (uint32_t s = 0; s < ns; s++) { if (ent_all[map[s]] < 0) { ok = 0; break; }
-                tix[s] = ix->dict[ent_all[map[s]]].idx; bb += sub[s].idf * l->max_comp[tix[s]]; }
-            if (!ok) continue;
-            if (heap_full(c->h) && bb < heap_min(c->h)) continue; /* block-max skip for this sub-query */
-            uint32_t drv = 0, dn = 0xffffffffu;
-            for (uint32_t s = 0; s < ns; s++) { uint32_t cnt = l->posting_offsets[tix[s]+1]-l->posting_offsets[tix[s]];
-                if (cnt < dn) { dn = cnt; drv = s; } }
-            uint32_t pos[ORC_MAX_TERMS]; memset(pos, 0, sizeof(pos));
-            const uint16_t* da = l->doc_ids + l->posting_offsets[tix[drv]];
-            for (uint32_t j = 0; j < dn; j++) {
-                uint16_t d = da[j]; int all = 1;
-                for (uint32_t s = 0; s < ns && all; s++) { if (s == drv) continue;
-                    uint32_t off = l->posting_offsets[tix[s]], cnt = l->posting_offsets[tix[s]+1]-off;
-                    uint32_t p = gallop(l->doc_ids+off, pos[s], cnt, d); pos[s] = p;
-                    if (p >= cnt || l->doc_ids[off+p] != d) all = 0; }
-                if (!all) continue;
-                float comp = ix->cache[l->doc_len_bytes[d]]; float sc = 0.0f;
-                for (uint32_t t = 0; t < n; t++) {   /* full score, query order */
-                    if (ent_all[t] < 0) continue;
-                    uint32_t ti = ix->dict[ent_all[t]].idx;
-                    uint32_t off = l->posting_offsets[ti], cnt = l->posting_offsets[ti+1]-off;
-                    uint32_t p = gallop(l->doc_ids+off, 0, cnt, d);
-                    if (p < cnt && l->doc_ids[off+p] == d) sc += orc_bm25_term(c->all[t].idf, l->tfs[off+p], comp);
+static void or_maxscore(orctx* c) {
+    const orc_index* ix = c->ix; const uint32_t n = c->n_all; heap_t* h = c->h;
+    float* bound = (float*)calloc(ix->n_levels ? ix->n_levels : 1, sizeof(float));
+    uint8_t* seen = (uint8_t*)calloc(ix->n_levels ? ix->n_levels : 1, 1);
+    for (uint32_t t = 0; t < n; t++)                     /* query order: the bound is summed like a score */
+        for (uint64_t i = c->all[t].first; i < c->all[t].last; i++) {
+            uint32_t lv = ix->dict[i].level;
+            bound[lv] += c->all[t].idf * ix->levels[lv].max_comp[ix->dict[i].idx]; seen[lv] = 1;
+        }
+    lvb_t* order = (lvb_t*)malloc((ix->n_levels ? ix->n_levels : 1) * sizeof(lvb_t)); uint32_t nl = 0;
+    for (uint32_t lv = 0; lv < ix->n_levels; lv++) if (seen[lv]) { order[nl].level = lv; order[nl].bound = bound[lv]; nl++; }
+    qsort(order, nl, sizeof(lvb_t), cmp_lvb_desc);
+    for (uint32_t oi = 0; oi < nl; oi++) {
+        if (heap_full(h) && order[oi].bound < heap_min(h)) break;
+        const uint32_t li = order[oi].level; const lvl_t* l = &ix->levels[li];
+        uint32_t off[ORC_MAX_TERMS], cnt[ORC_MAX_TERMS], rank[ORC_MAX_TERMS], pos[ORC_MAX_TERMS]; float ub[ORC_MAX_TERMS];
+        for (uint32_t t = 0; t < n; t++) {
+            int64_t e = term_in_level(ix, &c->all[t], li);
+            if (e < 0) { cnt[t] = 0; off[t] = 0; ub[t] = 0.0f; continue; }
+            uint32_t ti = ix->dict[e].idx;
+            off[t] = l->posting_offsets[ti]; cnt[t] = l->posting_offsets[ti + 1] - off[t];
+            ub[t] = c->all[t].idf * l->max_comp[ti];
+        }
+        for (uint32_t t = 0; t < n; t++) {                /* MAXSCORE order: present lists by bound desc */
+            uint32_t r = 0;
+            for (uint32_t u = 0; u < n; u++) if (u != t && cnt[u] && (ub[u] > ub[t] || (ub[u] == ub[t] && u < t))) r++;
+            rank[t] = cnt[t] ? r : 0xFFFFu;
+        }
+        uint32_t np = 0; for (uint32_t t = 0; t < n; t++) np += cnt[t] ? 1u : 0u;
+        for (uint32_t p = 0; p < np; p++) {
+            float S = 0.0f, R = 0.0f; uint32_t drv = 0;
+            for (uint32_t t = 0; t < n; t++) { if (!cnt[t]) continue; if (rank[t] >= p) S += ub[t]; if (rank[t] > p) R += ub[t]; if (rank[t] == p) drv = t; }
+            if (heap_full(h) && S < heap_min(h)) break;
+            memset(pos, 0, sizeof(uint32_t) * n);
+            const float didf = c->all[drv].idf;
+            for (uint32_t j = 0; j < cnt[drv]; j++) {
+                const uint16_t d = l->doc_ids[off[drv] + j];
+                const float comp = ix->cache[l->doc_len_bytes[d]];
+                const float cd = orc_bm25_term(didf, l->tfs[off[drv] + j], comp);
+                if (heap_full(h) && (cd + R) * 1.000002f < heap_min(h)) continue;
+                float sc = 0.0f; int dup = 0;
+                for (uint32_t t = 0; t < n && !dup; t++) {   /* full score, query order */
+                    if (t == drv) { sc += cd; continue; }
+                    if (!cnt[t]) continue;
+                    uint32_t q = gallop(l->doc_ids + off[t], pos[t], cnt[t], d); pos[t] = q;
+                    if (q < cnt[t] && l->doc_ids[off[t] + q] == d) {
+                        if (rank[t] < p) dup = 1;            /* already emitted when that list was the driver */
+                        else sc += orc_bm25_term(c->all[t].idf, l->tfs[off[t] + q], comp);
+                    }
                 }
-                heap_add(c->h, ((uint64_t)l->level_id << 16) | d, sc, 1);
+                if (!dup) heap_add(h, ((uint64_t)l->level_id << 16) | d, sc, 0);
             }
         }
     }
-    free(q);
+    free(order); free(seen); free(bound);
 }
 
 int orc_search_lexical_pruned(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, uint32_t query_type,
@@ -548,14 +555,13 @@ int orc_search_lexical_pruned(const orc_index* ix, const uint64_t* keys, uint32_
             if (!heap_full(&h) || mx >= heap_min(&h)) single_pass(ix, &live[t], &h, 1);
         }
     } else {
-        if (nl > 12) { free(h.e); return -2; }
         orctx c; c.ix = ix; c.all = live; c.n_all = nl; c.h = &h;
         for (uint32_t t = 0; t < nl; t++) { float mx = 0.0f;
             for (uint64_t i = live[t].first; i < live[t].last; i++) {
                 float b = live[t].idf * ix->levels[ix->dict[i].level].max_comp[ix->dict[i].idx];
                 if (b > mx) mx = b; }
             c.max_list[t] = mx; }
-        if (kk) or_subsets(&c);
+        if (kk) or_maxscore(&c);
         if (result_type != ORC_RESULT_TOPK) total = union_count_all(ix, live, nl);
     }
     /* search.rs:3565-3596: take heap, sort by score desc (canonical: then doc id asc) */

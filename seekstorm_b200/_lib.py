@@ -64,7 +64,8 @@ EXPORTS = [
     "ssb_abi_version", "ssb_last_error", "ssb_create", "ssb_destroy", "ssb_lexical_add_level",
     "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
     "ssb_vector_add_level", "ssb_vector_count", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_vector_ex", "ssb_search_hybrid",
-    "ssb_rrf_fuse", "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
+    "ssb_rrf_fuse", "ssb_comm_unique_id", "ssb_comm_init", "ssb_comm_attach", "ssb_comm_destroy", "ssb_lexical_sync_df",
+    "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
     "ssb_stream", "ssb_set_stream", "ssb_last_stats",
 ]
 
@@ -106,6 +107,11 @@ def lib():
         "ssb_search_lexical_keys": [vp, C.POINTER(SsbLexBatch), u32, u32, vp, vp],
         "ssb_merge_keys": [vp, vp, u32, u32, u32, vp, vp],
         "ssb_sync": [vp],
+        "ssb_comm_unique_id": [vp],
+        "ssb_comm_init": [vp, vp, u32, u32],
+        "ssb_comm_attach": [vp, vp, u32, u32],
+        "ssb_comm_destroy": [vp],
+        "ssb_lexical_sync_df": [vp],
         "ssb_set_stream": [vp, vp],
         "ssb_last_stats": [vp, C.POINTER(SsbStats)],
     }

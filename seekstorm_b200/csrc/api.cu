@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bm25.h"
+#include "comm.h"
 #include "common.cuh"
 #include "vec_scan.h"
 
@@ -73,7 +74,7 @@ struct SearchCtx {
     cudaStream_t own_st = nullptr;
     LexWorkspace lex;
     DevBuf<float> qpad, qstage, qhi, qlo; DevBuf<int8_t> q_i8;
-    DevBuf<uint64_t> ceil, scratch, keys_a, keys_b, counts;
+    DevBuf<uint64_t> ceil, scratch, keys_a, keys_b, counts, gather;
     std::vector<uint64_t> h_ceil, h_keys_a, h_keys_b, h_counts;
     ssb_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_used = false, last_lex = false;
@@ -98,6 +99,7 @@ struct ssb_index {
     bool ext_stream_set = false; cudaStream_t ext_stream = nullptr;   // ssb_set_stream: every search runs on the caller's stream (one context)
     std::mutex stats_mu; SearchCtx* last_ctx = nullptr; ssb_stats last_stats{};
     LexIndex* lex = nullptr;
+    ShardComm comm;                   // set: this handle is one shard of a `world`-way sharded index (one process per GPU)
     // vector index
     uint32_t dims = 0, dpad = 0, dpad8 = 0;
     bool quant_i8 = false;            // Cosine + ScalarQuantizationI8: int8 corpus, exact int32 dot products
@@ -118,7 +120,9 @@ struct CtxLease {
     // block = false: give up (c stays null, SSB_OK) instead of waiting when every context is busy
     int32_t acquire(bool block = true) {
         std::unique_lock<std::mutex> g(ix->pool_mu);
-        const size_t cap = ix->ext_stream_set ? 1 : SSB_MAX_CTX;
+        // one context when the caller owns the stream, and when searches contain collectives (every rank must issue them in the
+        // same order: concurrent searches on one communicator would interleave them)
+        const size_t cap = (ix->ext_stream_set || ix->comm.active()) ? 1 : SSB_MAX_CTX;
         for (;;) {
             if (!ix->free_ctx.empty()) { c = ix->free_ctx.back(); ix->free_ctx.pop_back(); break; }
             if (ix->pool.size() < cap) {
@@ -251,6 +255,24 @@ void decode_keys(const uint64_t* keys, uint32_t nq, uint32_t k, ssb_hit* hits, u
     }
 }
 
+// Sharded index: all-gather every rank's [nq][32] key lists and merge them (G*k -> k with the canonical tie rule; the reference
+// concatenates the shard results and sorts, search.rs:1875-1928, 2097-2106).  In place; identical result on every rank.
+int32_t shard_merge(ssb_index* ix, SearchCtx& c, uint64_t* keys_dev, uint32_t nq) {
+    if (!ix->comm.active() || nq == 0) return SSB_OK;
+    const size_t n = (size_t)nq * LIST;
+    SSB_TRY(c.gather.reserve(n * ix->comm.world, 0, c.st));
+    SSB_TRY(comm_all_gather_u64(ix->comm, keys_dev, c.gather.p, n, c.st));
+    SSB_TRY(vec::launch_merge_lists(c.gather.p, ix->comm.world, nq, keys_dev, c.st));
+    c.stats.kernel_launches += 2;
+    return SSB_OK;
+}
+int32_t shard_sum_counts(ssb_index* ix, SearchCtx& c, uint64_t* counts_dev, uint32_t nq) {
+    if (!ix->comm.active() || nq == 0 || !counts_dev) return SSB_OK;
+    SSB_TRY(comm_all_reduce_sum_u64(ix->comm, counts_dev, nq, c.st));   // result_count_total = sum over shards (search.rs:1875-1940)
+    c.stats.kernel_launches += 1;
+    return SSB_OK;
+}
+
 // Paging state of the host-facing search calls (k > SSB_K_MAX, or de-duplication of multi-chunk documents).
 struct PageState {
     SearchCtx& c; uint32_t nq, k; ssb_hit* hits; uint32_t* n_hits; std::vector<uint32_t> cnt; std::vector<uint8_t> open; bool dedup;
@@ -326,6 +348,7 @@ int32_t search_vector_host(ssb_index* ix, SearchCtx& c, const void* queries, boo
     uint32_t kk = ix->dup_docs ? SSB_K_MAX : (k < SSB_K_MAX ? k : SSB_K_MAX);
     for (uint32_t page = 0; page < 4096; page++) {
         SSB_TRY(vec_keys(ix, c, queries, queries_i8, nq, kk, c.keys_a.p, page ? c.ceil.p : nullptr));
+        SSB_TRY(shard_merge(ix, c, c.keys_a.p, nq));
         SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
         SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
         c.stats.d2h_bytes += (uint64_t)nq * LIST * 8;
@@ -387,6 +410,7 @@ int32_t ssb_destroy(ssb_index* ix) {
         cudaStreamSynchronize(ix->load_st);
         ix->pool.clear();                                  // ~SearchCtx synchronises its stream
         delete ix->lex; ix->lex = nullptr;
+        comm_destroy(ix->comm);
         ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->doc_ids.release();
         cudaStreamDestroy(ix->load_st);
     }
@@ -498,7 +522,8 @@ int32_t ssb_search_vector_keys(ssb_index* ix, const float* queries, uint32_t nq,
     std::shared_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     CtxLease l(ix); SSB_TRY(l.acquire());
-    return vec_keys(ix, *l.c, queries, false, nq, k, keys_out_dev);
+    SSB_TRY(vec_keys(ix, *l.c, queries, false, nq, k, keys_out_dev));
+    return shard_merge(ix, *l.c, keys_out_dev, nq);
     SSB_API_END
 }
 
@@ -568,7 +593,9 @@ int32_t ssb_search_lexical_keys(ssb_index* ix, const ssb_lex_batch* q, uint32_t 
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     CtxLease l(ix); SSB_TRY(l.acquire());
     l.c->ev_used = true; l.c->last_lex = true;
-    return ix->lex->search_keys(l.c->lex, l.c->st, q, k, result_type, keys_out_dev, count_dev, &l.c->stats.kernel_launches);
+    SSB_TRY(ix->lex->search_keys(l.c->lex, l.c->st, q, k, result_type, keys_out_dev, count_dev, &l.c->stats.kernel_launches));
+    SSB_TRY(shard_merge(ix, *l.c, keys_out_dev, q->n_queries));
+    return shard_sum_counts(ix, *l.c, count_dev, q->n_queries);
     SSB_API_END
 }
 
@@ -589,6 +616,8 @@ int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, ui
     const bool want_hits = hits && k && result_type != SSB_RESULT_COUNT;
     const uint32_t k1 = k < SSB_K_MAX ? k : SSB_K_MAX;
     SSB_TRY(ix->lex->search_keys(c.lex, c.st, q, k1, result_type, c.keys_a.p, c.counts.p, &c.stats.kernel_launches));
+    SSB_TRY(shard_merge(ix, c, c.keys_a.p, nq));
+    SSB_TRY(shard_sum_counts(ix, c, c.counts.p, nq));
     SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
     SSB_CUDA_TRY(cudaMemcpyAsync(c.h_counts.data(), c.counts.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, c.st));
     SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
@@ -604,6 +633,7 @@ int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, ui
             const uint32_t kk = ps.next_page_k();
             SSB_TRY(ps.upload_ceilings());
             SSB_TRY(ix->lex->search_keys(c.lex, c.st, q, kk, SSB_RESULT_TOPK, c.keys_a.p, nullptr, &c.stats.kernel_launches, c.ceil.p));
+            SSB_TRY(shard_merge(ix, c, c.keys_a.p, nq));
             SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
             SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
             c.stats.d2h_bytes += (uint64_t)nq * LIST * 8;
@@ -663,9 +693,13 @@ int32_t ssb_search_hybrid(ssb_index* ix, const ssb_lex_batch* q, const float* qu
     SSB_TRY(cv->keys_b.reserve((size_t)nq * LIST, 0, cv->st));
     c.h_keys_a.resize((size_t)nq * LIST); cv->h_keys_b.resize((size_t)nq * LIST);
     SSB_TRY(ix->lex->search_keys(c.lex, c.st, q, k, SSB_RESULT_TOPK, c.keys_a.p, nullptr, &c.stats.kernel_launches));
+    // sharded: both lists are merged over the shards FIRST and fused afterwards — RRF ranks are positions in the merged lists
+    // (search.rs:1962-2035 runs after the shard results were concatenated and sorted)
+    SSB_TRY(shard_merge(ix, c, c.keys_a.p, nq));
     SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
     // multi-chunk documents: fetch the full 32-list so that k distinct docs survive the per-doc de-duplication
     SSB_TRY(vec_keys(ix, *cv, queries, false, nq, ix->dup_docs ? SSB_K_MAX : k, cv->keys_b.p));
+    SSB_TRY(shard_merge(ix, *cv, cv->keys_b.p, nq));
     SSB_CUDA_TRY(cudaMemcpyAsync(cv->h_keys_b.data(), cv->keys_b.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, cv->st));
     SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
     if (cv != &c) SSB_CUDA_TRY(cudaStreamSynchronize(cv->st));
@@ -703,6 +737,95 @@ int32_t ssb_merge_keys(ssb_index* ix, const uint64_t* keys_dev, uint32_t n_lists
     SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
     decode_keys(c.h_keys_b.data(), nq, k, hits, n_hits, ix->dup_docs);
     return SSB_OK;
+    SSB_API_END
+}
+
+// ---- sharded index: one process per GPU, NCCL communicator owned by (or lent to) the handle -------------------------------
+int32_t ssb_comm_unique_id(uint8_t* id128) {
+    SSB_API_BEGIN
+    if (!id128) { set_error("ssb_comm_unique_id: null argument"); return SSB_E_INVALID; }
+    return comm_unique_id(id128);
+    SSB_API_END
+}
+
+int32_t ssb_comm_init(ssb_index* ix, const uint8_t* id128, uint32_t rank, uint32_t world) {
+    SSB_API_BEGIN
+    if (!ix || !id128) { set_error("ssb_comm_init: null argument"); return SSB_E_INVALID; }
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    if (ix->comm.comm) { set_error("ssb_comm_init: the index already has a communicator"); return SSB_E_STATE; }
+    SSB_TRY(comm_init(ix->comm, id128, rank, world));
+    std::lock_guard<std::mutex> g2(ix->pool_mu);
+    if (ix->pool.size() > 1) { ix->pool.resize(1); ix->free_ctx.clear(); ix->free_ctx.push_back(ix->pool[0].get()); ix->last_ctx = nullptr; }
+    return SSB_OK;
+    SSB_API_END
+}
+
+int32_t ssb_comm_attach(ssb_index* ix, void* nccl_comm, uint32_t rank, uint32_t world) {
+    SSB_API_BEGIN
+    if (!ix || !nccl_comm || world == 0 || rank >= world) { set_error("ssb_comm_attach: bad argument"); return SSB_E_INVALID; }
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    if (ix->comm.comm) { set_error("ssb_comm_attach: the index already has a communicator"); return SSB_E_STATE; }
+    ix->comm.comm = nccl_comm; ix->comm.rank = rank; ix->comm.world = world; ix->comm.owned = false;
+    std::lock_guard<std::mutex> g2(ix->pool_mu);
+    if (ix->pool.size() > 1) { ix->pool.resize(1); ix->free_ctx.clear(); ix->free_ctx.push_back(ix->pool[0].get()); ix->last_ctx = nullptr; }
+    return SSB_OK;
+    SSB_API_END
+}
+
+int32_t ssb_comm_destroy(ssb_index* ix) {
+    SSB_API_BEGIN
+    if (!ix) return SSB_E_INVALID;
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    comm_destroy(ix->comm);
+    return SSB_OK;
+    SSB_API_END
+}
+
+// Global document frequencies of a sharded index (idf must use the df of the WHOLE index, search.rs:3225-3230): every rank
+// contributes its dictionary (sorted keys + local df), the sum per key is installed on every rank.  Collective.
+int32_t ssb_lexical_sync_df(ssb_index* ix) {
+    SSB_API_BEGIN
+    if (!ix) return SSB_E_INVALID;
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    if (!ix->comm.active()) return SSB_OK;
+    if (!ix->lex->committed()) { set_error("ssb_lexical_sync_df before ssb_lexical_commit"); return SSB_E_STATE; }
+    cudaStream_t st = ix->load_st;
+    const std::vector<uint64_t>& keys = ix->lex->host_keys();
+    const std::vector<uint32_t>& dfs = ix->lex->host_local_df();
+    const uint32_t world = ix->comm.world;
+    DevTmp<uint64_t> d_n; SSB_CUDA_TRY(d_n.alloc(1));
+    uint64_t n_max = keys.size();
+    SSB_CUDA_TRY(cudaMemcpyAsync(d_n.p, &n_max, 8, cudaMemcpyHostToDevice, st));
+    SSB_TRY(comm_all_reduce_max_u64(ix->comm, d_n.p, 1, st));
+    SSB_CUDA_TRY(cudaMemcpyAsync(&n_max, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_max == 0) return SSB_OK;
+    // send [n_max] keys (padded with ~0, which sorts last and matches nothing) and [n_max] dfs
+    std::vector<uint64_t> sk(n_max, ~0ull), sd(n_max, 0);
+    for (size_t i = 0; i < keys.size(); i++) { sk[i] = keys[i]; sd[i] = dfs[i]; }
+    DevTmp<uint64_t> d_sk, d_sd, d_rk, d_rd;
+    SSB_CUDA_TRY(d_sk.alloc(n_max)); SSB_CUDA_TRY(d_sd.alloc(n_max)); SSB_CUDA_TRY(d_rk.alloc(n_max * world)); SSB_CUDA_TRY(d_rd.alloc(n_max * world));
+    SSB_CUDA_TRY(cudaMemcpyAsync(d_sk.p, sk.data(), n_max * 8, cudaMemcpyHostToDevice, st));
+    SSB_CUDA_TRY(cudaMemcpyAsync(d_sd.p, sd.data(), n_max * 8, cudaMemcpyHostToDevice, st));
+    SSB_TRY(comm_all_gather_u64(ix->comm, d_sk.p, d_rk.p, n_max, st));
+    SSB_TRY(comm_all_gather_u64(ix->comm, d_sd.p, d_rd.p, n_max, st));
+    std::vector<uint64_t> rk(n_max * world), rd(n_max * world);
+    SSB_CUDA_TRY(cudaMemcpyAsync(rk.data(), d_rk.p, n_max * world * 8, cudaMemcpyDeviceToHost, st));
+    SSB_CUDA_TRY(cudaMemcpyAsync(rd.data(), d_rd.p, n_max * world * 8, cudaMemcpyDeviceToHost, st));
+    SSB_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<uint32_t> total(keys.size(), 0);
+    for (uint32_t r = 0; r < world; r++) {          // merge-join of two sorted key arrays
+        const uint64_t* k2 = rk.data() + (size_t)r * n_max; const uint64_t* d2 = rd.data() + (size_t)r * n_max;
+        size_t j = 0;
+        for (size_t i = 0; i < keys.size(); i++) {
+            while (j < n_max && k2[j] < keys[i]) j++;
+            if (j < n_max && k2[j] == keys[i]) total[i] += (uint32_t)d2[j];
+        }
+    }
+    return ix->lex->set_global_df(keys.data(), total.data(), keys.size());
     SSB_API_END
 }
 

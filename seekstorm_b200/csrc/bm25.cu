@@ -1178,6 +1178,7 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     SSB_CUDA_TRY(cudaMemcpyAsync(h_dict_keys_.data(), d_dict_keys_, (size_t)nt * 8, cudaMemcpyDeviceToHost, st_));
     SSB_CUDA_TRY(cudaMemcpyAsync(h_term_df_.data(), d_term_df_, (size_t)nt * 4, cudaMemcpyDeviceToHost, st_));
     SSB_CUDA_TRY(cudaStreamSynchronize(st_));
+    h_local_df_ = h_term_df_;
     {   // idf on the host (same libm as the oracle)
         std::vector<float> idf(nt_alloc);
         for (uint32_t t = 0; t < nt; t++) idf[t] = host_idf(n_docs, h_term_df_[t]);

@@ -142,6 +142,8 @@ public:
     void set_stream(cudaStream_t st) { st_ = st; }   // load-time stream (add_level / commit)
     static LexStats read_stats(const LexWorkspace& ws, cudaStream_t st);
     uint64_t n_postings() const { return n_post_; }
+    const std::vector<uint64_t>& host_keys() const { return h_dict_keys_; }
+    const std::vector<uint32_t>& host_local_df() const { return h_local_df_; }   // df of THIS shard's levels (set_global_df does not touch it)
     uint32_t n_levels() const { return (uint32_t)levels_.size(); }
 
 private:
@@ -160,7 +162,7 @@ private:
     uint32_t* d_e_level_ = nullptr; uint64_t* d_e_off_ = nullptr; uint32_t* d_e_count_ = nullptr; float* d_e_maxcomp_ = nullptr; uint32_t* d_e_bitmap_ = nullptr;
     uint64_t* d_bm_words_ = nullptr; uint16_t* d_bm_rank_ = nullptr;
     uint32_t* d_level_ids_ = nullptr; float* d_cache_ = nullptr;
-    std::vector<uint64_t> h_dict_keys_; std::vector<uint32_t> h_term_df_;
+    std::vector<uint64_t> h_dict_keys_; std::vector<uint32_t> h_term_df_, h_local_df_;
     void free_committed();
     LexView view() const;
 };

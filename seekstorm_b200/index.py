@@ -186,6 +186,27 @@ class Index:
         dfs = np.ascontiguousarray(dfs, dtype=np.uint32)
         check(lib().ssb_lexical_set_global_df(self._h, keys.ctypes.data, dfs.ctypes.data, len(keys)))
 
+    # ------------------------------------------------------------------ sharded index (one process per GPU)
+    def comm_unique_id(self) -> np.ndarray:
+        """ncclGetUniqueId through the library (rank 0); ship the 128 bytes to the other ranks and call comm_init everywhere."""
+        ident = np.zeros(128, dtype=np.uint8)
+        check(lib().ssb_comm_unique_id(ident.ctypes.data))
+        return ident
+
+    def comm_init(self, ident: np.ndarray, rank: int, world: int):
+        """Collective.  From here on every search_* call returns the GLOBAL result on every rank: the library all-gathers the
+        per-shard top-k keys over NCCL and merges them (all-reduces the counts) on the search stream."""
+        ident = np.ascontiguousarray(ident, dtype=np.uint8)
+        assert ident.size == 128
+        check(lib().ssb_comm_init(self._h, ident.ctypes.data, rank, world))
+
+    def comm_destroy(self):
+        check(lib().ssb_comm_destroy(self._h))
+
+    def sync_df(self):
+        """Collective: install the index-wide document frequencies (idf of the whole index on every shard)."""
+        check(lib().ssb_lexical_sync_df(self._h))
+
     def add_vector_level(self, level_id: int, rows, local_ids=None):
         """rows: [n, dims] f32 (numpy or torch, host or device), n <= 65536."""
         n, dims = int(rows.shape[0]), int(rows.shape[1])
@@ -271,6 +292,26 @@ class Index:
     @staticmethod
     def hits_buffer(n):
         return _hits_array(n)
+
+    def search_vector_ex(self, queries, k: int, similarity_threshold=None, int8_queries: bool = False):
+        """ssb_search_vector_ex: threshold (vector.rs:388-399), int8 query codes, vb result fields, observed_vector_count.
+        Returns (hits per query, ext structured array [nq, k], observed [nq])."""
+        from ._lib import SsbHitExt, SsbVecQuery
+        nq = int(queries.shape[0])
+        if isinstance(queries, np.ndarray):
+            queries = np.ascontiguousarray(queries, dtype=np.int8 if int8_queries else np.float32)
+        hits = _hits_array(max(nq * k, 1))
+        n_hits = np.zeros(max(nq, 1), dtype=np.uint32)
+        ext = (SsbHitExt * max(nq * k, 1))()
+        observed = np.zeros(max(nq, 1), dtype=np.uint64)
+        vq = SsbVecQuery(_addr(queries), nq, k, 1 if int8_queries else 0, 0 if similarity_threshold is None else 1,
+                         0.0 if similarity_threshold is None else float(similarity_threshold), (C.c_uint32 * 3)(0, 0, 0))
+        check(lib().ssb_search_vector_ex(self._h, C.byref(vq), hits.ctypes.data, n_hits.ctypes.data, C.addressof(ext), observed.ctypes.data))
+        out = []
+        for i in range(nq):
+            h = hits[i * k: i * k + int(n_hits[i])]
+            out.append([(int(d), float(s)) for d, s in zip(h["doc_id"], h["score"])])
+        return out, ext, observed[:nq]
 
     def search_hybrid_batch(self, queries_keys, query_type: QueryType, queries, k: int):
         nq = len(queries_keys)
@@ -365,14 +406,10 @@ class Index:
             lex, total = res[0], int(counts[0])
         if want_vec:
             qv = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)
-            vec = self.search_vector_batch(qv, max(heap, 1))[0][:heap]
-            if search_mode.similarity_threshold is not None:
-                # TopK::new (vector.rs:388-399): threshold pre-map (2t-1)*16129 for Dot/Cosine, -t for Euclidean; hits below
-                # it are rejected in TopK::push (:421).  Filtering the top-k afterwards is equivalent (scores are sorted).
-                t = float(search_mode.similarity_threshold)
-                cut = -t if self.vector_similarity == VectorSimilarity.Euclidean else ((t * 2.0) - 1.0) * 16129.0
-                vec = [(d, s) for d, s in vec if s >= cut]
-            ro.observed_vector_count = self.vector_count
+            # similarity_threshold (TopK::new, vector.rs:388-399) and observed_vector_count are handled behind the C-ABI
+            res, _, observed = self.search_vector_ex(qv, max(heap, 1), search_mode.similarity_threshold)
+            vec = res[0][:heap]
+            ro.observed_vector_count = int(observed[0])
         if search_mode.kind == "Lexical":
             fused = lex
             ro.result_count_total = total

@@ -48,11 +48,31 @@ def allreduce_global_df(index, group=None, device=None) -> int:
     return int(uk.numel())
 
 
+def init_shard_comm(index, group=None, device=None):
+    """Give the index its own NCCL communicator (behind the C-ABI: ssb_comm_unique_id on rank 0, the 128 id bytes broadcast
+    with torch.distributed, ssb_comm_init on every rank).  Afterwards every `index.search_*` call is a collective that returns
+    the global result: the all-gather of the per-shard top-k keys, the merge and the count all-reduce are enqueued by the
+    library on its search stream — no Python in the exchange."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    ident = index.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
+    t = torch.from_numpy(ident.astype(np.uint8)).to(dev)
+    dist.broadcast(t, src=0, group=group)
+    index.comm_init(t.cpu().numpy(), rank, world)
+
+
 class ShardedSearcher:
-    """Per-rank searcher over a block-range shard; every rank issues the same query batch."""
+    """Host-side reference of the exchange step with torch.distributed collectives (kept for the gloo CPU tests and as the
+    cross-check of the in-library NCCL path; the product path is `init_shard_comm` + plain `index.search_*`).
+    Per-rank searcher over a block-range shard; every rank issues the same query batch."""
 
     def __init__(self, index, group=None, merge_fn=None):
         self.index = index
+        # the collectives below are ordered against torch's current stream only: make the index launch on it
+        if torch.cuda.is_available() and hasattr(index, "set_stream") and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            index.set_stream(torch.cuda.current_stream().cuda_stream)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0

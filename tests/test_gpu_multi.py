@@ -14,7 +14,7 @@ N_DOCS, VOCAB, DIMS, N_VEC = 200000, 20000, 64, 150000
 
 def _build(rank, world, dev):
     from seekstorm_b200 import Index, VectorSimilarity, synth
-    from seekstorm_b200.parallel import allreduce_global_df, level_range
+    from seekstorm_b200.parallel import init_shard_comm, level_range
     ix = Index(dev, vector_dims=DIMS, vector_similarity=VectorSimilarity.Cosine)
     n_levels = (N_DOCS + 65535) // 65536
     ls = 0
@@ -24,7 +24,8 @@ def _build(rank, world, dev):
             ix.add_synth_level(lv)
     ix.commit(N_DOCS, ls)
     if world > 1:
-        allreduce_global_df(ix)
+        init_shard_comm(ix)        # NCCL communicator owned by the library (ssb_comm_init)
+        ix.sync_df()               # ssb_lexical_sync_df: index-wide df on every shard
     rows = synth.gen_vectors(N_VEC, DIMS, 6, "cpu").numpy()
     nvl = (N_VEC + 65535) // 65536
     for l in level_range(nvl, rank, world):
@@ -47,20 +48,23 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world)
     try:
         from seekstorm_b200 import QueryType, ResultType
-        from seekstorm_b200.parallel import ShardedSearcher
-        st = torch.cuda.Stream()
-        torch.cuda.set_stream(st)
         ix = _build(rank, world, rank)
-        ix.set_stream(st.cuda_stream)
         qk, qv = _queries()
-        sh = ShardedSearcher(ix)
-        vec = sh.search_vector(torch.from_numpy(qv).cuda(), 10)
-        b, keep = ix.make_lex_batch(qk, QueryType.Union)
-        lex, counts = sh.search_lexical(b, len(qk), 10, ResultType.TopkCount, f"cuda:{rank}")
+        # plain C-ABI calls with host buffers: the exchange (ncclAllGather + merge, count all-reduce, RRF after the merge) is the library's
+        vec = ix.search_vector_batch(qv, 10)
+        lex, counts = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
+        land, acounts = ix.search_lexical_batch(qk, QueryType.Intersection, 10, ResultType.TopkCount)
+        hyb = ix.search_hybrid_batch(qk, QueryType.Union, qv, 10)
+        deep = ix.search_vector_batch(qv[:4], 50)          # paging beyond 32 across shards
+        ret[f"vec{rank}"] = vec
         if rank == 0:
             ret["vec"] = vec
             ret["lex"] = lex
-            ret["counts"] = counts.cpu().numpy().astype(np.uint64).tolist()
+            ret["counts"] = [int(c) for c in counts]
+            ret["and"] = land
+            ret["acounts"] = [int(c) for c in acounts]
+            ret["hyb"] = hyb
+            ret["deep"] = deep
         ix.close()
     finally:
         dist.destroy_process_group()
@@ -78,8 +82,15 @@ def test_two_gpu_sharding_matches_single_gpu():
     qk, qv = _queries()
     want_vec = ix.search_vector_batch(qv, 10)
     want_lex, want_counts = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
+    want_and, want_acounts = ix.search_lexical_batch(qk, QueryType.Intersection, 10, ResultType.TopkCount)
     assert ret["lex"] == want_lex                      # bit-exact: global N / avgdl / df on every shard
     assert ret["counts"] == [int(c) for c in want_counts]
+    assert ret["and"] == want_and and ret["acounts"] == [int(c) for c in want_acounts]
+    assert ret["vec0"] == ret["vec1"]                  # every rank returns the global result
+    want_hyb = ix.search_hybrid_batch(qk, QueryType.Union, qv, 10)
+    assert [[d for d, _ in h] for h in ret["hyb"]] == [[d for d, _ in h] for h in want_hyb]
+    want_deep = ix.search_vector_batch(qv[:4], 50)
+    assert [[d for d, _ in h] for h in ret["deep"]] == [[d for d, _ in h] for h in want_deep]
     for g, w in zip(ret["vec"], want_vec):
         assert [d for d, _ in g] == [d for d, _ in w]
         assert np.allclose([s for _, s in g], [s for _, s in w], rtol=1e-5)

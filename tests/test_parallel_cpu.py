@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from seekstorm_b200.parallel import ShardedSearcher, allreduce_global_df, level_range
+from seekstorm_b200.parallel import ShardedSearcher, allreduce_global_df, init_shard_comm, level_range
 
 
 def test_level_range_partitions():
@@ -55,6 +55,13 @@ class FakeIndex:
         self.dfs = np.array([3, 10 + rank, 2], dtype=np.uint32)
         self.global_df = None
 
+    # the C-ABI communicator bootstrap (ssb_comm_unique_id / ssb_comm_init) seen from the host side
+    def comm_unique_id(self):
+        return (np.arange(128) * 7 % 251).astype(np.uint8)
+
+    def comm_init(self, ident, rank, world):
+        self.comm = (bytes(ident.tobytes()), rank, world)
+
     def dict_export(self):
         o = np.argsort(self.keys)
         return self.keys[o], self.dfs[o]
@@ -79,6 +86,8 @@ def _worker(rank, world, port, ret):
         assert n == 5
         assert ix.global_df == {5: 21, 7: 2, 17: 2, 1000: 3, 1001: 3}
         assert ix.global_df[5] == 10 + 11 and ix.global_df[1000] == 3 and ix.global_df[1001] == 3
+        init_shard_comm(ix, device="cpu")      # rank 0's id bytes reach every rank, each calls comm_init(rank, world)
+        assert ix.comm == (bytes(((np.arange(128) * 7) % 251).astype(np.uint8).tobytes()), rank, world)
         sh = ShardedSearcher(ix, merge_fn=_np_merge)
         got = sh.search_vector(torch.zeros((4, 8)), 10)
         full = FakeIndex(0, 1)
