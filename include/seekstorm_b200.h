@@ -129,6 +129,25 @@ int32_t ssb_lexical_dict_size(const ssb_index* ix, uint64_t* n_terms);
 int32_t ssb_lexical_dict_export(const ssb_index* ix, uint64_t* keys, uint32_t* dfs, uint64_t cap);
 int32_t ssb_lexical_set_global_df(ssb_index* ix, const uint64_t* keys, const uint32_t* dfs, uint64_t n);
 
+/* ---- loading the reference's own shard files ------------------------------------ */
+/* index.bin of ONE shard as written by commit.rs:203-467 / read by open_shard (index.rs:3253-3516): header, then per 64K-doc level
+ * the byte4 length array, the cumulative statistics, the segment table, key heads (compress_postinglist.rs:339-409) and key bodies
+ * (Array / Bitmap / RLE doc-id containers, compress_postinglist.rs:694-977; tf from the rank-position pointers,
+ * add_result.rs:2036-2197).  Adds every level and commits with the file's own indexed_doc_count / positions_sum_normalized.
+ * bytes: HOST memory (e.g. the mmap of the file).  params come from the shard's index.json / schema.json. */
+typedef struct {
+    uint32_t indexed_field_count;   /* schema: indexed fields; only 1 is supported (multi-field BM25F is out of scope)        */
+    uint32_t key_head_size;         /* 20 without n-gram indexing, 22 / 23 with bigram / trigram df bytes                      */
+    uint32_t segment_number_bits;   /* 11 (create_shard(.., 11, ..), index.rs:3295): 2048 dictionary segments per level        */
+    uint32_t reserved;
+} ssb_index_bin_params;
+int32_t ssb_load_index_bin(ssb_index* ix, const void* bytes, uint64_t len, const ssb_index_bin_params* params, uint64_t* n_docs_out);
+/* host-only walk of an index.bin (no GPU needed): out = {levels, single-term keys, postings, sum of tf, indexed_doc_count,
+ * positions_sum_normalized, FNV checksum over every (key, level, doc id, tf) in file order, 0} */
+int32_t ssb_index_bin_inspect(const void* bytes, uint64_t len, const ssb_index_bin_params* params, uint64_t out[8]);
+/* vector.bin of one shard (vector.rs:1066-1094; Precision::F32 records of 24 + 4*dims bytes); dims = the index's vector_dims */
+int32_t ssb_load_vector_bin(ssb_index* ix, const void* bytes, uint64_t len, uint64_t* n_vectors_out);
+
 /* ---- vector index -------------------------------------------------------------------------------- */
 /* rows: [n, dims] row-major f32 (row_stride_floats >= dims, 0 = dims); local_ids: [n] u16 or NULL (= 0..n-1).
  * Cosine: rows are L2-normalised on load (vector.rs:585-596 does this at index time). */

@@ -505,6 +505,43 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
     SSB_API_END
 }
 
+int32_t ssb_load_index_bin(ssb_index* ix, const void* bytes, uint64_t len, const ssb_index_bin_params* params, uint64_t* n_docs_out) {
+    SSB_API_BEGIN
+    if (!ix || !bytes || !params) { set_error("ssb_load_index_bin: null argument"); return SSB_E_INVALID; }
+    if (dev_ptr(bytes)) { set_error("ssb_load_index_bin: bytes must be host memory"); return SSB_E_INVALID; }
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    return load_index_bin(ix->lex, (const uint8_t*)bytes, len, params, n_docs_out);
+    SSB_API_END
+}
+
+int32_t ssb_index_bin_inspect(const void* bytes, uint64_t len, const ssb_index_bin_params* params, uint64_t out[8]) {
+    SSB_API_BEGIN
+    if (!bytes || !params || !out) { set_error("ssb_index_bin_inspect: null argument"); return SSB_E_INVALID; }
+    return inspect_index_bin((const uint8_t*)bytes, len, params, out);
+    SSB_API_END
+}
+
+int32_t ssb_load_vector_bin(ssb_index* ix, const void* bytes, uint64_t len, uint64_t* n_vectors_out) {
+    SSB_API_BEGIN
+    if (!ix || !bytes) { set_error("ssb_load_vector_bin: null argument"); return SSB_E_INVALID; }
+    if (dev_ptr(bytes)) { set_error("ssb_load_vector_bin: bytes must be host memory"); return SSB_E_INVALID; }
+    if (ix->dims == 0) { set_error("ssb_load_vector_bin: the index has no vector_dims"); return SSB_E_STATE; }
+    std::vector<VectorLevel> levels;
+    SSB_TRY(parse_vector_bin((const uint8_t*)bytes, len, ix->dims, levels));
+    uint64_t total = 0;
+    for (auto& vl : levels) {
+        for (size_t s = 0; s < vl.ids.size(); s += 65536) {      // a level may hold more than 64K records (one per chunk)
+            const uint32_t n = (uint32_t)std::min<size_t>(65536, vl.ids.size() - s);
+            SSB_TRY(ssb_vector_add_level(ix, vl.level_id, vl.rows.data() + s * ix->dims, ix->dims, vl.ids.data() + s, n, ix->dims));
+            total += n;
+        }
+    }
+    if (n_vectors_out) *n_vectors_out = total;
+    return SSB_OK;
+    SSB_API_END
+}
+
 int32_t ssb_set_vector_kernel(ssb_index* ix, uint32_t kernel) {
     SSB_API_BEGIN
     if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_BF16_N64) { set_error("bad vector kernel"); return SSB_E_INVALID; }

@@ -168,6 +168,24 @@ class Index:
             self.add_lexical_level(n["level_id"], n["n_docs"], n["term_keys"], n["posting_offsets"], n["doc_ids"],
                                    n["tfs"], n["doc_len_bytes"])
 
+    def load_index_bin(self, data, indexed_field_count: int = 1, key_head_size: int = 20, segment_number_bits: int = 11) -> int:
+        """Load one shard's index.bin (bytes / mmap / numpy uint8 array, the reference's own format, index.rs:3253-3516) and commit.
+        Returns indexed_doc_count."""
+        from ._lib import SsbIndexBinParams
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        prm = SsbIndexBinParams(indexed_field_count, key_head_size, segment_number_bits, 0)
+        n = C.c_uint64(0)
+        check(lib().ssb_load_index_bin(self._h, buf.ctypes.data, buf.size, C.byref(prm), C.byref(n)))
+        self.indexed_doc_count = n.value
+        return n.value
+
+    def load_vector_bin(self, data) -> int:
+        """Load one shard's vector.bin (vector.rs:1066-1094, f32 records).  Returns the number of vectors."""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        n = C.c_uint64(0)
+        check(lib().ssb_load_vector_bin(self._h, buf.ctypes.data, buf.size, C.byref(n)))
+        return n.value
+
     def commit(self, n_docs: int, len_sum_normalized: int):
         """Global statistics of the whole shard (commit.rs:318-319) + directory / block-max build."""
         check(lib().ssb_lexical_commit(self._h, n_docs, len_sum_normalized))
