@@ -21,6 +21,16 @@ KEYS = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
     "l1tex__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "smsp__cycles_active.avg",
     "sm__inst_executed_pipe_lsu.sum", "smsp__warps_eligible.avg.per_cycle_active",
+    # round 2: spills / local memory, shared-memory conflicts, global request efficiency, launch shape
+    "launch__local_size_bytes", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "launch__occupancy_limit_shared_mem",
+    "launch__waves_per_multiprocessor", "sm__maximum_warps_per_active_cycle_pct",
+    "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+    "smsp__inst_executed_op_global_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+    "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+    "sm__inst_executed_pipe_uniform.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
 
 

@@ -852,8 +852,7 @@ __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const 
     WarpSm& w = wsm[(threadIdx.x >> 5) & 7];
     const int lane = threadIdx.x & 31;
     const uint64_t total = (uint64_t)(*(volatile uint32_t*)&ctr[1]) * nq;
-    uint32_t st_visited = 0, st_probes = 0, st_done = 0, st_skipped = 0, st_recs = 0;
-    uint64_t acc_visited = 0, acc_probes = 0;
+    uint32_t st_visited = 0, st_probes = 0, st_done = 0, st_skipped = 0, st_recs = 0;   // per warp: far below 2^32 each
     uint32_t j, q;
     while (next_item(&ctr[0], total, nq, lane, j, q)) {
         const QueryPlan* pl = &plans[q];
@@ -867,13 +866,13 @@ __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const 
         st_done++;
         score_records<IS_AND>(v, w, nrec, q, k, ceil, theta, lane, L, thr, dirty, st_visited, st_probes, st_recs, st_skipped);
         if (dirty) publish(L, q, k, lane, theta, lock, glist);
-        acc_visited += st_visited; acc_probes += st_probes; st_visited = 0; st_probes = 0;
     }
     // per-lane counters (probes) are summed over the warp; warp-uniform ones are taken from lane 0
+    unsigned long long acc_probes = st_probes;
     for (int s = 16; s; s >>= 1) acc_probes += __shfl_xor_sync(FULL, acc_probes, s);
     if (lane == 0) {
-        atomicAdd((unsigned long long*)&stats->postings_visited, (unsigned long long)acc_visited);
-        atomicAdd((unsigned long long*)&stats->probes, (unsigned long long)acc_probes);
+        atomicAdd((unsigned long long*)&stats->postings_visited, (unsigned long long)st_visited);
+        atomicAdd((unsigned long long*)&stats->probes, acc_probes);
         atomicAdd((unsigned long long*)&stats->items_processed, (unsigned long long)st_done);
         atomicAdd((unsigned long long*)&stats->items_skipped, (unsigned long long)st_skipped);
         atomicAdd((unsigned long long*)&stats->recs_processed, (unsigned long long)st_recs);
