@@ -22,3 +22,15 @@ try:
     b=d['bm25']; print('bm25', b.get('value'), b.get('e2e'), b.get('variants'), b.get('roofline'))
 except Exception as e: print('bench parse', e)
 PY
+# FFMA group-max seeding A/B (compile-time switch SSB_FFMA_GROUPMAX=1 in libseekstorm_b200_gm.so): parity + batch-1/16 latency
+SSB_LIB=$PWD/seekstorm_b200/libseekstorm_b200_gm.so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_abi.py -m gpu -q -x -k "vector_parity_small or vector_doc_ids or vector_paging" > gpurun_out/c1_gm_pytest.log 2>&1
+echo "gm pytest rc=$?" | tee -a gpurun_out/c1_gm_pytest.log
+timeout 300 python bench.py --sections "" --vector-kernel ffma --cpu-seconds 0 --batch 16 --steps 20 > gpurun_out/c1_ffma_base.json 2> gpurun_out/c1_ffma_base.err
+SSB_LIB=$PWD/seekstorm_b200/libseekstorm_b200_gm.so timeout 300 python bench.py --sections "" --vector-kernel ffma --cpu-seconds 0 --batch 16 --steps 20 > gpurun_out/c1_ffma_gm.json 2> gpurun_out/c1_ffma_gm.err
+python - <<'PY'
+import json
+for n in ("base", "gm"):
+    try:
+        d = json.load(open(f"gpurun_out/c1_ffma_{n}.json")); print(n, d["value"], d["batch_sweep_e2e"], d["roofline"]["frac"])
+    except Exception as e: print(n, "parse", e)
+PY
