@@ -38,7 +38,7 @@ extern "C" {
 #define SSB_ABI_VERSION 2
 #define SSB_K_MAX 32u            /* top-k capacity of one kernel pass (lane-distributed lists); *_keys calls */
 #define SSB_K_LIMIT 1024u        /* ssb_search_lexical / ssb_search_vector page beyond 32 internally         */
-#define SSB_MAX_QUERY_TERMS 16u  /* unique terms per lexical query                                        */
+#define SSB_MAX_QUERY_TERMS 32u  /* unique terms per lexical query (<= 4: record path; 5..32: one term per lane)  */
 
 enum { SSB_OK = 0, SSB_E_INVALID = -1, SSB_E_CUDA = -2, SSB_E_NOMEM = -3, SSB_E_STATE = -4,
        SSB_E_UNSUPPORTED = -5, SSB_E_NO_DEVICE = -6 };

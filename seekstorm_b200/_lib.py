@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SSB_LIB") or os.path.join(_HERE, "libseekstorm_b200.s
 
 SSB_OK = 0
 K_MAX = 32
-MAX_QUERY_TERMS = 16
+MAX_QUERY_TERMS = 32
 
 QUERY_UNION, QUERY_INTERSECTION = 0, 1
 RESULT_COUNT, RESULT_TOPK, RESULT_TOPKCOUNT = 0, 1, 2

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             uint32_t wsl = is_and ? and_drv : (perm & 3u);
             weight = cs[wsl];
         } else {
-            meta = nl << 29;
+            meta = (nl < 7u ? nl : 7u) << 29;
 #pragma unroll
             for (int p = 0; p < 4; p++) { r.S[p] = 0.f; r.R[p] = 0.f; }
         }

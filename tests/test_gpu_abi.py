@@ -129,12 +129,12 @@ def test_incremental_levels_recommit():
 
 
 def test_many_term_queries_generic_path():
-    """> 4 live terms take the shuffle-broadcast generic path (up to SSB_MAX_QUERY_TERMS = 16)."""
+    """> 4 live terms take the shuffle-broadcast generic path (up to SSB_MAX_QUERY_TERMS = 32, one term per lane)."""
     from seekstorm_b200 import QueryType, ResultType, SsbError
     lvs, ls = synth_levels(80000, 2000, 41)
     orc = oracle_index([l.to_numpy() for l in lvs], 80000, ls)
     ix = gpu_index([l.to_numpy() for l in lvs], 80000, ls)
-    qs = synth.gen_queries(30, 42, 2, 1800, (5, 8, 12), (0.4, 0.4, 0.2))
+    qs = synth.gen_queries(30, 42, 2, 1800, (5, 8, 12, 24, 32), (0.3, 0.3, 0.2, 0.1, 0.1))
     qk = query_keys(qs)
     got, cnt = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
     for i, k in enumerate(qk):
@@ -146,7 +146,7 @@ def test_many_term_queries_generic_path():
         want, tot = orc.search(k, O.QUERY_INTERSECTION, 10, O.RESULT_TOPKCOUNT)
         assert got[i] == want and int(cnt[i]) == tot
     with pytest.raises(SsbError):
-        ix.search_lexical_batch([list(range(17))], QueryType.Union, 10, ResultType.Topk)
+        ix.search_lexical_batch([list(range(33))], QueryType.Union, 10, ResultType.Topk)
     ix.close()
 
 
