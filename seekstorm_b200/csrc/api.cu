@@ -424,6 +424,7 @@ int32_t ssb_lexical_add_level(ssb_index* ix, const ssb_level_desc* level) {
     if (!ix) { set_error("null index"); return SSB_E_INVALID; }
     std::unique_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    if (level && (dev_ptr(level->doc_ids) || dev_ptr(level->term_keys))) SSB_CUDA_TRY(cudaDeviceSynchronize());   // inputs produced on another stream
     return ix->lex->add_level(level);
     SSB_API_END
 }
@@ -461,6 +462,9 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     if (n == 0) return SSB_OK;
     cudaStream_t st = ix->load_st;
+    // device-resident inputs may still be in flight on the caller's stream (the load stream is non-blocking): load time is not
+    // hot, wait for the device once
+    if (dev_ptr(rows) || (local_ids && dev_ptr(local_ids))) SSB_CUDA_TRY(cudaDeviceSynchronize());
     // multi-chunk documents: several rows may share a local id (one vector per chunk, vector.rs:62-73); the reference's TopK keeps
     // the best chunk per doc id (vector.rs:436-470) — remember that this index needs the de-duplicating result path
     std::vector<uint16_t> h_ids;
