@@ -213,3 +213,60 @@ def test_lexical_paging_beyond_32():
     assert [(r.doc_id, np.float32(r.score)) for r in ro.results] == [(d, np.float32(s)) for d, s in want[40:50]]
     assert ro.result_count_total == tot
     ix.close()
+
+
+def test_search_vector_ex_threshold_int8_and_ext():
+    """ssb_search_vector_ex: similarity_threshold pre-map (vector.rs:388-399), vb fields / post-map (vector.rs:1485-1503),
+    observed_vector_count, int8 query codes for a ScalarQuantizationI8 index."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    n, dims = 30000, 64
+    rows = synth.gen_vectors(n, dims, 91, "cpu").numpy()
+    qs = synth.gen_vectors(6, dims, 92, "cpu").numpy()
+    qs[1] = rows[777] + 0.01 * qs[1]
+    ix = Index(0, vector_dims=dims, vector_similarity=VectorSimilarity.Cosine)
+    ix.add_vectors(rows)
+    nrows = np.stack([O.normalize(r) for r in rows])
+    t = 0.50002                                            # cut = (2t-1)*16129 ~ 0.645: only the planted neighbour passes
+    cut = np.float32((np.float32(t) * np.float32(2.0) - np.float32(1.0)) / np.float32(1.0 / 16129.0))
+    got, ext, observed = ix.search_vector_ex(qs, 10, similarity_threshold=t)
+    for i in range(len(qs)):
+        want = [(d, s) for d, s in O.search_vector(nrows, O.normalize(qs[i]), 10, O.SIM_COSINE) if not (np.float32(s) < cut)]
+        assert [d for d, _ in got[i]] == [d for d, _ in want]
+        assert int(observed[i]) == n
+        for j, (d, s) in enumerate(got[i]):
+            e = ext[i * 10 + j]
+            assert e.level_id == d >> 16 and e.source == 1
+            assert abs(e.vector_score - O.lib().orc_vector_score_postmap(np.float32(s), O.SIM_COSINE)) < 1e-6
+    assert [d for d, _ in got[1]] == [777]
+    no_thr, _, _ = ix.search_vector_ex(qs, 10)
+    assert no_thr == ix.search_vector_batch(qs, 10)
+    ix.close()
+    # int8 query codes == f32 queries quantised by the library
+    ix8 = Index(0, vector_dims=dims, vector_similarity=VectorSimilarity.Cosine, vector_quantization=1)
+    ix8.add_vectors(rows)
+    q8 = O.quantize_rows_i8(qs)
+    a, _, _ = ix8.search_vector_ex(q8, 10, int8_queries=True)
+    assert a == ix8.search_vector_batch(qs, 10)
+    ix8.close()
+
+
+def test_vector_multi_chunk_documents_are_deduplicated():
+    """Several rows with one doc id (one vector per chunk): the best chunk per doc is returned once (TopK::push, vector.rs:436-470),
+    through paging, hybrid and the k <= 32 path."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    dims, n_docs, chunks = 32, 500, 6
+    rng = np.random.default_rng(5)
+    rows = rng.normal(size=(n_docs * chunks, dims)).astype(np.float32)
+    ids = np.repeat(np.arange(n_docs, dtype=np.uint16), chunks)
+    ix = Index(0, vector_dims=dims, vector_similarity=VectorSimilarity.Dot)
+    ix.add_vector_level(3, rows, ids)
+    qs = rng.normal(size=(5, dims)).astype(np.float32)
+    for k in (10, 32, 100):
+        got = ix.search_vector_batch(qs, k)
+        sc = rows @ qs.T                                                          # [rows, nq] (score tolerance 1e-4 below)
+        for i in range(len(qs)):
+            best = sc[:, i].reshape(n_docs, chunks).max(axis=1)
+            order = np.lexsort((np.arange(n_docs), -best))[:k]
+            assert [d for d, _ in got[i]] == [(3 << 16) | int(d) for d in order]
+            assert np.allclose([s for _, s in got[i]], best[order], rtol=1e-4, atol=1e-5)
+    ix.close()
