@@ -148,6 +148,12 @@ int32_t ssb_index_bin_inspect(const void* bytes, uint64_t len, const ssb_index_b
 /* vector.bin of one shard (vector.rs:1066-1094; Precision::F32 records of 24 + 4*dims bytes); dims = the index's vector_dims */
 int32_t ssb_load_vector_bin(ssb_index* ix, const void* bytes, uint64_t len, uint64_t* n_vectors_out);
 
+/* ---- delete set ---------------------------------------------------------------------------------------- */
+/* shard.delete_hashset (index.rs:1594; delete_document index.rs:5110): deleted docs are neither scored nor counted, in the
+ * lexical path (add_result.rs:3435, union_count union.rs:975-1000) and in the vector scan (vector.rs:1450-1451).  doc_ids: host
+ * array of shard-local ids (level << 16 | local); replaces the current set; n = 0 clears it.  Exclusive like a commit. */
+int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n);
+
 /* ---- vector index -------------------------------------------------------------------------------- */
 /* rows: [n, dims] row-major f32 (row_stride_floats >= dims, 0 = dims); local_ids: [n] u16 or NULL (= 0..n-1).
  * Cosine: rows are L2-normalised on load (vector.rs:585-596 does this at index time). */

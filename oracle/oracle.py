@@ -57,6 +57,7 @@ def lib():
         L.orc_index_free.argtypes = [C.c_void_p]
         L.orc_index_add_level.argtypes = [C.c_void_p, C.POINTER(OrcLevel)]
         L.orc_index_commit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.orc_index_set_deleted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_index_df.restype = C.c_uint32
         L.orc_index_df.argtypes = [C.c_void_p, C.c_uint64]
         for f in (L.orc_search_lexical, L.orc_search_lexical_pruned):
@@ -117,6 +118,10 @@ class OracleIndex:
     def commit(self, n_docs: int, len_sum: int):
         self.n_docs, self.len_sum = n_docs, len_sum
         assert lib().orc_index_commit(self._h, n_docs, len_sum) == 0
+
+    def set_deleted(self, doc_ids):
+        a = np.ascontiguousarray(np.asarray(list(doc_ids), dtype=np.uint64))
+        assert lib().orc_index_set_deleted(self._h, _ptr(a) if a.size else None, a.size) == 0
 
     def df(self, key: int) -> int:
         return lib().orc_index_df(self._h, C.c_uint64(key))

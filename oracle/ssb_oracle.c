@@ -82,6 +82,7 @@ struct orc_index {
     uint64_t n_docs, len_sum;
     float cache[256];
     int committed;
+    uint64_t* deleted; uint64_t n_deleted;   /* shard.delete_hashset, sorted (add_result.rs:3435) */
 };
 
 orc_index* orc_index_new(void) { return (orc_index*)calloc(1, sizeof(orc_index)); }
@@ -93,7 +94,23 @@ void orc_index_free(orc_index* ix) {
         free(l->term_keys); free(l->posting_offsets); free(l->doc_ids); free(l->tfs);
         free(l->doc_len_bytes); free(l->max_comp);
     }
-    free(ix->levels); free(ix->dict); free(ix);
+    free(ix->levels); free(ix->dict); free(ix->deleted); free(ix);
+}
+
+static int cmp_u64(const void* a, const void* b) { uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b; return x < y ? -1 : (x > y); }
+/* delete set: docs in it are neither scored nor counted by orc_search_lexical (add_result.rs:3435; union_count union.rs:975-1000) */
+int orc_index_set_deleted(orc_index* ix, const uint64_t* doc_ids, uint64_t n) {
+    if (!ix) return -1;
+    free(ix->deleted); ix->deleted = NULL; ix->n_deleted = 0;
+    if (!n) return 0;
+    ix->deleted = (uint64_t*)malloc(n * 8); memcpy(ix->deleted, doc_ids, n * 8); ix->n_deleted = n;
+    qsort(ix->deleted, n, 8, cmp_u64);
+    return 0;
+}
+static inline int is_deleted(const orc_index* ix, uint64_t doc) {
+    uint64_t lo = 0, hi = ix->n_deleted;
+    while (lo < hi) { uint64_t m = (lo + hi) / 2; if (ix->deleted[m] < doc) lo = m + 1; else hi = m; }
+    return lo < ix->n_deleted && ix->deleted[lo] == doc;
 }
 
 static void* dup_mem(const void* p, size_t n) {
@@ -269,6 +286,7 @@ int orc_search_lexical(const orc_index* ix, const uint64_t* keys, uint32_t n_ter
         for (uint32_t d = 0; d < l->n_docs; d++) {
             int match = query_type == ORC_QUERY_INTERSECTION ? (cnt[d] == n_live) : (cnt[d] > 0);
             if (!match) continue;
+            if (ix->n_deleted && is_deleted(ix, ((uint64_t)l->level_id << 16) | d)) continue;
             total++;
             if (kk) topk_push(&tk, ((uint64_t)l->level_id << 16) | d, acc[d]);
         }

@@ -65,6 +65,8 @@ int        orc_index_add_level(orc_index*, const orc_level*);   /* copies everyt
 /* global statistics (1-shard semantics); finalises the dictionary */
 int        orc_index_commit(orc_index*, uint64_t n_docs, uint64_t len_sum_normalized);
 uint32_t   orc_index_df(const orc_index*, uint64_t term_key);
+/* shard.delete_hashset (add_result.rs:3435): honoured by the EXHAUSTIVE search only (the pruned variant is the timed baseline) */
+int        orc_index_set_deleted(orc_index*, const uint64_t* doc_ids, uint64_t n);
 
 /* Exhaustive BM25 search, canonical tie rule (score desc, doc id asc).
  * Candidate semantics: AND intersection.rs:2023-2301, OR union.rs:1168-1479; score

@@ -99,6 +99,7 @@ struct ssb_index {
     bool ext_stream_set = false; cudaStream_t ext_stream = nullptr;   // ssb_set_stream: every search runs on the caller's stream (one context)
     std::mutex stats_mu; SearchCtx* last_ctx = nullptr; ssb_stats last_stats{};
     LexIndex* lex = nullptr;
+    DeleteSet del;                    // shard.delete_hashset mirrored on the device (ssb_set_deleted)
     ShardComm comm;                   // set: this handle is one shard of a `world`-way sharded index (one process per GPU)
     // vector index
     uint32_t dims = 0, dpad = 0, dpad8 = 0;
@@ -216,6 +217,7 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     a.keys_out = merged; a.ev0 = c.ev0; a.ev1 = c.ev1; c.ev_used = true;
     a.thr_buf = reinterpret_cast<uint32_t*>(merged + (size_t)nq_pad * LIST);
     a.ceil_keys = ceil_dev;
+    if (ix->del.n) { a.del_slot = ix->del.d_slot; a.del_words = ix->del.d_words; }
     a.launches = &c.stats.kernel_launches;
     if (ix->quant_i8) {
         a.rows_i8 = ix->rows_i8.p; a.queries_i8 = c.q_i8.p; a.dpad8 = ix->dpad8;
@@ -392,6 +394,7 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     if (cudaStreamCreateWithFlags(&ix->load_st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); set_error("stream create failed"); return SSB_E_CUDA; }
     ix->lex = new (std::nothrow) LexIndex(ix->load_st, ix->n_sms, ix->cfg.max_batch);
     if (!ix->lex) { cudaStreamDestroy(ix->load_st); set_error("out of host memory"); return SSB_E_NOMEM; }
+    ix->lex->set_deleted(&ix->del);
     ix->dims = cfg->vector_dims;
     ix->dpad = (cfg->vector_dims + 31) / 32 * 32;
     ix->dpad8 = (cfg->vector_dims + 127) / 128 * 128;
@@ -411,6 +414,7 @@ int32_t ssb_destroy(ssb_index* ix) {
         ix->pool.clear();                                  // ~SearchCtx synchronises its stream
         delete ix->lex; ix->lex = nullptr;
         comm_destroy(ix->comm);
+        ix->del.release();
         ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->doc_ids.release();
         cudaStreamDestroy(ix->load_st);
     }
@@ -542,6 +546,40 @@ int32_t ssb_load_vector_bin(ssb_index* ix, const void* bytes, uint64_t len, uint
         }
     }
     if (n_vectors_out) *n_vectors_out = total;
+    return SSB_OK;
+    SSB_API_END
+}
+
+// shard.delete_hashset (index.rs:1594, filled by delete_document index.rs:5110): deleted docs are neither scored nor counted
+// (add_result.rs:3435, vector.rs:1450-1451, union_count union.rs:975-1000).  Replaces the current set; n = 0 clears it.
+int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n) {
+    SSB_API_BEGIN
+    if (!ix || (n && !doc_ids)) { set_error("ssb_set_deleted: null argument"); return SSB_E_INVALID; }
+    if (n >= (1ull << 31)) { set_error("ssb_set_deleted: too many doc ids"); return SSB_E_UNSUPPORTED; }
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    std::vector<uint32_t> docs(n);
+    for (uint64_t i = 0; i < n; i++) {
+        if (doc_ids[i] >> 32) { set_error("ssb_set_deleted: doc id %llu out of range", (unsigned long long)doc_ids[i]); return SSB_E_INVALID; }
+        docs[i] = (uint32_t)doc_ids[i];
+    }
+    std::sort(docs.begin(), docs.end());
+    docs.erase(std::unique(docs.begin(), docs.end()), docs.end());
+    for (auto& c : ix->pool) cudaStreamSynchronize(c->own_st);
+    ix->del.release();
+    if (docs.empty()) return SSB_OK;
+    std::vector<uint32_t> slot(65536, 0xFFFFFFFFu);
+    uint32_t n_slots = 0;
+    for (uint32_t d : docs) if (slot[d >> 16] == 0xFFFFFFFFu) slot[d >> 16] = n_slots++;
+    std::vector<uint64_t> words((size_t)n_slots * 1024, 0ull);
+    for (uint32_t d : docs) words[(size_t)slot[d >> 16] * 1024 + ((d & 0xFFFFu) >> 6)] |= 1ull << (d & 63u);
+    SSB_CUDA_TRY(cudaMalloc(&ix->del.d_slot, 65536 * 4));
+    SSB_CUDA_TRY(cudaMalloc(&ix->del.d_words, words.size() * 8));
+    SSB_CUDA_TRY(cudaMalloc(&ix->del.d_docs, docs.size() * 4));
+    SSB_CUDA_TRY(cudaMemcpy(ix->del.d_slot, slot.data(), 65536 * 4, cudaMemcpyHostToDevice));
+    SSB_CUDA_TRY(cudaMemcpy(ix->del.d_words, words.data(), words.size() * 8, cudaMemcpyHostToDevice));
+    SSB_CUDA_TRY(cudaMemcpy(ix->del.d_docs, docs.data(), docs.size() * 4, cudaMemcpyHostToDevice));
+    ix->del.n = (uint32_t)docs.size();
     return SSB_OK;
     SSB_API_END
 }

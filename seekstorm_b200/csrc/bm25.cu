@@ -410,6 +410,14 @@ __device__ __forceinline__ float term_score(const LexView& v, float idf, uint64_
     return __fmul_rn(idf, comp_of(v, __ldg(&v.pay[pos])));
 }
 
+// shard.delete_hashset.contains(docid) (add_result.rs:3435): one table lookup + one bitmap word, only for exact-score survivors
+__device__ __forceinline__ bool is_deleted(const LexView& v, uint32_t doc) {
+    if (!v.del_slot) return false;
+    const uint32_t slot = __ldg(&v.del_slot[doc >> 16]);
+    if (slot == NONE) return false;
+    return ((__ldg(&v.del_words[(size_t)slot * 1024 + ((doc & 0xFFFFu) >> 6)]) >> (doc & 63u)) & 1ull) != 0;
+}
+
 __device__ __forceinline__ float bound_of_word(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bool cand, float score, uint32_t doc,
@@ -500,7 +508,9 @@ __device__ __forceinline__ void process_queued(const LexView& v, const WarpSm& w
         }
     }
     uint32_t t = thr.u;
-    insert_candidates(L, t, alive && ord_f32(score) >= thr.u, score, rec.docbase | d, k, lane, dirty, ceil);
+    alive = alive && ord_f32(score) >= thr.u;
+    if (alive && is_deleted(v, rec.docbase | d)) alive = false;
+    insert_candidates(L, t, alive, score, rec.docbase | d, k, lane, dirty, ceil);
     if (t != thr.u) thr.set(t);
 }
 
@@ -717,7 +727,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                 if (ok && c.scoring) score = __fadd_rn(score, term_score(v, ti, to + rank));
             }
             matches += __popc(__ballot_sync(FULL, ok));
-            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
+            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d), score, c.docbase | d, c.k, lane, dirty, c.ceil);
         }
         if (lane == 0) matches_out += matches;
         return;
@@ -761,7 +771,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                         else score = __fadd_rn(score, term_score(v, ti, to + rank));
                     }
                 }
-                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
+                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d), score, c.docbase | d, c.k, lane, dirty, c.ceil);
             }
         }
     }
@@ -955,6 +965,36 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
     }
 }
 
+// ---- exact counts with a delete set: the count kernels count every match; the deleted docs that match are subtracted here,
+// one thread per (query, deleted doc) — the reference does the same walk over delete_hashset (union_count, union.rs:975-1000) ----
+__global__ void lex_del_count(LexView v, const QueryPlan* __restrict__ plans, uint32_t nq, uint32_t query_type, uint64_t* count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)nq * v.n_del) return;
+    const uint32_t q = (uint32_t)(i / v.n_del), doc = __ldg(&v.del_docs[i % v.n_del]);
+    const QueryPlan* pl = &plans[q];
+    const uint32_t n = pl->n_live;
+    if (n == 0) return;
+    uint32_t lo = 0, hi = v.n_levels;                               // local level index of the doc's level id
+    const uint32_t lid = doc >> 16, d = doc & 0xFFFFu;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(&v.level_ids[m]) < lid) lo = m + 1; else hi = m; }
+    if (lo >= v.n_levels || __ldg(&v.level_ids[lo]) != lid) return;  // level not on this shard
+    const uint32_t lv = lo;
+    const bool is_and = query_type == SSB_QUERY_INTERSECTION;
+    bool any = false, all = true;
+    for (uint32_t t = 0; t < n; t++) {
+        const QTerm qt = pl->t[t];
+        uint32_t a = 0, b = qt.n;
+        while (a < b) { const uint32_t m = (a + b) >> 1; if (__ldg(&v.e_level[qt.first + m]) < lv) a = m + 1; else b = m; }
+        bool pres = false;
+        if (a < qt.n && __ldg(&v.e_level[qt.first + a]) == lv) {
+            const uint32_t e = qt.first + a;
+            pres = present_in(v, __ldg(&v.e_count[e]), __ldg(&v.e_off[e]), __ldg(&v.e_bitmap[e]), d);
+        }
+        any = any || pres; all = all && pres;
+    }
+    if (is_and ? all : any) atomicAdd((unsigned long long*)&count[q], ~0ull);   // -1
+}
+
 __global__ void copy_out(const uint64_t* __restrict__ glist, const uint64_t* __restrict__ count, uint32_t nq, uint32_t k,
                          uint64_t* keys_out, uint64_t* count_out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1098,6 +1138,7 @@ LexView LexIndex::view() const {
     v.post = post_.p; v.pay = pay_.p; v.bm_words = d_bm_words_; v.bm_rank = d_bm_rank_; v.level_ids = d_level_ids_;
     v.n_levels = (uint32_t)levels_.size(); v.cache = d_cache_;
     v.k1p = 1.2f + 1.0f;
+    if (del_ && del_->n) { v.del_slot = del_->d_slot; v.del_words = del_->d_words; v.del_docs = del_->d_docs; v.n_del = del_->n; }
     return v;
 }
 
@@ -1321,6 +1362,12 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     // queries with 5..16 live terms (the kernel returns at once when the batch has none)
     lex_generic<<<n_sms_ * 2, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, q->query_type, result_type, kk, ws.ctr, ws.theta, ws.lock, ws.count, glist, ws.stats, ceil_dev);
     SSB_CUDA_TRY(cudaGetLastError());
+    if (need_count && v.n_del) {
+        const uint64_t pairs = (uint64_t)nq * v.n_del;
+        lex_del_count<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(v, ws.plans, nq, q->query_type, ws.count);
+        SSB_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
     if (ws.ev1) cudaEventRecord(ws.ev1, st);
     copy_out<<<(nq * LIST + 255) / 256, 256, 0, st>>>(glist, ws.count, nq, result_type == SSB_RESULT_COUNT ? 0 : k, keys_out_dev, count_dev);
     SSB_CUDA_TRY(cudaGetLastError());

@@ -80,6 +80,17 @@ struct LexView {
     uint32_t n_levels;
     const float* cache;           // [256] bm25_component_cache
     float k1p;                    // K + 1
+    // delete set (shard.delete_hashset, add_result.rs:3435): null = no deleted docs
+    const uint32_t* del_slot;     // [65536] level_id -> bitmap slot or 0xFFFFFFFF
+    const uint64_t* del_words;    // [n_slots][1024]
+    const uint32_t* del_docs;     // [n_del] deleted doc ids, ascending
+    uint32_t n_del;
+};
+
+// device-resident delete set shared by the lexical and the vector path
+struct DeleteSet {
+    uint32_t* d_slot = nullptr; uint64_t* d_words = nullptr; uint32_t* d_docs = nullptr; uint32_t n = 0;
+    void release() { cudaFree(d_slot); cudaFree(d_words); cudaFree(d_docs); d_slot = nullptr; d_words = nullptr; d_docs = nullptr; n = 0; }
 };
 
 struct QTerm { uint32_t first, n; float idf; uint32_t df; };
@@ -140,6 +151,7 @@ public:
                         uint64_t* keys_out_dev, uint64_t* count_dev, uint64_t* launches, const uint64_t* ceil_dev = nullptr) const;
     bool committed() const { return committed_; }
     void set_stream(cudaStream_t st) { st_ = st; }   // load-time stream (add_level / commit)
+    void set_deleted(const DeleteSet* d) { del_ = d; }
     static LexStats read_stats(const LexWorkspace& ws, cudaStream_t st);
     uint64_t n_postings() const { return n_post_; }
     const std::vector<uint64_t>& host_keys() const { return h_dict_keys_; }
@@ -163,6 +175,7 @@ private:
     uint64_t* d_bm_words_ = nullptr; uint16_t* d_bm_rank_ = nullptr;
     uint32_t* d_level_ids_ = nullptr; float* d_cache_ = nullptr;
     std::vector<uint64_t> h_dict_keys_; std::vector<uint32_t> h_term_df_, h_local_df_;
+    const DeleteSet* del_ = nullptr;
     void free_committed();
     LexView view() const;
 };

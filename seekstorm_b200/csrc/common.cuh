@@ -106,6 +106,15 @@ __device__ __forceinline__ uint64_t wl_merge(uint64_t A, uint64_t B, int lane) {
     return M;
 }
 
+// delete set probe (shard.delete_hashset, vector.rs:1450-1451 / add_result.rs:3435): level table + one bitmap word; only on the
+// rare candidate-insert paths
+__device__ __forceinline__ bool doc_deleted(const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words, uint32_t doc) {
+    if (!del_slot) return false;
+    const uint32_t slot = __ldg(&del_slot[doc >> 16]);
+    if (slot == 0xFFFFFFFFu) return false;
+    return ((__ldg(&del_words[(size_t)slot * 1024 + ((doc & 0xFFFFu) >> 6)]) >> (doc & 63u)) & 1ull) != 0;
+}
+
 // ---------------------------------------------------------------- PTX: mbarrier + TMA
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

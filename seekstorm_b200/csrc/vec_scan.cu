@@ -59,7 +59,8 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
           const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*CWARPS/2][QT][32]*/,
           const uint32_t* __restrict__ thr_init /*[gridDim.y*QT] or null*/, uint32_t nq_valid,
-          const uint64_t* __restrict__ ceil_keys /*[gridDim.y*QT] or null*/
+          const uint64_t* __restrict__ ceil_keys /*[gridDim.y*QT] or null*/,
+          const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words
 #if SSB_FFMA_GROUPMAX
           , uint32_t sample_mode
 #endif
@@ -199,7 +200,7 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                     uint32_t row_s = __shfl_sync(FULL, row, src);
                                     uint32_t doc = doc_ids ? __ldg(&doc_ids[row_s]) : row_s;
                                     uint64_t key = ((uint64_t)so_s << 32) | (uint64_t)(0xFFFFFFFFu - doc);
-                                    if (key < ceil) wl_insert(Lq, key, lane);
+                                    if (key < ceil && !doc_deleted(del_slot, del_words, doc)) wl_insert(Lq, key, lane);
                                 }
                                 myL[q * LIST] = Lq;
                                 const uint32_t kth = (uint32_t)(shfl64(Lq, (int)k - 1) >> 32);
@@ -329,7 +330,8 @@ void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_
 // are unchanged, but the expected number of list insertions per query drops from ~k*ln(rows/k) PER LIST to ~k*N/S in total.
 template <class F>
 static int32_t with_presample(const ScanArgs& a, cudaStream_t st, F launch) {
-    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, false) == 0) return launch(a);
+    // with a delete set the sample pass is skipped: a deleted row must never seed a threshold
+    if (a.thr_init || !a.thr_buf || a.del_slot || vec_presample_rows(a.n_rows, false) == 0) return launch(a);
     ScanArgs pre = a;
     pre.n_rows = vec_presample_rows(a.n_rows, false); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
 #if SSB_FFMA_GROUPMAX
@@ -364,7 +366,7 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
     if (a.ev0) cudaEventRecord(a.ev0, st);
 #if SSB_FFMA_GROUPMAX
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
-                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, a.sample_groupmax ? 1u : 0u);
+                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, a.del_slot, a.del_words, a.sample_groupmax ? 1u : 0u);
     if (a.sample_groupmax) {
         SSB_CUDA_TRY(cudaGetLastError());
         launch_kth_from_groupmax(a.scratch, n_tiles * 16, a.nq_pad, a.k, a.thr_buf, 0, st);
@@ -373,7 +375,7 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
     }
 #else
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
-                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys);
+                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, a.del_slot, a.del_words);
 #endif
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());

@@ -32,6 +32,7 @@ struct ScanArgs {
     const int8_t* rows_i8 = nullptr;               // int8 path: [n_rows][dpad8] quantised corpus
     const int8_t* queries_i8 = nullptr;            //            [nq_pad][dpad8] quantised queries
     uint32_t dpad8 = 0;                            //            multiple of 128
+    const uint32_t* del_slot = nullptr; const uint64_t* del_words = nullptr;   // delete set (null = none): deleted docs never enter a list
     bool sample_groupmax = false;                  // internal (int8): threshold-seeding pass, writes thr_buf instead of lists
 };
 

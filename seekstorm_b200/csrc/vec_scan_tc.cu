@@ -121,6 +121,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*4][NQ][32]*/,
         const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/, uint32_t nq_valid,
         const uint64_t* __restrict__ ceil_keys /*[gridDim.y*NQ] or null*/, uint32_t nst_rt,
+        const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words /*delete set or null*/,
         uint32_t sample_mode /*int8 only: write per-(32-row group, query) score maxima instead of lists*/) {
     using C = Cfg<NQ, PREC, BRES>;
     const uint32_t STAGES = BRES ? nst_rt : (uint32_t)C::STAGES;
@@ -351,11 +352,13 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                         unsigned pm = __ballot_sync(FULL, pass);
                         if (pm) {                                           // rare after warm-up
                             uint64_t key = 0;
-                            if (pass) key = ((uint64_t)ord_f32((float)d) << 32)   // dot_i8 as f32: exact below 2^24
-                                            | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
-                            if (ceil_keys) {
-                                const uint64_t ceil = __ldg(&ceil_keys[blockIdx.y * NQ + q]);
-                                if (key >= ceil) key = 0;
+                            if (pass) {
+                                const uint32_t doc = doc_ids ? __ldg(&doc_ids[row]) : row;
+                                key = ((uint64_t)ord_f32((float)d) << 32) | (uint64_t)(0xFFFFFFFFu - doc);   // dot_i8 as f32: exact below 2^24
+                                if (doc_deleted(del_slot, del_words, doc)) key = 0;
+                            }
+                            if (ceil_keys || del_slot) {
+                                if (ceil_keys) { const uint64_t ceil = __ldg(&ceil_keys[blockIdx.y * NQ + q]); if (key >= ceil) key = 0; }
                                 pm = __ballot_sync(FULL, key != 0);
                                 if (!pm) continue;
                             }
@@ -441,10 +444,13 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     unsigned pm = __ballot_sync(FULL, pass);
                     if (pm) {                                           // rare after warm-up
                         uint64_t key = 0;
-                        if (pass) key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - (doc_ids ? __ldg(&doc_ids[row]) : row));
-                        if (ceil_keys) {   // paging: keys >= ceil were returned by an earlier page (0 = exhausted)
-                            const uint64_t ceil = __ldg(&ceil_keys[blockIdx.y * NQ + q]);
-                            if (key >= ceil) key = 0;
+                        if (pass) {
+                            const uint32_t doc = doc_ids ? __ldg(&doc_ids[row]) : row;
+                            key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - doc);
+                            if (doc_deleted(del_slot, del_words, doc)) key = 0;
+                        }
+                        if (ceil_keys || del_slot) {   // paging: keys >= ceil were returned by an earlier page (0 = exhausted)
+                            if (ceil_keys) { const uint64_t ceil = __ldg(&ceil_keys[blockIdx.y * NQ + q]); if (key >= ceil) key = 0; }
                             pm = __ballot_sync(FULL, key != 0);
                             if (!pm) continue;
                         }
@@ -587,7 +593,7 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     if (a.ev0) cudaEventRecord(a.ev0, st);
     tc::scan_tc<NQ, PREC, BRES><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmA2, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
                                                                              a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, nst,
-                                                                             a.sample_groupmax ? 1u : 0u);
+                                                                             a.del_slot, a.del_words, a.sample_groupmax ? 1u : 0u);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     if (a.sample_groupmax) {   // threshold seeding pass: scratch holds gmax[nq_pad][n_tiles * 8]
@@ -619,7 +625,8 @@ static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec
 
 int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int prec, cudaStream_t st) {
     // threshold pre-sampling (see vec_scan.cu): scan the first rows, seed the thresholds, then the full scan
-    if (a.thr_init || !a.thr_buf || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, prec, st);
+    // (with a delete set the sample pass is skipped: a deleted row must never seed a threshold)
+    if (a.thr_init || !a.thr_buf || a.del_slot || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, prec, st);
     ScanArgs pre = a;
     // The sample pass writes per-(32-row group, query) score maxima instead of lists (no insert storm) and costs the same for one
     // 256-row tile per CTA as for a handful of tiles: sample one tile per SM.  (An earlier version ran the normal list epilogue

@@ -225,6 +225,11 @@ class Index:
         """Collective: install the index-wide document frequencies (idf of the whole index on every shard)."""
         check(lib().ssb_lexical_sync_df(self._h))
 
+    def set_deleted(self, doc_ids):
+        """shard.delete_hashset: these docs are neither scored nor counted (lexical, vector, hybrid); [] clears the set."""
+        a = np.ascontiguousarray(np.asarray(list(doc_ids), dtype=np.uint64))
+        check(lib().ssb_set_deleted(self._h, a.ctypes.data if a.size else None, a.size))
+
     def add_vector_level(self, level_id: int, rows, local_ids=None):
         """rows: [n, dims] f32 (numpy or torch, host or device), n <= 65536."""
         n, dims = int(rows.shape[0]), int(rows.shape[1])

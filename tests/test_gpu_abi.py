@@ -270,3 +270,53 @@ def test_vector_multi_chunk_documents_are_deduplicated():
             assert [d for d, _ in got[i]] == [(3 << 16) | int(d) for d in order]
             assert np.allclose([s for _, s in got[i]], best[order], rtol=1e-4, atol=1e-5)
     ix.close()
+
+
+def test_delete_set_lexical_vector_hybrid():
+    """ssb_set_deleted (shard.delete_hashset): deleted docs are neither scored nor counted — lexical OR / AND incl. exact counts,
+    >4-term queries, vector scan (both kernels), hybrid; clearing the set restores the results."""
+    from seekstorm_b200 import Index, QueryType, ResultType, VectorSimilarity
+    n, dims = 140000, 48
+    lvs, ls = synth_levels(n, 3000, 51)
+    levels = [l.to_numpy() for l in lvs]
+    orc = oracle_index(levels, n, ls)
+    rows = synth.gen_vectors(n, dims, 52, "cpu").numpy()
+    ix = gpu_index(levels, n, ls, vector_dims=dims, vector_similarity=VectorSimilarity.Cosine)
+    ix.add_vectors(rows)
+    qk = query_keys(synth.gen_queries(60, 53, 2, 2500, (1, 2, 3, 4, 6), (0.1, 0.3, 0.3, 0.2, 0.1)))
+    qv = synth.gen_vectors(40, dims, 54, "cpu").numpy()
+    base_lex, _ = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
+    base_vec = ix.search_vector_batch(qv, 10)
+    # delete the current top hits of every query (forces new results) plus a random spread over all levels
+    rng = np.random.default_rng(55)
+    deleted = {d for r in base_lex for d, _ in r[:3]} | {d for r in base_vec for d, _ in r[:2]} | {int(x) for x in rng.integers(0, n, 3000)}
+    deleted = {((d >> 16) << 16) | (d & 0xFFFF) for d in deleted}
+    ix.set_deleted(sorted(deleted)); orc.set_deleted(sorted(deleted))
+    for qt, oqt in ((QueryType.Union, O.QUERY_UNION), (QueryType.Intersection, O.QUERY_INTERSECTION)):
+        got, cnt = ix.search_lexical_batch(qk, qt, 10, ResultType.TopkCount)
+        got_t, _ = ix.search_lexical_batch(qk, qt, 10, ResultType.Topk)
+        for i, k in enumerate(qk):
+            want, tot = orc.search(k, oqt, 10, O.RESULT_TOPKCOUNT)
+            if len(k) <= 4:
+                assert got[i] == want and got_t[i] == want, (i, k)
+            else:
+                assert [d for d, _ in got[i]] == [d for d, _ in want]
+            assert int(cnt[i]) == tot, (i, k, int(cnt[i]), tot)
+            assert not any(d in deleted for d, _ in got[i])
+    nrows = np.stack([O.normalize(r) for r in rows])
+    for kern in (1, 4):
+        ix.set_vector_kernel(kern)
+        got = ix.search_vector_batch(qv, 10)
+        for i in range(len(qv)):
+            want = [(d, s) for d, s in O.search_vector(nrows, O.normalize(qv[i]), 10 + len(deleted), O.SIM_COSINE) if d not in deleted][:10]
+            assert [d for d, _ in got[i]] == [d for d, _ in want]
+    ix.set_vector_kernel(0)
+    hyb = ix.search_hybrid_batch(qk[:20], QueryType.Union, qv[:20], 10)
+    for i in range(20):
+        lex, _ = orc.search(qk[i], O.QUERY_UNION, 10, O.RESULT_TOPK)
+        vec = [(d, s) for d, s in O.search_vector(nrows, O.normalize(qv[i]), 10 + len(deleted), O.SIM_COSINE) if d not in deleted][:10]
+        assert [d for d, _ in hyb[i]] == [d for d, _ in O.rrf(lex, vec)[:10]]
+    ix.set_deleted([])
+    again, _ = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
+    assert again == base_lex and ix.search_vector_batch(qv, 10) == base_vec
+    ix.close()
