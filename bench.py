@@ -292,6 +292,7 @@ def bench_vector(a, rank, world, out):
         init_shard_comm(ix)
     n_levels, mine = vector_levels(a.rows, rank, world)
     local_rows = 0
+    ix.reserve_vectors(sum(min(65536, a.rows - lv * 65536) for lv in mine))
     for lv in mine:
         r = gen_vector_level(lv, a.rows, a.dims, dev)
         ix.add_vector_level(lv, r)
@@ -346,6 +347,7 @@ def bench_vector_int8(a, rank, world):
         init_shard_comm(ix)
     n_levels, mine = vector_levels(a.rows, rank, world)
     local_rows = 0
+    ix.reserve_vectors(sum(min(65536, a.rows - lv * 65536) for lv in mine))
     for lv in mine:
         r = gen_vector_level(lv, a.rows, a.dims, dev)
         ix.add_vector_level(lv, r)
@@ -599,6 +601,7 @@ def _add_vector_levels(ix, n_rows, rank, world, dev, seed_base):
     from seekstorm_b200 import synth
     n_levels, mine = vector_levels(n_rows, rank, world)
     local = 0
+    ix.reserve_vectors(sum(min(65536, n_rows - lv * 65536) for lv in mine))
     for lv in mine:
         r = synth.gen_vectors(min(65536, n_rows - lv * 65536), C2_DIMS, seed_base * 1000 + lv, dev)
         ix.add_vector_level(lv, r)

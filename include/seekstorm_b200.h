@@ -160,6 +160,8 @@ int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n);
 int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride_floats,
                              const uint16_t* local_ids, uint32_t n, uint32_t dims);
 int32_t ssb_vector_count(const ssb_index* ix, uint64_t* n_rows);
+/* capacity hint: size the vector arenas for n_rows rows up front (loading level by level otherwise grows them geometrically) */
+int32_t ssb_vector_reserve(ssb_index* ix, uint64_t n_rows);
 /* switch the scan kernel (SSB_VEC_KERNEL_*) of an existing index */
 int32_t ssb_set_vector_kernel(ssb_index* ix, uint32_t vector_kernel);
 

@@ -453,6 +453,29 @@ int32_t ssb_lexical_set_global_df(ssb_index* ix, const uint64_t* keys, const uin
     SSB_API_END
 }
 
+// capacity hint: allocate the vector arenas for n_rows rows once instead of growing them level by level (growth = new
+// allocation + device copy of everything loaded so far)
+int32_t ssb_vector_reserve(ssb_index* ix, uint64_t n_rows) {
+    SSB_API_BEGIN
+    if (!ix) { set_error("null index"); return SSB_E_INVALID; }
+    if (ix->dims == 0) { set_error("no vector index configured (vector_dims = 0)"); return SSB_E_STATE; }
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    cudaStream_t st = ix->load_st;
+    if (n_rows <= ix->n_rows) return SSB_OK;
+    SSB_TRY(ix->doc_ids.reserve(n_rows, ix->n_rows, st, true));
+    if (ix->quant_i8) SSB_TRY(ix->rows_i8.reserve(n_rows * ix->dpad8, ix->n_rows * ix->dpad8, st, true));
+    else {
+        SSB_TRY(ix->rows.reserve(n_rows * ix->dpad, ix->n_rows * ix->dpad, st, true));
+        if (ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN) {
+            SSB_TRY(ix->rows_hi.reserve(n_rows * ix->dpad, ix->n_rows * ix->dpad, st, true));
+            SSB_TRY(ix->rows_lo.reserve(n_rows * ix->dpad, ix->n_rows * ix->dpad, st, true));
+        }
+    }
+    return SSB_OK;
+    SSB_API_END
+}
+
 int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride, const uint16_t* local_ids,
                              uint32_t n, uint32_t dims) {
     SSB_API_BEGIN

@@ -18,10 +18,11 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    int32_t reserve(size_t n, size_t used, cudaStream_t st) {
+    int32_t reserve(size_t n, size_t used, cudaStream_t st, bool exact = false) {
         if (n <= cap) return SSB_OK;
         size_t nc = cap ? cap : 1024;
         while (nc < n) nc += nc / 2 + 1024;
+        if (exact) nc = n;
         T* q = nullptr;
         cudaError_t e = cudaMalloc(&q, nc * sizeof(T));
         if (e != cudaSuccess) {

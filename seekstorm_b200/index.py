@@ -236,9 +236,14 @@ class Index:
         stride = rows.strides[0] // 4 if isinstance(rows, np.ndarray) else rows.stride(0)
         check(lib().ssb_vector_add_level(self._h, level_id, _addr(rows), stride, _addr(local_ids), n, dims))
 
+    def reserve_vectors(self, n_rows: int):
+        """Capacity hint (ssb_vector_reserve): one allocation for n_rows rows instead of geometric growth while loading."""
+        check(lib().ssb_vector_reserve(self._h, int(n_rows)))
+
     def add_vectors(self, rows, first_level: int = 0):
         """Split a big [N, dims] matrix into 64K-row levels (doc_id = row index when first_level = 0)."""
         n = int(rows.shape[0])
+        self.reserve_vectors(self.vector_count + n)
         for s in range(0, n, 65536):
             self.add_vector_level(first_level + s // 65536, rows[s:min(n, s + 65536)])
 

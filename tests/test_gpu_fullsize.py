@@ -169,6 +169,7 @@ def test_c4_full_size_hybrid_identity():
     n, d = 5_000_000, 768
     ix, orc = _build_full_lexical(n, 1004, vector_dims=d, vector_similarity=VectorSimilarity.Cosine)
     host_rows = np.empty((n, d), dtype=np.float32)
+    ix.reserve_vectors(n)
     for lv in range((n + 65535) // 65536):
         r = synth.gen_vectors(min(65536, n - lv * 65536), d, 1005 * 1000 + lv, "cuda")
         ix.add_vector_level(lv, r)
