@@ -1,10 +1,10 @@
 #!/bin/bash
 # usage: tools/gpurun_retry.sh <timeout_s> <logfile> <command...> — retries while the pod answers busy (exit code 3, nothing charged)
 T=$1; LOG=$2; shift 2
-for i in $(seq 1 40); do
+for i in $(seq 1 400); do
   /usr/local/graft/bin/gpurun --timeout $T -- "$@" > $LOG 2>&1
   rc=$?
   if [ $rc -ne 3 ]; then echo "gpurun rc=$rc (attempt $i)" >> $LOG; exit $rc; fi
-  sleep 120
+  sleep 45
 done
 exit 3
