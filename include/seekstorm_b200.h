@@ -49,9 +49,15 @@ enum { SSB_QUERY_UNION = 0, SSB_QUERY_INTERSECTION = 1 };
 enum { SSB_RESULT_COUNT = 0, SSB_RESULT_TOPK = 1, SSB_RESULT_TOPKCOUNT = 2 };
 /* VectorSimilarity (vector_similarity.rs:20-30) */
 enum { SSB_SIM_DOT = 0, SSB_SIM_COSINE = 1, SSB_SIM_EUCLIDEAN = 2 };
-/* Quantization (vector_similarity.rs `Quantization`): SCALAR_I8 = ScalarQuantizationI8 with Cosine similarity —
- * rows and queries are normalised, then quantised round(v*127) clamped to [-127,127] (vector_similarity.rs:1226-1232,
- * vector.rs:585-640); score = the exact int32 dot product as f32 (vector_similarity.rs:193-206, 1011-1016). */
+/* Quantization (vector_similarity.rs `Quantization`): SCALAR_I8 = ScalarQuantizationI8.
+ *   Cosine   : rows and queries are normalised, then quantised round(v*127) clamped to [-127,127] (vector_similarity.rs:1226-1232,
+ *              vector.rs:585-640); score = the exact int32 dot product as f32 (vector_similarity.rs:193-206, 1011-1016).
+ *   Dot      : per-vector scale = max|x|/127, codes round(x/scale) (QuantizedVector::new_scale, vector_similarity.rs:1340-1353);
+ *              score = dot_i32 as f32 * query_scale * row_scale (dot_i8_quantized, :1754-1758).
+ *   Euclidean: new_scale_norm (:1356-1371), the NON-AFFINE variant the reference uses for non-integer data (vector.rs:651-660);
+ *              score = -max(0, query_norm + row_norm - 2*dot) (euclidean_i8_quantized, :1721-1734).  Integer-valued 0..255 data
+ *              (affine quantisation) and TurboQuantI8 are not built: SSB_E_UNSUPPORTED.
+ * All three are bit-exact with the scalar CPU arithmetic (integer accumulation on tcgen05 kind::i8, reference operation order). */
 enum { SSB_QUANT_NONE = 0, SSB_QUANT_SCALAR_I8 = 1 };
 /* which vector scan kernel to use */
 /* FFMA: packed-FP32 scan, 16 queries per corpus pass (HBM-bound).  TCGEN05[_N64]: tensor-core scan with the 3xTF32

@@ -78,6 +78,9 @@ def lib():
         L.orc_dot_i8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_search_vector_i8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
                                            C.c_void_p, C.POINTER(C.c_uint32)]
+        L.orc_quantize_scale_i8.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.orc_search_vector_i8_scaled.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                  C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
         L.orc_rrf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                               C.POINTER(C.c_uint32)]
         _lib = L
@@ -186,6 +189,31 @@ def search_vector_i8(rows_i8: np.ndarray, query_i8: np.ndarray, k: int, doc_ids=
     n = C.c_uint32(0)
     rc = lib().orc_search_vector_i8(_ptr(rows_i8), None if ids is None else _ptr(ids), rows_i8.shape[0], rows_i8.shape[1],
                                     rows_i8.strides[0], _ptr(q), k, buf, C.byref(n))
+    assert rc == 0
+    return _hits_to_list(buf, n.value)
+
+
+def quantize_scale_rows_i8(rows: np.ndarray, want_norm: bool):
+    """QuantizedVector::new_scale / new_scale_norm per row -> (codes int8 [n, d], scale f32 [n], norm f32 [n])."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    n, d = rows.shape
+    out = np.zeros((n, d), dtype=np.int8); scale = np.zeros(n, dtype=np.float32); norm = np.zeros(n, dtype=np.float32)
+    s, nn = C.c_float(0), C.c_float(0)
+    for i in range(n):
+        lib().orc_quantize_scale_i8(_ptr(rows[i]), d, int(want_norm), _ptr(out[i]), C.byref(s), C.byref(nn))
+        scale[i], norm[i] = s.value, nn.value
+    return out, scale, norm
+
+
+def search_vector_i8_scaled(rows_i8, row_scale, row_norm, query_i8, q_scale, q_norm, similarity, k, doc_ids=None):
+    rows_i8 = np.ascontiguousarray(rows_i8, dtype=np.int8)
+    rs = np.ascontiguousarray(row_scale, dtype=np.float32); rn = np.ascontiguousarray(row_norm, dtype=np.float32)
+    q = np.ascontiguousarray(query_i8, dtype=np.int8)
+    ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint32)
+    buf = (OrcHit * max(k, 1))()
+    n = C.c_uint32(0)
+    rc = lib().orc_search_vector_i8_scaled(_ptr(rows_i8), _ptr(rs), _ptr(rn), None if ids is None else _ptr(ids), rows_i8.shape[0], rows_i8.shape[1],
+                                           rows_i8.strides[0], _ptr(q), C.c_float(q_scale), C.c_float(q_norm), similarity, k, buf, C.byref(n))
     assert rc == 0
     return _hits_to_list(buf, n.value)
 

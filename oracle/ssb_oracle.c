@@ -734,3 +734,42 @@ int orc_rrf(const orc_hit* lex, uint32_t n_lex, const orc_hit* vec, uint32_t n_v
     if (n_out) *n_out = n;
     return 0;
 }
+
+
+/* ---- Dot / Euclidean + ScalarQuantizationI8 (vector.rs:597-660, search.rs:1499-1530) ----
+ * QuantizedVector::new_scale / new_scale_norm (vector_similarity.rs:1340-1371): scale = max|x| / 127, codes = (x / scale).round() as i8
+ * (Rust `as i8` saturates, NaN -> 0), norm = sum(code^2) as f32 * scale * scale. */
+void orc_quantize_scale_i8(const float* v, uint32_t n, int want_norm, int8_t* out, float* scale_out, float* norm_out) {
+    float mx = 0.0f;
+    for (uint32_t i = 0; i < n; i++) { float a = fabsf(v[i]); if (a > mx) mx = a; }   /* fold(0.0, f32::max) */
+    volatile float scale = mx / 127.0f;
+    int32_t sum = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        volatile float q = v[i] / scale;
+        float r = roundf(q);
+        int8_t c = 0;
+        if (r == r) { if (r > 127.0f) r = 127.0f; if (r < -128.0f) r = -128.0f; c = (int8_t)r; }
+        out[i] = c; sum += (int32_t)c * (int32_t)c;
+    }
+    *scale_out = scale;
+    if (norm_out) { volatile float a = (float)sum * scale; volatile float b = a * scale; *norm_out = want_norm ? b : 0.0f; }
+}
+/* dot_i8_quantized (vector_similarity.rs:1754-1758) / -euclidean_i8_quantized (:1721-1734), query = v1 */
+float orc_score_i8_scaled(const int8_t* q, float q_scale, float q_norm, const int8_t* e, float e_scale, float e_norm, uint32_t n, uint32_t similarity) {
+    int32_t dot = orc_dot_i8(q, e, n);
+    volatile float a = (float)dot * q_scale; volatile float d = a * e_scale;
+    if (similarity != ORC_SIM_EUCLIDEAN) return d;
+    volatile float s = q_norm + e_norm; volatile float t = 2.0f * d; volatile float r = s - t;
+    return -(r > 0.0f ? r : 0.0f);
+}
+int orc_search_vector_i8_scaled(const int8_t* rows, const float* row_scale, const float* row_norm, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims,
+                                uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm, uint32_t similarity, uint32_t k,
+                                orc_hit* hits, uint32_t* n_hits) {
+    topk_t tk = { hits, 0, k };
+    for (uint64_t r = 0; r < n_rows; r++) {
+        float s = orc_score_i8_scaled(query, q_scale, q_norm, rows + r * row_pitch, row_scale[r], row_norm ? row_norm[r] : 0.0f, dims, similarity);
+        topk_push(&tk, doc_ids ? doc_ids[r] : r, s);
+    }
+    if (n_hits) *n_hits = tk.n;
+    return 0;
+}

@@ -108,6 +108,14 @@ int32_t orc_dot_i8(const int8_t* a, const int8_t* b, uint32_t n);
 int orc_search_vector_i8(const int8_t* rows, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims, uint32_t row_pitch,
                          const int8_t* query, uint32_t k, orc_hit* hits, uint32_t* n_hits);
 
+/* Dot / Euclidean + ScalarQuantizationI8: QuantizedVector::new_scale / new_scale_norm (vector_similarity.rs:1340-1371),
+ * dot_i8_quantized (:1754-1758), -euclidean_i8_quantized (:1721-1734; the non-affine variant, vector.rs:651-660) */
+void  orc_quantize_scale_i8(const float* v, uint32_t n, int want_norm, int8_t* out, float* scale_out, float* norm_out);
+float orc_score_i8_scaled(const int8_t* q, float q_scale, float q_norm, const int8_t* e, float e_scale, float e_norm, uint32_t n, uint32_t similarity);
+int   orc_search_vector_i8_scaled(const int8_t* rows, const float* row_scale, const float* row_norm, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims,
+                                  uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm, uint32_t similarity, uint32_t k,
+                                  orc_hit* hits, uint32_t* n_hits);
+
 /* ---- hybrid: search.rs:1962-2035 RRF k=0.6, rank from 0; then sort score desc (:2097-2121).
  * Tie order in the reference is hash-map iteration order; canonical here: doc id asc. */
 int orc_rrf(const orc_hit* lex, uint32_t n_lex, const orc_hit* vec, uint32_t n_vec,

@@ -73,7 +73,7 @@ struct SearchCtx {
     cudaStream_t st = nullptr;       // stream this context launches on (its own, or the caller's after ssb_set_stream)
     cudaStream_t own_st = nullptr;
     LexWorkspace lex;
-    DevBuf<float> qpad, qstage, qhi, qlo; DevBuf<int8_t> q_i8;
+    DevBuf<float> qpad, qstage, qhi, qlo, q_scale, q_norm; DevBuf<int8_t> q_i8;
     DevBuf<uint64_t> ceil, scratch, keys_a, keys_b, counts, gather;
     std::vector<uint64_t> h_ceil, h_keys_a, h_keys_b, h_counts;
     ssb_stats stats{};
@@ -108,6 +108,7 @@ struct ssb_index {
     DevBuf<float> rows;
     DevBuf<uint16_t> rows_hi, rows_lo;   // bf16 planes of `rows` (hi = bf16_rn(x), lo = bf16_rn(x - hi)): what the tcgen05 bf16 scan streams
     DevBuf<int8_t> rows_i8;
+    DevBuf<float> row_scale, row_norm;   // Dot / Euclidean + ScalarQuantizationI8: per-vector scale (and norm), QuantizedVector vector_similarity.rs:1340-1371
     DevBuf<uint32_t> doc_ids;
     uint64_t n_rows = 0;
 };
@@ -172,7 +173,7 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     uint32_t kern = ix->cfg.vector_kernel;
     if (ix->quant_i8) kern = SSB_VEC_KERNEL_TCGEN05;   // one kernel for the int8 corpus: tcgen05 kind::i8, 128-query tile
     if (kern == SSB_VEC_KERNEL_AUTO) kern = nq > 16 ? SSB_VEC_KERNEL_TCGEN05_BF16 : SSB_VEC_KERNEL_FFMA;
-    const bool use_tc = kern >= SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN;
+    const bool use_tc = ix->quant_i8 || (kern >= SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN);   // the int8 index is always scanned on the tensor cores
     const bool tc_bf16 = kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64;
     const uint32_t qt = !use_tc ? vec::VEC_QT : ((kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : 128u);
     const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
@@ -188,7 +189,13 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     }
     if (ix->quant_i8) {
         SSB_TRY(c.q_i8.reserve((size_t)nq_pad * ix->dpad8, 0, st));
-        if (queries_i8) {
+        if (queries_i8 && ix->cfg.vector_similarity != SSB_SIM_COSINE) { set_error("int8 query codes are accepted for Cosine + ScalarQuantizationI8 only (Dot / Euclidean need the query scale)"); return SSB_E_UNSUPPORTED; }
+        if (ix->cfg.vector_similarity != SSB_SIM_COSINE) {
+            // Dot / Euclidean: the query goes through the same QuantizedVector::new_scale[_norm] as the rows (search.rs:1499-1530)
+            SSB_TRY(c.q_scale.reserve(nq_pad, 0, st)); SSB_TRY(c.q_norm.reserve(nq_pad, 0, st));
+            SSB_TRY(vec::launch_quantize_rows_scale_i8((const float*)qsrc, ix->dims, nq, nq_pad, ix->dims, c.q_i8.p, ix->dpad8, c.q_scale.p, c.q_norm.p,
+                                                       ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN, st));
+        } else if (queries_i8) {
             // the caller already ran normalize + quantize_f32_to_i8 (what the reference's server holds after search.rs:1477-1490): pad only
             SSB_CUDA_TRY(cudaMemsetAsync(c.q_i8.p, 0, (size_t)nq_pad * ix->dpad8, st));
             SSB_CUDA_TRY(cudaMemcpy2DAsync(c.q_i8.p, ix->dpad8, qsrc, ix->dims, ix->dims, nq, cudaMemcpyDeviceToDevice, st));
@@ -221,6 +228,10 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     a.launches = &c.stats.kernel_launches;
     if (ix->quant_i8) {
         a.rows_i8 = ix->rows_i8.p; a.queries_i8 = c.q_i8.p; a.dpad8 = ix->dpad8;
+        if (ix->cfg.vector_similarity != SSB_SIM_COSINE) {
+            a.i8_scaled = ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN ? 2 : 1;
+            a.row_scale = ix->row_scale.p; a.row_norm = ix->row_norm.p; a.q_scale = c.q_scale.p; a.q_norm = c.q_norm.p;
+        }
         SSB_TRY(vec::launch_scan_tc(a, 128, 2, st));
     } else if (use_tc) {
         SSB_TRY(c.qhi.reserve((size_t)nq_pad * ix->dpad, 0, st));
@@ -378,10 +389,6 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     if (cfg->device < 0 || cfg->device >= ndev) { set_error("device %d out of range (%d visible)", cfg->device, ndev); return SSB_E_INVALID; }
     if (cfg->vector_similarity > SSB_SIM_EUCLIDEAN) { set_error("bad vector_similarity"); return SSB_E_INVALID; }
     if (cfg->vector_quantization > SSB_QUANT_SCALAR_I8) { set_error("bad vector_quantization"); return SSB_E_INVALID; }
-    if (cfg->vector_quantization == SSB_QUANT_SCALAR_I8 && cfg->vector_similarity != SSB_SIM_COSINE) {
-        // Dot / Euclidean + SQ carry per-vector scale / zero point (vector.rs:597-660): not built
-        set_error("ScalarQuantizationI8 is built for Cosine similarity only"); return SSB_E_UNSUPPORTED;
-    }
     SSB_CUDA_TRY(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
     SSB_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
@@ -415,7 +422,7 @@ int32_t ssb_destroy(ssb_index* ix) {
         delete ix->lex; ix->lex = nullptr;
         comm_destroy(ix->comm);
         ix->del.release();
-        ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->doc_ids.release();
+        ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->row_scale.release(); ix->row_norm.release(); ix->doc_ids.release();
         cudaStreamDestroy(ix->load_st);
     }
     delete ix;
@@ -464,8 +471,10 @@ int32_t ssb_vector_reserve(ssb_index* ix, uint64_t n_rows) {
     cudaStream_t st = ix->load_st;
     if (n_rows <= ix->n_rows) return SSB_OK;
     SSB_TRY(ix->doc_ids.reserve(n_rows, ix->n_rows, st, true));
-    if (ix->quant_i8) SSB_TRY(ix->rows_i8.reserve(n_rows * ix->dpad8, ix->n_rows * ix->dpad8, st, true));
-    else {
+    if (ix->quant_i8) {
+        SSB_TRY(ix->rows_i8.reserve(n_rows * ix->dpad8, ix->n_rows * ix->dpad8, st, true));
+        if (ix->cfg.vector_similarity != SSB_SIM_COSINE) { SSB_TRY(ix->row_scale.reserve(n_rows, ix->n_rows, st, true)); SSB_TRY(ix->row_norm.reserve(n_rows, ix->n_rows, st, true)); }
+    } else {
         SSB_TRY(ix->rows.reserve(n_rows * ix->dpad, ix->n_rows * ix->dpad, st, true));
         if (ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN) {
             SSB_TRY(ix->rows_hi.reserve(n_rows * ix->dpad, ix->n_rows * ix->dpad, st, true));
@@ -508,7 +517,25 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
         SSB_TRY(ix->rows_i8.reserve((ix->n_rows + n) * ix->dpad8, ix->n_rows * ix->dpad8, st));
         SSB_CUDA_TRY(stage.alloc((size_t)n * dims));
         SSB_CUDA_TRY(cudaMemcpy2DAsync(stage.p, (size_t)dims * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, st));
-        SSB_TRY(vec::launch_quantize_rows_i8(stage.p, dims, n, n, dims, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8, st));
+        if (ix->cfg.vector_similarity == SSB_SIM_COSINE)
+            SSB_TRY(vec::launch_quantize_rows_i8(stage.p, dims, n, n, dims, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8, st));
+        else {
+            // Dot: QuantizedVector::new_scale; Euclidean: new_scale_norm — the NON-AFFINE variant the reference picks when the first
+            // vector is not all integers in 0..255 (vector.rs:651-660); integer-valued data (affine quantisation) is not built
+            if (ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN && ix->n_rows == 0) {
+                std::vector<float> first(dims);
+                SSB_CUDA_TRY(cudaMemcpyAsync(first.data(), stage.p, (size_t)dims * 4, cudaMemcpyDeviceToHost, st));
+                SSB_CUDA_TRY(cudaStreamSynchronize(st));
+                bool non_affine = false;
+                for (float x : first) non_affine = non_affine || x != floorf(x) || x < 0.0f || x > 255.0f;
+                if (!non_affine) { set_error("Euclidean + ScalarQuantizationI8 over integer-valued 0..255 data uses the reference's affine quantisation, which is not built"); return SSB_E_UNSUPPORTED; }
+            }
+            SSB_TRY(ix->row_scale.reserve(ix->n_rows + n, ix->n_rows, st));
+            SSB_TRY(ix->row_norm.reserve(ix->n_rows + n, ix->n_rows, st));
+            SSB_TRY(vec::launch_quantize_rows_scale_i8(stage.p, dims, n, n, dims, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8,
+                                                       ix->row_scale.p + ix->n_rows, ix->row_norm.p + ix->n_rows,
+                                                       ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN, st));
+        }
     } else {
         SSB_TRY(ix->rows.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, st));
         float* dst = ix->rows.p + ix->n_rows * ix->dpad;

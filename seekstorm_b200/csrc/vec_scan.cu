@@ -311,6 +311,37 @@ __global__ void quantize_rows_i8(const float* __restrict__ src, uint64_t src_str
     }
 }
 
+// Dot / Euclidean + ScalarQuantizationI8: QuantizedVector::new_scale / new_scale_norm (vector_similarity.rs:1340-1371).  One warp per row.
+__global__ void quantize_rows_scale_i8(const float* __restrict__ src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims,
+                                       int8_t* __restrict__ dst, uint32_t dpad8, float* __restrict__ scale_out, float* __restrict__ norm_out, int want_norm) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_out) return;
+    int8_t* o = dst + row * dpad8;
+    if (row >= n) { for (uint32_t i = lane; i < dpad8; i += 32) o[i] = 0; if (lane == 0) { scale_out[row] = 0.f; if (norm_out) norm_out[row] = 0.f; } return; }
+    const float* r = src + row * src_stride;
+    float mx = 0.0f;                                            // values.iter().map(|x| x.abs()).fold(0.0, f32::max): NaN is ignored by f32::max
+    for (uint32_t i = lane; i < dims; i += 32) mx = fmaxf(mx, fabsf(r[i]));
+    for (int m = 16; m; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, m));
+    const float scale = __fdiv_rn(mx, 127.0f);
+    int sum = 0;
+    for (uint32_t i = lane; i < dpad8; i += 32) {
+        int8_t q = 0;
+        if (i < dims) {
+            float x = roundf(__fdiv_rn(r[i], scale));         // Rust f32::round: half away from zero; `as i8` saturates, NaN -> 0
+            x = fminf(fmaxf(x, -128.0f), 127.0f);
+            q = x == x ? (int8_t)x : (int8_t)0;
+        }
+        o[i] = q;
+        sum += (int)q * (int)q;
+    }
+    for (int m = 16; m; m >>= 1) sum += __shfl_xor_sync(FULL, sum, m);
+    if (lane == 0) {
+        scale_out[row] = scale;
+        if (norm_out) norm_out[row] = want_norm ? __fmul_rn(__fmul_rn((float)sum, scale), scale) : 0.0f;
+    }
+}
+
 __global__ void fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (level_id << 16) | (local_ids ? (uint32_t)local_ids[i] : i);
@@ -409,6 +440,14 @@ int32_t launch_quantize_rows_i8(const float* src, uint64_t src_stride, uint64_t 
                                 uint32_t dpad8, cudaStream_t st) {
     if (n_out == 0) return SSB_OK;
     quantize_rows_i8<<<(unsigned)((n_out + 7) / 8), 256, 0, st>>>(src, src_stride, n, n_out, dims, dst, dpad8);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_quantize_rows_scale_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, int8_t* dst,
+                                      uint32_t dpad8, float* scale_out, float* norm_out, int want_norm, cudaStream_t st) {
+    if (n_out == 0) return SSB_OK;
+    quantize_rows_scale_i8<<<(unsigned)((n_out + 7) / 8), 256, 0, st>>>(src, src_stride, n, n_out, dims, dst, dpad8, scale_out, norm_out, want_norm);
     SSB_CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

@@ -32,6 +32,9 @@ struct ScanArgs {
     const int8_t* rows_i8 = nullptr;               // int8 path: [n_rows][dpad8] quantised corpus
     const int8_t* queries_i8 = nullptr;            //            [nq_pad][dpad8] quantised queries
     uint32_t dpad8 = 0;                            //            multiple of 128
+    int i8_scaled = 0;                             // int8 path: 0 = Cosine SQ (plain int32 dot), 1 = Dot SQ (per-vector scales), 2 = Euclidean SQ non-affine (+ norms)
+    const float* row_scale = nullptr; const float* row_norm = nullptr;   // [n_rows]
+    const float* q_scale = nullptr; const float* q_norm = nullptr;       // [nq_pad]
     const uint32_t* del_slot = nullptr; const uint64_t* del_words = nullptr;   // delete set (null = none): deleted docs never enter a list
     bool sample_groupmax = false;                  // internal (int8): threshold-seeding pass, writes thr_buf instead of lists
 };
@@ -68,6 +71,10 @@ int32_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dims, uint64_t
 // f32 rows -> normalize_f32 + quantize_f32_to_i8 (bit-identical to the reference's scalar arithmetic); rows >= n are zero
 int32_t launch_quantize_rows_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, int8_t* dst,
                                 uint32_t dpad8, cudaStream_t st);
+// QuantizedVector::new_scale / new_scale_norm (vector_similarity.rs:1340-1371): scale = max|x| / 127, codes = round(x / scale) as i8,
+// norm = sum(code^2) as f32 * scale * scale (want_norm).  Every step is order-independent (max, exact integer sum): bit-identical to the CPU.
+int32_t launch_quantize_rows_scale_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, int8_t* dst,
+                                      uint32_t dpad8, float* scale_out, float* norm_out, int want_norm, cudaStream_t st);
 int32_t launch_normalize_rows(float* rows, uint64_t n, uint32_t dims, uint32_t dpad, int normalize, cudaStream_t st);
 int32_t launch_fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n, cudaStream_t st);
 // in: [n_lists][nq][32] descending lists -> out [nq][32]

@@ -68,7 +68,7 @@ template <int NQ, int PREC, bool BRES = false> struct Cfg {
     // so the per-stage L2->SM traffic is the corpus tile alone (stage count chosen at launch from what is left of 227 KB)
     static constexpr int STAGE_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : (PREC == PREC_BF16 ? A_BYTES + 2 * B_BYTES : 2 * A_BYTES + 2 * B_BYTES));
     static constexpr int TX_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : A_BYTES + 2 * B_BYTES);
-    static constexpr int SMEM = STAGES * STAGE_BYTES + NQ * 4 + 256;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + NQ * 12 + 256;   // thresholds + (scaled int8) per-query scale / norm
     static constexpr int TMEM_COLS = 2 * MT * NQ;                              // double-buffered MT accumulators
 };
 
@@ -114,7 +114,10 @@ __device__ __forceinline__ int ord_to_int(uint32_t o) {
     return o == 0u ? INT_MIN : (o == 0xFFFFFFFFu ? INT_MAX : (int)unord_f32(o));
 }
 
-template <int NQ, int PREC, bool BRES>
+// SCALED (int8 only): 0 = Cosine + ScalarQuantizationI8 (score = the int32 dot product); 1 = Dot + ScalarQuantizationI8 (per-vector
+// scale, score = dot_i32 as f32 * query_scale * row_scale, dot_i8_quantized vector_similarity.rs:1754-1758); 2 = Euclidean +
+// ScalarQuantizationI8, non-affine (score = -max(0, query_norm + row_norm - 2*dot), euclidean_i8_quantized :1721-1734)
+template <int NQ, int PREC, bool BRES, int SCALED>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2 /*bf16: lo plane*/,
         const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_tiles, uint32_t k,
@@ -122,6 +125,8 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         const uint32_t* __restrict__ thr_init /*[gridDim.y*NQ] or null*/, uint32_t nq_valid,
         const uint64_t* __restrict__ ceil_keys /*[gridDim.y*NQ] or null*/, uint32_t nst_rt,
         const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words /*delete set or null*/,
+        const float* __restrict__ row_scale, const float* __restrict__ row_norm /*SCALED: [n_rows]*/,
+        const float* __restrict__ q_scale, const float* __restrict__ q_norm /*SCALED: [gridDim.y*NQ]*/,
         uint32_t sample_mode /*int8 only: write per-(32-row group, query) score maxima instead of lists*/) {
     using C = Cfg<NQ, PREC, BRES>;
     const uint32_t STAGES = BRES ? nst_rt : (uint32_t)C::STAGES;
@@ -134,7 +139,9 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     uint64_t* lists = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 * NQ * LIST;   // [4 epilogue warps][NQ][32]
     uint8_t* bres = base + STAGES * C::STAGE_BYTES;                           // BRES: resident query block
     uint32_t* thr_u = (uint32_t*)(bres + (BRES ? n_kchunks * C::B_BYTES : 0)); // [NQ] ordered-uint score thresholds
-    uint64_t* bars = (uint64_t*)(thr_u + NQ);
+    float* qs_sm = (float*)(thr_u + NQ);          // [NQ] SCALED: query scale
+    float* qn_sm = qs_sm + NQ;                    // [NQ] SCALED: query norm
+    uint64_t* bars = (uint64_t*)(thr_u + 3 * NQ);
     uint64_t* full = bars;                     // [STAGES]
     uint64_t* split = full + MAX_STAGES;       // [STAGES]
     uint64_t* empty = split + MAX_STAGES;      // [STAGES]
@@ -149,14 +156,15 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     if (threadIdx.x == 0) {
         mbar_init(bfull, 1);
         for (uint32_t s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&split[s], SPLIT_THREADS / 32); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PREC == PREC_I8 ? 12 : 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], (PREC == PREC_I8 && !SCALED) ? 12 : 4); }
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < NQ; i += THREADS) {  // seeded by the pre-sample pass when present
         uint32_t t = blockIdx.y * NQ + i >= nq_valid ? 0xFFFFFFFFu   // zero-padded query slot: unreachable threshold
                                                      : (thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u);
-        if (PREC == PREC_I8) t = (uint32_t)ord_to_int(t);            // int8 path compares the raw int32 dot products
+        if (PREC == PREC_I8 && !SCALED) t = (uint32_t)ord_to_int(t);   // unscaled int8 path compares the raw int32 dot products
         thr_u[i] = t;
+        if (SCALED) { qs_sm[i] = __ldg(&q_scale[blockIdx.y * NQ + i]); qn_sm[i] = SCALED == 2 ? __ldg(&q_norm[blockIdx.y * NQ + i]) : 0.f; }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
@@ -284,7 +292,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 if (lane == 0) mbar_arrive(&split[s]);
             }
         }
-    } else if (warp >= 4 && PREC == PREC_I8) {
+    } else if (warp >= 4 && PREC == PREC_I8 && !SCALED) {
         // ===================== int8 epilogue: 12 warps = 4 TMEM lane quadrants x 3 query-column groups =====================
         // With the int8 operands the MMA + smem side of a 128-query pass costs a fraction of the HBM time, so the epilogue
         // (one compare + ballot per (row, query) pair) is what has to keep up: the 8 warps that are splitters in the f32
@@ -408,6 +416,18 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                              : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (SCALED) {
+                    // scaled int8: the accumulators are exact int32 dot products; the score is rebuilt with the reference's
+                    // operation order so that it is bit-identical to the CPU path, then treated like an f32 score below
+                    const float rs = valid ? __ldg(&row_scale[row]) : 0.f;
+                    const float rn = (SCALED == 2 && valid) ? __ldg(&row_norm[row]) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < CHUNK; j++) {
+                        const float dotf = __fmul_rn(__fmul_rn((float)(int)v[j], qs_sm[c * CHUNK + j]), rs);
+                        const float sc = SCALED == 2 ? -fmaxf(__fsub_rn(__fadd_rn(qn_sm[c * CHUNK + j], rn), __fmul_rn(2.0f, dotf)), 0.0f) : dotf;
+                        v[j] = __float_as_uint(sc);
+                    }
+                }
                 if (sample_mode) {
                     uint32_t keep = 0;
 #pragma unroll
@@ -547,7 +567,7 @@ __global__ void kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, u
 
 }  // namespace tc
 
-template <int NQ, int PREC, bool BRES = false>
+template <int NQ, int PREC, bool BRES = false, int SCALED = 0>
 static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     using C = tc::Cfg<NQ, PREC, BRES>;
     CUtensorMap tmA, tmA2, tmBh, tmBl;
@@ -582,23 +602,24 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     uint32_t nst = C::STAGES;
     int smem = C::SMEM;
     if (BRES) {   // resident query block + as many corpus stages as fit (launch_scan_tc_impl guarantees >= 3)
-        const int fixed = (int)n_kchunks * C::B_BYTES + NQ * 4 + 256;
+        const int fixed = (int)n_kchunks * C::B_BYTES + NQ * 12 + 256;
         nst = (uint32_t)((SMEM_MAX - fixed) / C::STAGE_BYTES);
         if (nst > (uint32_t)tc::MAX_STAGES) nst = tc::MAX_STAGES;
         smem = fixed + (int)nst * C::STAGE_BYTES;
     }
     // per launch, not once per process: the opt-in applies to the CURRENT device's context only (ssb_config.device allows
     // several indexes on different GPUs in one process); the call is a cheap host-side attribute write
-    SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ, PREC, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRES ? SMEM_MAX : C::SMEM));
+    SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc<NQ, PREC, BRES, SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRES ? SMEM_MAX : C::SMEM));
     if (a.ev0) cudaEventRecord(a.ev0, st);
-    tc::scan_tc<NQ, PREC, BRES><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmA2, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
+    tc::scan_tc<NQ, PREC, BRES, SCALED><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmA2, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
                                                                              a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, nst,
-                                                                             a.del_slot, a.del_words, a.sample_groupmax ? 1u : 0u);
+                                                                             a.del_slot, a.del_words, a.row_scale, a.row_norm, a.q_scale, a.q_norm,
+                                                                             a.sample_groupmax ? 1u : 0u);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     if (a.sample_groupmax) {   // threshold seeding pass: scratch holds gmax[nq_pad][n_tiles * 8]
         tc::kth_from_groupmax<<<(a.nq_pad + 7) / 8, 256, 0, st>>>((const int*)a.scratch, n_tiles * (tc::MT * 4), a.nq_pad, a.k, a.thr_buf,
-                                                                      PREC == tc::PREC_I8 ? 1 : 0);
+                                                                      (PREC == tc::PREC_I8 && !SCALED) ? 1 : 0);
         SSB_CUDA_TRY(cudaGetLastError());
         if (a.launches) *a.launches += PREC == tc::PREC_TF32 ? 3 : 2;   // (tf32 query split +) scan + kth
         return SSB_OK;
@@ -615,6 +636,11 @@ static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec
     if (prec == 2) {
         if (nq_tile != 128 || a.nq_pad % 128 != 0 || !a.rows_i8 || !a.queries_i8 || a.dpad8 % 128) { set_error("int8 scan: bad arguments"); return SSB_E_INVALID; }
         // query block resident in smem when it leaves room for >= 3 corpus stages (dims <= 1024), else streamed per stage
+        if (a.i8_scaled) {
+            if (!a.row_scale || !a.q_scale || (a.i8_scaled == 2 && (!a.row_norm || !a.q_norm))) { set_error("scaled int8 scan: missing scale / norm arrays"); return SSB_E_INVALID; }
+            if (a.i8_scaled == 1) return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true, 1>(a, st) : launch_tc_n<128, tc::PREC_I8, false, 1>(a, st);
+            return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true, 2>(a, st) : launch_tc_n<128, tc::PREC_I8, false, 2>(a, st);
+        }
         return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true>(a, st) : launch_tc_n<128, tc::PREC_I8, false>(a, st);
     }
     if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }

@@ -287,9 +287,37 @@ def test_vector_int8_config_errors():
     from seekstorm_b200 import Index, VectorSimilarity
     from seekstorm_b200._lib import SsbError
     with pytest.raises(SsbError):
-        Index(0, vector_dims=64, vector_similarity=VectorSimilarity.Dot, vector_quantization=1)
-    with pytest.raises(SsbError):
         Index(0, vector_dims=64, vector_quantization=7)
+    # Euclidean + SQ over integer-valued 0..255 data would take the reference's affine quantisation: not built, fails loudly
+    ix = Index(0, vector_dims=8, vector_similarity=VectorSimilarity.Euclidean, vector_quantization=1)
+    with pytest.raises(SsbError, match="affine"):
+        ix.add_vectors(np.arange(16, dtype=np.float32).reshape(2, 8))
+    ix.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sim", ["dot", "euc"])
+@pytest.mark.parametrize("n,dims", [(300, 100), (5000, 128), (70000, 200), (3000, 1100)])
+def test_vector_int8_scaled_parity(n, dims, sim):
+    """Dot / Euclidean + ScalarQuantizationI8 (per-vector scale [+ norm], vector.rs:597-660): tcgen05 kind::i8 scan with the scaled
+    epilogue, BIT-EXACT ids and scores vs the oracle (QuantizedVector::new_scale[_norm], dot_i8_quantized / euclidean_i8_quantized)."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    simv, osim = (VectorSimilarity.Dot, O.SIM_DOT) if sim == "dot" else (VectorSimilarity.Euclidean, O.SIM_EUCLIDEAN)
+    rows = synth.gen_vectors(n, dims, 7000 + n, "cpu").numpy() * np.float32(0.37)
+    qs = synth.gen_vectors(40, dims, 8000 + n, "cpu").numpy()
+    qs[3] = rows[n // 2] + 0.01 * qs[3]
+    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_quantization=1)
+    ix.add_vectors(rows)
+    rc, rs, rn = O.quantize_scale_rows_i8(rows, sim == "euc")
+    qc, qsc, qn = O.quantize_scale_rows_i8(qs, sim == "euc")
+    for k in (1, 10, 32, 50):
+        got = ix.search_vector_batch(qs, k)
+        for i in range(0, len(qs), 3):
+            want = O.search_vector_i8_scaled(rc, rs, rn, qc[i], float(qsc[i]), float(qn[i]), osim, k)
+            assert [d for d, _ in got[i]] == [d for d, _ in want], (i, k, got[i][:3], want[:3])
+            assert [np.float32(s) for _, s in got[i]] == [np.float32(s) for _, s in want]
+    assert ix.search_vector_batch(qs[3:4], 1)[0][0][0] == n // 2
+    ix.close()
 
 
 @pytest.mark.gpu
