@@ -36,6 +36,7 @@
 
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
@@ -201,7 +202,8 @@ __device__ __forceinline__ uint32_t meta_cperm(uint32_t m, uint32_t c) { return 
 // 128-byte record.  Thread 0 finally cuts the sorted record list into work items.
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
                                                 uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
-                                                uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2) {
+                                                uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2,
+                                                uint32_t item_w, uint32_t first_lim, uint32_t gmax) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     float* bound = (float*)sm_raw;                                     // [n_levels]
     uint32_t* cnt = (uint32_t*)(bound + v.n_levels);                   // [n_levels]; after the sort: item weights by sorted position
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         LvRec r;
         r.docbase = v.level_ids[lv] << 16; r.bound = bound[lv]; r.lv = lv;
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0; float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
-        uint32_t weight = ITEM_W;
+        uint32_t weight = item_w;
         uint32_t meta = 0;
 #pragma unroll
         for (uint32_t s = 0; s < FAST_T; s++) {
@@ -363,9 +365,9 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         uint32_t ni = 0, acc = 0, nin = 0;
         is[0] = 0;
         for (uint32_t j = 0; j < nv; j++) {
-            const uint32_t lim = ni == 0 ? 2u : GMAX;
+            const uint32_t lim = ni == 0 ? first_lim : gmax;
             const uint32_t w = cnt[j] + 64u;
-            if (nin > 0 && (nin >= lim || acc + w > ITEM_W)) { ni++; is[ni] = (uint16_t)j; acc = 0; nin = 0; }
+            if (nin > 0 && (nin >= lim || acc + w > item_w)) { ni++; is[ni] = (uint16_t)j; acc = 0; nin = 0; }
             acc += w; nin++;
         }
         if (nv) { ni++; is[ni] = (uint16_t)nv; }
@@ -1025,6 +1027,13 @@ void LexWorkspace::release() {
     qoff = nullptr; qkeys = nullptr; stats = nullptr; cap_q = cap_terms = cap_levels = 0;
 }
 
+static uint32_t env_u32(const char* name, uint32_t dflt, uint32_t lo, uint32_t hi) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    long v = strtol(e, nullptr, 10);
+    return v < (long)lo ? lo : (v > (long)hi ? hi : (uint32_t)v);
+}
+
 static bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1340,7 +1349,11 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     // keys_out_dev doubles as the per-query global list (32 u64 per query); copy_out masks the entries >= k afterwards
     uint64_t* glist = keys_out_dev;
     if (plan_smem > 48 * 1024) SSB_CUDA_TRY(cudaFuncSetAttribute(lex_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
-    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2);
+    // item shape (tunable for experiments; defaults measured on C3): target postings per item, levels of a query's first item, levels per item
+    static const uint32_t item_w = env_u32("SSB_LEX_ITEM_W", ITEM_W, 64, 1u << 20), first_lim = env_u32("SSB_LEX_FIRST", 2, 1, GMAX),
+                          gmax = env_u32("SSB_LEX_GMAX", GMAX, 1, GMAX), grid_mult = env_u32("SSB_LEX_GRID", SSB_LEX_MINB, 1, 16);
+    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
+                                         item_w, first_lim, gmax);
     SSB_CUDA_TRY(cudaGetLastError());
     const bool is_and = q->query_type == SSB_QUERY_INTERSECTION;
     const bool want_topk = result_type != SSB_RESULT_COUNT && k > 0;
@@ -1348,7 +1361,7 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     const uint32_t kk = k ? k : 1;
     if (ws.ev0) cudaEventRecord(ws.ev0, st);
     if (want_topk) {
-        const int grid = n_sms_ * SSB_LEX_MINB;
+        const int grid = n_sms_ * (int)grid_mult;
         if (is_and) lex_score<true><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev);
         else lex_score<false><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev);
         SSB_CUDA_TRY(cudaGetLastError());

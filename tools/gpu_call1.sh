@@ -34,3 +34,18 @@ for n in ("base", "gm"):
         d = json.load(open(f"gpurun_out/c1_ffma_{n}.json")); print(n, d["value"], d["batch_sweep_e2e"], d["roofline"]["frac"])
     except Exception as e: print(n, "parse", e)
 PY
+# item-shape sweep of the BM25 engine (env knobs read once per process)
+for W in 1024 2048 8192 16384; do
+  SSB_LEX_ITEM_W=$W timeout 400 python bench.py --sections bm25 --rows 65536 --cpu-seconds 0 --steps 6 > gpurun_out/c1_bm25_w$W.json 2> gpurun_out/c1_bm25_w$W.err
+done
+for G in 2 4; do
+  SSB_LEX_GRID=$G timeout 400 python bench.py --sections bm25 --rows 65536 --cpu-seconds 0 --steps 6 > gpurun_out/c1_bm25_g$G.json 2> gpurun_out/c1_bm25_g$G.err
+done
+SSB_LEX_FIRST=1 timeout 400 python bench.py --sections bm25 --rows 65536 --cpu-seconds 0 --steps 6 > gpurun_out/c1_bm25_f1.json 2> gpurun_out/c1_bm25_f1.err
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/c1_bm25_*.json")):
+    try:
+        b = json.load(open(f))["bm25"]; print(f, round(b["value"]), {k: round(v["value"]) for k, v in b["variants"].items()}, b["roofline"]["kernel_ms"])
+    except Exception as e: print(f, "parse", e)
+PY
