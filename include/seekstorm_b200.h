@@ -110,11 +110,16 @@ typedef struct {
 /* A batch of lexical queries, already tokenised by the host (tokenizer.rs is out of scope): unique terms
  * per query as 64-bit keys, CSR layout; at most SSB_MAX_QUERY_TERMS per query (checked for host arrays; with device
  * arrays extra terms are ignored).  Repeated keys inside a query count once, as in the reference's unique_terms. */
+#define SSB_TERM_NOT 1u            /* term_flags bit 0: the '-' operator — docs containing the term are excluded (not_query_list,  */
+                                  /* add_result.rs:3440-3496); NOT terms neither score nor count towards the 32-term limit       */
+#define SSB_MAX_NOT_TERMS 4u
 typedef struct {
     uint32_t n_queries;
     uint32_t query_type;              /* SSB_QUERY_* (applies to the whole batch)                         */
     const uint32_t* term_offsets;     /* [n_queries+1]                                                    */
     const uint64_t* term_keys;        /* [term_offsets[n_queries]]                                        */
+    const uint8_t*  term_flags;       /* [term_offsets[n_queries]] SSB_TERM_* per term, or NULL (all positive); at most        */
+                                      /* SSB_MAX_NOT_TERMS NOT terms per query                                                 */
 } ssb_lex_batch;
 
 uint32_t    ssb_abi_version(void);

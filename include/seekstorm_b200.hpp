@@ -111,12 +111,19 @@ public:
         const size_t heap = offset + length;                                   // search.rs:1708: per-shard length = offset+length
         // tokenizer stand-in (tokenizer.rs is out of scope): whitespace split, leading '+' = mandatory, unique terms
         QueryType qt = query_type_default;
-        std::vector<std::string> terms;
+        std::vector<std::string> terms, not_terms;
         {
             std::istringstream is(query_string);
             std::string tok; bool all_plus = true, any = false;
             while (is >> tok) {
-                if (tok[0] == '"' || tok[0] == '-') throw Error(SSB_E_UNSUPPORTED, "phrase / NOT operators are outside the GPU hot path");
+                if (tok[0] == '"') throw Error(SSB_E_UNSUPPORTED, "phrase queries are outside the GPU hot path");
+                if (tok[0] == '-') {                                            // '-' operator: not_query_list (add_result.rs:3440-3496)
+                    tok.erase(0, 1);
+                    bool dup = tok.empty();
+                    for (auto& t : not_terms) dup = dup || t == tok;
+                    if (!dup) not_terms.push_back(tok);
+                    continue;
+                }
                 any = true;
                 if (tok[0] == '+') tok.erase(0, 1); else all_plus = false;
                 if (tok.empty()) continue;
@@ -134,10 +141,11 @@ public:
         const bool want_lex = (search_mode.kind != SearchMode::Vector) && !terms.empty();
         const bool want_vec = (search_mode.kind != SearchMode::Lexical) && query_vector.has_value();
         if (want_lex) {
-            std::vector<uint64_t> keys;
-            for (auto& t : terms) keys.push_back(key_fn_(t));
+            std::vector<uint64_t> keys; std::vector<uint8_t> flags;
+            for (auto& t : terms) { keys.push_back(key_fn_(t)); flags.push_back(0); }
+            for (auto& t : not_terms) { keys.push_back(key_fn_(t)); flags.push_back(SSB_TERM_NOT); }
             uint32_t offs[2] = {0, static_cast<uint32_t>(keys.size())};
-            ssb_lex_batch b{1, static_cast<uint32_t>(qt), offs, keys.data()};
+            ssb_lex_batch b{1, static_cast<uint32_t>(qt), offs, keys.data(), not_terms.empty() ? nullptr : flags.data()};
             const uint32_t k = rt == ResultType::Count ? 0u : static_cast<uint32_t>(heap);
             lex.resize(k ? k : 1);
             uint32_t n = 0;

@@ -63,6 +63,8 @@ def lib():
         for f in (L.orc_search_lexical, L.orc_search_lexical_pruned):
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                           C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_search_lexical_not.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                             C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_normalize_f32.argtypes = [C.c_void_p, C.c_uint32]
         for f in (L.orc_dot_f32, L.orc_dot_f32_lanes8, L.orc_euclidean_f32):
             f.restype = C.c_float
@@ -129,11 +131,16 @@ class OracleIndex:
     def df(self, key: int) -> int:
         return lib().orc_index_df(self._h, C.c_uint64(key))
 
-    def search(self, term_keys, query_type, k, result_type, pruned=False):
+    def search(self, term_keys, query_type, k, result_type, pruned=False, not_keys=None):
         keys = np.ascontiguousarray(np.array(term_keys, dtype=np.uint64))
         buf = (OrcHit * max(k, 1))()
         n = C.c_uint32(0)
         tot = C.c_uint64(0)
+        if not_keys:
+            nk = np.ascontiguousarray(np.array(not_keys, dtype=np.uint64))
+            rc = lib().orc_search_lexical_not(self._h, _ptr(keys), len(keys), _ptr(nk), len(nk), query_type, k, result_type, buf, C.byref(n), C.byref(tot))
+            assert rc == 0, rc
+            return _hits_to_list(buf, n.value), int(tot.value)
         f = lib().orc_search_lexical_pruned if pruned else lib().orc_search_lexical
         rc = f(self._h, _ptr(keys), len(keys), query_type, k, result_type, buf, C.byref(n), C.byref(tot))
         assert rc == 0, rc

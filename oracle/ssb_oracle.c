@@ -242,7 +242,14 @@ static int64_t term_in_level(const orc_index* ix, const qterm_t* q, uint32_t li)
 int orc_search_lexical(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, uint32_t query_type,
                        uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
                        uint64_t* count_total) {
-    if (!ix || !ix->committed || n_terms > ORC_MAX_TERMS) return -1;
+    return orc_search_lexical_not(ix, keys, n_terms, NULL, 0, query_type, k, result_type, hits, n_hits, count_total);
+}
+
+/* same with NOT terms ('-' operator, not_query_list add_result.rs:3440-3496): a doc that contains any of them is neither scored nor counted */
+int orc_search_lexical_not(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, const uint64_t* not_keys, uint32_t n_not,
+                           uint32_t query_type, uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
+                           uint64_t* count_total) {
+    if (!ix || !ix->committed || n_terms > ORC_MAX_TERMS || n_not > ORC_MAX_TERMS) return -1;
     if (n_hits) *n_hits = 0;
     if (count_total) *count_total = 0;
     if (n_terms == 0) return 0;
@@ -264,6 +271,9 @@ int orc_search_lexical(const orc_index* ix, const uint64_t* keys, uint32_t n_ter
     topk_t tk = { hits, 0, kk };
     float* acc = (float*)malloc(65536 * sizeof(float));
     uint8_t* cnt = (uint8_t*)malloc(65536);
+    uint8_t* excl = (uint8_t*)malloc(65536);
+    qterm_t nq[ORC_MAX_TERMS];
+    if (n_not) resolve_terms(ix, not_keys, n_not, nq);
     uint64_t total = 0;
     for (uint32_t li = 0; li < ix->n_levels; li++) {
         const lvl_t* l = &ix->levels[li];
@@ -272,6 +282,13 @@ int orc_search_lexical(const orc_index* ix, const uint64_t* keys, uint32_t n_ter
         if (!any) continue;
         memset(acc, 0, l->n_docs * sizeof(float));
         memset(cnt, 0, l->n_docs);
+        memset(excl, 0, l->n_docs);
+        for (uint32_t t = 0; t < n_not; t++) {
+            int64_t e = nq[t].df ? term_in_level(ix, &nq[t], li) : -1;
+            if (e < 0) continue;
+            uint32_t ti = ix->dict[e].idx;
+            for (uint32_t j = l->posting_offsets[ti]; j < l->posting_offsets[ti + 1]; j++) excl[l->doc_ids[j]] = 1;
+        }
         for (uint32_t t = 0; t < n_live; t++) {   /* QUERY ORDER: bm25f += ... from 0.0 */
             int64_t e = term_in_level(ix, &live[t], li);
             if (e < 0) continue;
@@ -285,13 +302,13 @@ int orc_search_lexical(const orc_index* ix, const uint64_t* keys, uint32_t n_ter
         }
         for (uint32_t d = 0; d < l->n_docs; d++) {
             int match = query_type == ORC_QUERY_INTERSECTION ? (cnt[d] == n_live) : (cnt[d] > 0);
-            if (!match) continue;
+            if (!match || excl[d]) continue;
             if (ix->n_deleted && is_deleted(ix, ((uint64_t)l->level_id << 16) | d)) continue;
             total++;
             if (kk) topk_push(&tk, ((uint64_t)l->level_id << 16) | d, acc[d]);
         }
     }
-    free(acc); free(cnt);
+    free(acc); free(cnt); free(excl);
     if (n_hits) *n_hits = tk.n;
     if (count_total) *count_total = total;
     return 0;

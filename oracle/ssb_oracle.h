@@ -75,6 +75,11 @@ int orc_search_lexical(const orc_index*, const uint64_t* term_keys, uint32_t n_t
                        uint32_t query_type, uint32_t k, uint32_t result_type,
                        orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
 
+/* the same with NOT terms ('-' operator, not_query_list add_result.rs:3440-3496) */
+int orc_search_lexical_not(const orc_index*, const uint64_t* term_keys, uint32_t n_terms, const uint64_t* not_keys, uint32_t n_not,
+                           uint32_t query_type, uint32_t k, uint32_t result_type,
+                           orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
+
 /* Reference-shaped search: block-max ordered, heap-pruned, same control flow as
  * single.rs:292-417, intersection.rs:2023-2301, union.rs:1168-1479.  Used as the timed CPU baseline
  * ("port") and cross-checked against the exhaustive search in tests. */

@@ -54,7 +54,7 @@ class SsbLevelDesc(C.Structure):
 
 class SsbLexBatch(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("query_type", C.c_uint32), ("term_offsets", C.c_void_p),
-                ("term_keys", C.c_void_p)]
+                ("term_keys", C.c_void_p), ("term_flags", C.c_void_p)]
 
 
 class SsbStats(C.Structure):

@@ -201,7 +201,7 @@ __device__ __forceinline__ uint32_t meta_cperm(uint32_t m, uint32_t c) { return 
 // block bound), the in-query-order suffix sums S[p] / R[p], the count order, the AND driver — and writes them as one
 // 128-byte record.  Thread 0 finally cuts the sorted record list into work items.
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
-                                                uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
+                                                const uint8_t* __restrict__ q_flags /*or null*/, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
                                                 uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2,
                                                 uint32_t item_w, uint32_t first_lim, uint32_t gmax) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -209,14 +209,15 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
     uint32_t* cnt = (uint32_t*)(bound + v.n_levels);                   // [n_levels]; after the sort: item weights by sorted position
     uint16_t* ent = (uint16_t*)(cnt + v.n_levels);                     // [FAST_T][n_levels] entry index relative to term.first
     uint64_t* skey = (uint64_t*)(((uintptr_t)(ent + FAST_T * v.n_levels) + 7) & ~(uintptr_t)7);  // [n_pow2]
-    __shared__ QTerm st[SSB_MAX_QUERY_TERMS];
+    __shared__ QTerm st[SSB_MAX_QUERY_TERMS + SSB_MAX_NOT_TERMS];
+    __shared__ uint8_t sflag[SSB_MAX_QUERY_TERMS + SSB_MAX_NOT_TERMS];
     __shared__ QueryPlan pl;
     __shared__ uint32_t n_valid;
 
     const uint32_t q = blockIdx.x;
     const uint32_t nlv = v.n_levels;
     const uint32_t t0 = q_off[q], nt_raw = q_off[q + 1] - t0;
-    const uint32_t nt = nt_raw > SSB_MAX_QUERY_TERMS ? SSB_MAX_QUERY_TERMS : nt_raw;
+    const uint32_t nt = nt_raw > SSB_MAX_QUERY_TERMS + SSB_MAX_NOT_TERMS ? SSB_MAX_QUERY_TERMS + SSB_MAX_NOT_TERMS : nt_raw;
     if (threadIdx.x < 32) glist[(size_t)q * LIST + threadIdx.x] = 0;
     if (threadIdx.x == 0) { theta[q] = 0; lock[q] = 0; count[q] = 0; n_valid = 0; }
     if (threadIdx.x < nt) {
@@ -228,11 +229,19 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             t.first = v.term_first[lo]; t.n = v.term_first[lo + 1] - t.first; t.idf = v.term_idf[lo]; t.df = v.term_df[lo];
         }
         st[threadIdx.x] = t;
+        sflag[threadIdx.x] = q_flags ? q_flags[t0 + threadIdx.x] : (uint8_t)0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t nl = 0; bool missing = false;
+        uint32_t nl = 0, nn = 0; bool missing = false;
         for (uint32_t t = 0; t < nt; t++) {
+            if (sflag[t] & SSB_TERM_NOT) {                  // '-' terms: exclusion lists, never scored (an unknown NOT term excludes nothing)
+                bool dup = false;
+                for (uint32_t u = 0; u < nn; u++) dup = dup || pl.tn[u].first == st[t].first;
+                if (st[t].n && !dup && nn < SSB_MAX_NOT_TERMS) pl.tn[nn++] = st[t];
+                continue;
+            }
+            if (nl >= SSB_MAX_QUERY_TERMS) continue;
             if (!st[t].n) { missing = true; continue; }
             bool dup = false;                       // the reference scores unique_terms (search.rs:3023-3039): drop repeated keys
             for (uint32_t u = 0; u < nl; u++) dup = dup || pl.t[u].first == st[t].first;
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         }
         // search.rs:3290-3296: AND with an unknown term -> empty result; OR drops the term
         if (query_type == SSB_QUERY_INTERSECTION && missing) nl = 0;
-        pl.n_live = nl; pl.n_items = 0; pl.n_recs = 0; pl.pad = 0;
+        pl.n_live = nl; pl.n_items = 0; pl.n_recs = 0; pl.n_not = nl ? nn : 0;
     }
     for (uint32_t b = threadIdx.x; b < nlv; b += blockDim.x) {
         bound[b] = 0.f; cnt[b] = 0;
@@ -375,6 +384,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         plans[q] = pl;
         atomicMax(&ctr[1], ni);
         if (pl.n_live > FAST_T) atomicOr(&ctr[4], 1u);
+        if (pl.n_not) atomicOr(&ctr[5], 1u);
     }
 }
 
@@ -420,6 +430,31 @@ __device__ __forceinline__ bool is_deleted(const LexView& v, uint32_t doc) {
     return ((__ldg(&v.del_words[(size_t)slot * 1024 + ((doc & 0xFFFFu) >> 6)]) >> (doc & 63u)) & 1ull) != 0;
 }
 
+// not_query_list (add_result.rs:3440-3496): is doc d of local level lv in one of the query's NOT lists?  Out of line and fed by
+// value (no LexView reference: that would force the whole view onto the thread stack) — the call sits on the rare survivor path.
+struct NotView { const uint32_t* e_level; const uint32_t* e_count; const uint32_t* e_bitmap; const uint32_t* post; const uint64_t* e_off; const uint64_t* bm_words; };
+__device__ __forceinline__ NotView not_view(const LexView& v) { return NotView{v.e_level, v.e_count, v.e_bitmap, v.post, v.e_off, v.bm_words}; }
+__device__ __noinline__ bool in_not_lists_impl(NotView v, const QueryPlan* pl, uint32_t n_not, uint32_t lv, uint32_t d) {
+    for (uint32_t i = 0; i < n_not; i++) {
+        const QTerm qt = pl->tn[i];
+        uint32_t a = 0, b = qt.n;
+        while (a < b) { const uint32_t m = (a + b) >> 1; if (__ldg(&v.e_level[qt.first + m]) < lv) a = m + 1; else b = m; }
+        if (a < qt.n && __ldg(&v.e_level[qt.first + a]) == lv) {
+            const uint32_t e = qt.first + a;
+            const uint32_t cnt = __ldg(&v.e_count[e]), bmi = __ldg(&v.e_bitmap[e]); const uint64_t off = __ldg(&v.e_off[e]);
+            if (bmi != NONE) { if ((__ldg(&v.bm_words[(size_t)bmi * 1024 + (d >> 6)]) >> (d & 63)) & 1ull) return true; continue; }
+            uint32_t lo = 0, hi = cnt;
+            const uint32_t* p = v.post + off;
+            while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if ((__ldg(&p[m]) & 0xFFFFu) < d) lo = m + 1; else hi = m; }
+            if (lo < cnt && (__ldg(&p[lo]) & 0xFFFFu) == d) return true;
+        }
+    }
+    return false;
+}
+__device__ __forceinline__ bool in_not_lists(const LexView& v, const QueryPlan* pl, uint32_t n_not, uint32_t lv, uint32_t d) {
+    return in_not_lists_impl(not_view(v), pl, n_not, lv, d);
+}
+
 __device__ __forceinline__ float bound_of_word(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bool cand, float score, uint32_t doc,
@@ -438,12 +473,12 @@ __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bo
 }
 
 struct ItemCtx {
-    uint32_t q, lv, n, k, docbase, bound_ord;
+    uint32_t q, lv, n, k, docbase, bound_ord, n_not;
     uint64_t ceil;
     bool scoring, need_count, is_and;
 };
 
-struct WarpSm { LvRec recs[GMAX]; uint2 queue[QCAP]; };   // 1024 + 1536 B per warp
+struct WarpSm { LvRec recs[GMAX]; uint2 queue[QCAP]; const QueryPlan* pl; uint32_t n_not; uint32_t pad; };   // 1024 + 1536 + 16 B per warp
 
 // thresholds derived from the ordered-uint k-th score `thr` (0 = list not full yet): BM25 scores are non-negative, so
 // the per-posting tests are plain float compares against thr_lo = thr_f / INFL (rounded down).
@@ -453,7 +488,7 @@ struct Thr {
 };
 
 // ---- stages 2 + 3 on up to 32 queued survivors (one per lane; lanes may belong to different records / drivers) ----
-template <bool IS_AND>
+template <bool IS_AND, bool HAS_NOT>
 __device__ __forceinline__ void process_queued(const LexView& v, const WarpSm& w, uint2 e, bool active, int lane, uint32_t k, uint64_t ceil,
                                                uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
     const uint32_t pos = e.x & 0x1FFFFu, ri = (e.x >> 17) & 7u, p = (e.x >> 20) & 3u;
@@ -512,19 +547,20 @@ __device__ __forceinline__ void process_queued(const LexView& v, const WarpSm& w
     uint32_t t = thr.u;
     alive = alive && ord_f32(score) >= thr.u;
     if (alive && is_deleted(v, rec.docbase | d)) alive = false;
+    if (HAS_NOT) { if (alive && w.n_not && in_not_lists(v, w.pl, w.n_not, rec.lv, d)) alive = false; }   // '-' terms (not_query_list); own kernel instantiation
     insert_candidates(L, t, alive, score, rec.docbase | d, k, lane, dirty, ceil);
     if (t != thr.u) thr.set(t);
 }
 
 // drain full batches of the survivor queue; keeps < 32 entries at the front
-template <bool IS_AND>
+template <bool IS_AND, bool HAS_NOT>
 __device__ __forceinline__ void drain_queue(const LexView& v, WarpSm& w, uint32_t& nq_in, bool flush, int lane, uint32_t k, uint64_t ceil,
                                             uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
     uint32_t head = 0;
     while (nq_in - head >= 32u || (flush && nq_in > head)) {
         const bool act = head + (uint32_t)lane < nq_in;
         const uint2 e = act ? w.queue[head + lane] : make_uint2(0u, 0u);
-        process_queued<IS_AND>(v, w, e, act, lane, k, ceil, L, thr, dirty, st_probes);
+        process_queued<IS_AND, HAS_NOT>(v, w, e, act, lane, k, ceil, L, thr, dirty, st_probes);
         head += 32u;
         if (head > nq_in) head = nq_in;
     }
@@ -540,7 +576,7 @@ __device__ __forceinline__ void drain_queue(const LexView& v, WarpSm& w, uint32_
 }
 
 // stream one list 128 postings per iteration (one 16-byte load per lane) and queue the postings whose bound reaches θ
-template <bool IS_AND>
+template <bool IS_AND, bool HAS_NOT>
 __device__ __forceinline__ void stream_driver(const LexView& v, WarpSm& w, uint32_t tag /* ri<<17 | p<<20 */, uint64_t doff, uint32_t dcnt,
                                               float didf, float R, uint32_t& nq_in, int lane, uint32_t k, uint64_t ceil,
                                               uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
@@ -567,7 +603,7 @@ __device__ __forceinline__ void stream_driver(const LexView& v, WarpSm& w, uint3
         m = __ballot_sync(FULL, a2); if (a2) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 2u - r0) | tag, cur.z); nq_in += __popc(m);
         m = __ballot_sync(FULL, a3); if (a3) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 3u - r0) | tag, cur.w); nq_in += __popc(m);
         __syncwarp();
-        if (nq_in >= 32u) drain_queue<IS_AND>(v, w, nq_in, false, lane, k, ceil, L, thr, dirty, st_probes);
+        if (nq_in >= 32u) drain_queue<IS_AND, HAS_NOT>(v, w, nq_in, false, lane, k, ceil, L, thr, dirty, st_probes);
     }
 }
 
@@ -653,7 +689,7 @@ __device__ __forceinline__ uint32_t count_record(const LexView& v, const LvRec& 
 }
 
 // ---- record path (n <= FAST_T live terms), scoring of one item ----
-template <bool IS_AND>
+template <bool IS_AND, bool HAS_NOT>
 __device__ __forceinline__ void score_records(const LexView& v, WarpSm& w, uint32_t nrec, uint32_t q, uint32_t k, uint64_t ceil,
                                               const uint64_t* theta, int lane, uint64_t& L, Thr& thr, bool& dirty,
                                               uint32_t& st_visited, uint32_t& st_probes, uint32_t& st_recs, uint32_t& st_skipped) {
@@ -670,7 +706,7 @@ __device__ __forceinline__ void score_records(const LexView& v, WarpSm& w, uint3
             const uint32_t drv = meta_anddrv(meta);
             const uint32_t dcnt = slot_cnt(rec.t[drv]);
             st_visited += dcnt;
-            stream_driver<true>(v, w, ri << 17, slot_off(rec.t[drv]), dcnt, rec.idf[drv], rec.R[0], nq_in, lane, k, ceil, L, thr, dirty, st_probes);
+            stream_driver<true, HAS_NOT>(v, w, ri << 17, slot_off(rec.t[drv]), dcnt, rec.idf[drv], rec.R[0], nq_in, lane, k, ceil, L, thr, dirty, st_probes);
         } else {
             const uint32_t np = meta_npres(meta);
             for (uint32_t p = 0; p < np; p++) {
@@ -680,11 +716,11 @@ __device__ __forceinline__ void score_records(const LexView& v, WarpSm& w, uint3
                 const uint32_t drv = meta_perm(meta, p);
                 const uint32_t dcnt = slot_cnt(rec.t[drv]);
                 st_visited += dcnt;
-                stream_driver<false>(v, w, (ri << 17) | (p << 20), slot_off(rec.t[drv]), dcnt, rec.idf[drv], rec.R[p], nq_in, lane, k, ceil, L, thr, dirty, st_probes);
+                stream_driver<false, HAS_NOT>(v, w, (ri << 17) | (p << 20), slot_off(rec.t[drv]), dcnt, rec.idf[drv], rec.R[p], nq_in, lane, k, ceil, L, thr, dirty, st_probes);
             }
         }
     }
-    if (nq_in) drain_queue<IS_AND>(v, w, nq_in, true, lane, k, ceil, L, thr, dirty, st_probes);
+    if (nq_in) drain_queue<IS_AND, HAS_NOT>(v, w, nq_in, true, lane, k, ceil, L, thr, dirty, st_probes);
 }
 
 // ---- generic path: up to SSB_MAX_QUERY_TERMS live terms, lane t holds term t, values broadcast by shuffles ----
@@ -729,7 +765,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                 if (ok && c.scoring) score = __fadd_rn(score, term_score(v, ti, to + rank));
             }
             matches += __popc(__ballot_sync(FULL, ok));
-            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d), score, c.docbase | d, c.k, lane, dirty, c.ceil);
+            if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
         }
         if (lane == 0) matches_out += matches;
         return;
@@ -773,7 +809,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                         else score = __fadd_rn(score, term_score(v, ti, to + rank));
                     }
                 }
-                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d), score, c.docbase | d, c.k, lane, dirty, c.ceil);
+                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
             }
         }
     }
@@ -856,7 +892,7 @@ __device__ __forceinline__ void publish(uint64_t L, uint32_t q, uint32_t k, int 
 }
 
 // ---- scoring, queries with <= 4 live terms (ResultType Topk / TopkCount) ----
-template <bool IS_AND>
+template <bool IS_AND, bool HAS_NOT>
 __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const QueryPlan* __restrict__ plans, const LvRec* __restrict__ recs,
                                                  const uint16_t* __restrict__ item_start, uint32_t nq, uint32_t k, uint32_t* ctr, uint64_t* theta,
                                                  int* lock, uint64_t* glist, LexStats* stats, const uint64_t* __restrict__ ceil_keys) {
@@ -872,11 +908,13 @@ __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const 
         const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
         if (ceil == 0) continue;                         // this query's result list is already exhausted
         const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
+        if (lane == 0) { w.pl = pl; w.n_not = __ldg(&pl->n_not); }
+        __syncwarp();
         Thr thr; thr.set((uint32_t)(__ldcg(&theta[q]) >> 32));
         if (ord_f32(w.recs[0].bound) < thr.u) { st_skipped += nrec; continue; }   // whole item below θ
         uint64_t L = 0; bool dirty = false;
         st_done++;
-        score_records<IS_AND>(v, w, nrec, q, k, ceil, theta, lane, L, thr, dirty, st_visited, st_probes, st_recs, st_skipped);
+        score_records<IS_AND, HAS_NOT>(v, w, nrec, q, k, ceil, theta, lane, L, thr, dirty, st_visited, st_probes, st_recs, st_skipped);
         if (dirty) publish(L, q, k, lane, theta, lock, glist);
     }
     // per-lane counters (probes) are summed over the warp; warp-uniform ones are taken from lane 0
@@ -947,7 +985,7 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
         uint64_t L = 0; bool dirty = false; uint32_t matches = 0;
         for (uint32_t ri = 0; ri < nrec; ri++) {
             ItemCtx c;
-            c.ceil = ceil; c.q = q; c.n = n_live; c.k = k; c.lv = w.recs[ri].lv; c.bound_ord = ord_f32(w.recs[ri].bound);
+            c.ceil = ceil; c.q = q; c.n = n_live; c.k = k; c.lv = w.recs[ri].lv; c.bound_ord = ord_f32(w.recs[ri].bound); c.n_not = __ldg(&pl->n_not);
             c.scoring = want_topk && c.bound_ord >= thr;
             c.need_count = need_count; c.is_and = query_type == SSB_QUERY_INTERSECTION; c.docbase = w.recs[ri].docbase;
             if (!c.scoring && !need_count) { st_skipped++; continue; }
@@ -964,6 +1002,53 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
         atomicAdd((unsigned long long*)&stats->probes, pr);
         atomicAdd((unsigned long long*)&stats->items_processed, (unsigned long long)st_done);
         atomicAdd((unsigned long long*)&stats->items_skipped, (unsigned long long)st_skipped);
+    }
+}
+
+// ---- exact counts with NOT lists: the count kernels count every match of the positive terms; the matches that sit in a NOT list are
+// subtracted here.  One warp per (query, local level); a NOT list's postings are enumerated (each doc once: docs already seen in an
+// earlier NOT list are skipped), deleted docs are left to lex_del_count. ----
+__global__ void __launch_bounds__(256) lex_not_count(LexView v, const QueryPlan* __restrict__ plans, uint32_t nq, uint32_t query_type, const uint32_t* ctr,
+                                                    uint64_t* count) {
+    if (*(volatile const uint32_t*)&ctr[5] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const bool is_and = query_type == SSB_QUERY_INTERSECTION;
+    for (uint64_t it = wid; it < (uint64_t)nq * v.n_levels; it += n_warps) {
+        const uint32_t q = (uint32_t)(it / v.n_levels), lv = (uint32_t)(it % v.n_levels);
+        const QueryPlan* pl = &plans[q];
+        const uint32_t n_not = pl->n_not, n = pl->n_live;
+        if (!n_not || !n) continue;
+        const uint32_t docbase = __ldg(&v.level_ids[lv]) << 16;
+        uint32_t sub = 0;
+        for (uint32_t i = 0; i < n_not; i++) {
+            const QTerm qt = pl->tn[i];
+            uint32_t a = 0, b = qt.n;
+            while (a < b) { const uint32_t m = (a + b) >> 1; if (__ldg(&v.e_level[qt.first + m]) < lv) a = m + 1; else b = m; }
+            if (a >= qt.n || __ldg(&v.e_level[qt.first + a]) != lv) continue;
+            const uint32_t e = qt.first + a;
+            for_each_posting(v, __ldg(&v.e_off[e]), __ldg(&v.e_count[e]), lane, [&](uint32_t d, bool valid) {
+                if (!valid) return;
+                if (i && in_not_lists(v, pl, i, lv, d)) return;          // counted with an earlier NOT list
+                if (is_deleted(v, docbase | d)) return;
+                bool any = false, all = true;
+                for (uint32_t t = 0; t < n; t++) {
+                    const QTerm pt = pl->t[t];
+                    uint32_t x = 0, y = pt.n;
+                    while (x < y) { const uint32_t m = (x + y) >> 1; if (__ldg(&v.e_level[pt.first + m]) < lv) x = m + 1; else y = m; }
+                    bool pres = false;
+                    if (x < pt.n && __ldg(&v.e_level[pt.first + x]) == lv) {
+                        const uint32_t pe = pt.first + x;
+                        pres = present_in(v, __ldg(&v.e_count[pe]), __ldg(&v.e_off[pe]), __ldg(&v.e_bitmap[pe]), d);
+                    }
+                    any = any || pres; all = all && pres;
+                }
+                sub += (is_and ? all : any) ? 1u : 0u;
+            });
+        }
+        for (int s = 16; s; s >>= 1) sub += __shfl_xor_sync(FULL, sub, s);
+        if (lane == 0 && sub) atomicAdd((unsigned long long*)&count[q], 0ull - (unsigned long long)sub);
     }
 }
 
@@ -1022,8 +1107,8 @@ void LexIndex::free_committed() {
 
 void LexWorkspace::release() {
     cudaFree(plans); cudaFree(recs); cudaFree(item_start); cudaFree(theta); cudaFree(lock); cudaFree(count); cudaFree(ctr);
-    cudaFree(qoff); cudaFree(qkeys); cudaFree(stats);
-    plans = nullptr; recs = nullptr; item_start = nullptr; theta = nullptr; lock = nullptr; count = nullptr; ctr = nullptr;
+    cudaFree(qoff); cudaFree(qkeys); cudaFree(qflags); cudaFree(stats);
+    qflags = nullptr; plans = nullptr; recs = nullptr; item_start = nullptr; theta = nullptr; lock = nullptr; count = nullptr; ctr = nullptr;
     qoff = nullptr; qkeys = nullptr; stats = nullptr; cap_q = cap_terms = cap_levels = 0;
 }
 
@@ -1309,6 +1394,7 @@ int32_t LexIndex::ensure_workspace(LexWorkspace& ws, uint32_t nq, uint32_t total
     SSB_CUDA_TRY(cudaMalloc(&ws.theta, (size_t)cq * 8)); SSB_CUDA_TRY(cudaMalloc(&ws.lock, (size_t)cq * 4));
     SSB_CUDA_TRY(cudaMalloc(&ws.count, (size_t)cq * 8)); SSB_CUDA_TRY(cudaMalloc(&ws.ctr, 32));
     SSB_CUDA_TRY(cudaMalloc(&ws.qoff, ((size_t)cq + 1) * 4)); SSB_CUDA_TRY(cudaMalloc(&ws.qkeys, (size_t)ct * 8));
+    SSB_CUDA_TRY(cudaMalloc(&ws.qflags, (size_t)ct));
     SSB_CUDA_TRY(cudaMalloc(&ws.stats, sizeof(LexStats)));
     ws.cap_q = cq; ws.cap_terms = ct; ws.cap_levels = nlv;
     return SSB_OK;
@@ -1328,17 +1414,23 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     if (off_dev) SSB_CUDA_TRY(cudaMemcpy(&total_terms, q->term_offsets + nq, 4, cudaMemcpyDeviceToHost));
     else {
         total_terms = q->term_offsets[nq];
-        for (uint32_t i = 0; i < nq; i++)
-            if (q->term_offsets[i + 1] < q->term_offsets[i] || q->term_offsets[i + 1] - q->term_offsets[i] > SSB_MAX_QUERY_TERMS) {
-                set_error("query %u has %u terms (max %u unique terms per query)", i, q->term_offsets[i + 1] - q->term_offsets[i], SSB_MAX_QUERY_TERMS);
+        for (uint32_t i = 0; i < nq; i++) {
+            if (q->term_offsets[i + 1] < q->term_offsets[i]) { set_error("query %u: term_offsets must ascend", i); return SSB_E_INVALID; }
+            uint32_t n_pos = q->term_offsets[i + 1] - q->term_offsets[i], n_neg = 0;
+            if (q->term_flags && !is_device_ptr(q->term_flags))
+                for (uint32_t t = q->term_offsets[i]; t < q->term_offsets[i + 1]; t++) if (q->term_flags[t] & SSB_TERM_NOT) { n_neg++; n_pos--; }
+            if (n_pos > SSB_MAX_QUERY_TERMS || n_neg > SSB_MAX_NOT_TERMS) {
+                set_error("query %u has %u terms + %u NOT terms (max %u + %u per query)", i, n_pos, n_neg, SSB_MAX_QUERY_TERMS, SSB_MAX_NOT_TERMS);
                 return SSB_E_UNSUPPORTED;
             }
+        }
     }
     if (total_terms && !q->term_keys) { set_error("search_lexical: null term_keys"); return SSB_E_INVALID; }
     if ((uint64_t)nq * (levels_.size() ? levels_.size() : 1) >= 0xFFFFFFFFull) { set_error("batch too large: n_queries * n_levels must be < 2^32"); return SSB_E_UNSUPPORTED; }
     SSB_TRY(ensure_workspace(ws, nq, total_terms));
     SSB_CUDA_TRY(to_device(ws.qoff, q->term_offsets, ((size_t)nq + 1) * 4, st));
     SSB_CUDA_TRY(to_device(ws.qkeys, q->term_keys, (size_t)total_terms * 8, st));
+    if (q->term_flags) SSB_CUDA_TRY(to_device(ws.qflags, q->term_flags, (size_t)total_terms, st));
     SSB_CUDA_TRY(cudaMemsetAsync(ws.ctr, 0, 32, st));
     SSB_CUDA_TRY(cudaMemsetAsync(ws.stats, 0, sizeof(LexStats), st));
 
@@ -1352,7 +1444,7 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     // item shape (tunable for experiments; defaults measured on C3): target postings per item, levels of a query's first item, levels per item
     static const uint32_t item_w = env_u32("SSB_LEX_ITEM_W", ITEM_W, 64, 1u << 20), first_lim = env_u32("SSB_LEX_FIRST", 2, 1, GMAX),
                           gmax = env_u32("SSB_LEX_GMAX", GMAX, 1, GMAX), grid_mult = env_u32("SSB_LEX_GRID", SSB_LEX_MINB, 1, 16);
-    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
+    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
                                          item_w, first_lim, gmax);
     SSB_CUDA_TRY(cudaGetLastError());
     const bool is_and = q->query_type == SSB_QUERY_INTERSECTION;
@@ -1362,8 +1454,12 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     if (ws.ev0) cudaEventRecord(ws.ev0, st);
     if (want_topk) {
         const int grid = n_sms_ * (int)grid_mult;
-        if (is_and) lex_score<true><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev);
-        else lex_score<false><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev);
+        // batches that carry NOT terms ('-' operator) run their own instantiation: the common kernel stays free of the out-of-line probe
+        const bool hn = q->term_flags != nullptr;
+#define SSB_LAUNCH_SCORE(A, N) lex_score<A, N><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev)
+        if (is_and) { if (hn) SSB_LAUNCH_SCORE(true, true); else SSB_LAUNCH_SCORE(true, false); }
+        else { if (hn) SSB_LAUNCH_SCORE(false, true); else SSB_LAUNCH_SCORE(false, false); }
+#undef SSB_LAUNCH_SCORE
         SSB_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }
@@ -1375,6 +1471,11 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     // queries with 5..16 live terms (the kernel returns at once when the batch has none)
     lex_generic<<<n_sms_ * 2, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, q->query_type, result_type, kk, ws.ctr, ws.theta, ws.lock, ws.count, glist, ws.stats, ceil_dev);
     SSB_CUDA_TRY(cudaGetLastError());
+    if (need_count) {     // returns at once unless some query of the batch carries NOT terms
+        lex_not_count<<<n_sms_ * 4, 256, 0, st>>>(v, ws.plans, nq, q->query_type, ws.ctr, ws.count);
+        SSB_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
     if (need_count && v.n_del) {
         const uint64_t pairs = (uint64_t)nq * v.n_del;
         lex_del_count<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(v, ws.plans, nq, q->query_type, ws.count);

@@ -95,7 +95,7 @@ struct DeleteSet {
 };
 
 struct QTerm { uint32_t first, n; float idf; uint32_t df; };
-struct QueryPlan { QTerm t[SSB_MAX_QUERY_TERMS]; uint32_t n_live, n_items, n_recs, pad; };
+struct QueryPlan { QTerm t[SSB_MAX_QUERY_TERMS]; QTerm tn[SSB_MAX_NOT_TERMS]; uint32_t n_live, n_items, n_recs, n_not; };
 
 // One (query, level) record, built by lex_plan for queries with <= 4 live terms; 128 bytes = one cache line.
 // Slots are in QUERY order (scores are summed in query order, add_result.rs:1450-1452); cnt == 0 marks a term
@@ -127,7 +127,7 @@ struct LexWorkspace {
     uint32_t cap_q = 0, cap_terms = 0, cap_levels = 0;
     QueryPlan* plans = nullptr; uint64_t* items = nullptr; LvRec* recs = nullptr; uint16_t* item_start = nullptr;
     uint64_t* theta = nullptr; int* lock = nullptr; uint64_t* count = nullptr; uint32_t* ctr = nullptr; /* [0] score / [2] count / [3] generic work counters, [1] max_items, [4] any query with > 4 live terms */
-    uint32_t* qoff = nullptr; uint64_t* qkeys = nullptr; LexStats* stats = nullptr;
+    uint32_t* qoff = nullptr; uint64_t* qkeys = nullptr; uint8_t* qflags = nullptr; LexStats* stats = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // recorded around lex_score when set
     void release();
     ~LexWorkspace() { release(); }

@@ -258,26 +258,34 @@ class Index:
         return n.value
 
     # ------------------------------------------------------------------ batched shard-level search
-    def _lex_batch(self, queries_keys: Sequence[Sequence[int]], query_type: QueryType):
+    def _lex_batch(self, queries_keys: Sequence[Sequence[int]], query_type: QueryType, not_keys: Optional[Sequence[Sequence[int]]] = None):
+        """not_keys: per query the keys of its '-' terms (not_query_list, add_result.rs:3440-3496) or None."""
+        nots = not_keys if not_keys is not None else [[] for _ in queries_keys]
         offs = np.zeros(len(queries_keys) + 1, dtype=np.uint32)
         for i, q in enumerate(queries_keys):
             if len(q) > _lib.MAX_QUERY_TERMS:
                 raise _lib.SsbError(f"query {i} has {len(q)} terms (> {_lib.MAX_QUERY_TERMS})")
-            offs[i + 1] = offs[i] + len(q)
+            offs[i + 1] = offs[i] + len(q) + len(nots[i])
         keys = np.zeros(max(int(offs[-1]), 1), dtype=np.uint64)
+        flags = np.zeros(max(int(offs[-1]), 1), dtype=np.uint8)
         p = 0
-        for q in queries_keys:
+        for q, nq_ in zip(queries_keys, nots):
             for t in q:
                 keys[p] = t
                 p += 1
-        b = SsbLexBatch(len(queries_keys), int(query_type), offs.ctypes.data, keys.ctypes.data)
-        return b, (offs, keys)
+            for t in nq_:
+                keys[p] = t
+                flags[p] = 1
+                p += 1
+        b = SsbLexBatch(len(queries_keys), int(query_type), offs.ctypes.data, keys.ctypes.data,
+                        flags.ctypes.data if not_keys is not None else None)
+        return b, (offs, keys, flags)
 
     def search_lexical_batch(self, queries_keys, query_type: QueryType, k: int,
-                             result_type: ResultType = ResultType.TopkCount):
-        """Batched search_lexical_shard.  Returns (list of [(doc_id, score)...], counts ndarray)."""
+                             result_type: ResultType = ResultType.TopkCount, not_keys=None):
+        """Batched search_lexical_shard.  Returns (list of [(doc_id, score)...], counts ndarray).  not_keys: '-' terms per query."""
         nq = len(queries_keys)
-        b, keep = self._lex_batch(queries_keys, query_type)
+        b, keep = self._lex_batch(queries_keys, query_type, not_keys)
         hits = _hits_array(max(nq * max(k, 1), 1))
         n_hits = np.zeros(max(nq, 1), dtype=np.uint32)
         counts = np.zeros(max(nq, 1), dtype=np.uint64)
@@ -411,8 +419,10 @@ class Index:
         heap = offset + length                       # search.rs:1708 per-shard length = offset+length
         # tokenizer stand-in: whitespace, '+' = mandatory (tokenizer.rs:546-563); unique terms (search.rs:3023-3039)
         toks = query_string.split()
-        if any(t.startswith('"') or t.startswith("-") for t in toks):
-            raise NotImplementedError("phrase / NOT operators are outside the GPU hot path")
+        if any(t.startswith('"') for t in toks):
+            raise NotImplementedError("phrase queries are outside the GPU hot path")
+        not_terms = [t[1:] for t in toks if t.startswith("-") and len(t) > 1]          # '-' operator: not_query_list (tokenizer.rs:546-563)
+        toks = [t for t in toks if not t.startswith("-")]
         qt = query_type_default
         if toks and all(t.startswith("+") for t in toks):
             qt = QueryType.Intersection
@@ -423,6 +433,7 @@ class Index:
                 terms.append(t)
         ro.query_terms = list(terms)
         keys = [self.term_key_fn(t) for t in terms]
+        nkeys = [self.term_key_fn(t) for t in dict.fromkeys(not_terms)]
         lex, vec, total = [], [], 0
         want_lex = search_mode.kind in ("Lexical", "Hybrid") and len(keys) > 0
         want_vec = search_mode.kind in ("Vector", "Hybrid") and query_vector is not None
@@ -430,7 +441,7 @@ class Index:
         if length == 0 and rt == ResultType.TopkCount:   # search.rs:2472-2478
             rt = ResultType.Count
         if want_lex:
-            res, counts = self.search_lexical_batch([keys], qt, heap if rt != ResultType.Count else 0, rt)
+            res, counts = self.search_lexical_batch([keys], qt, heap if rt != ResultType.Count else 0, rt, [nkeys] if nkeys else None)
             lex, total = res[0], int(counts[0])
         if want_vec:
             qv = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)

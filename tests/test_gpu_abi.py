@@ -320,3 +320,39 @@ def test_delete_set_lexical_vector_hybrid():
     again, _ = ix.search_lexical_batch(qk, QueryType.Union, 10, ResultType.TopkCount)
     assert again == base_lex and ix.search_vector_batch(qv, 10) == base_vec
     ix.close()
+
+
+def test_not_lists_lexical():
+    """'-' terms (not_query_list, add_result.rs:3440-3496): docs containing a NOT term are neither scored nor counted — OR / AND,
+    exact counts, > 4 positive terms, combined with a delete set, and through the mirrored Search::search ('-t7')."""
+    from seekstorm_b200 import QueryType, ResultType, SearchMode
+    n = 140000
+    lvs, ls = synth_levels(n, 1500, 61)
+    levels = [l.to_numpy() for l in lvs]
+    orc = oracle_index(levels, n, ls)
+    ix = gpu_index(levels, n, ls)
+    rng = np.random.default_rng(62)
+    qs = synth.gen_queries(50, 63, 2, 1200, (1, 2, 3, 4, 6), (0.1, 0.3, 0.3, 0.2, 0.1))
+    qk = query_keys(qs)
+    nots_ids = [[int(x) for x in rng.integers(0, 60, int(rng.integers(0, 3)))] for _ in qs]       # frequent terms: real exclusions
+    nots_ids = [[t for t in ns if t not in q] for ns, q in zip(nots_ids, qs)]
+    nk = query_keys([ns if ns else [0] for ns in nots_ids])
+    nk = [k if ns else [] for k, ns in zip(nk, nots_ids)]
+    nk[3] = nk[3] + [0xDEAD0008]                                          # unknown NOT term: excludes nothing
+    for deleted in ([], [int(x) for x in rng.integers(0, n, 2000)]):
+        ix.set_deleted(deleted); orc.set_deleted(deleted)
+        for qt, oqt in ((QueryType.Union, O.QUERY_UNION), (QueryType.Intersection, O.QUERY_INTERSECTION)):
+            got, cnt = ix.search_lexical_batch(qk, qt, 10, ResultType.TopkCount, not_keys=nk)
+            for i, k in enumerate(qk):
+                want, tot = orc.search(k, oqt, 10, O.RESULT_TOPKCOUNT, not_keys=nk[i])
+                if len(k) <= 4:
+                    assert got[i] == want, (i, k, nk[i])
+                else:
+                    assert [d for d, _ in got[i]] == [d for d, _ in want]
+                assert int(cnt[i]) == tot, (i, k, nk[i], int(cnt[i]), tot)
+    ix.set_deleted([]); orc.set_deleted([])
+    ro = ix.search("t30 t700 -t5", None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.TopkCount)
+    k3 = query_keys([[30, 700], [5]])
+    want, tot = orc.search(k3[0], O.QUERY_UNION, 10, O.RESULT_TOPKCOUNT, not_keys=k3[1])
+    assert [(r.doc_id, np.float32(r.score)) for r in ro.results] == [(d, np.float32(s)) for d, s in want] and ro.result_count_total == tot
+    ix.close()
