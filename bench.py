@@ -57,7 +57,7 @@ def parse():
     p.add_argument("--c5-docs", type=int, default=10_000_000, help="C5: docs AND vectors of the sharded hybrid index")
     p.add_argument("--parity-queries", type=int, default=64, help="queries per path of the post-run oracle check")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
-    p.add_argument("--vector-kernel", default="both", choices=["both", "ffma", "tc", "tc64", "tcb", "tcb64"],
+    p.add_argument("--vector-kernel", default="both", choices=["both", "all", "ffma", "tc", "tc64", "tcb", "tcb64", "tcb256"],
                    help="FP32 FFMA2 scan, tcgen05 3xTF32 scan (128 / 64 queries per pass) or both (headline = the faster)")
     return p.parse_args()
 
@@ -228,7 +228,8 @@ KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + wa
            "tc": (2, 128, "scan_tc", "scan_tc (TMA + tcgen05 3xTF32 split, TMEM accumulators, TMEM-epilogue top-k)"),
            "tc64": (3, 64, "scan_tc", "scan_tc<64> (tcgen05 3xTF32, 64 queries per pass)"),
            "tcb": (4, 128, "scan_tc", "scan_tc (TMA + tcgen05 3xBF16 split, TMEM accumulators, TMEM-epilogue top-k)"),
-           "tcb64": (5, 64, "scan_tc", "scan_tc<64> (tcgen05 3xBF16, 64 queries per pass)")}
+           "tcb64": (5, 64, "scan_tc", "scan_tc<64> (tcgen05 3xBF16, 64 queries per pass)"),
+           "tcb256": (6, 256, "scan_tc", "scan_tc<256> (tcgen05 3xBF16 over bf16 planes, 256 queries per pass: half the HBM bytes per query)")}
 # DRAM traffic per corpus pass (dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture, divided by
 # the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
 # (3.072 GB), i.e. no re-reads.
@@ -301,7 +302,7 @@ def bench_vector(a, rank, world, out):
     q_host = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").pin_memory()
     q_dev = q_host.to(dev)
     keys = torch.zeros((a.batch, 32), dtype=torch.int64, device=dev)
-    names = ["ffma", "tcb"] if a.vector_kernel == "both" else [a.vector_kernel]
+    names = ["ffma", "tcb"] if a.vector_kernel == "both" else (["ffma", "tcb", "tcb256"] if a.vector_kernel == "all" else [a.vector_kernel])
     res = {k: measure_vector_kernel(a, ix, k, q_host, q_dev, keys, local_rows, rank, world, dev, rank == 0) for k in names}
     # batch-size sweep through the reference-facing call (host buffers, AUTO kernel choice): latency at batch 1 .. 256
     sweep = {}
@@ -329,7 +330,7 @@ def bench_vector(a, rank, world, out):
                    "parallelism": f"64K-row levels sharded over {world} GPU(s)", "kernel": r["kernel_desc"]},
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "clocks": r["clocks"],
         "batch_sweep_e2e": sweep,
-        "kernels": {{"ffma": "scan_ffma", "tc": "scan_tc_tf32", "tc64": "scan_tc_tf32_n64", "tcb": "scan_tc_bf16", "tcb64": "scan_tc_bf16_n64"}[k]:
+        "kernels": {{"ffma": "scan_ffma", "tc": "scan_tc_tf32", "tc64": "scan_tc_tf32_n64", "tcb": "scan_tc_bf16", "tcb64": "scan_tc_bf16_n64", "tcb256": "scan_tc_bf16_n256"}[k]:
                     {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
     })
     return ix, q_host

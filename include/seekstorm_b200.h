@@ -65,7 +65,8 @@ enum { SSB_QUANT_NONE = 0, SSB_QUANT_SCALAR_I8 = 1 };
  * operand bytes; score error ~1e-5 relative, inside the 1e-4 tolerance).  AUTO: TCGEN05_BF16 for batches of > 16
  * Dot/Cosine queries, else FFMA; Euclidean always FFMA. */
 enum { SSB_VEC_KERNEL_AUTO = 0, SSB_VEC_KERNEL_FFMA = 1, SSB_VEC_KERNEL_TCGEN05 = 2, SSB_VEC_KERNEL_TCGEN05_N64 = 3,
-       SSB_VEC_KERNEL_TCGEN05_BF16 = 4, SSB_VEC_KERNEL_TCGEN05_BF16_N64 = 5 };
+       SSB_VEC_KERNEL_TCGEN05_BF16 = 4, SSB_VEC_KERNEL_TCGEN05_BF16_N64 = 5,
+       SSB_VEC_KERNEL_TCGEN05_BF16_N256 = 6 /* 256 queries per corpus pass: half the HBM bytes per query, tensor / shared-memory bound */ };
 
 typedef struct ssb_index ssb_index;
 

@@ -174,8 +174,8 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     if (ix->quant_i8) kern = SSB_VEC_KERNEL_TCGEN05;   // one kernel for the int8 corpus: tcgen05 kind::i8, 128-query tile
     if (kern == SSB_VEC_KERNEL_AUTO) kern = nq > 16 ? SSB_VEC_KERNEL_TCGEN05_BF16 : SSB_VEC_KERNEL_FFMA;
     const bool use_tc = ix->quant_i8 || (kern >= SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN);   // the int8 index is always scanned on the tensor cores
-    const bool tc_bf16 = kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64;
-    const uint32_t qt = !use_tc ? vec::VEC_QT : ((kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : 128u);
+    const bool tc_bf16 = kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256;
+    const uint32_t qt = !use_tc ? vec::VEC_QT : (ix->quant_i8 ? 128u : (kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : (kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256 ? 256u : 128u));
     const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
     cudaStream_t st = c.st;
     if (!ix->quant_i8) SSB_TRY(c.qpad.reserve((size_t)nq_pad * ix->dpad, 0, st));
@@ -636,7 +636,7 @@ int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n) {
 
 int32_t ssb_set_vector_kernel(ssb_index* ix, uint32_t kernel) {
     SSB_API_BEGIN
-    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_BF16_N64) { set_error("bad vector kernel"); return SSB_E_INVALID; }
+    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_BF16_N256) { set_error("bad vector kernel"); return SSB_E_INVALID; }
     std::unique_lock<std::shared_mutex> g(ix->rw);
     ix->cfg.vector_kernel = kernel;
     return SSB_OK;

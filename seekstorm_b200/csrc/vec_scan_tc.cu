@@ -53,6 +53,11 @@ enum { PREC_TF32 = 0, PREC_BF16 = 1, PREC_I8 = 2 };
 
 constexpr int MAX_STAGES = 6;
 template <int NQ, int PREC, bool BRES = false> struct Cfg {
+    // NQ = 256 (bf16 only): ONE 128-row corpus tile per stage against 256 queries — the corpus is streamed once per 256 queries (half
+    // the HBM bytes per query) and an MMA reads 4 KB of A per 8 KB of B (6 KB per 128x128x16 instead of 8); TMEM: 2 x 1 x 256 columns
+    static constexpr int MT = NQ == 256 ? 1 : 2;
+    static constexpr int TROWS = TM * MT;
+    static constexpr int A_BYTES = MT * A1_BYTES;
     // TF32: [A (-> A_hi in place) | A_lo | B_hi | B_lo], all f32 SWIZZLE_128B tiles
     // BF16: [A1 bf16 (hi plane) | A2 bf16 (lo plane) | B1 bf16 | B2 bf16], 64-byte rows, SWIZZLE_64B, all four delivered by TMA.
     //       48 KB per stage -> 4 stages.
@@ -129,6 +134,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         const float* __restrict__ q_scale, const float* __restrict__ q_norm /*SCALED: [gridDim.y*NQ]*/,
         uint32_t sample_mode /*int8 only: write per-(32-row group, query) score maxima instead of lists*/) {
     using C = Cfg<NQ, PREC, BRES>;
+    constexpr int MT = C::MT, TROWS = C::TROWS, A_BYTES = C::A_BYTES;   // (shadow the namespace-level 2-tile defaults)
     const uint32_t STAGES = BRES ? nst_rt : (uint32_t)C::STAGES;
     // no static shared memory: the dynamic segment starts at offset 0 of the CTA window (1024-aligned for the swizzled
     // tiles) and pointers derived from it stay in the shared address space (LDS/STS instead of generic LD/ST)
@@ -571,18 +577,18 @@ template <int NQ, int PREC, bool BRES = false, int SCALED = 0>
 static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     using C = tc::Cfg<NQ, PREC, BRES>;
     CUtensorMap tmA, tmA2, tmBh, tmBl;
-    uint32_t n_tiles = (uint32_t)((a.n_rows + tc::TROWS - 1) / tc::TROWS);
+    uint32_t n_tiles = (uint32_t)((a.n_rows + C::TROWS - 1) / C::TROWS);
     uint32_t n_groups = a.nq_pad / NQ;
     size_t nel = (size_t)a.nq_pad * a.dpad;
     uint32_t n_kchunks = a.dpad / tc::KC;
     if constexpr (PREC == tc::PREC_I8) {
         // int8 corpus / queries (quantised by the caller): 128 dims per 128-byte swizzle row
-        SSB_TRY(encode_tmap_2d(&tmA, a.rows_i8, 1, a.dpad8, a.n_rows, a.dpad8, 128, tc::TROWS, 128));
+        SSB_TRY(encode_tmap_2d(&tmA, a.rows_i8, 1, a.dpad8, a.n_rows, a.dpad8, 128, C::TROWS, 128));
         SSB_TRY(encode_tmap_2d(&tmBh, a.queries_i8, 1, a.dpad8, a.nq_pad, a.dpad8, 128, NQ, 128));
         tmBl = tmBh; tmA2 = tmA;
         n_kchunks = a.dpad8 / 128;
     } else if constexpr (PREC == tc::PREC_TF32) {
-        SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, tc::TROWS, 1));
+        SSB_TRY(encode_tmap_2d_f32(&tmA, a.rows, a.dpad, a.n_rows, (uint64_t)a.dpad * 4, tc::KC, C::TROWS, 1));
         SSB_TRY(encode_tmap_2d_f32(&tmBh, a.q_hi, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
         SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
         tmA2 = tmA;
@@ -591,8 +597,8 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
         // corpus: the two bf16 planes written at load time; queries: the two bf16 parts live in the q_hi / q_lo buffers (half of
         // each is used) and were written by prep_split_queries_bf16 (launch_prep_split_queries_bf16)
         if (!a.rows_hi || !a.rows_lo) { set_error("tcgen05 bf16 scan: the index holds no bf16 planes"); return SSB_E_STATE; }
-        SSB_TRY(encode_tmap_2d(&tmA, a.rows_hi, 2 /*bf16*/, a.dpad, a.n_rows, (uint64_t)a.dpad * 2, tc::KC, tc::TROWS, 64));
-        SSB_TRY(encode_tmap_2d(&tmA2, a.rows_lo, 2 /*bf16*/, a.dpad, a.n_rows, (uint64_t)a.dpad * 2, tc::KC, tc::TROWS, 64));
+        SSB_TRY(encode_tmap_2d(&tmA, a.rows_hi, 2 /*bf16*/, a.dpad, a.n_rows, (uint64_t)a.dpad * 2, tc::KC, C::TROWS, 64));
+        SSB_TRY(encode_tmap_2d(&tmA2, a.rows_lo, 2 /*bf16*/, a.dpad, a.n_rows, (uint64_t)a.dpad * 2, tc::KC, C::TROWS, 64));
         SSB_TRY(encode_tmap_2d(&tmBh, a.q_hi, 2 /*bf16*/, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, tc::KC, NQ, 64));
         SSB_TRY(encode_tmap_2d(&tmBl, a.q_lo, 2 /*bf16*/, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, tc::KC, NQ, 64));
     }
@@ -618,7 +624,7 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     if (a.sample_groupmax) {   // threshold seeding pass: scratch holds gmax[nq_pad][n_tiles * 8]
-        tc::kth_from_groupmax<<<(a.nq_pad + 7) / 8, 256, 0, st>>>((const int*)a.scratch, n_tiles * (tc::MT * 4), a.nq_pad, a.k, a.thr_buf,
+        tc::kth_from_groupmax<<<(a.nq_pad + 7) / 8, 256, 0, st>>>((const int*)a.scratch, n_tiles * (C::MT * 4), a.nq_pad, a.k, a.thr_buf,
                                                                       (PREC == tc::PREC_I8 && !SCALED) ? 1 : 0);
         SSB_CUDA_TRY(cudaGetLastError());
         if (a.launches) *a.launches += PREC == tc::PREC_TF32 ? 3 : 2;   // (tf32 query split +) scan + kth
@@ -644,8 +650,8 @@ static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec
         return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true>(a, st) : launch_tc_n<128, tc::PREC_I8, false>(a, st);
     }
     if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }
-    if ((nq_tile != 64 && nq_tile != 128) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 scan: query count must be padded to the 64/128 query tile"); return SSB_E_INVALID; }
-    if (prec == 1) return nq_tile == 64 ? launch_tc_n<64, tc::PREC_BF16>(a, st) : launch_tc_n<128, tc::PREC_BF16>(a, st);
+    if ((nq_tile != 64 && nq_tile != 128 && !(nq_tile == 256 && prec == 1)) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 scan: query count must be padded to the 64/128(/256 bf16) query tile"); return SSB_E_INVALID; }
+    if (prec == 1) return nq_tile == 64 ? launch_tc_n<64, tc::PREC_BF16>(a, st) : (nq_tile == 256 ? launch_tc_n<256, tc::PREC_BF16>(a, st) : launch_tc_n<128, tc::PREC_BF16>(a, st));
     return nq_tile == 64 ? launch_tc_n<64, tc::PREC_TF32>(a, st) : launch_tc_n<128, tc::PREC_TF32>(a, st);
 }
 
@@ -658,8 +664,9 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int prec, cudaStream
     // 256-row tile per CTA as for a handful of tiles: sample one tile per SM.  (An earlier version ran the normal list epilogue
     // over N/128 rows: ~90 us per pass, and ncu showed the full scan's epilogue warps waiting on list loads for candidates that
     // a better seed rejects.)
-    uint64_t s = (uint64_t)a.n_sms * tc::TROWS;
-    if (s > a.n_rows / 4) s = a.n_rows / 4 / tc::TROWS * tc::TROWS;
+    const uint64_t trows = nq_tile == 256 ? 128 : tc::TROWS;      // rows per stage of the variant that will run
+    uint64_t s = (uint64_t)a.n_sms * trows;
+    if (s > a.n_rows / 4) s = a.n_rows / 4 / trows * trows;
     pre.n_rows = s; pre.ev0 = nullptr; pre.ev1 = nullptr;
     pre.sample_groupmax = true;                          // writes the thresholds straight into thr_buf
     SSB_TRY(launch_scan_tc_impl(pre, nq_tile, prec, st));

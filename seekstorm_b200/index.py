@@ -248,7 +248,7 @@ class Index:
             self.add_vector_level(first_level + s // 65536, rows[s:min(n, s + 65536)])
 
     def set_vector_kernel(self, kernel: int):
-        """0 = auto, 1 = FP32 FFMA2 scan, 2/3 = tcgen05 3xTF32 (128/64 queries per pass), 4/5 = tcgen05 3xBF16 (128/64)."""
+        """0 = auto, 1 = FP32 FFMA2 scan, 2/3 = tcgen05 3xTF32 (128/64 queries per pass), 4/5/6 = tcgen05 3xBF16 (128/64/256)."""
         check(lib().ssb_set_vector_kernel(self._h, kernel))
 
     @property

@@ -222,7 +222,7 @@ def test_errors_are_status_codes():
     ix.close()
 
 
-@pytest.mark.parametrize("kernel", [2, 3, 4, 5])
+@pytest.mark.parametrize("kernel", [2, 3, 4, 5, 6])
 @pytest.mark.parametrize("n,dims,sim", [(300, 32, "dot"), (5000, 128, "cos"), (40000, 768, "cos"), (1000, 100, "dot")])
 def test_vector_tcgen05_parity(n, dims, sim, kernel):
     """tcgen05 (3xTF32 split, TMEM accumulators) scan vs the oracle: same ids, scores within 1e-4 relative."""
@@ -232,7 +232,7 @@ def test_vector_tcgen05_parity(n, dims, sim, kernel):
     rows = synth.gen_vectors(n, dims, 3000 + n, "cpu").numpy()
     qs = synth.gen_vectors(150, dims, 4000 + n, "cpu").numpy()      # 150 -> padded to 256 = two query groups
     qs[3] = rows[n // 2] + 0.05 * qs[3]
-    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_kernel=kernel)   # 2/3: 3xTF32 (128/64 queries per pass), 4/5: 3xBF16
+    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_kernel=kernel)   # 2/3: 3xTF32 (128/64 queries per pass), 4/5/6: 3xBF16 (128/64/256)
     ix.add_vectors(rows)
     ref_rows = np.stack([O.normalize(r) for r in rows]) if sim == "cos" else rows
     for k in (10, 32):

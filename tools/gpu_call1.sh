@@ -49,3 +49,13 @@ for f in sorted(glob.glob("gpurun_out/c1_bm25_*.json")):
         b = json.load(open(f))["bm25"]; print(f, round(b["value"]), {k: round(v["value"]) for k, v in b["variants"].items()}, b["roofline"]["kernel_ms"])
     except Exception as e: print(f, "parse", e)
 PY
+# vector kernels A/B: FP32, bf16 128-query tile, bf16 256-query tile
+timeout 400 python bench.py --sections "" --vector-kernel all --cpu-seconds 0 --steps 20 > gpurun_out/c1_vec_all.json 2> gpurun_out/c1_vec_all.err
+python - <<'PY'
+import json
+try:
+    d = json.load(open("gpurun_out/c1_vec_all.json"))
+    for k, v in d["kernels"].items(): print(k, round(v["value"]), round(v["e2e"]["value"]), v["roofline"]["kernel_ms"], v["roofline"]["frac"])
+    print("sweep", d.get("batch_sweep_e2e"))
+except Exception as e: print("vec parse", e)
+PY
