@@ -15,7 +15,7 @@ if what in ("tcb", "ffma", "i8"):
     nq = {"tcb": 256, "ffma": 16, "i8": 1024}[what]
     q = synth.gen_vectors(nq, d, 2002, "cuda")
     keys = torch.zeros((nq, 32), dtype=torch.int64, device="cuda")
-    ix.set_vector_kernel({"tcb": 4, "ffma": 1, "i8": 0}[what])
+    ix.set_vector_kernel(int(os.environ.get("SSB_PROF_KERNEL", {"tcb": 4, "ffma": 1, "i8": 0}[what])))
     for _ in range(3):
         ix.search_vector_keys(q, 10, keys); torch.cuda.synchronize()
 else:
