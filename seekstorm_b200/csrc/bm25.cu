@@ -57,6 +57,7 @@ constexpr uint32_t ENT_NONE = 0xFFFFu;
 constexpr uint32_t GMAX = 8;            // records (levels) per work item
 constexpr uint32_t ITEM_W = 4096;       // target size of an item: postings of its top-ranked lists (+64 per record)
 constexpr uint32_t QCAP = 192;          // survivor queue slots per warp: < 32 pending + 4 x 32 pushed per iteration
+constexpr float Q8_STEP = (2.2f * 1.01f) / 255.0f;   // coarse byte bounds: components are < K + 1 = 2.2 (fp16 round-up included in the 1 %)
 constexpr float INFL = 1.000002f;       // bound inflation covering the fp16 round-up + different association of <= 4 additions
 
 // ================================================================= build kernels
@@ -96,10 +97,12 @@ __device__ __forceinline__ float comp_of(const LexView& v, uint32_t payload) {
     return __fdiv_rn(__fmul_rn(tf, v.k1p), __fadd_rn(tf, __ldg(&v.cache[(payload >> 16) & 255u])));
 }
 
-__global__ void fill_bounds(LexView v, uint32_t* __restrict__ post, uint64_t n) {
+__global__ void fill_bounds(LexView v, uint32_t* __restrict__ post, float* __restrict__ comp, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const __half h = __float2half_ru(comp_of(v, v.pay[i]));       // rounded UP: idf*h >= idf*comp
+    const float c = comp_of(v, v.pay[i]);
+    comp[i] = c;                                                  // the IEEE divide + cache lookup happen once, here
+    const __half h = __float2half_ru(c);                          // rounded UP: idf*h >= idf*comp
     post[i] = (post[i] & 0xFFFFu) | ((uint32_t)__half_as_ushort(h) << 16);
 }
 
@@ -128,7 +131,7 @@ __global__ void entry_maxcomp(LexView v, uint32_t n_entries, float* __restrict__
     int lane = threadIdx.x & 31;
     uint64_t off = v.e_off[e]; uint32_t cnt = v.e_count[e];
     float m = 0.f;
-    for (uint32_t i = lane; i < cnt; i += 32) m = fmaxf(m, comp_of(v, v.pay[off + i]));
+    for (uint32_t i = lane; i < cnt; i += 32) m = fmaxf(m, v.comp[off + i]);
     for (int s = 16; s; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
     if (lane == 0) out[e] = m;
 }
@@ -144,18 +147,21 @@ __global__ void assign_bitmap(const uint32_t* __restrict__ e_count, const uint32
 // one CTA (256 threads) per dense entry
 __global__ void __launch_bounds__(256) build_bitmaps(const uint32_t* __restrict__ e_bitmap, const uint64_t* __restrict__ e_off,
                                                      const uint32_t* __restrict__ e_count, uint32_t n_entries,
-                                                     const uint32_t* __restrict__ post, uint64_t* bm_words, uint16_t* bm_rank,
-                                                     const uint32_t* __restrict__ dense_list) {
+                                                     const uint32_t* __restrict__ post, uint64_t* bm_words, BmSec* bm, uint8_t* bm_q8,
+                                                     float q8_step, const uint32_t* __restrict__ dense_list) {
     __shared__ unsigned long long w[1024];
     __shared__ uint32_t pc[1024];
+    __shared__ uint32_t mx[1024];      // fp16 bits of the word's largest bound (non-negative halves order like integers)
     uint32_t e = dense_list[blockIdx.x];
     uint32_t b = e_bitmap[e];
-    for (int i = threadIdx.x; i < 1024; i += 256) w[i] = 0ull;
+    for (int i = threadIdx.x; i < 1024; i += 256) { w[i] = 0ull; mx[i] = 0u; }
     __syncthreads();
     uint64_t off = e_off[e]; uint32_t cnt = e_count[e];
     for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
-        uint32_t d = post[off + i] & 0xFFFFu;
+        const uint32_t pw = post[off + i];
+        const uint32_t d = pw & 0xFFFFu;
         atomicOr(&w[d >> 6], 1ull << (d & 63));
+        atomicMax(&mx[d >> 6], pw >> 16);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 1024; i += 256) pc[i] = __popcll(w[i]);
@@ -173,9 +179,21 @@ __global__ void __launch_bounds__(256) build_bitmaps(const uint32_t* __restrict_
     }
     uint32_t run = part[threadIdx.x] - s4;
     for (int j = 0; j < 4; j++) {
-        int wi = 4 * threadIdx.x + j;
+        const int wi = 4 * threadIdx.x + j;
         bm_words[(size_t)b * 1024 + wi] = w[wi];
-        bm_rank[(size_t)b * 1024 + wi] = (uint16_t)run;
+        BmSec* sec = bm + (size_t)b * 512 + (wi >> 1);
+        sec->w[wi & 1] = w[wi];
+        sec->meta[wi & 1] = (run & 0xFFFFu) | (mx[wi] << 16);
+        sec->pad[wi & 1] = 0u;
+        // coarse byte bound: the smallest q with q * step >= word maximum (checked in float, the way the kernels evaluate it)
+        uint32_t q = 0;
+        if (w[wi]) {
+            const float h = __half2float(__ushort_as_half((unsigned short)mx[wi]));
+            q = (uint32_t)ceilf(h / q8_step);
+            while ((float)q * q8_step < h) q++;
+            q = q < 1u ? 1u : (q > 255u ? 255u : q);
+        }
+        bm_q8[(size_t)b * 1024 + wi] = (uint8_t)q;
         run += pc[wi];
     }
 }
@@ -396,9 +414,10 @@ struct TermRegs {   // generic path: lane t holds query term t of the current it
 // membership + rank probe of doc d in the list described by (cnt, off, bmi)
 __device__ __forceinline__ bool probe(const LexView& v, uint32_t cnt, uint64_t off, uint32_t bmi, uint32_t d, uint32_t& rank) {
     if (bmi != NONE) {
-        // both loads depend only on d: issue them together (one memory latency instead of two)
-        const uint64_t w = __ldg(&v.bm_words[(size_t)bmi * 1024 + (d >> 6)]);
-        const uint32_t r0 = (uint32_t)__ldg(&v.bm_rank[(size_t)bmi * 1024 + (d >> 6)]);
+        // word + rank sit in the same 32-byte sector: one DRAM access, two independent loads
+        const BmSec* sec = v.bm + (size_t)bmi * 512 + (d >> 7);
+        const uint64_t w = __ldg(&sec->w[(d >> 6) & 1u]);
+        const uint32_t r0 = __ldg(&sec->meta[(d >> 6) & 1u]) & 0xFFFFu;
         rank = r0 + (uint32_t)__popcll(w & ((1ull << (d & 63)) - 1ull));
         return ((w >> (d & 63)) & 1ull) != 0;
     }
@@ -418,8 +437,8 @@ __device__ __forceinline__ bool present_in(const LexView& v, uint32_t cnt, uint6
 }
 
 __device__ __forceinline__ float term_score(const LexView& v, float idf, uint64_t pos) {
-    // idf * ((tf*(K+1)/(tf+comp)) + SIGMA), SIGMA = 0 (x + 0.0 == x)
-    return __fmul_rn(idf, comp_of(v, __ldg(&v.pay[pos])));
+    // idf * ((tf*(K+1)/(tf+comp)) + SIGMA), SIGMA = 0 (x + 0.0 == x); the bracket is precomputed at commit (fill_bounds)
+    return __fmul_rn(idf, __ldg(&v.comp[pos]));
 }
 
 // shard.delete_hashset.contains(docid) (add_result.rs:3435): one table lookup + one bitmap word, only for exact-score survivors
@@ -478,7 +497,7 @@ struct ItemCtx {
     bool scoring, need_count, is_and;
 };
 
-struct WarpSm { LvRec recs[GMAX]; uint2 queue[QCAP]; const QueryPlan* pl; uint32_t n_not; uint32_t pad; };   // 1024 + 1536 + 16 B per warp
+struct WarpSm { LvRec recs[GMAX]; uint2 queue[QCAP]; uint4 q2[64]; const QueryPlan* pl; uint32_t n_not; uint32_t nq2; uint32_t it_base; unsigned it_mask; uint32_t pad[2]; };   // 1024 + 1536 + 1024 + 32 B per warp
 
 // thresholds derived from the ordered-uint k-th score `thr` (0 = list not full yet): BM25 scores are non-negative, so
 // the per-posting tests are plain float compares against thr_lo = thr_f / INFL (rounded down).
@@ -487,62 +506,42 @@ struct Thr {
     __device__ __forceinline__ void set(uint32_t t) { u = t; lo = t ? __fdiv_rd(unord_f32(t), INFL) : -1.0f; }
 };
 
-// ---- stages 2 + 3 on up to 32 queued survivors (one per lane; lanes may belong to different records / drivers) ----
+// ---- stage 3 on up to 32 survivors of stage 2 (queue 2, full lanes): exact in-query-order score (add_result.rs:1450-1452).
+// Entry: x = pos(17) | record(3) | driver rank(2) | 4 x 2 flag bits (0 absent, 1 present at the stored rank, 3 no bitmap: search),
+// y = the driver's posting word, z / w = posting ranks of slots 0..3 inside their lists (u16 each).  Every address is known up front:
+// the component loads of all terms are independent (one memory latency), the IEEE divide and the cache lookup happened at commit.
 template <bool IS_AND, bool HAS_NOT>
-__device__ __forceinline__ void process_queued(const LexView& v, const WarpSm& w, uint2 e, bool active, int lane, uint32_t k, uint64_t ceil,
-                                               uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
+__device__ __forceinline__ void score_queued(const LexView& v, const WarpSm& w, uint4 e, bool active, int lane, uint32_t k, uint64_t ceil,
+                                             uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
     const uint32_t pos = e.x & 0x1FFFFu, ri = (e.x >> 17) & 7u, p = (e.x >> 20) & 3u;
     const uint32_t d = e.y & 0xFFFFu;
     const LvRec& rec = w.recs[ri];
     const uint32_t meta = rec.meta;
     const uint32_t drv = IS_AND ? meta_anddrv(meta) : meta_perm(meta, p);
-    const float didf = rec.idf[drv];
-    // ---- stage 2: replace the level-wide bound by what the bitmaps say about THIS doc.  One 8-byte load per bitmap-backed
-    // term gives membership: (OR) a doc that is in an earlier-ranked list was already emitted there, and a term the doc is
-    // not in contributes nothing; (AND) a doc missing from any list is dead.  Lists without a bitmap count as "maybe".
-    uint64_t bw[FAST_T];
-    uint32_t bmi[FAST_T], cnts[FAST_T];
+    bool alive = active;
+    float comp[FAST_T];
 #pragma unroll
     for (uint32_t s = 0; s < FAST_T; s++) {
-        cnts[s] = slot_cnt(rec.t[s]); bmi[s] = rec.t[s].bmi;
-        const bool need = active && s != drv && cnts[s] != 0 && bmi[s] != NONE;
-        bw[s] = need ? __ldg(&v.bm_words[(size_t)bmi[s] * 1024 + (d >> 6)]) : 0ull;
+        const uint32_t fl = s == drv ? 1u : ((e.x >> (22 + 2 * s)) & 3u);
+        const uint32_t rank = s == drv ? pos : ((s & 2 ? e.w : e.z) >> (16 * (s & 1))) & 0xFFFFu;
+        comp[s] = 0.f;
+        if (active && fl == 1u) comp[s] = __ldg(&v.comp[slot_off(rec.t[s]) + rank]);
     }
-    float B = didf * bound_of_word(e.y);
-    bool dead = !active;
-#pragma unroll
-    for (uint32_t s = 0; s < FAST_T; s++) {
-        if (s == drv || cnts[s] == 0) continue;
-        const uint32_t rk = meta_rank(meta, s);
-        const float ub = rec.t[s].ub;
-        if (bmi[s] != NONE) {
-            const bool pres = ((bw[s] >> (d & 63)) & 1ull) != 0;
-            if (IS_AND) { if (!pres) dead = true; else B += ub; }
-            else if (pres) { if (rk < p) dead = true; else B += ub; }
-        } else if (IS_AND || rk > p) B += ub;
-    }
-    bool alive = !dead && B >= thr.lo;
-    if (!__any_sync(FULL, alive)) return;
-    // ---- stage 3: exact in-query-order score (add_result.rs:1450-1452) of the survivors ----
     float score = 0.f;
-    if (alive) {
-        const uint64_t doff = slot_off(rec.t[drv]);
 #pragma unroll
-        for (uint32_t s = 0; s < FAST_T; s++) {
-            if (cnts[s] == 0 || !alive) continue;
-            if (s == drv) { score = __fadd_rn(score, __fmul_rn(didf, comp_of(v, __ldg(&v.pay[doff + pos])))); continue; }
+    for (uint32_t s = 0; s < FAST_T; s++) {
+        if (!alive) continue;
+        const uint32_t fl = s == drv ? 1u : ((e.x >> (22 + 2 * s)) & 3u);
+        if (fl == 0u) continue;
+        float c = comp[s];
+        if (fl == 3u) {                                      // list without a bitmap (< 256 postings): binary search now
+            uint32_t rank; st_probes++;
             const uint64_t soff = slot_off(rec.t[s]);
-            bool pres; uint32_t rank;
-            st_probes++;
-            if (bmi[s] != NONE) {
-                pres = ((bw[s] >> (d & 63)) & 1ull) != 0;
-                if (pres) rank = (uint32_t)__ldg(&v.bm_rank[(size_t)bmi[s] * 1024 + (d >> 6)]) + (uint32_t)__popcll(bw[s] & ((1ull << (d & 63)) - 1ull));
-            } else pres = probe(v, cnts[s], soff, NONE, d, rank);
-            if (pres) {
-                if (!IS_AND && meta_rank(meta, s) < p) alive = false;   // already emitted when that term was the driver
-                else score = __fadd_rn(score, __fmul_rn(rec.idf[s], comp_of(v, __ldg(&v.pay[soff + rank]))));
-            } else if (IS_AND) alive = false;
+            if (!probe(v, slot_cnt(rec.t[s]), soff, NONE, d, rank)) { if (IS_AND) alive = false; continue; }
+            if (!IS_AND && meta_rank(meta, s) < p) { alive = false; continue; }   // already emitted when that term was the driver
+            c = __ldg(&v.comp[soff + rank]);
         }
+        score = __fadd_rn(score, __fmul_rn(rec.idf[s], c));
     }
     uint32_t t = thr.u;
     alive = alive && ord_f32(score) >= thr.u;
@@ -552,37 +551,132 @@ __device__ __forceinline__ void process_queued(const LexView& v, const WarpSm& w
     if (t != thr.u) thr.set(t);
 }
 
-// drain full batches of the survivor queue; keeps < 32 entries at the front
+// ---- stage 2 on up to 32 survivors of the stream filter (queue 1; lanes may belong to different records / drivers): replace the
+// level-wide bound by what the bitmap sectors say about THIS doc.  One 32-byte sector per bitmap-backed term holds the membership
+// word, the posting rank before the word and the largest fp16 bound of the word's 64 docs: (OR) a doc that is in an earlier-ranked
+// list was already emitted there, a term the doc is not in contributes nothing, and a term it is in contributes at most
+// idf * (word maximum); (AND) a doc missing from any list is dead.  Lists without a bitmap count as "maybe".  Survivors go to
+// queue 2 together with the ranks found, so that stage 3 runs on 32 of them at a time. ----
+template <bool IS_AND, bool HAS_NOT>
+__device__ __forceinline__ void filter_queued(const LexView& v, WarpSm& w, uint2 e, bool active, bool flush2, int lane, uint32_t k, uint64_t ceil,
+                                              uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
+    const uint32_t ri = (e.x >> 17) & 7u, p = (e.x >> 20) & 3u;
+    const uint32_t d = e.y & 0xFFFFu;
+    const LvRec& rec = w.recs[ri];
+    const uint32_t meta = rec.meta;
+    const uint32_t drv = IS_AND ? meta_anddrv(meta) : meta_perm(meta, p);
+    uint64_t bw[FAST_T]; uint32_t bm[FAST_T];
+    uint32_t bmi[FAST_T], cnts[FAST_T];
+#pragma unroll
+    for (uint32_t s = 0; s < FAST_T; s++) {
+        cnts[s] = slot_cnt(rec.t[s]); bmi[s] = rec.t[s].bmi;
+        const bool need = active && s != drv && cnts[s] != 0 && bmi[s] != NONE;
+        const BmSec* sec = v.bm + (size_t)bmi[s] * 512 + (d >> 7);
+        bw[s] = need ? __ldg(&sec->w[(d >> 6) & 1u]) : 0ull;
+        bm[s] = need ? __ldg(&sec->meta[(d >> 6) & 1u]) : 0u;          // same sector as the word
+    }
+    float B = rec.idf[drv] * bound_of_word(e.y);
+    bool dead = !active;
+    uint32_t flags = 0, r01 = 0, r23 = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < FAST_T; s++) {
+        if (s == drv || cnts[s] == 0) continue;
+        const uint32_t rk = meta_rank(meta, s);
+        if (bmi[s] != NONE) {
+            const bool pres = ((bw[s] >> (d & 63)) & 1ull) != 0;
+            if (!pres) { if (IS_AND) dead = true; continue; }
+            if (!IS_AND && rk < p) { dead = true; continue; }
+            B += rec.idf[s] * bound_of_word(bm[s]);                       // meta = rank16 | (fp16 word maximum) << 16
+            const uint32_t rank = (bm[s] & 0xFFFFu) + (uint32_t)__popcll(bw[s] & ((1ull << (d & 63)) - 1ull));
+            flags |= 1u << (2 * s);
+            if (s & 2) r23 |= rank << (16 * (s & 1)); else r01 |= rank << (16 * (s & 1));
+        } else {
+            if (IS_AND || rk > p) B += rec.t[s].ub;
+            flags |= 3u << (2 * s);
+        }
+    }
+    const bool alive = !dead && B >= thr.lo;
+    const unsigned m = __ballot_sync(FULL, alive);
+    uint32_t n2 = w.nq2;
+    if (alive) w.q2[n2 + __popc(m & ((1u << lane) - 1u))] = make_uint4((e.x & 0x3FFFFFu) | (flags << 22), e.y, r01, r23);
+    n2 += __popc(m);
+    __syncwarp();
+#pragma unroll 1
+    while (n2 >= 32u || (flush2 && n2)) {                    // the ONE place exact scores are computed (code size: instruction cache)
+        const bool act = (uint32_t)lane < n2;
+        const uint4 e4 = act ? w.q2[lane] : make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        score_queued<IS_AND, HAS_NOT>(v, w, e4, act, lane, k, ceil, L, thr, dirty, st_probes);
+        const uint32_t rem = n2 > 32u ? n2 - 32u : 0u;
+        uint4 tmp = make_uint4(0u, 0u, 0u, 0u);
+        if ((uint32_t)lane < rem) tmp = w.q2[32 + lane];
+        __syncwarp();
+        if ((uint32_t)lane < rem) w.q2[lane] = tmp;
+        n2 = rem;
+        __syncwarp();
+    }
+    if (lane == 0) w.nq2 = n2;
+    __syncwarp();
+}
+
+// drain full batches of the survivor queue; keeps < 32 entries at the front.  flush: everything goes, queue 2 included (one
+// batch runs even when queue 1 is empty, so that the leftovers of queue 2 get their exact score).
 template <bool IS_AND, bool HAS_NOT>
 __device__ __forceinline__ void drain_queue(const LexView& v, WarpSm& w, uint32_t& nq_in, bool flush, int lane, uint32_t k, uint64_t ceil,
                                             uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
     uint32_t head = 0;
-    while (nq_in - head >= 32u || (flush && nq_in > head)) {
+#pragma unroll 1
+    for (;;) {
         const bool act = head + (uint32_t)lane < nq_in;
+        const bool lastb = flush && head + 32u >= nq_in;
         const uint2 e = act ? w.queue[head + lane] : make_uint2(0u, 0u);
-        process_queued<IS_AND, HAS_NOT>(v, w, e, act, lane, k, ceil, L, thr, dirty, st_probes);
-        head += 32u;
-        if (head > nq_in) head = nq_in;
+        filter_queued<IS_AND, HAS_NOT>(v, w, e, act, lastb, lane, k, ceil, L, thr, dirty, st_probes);
+        head = head + 32u < nq_in ? head + 32u : nq_in;
+        if (flush ? head >= nq_in : nq_in - head < 32u) break;
     }
-    if (head) {
-        const uint32_t rem = nq_in - head;
-        uint2 tmp = make_uint2(0u, 0u);
-        if ((uint32_t)lane < rem) tmp = w.queue[head + lane];
-        __syncwarp();
-        if ((uint32_t)lane < rem) w.queue[lane] = tmp;
-        __syncwarp();
-        nq_in = rem;
-    }
+    const uint32_t rem = nq_in - head;
+    uint2 tmp = make_uint2(0u, 0u);
+    if ((uint32_t)lane < rem) tmp = w.queue[head + lane];
+    __syncwarp();
+    if ((uint32_t)lane < rem) w.queue[lane] = tmp;
+    __syncwarp();
+    nq_in = rem;
 }
 
-// stream one list 128 postings per iteration (one 16-byte load per lane) and queue the postings whose bound reaches θ
+// coarse per-word bounds of the terms a driven posting may still collect from (OR: MAXSCORE rank > p; AND: every other term):
+// dense lists contribute cf * q8[d >> 6] (q8 = 0: no posting of that term within the 64 docs around d), the others their list
+// maximum, folded into `base`.  Warp-uniform.
+struct Coarse { uint32_t off[FAST_T - 1]; float cf[FAST_T - 1]; uint32_t n; float base; };
+
+template <bool IS_AND>
+__device__ __forceinline__ Coarse coarse_of(const LexView& v, const LvRec& rec, uint32_t drv, uint32_t p) {
+    Coarse c; c.n = 0; c.base = 0.f;
+#pragma unroll
+    for (uint32_t j = 0; j < FAST_T - 1; j++) { c.off[j] = 0; c.cf[j] = 0.f; }
+#pragma unroll
+    for (uint32_t s = 0; s < FAST_T; s++) {
+        if (s == drv || slot_cnt(rec.t[s]) == 0) continue;
+        if (!IS_AND && meta_rank(rec.meta, s) < p) continue;
+        if (rec.t[s].bmi != NONE) {
+#pragma unroll
+            for (uint32_t j = 0; j < FAST_T - 1; j++) if (j == c.n) { c.off[j] = rec.t[s].bmi * 1024u; c.cf[j] = rec.idf[s] * v.q8_step; }
+            c.n++;
+        } else c.base += rec.t[s].ub;
+    }
+    return c;
+}
+
+// stream one list 128 postings per iteration (one 16-byte load per lane) and queue the postings whose bound reaches θ.
+// The bound of a posting is idf * (its own fp16 component bound) + the coarse bounds of the other terms AT ITS DOC ID (a byte
+// per 64 docs, L1-resident: 1 KB per dense list) — the sector probes of stage 2 are only paid by postings that pass it.
 template <bool IS_AND, bool HAS_NOT>
 __device__ __forceinline__ void stream_driver(const LexView& v, WarpSm& w, uint32_t tag /* ri<<17 | p<<20 */, uint64_t doff, uint32_t dcnt,
-                                              float didf, float R, uint32_t& nq_in, int lane, uint32_t k, uint64_t ceil,
+                                              float didf, float R, const Coarse& co, bool flush, uint32_t& nq_in, int lane, uint32_t k, uint64_t ceil,
                                               uint64_t& L, Thr& thr, bool& dirty, uint32_t& st_probes) {
     // 32-bit indices relative to the 16-byte aligned start: the list occupies [r0, r1) of the words fetched
+    // (flush: dcnt = 0 and one empty iteration whose only effect is the final drain — one call site for everything downstream)
     const uint32_t r0 = (uint32_t)doff & 3u, r1 = r0 + dcnt;
-    const uint32_t n_it = (r1 + 127u) >> 7;
+    const uint32_t n_it = flush ? 1u : (r1 + 127u) >> 7;
     const uint4* src = reinterpret_cast<const uint4*>(v.post + (doff - r0)) + lane;
     uint32_t rel = 4u * lane;                                   // first word of this lane's vector
     uint4 nxt = rel < r1 ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
@@ -591,19 +685,37 @@ __device__ __forceinline__ void stream_driver(const LexView& v, WarpSm& w, uint3
         // software pipelining: the next 128 postings are requested before these are filtered
         src += 32;
         nxt = rel + 128u < r1 ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
-        const bool a0 = rel      >= r0 && rel      < r1 && fmaf(didf, bound_of_word(cur.x), R) >= thr.lo;
-        const bool a1 = rel + 1u >= r0 && rel + 1u < r1 && fmaf(didf, bound_of_word(cur.y), R) >= thr.lo;
-        const bool a2 = rel + 2u >= r0 && rel + 2u < r1 && fmaf(didf, bound_of_word(cur.z), R) >= thr.lo;
-        const bool a3 = rel + 3u >= r0 && rel + 3u < r1 && fmaf(didf, bound_of_word(cur.w), R) >= thr.lo;
-        if (!__any_sync(FULL, a0 | a1 | a2 | a3)) continue;
-        const uint32_t lt = (1u << lane) - 1u;
-        unsigned m;
-        m = __ballot_sync(FULL, a0); if (a0) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel      - r0) | tag, cur.x); nq_in += __popc(m);
-        m = __ballot_sync(FULL, a1); if (a1) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 1u - r0) | tag, cur.y); nq_in += __popc(m);
-        m = __ballot_sync(FULL, a2); if (a2) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 2u - r0) | tag, cur.z); nq_in += __popc(m);
-        m = __ballot_sync(FULL, a3); if (a3) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 3u - r0) | tag, cur.w); nq_in += __popc(m);
-        __syncwarp();
-        if (nq_in >= 32u) drain_queue<IS_AND, HAS_NOT>(v, w, nq_in, false, lane, k, ceil, L, thr, dirty, st_probes);
+        bool a0 = rel      >= r0 && rel      < r1 && fmaf(didf, bound_of_word(cur.x), R) >= thr.lo;
+        bool a1 = rel + 1u >= r0 && rel + 1u < r1 && fmaf(didf, bound_of_word(cur.y), R) >= thr.lo;
+        bool a2 = rel + 2u >= r0 && rel + 2u < r1 && fmaf(didf, bound_of_word(cur.z), R) >= thr.lo;
+        bool a3 = rel + 3u >= r0 && rel + 3u < r1 && fmaf(didf, bound_of_word(cur.w), R) >= thr.lo;
+        bool any = __any_sync(FULL, a0 | a1 | a2 | a3);
+        if (any && co.n) {
+            float b0 = fmaf(didf, bound_of_word(cur.x), co.base), b1 = fmaf(didf, bound_of_word(cur.y), co.base);
+            float b2 = fmaf(didf, bound_of_word(cur.z), co.base), b3 = fmaf(didf, bound_of_word(cur.w), co.base);
+#pragma unroll
+            for (uint32_t j = 0; j < FAST_T - 1; j++) {
+                if (j >= co.n) break;
+                const uint8_t* tb = v.bm_q8 + co.off[j];
+                const uint32_t q0 = a0 ? __ldg(tb + ((cur.x & 0xFFFFu) >> 6)) : 0u, q1 = a1 ? __ldg(tb + ((cur.y & 0xFFFFu) >> 6)) : 0u;
+                const uint32_t q2 = a2 ? __ldg(tb + ((cur.z & 0xFFFFu) >> 6)) : 0u, q3 = a3 ? __ldg(tb + ((cur.w & 0xFFFFu) >> 6)) : 0u;
+                if (IS_AND) { a0 = a0 && q0; a1 = a1 && q1; a2 = a2 && q2; a3 = a3 && q3; }
+                b0 = fmaf(co.cf[j], (float)q0, b0); b1 = fmaf(co.cf[j], (float)q1, b1);
+                b2 = fmaf(co.cf[j], (float)q2, b2); b3 = fmaf(co.cf[j], (float)q3, b3);
+            }
+            a0 = a0 && b0 >= thr.lo; a1 = a1 && b1 >= thr.lo; a2 = a2 && b2 >= thr.lo; a3 = a3 && b3 >= thr.lo;
+            any = __any_sync(FULL, a0 | a1 | a2 | a3);
+        }
+        if (any) {
+            const uint32_t lt = (1u << lane) - 1u;
+            unsigned m;
+            m = __ballot_sync(FULL, a0); if (a0) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel      - r0) | tag, cur.x); nq_in += __popc(m);
+            m = __ballot_sync(FULL, a1); if (a1) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 1u - r0) | tag, cur.y); nq_in += __popc(m);
+            m = __ballot_sync(FULL, a2); if (a2) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 2u - r0) | tag, cur.z); nq_in += __popc(m);
+            m = __ballot_sync(FULL, a3); if (a3) w.queue[nq_in + __popc(m & lt)] = make_uint2((rel + 3u - r0) | tag, cur.w); nq_in += __popc(m);
+            __syncwarp();
+        }
+        if (nq_in >= 32u || flush) drain_queue<IS_AND, HAS_NOT>(v, w, nq_in, flush, lane, k, ceil, L, thr, dirty, st_probes);
     }
 }
 
@@ -694,33 +806,31 @@ __device__ __forceinline__ void score_records(const LexView& v, WarpSm& w, uint3
                                               const uint64_t* theta, int lane, uint64_t& L, Thr& thr, bool& dirty,
                                               uint32_t& st_visited, uint32_t& st_probes, uint32_t& st_recs, uint32_t& st_skipped) {
     uint32_t nq_in = 0;
-    for (uint32_t ri = 0; ri < nrec; ri++) {
-        const LvRec& rec = w.recs[ri];
+#pragma unroll 1
+    for (uint32_t ri = 0; ; ri++) {
+        // one extra pass (flush) after the last record — or after the first record the block-max test prunes — drains the queues
+        bool flush = ri >= nrec;
+        const LvRec& rec = w.recs[flush ? 0u : ri];
         const uint32_t meta = rec.meta;
-        if (ri) { const uint32_t t2 = (uint32_t)(__ldcg(&theta[q]) >> 32); if (t2 > thr.u) thr.set(t2); }   // other warps' progress
+        if (ri && !flush) { const uint32_t t2 = (uint32_t)(__ldcg(&theta[q]) >> 32); if (t2 > thr.u) thr.set(t2); }   // other warps' progress
         // block-max: records are sorted by bound, so the first one below θ ends the scoring of this item
         // (only strictly smaller bounds prune: intersection.rs:2227-2233, single.rs:386-394)
-        if (ord_f32(rec.bound) < thr.u) { st_skipped += nrec - ri; break; }
-        st_recs++;
-        if (IS_AND) {
-            const uint32_t drv = meta_anddrv(meta);
-            const uint32_t dcnt = slot_cnt(rec.t[drv]);
+        if (!flush && ord_f32(rec.bound) < thr.u) { st_skipped += nrec - ri; flush = true; }
+        if (!flush) st_recs++;
+        const uint32_t np = (IS_AND || flush) ? 1u : meta_npres(meta);
+#pragma unroll 1
+        for (uint32_t p = 0; p < np; p++) {
+            // OR, MAXSCORE: a list is essential while the in-query-order sum of the not-yet-driven bounds can reach θ (the role
+            // of union_docid_2/3's "single pass only if max_list_score > heap.min", union.rs:1259-1301, 1371-1412)
+            if (!IS_AND && !flush && ord_f32(rec.S[p]) < thr.u) break;
+            const uint32_t drv = IS_AND ? meta_anddrv(meta) : meta_perm(meta, p);
+            const uint32_t dcnt = flush ? 0u : slot_cnt(rec.t[drv]);
             st_visited += dcnt;
-            stream_driver<true, HAS_NOT>(v, w, ri << 17, slot_off(rec.t[drv]), dcnt, rec.idf[drv], rec.R[0], nq_in, lane, k, ceil, L, thr, dirty, st_probes);
-        } else {
-            const uint32_t np = meta_npres(meta);
-            for (uint32_t p = 0; p < np; p++) {
-                // MAXSCORE: a list is essential while the in-query-order sum of the not-yet-driven bounds can reach θ (the role
-                // of union_docid_2/3's "single pass only if max_list_score > heap.min", union.rs:1259-1301, 1371-1412)
-                if (ord_f32(rec.S[p]) < thr.u) break;
-                const uint32_t drv = meta_perm(meta, p);
-                const uint32_t dcnt = slot_cnt(rec.t[drv]);
-                st_visited += dcnt;
-                stream_driver<false, HAS_NOT>(v, w, (ri << 17) | (p << 20), slot_off(rec.t[drv]), dcnt, rec.idf[drv], rec.R[p], nq_in, lane, k, ceil, L, thr, dirty, st_probes);
-            }
+            stream_driver<IS_AND, HAS_NOT>(v, w, (ri << 17) | (p << 20), flush ? 0ull : slot_off(rec.t[drv]), dcnt, rec.idf[drv],
+                                           rec.R[IS_AND ? 0u : p], coarse_of<IS_AND>(v, rec, drv, p), flush, nq_in, lane, k, ceil, L, thr, dirty, st_probes);
         }
+        if (flush) break;
     }
-    if (nq_in) drain_queue<IS_AND, HAS_NOT>(v, w, nq_in, true, lane, k, ceil, L, thr, dirty, st_probes);
 }
 
 // ---- generic path: up to SSB_MAX_QUERY_TERMS live terms, lane t holds term t, values broadcast by shuffles ----
@@ -852,11 +962,32 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
 
 // claim the next work item: wave order — item i -> (j = i / nq, q = i % nq) = the j-th item of query q, so every query's best
 // levels are scored first and its θ is published before most of its other items start
-__device__ __forceinline__ bool next_item(uint32_t* counter, uint64_t total, uint32_t nq, int lane, uint32_t& j, uint32_t& q) {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(counter, 1u);
-    i = __shfl_sync(FULL, i, 0);
-    if ((uint64_t)i >= total) return false;
+// Work distribution: item index i -> (j = i / nq, q = i % nq), i.e. the first items of all queries, then the second ones, ...
+// A warp takes ITEM_CHUNK consecutive indices per atomic; its lanes test them in parallel (most indices of the later waves
+// name items a query does not have) and the warp then works through the valid ones.
+constexpr uint32_t ITEM_CHUNK = 8;
+template <bool FAST>
+__device__ __forceinline__ bool next_item(WarpSm& it, uint32_t* counter, uint64_t total, uint32_t nq, const QueryPlan* __restrict__ plans,
+                                          int lane, uint32_t& j, uint32_t& q) {
+    unsigned mask = it.it_mask; uint32_t base = it.it_base;      // warp-private shared memory: keeps two registers out of the hot loops
+    __syncwarp();
+    while (!mask) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(counter, ITEM_CHUNK);
+        b = __shfl_sync(FULL, b, 0);
+        if ((uint64_t)b >= total) return false;
+        const uint64_t i = (uint64_t)b + (uint32_t)lane;
+        bool ok = (uint32_t)lane < ITEM_CHUNK && i < total;
+        if (ok) {
+            const uint32_t jj = (uint32_t)(i / nq), qq = (uint32_t)(i - (uint64_t)jj * nq);
+            const QueryPlan* pl = &plans[qq];
+            ok = jj < __ldg(&pl->n_items) && ((__ldg(&pl->n_live) <= FAST_T) == FAST);
+        }
+        mask = __ballot_sync(FULL, ok); base = b;
+    }
+    const uint32_t i = base + (uint32_t)(__ffs(mask) - 1);
+    if (lane == 0) { it.it_mask = mask & (mask - 1); it.it_base = base; }
+    __syncwarp();
     j = i / nq; q = i - j * nq;
     return true;
 }
@@ -902,13 +1033,14 @@ __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const 
     const uint64_t total = (uint64_t)(*(volatile uint32_t*)&ctr[1]) * nq;
     uint32_t st_visited = 0, st_probes = 0, st_done = 0, st_skipped = 0, st_recs = 0;   // per warp: far below 2^32 each
     uint32_t j, q;
-    while (next_item(&ctr[0], total, nq, lane, j, q)) {
+    if (lane == 0) { w.it_mask = 0; w.it_base = 0; }
+    __syncwarp();
+    while (next_item<true>(w, &ctr[0], total, nq, plans, lane, j, q)) {
         const QueryPlan* pl = &plans[q];
-        if (j >= __ldg(&pl->n_items) || __ldg(&pl->n_live) > FAST_T) continue;
         const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
         if (ceil == 0) continue;                         // this query's result list is already exhausted
         const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
-        if (lane == 0) { w.pl = pl; w.n_not = __ldg(&pl->n_not); }
+        if (lane == 0) { w.pl = pl; w.n_not = __ldg(&pl->n_not); w.nq2 = 0; }
         __syncwarp();
         Thr thr; thr.set((uint32_t)(__ldcg(&theta[q]) >> 32));
         if (ord_f32(w.recs[0].bound) < thr.u) { st_skipped += nrec; continue; }   // whole item below θ
@@ -940,9 +1072,9 @@ __global__ void __launch_bounds__(256, 4) lex_count(LexView v, const QueryPlan* 
     const bool is_and = query_type == SSB_QUERY_INTERSECTION;
     uint64_t acc_visited = 0, acc_probes = 0, acc_words = 0; uint32_t st_recs = 0;
     uint32_t j, q;
-    while (next_item(&ctr[2], total, nq, lane, j, q)) {
-        const QueryPlan* pl = &plans[q];
-        if (j >= __ldg(&pl->n_items) || __ldg(&pl->n_live) > FAST_T) continue;
+    if (lane == 0) { w.it_mask = 0; w.it_base = 0; }
+    __syncwarp();
+    while (next_item<true>(w, &ctr[2], total, nq, plans, lane, j, q)) {
         const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
         uint32_t matches = 0, st_visited = 0, st_probes = 0, st_words = 0;
         for (uint32_t ri = 0; ri < nrec; ri++) matches += count_record(v, w.recs[ri], is_and, lane, st_visited, st_probes, st_words);
@@ -974,10 +1106,11 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
     const bool need_count = result_type != SSB_RESULT_TOPK;
     uint32_t st_visited = 0, st_probes = 0, st_done = 0, st_skipped = 0;
     uint32_t j, q;
-    while (next_item(&ctr[3], total, nq, lane, j, q)) {
+    if (lane == 0) { w.it_mask = 0; w.it_base = 0; }
+    __syncwarp();
+    while (next_item<false>(w, &ctr[3], total, nq, plans, lane, j, q)) {
         const QueryPlan* pl = &plans[q];
         const uint32_t n_live = __ldg(&pl->n_live);
-        if (j >= __ldg(&pl->n_items) || n_live <= FAST_T) continue;
         const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
         if (ceil == 0) continue;
         const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
@@ -1098,10 +1231,10 @@ LexIndex::~LexIndex() {
 void LexIndex::free_committed() {
     cudaFree(d_dict_keys_); cudaFree(d_term_first_); cudaFree(d_term_idf_); cudaFree(d_term_df_);
     cudaFree(d_e_level_); cudaFree(d_e_off_); cudaFree(d_e_count_); cudaFree(d_e_maxcomp_); cudaFree(d_e_bitmap_);
-    cudaFree(d_bm_words_); cudaFree(d_bm_rank_); cudaFree(d_level_ids_); cudaFree(d_cache_);
+    cudaFree(d_bm_words_); cudaFree(d_bm_); cudaFree(d_bm_q8_); cudaFree(d_level_ids_); cudaFree(d_cache_);
     d_dict_keys_ = nullptr; d_term_first_ = nullptr; d_term_idf_ = nullptr; d_term_df_ = nullptr;
     d_e_level_ = nullptr; d_e_off_ = nullptr; d_e_count_ = nullptr; d_e_maxcomp_ = nullptr; d_e_bitmap_ = nullptr;
-    d_bm_words_ = nullptr; d_bm_rank_ = nullptr; d_level_ids_ = nullptr; d_cache_ = nullptr;
+    d_bm_words_ = nullptr; d_bm_ = nullptr; d_bm_q8_ = nullptr; d_level_ids_ = nullptr; d_cache_ = nullptr;
     committed_ = false;
 }
 
@@ -1229,7 +1362,7 @@ LexView LexIndex::view() const {
     LexView v{};
     v.dict_keys = d_dict_keys_; v.n_terms = n_terms_; v.term_first = d_term_first_; v.term_idf = d_term_idf_; v.term_df = d_term_df_;
     v.e_level = d_e_level_; v.e_off = d_e_off_; v.e_count = d_e_count_; v.e_maxcomp = d_e_maxcomp_; v.e_bitmap = d_e_bitmap_;
-    v.post = post_.p; v.pay = pay_.p; v.bm_words = d_bm_words_; v.bm_rank = d_bm_rank_; v.level_ids = d_level_ids_;
+    v.post = post_.p; v.pay = pay_.p; v.comp = comp_.p; v.bm_words = d_bm_words_; v.bm = d_bm_; v.bm_q8 = d_bm_q8_; v.q8_step = Q8_STEP; v.level_ids = d_level_ids_;
     v.n_levels = (uint32_t)levels_.size(); v.cache = d_cache_;
     v.k1p = 1.2f + 1.0f;
     if (del_ && del_->n) { v.del_slot = del_->d_slot; v.del_words = del_->d_words; v.del_docs = del_->d_docs; v.n_del = del_->n; }
@@ -1262,7 +1395,8 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     if (n_post_) {
         LexView v{};
         v.pay = pay_.p; v.cache = d_cache_; v.k1p = 1.2f + 1.0f;
-        fill_bounds<<<(unsigned)((n_post_ + 255) / 256), 256, 0, st_>>>(v, post_.p, n_post_);
+        SSB_TRY(comp_.reserve(n_post_ + 160, 0, st_, true));
+        fill_bounds<<<(unsigned)((n_post_ + 255) / 256), 256, 0, st_>>>(v, post_.p, comp_.p, n_post_);
         SSB_CUDA_TRY(cudaGetLastError());
     }
     if (post_.p) SSB_CUDA_TRY(cudaMemsetAsync(post_.p + n_post_, 0, 160 * 4, st_));   // tail read by the vector loads
@@ -1337,11 +1471,12 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
         SSB_CUDA_TRY(cudaGetLastError());
         if (n_bitmaps_) {
             SSB_CUDA_TRY(cudaMalloc(&d_bm_words_, (size_t)n_bitmaps_ * 1024 * 8));
-            SSB_CUDA_TRY(cudaMalloc(&d_bm_rank_, (size_t)n_bitmaps_ * 1024 * 2));
+            SSB_CUDA_TRY(cudaMalloc(&d_bm_, (size_t)n_bitmaps_ * 512 * sizeof(BmSec)));
+            SSB_CUDA_TRY(cudaMalloc(&d_bm_q8_, (size_t)n_bitmaps_ * 1024));
             SSB_CUDA_TRY(t_dense.alloc(n_bitmaps_));
             uint32_t* d_dense = t_dense.p;
             compact_dense<<<(total + 255) / 256, 256, 0, st_>>>(d_e_bitmap_, total, d_dense);
-            build_bitmaps<<<n_bitmaps_, 256, 0, st_>>>(d_e_bitmap_, d_e_off_, d_e_count_, total, post_.p, d_bm_words_, d_bm_rank_, d_dense);
+            build_bitmaps<<<n_bitmaps_, 256, 0, st_>>>(d_e_bitmap_, d_e_off_, d_e_count_, total, post_.p, d_bm_words_, d_bm_, d_bm_q8_, Q8_STEP, d_dense);
             SSB_CUDA_TRY(cudaGetLastError());
             SSB_CUDA_TRY(cudaStreamSynchronize(st_));
         }

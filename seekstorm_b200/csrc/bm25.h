@@ -62,6 +62,12 @@ struct LexLevel {
     uint32_t* d_posting_offsets;   // [n_terms+1]
 };
 
+// One 32-byte DRAM sector of a dense list's probe structure: the membership words of 128 consecutive doc ids, and per word the
+// number of postings before it (rank, low 16 bits of meta) and the largest fp16 bound among its postings (high 16 bits): a probe
+// learns presence, the posting's index and a tight score bound from ONE sector.
+struct BmSec { uint64_t w[2]; uint32_t meta[2]; uint32_t pad[2]; };
+static_assert(sizeof(BmSec) == 32, "BmSec must be one 32-byte sector");
+
 // device view handed to the kernels (all pointers device)
 struct LexView {
     const uint64_t* dict_keys; uint32_t n_terms;
@@ -75,8 +81,11 @@ struct LexView {
     const uint32_t* e_bitmap;     // index into bm_* or 0xFFFFFFFF
     const uint32_t* post;         // stream arena: id16 | bound16<<16 (fp16 bits of the posting's score component, rounded UP)
     const uint32_t* pay;          // payload arena, same index: tf16 | doclen_byte<<16 (read for exact scores only)
-    const uint64_t* bm_words;     // [n_bitmaps][1024]
-    const uint16_t* bm_rank;      // [n_bitmaps][1024] postings before word w
+    const float* comp;            // component arena, same index: tf*(K+1)/(tf+cache[len]) as f32 (the exact score is idf * comp)
+    const uint64_t* bm_words;     // [n_bitmaps][1024] plain membership words (count algebra, NOT lists)
+    const BmSec* bm;              // [n_bitmaps][512] sector-packed membership + rank + per-word bound (scoring probes)
+    const uint8_t* bm_q8;         // [n_bitmaps][1024] coarse bound per 64-doc word: ceil(word maximum / q8_step), 0 = no posting
+    float q8_step;
     const uint32_t* level_ids;    // [n_levels]
     uint32_t n_levels;
     const float* cache;           // [256] bm25_component_cache
@@ -167,13 +176,14 @@ private:
     bool committed_ = false;
     std::vector<LexLevel> levels_;
     DevBuf<uint32_t> post_, pay_;
+    DevBuf<float> comp_;
     uint64_t n_post_ = 0;
     // committed structures
     uint64_t n_docs_ = 0, len_sum_ = 0;
     uint32_t n_terms_ = 0, n_entries_ = 0, n_bitmaps_ = 0;
     uint64_t* d_dict_keys_ = nullptr; uint32_t* d_term_first_ = nullptr; float* d_term_idf_ = nullptr; uint32_t* d_term_df_ = nullptr;
     uint32_t* d_e_level_ = nullptr; uint64_t* d_e_off_ = nullptr; uint32_t* d_e_count_ = nullptr; float* d_e_maxcomp_ = nullptr; uint32_t* d_e_bitmap_ = nullptr;
-    uint64_t* d_bm_words_ = nullptr; uint16_t* d_bm_rank_ = nullptr;
+    uint64_t* d_bm_words_ = nullptr; BmSec* d_bm_ = nullptr; uint8_t* d_bm_q8_ = nullptr;
     uint32_t* d_level_ids_ = nullptr; float* d_cache_ = nullptr;
     std::vector<uint64_t> h_dict_keys_; std::vector<uint32_t> h_term_df_, h_local_df_;
     const DeleteSet* del_ = nullptr;
