@@ -49,8 +49,10 @@
 namespace ssb {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr uint32_t DENSE_MIN = 256;     // lists at least this long get a bitmap + rank index (O(1) probes)
-constexpr uint32_t COUNT_DENSE = 512;   // lists at least this long are counted by bitmap-word algebra (8 KB stream < 512 sector probes)
+#ifndef SSB_DENSE_MIN
+#define SSB_DENSE_MIN 128
+#endif
+constexpr uint32_t DENSE_MIN = SSB_DENSE_MIN;     // lists at least this long get a bitmap + rank index (O(1) probes)
 constexpr uint32_t MAX_LEVELS = 4096;   // per GPU (268M docs); plan kernel smem bound
 constexpr uint32_t FAST_T = 4;          // queries with <= 4 live terms take the record path
 constexpr uint32_t ENT_NONE = 0xFFFFu;
@@ -682,7 +684,8 @@ __device__ __forceinline__ void stream_driver(const LexView& v, WarpSm& w, uint3
     uint4 nxt = rel < r1 ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t it = 0; it < n_it; it++, rel += 128u) {
         const uint4 cur = nxt;
-        // software pipelining: the next 128 postings are requested before these are filtered
+        // software pipelining: the next 128 postings are requested before these are filtered (two vectors ahead was measured:
+        // the extra registers spill and cost more than the deeper prefetch gains)
         src += 32;
         nxt = rel + 128u < r1 ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
         bool a0 = rel      >= r0 && rel      < r1 && fmaf(didf, bound_of_word(cur.x), R) >= thr.lo;
@@ -733,71 +736,179 @@ __device__ __forceinline__ void for_each_posting(const LexView& v, uint64_t doff
     }
 }
 
-// ---- exact match counts of one record (TopkCount / Count) ----
-// OR: |union| = (dense lists: popcount of the OR of their bitmap words, union_count union.rs:807-1164) + for every sparse list the
-// postings that are in no longer list (2 terms: df0 + df1 - |AND|, union.rs:1236-1244).  AND: popcount of the AND of the bitmap
-// words when every list is dense (intersection_bitmap_2, intersection.rs:33-108), else the shortest list probes the others.
-__device__ __forceinline__ uint32_t count_record(const LexView& v, const LvRec& rec, bool is_and, int lane, uint32_t& st_visited,
-                                                 uint32_t& st_probes, uint32_t& st_words) {
+// enumerate several lists of one record back to back, 128 postings per iteration, with the NEXT vector (of this or of the
+// following list) always in flight: f(list position, doc id, valid) 4x per lane per iteration; list_done(position) after a list's
+// last vector.  slot_of(position) names the record slot.
+template <class SlotOf, class F, class G>
+__device__ __forceinline__ void stream_lists(const LexView& v, const LvRec& rec, uint32_t nlists, int lane, SlotOf slot_of, F f, G list_done) {
+    if (nlists == 0) return;
+    uint32_t li = 0, r0n = 0, r1n = 0, reln = 0;
+    const uint4* srcn = nullptr;
+    auto open = [&](uint32_t i) {
+        const LvSlot& t = rec.t[slot_of(i)];
+        const uint64_t off = slot_off(t);
+        r0n = (uint32_t)off & 3u; r1n = r0n + slot_cnt(t); reln = 4u * lane;
+        srcn = reinterpret_cast<const uint4*>(v.post + (off - r0n)) + lane;
+    };
+    open(0);
+    // two vectors in flight per lane (1 KB per warp): the fetch position runs two steps ahead of the processing position
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4 q0, q1;                                                       // fetched vectors and what they are (a_*)
+    uint32_t a_r0[2], a_r1[2], a_rel[2], a_ci[2]; bool a_end[2], a_has[2];
+    auto fetch = [&](int k, uint4& dst) {
+        a_has[k] = li < nlists;
+        a_r0[k] = r0n; a_r1[k] = r1n; a_rel[k] = reln; a_ci[k] = li;
+        dst = (a_has[k] && reln < r1n) ? __ldg(srcn) : zero;
+        reln += 128u; srcn += 32;
+        a_end[k] = a_has[k] && (reln - 4u * lane >= r1n);               // warp-uniform
+        if (a_end[k]) { li++; if (li < nlists) open(li); }
+    };
+    fetch(0, q0); fetch(1, q1);
+    for (;;) {
+        const uint4 cur = q0;
+        const uint32_t r0 = a_r0[0], r1 = a_r1[0], rel = a_rel[0], ci = a_ci[0];
+        const bool end = a_end[0];
+        if (!a_has[0]) break;
+        q0 = q1; a_r0[0] = a_r0[1]; a_r1[0] = a_r1[1]; a_rel[0] = a_rel[1]; a_ci[0] = a_ci[1]; a_end[0] = a_end[1]; a_has[0] = a_has[1];
+        fetch(1, q1);
+        f(ci, cur.x & 0xFFFFu, rel      >= r0 && rel      < r1);
+        f(ci, cur.y & 0xFFFFu, rel + 1u >= r0 && rel + 1u < r1);
+        f(ci, cur.z & 0xFFFFu, rel + 2u >= r0 && rel + 2u < r1);
+        f(ci, cur.w & 0xFFFFu, rel + 3u >= r0 && rel + 3u < r1);
+        if (end) list_done(ci);
+    }
+}
+
+// counting kernels: a bitmap of the level's 65536 doc ids per warp in shared memory
+constexpr uint32_t UNION_WORDS = 2048;   // 8 KB of words vs 4 B per posting
+struct CountSm { LvRec recs[GMAX]; uint32_t bm[2048]; uint32_t it_base; unsigned it_mask; uint32_t pad[2]; };
+
+// ---- exact match count of one AND record (TopkCount / Count) ----
+// Every list >= UNION_WORDS postings: popcount of the AND of the bitmap words (intersection_bitmap_2, intersection.rs:33-108).
+// Otherwise the shortest list A marks its docs in the warp-private shared-memory bitmap and the second shortest list B is streamed
+// against it (4 B per posting, no global probes); hits are checked against the remaining lists.  When B is much longer than A,
+// A's postings probe the other lists instead (one 32-byte sector per probe).
+__device__ __forceinline__ uint32_t count_intersection(const LexView& v, const LvRec& rec, uint32_t* bm, int lane, uint32_t& st_visited,
+                                                       uint32_t& st_probes, uint32_t& st_words) {
     const uint32_t meta = rec.meta, np = meta_npres(meta);
     uint32_t acc = 0;
     if (np == 0) return 0;
-    if (is_and) {
-        const uint32_t drv = meta_anddrv(meta);
-        const uint32_t dcnt = slot_cnt(rec.t[drv]);
-        if (np == 1) return lane == 0 ? dcnt : 0u;
-        if (dcnt >= COUNT_DENSE) {
-            for (uint32_t wi = lane; wi < 1024u; wi += 32u) {
-                uint64_t a = ~0ull;
-                for (uint32_t c = 0; c < np; c++) a &= __ldg(&v.bm_words[(size_t)rec.t[meta_cperm(meta, c)].bmi * 1024 + wi]);
-                acc += (uint32_t)__popcll(a);
-            }
-            st_words += np * 32u;
-            return acc;
-        }
-        st_visited += dcnt;
-        for_each_posting(v, slot_off(rec.t[drv]), dcnt, lane, [&](uint32_t d, bool valid) {
-            bool ok = valid;
-            for (uint32_t c = 0; c < np; c++) {
-                const uint32_t s = meta_cperm(meta, c);
-                if (s == drv || !ok) continue;
-                st_probes++;
-                ok = present_in(v, slot_cnt(rec.t[s]), slot_off(rec.t[s]), rec.t[s].bmi, d);
-            }
-            acc += ok ? 1u : 0u;
-        });
-        return acc;
-    }
-    uint32_t n_dense = 0;
-    for (uint32_t c = 0; c < np; c++) n_dense += slot_cnt(rec.t[meta_cperm(meta, c)]) >= COUNT_DENSE ? 1u : 0u;   // cperm: cnt descending
-    uint32_t first_sparse = n_dense;
-    if (n_dense >= 2) {
+    const uint32_t sa = meta_cperm(meta, np - 1u);                       // cperm: count descending -> the shortest list
+    const uint32_t cnt_a = slot_cnt(rec.t[sa]);
+    if (np == 1) return lane == 0 ? cnt_a : 0u;
+    if (cnt_a >= UNION_WORDS) {
         for (uint32_t wi = lane; wi < 1024u; wi += 32u) {
-            uint64_t a = 0ull;
-            for (uint32_t c = 0; c < n_dense; c++) a |= __ldg(&v.bm_words[(size_t)rec.t[meta_cperm(meta, c)].bmi * 1024 + wi]);
+            uint64_t a = ~0ull;
+            for (uint32_t c = 0; c < np; c++) a &= __ldg(&v.bm_words[(size_t)rec.t[meta_cperm(meta, c)].bmi * 1024 + wi]);
             acc += (uint32_t)__popcll(a);
         }
-        st_words += n_dense * 32u;
-    } else {
-        if (lane == 0) acc += slot_cnt(rec.t[meta_cperm(meta, 0)]);     // the longest list counts in full
-        first_sparse = 1;
+        st_words += np * 32u;
+        return acc;
     }
-    for (uint32_t c = first_sparse; c < np; c++) {
-        const uint32_t s = meta_cperm(meta, c);
-        const uint32_t dcnt = slot_cnt(rec.t[s]);
-        st_visited += dcnt;
-        for_each_posting(v, slot_off(rec.t[s]), dcnt, lane, [&](uint32_t d, bool valid) {
-            bool fresh = valid;
-            for (uint32_t c2 = 0; c2 < c; c2++) {                          // longer lists
-                if (!fresh) continue;
-                const uint32_t s2 = meta_cperm(meta, c2);
+    const uint32_t sb = meta_cperm(meta, np - 2u);
+    const uint32_t cnt_b = slot_cnt(rec.t[sb]);
+    if (cnt_b <= 8u * cnt_a) {
+        uint4* b4 = reinterpret_cast<uint4*>(bm);
+        for (uint32_t i = lane; i < 512u; i += 32u) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        st_visited += cnt_a + cnt_b;
+        stream_lists(v, rec, 2u, lane, [&](uint32_t i) { return i ? sb : sa; },
+            [&](uint32_t i, uint32_t d, bool valid) {
+                if (i == 0) { if (valid) atomicOr(&bm[d >> 5], 1u << (d & 31u)); return; }
+                bool ok = valid && ((bm[d >> 5] >> (d & 31u)) & 1u);
+                for (uint32_t c = 0; c + 2u < np; c++) {                 // longer lists, rarely reached
+                    if (!ok) continue;
+                    const LvSlot& t = rec.t[meta_cperm(meta, c)];
+                    st_probes++;
+                    ok = present_in(v, slot_cnt(t), slot_off(t), t.bmi, d);
+                }
+                acc += ok ? 1u : 0u;
+            },
+            [&](uint32_t) { __syncwarp(); });
+        __syncwarp();
+        return acc;
+    }
+    st_visited += cnt_a;
+    stream_lists(v, rec, 1u, lane, [&](uint32_t) { return sa; },
+        [&](uint32_t, uint32_t d, bool valid) {
+            bool ok = valid;
+            for (uint32_t c = 0; c + 1u < np; c++) {
+                if (!ok) continue;
+                const LvSlot& t = rec.t[meta_cperm(meta, c)];
                 st_probes++;
-                if (present_in(v, slot_cnt(rec.t[s2]), slot_off(rec.t[s2]), rec.t[s2].bmi, d)) fresh = false;
+                ok = present_in(v, slot_cnt(t), slot_off(t), t.bmi, d);
             }
-            acc += fresh ? 1u : 0u;
-        });
-    }
+            acc += ok ? 1u : 0u;
+        },
+        [&](uint32_t) {});
     return acc;
+}
+
+// ---- |union| of one record through a warp-private bitmap of the level's 65536 doc ids in shared memory (8 KB) ----
+// Every list is read once, sequentially: lists of >= UNION_WORDS postings as their 8 KB of bitmap words (OR-ed in, fresh bits
+// counted by popcount), shorter ones as postings (4 B each) that set their bit with a shared-memory atomicOr — the bit was
+// clear before <=> the doc is new to the union.  No probes of other lists, no global random access (union_count, union.rs:807-1164,
+// computes the same number from bitmap words; for two lists it is df0 + df1 - |AND|, union.rs:1236-1244).
+__device__ __forceinline__ uint32_t count_union(const LexView& v, const LvRec& rec, uint32_t* bm, int lane, uint32_t& st_visited, uint32_t& st_words) {
+    const uint32_t meta = rec.meta, np = meta_npres(meta);
+    if (np == 0) return 0;
+    if (np == 1) return lane == 0 ? slot_cnt(rec.t[meta_cperm(meta, 0)]) : 0u;
+    uint4* b4 = reinterpret_cast<uint4*>(bm);
+    uint32_t acc = 0, nw = 0;
+    for (uint32_t c = 0; c < np; c++) {                                  // cperm: count descending -> the word-wise lists come first
+        const LvSlot& t = rec.t[meta_cperm(meta, c)];
+        if (slot_cnt(t) < UNION_WORDS || t.bmi == NONE) break;
+        const uint4* g = reinterpret_cast<const uint4*>(v.bm_words + (size_t)t.bmi * 1024);
+#pragma unroll 1
+        for (uint32_t i0 = lane; i0 < 512u; i0 += 128u) {                // four 16-byte loads in flight per lane
+            uint4 n[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; u++) n[u] = __ldg(g + i0 + 32u * u);
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; u++) {
+                if (c) {
+                    const uint4 o = b4[i0 + 32u * u];
+                    acc -= __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
+                    n[u].x |= o.x; n[u].y |= o.y; n[u].z |= o.z; n[u].w |= o.w;
+                }
+                acc += __popc(n[u].x) + __popc(n[u].y) + __popc(n[u].z) + __popc(n[u].w);
+                b4[i0 + 32u * u] = n[u];
+            }
+        }
+        st_words += 32u; nw++;
+    }
+    if (nw == 0) for (uint32_t i = lane; i < 512u; i += 32u) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    for (uint32_t c = nw; c < np; c++) st_visited += slot_cnt(rec.t[meta_cperm(meta, c)]);
+    // the order in which postings claim their bits does not matter: |union| = number of bits that were clear when claimed
+    stream_lists(v, rec, np - nw, lane, [&](uint32_t i) { return meta_cperm(meta, nw + i); },
+        [&](uint32_t, uint32_t d, bool valid) {
+            if (valid) {
+                const uint32_t bit = 1u << (d & 31u);
+                acc += (atomicOr(&bm[d >> 5], bit) & bit) ? 0u : 1u;
+            }
+        },
+        [&](uint32_t) {});
+    __syncwarp();
+    return acc;
+}
+
+// Pull what the scoring of a record touches first into L1: the coarse tables of its dense lists (8 lines each) and the first
+// 128 postings of every list (4 lines each).  Two instructions per record; the loads that follow hit L1 instead of paying a DRAM
+// round trip each (the average list has only ~3 stream iterations, so first-touch latency is most of a short list's time).
+__device__ __forceinline__ void prefetch_record(const LexView& v, const LvRec& rec, int lane) {
+#ifdef SSB_NO_PREFETCH
+    return;
+#endif
+    {
+        const LvSlot& t = rec.t[lane >> 3];
+        if (slot_cnt(t) && t.bmi != NONE) asm volatile("prefetch.global.L1 [%0];" :: "l"(v.bm_q8 + (size_t)t.bmi * 1024u + (uint32_t)(lane & 7) * 128u));
+    }
+    if (lane < 16) {
+        const LvSlot& t = rec.t[lane >> 2];
+        const uint32_t cnt = slot_cnt(t), ln = (uint32_t)(lane & 3);
+        if (cnt > ln * 32u) asm volatile("prefetch.global.L1 [%0];" :: "l"(v.post + slot_off(t) + ln * 32u));
+    }
 }
 
 // ---- record path (n <= FAST_T live terms), scoring of one item ----
@@ -806,8 +917,10 @@ __device__ __forceinline__ void score_records(const LexView& v, WarpSm& w, uint3
                                               const uint64_t* theta, int lane, uint64_t& L, Thr& thr, bool& dirty,
                                               uint32_t& st_visited, uint32_t& st_probes, uint32_t& st_recs, uint32_t& st_skipped) {
     uint32_t nq_in = 0;
+    prefetch_record(v, w.recs[0], lane);
 #pragma unroll 1
     for (uint32_t ri = 0; ; ri++) {
+        if (ri + 1u < nrec) prefetch_record(v, w.recs[ri + 1u], lane);      // its lines arrive while this record is scored
         // one extra pass (flush) after the last record — or after the first record the block-max test prunes — drains the queues
         bool flush = ri >= nrec;
         const LvRec& rec = w.recs[flush ? 0u : ri];
@@ -966,8 +1079,8 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
 // A warp takes ITEM_CHUNK consecutive indices per atomic; its lanes test them in parallel (most indices of the later waves
 // name items a query does not have) and the warp then works through the valid ones.
 constexpr uint32_t ITEM_CHUNK = 8;
-template <bool FAST>
-__device__ __forceinline__ bool next_item(WarpSm& it, uint32_t* counter, uint64_t total, uint32_t nq, const QueryPlan* __restrict__ plans,
+template <bool FAST, class SM>
+__device__ __forceinline__ bool next_item(SM& it, uint32_t* counter, uint64_t total, uint32_t nq, const QueryPlan* __restrict__ plans,
                                           int lane, uint32_t& j, uint32_t& q) {
     unsigned mask = it.it_mask; uint32_t base = it.it_base;      // warp-private shared memory: keeps two registers out of the hot loops
     __syncwarp();
@@ -992,7 +1105,8 @@ __device__ __forceinline__ bool next_item(WarpSm& it, uint32_t* counter, uint64_
     return true;
 }
 // stage the item's records in shared memory: 128 B per record, one coalesced word per lane
-__device__ __forceinline__ uint32_t stage_item(WarpSm& w, const LvRec* __restrict__ recs, const uint16_t* __restrict__ item_start,
+template <class SM>
+__device__ __forceinline__ uint32_t stage_item(SM& w, const LvRec* __restrict__ recs, const uint16_t* __restrict__ item_start,
                                                uint32_t nlv, uint32_t q, uint32_t j, int lane) {
     const uint16_t* is = item_start + (size_t)q * (nlv + 1);
     const uint32_t r0 = __ldg(&is[j]), r1 = __ldg(&is[j + 1]);
@@ -1062,11 +1176,11 @@ __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const 
 }
 
 // ---- exact match counts, queries with <= 4 live terms (ResultType Count / TopkCount): independent of θ, own kernel ----
-__global__ void __launch_bounds__(256, 4) lex_count(LexView v, const QueryPlan* __restrict__ plans, const LvRec* __restrict__ recs,
+__global__ void __launch_bounds__(128, 6) lex_count(LexView v, const QueryPlan* __restrict__ plans, const LvRec* __restrict__ recs,
                                                 const uint16_t* __restrict__ item_start, uint32_t nq, uint32_t query_type, uint32_t* ctr,
                                                 uint64_t* count, LexStats* stats) {
-    __shared__ __align__(16) WarpSm wsm[8];
-    WarpSm& w = wsm[(threadIdx.x >> 5) & 7];
+    __shared__ __align__(16) CountSm csm[4];
+    CountSm& w = csm[(threadIdx.x >> 5) & 3];
     const int lane = threadIdx.x & 31;
     const uint64_t total = (uint64_t)(*(volatile uint32_t*)&ctr[1]) * nq;
     const bool is_and = query_type == SSB_QUERY_INTERSECTION;
@@ -1077,7 +1191,9 @@ __global__ void __launch_bounds__(256, 4) lex_count(LexView v, const QueryPlan* 
     while (next_item<true>(w, &ctr[2], total, nq, plans, lane, j, q)) {
         const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
         uint32_t matches = 0, st_visited = 0, st_probes = 0, st_words = 0;
-        for (uint32_t ri = 0; ri < nrec; ri++) matches += count_record(v, w.recs[ri], is_and, lane, st_visited, st_probes, st_words);
+        for (uint32_t ri = 0; ri < nrec; ri++)
+            matches += is_and ? count_intersection(v, w.recs[ri], w.bm, lane, st_visited, st_probes, st_words)
+                              : count_union(v, w.recs[ri], w.bm, lane, st_visited, st_words);
         st_recs += nrec;
         for (int s = 16; s; s >>= 1) matches += __shfl_xor_sync(FULL, matches, s);
         if (lane == 0 && matches) atomicAdd((unsigned long long*)&count[q], (unsigned long long)matches);
@@ -1599,7 +1715,7 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
         if (launches) *launches += 1;
     }
     if (need_count) {
-        lex_count<<<n_sms_ * 4, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, q->query_type, ws.ctr, ws.count, ws.stats);
+        lex_count<<<n_sms_ * 6, 128, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, q->query_type, ws.ctr, ws.count, ws.stats);
         SSB_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }

@@ -18,5 +18,6 @@ except Exception as e: print("parse", e)
 PY
 if [ -n "$NCU" ]; then
   sed -n '/^cat > \/tmp\/prof_driver.py/,/^PY$/p' tools/gpu_call2.sh > /tmp/mk_driver.sh; bash /tmp/mk_driver.sh
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:lex_score -s 2 -c 1 -f -o gpurun_out/r02_lex_score_${T} python /tmp/prof_driver.py lex_or > gpurun_out/${T}_ncu_lex.log 2>&1; echo "ncu lex rc=$?"
+  case "$NCU" in *score*|1) timeout 900 ncu --set full --clock-control none --import-source on -k regex:lex_score -s 2 -c 1 -f -o gpurun_out/r02_lex_score_${T} python /tmp/prof_driver.py lex_or > gpurun_out/${T}_ncu_lex.log 2>&1; echo "ncu lex rc=$?";; esac
+  case "$NCU" in *count*) timeout 900 ncu --set full --clock-control none --import-source on -k regex:lex_count -s 2 -c 1 -f -o gpurun_out/r02_lex_count_${T} python /tmp/prof_driver.py lex_count > gpurun_out/${T}_ncu_lexc.log 2>&1; echo "ncu lexc rc=$?";; esac
 fi

@@ -4,7 +4,9 @@ import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
 hdr = rows[hi]
-def ci(name, start=0): return hdr.index(name, start)
+def ci(name, start=0):
+    try: return hdr.index(name, start)
+    except ValueError: return None
 c_s, c_i, c_l2, c_lsb, c_ssb, c_mio = ci("# Samples"), ci("Instructions Executed"), ci("L2 Theoretical Sectors Global"), ci("stall_long_sb"), ci("stall_short_sb"), ci("stall_mio")
 c_loc = ci("L2 Theoretical Sectors Local")
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 30
@@ -12,6 +14,7 @@ lines = []
 for r in rows[hi + 1:]:
     if len(r) < len(hdr) or not r[0].isdigit(): continue
     def f(c):
+        if c is None: return 0.0
         try: return float(r[c])
         except Exception: return 0.0
     lines.append((int(r[0]), r[1].strip()[:110], f(c_s), f(c_i), f(c_l2), f(c_lsb), f(c_ssb), f(c_mio), f(c_loc)))
