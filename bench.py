@@ -58,7 +58,7 @@ def parse():
     p.add_argument("--parity-queries", type=int, default=64, help="queries per path of the post-run oracle check")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
     p.add_argument("--vector-kernel", default="both", choices=["both", "all", "ffma", "tc", "tc64", "tcb", "tcb64", "tcb256"],
-                   help="FP32 FFMA2 scan, tcgen05 3xTF32 scan (128 / 64 queries per pass) or both (headline = the faster)")
+                   help="FP32 FFMA2 scan, tcgen05 scans, or both = ffma + tcb + tcb256 (headline = the fastest: what AUTO picks)")
     return p.parse_args()
 
 
@@ -68,6 +68,15 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def tensor_peak():
+    """dense bf16 TFLOP/s: the burst figure (kernel timed alone) of MEASURED_PEAKS.json, else the nominal 2250."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured (burst)"
+    except Exception:
+        return 2250.0, "nominal"
 
 
 class ClockSampler:
@@ -234,7 +243,9 @@ KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + wa
 # the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
 # (3.072 GB), i.e. no re-reads.
 NCU = {"scan_ffma": {"traffic_per_pass": 24.608e9 / 8, "source": "profiles/r01_scan_ffma_v3.summary.txt"},
-       "scan_tc": {"traffic_per_pass": 3.1149e9, "source": "profiles/r01_scan_tc_bf16.summary.txt"},
+       # bf16 hi/lo corpus planes: (6.1655 GB read + 58.7 MB written) / 2 passes; 256-query tile: 3.1087 GB + 75.5 MB, one pass
+       "scan_tc": {"traffic_per_pass": 3.1121e9, "source": "profiles/r02_scan_tc_bf16_planes_v1.summary.txt", "tensor_pipe_pct": 66.1},
+       "tcb256": {"traffic_per_pass": 3.1842e9, "source": "profiles/r02_scan_tc_bf16_n256_v1.summary.txt", "tensor_pipe_pct": 84.2},
        # int8 full scan of 1M x 768: dram read 777.6 MB + write 29.3 MB (per-warp list scratch)
        "scan_tc_i8": {"traffic_per_pass": 0.8069e9, "source": "profiles/r01_scan_tc_i8_v1.summary.txt"},
        "lex_score": {"traffic": None, "source": None}}
@@ -269,6 +280,13 @@ def measure_vector_kernel(a, ix, kname, q_host, q_dev, keys, local_rows, rank, w
     alg_bytes = float(local_rows) * a.dims * 4 * passes          # per launch (one launch = all passes of the batch)
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
     ncu = NCU.get(kname, NCU.get(kshort, {}))
+    tensor = None
+    if kshort == "scan_tc" and kern_ms:
+        # every f32 product is three bf16 MMAs (hi*hi + hi*lo + lo*hi): executed flops = 3 x the algorithmic 2*rows*dims*queries
+        tpeak, tkind = tensor_peak()
+        alg_tf = 2.0 * local_rows * a.dims * qt * passes / (kern_ms / 1e3) / 1e12
+        tensor = {"algorithmic_tflops": alg_tf, "executed_tflops": 3 * alg_tf, "peak": tpeak, "peak_kind": tkind,
+                  "frac_executed": 3 * alg_tf / tpeak, "tensor_pipe_pct_ncu": ncu.get("tensor_pipe_pct")}
     return {
         "value": a.batch * a.steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / a.steps,
         "e2e": {"value": a.batch * a.steps / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / a.steps,
@@ -278,7 +296,7 @@ def measure_vector_kernel(a, ix, kname, q_host, q_dev, keys, local_rows, rank, w
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": (ncu["traffic_per_pass"] * passes * local_rows / 1e6) if (ncu and a.dims == C2_DIMS) else None,
                      "traffic_source": ncu.get("source"), "peak_kind": f"of {peak_kind}", "kernel": kshort, "kernel_ms": kern_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes},
+                     "algorithmic_bytes_per_launch": alg_bytes, "tensor": tensor},
         "clocks": clocks,
     }
 
@@ -302,7 +320,7 @@ def bench_vector(a, rank, world, out):
     q_host = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").pin_memory()
     q_dev = q_host.to(dev)
     keys = torch.zeros((a.batch, 32), dtype=torch.int64, device=dev)
-    names = ["ffma", "tcb"] if a.vector_kernel == "both" else (["ffma", "tcb", "tcb256"] if a.vector_kernel == "all" else [a.vector_kernel])
+    names = ["ffma", "tcb", "tcb256"] if a.vector_kernel == "both" else (["ffma", "tcb", "tcb256"] if a.vector_kernel == "all" else [a.vector_kernel])
     res = {k: measure_vector_kernel(a, ix, k, q_host, q_dev, keys, local_rows, rank, world, dev, rank == 0) for k in names}
     # batch-size sweep through the reference-facing call (host buffers, AUTO kernel choice): latency at batch 1 .. 256
     sweep = {}

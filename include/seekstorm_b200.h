@@ -62,8 +62,8 @@ enum { SSB_QUANT_NONE = 0, SSB_QUANT_SCALAR_I8 = 1 };
 /* which vector scan kernel to use */
 /* FFMA: packed-FP32 scan, 16 queries per corpus pass (HBM-bound).  TCGEN05[_N64]: tensor-core scan with the 3xTF32
  * split, 128 (or 64) queries per corpus pass.  TCGEN05_BF16[_N64]: tensor-core scan with the 3xBF16 split (half the
- * operand bytes; score error ~1e-5 relative, inside the 1e-4 tolerance).  AUTO: TCGEN05_BF16 for batches of > 16
- * Dot/Cosine queries, else FFMA; Euclidean always FFMA. */
+ * operand bytes; score error ~1e-5 relative, inside the 1e-4 tolerance).  AUTO: FFMA up to 16 queries and
+ * for Euclidean; above that TCGEN05_BF16, or TCGEN05_BF16_N256 when its passes take less time for the batch size. */
 enum { SSB_VEC_KERNEL_AUTO = 0, SSB_VEC_KERNEL_FFMA = 1, SSB_VEC_KERNEL_TCGEN05 = 2, SSB_VEC_KERNEL_TCGEN05_N64 = 3,
        SSB_VEC_KERNEL_TCGEN05_BF16 = 4, SSB_VEC_KERNEL_TCGEN05_BF16_N64 = 5,
        SSB_VEC_KERNEL_TCGEN05_BF16_N256 = 6 /* 256 queries per corpus pass: half the HBM bytes per query, tensor / shared-memory bound */ };

@@ -172,7 +172,12 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     // ~0.6 ms -> FP32 scan for <= 16 queries, tensor-core scan above.  Euclidean always takes the FP32 scan.
     uint32_t kern = ix->cfg.vector_kernel;
     if (ix->quant_i8) kern = SSB_VEC_KERNEL_TCGEN05;   // one kernel for the int8 corpus: tcgen05 kind::i8, 128-query tile
-    if (kern == SSB_VEC_KERNEL_AUTO) kern = nq > 16 ? SSB_VEC_KERNEL_TCGEN05_BF16 : SSB_VEC_KERNEL_FFMA;
+    if (kern == SSB_VEC_KERNEL_AUTO) {
+        // tensor-core scan above 16 queries; the 256-query tile (0.95 ms per pass vs 0.55 ms for 128 queries, measured) when it
+        // needs fewer milliseconds for this batch: ceil(nq/256) * 0.95 < ceil(nq/128) * 0.55
+        const uint32_t p128 = (nq + 127u) / 128u, p256 = (nq + 255u) / 256u;
+        kern = nq <= 16 ? SSB_VEC_KERNEL_FFMA : (p256 * 95u < p128 * 55u ? SSB_VEC_KERNEL_TCGEN05_BF16_N256 : SSB_VEC_KERNEL_TCGEN05_BF16);
+    }
     const bool use_tc = ix->quant_i8 || (kern >= SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN);   // the int8 index is always scanned on the tensor cores
     const bool tc_bf16 = kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256;
     const uint32_t qt = !use_tc ? vec::VEC_QT : (ix->quant_i8 ? 128u : (kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : (kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256 ? 256u : 128u));

@@ -48,10 +48,6 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
     return d;
 }
 
-#ifndef SSB_FFMA_GROUPMAX
-#define SSB_FFMA_GROUPMAX 0   // EXPERIMENT (default off, compile-checked only, never run): group-maximum threshold sampling as in
-                                // vec_scan_tc.cu instead of the list-based sample pass — DESIGN.md §7 item 3
-#endif
 
 template <int SIM>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -60,11 +56,8 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*CWARPS/2][QT][32]*/,
           const uint32_t* __restrict__ thr_init /*[gridDim.y*QT] or null*/, uint32_t nq_valid,
           const uint64_t* __restrict__ ceil_keys /*[gridDim.y*QT] or null*/,
-          const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words
-#if SSB_FFMA_GROUPMAX
-          , uint32_t sample_mode
-#endif
-          ) {
+          const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words,
+          uint32_t sample_mode /* 1: threshold-seeding pass — keep the row-group score maxima, no lists */) {
     // no static shared memory in this kernel: the dynamic segment starts at offset 0 of the CTA window, so the
     // 1024-byte alignment SWIZZLE_128B needs holds and the pointers stay in the shared address space (LDS, not LD)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -149,7 +142,6 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
 
-#if SSB_FFMA_GROUPMAX
                 if (kc + 1 == n_kchunks && sample_mode) {
                     // sample mode: lane (j*8 + q) keeps the best ordered-uint score of row group j (32 rows) for query q
                     uint32_t keep = 0;
@@ -175,7 +167,6 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     gmax[(size_t)(group * QT + qh + (lane & 7)) * (n_tiles * 16) + (tile * 16 + rg * 4 + (lane >> 3))] = keep;
                     continue;
                 }
-#endif
                 if (kc + 1 == n_kchunks) {
                     // ---- tile finished: fused top-k (TopK::push, vector.rs:410-497) ----
 #pragma unroll
@@ -212,9 +203,7 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
         // ---- publish the warp's lists: scratch[group][list][q][lane], list = (cta*4 + rg) ----
-#if SSB_FFMA_GROUPMAX
         if (sample_mode) return;                          // scratch holds the group maxima, not lists
-#endif
         const uint32_t n_lists = gridDim.x * (CWARPS / 2);
         uint64_t* out = scratch + ((size_t)group * n_lists + (size_t)blockIdx.x * (CWARPS / 2) + rg) * QT * LIST;
 #pragma unroll
@@ -348,31 +337,18 @@ __global__ void fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t 
 }
 
 // ---------------------------------------------------------------- host side
-__global__ void kth_threshold(const uint64_t* __restrict__ keys, uint32_t nq, uint32_t k, uint32_t* __restrict__ thr) {
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) thr[q] = (uint32_t)(keys[(size_t)q * LIST + (k - 1)] >> 32);
-}
-void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_t* thr, cudaStream_t st) {
-    if (nq) kth_threshold<<<(nq + 127) / 128, 128, 0, st>>>(keys, nq, k, thr);
-}
-
-// Threshold pre-sampling: scan the first vec_presample_rows() rows (1/16 of the shard, 4K..32K), take each query's k-th best score there as the initial
-// threshold of the full scan.  It is the k-th best of a subset, hence a valid lower bound of the final k-th best: results
-// are unchanged, but the expected number of list insertions per query drops from ~k*ln(rows/k) PER LIST to ~k*N/S in total.
+// Threshold pre-sampling: scan the first vec_presample_rows() rows (1/16 of the shard, 4K..32K) keeping only each 32-row group's
+// best score per query (no lists, no merge); the k-th largest of those group maxima (kth_from_groupmax) is a valid lower bound of
+// the final k-th best score — k different groups each hold a row at least that good — and seeds the threshold of the full scan:
+// results are unchanged, but the expected number of list insertions per query drops from ~k*ln(rows/k) PER LIST to ~k*N/S in total.
 template <class F>
 static int32_t with_presample(const ScanArgs& a, cudaStream_t st, F launch) {
     // with a delete set the sample pass is skipped: a deleted row must never seed a threshold
     if (a.thr_init || !a.thr_buf || a.del_slot || vec_presample_rows(a.n_rows, false) == 0) return launch(a);
     ScanArgs pre = a;
-    pre.n_rows = vec_presample_rows(a.n_rows, false); pre.ev0 = nullptr; pre.ev1 = nullptr; pre.thr_buf = nullptr;
-#if SSB_FFMA_GROUPMAX
-    pre.sample_groupmax = true; pre.thr_buf = a.thr_buf;     // the sample launch writes the thresholds itself
+    pre.n_rows = vec_presample_rows(a.n_rows, false); pre.ev0 = nullptr; pre.ev1 = nullptr;
+    pre.sample_groupmax = true;                              // the sample launch writes the thresholds (thr_buf) itself
     SSB_TRY(launch(pre));
-#else
-    SSB_TRY(launch(pre));
-    launch_kth_threshold(a.keys_out, a.nq_pad, a.k, a.thr_buf, st);
-    if (a.launches) *a.launches += 1;
-#endif
     ScanArgs full = a;
     full.thr_init = a.thr_buf;
     return launch(full);
@@ -395,7 +371,6 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
     // per launch: the attribute belongs to the current device's context (several devices per process are allowed)
     SSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     if (a.ev0) cudaEventRecord(a.ev0, st);
-#if SSB_FFMA_GROUPMAX
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
                                             a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, a.del_slot, a.del_words, a.sample_groupmax ? 1u : 0u);
     if (a.sample_groupmax) {
@@ -404,10 +379,6 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
         if (a.launches) *a.launches += 2;   // scan + kth
         return SSB_OK;
     }
-#else
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
-                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, a.del_slot, a.del_words);
-#endif
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     merge_lists<<<a.nq_pad, 256, 0, st>>>(a.scratch, n_lists, QT, a.keys_out);

@@ -62,7 +62,6 @@ int32_t launch_prep_split_queries_bf16(const float* q, uint32_t nq, uint32_t dim
 int32_t launch_split_rows_bf16(const float* rows, void* hi, void* lo, size_t n_elems, cudaStream_t st);
 // lists laid out [group][n_lists][qt][32] -> out [nq][32]
 // thr[q] = ordered-uint score of the k-th entry of keys[q][32] (0 if the list is shorter)
-void launch_kth_threshold(const uint64_t* keys, uint32_t nq, uint32_t k, uint32_t* thr, cudaStream_t st);
 // thr[q] = k-th largest group maximum (sample mode of the scans; is_int: int32 dot products instead of ordered-uint scores)
 void launch_kth_from_groupmax(const void* gmax, uint32_t n_groups, uint32_t nq, uint32_t k, uint32_t* thr, int is_int, cudaStream_t st);
 void merge_lists_generic(const uint64_t* in, uint32_t n_lists, uint32_t qt, uint32_t nq, uint64_t* out, cudaStream_t st);

@@ -22,7 +22,7 @@ def test_stats_and_kernel_selection():
         ix.set_vector_kernel(kern)
         outs[kern] = ix.search_vector_batch(q, 10)
         st = ix.last_stats()
-        assert st["kernel_launches"] == {1: 6, 2: 6, 3: 6, 4: 5, 5: 5, 0: 5}[kern]   # FP32: prep + presample(scan, merge, kth) + scan + merge; tf32: prep + split + sample(scan, kth) + scan + merge; bf16: fused prep/split + sample(scan, kth) + scan + merge
+        assert st["kernel_launches"] == {1: 5, 2: 6, 3: 6, 4: 5, 5: 5, 0: 5}[kern]   # FP32: prep + sample(scan, kth) + scan + merge; tf32: prep + split + sample(scan, kth) + scan + merge; bf16: fused prep/split + sample(scan, kth) + scan + merge
         assert st["dominant_kernel_ns"] > 0
         assert st["h2d_bytes"] == 50 * 64 * 4 and st["d2h_bytes"] == 50 * 32 * 8
         passes = {1: 4, 2: 1, 3: 1, 4: 1, 5: 1, 0: 1}[kern]   # 50 queries: 4 x 16, 1 x 128, 1 x 64, AUTO -> tcgen05
