@@ -242,13 +242,15 @@ KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + wa
 # DRAM traffic per corpus pass (dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture, divided by
 # the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
 # (3.072 GB), i.e. no re-reads.
-NCU = {"scan_ffma": {"traffic_per_pass": 24.608e9 / 8, "source": "profiles/r01_scan_ffma_v3.summary.txt"},
+NCU = {"scan_ffma": {"traffic_per_pass": 3.0770e9, "source": "profiles/r02_scan_ffma.summary.txt"},   # 3.0734 GB read + 3.6 MB written, one pass of 16 queries
        # bf16 hi/lo corpus planes: (6.1655 GB read + 58.7 MB written) / 2 passes; 256-query tile: 3.1087 GB + 75.5 MB, one pass
        "scan_tc": {"traffic_per_pass": 3.1121e9, "source": "profiles/r02_scan_tc_bf16_planes_v1.summary.txt", "tensor_pipe_pct": 66.1},
        "tcb256": {"traffic_per_pass": 3.1842e9, "source": "profiles/r02_scan_tc_bf16_n256_v1.summary.txt", "tensor_pipe_pct": 84.2},
-       # int8 full scan of 1M x 768: dram read 777.6 MB + write 29.3 MB (per-warp list scratch)
-       "scan_tc_i8": {"traffic_per_pass": 0.8069e9, "source": "profiles/r01_scan_tc_i8_v1.summary.txt"},
-       "lex_score": {"traffic": None, "source": None}}
+       # int8 full scan of 1M x 768, 1024 queries = 8 passes in one launch: (6.2222 GB read + 219.8 MB written) / 8
+       "scan_tc_i8": {"traffic_per_pass": 0.8052e9, "source": "profiles/r02_scan_tc_i8.summary.txt"},
+       # lex_score<OR>, C3 10M docs, 4096 queries, Topk: 6.8986 GB read + 60.6 MB written (random 32-byte sector probes of the
+       # bitmap sectors and the coarse tables on top of the 1.5 GB the algorithm names)
+       "lex_score": {"traffic": 6.9592e9, "source": "profiles/r02_lex_score_v6.summary.txt"}}
 
 
 def measure_vector_kernel(a, ix, kname, q_host, q_dev, keys, local_rows, rank, world, dev, want_clocks):
@@ -598,7 +600,7 @@ def bench_bm25(a, rank, world, keep_index=False, vector_dims=0):
         "metric": "queries/sec at top-10 (BM25 OR, block-max pruned, ResultType::Topk)", "value": len(qk) * steps / (ms / 1e3),
         "unit": "queries/s", "ms_per_step": ms / steps, "steps": steps, "dtype": "f32 scores / u16 postings",
         "config": {"workload": f"C3 BM25 OR top-{TOPK}: {a.bm25_docs} docs Zipf(1) V={C3_VOCAB}, {len(qk)} queries/step of 2-4 terms (40/40/20%), ranks log-uniform [20,1e5]",
-                   "index_build_s": build_s, "l2": "posting arenas larger than L2 (8 B per posting, %.1f GB per GPU)" % (8 * 0.08 * a.bm25_docs / world / 1e6 / 1e3 * 1e3)},
+                   "index_build_s": build_s, "l2": "posting arenas larger than L2 (12 B per posting: stream word, payload, f32 component; %.1f GB per GPU)" % (12 * 0.08 * a.bm25_docs / world / 1e6 / 1e3 * 1e3)},
         "e2e": {"value": len(qk) * steps / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(keep[0].nbytes + keep[1].nbytes), "d2h_bytes_per_step": len(qk) * (32 * 8 + 8)},
         "gpu_launches": int(launches) * steps, "variants": variants,

@@ -777,9 +777,10 @@ int32_t ssb_search_lexical(ssb_index* ix, const ssb_lex_batch* q, uint32_t k, ui
     } else if (n_hits) for (uint32_t i = 0; i < nq; i++) n_hits[i] = 0;
     if (count_total) for (uint32_t i = 0; i < nq; i++) count_total[i] = c.h_counts[i];
     c.stats.postings_visited = ls.postings_visited;
-    // SURVEY.md §8(d) accounting with this layout's sizes: 4 B per streamed posting word, 14 B per exact probe (8 B bitmap word + 2 B
-    // rank + 4 B payload), 128 B per (query, level) record read, 8 B per bitmap word of the dense count paths
-    c.stats.algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 14 + ls.recs_processed * 128 + ls.dense_words * 8;
+    // SURVEY.md §8(d) accounting with this layout's sizes: 4 B per streamed posting word, 16 B per probe (8 B bitmap word + 4 B
+    // rank / word bound + 4 B component), 128 B per (query, level) record read, 8 B per bitmap word of the word-wise count paths;
+    // the 1-byte coarse-table lookups of the stream filter are not counted
+    c.stats.algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 16 + ls.recs_processed * 128 + ls.dense_words * 8;
     c.stats.probes = ls.probes; c.stats.items_processed = ls.items_processed; c.stats.items_skipped = ls.items_skipped;
     return SSB_OK;
     SSB_API_END
@@ -1018,7 +1019,7 @@ int32_t ssb_last_stats(const ssb_index* cix, ssb_stats* out) {
         if (c->last_lex && out->postings_visited == 0 && c->lex.stats) {
             const LexStats ls = LexIndex::read_stats(c->lex, ix->ext_stream_set ? ix->ext_stream : c->own_st);
             out->postings_visited = ls.postings_visited; out->probes = ls.probes; out->items_processed = ls.items_processed; out->items_skipped = ls.items_skipped;
-            if (ls.postings_visited) out->algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 14 + ls.recs_processed * 128 + ls.dense_words * 8;
+            if (ls.postings_visited) out->algorithmic_bytes = ls.postings_visited * 4 + ls.probes * 16 + ls.recs_processed * 128 + ls.dense_words * 8;
         }
     }
     return SSB_OK;

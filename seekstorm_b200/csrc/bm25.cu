@@ -576,6 +576,7 @@ __device__ __forceinline__ void filter_queued(const LexView& v, WarpSm& w, uint2
         const BmSec* sec = v.bm + (size_t)bmi[s] * 512 + (d >> 7);
         bw[s] = need ? __ldg(&sec->w[(d >> 6) & 1u]) : 0ull;
         bm[s] = need ? __ldg(&sec->meta[(d >> 6) & 1u]) : 0u;          // same sector as the word
+        st_probes += need ? 1u : 0u;
     }
     float B = rec.idf[drv] * bound_of_word(e.y);
     bool dead = !active;
