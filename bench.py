@@ -57,7 +57,7 @@ def parse():
     p.add_argument("--c5-docs", type=int, default=10_000_000, help="C5: docs AND vectors of the sharded hybrid index")
     p.add_argument("--parity-queries", type=int, default=64, help="queries per path of the post-run oracle check")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
-    p.add_argument("--vector-kernel", default="both", choices=["both", "all", "ffma", "tc", "tc64", "tcb", "tcb64", "tcb256"],
+    p.add_argument("--vector-kernel", default="both", choices=["both", "all", "ffma", "tc", "tc64", "tcb", "tcb64", "tcb256", "filt", "filt256"],
                    help="FP32 FFMA2 scan, tcgen05 scans, or both = ffma + tcb + tcb256 (headline = the fastest: what AUTO picks)")
     return p.parse_args()
 
@@ -238,7 +238,11 @@ KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + wa
            "tc64": (3, 64, "scan_tc", "scan_tc<64> (tcgen05 3xTF32, 64 queries per pass)"),
            "tcb": (4, 128, "scan_tc", "scan_tc (TMA + tcgen05 3xBF16 split, TMEM accumulators, TMEM-epilogue top-k)"),
            "tcb64": (5, 64, "scan_tc", "scan_tc<64> (tcgen05 3xBF16, 64 queries per pass)"),
-           "tcb256": (6, 256, "scan_tc", "scan_tc<256> (tcgen05 3xBF16 over bf16 planes, 256 queries per pass: half the HBM bytes per query)")}
+           "tcb256": (6, 256, "scan_tc", "scan_tc<256> (tcgen05 3xBF16 over bf16 planes, 256 queries per pass: half the HBM bytes per query)"),
+           # filter scan: ONE fp16 product over the 2-byte plane selects (proven margin) the <= 32 rows that can be in the top-10, refine
+           # re-scores them with the f32 dot product; the result is the exact f32 top-k
+           "filt": (7, 128, "scan_tc", "scan_tc<128, f16 filter> + refine_candidates (tcgen05 1xFP16 over the 2-byte plane, exact f32 re-scoring of <= 32 candidates per query)"),
+           "filt256": (8, 256, "scan_tc", "scan_tc<256, f16 filter> + refine_candidates (256 queries per pass)")}
 # DRAM traffic per corpus pass (dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture, divided by
 # the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
 # (3.072 GB), i.e. no re-reads.
@@ -277,9 +281,13 @@ def measure_vector_kernel(a, ix, kname, q_host, q_dev, keys, local_rows, rank, w
     def step_e2e():
         ix.search_vector_raw(q_np, TOPK, hits_buf, nh_buf)     # ssb_search_vector: host queries in, host hits out
     ms_e2e = timed_steps(step_e2e, a.steps, a.warmup, world)
+    fallbacks = ix.last_stats().get("filter_fallbacks", 0)       # queries of the last e2e call that took the exact fallback scan
     peak, peak_kind = peaks()
     kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
-    alg_bytes = float(local_rows) * a.dims * 4 * passes          # per launch (one launch = all passes of the batch)
+    filt = kname.startswith("filt")
+    # per launch (one launch = all passes of the batch).  SURVEY 8(d) counts rows*dims*4 per pass for an f32 scan; the filter scan's own
+    # algorithm only has to stream the 2-byte plane, so ITS roofline is counted on rows*dims*2 (the f32-equivalent figure is reported beside it)
+    alg_bytes = float(local_rows) * a.dims * (2 if filt else 4) * passes
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
     ncu = NCU.get(kname, NCU.get(kshort, {}))
     tensor = None
@@ -287,8 +295,9 @@ def measure_vector_kernel(a, ix, kname, q_host, q_dev, keys, local_rows, rank, w
         # every f32 product is three bf16 MMAs (hi*hi + hi*lo + lo*hi): executed flops = 3 x the algorithmic 2*rows*dims*queries
         tpeak, tkind = tensor_peak()
         alg_tf = 2.0 * local_rows * a.dims * qt * passes / (kern_ms / 1e3) / 1e12
-        tensor = {"algorithmic_tflops": alg_tf, "executed_tflops": 3 * alg_tf, "peak": tpeak, "peak_kind": tkind,
-                  "frac_executed": 3 * alg_tf / tpeak, "tensor_pipe_pct_ncu": ncu.get("tensor_pipe_pct")}
+        nprod = 1 if filt else 3
+        tensor = {"algorithmic_tflops": alg_tf, "executed_tflops": nprod * alg_tf, "peak": tpeak, "peak_kind": tkind,
+                  "frac_executed": nprod * alg_tf / tpeak, "tensor_pipe_pct_ncu": ncu.get("tensor_pipe_pct")}
     return {
         "value": a.batch * a.steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / a.steps,
         "e2e": {"value": a.batch * a.steps / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / a.steps,
@@ -298,7 +307,11 @@ def measure_vector_kernel(a, ix, kname, q_host, q_dev, keys, local_rows, rank, w
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": (ncu["traffic_per_pass"] * passes * local_rows / 1e6) if (ncu and a.dims == C2_DIMS) else None,
                      "traffic_source": ncu.get("source"), "peak_kind": f"of {peak_kind}", "kernel": kshort, "kernel_ms": kern_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes, "tensor": tensor},
+                     "algorithmic_bytes_per_launch": alg_bytes, "tensor": tensor,
+                     **({"f32_equivalent_gbs": float(local_rows) * a.dims * 4 * passes / (kern_ms / 1e3) / 1e9 if kern_ms else None,
+                         "note": "filter scan: streams rows*dims*2 bytes per pass (fp16 plane) + <= 32 f32 rows per query in the refine step; "
+                                 "achieved/frac are counted on the 2-byte plane, f32_equivalent_gbs is the SURVEY 8(d) figure rows*dims*4/t"} if filt else {})},
+        "filter_fallbacks": int(fallbacks) if filt else None,
         "clocks": clocks,
     }
 
@@ -322,7 +335,7 @@ def bench_vector(a, rank, world, out):
     q_host = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").pin_memory()
     q_dev = q_host.to(dev)
     keys = torch.zeros((a.batch, 32), dtype=torch.int64, device=dev)
-    names = ["ffma", "tcb", "tcb256"] if a.vector_kernel == "both" else (["ffma", "tcb", "tcb256"] if a.vector_kernel == "all" else [a.vector_kernel])
+    names = ["ffma", "tcb", "tcb256", "filt", "filt256"] if a.vector_kernel in ("both", "all") else [a.vector_kernel]
     res = {k: measure_vector_kernel(a, ix, k, q_host, q_dev, keys, local_rows, rank, world, dev, rank == 0) for k in names}
     # batch-size sweep through the reference-facing call (host buffers, AUTO kernel choice): latency at batch 1 .. 256
     sweep = {}
@@ -350,7 +363,8 @@ def bench_vector(a, rank, world, out):
                    "parallelism": f"64K-row levels sharded over {world} GPU(s)", "kernel": r["kernel_desc"]},
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "clocks": r["clocks"],
         "batch_sweep_e2e": sweep,
-        "kernels": {{"ffma": "scan_ffma", "tc": "scan_tc_tf32", "tc64": "scan_tc_tf32_n64", "tcb": "scan_tc_bf16", "tcb64": "scan_tc_bf16_n64", "tcb256": "scan_tc_bf16_n256"}[k]:
+        "kernels": {{"ffma": "scan_ffma", "tc": "scan_tc_tf32", "tc64": "scan_tc_tf32_n64", "tcb": "scan_tc_bf16", "tcb64": "scan_tc_bf16_n64", "tcb256": "scan_tc_bf16_n256",
+                     "filt": "scan_tc_f16_filter", "filt256": "scan_tc_f16_filter_n256"}[k]:
                     {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
     })
     return ix, q_host

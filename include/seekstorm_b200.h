@@ -66,7 +66,11 @@ enum { SSB_QUANT_NONE = 0, SSB_QUANT_SCALAR_I8 = 1 };
  * for Euclidean; above that TCGEN05_BF16, or TCGEN05_BF16_N256 when its passes take less time for the batch size. */
 enum { SSB_VEC_KERNEL_AUTO = 0, SSB_VEC_KERNEL_FFMA = 1, SSB_VEC_KERNEL_TCGEN05 = 2, SSB_VEC_KERNEL_TCGEN05_N64 = 3,
        SSB_VEC_KERNEL_TCGEN05_BF16 = 4, SSB_VEC_KERNEL_TCGEN05_BF16_N64 = 5,
-       SSB_VEC_KERNEL_TCGEN05_BF16_N256 = 6 /* 256 queries per corpus pass: half the HBM bytes per query, tensor / shared-memory bound */ };
+       SSB_VEC_KERNEL_TCGEN05_BF16_N256 = 6 /* 256 queries per corpus pass: half the HBM bytes per query, tensor / shared-memory bound */,
+       /* FILTER: one bf16 product over the 2-byte hi plane of the corpus selects, with a proven error margin, the <= 32 rows that can be
+        * in the top-k (k <= 16); those are re-scored with the plain f32 dot product and queries whose candidate set did not fit are re-run
+        * by an exact f32 scan on the device.  Results are the exact f32 top-k.  128 / 256 queries per corpus pass. */
+       SSB_VEC_KERNEL_TCGEN05_FILTER = 7, SSB_VEC_KERNEL_TCGEN05_FILTER_N256 = 8 };
 
 typedef struct ssb_index ssb_index;
 
@@ -171,6 +175,13 @@ int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n);
  * Cosine: rows are L2-normalised on load (vector.rs:585-596 does this at index time). */
 int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride_floats,
                              const uint16_t* local_ids, uint32_t n, uint32_t dims);
+/* The same level with its IVF cluster table (vector.bin: `u32 clusters; u32 child_count x clusters; records`, vector.rs:1066-1094): rows
+ * are in cluster order, cluster c holds the next cluster_counts[c] rows, its medoid is its FIRST row (vector.rs:1316-1320).  Levels added
+ * without a table are one cluster (what the reference writes below 100 vectors or with Clustering::None, vector.rs:1048-1062).  The
+ * clusters only matter to ssb_search_vector_ex calls with ann_mode != SSB_ANN_ALL.  f32 indexes only. */
+int32_t ssb_vector_add_level_clustered(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride_floats,
+                                       const uint16_t* local_ids, uint32_t n, uint32_t dims,
+                                       const uint32_t* cluster_counts, uint32_t n_clusters);
 int32_t ssb_vector_count(const ssb_index* ix, uint64_t* n_rows);
 /* capacity hint: size the vector arenas for n_rows rows up front (loading level by level otherwise grows them geometrically) */
 int32_t ssb_vector_reserve(ssb_index* ix, uint64_t n_rows);
@@ -193,13 +204,19 @@ int32_t ssb_search_vector(ssb_index* ix, const float* queries, uint32_t n_querie
  * observed: [n_queries] or NULL (observed_vector_count: every record under AnnMode::All).  Rows that share a doc id (one vector
  * per chunk) are collapsed to the best-scoring one, as TopK::push does (vector.rs:436-470). */
 enum { SSB_QFMT_F32 = 0, SSB_QFMT_I8 = 1 };
+/* AnnMode (vector_similarity.rs:43-66) — which IVF clusters of each level are searched (vector.rs:1300-1392): per (query, level) the
+ * query is scored against every cluster's medoid, the n_probe best clusters (score desc, cluster id asc) whose medoid score is not below
+ * the pre-mapped cluster threshold are scanned, the others are skipped.  observed = the vectors in the selected clusters. */
+enum { SSB_ANN_ALL = 0, SSB_ANN_NPROBE = 1, SSB_ANN_SIMILARITY_THRESHOLD = 2, SSB_ANN_NPROBE_SIMILARITY_THRESHOLD = 3 };
 typedef struct {
     const void* queries;          /* [n_queries, dims] f32 or i8, host or device                              */
     uint32_t n_queries, k;
     uint32_t query_format;        /* SSB_QFMT_*                                                               */
     uint32_t has_threshold;       /* 0 = None                                                                 */
     float    similarity_threshold;
-    uint32_t reserved[3];
+    uint32_t ann_mode;            /* SSB_ANN_* (0 = All: exhaustive)                                          */
+    uint32_t n_probe;             /* Nprobe / NprobeSimilaritythreshold                                       */
+    float    cluster_threshold;   /* Similaritythreshold / NprobeSimilaritythreshold (pre-mapped like similarity_threshold) */
 } ssb_vec_query;
 int32_t ssb_search_vector_ex(ssb_index* ix, const ssb_vec_query* q, ssb_hit* hits, uint32_t* n_hits, ssb_hit_ext* ext,
                              uint64_t* observed);
@@ -259,7 +276,9 @@ typedef struct {
     uint64_t items_processed;     /* lexical: (query, block) work items executed                          */
     uint64_t items_skipped;       /* lexical: work items pruned by block-max                              */
     uint64_t dominant_kernel_ns;  /* CUDA-event duration of the call's dominant kernel (scan / scoring)   */
-    uint64_t reserved[3];
+    uint64_t scan_bytes_read;     /* vector: bytes the scan (+ refine) kernels stream from HBM by construction */
+    uint64_t filter_fallbacks;    /* vector, host-facing calls: queries of the filter scan that took the exact fallback scan */
+    uint64_t reserved[1];
 } ssb_stats;
 int32_t ssb_last_stats(const ssb_index* ix, ssb_stats* out);
 

@@ -167,6 +167,51 @@ def search_vector(rows: np.ndarray, query: np.ndarray, k: int, similarity: int, 
     return _hits_to_list(buf, n.value)
 
 
+def ivf_premap_threshold(t: float, similarity: int) -> np.float32:
+    """TopK::new (vector.rs:388-399): (2t - 1) * 16129 for Dot / Cosine, -t for Euclidean."""
+    t = np.float32(t)
+    if similarity == SIM_EUCLIDEAN:
+        return np.float32(-t)
+    return np.float32((t * np.float32(2.0) - np.float32(1.0)) / np.float32(1.0 / 16129.0))
+
+
+def search_vector_ivf(levels, query: np.ndarray, k: int, similarity: int, ann_mode: int, n_probe: int = 0, cluster_threshold: float = 0.0):
+    """search_vector_shard with AnnMode::Nprobe / Similaritythreshold / NprobeSimilaritythreshold (vector.rs:1300-1467).
+    levels: list of (level_id, rows [n, d] f32 — already normalised for Cosine, local ids [n] or None, cluster child counts); a cluster is a
+    contiguous row range, its medoid its first row (:1316-1320).  Per level: score the query against every medoid, keep the n_probe best
+    (score desc, earlier cluster first) that are not below the pre-mapped threshold (:1300-1309, TopK::push :421), scan only their rows.
+    ann_mode: 0 All, 1 Nprobe, 2 Similaritythreshold, 3 NprobeSimilaritythreshold.  Returns (hits, observed_vector_count)."""
+    q = np.ascontiguousarray(query, dtype=np.float32)
+    sel_rows, sel_ids, observed = [], [], 0
+    thr = ivf_premap_threshold(cluster_threshold, similarity) if ann_mode in (2, 3) else None
+    for level_id, rows, local_ids, counts in levels:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        n = rows.shape[0]
+        ids = (np.arange(n, dtype=np.uint32) if local_ids is None else np.asarray(local_ids, dtype=np.uint32)) | np.uint32(level_id << 16)
+        counts = [n] if counts is None else [int(c) for c in counts]
+        starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+        if ann_mode == 0:
+            chosen = list(range(len(counts)))
+        else:
+            scored = []
+            for c, st in enumerate(starts):
+                m = np.ascontiguousarray(rows[st])
+                s = -lib().orc_euclidean_f32(_ptr(q), _ptr(m), q.size) if similarity == SIM_EUCLIDEAN else lib().orc_dot_f32(_ptr(q), _ptr(m), q.size)
+                s = np.float32(s)
+                if thr is not None and s < thr:
+                    continue
+                scored.append((-float(s), c))
+            scored.sort()
+            np_eff = min(n_probe, len(counts)) if ann_mode in (1, 3) else len(counts)
+            chosen = [c for _, c in scored[:np_eff]]
+        for c in chosen:
+            sel_rows.append(rows[starts[c]: starts[c] + counts[c]]); sel_ids.append(ids[starts[c]: starts[c] + counts[c]])
+            observed += counts[c]
+    if not sel_rows:
+        return [], 0
+    return search_vector(np.concatenate(sel_rows), q, k, similarity, doc_ids=np.concatenate(sel_ids)), observed
+
+
 def normalize(v: np.ndarray) -> np.ndarray:
     v = np.ascontiguousarray(v, dtype=np.float32).copy()
     lib().orc_normalize_f32(_ptr(v), v.size)

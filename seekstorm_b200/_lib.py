@@ -38,7 +38,8 @@ class SsbHitExt(C.Structure):
 
 class SsbVecQuery(C.Structure):
     _fields_ = [("queries", C.c_void_p), ("n_queries", C.c_uint32), ("k", C.c_uint32), ("query_format", C.c_uint32),
-                ("has_threshold", C.c_uint32), ("similarity_threshold", C.c_float), ("reserved", C.c_uint32 * 3)]
+                ("has_threshold", C.c_uint32), ("similarity_threshold", C.c_float), ("ann_mode", C.c_uint32), ("n_probe", C.c_uint32),
+                ("cluster_threshold", C.c_float)]
 
 
 class SsbIndexBinParams(C.Structure):
@@ -61,13 +62,13 @@ class SsbStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("postings_visited", C.c_uint64), ("probes", C.c_uint64),
                 ("items_processed", C.c_uint64), ("items_skipped", C.c_uint64), ("dominant_kernel_ns", C.c_uint64),
-                ("reserved", C.c_uint64 * 3)]
+                ("scan_bytes_read", C.c_uint64), ("filter_fallbacks", C.c_uint64), ("reserved", C.c_uint64 * 1)]
 
 
 # every symbol include/seekstorm_b200.h declares
 EXPORTS = [
     "ssb_abi_version", "ssb_last_error", "ssb_create", "ssb_destroy", "ssb_lexical_add_level",
-    "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
+    "ssb_vector_add_level_clustered", "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
     "ssb_load_index_bin", "ssb_load_vector_bin", "ssb_index_bin_inspect", "ssb_set_deleted", "ssb_vector_add_level", "ssb_vector_count", "ssb_vector_reserve", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_vector_ex", "ssb_search_hybrid",
     "ssb_rrf_fuse", "ssb_comm_unique_id", "ssb_comm_init", "ssb_comm_attach", "ssb_comm_destroy", "ssb_lexical_sync_df",
     "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
@@ -101,6 +102,7 @@ def lib():
         "ssb_lexical_dict_export": [vp, vp, vp, u64],
         "ssb_lexical_set_global_df": [vp, vp, vp, u64],
         "ssb_vector_add_level": [vp, u32, vp, u64, vp, u32, u32],
+        "ssb_vector_add_level_clustered": [vp, u32, vp, u64, vp, u32, u32, vp, u32],
         "ssb_load_index_bin": [vp, vp, u64, C.POINTER(SsbIndexBinParams), C.POINTER(u64)],
         "ssb_load_vector_bin": [vp, vp, u64, C.POINTER(u64)],
         "ssb_index_bin_inspect": [vp, u64, C.POINTER(SsbIndexBinParams), vp],

@@ -75,9 +75,11 @@ struct SearchCtx {
     LexWorkspace lex;
     DevBuf<float> qpad, qstage, qhi, qlo, q_scale, q_norm; DevBuf<int8_t> q_i8;
     DevBuf<uint64_t> ceil, scratch, keys_a, keys_b, counts, gather;
+    DevBuf<float> ivf_scores; DevBuf<uint32_t> ivf_sel; DevBuf<uint64_t> ivf_obs; std::vector<uint64_t> h_obs;   // IVF probe (vec_ivf.cu)
     std::vector<uint64_t> h_ceil, h_keys_a, h_keys_b, h_counts;
     ssb_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_used = false, last_lex = false;
+    const uint32_t* fb_state = nullptr;   // filter scan of the current call: device count of queries that took the exact fallback
     ~SearchCtx() {
         if (own_st) cudaStreamSynchronize(own_st);
         if (ev0) cudaEventDestroy(ev0);
@@ -110,6 +112,12 @@ struct ssb_index {
     DevBuf<int8_t> rows_i8;
     DevBuf<float> row_scale, row_norm;   // Dot / Euclidean + ScalarQuantizationI8: per-vector scale (and norm), QuantizedVector vector_similarity.rs:1340-1371
     DevBuf<uint32_t> doc_ids;
+    DevBuf<uint16_t> rows_h16;        // filter scan: fp16 plane half_rn(rows * vec_scale)
+    DevBuf<uint32_t> vec_err;         // filter scan: {max_r |a_r*scale - h_r|, max_r |h_r|, scratch} as f32 bits (launch_rows_f16_err)
+    float vec_scale = 0.f;            // power of two; 0 = not chosen yet (first add_level)
+    // IVF cluster tables (vector.rs:1066-1094; f32 indexes): one entry per add call ("level"), clusters numbered across levels
+    DevBuf<float> medoids; DevBuf<uint32_t> row_cluster, cl_count, lvl_begin;
+    std::vector<uint32_t> h_lvl_begin; uint32_t n_clusters = 0, max_level_clusters = 0;
     uint64_t n_rows = 0;
 };
 
@@ -140,7 +148,7 @@ struct CtxLease {
             ix->pool_cv.wait(g);
         }
         c->st = ix->ext_stream_set ? ix->ext_stream : c->own_st;
-        c->stats = ssb_stats{}; c->ev_used = false; c->last_lex = false;
+        c->stats = ssb_stats{}; c->ev_used = false; c->last_lex = false; c->fb_state = nullptr;
         return SSB_OK;
     }
     ~CtxLease() {
@@ -162,8 +170,11 @@ struct CtxLease {
 
 namespace {
 
+struct IvfQuery { uint32_t mode, n_probe; float thr; };   // AnnMode of one call (thr pre-mapped, vector.rs:388-399)
+
 int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_i8, uint32_t nq, uint32_t k, uint64_t* keys_out_dev /*[nq][32]*/,
-                 const uint64_t* ceil_dev = nullptr /*[>= nq_pad] paging ceilings*/) {
+                 const uint64_t* ceil_dev = nullptr /*[>= nq_pad] paging ceilings*/, const IvfQuery* ivf = nullptr /*null = AnnMode::All*/) {
+    if (ivf && (ix->quant_i8 || !ix->medoids.p)) { set_error("AnnMode other than All needs an f32 vector index"); return SSB_E_UNSUPPORTED; }
     if (ix->dims == 0) { set_error("no vector index configured (vector_dims = 0)"); return SSB_E_STATE; }
     if (k == 0 || k > SSB_K_MAX) { set_error("k must be in 1..%u", SSB_K_MAX); return SSB_E_UNSUPPORTED; }
     if (queries_i8 && !ix->quant_i8) { set_error("int8 queries need a ScalarQuantizationI8 index"); return SSB_E_INVALID; }
@@ -177,10 +188,20 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
         // needs fewer milliseconds for this batch: ceil(nq/256) * 0.95 < ceil(nq/128) * 0.55
         const uint32_t p128 = (nq + 127u) / 128u, p256 = (nq + 255u) / 256u;
         kern = nq <= 16 ? SSB_VEC_KERNEL_FFMA : (p256 * 95u < p128 * 55u ? SSB_VEC_KERNEL_TCGEN05_BF16_N256 : SSB_VEC_KERNEL_TCGEN05_BF16);
+        // filter scan + exact refine: half the bytes and a third of the tensor work per pass
+        if (nq > 16) kern = nq <= 128 ? SSB_VEC_KERNEL_TCGEN05_FILTER : SSB_VEC_KERNEL_TCGEN05_FILTER_N256;
+    }
+    // the filter scan keeps a candidate set sized for k <= 16 in the 32-entry lists and has no paging (ceilings are exact keys): those
+    // calls take the exact 3-product scan
+    bool filter = (kern == SSB_VEC_KERNEL_TCGEN05_FILTER || kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256);
+    if (filter && (ix->quant_i8 || ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN || k > 16 || ceil_dev || !ix->rows_h16.p || !ix->vec_err.p)) {
+        kern = kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256 && (nq + 255u) / 256u * 95u < (nq + 127u) / 128u * 55u ? SSB_VEC_KERNEL_TCGEN05_BF16_N256 : SSB_VEC_KERNEL_TCGEN05_BF16;
+        filter = false;
+        if (ix->quant_i8) kern = SSB_VEC_KERNEL_TCGEN05;
     }
     const bool use_tc = ix->quant_i8 || (kern >= SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN);   // the int8 index is always scanned on the tensor cores
-    const bool tc_bf16 = kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256;
-    const uint32_t qt = !use_tc ? vec::VEC_QT : (ix->quant_i8 ? 128u : (kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : (kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256 ? 256u : 128u));
+    const bool tc_bf16 = filter || kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256;
+    const uint32_t qt = !use_tc ? vec::VEC_QT : (ix->quant_i8 ? 128u : (kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : ((kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256 || kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256) ? 256u : 128u));
     const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
     cudaStream_t st = c.st;
     if (!ix->quant_i8) SSB_TRY(c.qpad.reserve((size_t)nq_pad * ix->dpad, 0, st));
@@ -212,17 +233,20 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
         // one launch: pad + normalise + bf16 hi/lo split (the scan reads only the split parts)
         SSB_TRY(c.qhi.reserve((size_t)nq_pad * ix->dpad, 0, st));
         SSB_TRY(c.qlo.reserve((size_t)nq_pad * ix->dpad, 0, st));
+        if (filter) SSB_TRY(c.q_scale.reserve(nq_pad, 0, st));   // per-query margins 2 eps_q
         SSB_TRY(vec::launch_prep_split_queries_bf16((const float*)qsrc, nq, ix->dims, ix->dims, c.qhi.p, c.qlo.p, nq_pad, ix->dpad,
-                                                    ix->cfg.vector_similarity == SSB_SIM_COSINE, st));
+                                                    ix->cfg.vector_similarity == SSB_SIM_COSINE, st, (filter || ivf) ? c.qpad.p : nullptr,
+                                                    filter ? c.q_scale.p : nullptr, filter ? ix->vec_err.p : nullptr));
     } else
     SSB_TRY(vec::launch_prep_queries((const float*)qsrc, nq, ix->dims, ix->dims, c.qpad.p, nq_pad, ix->dpad,
                                      ix->cfg.vector_similarity == SSB_SIM_COSINE, st));
     c.stats.kernel_launches += 1;
     if (ix->n_rows == 0) { SSB_CUDA_TRY(cudaMemsetAsync(keys_out_dev, 0, (size_t)nq * LIST * 8, st)); return SSB_OK; }
     size_t sb = use_tc ? vec::scan_tc_scratch_bytes(ix->n_sms, nq_pad) : vec::scan_scratch_bytes(ix->n_sms, nq_pad);
-    SSB_TRY(c.scratch.reserve(sb / 8 + (size_t)nq_pad * LIST + (nq_pad + 1) / 2, 0, st));
+    const size_t head_words = sb / 8 + (size_t)nq_pad * LIST + (nq_pad + 1) / 2;
+    SSB_TRY(c.scratch.reserve(head_words + (filter ? vec::refine_scratch_words(ix->n_sms, nq_pad) : 0), 0, st));
     vec::ScanArgs a{};
-    a.rows = ix->rows.p; a.rows_hi = ix->rows_hi.p; a.rows_lo = ix->rows_lo.p; a.doc_ids = ix->doc_ids.p; a.n_rows = ix->n_rows; a.dpad = ix->dpad; a.queries_padded = c.qpad.p;
+    a.rows = ix->rows.p; a.rows_hi = ix->rows_hi.p; a.rows_lo = ix->rows_lo.p; a.rows_h16 = ix->rows_h16.p; a.doc_ids = ix->doc_ids.p; a.n_rows = ix->n_rows; a.dpad = ix->dpad; a.queries_padded = c.qpad.p;
     a.nq_pad = nq_pad; a.nq_valid = nq; a.k = k; a.similarity = ix->cfg.vector_similarity; a.n_sms = ix->n_sms;
     a.scratch = c.scratch.p; a.scratch_bytes = sb;
     uint64_t* merged = c.scratch.p + sb / 8;   // [nq_pad][32]
@@ -231,6 +255,21 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     a.ceil_keys = ceil_dev;
     if (ix->del.n) { a.del_slot = ix->del.d_slot; a.del_words = ix->del.d_words; }
     a.launches = &c.stats.kernel_launches;
+    if (ivf) {
+        // cluster probe: medoid scores, per-(query, level) selection -> one bit per (query, cluster); the scans test it per candidate
+        vec::IvfArgs v{};
+        v.medoids = ix->medoids.p; v.lvl_begin = ix->lvl_begin.p; v.cl_count = ix->cl_count.p;
+        v.n_clusters = ix->n_clusters; v.n_levels = (uint32_t)ix->h_lvl_begin.size(); v.max_level_clusters = ix->max_level_clusters;
+        v.queries_padded = c.qpad.p; v.nq = nq; v.nq_pad = nq_pad; v.dpad = ix->dpad; v.similarity = ix->cfg.vector_similarity;
+        v.ann_mode = ivf->mode; v.n_probe = ivf->n_probe; v.cluster_threshold = ivf->thr;
+        v.words = (ix->n_clusters + 31) / 32;
+        SSB_TRY(c.ivf_scores.reserve((size_t)nq * ix->n_clusters, 0, st));
+        SSB_TRY(c.ivf_sel.reserve((size_t)nq_pad * v.words, 0, st));
+        SSB_TRY(c.ivf_obs.reserve(nq, 0, st));
+        v.scores = c.ivf_scores.p; v.sel = c.ivf_sel.p; v.observed = c.ivf_obs.p; v.launches = &c.stats.kernel_launches;
+        SSB_TRY(vec::launch_ivf_select(v, st));
+        a.ivf_sel = c.ivf_sel.p; a.ivf_words = v.words; a.row_cluster = ix->row_cluster.p;
+    }
     if (ix->quant_i8) {
         a.rows_i8 = ix->rows_i8.p; a.queries_i8 = c.q_i8.p; a.dpad8 = ix->dpad8;
         if (ix->cfg.vector_similarity != SSB_SIM_COSINE) {
@@ -242,12 +281,26 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
         SSB_TRY(c.qhi.reserve((size_t)nq_pad * ix->dpad, 0, st));
         SSB_TRY(c.qlo.reserve((size_t)nq_pad * ix->dpad, 0, st));
         a.q_hi = c.qhi.p; a.q_lo = c.qlo.p;
-        SSB_TRY(vec::launch_scan_tc(a, qt, tc_bf16 ? 1 : 0, st));
+        if (filter) a.q_scale = c.q_scale.p;
+        SSB_TRY(vec::launch_scan_tc(a, qt, filter ? 3 : (tc_bf16 ? 1 : 0), st));
+        if (filter) {
+            vec::RefineArgs r{};
+            r.rows = ix->rows.p; r.doc_ids = ix->doc_ids.p; r.n_rows = ix->n_rows; r.dpad = ix->dpad; r.queries_padded = c.qpad.p; r.margin = c.q_scale.p;
+            r.keys = merged; r.nq = nq; r.nq_pad = nq_pad; r.k = k;
+            r.fb_lists = c.scratch.p + head_words;
+            r.fb_state = reinterpret_cast<uint32_t*>(r.fb_lists + (size_t)nq_pad * ix->n_sms * LIST);
+            r.del_slot = a.del_slot; r.del_words = a.del_words; r.ivf_sel = a.ivf_sel; r.ivf_words = a.ivf_words; r.row_cluster = a.row_cluster; r.n_sms = ix->n_sms; r.launches = &c.stats.kernel_launches;
+            SSB_TRY(vec::launch_refine(r, st));
+            c.fb_state = r.fb_state;
+        }
     } else {
         SSB_TRY(vec::launch_scan_ffma(a, st));
     }
     SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, st));
     c.stats.algorithmic_bytes += (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * (ix->quant_i8 ? 1 : 4);
+    // bytes the scan kernel actually streams per call: the filter scan reads the 2-byte hi plane, the refine step <= 32 f32 rows per query
+    c.stats.scan_bytes_read += filter ? (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * 2 + (uint64_t)nq * LIST * ix->dims * 4
+                                      : (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * (ix->quant_i8 ? 1 : 4);
     return SSB_OK;
 }
 
@@ -357,7 +410,8 @@ void finish_stats(ssb_index* ix, SearchCtx& c) {
 }
 
 // host-facing vector search: paging beyond 32 results, de-duplication, optional threshold
-int32_t search_vector_host(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_i8, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits) {
+int32_t search_vector_host(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_i8, uint32_t nq, uint32_t k, ssb_hit* hits, uint32_t* n_hits,
+                           const IvfQuery* ivf = nullptr) {
     SSB_TRY(c.keys_a.reserve((size_t)nq * LIST, 0, c.st));
     c.h_keys_a.resize((size_t)nq * LIST);
     PageState ps(c, nq, k, hits, n_hits, ix->dup_docs);
@@ -365,10 +419,18 @@ int32_t search_vector_host(ssb_index* ix, SearchCtx& c, const void* queries, boo
     // keys strictly below the last key of the previous one (keys are a total order on (score desc, doc id asc))
     uint32_t kk = ix->dup_docs ? SSB_K_MAX : (k < SSB_K_MAX ? k : SSB_K_MAX);
     for (uint32_t page = 0; page < 4096; page++) {
-        SSB_TRY(vec_keys(ix, c, queries, queries_i8, nq, kk, c.keys_a.p, page ? c.ceil.p : nullptr));
+        SSB_TRY(vec_keys(ix, c, queries, queries_i8, nq, kk, c.keys_a.p, page ? c.ceil.p : nullptr, ivf));
         SSB_TRY(shard_merge(ix, c, c.keys_a.p, nq));
+        if (ivf && page == 0) {   // observed_vector_count = the vectors of the selected clusters (summed over the shards)
+            SSB_TRY(shard_sum_counts(ix, c, c.ivf_obs.p, nq));
+            c.h_obs.resize(nq);
+            SSB_CUDA_TRY(cudaMemcpyAsync(c.h_obs.data(), c.ivf_obs.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, c.st));
+        }
         SSB_CUDA_TRY(cudaMemcpyAsync(c.h_keys_a.data(), c.keys_a.p, (size_t)nq * LIST * 8, cudaMemcpyDeviceToHost, c.st));
+        uint32_t n_fb = 0;
+        if (c.fb_state) SSB_CUDA_TRY(cudaMemcpyAsync(&n_fb, c.fb_state, 4, cudaMemcpyDeviceToHost, c.st));
         SSB_CUDA_TRY(cudaStreamSynchronize(c.st));
+        c.stats.filter_fallbacks += n_fb;
         c.stats.d2h_bytes += (uint64_t)nq * LIST * 8;
         if (!ps.append(c.h_keys_a.data(), kk)) break;
         kk = ps.next_page_k();
@@ -484,18 +546,29 @@ int32_t ssb_vector_reserve(ssb_index* ix, uint64_t n_rows) {
         if (ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN) {
             SSB_TRY(ix->rows_hi.reserve(n_rows * ix->dpad, ix->n_rows * ix->dpad, st, true));
             SSB_TRY(ix->rows_lo.reserve(n_rows * ix->dpad, ix->n_rows * ix->dpad, st, true));
+            SSB_TRY(ix->rows_h16.reserve(n_rows * ix->dpad, ix->n_rows * ix->dpad, st, true));
         }
     }
     return SSB_OK;
     SSB_API_END
 }
 
-int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride, const uint16_t* local_ids,
-                             uint32_t n, uint32_t dims) {
+}  // extern "C"
+
+// one level (= one add call) of the vector index; cluster_counts = the level's IVF cluster table or null (one cluster).  n is only
+// bounded by the loader (a level may hold one record per chunk, i.e. more than 64K).
+static int32_t vector_add_level_impl(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride, const uint16_t* local_ids,
+                                     uint32_t n, uint32_t dims, const uint32_t* cluster_counts, uint32_t n_clusters) {
     SSB_API_BEGIN
     if (!ix || (n && !rows)) { set_error("ssb_vector_add_level: null argument"); return SSB_E_INVALID; }
     if (ix->dims == 0 || dims != ix->dims) { set_error("dims %u != configured vector_dims %u", dims, ix->dims); return SSB_E_INVALID; }
-    if (n > 65536) { set_error("a level holds at most 65536 vectors"); return SSB_E_INVALID; }
+    if (cluster_counts) {
+        if (dev_ptr(cluster_counts)) { set_error("cluster_counts must be host memory"); return SSB_E_INVALID; }
+        uint64_t sum = 0;
+        for (uint32_t c = 0; c < n_clusters; c++) { if (cluster_counts[c] == 0) { set_error("empty cluster %u", c); return SSB_E_INVALID; } sum += cluster_counts[c]; }
+        if (sum != n || (n && n_clusters == 0)) { set_error("cluster table covers %llu of %u rows", (unsigned long long)sum, n); return SSB_E_INVALID; }
+        if (ix->quant_i8 && n_clusters > 1) { set_error("IVF cluster tables need an f32 vector index"); return SSB_E_UNSUPPORTED; }
+    }
     if (level_id >= 65536) { set_error("level_id must be < 65536 (doc id = level_id << 16 | local)"); return SSB_E_INVALID; }
     if (row_stride == 0) row_stride = dims;
     if (row_stride < dims) { set_error("row stride < dims"); return SSB_E_INVALID; }
@@ -552,6 +625,23 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
             SSB_TRY(ix->rows_hi.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, st));
             SSB_TRY(ix->rows_lo.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, st));
             SSB_TRY(vec::launch_split_rows_bf16(dst, ix->rows_hi.p + ix->n_rows * ix->dpad, ix->rows_lo.p + ix->n_rows * ix->dpad, (size_t)n * ix->dpad, st));
+            // filter scan: scaled fp16 plane + its index-wide error bounds.  The scale (a power of two, fixed for the life of the index)
+            // puts Cosine's unit rows below 256 and a Dot index's first level into [128, 256): later rows may be 255x larger before fp16
+            // overflows — an overflowing row makes the error bound infinite and every filter query takes the exact fallback.
+            if (!ix->vec_err.p) { SSB_TRY(ix->vec_err.reserve(4, 0, st, true)); SSB_CUDA_TRY(cudaMemsetAsync(ix->vec_err.p, 0, 16, st)); }
+            if (ix->vec_scale == 0.f) {
+                if (ix->cfg.vector_similarity == SSB_SIM_COSINE) ix->vec_scale = 256.f;
+                else {
+                    uint32_t bits = 0;
+                    SSB_TRY(vec::launch_max_abs_f32(dst, (size_t)n * ix->dpad, ix->vec_err.p + 2, st));
+                    SSB_CUDA_TRY(cudaMemcpyAsync(&bits, ix->vec_err.p + 2, 4, cudaMemcpyDeviceToHost, st));
+                    SSB_CUDA_TRY(cudaStreamSynchronize(st));
+                    float mx; memcpy(&mx, &bits, 4);
+                    ix->vec_scale = mx > 0.f ? exp2f((float)(7 - ilogbf(mx))) : 1.f;
+                }
+            }
+            SSB_TRY(ix->rows_h16.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, st));
+            SSB_TRY(vec::launch_rows_f16_err(dst, ix->rows_h16.p + ix->n_rows * ix->dpad, n, ix->dpad, ix->vec_scale, ix->vec_err.p, st));
         }
     }
     DevTmp<uint16_t> tmp;
@@ -562,10 +652,51 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
         lid = tmp.p;
     }
     SSB_TRY(vec::launch_fill_doc_ids(ix->doc_ids.p + ix->n_rows, lid, level_id, n, st));
+    if (!ix->quant_i8) {
+        // IVF tables: clusters are numbered across levels; a cluster's medoid is its first row (vector.rs:1316-1320)
+        const uint32_t one = n;
+        if (!cluster_counts) { cluster_counts = &one; n_clusters = 1; }
+        std::vector<uint32_t> rc(n), mrow(n_clusters);
+        uint32_t r = 0;
+        for (uint32_t c = 0; c < n_clusters; c++) {
+            mrow[c] = (uint32_t)ix->n_rows + r;
+            for (uint32_t i = 0; i < cluster_counts[c]; i++) rc[r++] = ix->n_clusters + c;
+        }
+        SSB_TRY(ix->row_cluster.reserve(ix->n_rows + n, ix->n_rows, st));
+        SSB_TRY(ix->cl_count.reserve(ix->n_clusters + n_clusters, ix->n_clusters, st));
+        SSB_TRY(ix->medoids.reserve((size_t)(ix->n_clusters + n_clusters) * ix->dpad, (size_t)ix->n_clusters * ix->dpad, st));
+        SSB_TRY(ix->lvl_begin.reserve(ix->h_lvl_begin.size() + 2, 0, st));
+        DevTmp<uint32_t> midx; SSB_CUDA_TRY(midx.alloc(n_clusters));
+        SSB_CUDA_TRY(cudaMemcpyAsync(ix->row_cluster.p + ix->n_rows, rc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        SSB_CUDA_TRY(cudaMemcpyAsync(ix->cl_count.p + ix->n_clusters, cluster_counts, (size_t)n_clusters * 4, cudaMemcpyHostToDevice, st));
+        SSB_CUDA_TRY(cudaMemcpyAsync(midx.p, mrow.data(), (size_t)n_clusters * 4, cudaMemcpyHostToDevice, st));
+        SSB_TRY(vec::launch_gather_rows(ix->rows.p, midx.p, n_clusters, ix->dpad, ix->medoids.p + (size_t)ix->n_clusters * ix->dpad, st));
+        std::vector<uint32_t> lb = ix->h_lvl_begin; lb.push_back(ix->n_clusters); lb.push_back(ix->n_clusters + n_clusters);
+        SSB_CUDA_TRY(cudaMemcpyAsync(ix->lvl_begin.p, lb.data(), lb.size() * 4, cudaMemcpyHostToDevice, st));
+        SSB_CUDA_TRY(cudaStreamSynchronize(st));
+        ix->h_lvl_begin.push_back(ix->n_clusters);
+        ix->n_clusters += n_clusters;
+        if (n_clusters > ix->max_level_clusters) ix->max_level_clusters = n_clusters;
+    }
     SSB_CUDA_TRY(cudaStreamSynchronize(st));
     ix->n_rows += n;
     return SSB_OK;
     SSB_API_END
+}
+
+extern "C" {
+
+int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride, const uint16_t* local_ids,
+                             uint32_t n, uint32_t dims) {
+    if (n > 65536) { set_error("a level holds at most 65536 vectors"); return SSB_E_INVALID; }
+    return vector_add_level_impl(ix, level_id, rows, row_stride, local_ids, n, dims, nullptr, 0);
+}
+
+int32_t ssb_vector_add_level_clustered(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride, const uint16_t* local_ids,
+                                       uint32_t n, uint32_t dims, const uint32_t* cluster_counts, uint32_t n_clusters) {
+    if (n > 65536) { set_error("a level holds at most 65536 vectors"); return SSB_E_INVALID; }
+    if (n && !cluster_counts) { set_error("ssb_vector_add_level_clustered: null cluster table"); return SSB_E_INVALID; }
+    return vector_add_level_impl(ix, level_id, rows, row_stride, local_ids, n, dims, n ? cluster_counts : nullptr, n_clusters);
 }
 
 int32_t ssb_load_index_bin(ssb_index* ix, const void* bytes, uint64_t len, const ssb_index_bin_params* params, uint64_t* n_docs_out) {
@@ -594,11 +725,13 @@ int32_t ssb_load_vector_bin(ssb_index* ix, const void* bytes, uint64_t len, uint
     SSB_TRY(parse_vector_bin((const uint8_t*)bytes, len, ix->dims, levels));
     uint64_t total = 0;
     for (auto& vl : levels) {
-        for (size_t s = 0; s < vl.ids.size(); s += 65536) {      // a level may hold more than 64K records (one per chunk)
-            const uint32_t n = (uint32_t)std::min<size_t>(65536, vl.ids.size() - s);
-            SSB_TRY(ssb_vector_add_level(ix, vl.level_id, vl.rows.data() + s * ix->dims, ix->dims, vl.ids.data() + s, n, ix->dims));
-            total += n;
-        }
+        // a level may hold more than 64K records (one per chunk); its cluster table (IVF, vector.rs:1066-1094) rides along.  Empty clusters
+        // cannot be probed (their medoid would be another cluster's record): such a table is dropped, the level becomes one cluster.
+        bool ok = !vl.cluster_counts.empty() && !ix->quant_i8;
+        for (uint32_t c : vl.cluster_counts) ok = ok && c != 0;
+        SSB_TRY(vector_add_level_impl(ix, vl.level_id, vl.rows.data(), ix->dims, vl.ids.data(), (uint32_t)vl.ids.size(), ix->dims,
+                                      ok ? vl.cluster_counts.data() : nullptr, ok ? (uint32_t)vl.cluster_counts.size() : 0));
+        total += vl.ids.size();
     }
     if (n_vectors_out) *n_vectors_out = total;
     return SSB_OK;
@@ -641,7 +774,7 @@ int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n) {
 
 int32_t ssb_set_vector_kernel(ssb_index* ix, uint32_t kernel) {
     SSB_API_BEGIN
-    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_BF16_N256) { set_error("bad vector kernel"); return SSB_E_INVALID; }
+    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_FILTER_N256) { set_error("bad vector kernel"); return SSB_E_INVALID; }
     std::unique_lock<std::shared_mutex> g(ix->rw);
     ix->cfg.vector_kernel = kernel;
     return SSB_OK;
@@ -686,9 +819,16 @@ int32_t ssb_search_vector_ex(ssb_index* ix, const ssb_vec_query* vq, ssb_hit* hi
     if (k == 0 || k > SSB_K_LIMIT) { set_error("k must be in 1..%u", SSB_K_LIMIT); return SSB_E_UNSUPPORTED; }
     CtxLease l(ix); SSB_TRY(l.acquire());
     std::vector<uint32_t> nh(nq, 0);
-    SSB_TRY(search_vector_host(ix, *l.c, vq->queries, vq->query_format == SSB_QFMT_I8, nq, k, hits, nh.data()));
-    finish_stats(ix, *l.c);
     const bool euclid = ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN;
+    if (vq->ann_mode > SSB_ANN_NPROBE_SIMILARITY_THRESHOLD) { set_error("bad ann_mode"); return SSB_E_INVALID; }
+    IvfQuery ivf{vq->ann_mode, vq->n_probe, 0.f};
+    {   // the cluster threshold goes through the same pre-map as the result threshold (TopK::new, vector.rs:388-399)
+        volatile float c2 = vq->cluster_threshold * 2.0f; volatile float c21 = c2 - 1.0f;
+        ivf.thr = euclid ? -vq->cluster_threshold : c21 / (1.0f / 16129.0f);
+    }
+    const bool use_ivf = vq->ann_mode != SSB_ANN_ALL;
+    SSB_TRY(search_vector_host(ix, *l.c, vq->queries, vq->query_format == SSB_QFMT_I8, nq, k, hits, nh.data(), use_ivf ? &ivf : nullptr));
+    finish_stats(ix, *l.c);
     // TopK::new (vector.rs:388-399): threshold pre-map (2t-1)*16129 for Dot/Cosine, -t for Euclidean; TopK::push (:421) rejects
     // score < threshold.  The hits are sorted by score, so dropping the tail is the same filter.
     volatile float t2 = vq->similarity_threshold * 2.0f; volatile float t21 = t2 - 1.0f;
@@ -702,7 +842,7 @@ int32_t ssb_search_vector_ex(ssb_index* ix, const ssb_vec_query* vq, ssb_hit* hi
             n = m;
         }
         if (n_hits) n_hits[q] = n;
-        if (observed) observed[q] = ix->n_rows;              // AnnMode::All scores every record (observed_vector_count, vector.rs:420)
+        if (observed) observed[q] = use_ivf ? l.c->h_obs[q] : ix->n_rows;   // AnnMode::All scores every record (observed_vector_count, vector.rs:420); else: the selected clusters' vectors
         if (ext) for (uint32_t j = 0; j < k; j++) {
             ssb_hit_ext& e = ext[(size_t)q * k + j];
             memset(&e, 0, sizeof(e));

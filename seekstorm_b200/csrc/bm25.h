@@ -192,7 +192,7 @@ private:
 };
 
 // loader.cu: the reference's on-disk files -> index
-struct VectorLevel { uint32_t level_id; std::vector<uint16_t> ids; std::vector<float> rows; };
+struct VectorLevel { uint32_t level_id; std::vector<uint16_t> ids; std::vector<float> rows; std::vector<uint32_t> cluster_counts; };
 int32_t load_index_bin(LexIndex* lex, const uint8_t* bytes, uint64_t len, const ssb_index_bin_params* prm, uint64_t* n_docs_out);
 int32_t inspect_index_bin(const uint8_t* bytes, uint64_t len, const ssb_index_bin_params* prm, uint64_t out[8]);
 int32_t parse_vector_bin(const uint8_t* bytes, uint64_t len, uint32_t dims, std::vector<VectorLevel>& out);

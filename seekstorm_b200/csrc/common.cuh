@@ -115,6 +115,13 @@ __device__ __forceinline__ bool doc_deleted(const uint32_t* __restrict__ del_slo
     return ((__ldg(&del_words[(size_t)slot * 1024 + ((doc & 0xFFFFu) >> 6)]) >> (doc & 63u)) & 1ull) != 0;
 }
 
+// IVF probe (vec_ivf.cu): is the row's cluster NOT selected for this query?  sel = [nq][words] bit per (query, cluster), null = AnnMode::All
+__device__ __forceinline__ bool ivf_skipped(const uint32_t* __restrict__ sel, uint32_t words, uint32_t q, const uint32_t* __restrict__ row_cluster, uint32_t row) {
+    if (!sel) return false;
+    const uint32_t c = __ldg(&row_cluster[row]);
+    return ((__ldg(&sel[(size_t)q * words + (c >> 5)]) >> (c & 31u)) & 1u) == 0u;
+}
+
 // ---------------------------------------------------------------- PTX: mbarrier + TMA
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

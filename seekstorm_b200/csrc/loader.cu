@@ -220,10 +220,11 @@ int32_t parse_vector_bin(const uint8_t* bytes, uint64_t len, uint32_t dims, std:
         const uint32_t clusters = r.u32();
         if (!r.ok || !r.need((uint64_t)clusters * 4)) { set_error("load_vector_bin: truncated cluster table (level %u)", level); return SSB_E_INVALID; }
         uint64_t n = 0;
-        for (uint32_t c = 0; c < clusters; c++) n += r.u32();
+        std::vector<uint32_t> counts(clusters);
+        for (uint32_t c = 0; c < clusters; c++) { counts[c] = r.u32(); n += counts[c]; }
         if (n > 65536ull * 64) { set_error("load_vector_bin: level %u holds %llu records", level, (unsigned long long)n); return SSB_E_INVALID; }
         if (!r.need(n * rec)) { set_error("load_vector_bin: truncated records (level %u)", level); return SSB_E_INVALID; }
-        VectorLevel vl; vl.level_id = level; vl.ids.resize(n); vl.rows.resize(n * dims);
+        VectorLevel vl; vl.level_id = level; vl.ids.resize(n); vl.rows.resize(n * dims); vl.cluster_counts = std::move(counts);
         for (uint64_t i = 0; i < n; i++) {
             const uint8_t* h = bytes + r.pos + i * rec;
             vl.ids[i] = rd16(h);                                   // VectorHeader.doc_id (vector.rs:65-73); field / chunk ids are not kept

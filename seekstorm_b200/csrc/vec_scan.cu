@@ -57,6 +57,7 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint32_t* __restrict__ thr_init /*[gridDim.y*QT] or null*/, uint32_t nq_valid,
           const uint64_t* __restrict__ ceil_keys /*[gridDim.y*QT] or null*/,
           const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words,
+          const uint32_t* __restrict__ ivf_sel, uint32_t ivf_words, const uint32_t* __restrict__ row_cluster /*IVF selection mask or null*/,
           uint32_t sample_mode /* 1: threshold-seeding pass — keep the row-group score maxima, no lists */) {
     // no static shared memory in this kernel: the dynamic segment starts at offset 0 of the CTA window, so the
     // 1024-byte alignment SWIZZLE_128B needs holds and the pointers stay in the shared address space (LDS, not LD)
@@ -191,7 +192,8 @@ scan_ffma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                     uint32_t row_s = __shfl_sync(FULL, row, src);
                                     uint32_t doc = doc_ids ? __ldg(&doc_ids[row_s]) : row_s;
                                     uint64_t key = ((uint64_t)so_s << 32) | (uint64_t)(0xFFFFFFFFu - doc);
-                                    if (key < ceil && !doc_deleted(del_slot, del_words, doc)) wl_insert(Lq, key, lane);
+                                    if (key < ceil && !doc_deleted(del_slot, del_words, doc) && !ivf_skipped(ivf_sel, ivf_words, group * QT + qh + q, row_cluster, row_s))
+                                        wl_insert(Lq, key, lane);
                                 }
                                 myL[q * LIST] = Lq;
                                 const uint32_t kth = (uint32_t)(shfl64(Lq, (int)k - 1) >> 32);
@@ -220,9 +222,14 @@ merge_lists(const uint64_t* __restrict__ in, uint32_t n_lists, uint32_t qt, uint
     const uint32_t q = blockIdx.x;
     const uint64_t* base = in + (size_t)(q / qt) * n_lists * qt * LIST + (size_t)(q % qt) * LIST;
     uint64_t L = 0;
-    for (uint32_t l = warp; l < n_lists; l += 8) {
-        uint64_t B = __ldg(&base[(size_t)l * qt * LIST + lane]);
-        if (__any_sync(FULL, B != 0)) L = wl_merge(L, B, lane);
+    // four independent loads in flight per warp (the walk is latency-bound: 74 dependent L2 / HBM round trips per warp for the 592 lists of
+    // a tensor-core scan took 43 us under ncu); most lists are empty and skip the merge
+    for (uint32_t l = warp; l < n_lists; l += 32) {
+        uint64_t B[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) B[u] = l + 8 * u < n_lists ? __ldg(&base[(size_t)(l + 8 * u) * qt * LIST + lane]) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (__any_sync(FULL, B[u] != 0)) L = wl_merge(L, B[u], lane);
     }
     sm[warp][lane] = L;
     __syncthreads();
@@ -344,7 +351,7 @@ __global__ void fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t 
 template <class F>
 static int32_t with_presample(const ScanArgs& a, cudaStream_t st, F launch) {
     // with a delete set the sample pass is skipped: a deleted row must never seed a threshold
-    if (a.thr_init || !a.thr_buf || a.del_slot || vec_presample_rows(a.n_rows, false) == 0) return launch(a);
+    if (a.thr_init || !a.thr_buf || a.del_slot || a.ivf_sel || vec_presample_rows(a.n_rows, false) == 0) return launch(a);   // (IVF mask: same reason)
     ScanArgs pre = a;
     pre.n_rows = vec_presample_rows(a.n_rows, false); pre.ev0 = nullptr; pre.ev1 = nullptr;
     pre.sample_groupmax = true;                              // the sample launch writes the thresholds (thr_buf) itself
@@ -372,7 +379,8 @@ static int32_t launch_scan_ffma_impl(const ScanArgs& a, cudaStream_t st) {
     SSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     if (a.ev0) cudaEventRecord(a.ev0, st);
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmQ, (uint32_t)a.n_rows, a.dpad / KC, n_tiles, a.k, a.doc_ids,
-                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, a.del_slot, a.del_words, a.sample_groupmax ? 1u : 0u);
+                                            a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, a.del_slot, a.del_words, a.ivf_sel, a.ivf_words, a.row_cluster,
+                                            a.sample_groupmax ? 1u : 0u);
     if (a.sample_groupmax) {
         SSB_CUDA_TRY(cudaGetLastError());
         launch_kth_from_groupmax(a.scratch, n_tiles * 16, a.nq_pad, a.k, a.thr_buf, 0, st);

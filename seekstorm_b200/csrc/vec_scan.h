@@ -11,6 +11,7 @@ constexpr int VEC_QT = 16;      // queries per corpus pass of the FFMA kernel
 struct ScanArgs {
     const float* rows;            // [n_rows][dpad]
     const void* rows_hi = nullptr; const void* rows_lo = nullptr;   // bf16 planes [n_rows][dpad] of the same rows (tcgen05 bf16 scan)
+    const void* rows_h16 = nullptr;   // scaled fp16 plane [n_rows][dpad] (filter scan)
     const uint32_t* doc_ids;      // [n_rows] or nullptr
     uint64_t n_rows;
     uint32_t dpad;                // multiple of 32
@@ -37,6 +38,9 @@ struct ScanArgs {
     const float* q_scale = nullptr; const float* q_norm = nullptr;       // [nq_pad]
     const uint32_t* del_slot = nullptr; const uint64_t* del_words = nullptr;   // delete set (null = none): deleted docs never enter a list
     bool sample_groupmax = false;                  // internal (int8): threshold-seeding pass, writes thr_buf instead of lists
+    // IVF probe (vec_ivf.cu): selection mask [nq_pad][ivf_words] (bit per (query, cluster)) and each row's cluster id; null = AnnMode::All.
+    // f32 scans only.  Like the delete set it disables the threshold-seeding sample pass (an unselected row must never seed a threshold).
+    const uint32_t* ivf_sel = nullptr; uint32_t ivf_words = 0; const uint32_t* row_cluster = nullptr;
 };
 
 // rows scanned first to seed the per-query top-k thresholds (0 = shard too small to bother).  With S sample rows the full
@@ -53,11 +57,48 @@ inline uint64_t vec_presample_rows(uint64_t n_rows, bool tensor_core) {
 
 int32_t launch_scan_ffma(const ScanArgs& a, cudaStream_t st);
 size_t scan_scratch_bytes(int n_sms, uint32_t nq_pad);
-int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128*/, int prec /*0: 3xTF32, 1: 3xBF16, 2: int8 (exact)*/, cudaStream_t st);
+int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile /*64|128|256*/, int prec /*0: 3xTF32, 1: 3xBF16, 2: int8 (exact), 3: fp16 filter (q_scale = margins)*/, cudaStream_t st);
 size_t scan_tc_scratch_bytes(int n_sms, uint32_t nq_pad);
 // fused query preparation of the bf16 tensor-core scan: pad + (Cosine) normalise + hi/lo split in one launch
 int32_t launch_prep_split_queries_bf16(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, void* hi, void* lo, uint32_t nq_pad,
-                                       uint32_t dpad, int normalize, cudaStream_t st);
+                                       uint32_t dpad, int normalize, cudaStream_t st, float* f32_out = nullptr, float* margin_out = nullptr,
+                                       const uint32_t* row_err = nullptr);
+// filter scan (vec_refine.cu / DESIGN.md §3.2c).  launch_rows_f16_err: load time, h16 = half_rn(rows * scale), err[0] = max_r |a_r*scale - h_r|,
+// err[1] = max_r |h_r| (f32 bits, atomicMax).  launch_max_abs_f32: *out_bits = max(*out_bits, max|x|) over finite elements.
+int32_t launch_rows_f16_err(const float* rows, void* h16, uint64_t n, uint32_t dpad, float scale, uint32_t* err, cudaStream_t st);
+int32_t launch_max_abs_f32(const float* x, size_t n, uint32_t* out_bits, cudaStream_t st);
+struct RefineArgs {
+    const float* rows; const uint32_t* doc_ids; uint64_t n_rows; uint32_t dpad;
+    const float* queries_padded;      // [nq_pad][dpad] f32 (normalised for Cosine)
+    const float* margin;              // [nq_pad] 2 eps_q
+    uint64_t* keys;                   // in: merged approximate keys [nq_pad][32] (low word = 0xFFFFFFFF - row); out: exact keys (low word = doc id)
+    uint32_t nq, nq_pad, k;
+    uint32_t* fb_state;               // [1 + nq_pad]: count of flagged queries + their indices (zeroed by the refine launch)
+    uint64_t* fb_lists;               // [nq_pad][n_sms][32] fallback scratch
+    const uint32_t* del_slot; const uint64_t* del_words;
+    const uint32_t* ivf_sel; uint32_t ivf_words; const uint32_t* row_cluster;   // IVF selection mask (null = all clusters)
+    int n_sms;
+    uint64_t* launches;
+};
+// IVF probe: medoid scores + per-(query, level) cluster selection -> sel bits, observed vector counts (vec_ivf.cu)
+struct IvfArgs {
+    const float* medoids;             // [n_clusters][dpad] f32 copies of each cluster's first row
+    const uint32_t* lvl_begin;        // [n_levels + 1] first cluster id of every level (arena order)
+    const uint32_t* cl_count;         // [n_clusters] vectors per cluster
+    uint32_t n_clusters, n_levels, max_level_clusters;
+    const float* queries_padded;      // [nq_pad][dpad] f32 (normalised for Cosine)
+    uint32_t nq, nq_pad, dpad, similarity;
+    uint32_t ann_mode, n_probe; float cluster_threshold;   // SSB_ANN_*; threshold already pre-mapped (vector.rs:388-399)
+    float* scores;                    // [nq][n_clusters] scratch
+    uint32_t* sel; uint32_t words;    // [nq_pad][words]
+    uint64_t* observed;               // [nq]
+    uint64_t* launches;
+};
+int32_t launch_ivf_select(const IvfArgs& a, cudaStream_t st);
+int32_t launch_gather_rows(const float* src, const uint32_t* idx_dev, uint32_t n, uint32_t dpad, float* dst, cudaStream_t st);
+// re-score the candidates in f32, sort, flag candidate-set overflows; then the exact fallback scan for flagged queries (exits at once when none)
+int32_t launch_refine(const RefineArgs& a, cudaStream_t st);
+size_t refine_scratch_words(int n_sms, uint32_t nq_pad);   // u64 words behind fb_lists + fb_state
 // load time: f32 rows (already normalised) -> bf16 hi / lo planes
 int32_t launch_split_rows_bf16(const float* rows, void* hi, void* lo, size_t n_elems, cudaStream_t st);
 // lists laid out [group][n_lists][qt][32] -> out [nq][32]

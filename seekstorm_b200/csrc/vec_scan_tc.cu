@@ -32,6 +32,8 @@
 // Threshold seeding: the same kernel runs first in sample mode over one tile per SM and writes per-(32-row group, query)
 // score maxima; kth_from_groupmax turns them into valid lower bounds of the k-th best score.
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "vec_scan.h"
@@ -49,7 +51,15 @@ constexpr int A_BYTES = MT * A1_BYTES; // 32 KB
 constexpr int THREADS = 512;            // 16 warps: TMA, MMA, 2 idle, 4 epilogue, 8 splitters
 constexpr int SPLIT_THREADS = 256;
 constexpr int CHUNK = 8;               // query columns per epilogue step
-enum { PREC_TF32 = 0, PREC_BF16 = 1, PREC_I8 = 2 };
+enum { PREC_TF32 = 0, PREC_BF16 = 1, PREC_I8 = 2, PREC_F16F = 3 };
+// PREC_F16F — the FILTER scan: ONE product h(a).h(b) over an fp16 plane of the corpus (2 bytes per element, a third of
+// the tensor work of the 3-product split; fp16 keeps 11 significand bits, bf16 8 — the margin below is 8x tighter than with the bf16
+// hi plane; rows and queries are pre-scaled by powers of two into fp16's range, everything below lives in that scaled space and is
+// never returned).  The approximate score s^ differs from the (scaled) f32 score s by at most eps_q =
+// max_r|a_r - h(a_r)| * |b| + max_r|h(a_r)| * |b - h(b)| + accumulation slack (Cauchy-Schwarz; both row maxima are computed at load time),
+// so every row of the exact top-k satisfies s^ >= (k-th best s^) - 2 eps_q.  The epilogue keeps exactly that candidate set (keys carry
+// the ROW index, thresholds are lowered by the per-query margin 2 eps_q), refine_candidates (vec_refine.cu) re-scores the <= 32 candidates
+// in f32 from the f32 rows and flags the queries whose candidate set may not have fitted the 32-entry list for the exact fallback scan.
 
 constexpr int MAX_STAGES = 6;
 template <int NQ, int PREC, bool BRES = false> struct Cfg {
@@ -64,15 +74,15 @@ template <int NQ, int PREC, bool BRES = false> struct Cfg {
     // I8  : [A i8 | B i8]: the int8 corpus (quantised at load time) is the MMA operand as TMA delivers it — no splitter
     //       pass, 128 dims per 128-byte swizzle row, 4 smem stages
     static constexpr int STAGES = PREC == PREC_TF32 ? 2 : 4;
-    static constexpr int KCE = PREC == PREC_I8 ? 128 : KC;                     // elements per k-chunk (128 bytes either way)
+    static constexpr int KCE = PREC == PREC_I8 ? 128 : (PREC == PREC_F16F ? 64 : KC);   // elements per k-chunk (128 bytes; bf16 3-product: 64-byte rows)
     static constexpr int B_BYTES = PREC == PREC_BF16 ? NQ * KC * 2 : NQ * KC * 4;
     static constexpr int ALO_OFF = PREC == PREC_BF16 ? 0 : A_BYTES;            // TF32: A_lo   | BF16: A1 (in place)
     static constexpr int A2_OFF = A_BYTES / 2;                                 // BF16: A2 (in place)
     static constexpr int B_OFF = PREC == PREC_TF32 ? 2 * A_BYTES : A_BYTES;
     // BRES (int8 only): the whole quantised query block [n_kchunks][NQ x 128 B] stays resident in smem behind the A stages,
     // so the per-stage L2->SM traffic is the corpus tile alone (stage count chosen at launch from what is left of 227 KB)
-    static constexpr int STAGE_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : (PREC == PREC_BF16 ? A_BYTES + 2 * B_BYTES : 2 * A_BYTES + 2 * B_BYTES));
-    static constexpr int TX_BYTES = BRES ? A_BYTES : (PREC == PREC_I8 ? A_BYTES + B_BYTES : A_BYTES + 2 * B_BYTES);
+    static constexpr int STAGE_BYTES = BRES ? A_BYTES : ((PREC == PREC_I8 || PREC == PREC_F16F) ? A_BYTES + B_BYTES : (PREC == PREC_BF16 ? A_BYTES + 2 * B_BYTES : 2 * A_BYTES + 2 * B_BYTES));
+    static constexpr int TX_BYTES = BRES ? A_BYTES : ((PREC == PREC_I8 || PREC == PREC_F16F) ? A_BYTES + B_BYTES : A_BYTES + 2 * B_BYTES);
     static constexpr int SMEM = STAGES * STAGE_BYTES + NQ * 12 + 256;   // thresholds + (scaled int8) per-query scale / norm
     static constexpr int TMEM_COLS = 2 * MT * NQ;                              // double-buffered MT accumulators
 };
@@ -132,6 +142,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words /*delete set or null*/,
         const float* __restrict__ row_scale, const float* __restrict__ row_norm /*SCALED: [n_rows]*/,
         const float* __restrict__ q_scale, const float* __restrict__ q_norm /*SCALED: [gridDim.y*NQ]*/,
+        const uint32_t* __restrict__ ivf_sel, uint32_t ivf_words, const uint32_t* __restrict__ row_cluster /*IVF selection mask (f32 epilogue) or null*/,
         uint32_t sample_mode /*int8 only: write per-(32-row group, query) score maxima instead of lists*/) {
     using C = Cfg<NQ, PREC, BRES>;
     constexpr int MT = C::MT, TROWS = C::TROWS, A_BYTES = C::A_BYTES;   // (shadow the namespace-level 2-tile defaults)
@@ -162,7 +173,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     if (threadIdx.x == 0) {
         mbar_init(bfull, 1);
         for (uint32_t s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&split[s], SPLIT_THREADS / 32); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], (PREC == PREC_I8 && !SCALED) ? 12 : 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PREC == PREC_TF32 ? 4 : 12); }
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < NQ; i += THREADS) {  // seeded by the pre-sample pass when present
@@ -170,6 +181,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                                                      : (thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u);
         if (PREC == PREC_I8 && !SCALED) t = (uint32_t)ord_to_int(t);   // unscaled int8 path compares the raw int32 dot products
         thr_u[i] = t;
+        if (PREC == PREC_F16F) qs_sm[i] = __ldg(&q_scale[blockIdx.y * NQ + i]);   // filter scan: per-query margin 2 eps_q
         if (SCALED) { qs_sm[i] = __ldg(&q_scale[blockIdx.y * NQ + i]); qn_sm[i] = SCALED == 2 ? __ldg(&q_norm[blockIdx.y * NQ + i]) : 0.f; }
     }
     if (warp == 1) {
@@ -200,17 +212,17 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     tma_load_2d(st, &tmA, (int)(kc * C::KCE), (int)(tile * TROWS), &full[s]);   // 256-row box = MT swizzled tiles
                     if (PREC == PREC_BF16) tma_load_2d(st + C::A2_OFF, &tmA2, (int)(kc * C::KCE), (int)(tile * TROWS), &full[s]);   // lo plane
                     if (!BRES) tma_load_2d(st + C::B_OFF, &tmBh, (int)(kc * C::KCE), (int)(group * NQ), &full[s]);
-                    if (PREC != PREC_I8) tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmBl, (int)(kc * C::KCE), (int)(group * NQ), &full[s]);
+                    if (PREC == PREC_TF32 || PREC == PREC_BF16) tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmBl, (int)(kc * C::KCE), (int)(group * NQ), &full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (tf32 = 2, bf16 = 1), both K-major,
+            // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (tf32 = 2, bf16 = 1, f16 = 0), both K-major,
             // N>>3 at bit 17, M>>4 at bit 24
             // (kind::i8: D = s32 (2 at bit 4), A/B format 1 = signed int8)
-            constexpr uint32_t fmt = PREC == PREC_TF32 ? 2u : 1u;
+            constexpr uint32_t fmt = PREC == PREC_TF32 ? 2u : (PREC == PREC_F16F ? 0u /*kind::f16: F16*/ : 1u);
             constexpr uint32_t cfmt = PREC == PREC_I8 ? 2u : 1u;
             const uint32_t idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t it = 0, ti = 0;
@@ -226,7 +238,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     if (PREC == PREC_TF32) mbar_wait(&split[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stage0 + s * C::STAGE_BYTES);
-                    if (PREC == PREC_I8) {
+                    if (PREC == PREC_I8 || PREC == PREC_F16F) {   // one product; 4 x (K = 32 bytes) inside the 128-byte swizzle row
                         const uint64_t a = umma_desc_k128(sa), b = umma_desc_k128(BRES ? smem_u32(bres + kc * C::B_BYTES) : sa + C::B_OFF);
 #pragma unroll
                         for (uint32_t m = 0; m < MT; m++) {
@@ -393,7 +405,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && (warp < 8 || PREC != PREC_TF32)) {
         // ===================== epilogue: TMEM -> filter -> per-warp per-query top-k (no CTA-level barriers) =====================
         // Each epilogue warp owns the 32 TMEM lanes (= corpus rows) of its quadrant and keeps its own sorted list per
         // query.  The per-query threshold (ordered-uint score of the best k-th entry any warp of the CTA has seen, seeded
@@ -401,9 +413,17 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         // insert.  (An earlier version pushed candidates into per-query buckets with two CTA-wide named barriers per
         // 8-query chunk and inserted them one by one: the dependent-shuffle insert chain made the epilogue, not the
         // tensor pipe, the limiter.)
-        const int ew = warp - 4;                          // == warp % 4 == TMEM lane quadrant
+        // Except in the tf32 variant (warps 8-15 are its splitters) all 12 warps 4-15 run the epilogue: quadrant ew = warp % 4, column group
+        // g = (warp - 4) / 4 owns the 8-query chunks c = g, g + 3, ... of both M tiles and with them the lists (ew, q) of those queries —
+        // same scratch layout as with 4 warps.  A candidate insert is a dependent global (L2) load + shuffle insert + store, ~1 us of pure
+        // latency for the warp: with one warp per quadrant those inserts, not the tensor pipe or HBM, set the tile period of the filter scan.
+        constexpr int EG = PREC == PREC_TF32 ? 1 : 3;
+        constexpr int NCH3 = (NQ / CHUNK + EG - 1) / EG * EG;   // chunk slots per M tile, rounded up to a multiple of EG so that mc % EG == c % EG
+        const int ew = warp & 3, g = (warp - 4) >> 2;
         uint64_t* mylists = lists + (size_t)ew * NQ * LIST;
-        if (!sample_mode) for (int i = lane; i < NQ * LIST; i += 32) mylists[i] = 0;
+        if (!sample_mode)
+            for (int c = g; c < NQ / CHUNK; c += EG)
+                for (int i = lane; i < CHUNK * LIST; i += 32) mylists[c * CHUNK * LIST + i] = 0;
         __syncwarp();
         uint32_t* gmaxu = (uint32_t*)scratch;            // sample mode (see the int8 epilogue): ordered-uint group maxima
         const uint32_t n_rg = n_tiles * (MT * 4);
@@ -412,8 +432,9 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
             mbar_wait(&tfull[buf], tph);
             tc_fence_after();
-            for (int mc = 0; mc < MT * (NQ / CHUNK); mc++) {
-                const int m = mc / (NQ / CHUNK), c = mc % (NQ / CHUNK);
+            for (int mc = g; mc < MT * NCH3; mc += EG) {             // chunk c of either M tile belongs to warp group c % EG (list ownership)
+                const int m = mc / NCH3, c = mc % NCH3;
+                if (c >= NQ / CHUNK) continue;                        // padding slot of the rounded-up chunk count
                 const uint32_t row = tile * TROWS + (uint32_t)(m * TM) + (uint32_t)(ew * 32 + lane);
                 const bool valid = row < n_rows;
                 uint32_t v[CHUNK];
@@ -472,10 +493,10 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                         uint64_t key = 0;
                         if (pass) {
                             const uint32_t doc = doc_ids ? __ldg(&doc_ids[row]) : row;
-                            key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - doc);
-                            if (doc_deleted(del_slot, del_words, doc)) key = 0;
+                            key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - (PREC == PREC_F16F ? row : doc));   // filter scan: candidates are named by row
+                            if (doc_deleted(del_slot, del_words, doc) || ivf_skipped(ivf_sel, ivf_words, blockIdx.y * NQ + q, row_cluster, row)) key = 0;
                         }
-                        if (ceil_keys || del_slot) {   // paging: keys >= ceil were returned by an earlier page (0 = exhausted)
+                        if (ceil_keys || del_slot || ivf_sel) {   // paging: keys >= ceil were returned by an earlier page (0 = exhausted)
                             if (ceil_keys) { const uint64_t ceil = __ldg(&ceil_keys[blockIdx.y * NQ + q]); if (key >= ceil) key = 0; }
                             pm = __ballot_sync(FULL, key != 0);
                             if (!pm) continue;
@@ -488,7 +509,8 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                             while (pm) { const int src = __ffs(pm) - 1; pm &= pm - 1; wl_insert(L, shfl64(key, src), lane); }
                         }
                         mylists[q * LIST + lane] = L;
-                        const uint32_t kth = (uint32_t)(shfl64(L, (int)k - 1) >> 32);
+                        uint32_t kth = (uint32_t)(shfl64(L, (int)k - 1) >> 32);
+                        if (PREC == PREC_F16F && kth) kth = ord_f32(__fsub_rd(unord_f32(kth), qs_sm[q]));   // candidates: s^ >= k-th best s^ - 2 eps_q
                         if (lane == 0 && kth > thr_u[q]) atomicMax(&thr_u[q], kth);
                     }
                 }
@@ -518,13 +540,22 @@ __global__ void split_queries_tf32(const float* __restrict__ q, float* __restric
 // queries [nq][dims] f32 -> padded, (Cosine:) L2-normalised exactly like prep_queries (vec_scan.cu), split into bf16 hi / lo parts:
 // one launch instead of prep_queries + split (the per-batch launch chain is what limits small shards, SCALE_r01)
 __global__ void prep_split_queries_bf16(const float* __restrict__ q, uint32_t nq, uint32_t dims, uint64_t qstride,
-                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, uint32_t nq_pad, uint32_t dpad, int normalize) {
+                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, uint32_t nq_pad, uint32_t dpad, int normalize,
+                                        float* __restrict__ f32_out /*filter scan: padded f32 queries for the refine step, else null*/,
+                                        float* __restrict__ margin_out /*filter scan: [nq_pad] 2 eps_q*/, const uint32_t* __restrict__ row_err /*{max|a-h(a)|, max|h(a)|} bits*/) {
     const int lane = threadIdx.x & 31;
     const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= nq_pad) return;
+    const bool filter = margin_out != nullptr;             // filter scan: `hi` receives the scaled fp16 query, `lo` is not written
     __nv_bfloat16* oh = hi + (size_t)row * dpad;
     __nv_bfloat16* ol = lo + (size_t)row * dpad;
-    if (row >= nq) { for (uint32_t i = lane; i < dpad; i += 32) { oh[i] = __float2bfloat16_rn(0.f); ol[i] = __float2bfloat16_rn(0.f); } return; }
+    __half* o16 = reinterpret_cast<__half*>(oh);
+    float* of = f32_out ? f32_out + (size_t)row * dpad : nullptr;
+    if (row >= nq) {
+        for (uint32_t i = lane; i < dpad; i += 32) { oh[i] = __float2bfloat16_rn(0.f); if (!filter) ol[i] = __float2bfloat16_rn(0.f); if (of) of[i] = 0.f; }
+        if (filter && lane == 0) margin_out[row] = 0.f;
+        return;
+    }
     const float* src = q + (size_t)row * qstride;
     float f = 1.f;
     if (normalize) {
@@ -533,13 +564,74 @@ __global__ void prep_split_queries_bf16(const float* __restrict__ q, uint32_t nq
         for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(FULL, s, m);
         f = 1.0f / sqrtf(s);
     }
+    if (!filter) {
+        for (uint32_t i = lane; i < dpad; i += 32) {
+            const float x = i < dims ? src[i] * f : 0.f;
+            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+            oh[i] = h;
+            ol[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+            if (of) of[i] = x;
+        }
+        return;
+    }
+    // filter scan: scale the query by a power of two so that its largest element lands in [128, 256) (exact; keeps the small elements
+    // out of fp16's subnormal range), round to fp16, and bound the error of s^ for this query
+    float mx = 0.f;
+    for (uint32_t i = lane; i < dims; i += 32) mx = fmaxf(mx, fabsf(src[i] * f));
+    for (int m = 16; m; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, m));
+    const float sb = (mx > 0.f && mx < 3.0e38f) ? exp2f((float)(7 - ilogbf(mx))) : 1.f;
+    float nb2 = 0.f, eb2 = 0.f;   // |b|^2 and |b - h(b)|^2 of the scaled query
     for (uint32_t i = lane; i < dpad; i += 32) {
         const float x = i < dims ? src[i] * f : 0.f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(x);
-        oh[i] = h;
-        ol[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+        const float xs = x * sb;
+        const __half h = __float2half_rn(xs);
+        const float r = xs - __half2float(h);
+        o16[i] = h;
+        if (of) of[i] = x;
+        nb2 = fmaf(xs, xs, nb2); eb2 = fmaf(r, r, eb2);
+    }
+    // eps_q >= |s - s^| for every row: |a.b - h(a).h(b)| = |(a - h(a)).b + h(a).(b - h(b))| <= E_a |b| + H_a |b - h(b)| (Cauchy-Schwarz, E_a / H_a =
+    // the row maxima computed at load time), plus the f32 accumulation slack of the tensor core (truncating adds: <= 2^-23 of the absolute
+    // sum per element) and of the refine dot product (<= 2^-24): dpad * 2^-22 * H_a |b| covers both with room.  1.001 absorbs the rounding
+    // of this arithmetic itself.
+    for (int m = 16; m; m >>= 1) { nb2 += __shfl_xor_sync(FULL, nb2, m); eb2 += __shfl_xor_sync(FULL, eb2, m); }
+    if (lane == 0) {
+        const float Ea = __uint_as_float(row_err[0]), Ha = __uint_as_float(row_err[1]);
+        const float nb = sqrtf(nb2) * 1.00001f, eb = sqrtf(eb2) * 1.00001f;
+        const float eps = (Ea * nb + Ha * eb + (float)dpad * 2.38418579e-7f * Ha * nb) * 1.001f;
+        margin_out[row] = 2.0f * eps;
     }
 }
+// load time (filter scan): the fp16 plane h = half_rn(x * scale) (scale = a power of two chosen per index) and the index-wide error bounds
+// E_a = max over rows of |x*scale - h|_2, H_a = max over rows of |h|_2, rounded up; one warp per row, maxima kept as f32 bit patterns
+// (non-negative floats order like their bits)
+__global__ void rows_f16_err(const float* __restrict__ x, __half* __restrict__ h16, uint64_t n, uint32_t dpad, float scale, uint32_t* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    float e2 = 0.f, h2 = 0.f;
+    for (uint32_t i = lane; i < dpad; i += 32) {
+        const float xs = x[row * dpad + i] * scale;
+        const __half hh = __float2half_rn(xs);
+        const float h = __half2float(hh), r = xs - h;
+        h16[row * dpad + i] = hh;
+        e2 = fmaf(r, r, e2); h2 = fmaf(h, h, h2);
+    }
+    for (int m = 16; m; m >>= 1) { e2 += __shfl_xor_sync(FULL, e2, m); h2 += __shfl_xor_sync(FULL, h2, m); }
+    if (lane == 0) {
+        const float e = sqrtf(e2) * 1.00001f, h = sqrtf(h2) * 1.00001f;
+        if (!(e < 3.0e38f) || !(h < 3.0e38f)) { atomicMax(&err[0], 0x7F800000u); atomicMax(&err[1], 0x7F800000u); return; }   // NaN / overflowing row: infinite margin -> every query falls back
+        atomicMax(&err[0], __float_as_uint(e)); atomicMax(&err[1], __float_as_uint(h));
+    }
+}
+// max |x| over a block of rows (chooses the fp16 scale of a Dot index from its first level); err[0] as f32 bits
+__global__ void max_abs_f32(const float* __restrict__ x, size_t n, uint32_t* __restrict__ out) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { const float v = fabsf(x[i]); if (v < 3.0e38f) m = fmaxf(m, v); }
+    for (int s = 16; s; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
 // load time: (normalised) f32 corpus rows -> the two bf16 planes the tensor-core scan streams (hi = bf16_rn(x), lo = bf16_rn(x - hi))
 __global__ void split_rows_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -552,14 +644,18 @@ __global__ void split_rows_bf16(const float* __restrict__ x, __nv_bfloat16* __re
 
 // thr[q] = ordered-uint of the k-th largest of gmax[q][0..n_rg) as an f32 score (0 = no threshold when fewer than k groups
 // hold an eligible row).  One warp per query, lane-distributed sorted list, chunks that cannot enter the list are skipped.
-__global__ void kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, uint32_t nq, uint32_t k, uint32_t* __restrict__ thr,
-                                  int is_int /*1: int32 dot products (INT_MIN = none), 0: ordered-uint f32 scores (0 = none)*/) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= nq) return;
+__global__ void __launch_bounds__(256)
+kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, uint32_t nq, uint32_t k, uint32_t* __restrict__ thr,
+                  int is_int /*1: int32 dot products (INT_MIN = none), 0: ordered-uint f32 scores (0 = none)*/,
+                  const float* __restrict__ margin /*filter scan: thr = k-th - margin[q]; else null*/) {
+    // one CTA per query: 8 warps each reduce a slice of the group maxima to a sorted top-32, warp 0 merges the 8 lists (one warp per
+    // query walked n_rg / 32 dependent iterations: 57 us under ncu for 2368 groups x 256 queries, as long as the sample scan itself)
+    __shared__ uint64_t sm[8][LIST];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x;
     const int* g = gmax + (size_t)q * n_rg;
     uint64_t L = 0;
-    for (uint32_t base = 0; base < n_rg; base += 32) {
+    for (uint32_t base = warp * 32; base < n_rg; base += 256) {
         const uint32_t i = base + lane;
         // key: order-preserving unsigned value in the high word (> 0 for every eligible row), group index below it keeps keys distinct
         const uint32_t u = i < n_rg ? ((uint32_t)g[i] ^ (is_int ? 0x80000000u : 0u)) : 0u;
@@ -567,8 +663,16 @@ __global__ void kth_from_groupmax(const int* __restrict__ gmax, uint32_t n_rg, u
         const uint64_t kth = shfl64(L, (int)k - 1);
         if (__any_sync(FULL, key > kth)) L = wl_merge(L, wl_sort_desc(key, lane), lane);
     }
+    sm[warp][lane] = L;
+    __syncthreads();
+    if (warp != 0) return;
+    for (int w = 1; w < 8; w++) L = wl_merge(L, sm[w][lane], lane);
     const uint64_t kth = shfl64(L, (int)k - 1);
-    if (lane == 0) thr[q] = !kth ? 0u : (is_int ? ord_f32((float)(int)((uint32_t)(kth >> 32) ^ 0x80000000u)) : (uint32_t)(kth >> 32));
+    if (lane == 0) {
+        uint32_t t = !kth ? 0u : (is_int ? ord_f32((float)(int)((uint32_t)(kth >> 32) ^ 0x80000000u)) : (uint32_t)(kth >> 32));
+        if (t && margin) t = ord_f32(__fsub_rd(unord_f32(t), margin[q]));
+        thr[q] = t;
+    }
 }
 
 }  // namespace tc
@@ -593,6 +697,13 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
         SSB_TRY(encode_tmap_2d_f32(&tmBl, a.q_lo, a.dpad, a.nq_pad, (uint64_t)a.dpad * 4, tc::KC, NQ, 1));
         tmA2 = tmA;
         if (!a.thr_init) tc::split_queries_tf32<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(a.queries_padded, a.q_hi, a.q_lo, nel);
+    } else if constexpr (PREC == tc::PREC_F16F) {
+        // filter scan: fp16 plane and fp16 queries only, 64 halves (128 bytes) per swizzle row; the box may run past dpad (zero fill)
+        if (!a.rows_h16 || !a.q_scale) { set_error("tcgen05 filter scan: the index holds no fp16 plane / no margins"); return SSB_E_STATE; }
+        SSB_TRY(encode_tmap_2d(&tmA, a.rows_h16, 2 /*fp16: 2-byte elements*/, a.dpad, a.n_rows, (uint64_t)a.dpad * 2, 64, C::TROWS, 128));
+        SSB_TRY(encode_tmap_2d(&tmBh, a.q_hi, 2, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, 64, NQ, 128));
+        tmBl = tmBh; tmA2 = tmA;
+        n_kchunks = (a.dpad + 63) / 64;
     } else {
         // corpus: the two bf16 planes written at load time; queries: the two bf16 parts live in the q_hi / q_lo buffers (half of
         // each is used) and were written by prep_split_queries_bf16 (launch_prep_split_queries_bf16)
@@ -620,12 +731,13 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     tc::scan_tc<NQ, PREC, BRES, SCALED><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmA2, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
                                                                              a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, nst,
                                                                              a.del_slot, a.del_words, a.row_scale, a.row_norm, a.q_scale, a.q_norm,
+                                                                             PREC == tc::PREC_I8 ? nullptr : a.ivf_sel, a.ivf_words, a.row_cluster,
                                                                              a.sample_groupmax ? 1u : 0u);
     if (a.ev1) cudaEventRecord(a.ev1, st);
     SSB_CUDA_TRY(cudaGetLastError());
     if (a.sample_groupmax) {   // threshold seeding pass: scratch holds gmax[nq_pad][n_tiles * 8]
-        tc::kth_from_groupmax<<<(a.nq_pad + 7) / 8, 256, 0, st>>>((const int*)a.scratch, n_tiles * (C::MT * 4), a.nq_pad, a.k, a.thr_buf,
-                                                                      (PREC == tc::PREC_I8 && !SCALED) ? 1 : 0);
+        tc::kth_from_groupmax<<<a.nq_pad, 256, 0, st>>>((const int*)a.scratch, n_tiles * (C::MT * 4), a.nq_pad, a.k, a.thr_buf,
+                                                                      (PREC == tc::PREC_I8 && !SCALED) ? 1 : 0, PREC == tc::PREC_F16F ? a.q_scale : nullptr);
         SSB_CUDA_TRY(cudaGetLastError());
         if (a.launches) *a.launches += PREC == tc::PREC_TF32 ? 3 : 2;   // (tf32 query split +) scan + kth
         return SSB_OK;
@@ -650,6 +762,10 @@ static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec
         return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true>(a, st) : launch_tc_n<128, tc::PREC_I8, false>(a, st);
     }
     if (a.similarity == SSB_SIM_EUCLIDEAN) { set_error("tcgen05 scan supports Dot/Cosine only"); return SSB_E_UNSUPPORTED; }
+    if (prec == 3) {
+        if ((nq_tile != 128 && nq_tile != 256) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 filter scan: query count must be padded to the 128/256 query tile"); return SSB_E_INVALID; }
+        return nq_tile == 256 ? launch_tc_n<256, tc::PREC_F16F>(a, st) : launch_tc_n<128, tc::PREC_F16F>(a, st);
+    }
     if ((nq_tile != 64 && nq_tile != 128 && !(nq_tile == 256 && prec == 1)) || a.nq_pad % nq_tile != 0) { set_error("tcgen05 scan: query count must be padded to the 64/128(/256 bf16) query tile"); return SSB_E_INVALID; }
     if (prec == 1) return nq_tile == 64 ? launch_tc_n<64, tc::PREC_BF16>(a, st) : (nq_tile == 256 ? launch_tc_n<256, tc::PREC_BF16>(a, st) : launch_tc_n<128, tc::PREC_BF16>(a, st));
     return nq_tile == 64 ? launch_tc_n<64, tc::PREC_TF32>(a, st) : launch_tc_n<128, tc::PREC_TF32>(a, st);
@@ -658,14 +774,19 @@ static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec
 int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int prec, cudaStream_t st) {
     // threshold pre-sampling (see vec_scan.cu): scan the first rows, seed the thresholds, then the full scan
     // (with a delete set the sample pass is skipped: a deleted row must never seed a threshold)
-    if (a.thr_init || !a.thr_buf || a.del_slot || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, prec, st);
+    if (a.thr_init || !a.thr_buf || a.del_slot || a.ivf_sel || vec_presample_rows(a.n_rows, true) == 0) return launch_scan_tc_impl(a, nq_tile, prec, st);
     ScanArgs pre = a;
     // The sample pass writes per-(32-row group, query) score maxima instead of lists (no insert storm) and costs the same for one
     // 256-row tile per CTA as for a handful of tiles: sample one tile per SM.  (An earlier version ran the normal list epilogue
     // over N/128 rows: ~90 us per pass, and ncu showed the full scan's epilogue warps waiting on list loads for candidates that
     // a better seed rejects.)
     const uint64_t trows = nq_tile == 256 ? 128 : tc::TROWS;      // rows per stage of the variant that will run
-    uint64_t s = (uint64_t)a.n_sms * trows;
+    // sample tiles per SM: the seed is the k-th best of S sampled rows, the full scan then sees ~k*N/S candidates per query, each a
+    // ~1 us latency-bound list insert for an epilogue warp.  The filter scan streams a pass in half the time of the 3-product scan, so the
+    // same insert load weighs twice as much: it samples more (SSB_TC_SAMPLE_TILES overrides; measured in DESIGN.md §3.2c)
+    static const int env_tiles = [] { const char* e = getenv("SSB_TC_SAMPLE_TILES"); return e ? atoi(e) : 0; }();
+    const int sample_tiles = env_tiles > 0 ? (env_tiles > 16 ? 16 : env_tiles) : ((prec == 3 && nq_tile == 256) ? 2 : 1);
+    uint64_t s = (uint64_t)a.n_sms * trows * sample_tiles;
     if (s > a.n_rows / 4) s = a.n_rows / 4 / trows * trows;
     pre.n_rows = s; pre.ev0 = nullptr; pre.ev1 = nullptr;
     pre.sample_groupmax = true;                          // writes the thresholds straight into thr_buf
@@ -676,13 +797,14 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int prec, cudaStream
 }
 
 void launch_kth_from_groupmax(const void* gmax, uint32_t n_groups, uint32_t nq, uint32_t k, uint32_t* thr, int is_int, cudaStream_t st) {
-    if (nq) tc::kth_from_groupmax<<<(nq + 7) / 8, 256, 0, st>>>((const int*)gmax, n_groups, nq, k, thr, is_int);
+    if (nq) tc::kth_from_groupmax<<<nq, 256, 0, st>>>((const int*)gmax, n_groups, nq, k, thr, is_int, nullptr);
 }
 
 int32_t launch_prep_split_queries_bf16(const float* q, uint32_t nq, uint32_t dims, uint64_t qstride, void* hi, void* lo, uint32_t nq_pad,
-                                       uint32_t dpad, int normalize, cudaStream_t st) {
+                                       uint32_t dpad, int normalize, cudaStream_t st, float* f32_out, float* margin_out, const uint32_t* row_err) {
     if (nq_pad == 0) return SSB_OK;
-    tc::prep_split_queries_bf16<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, dims, qstride, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, nq_pad, dpad, normalize);
+    tc::prep_split_queries_bf16<<<(nq_pad + 7) / 8, 256, 0, st>>>(q, nq, dims, qstride, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, nq_pad, dpad, normalize,
+                                                                  f32_out, margin_out, row_err);
     SSB_CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }
@@ -690,6 +812,19 @@ int32_t launch_prep_split_queries_bf16(const float* q, uint32_t nq, uint32_t dim
 int32_t launch_split_rows_bf16(const float* rows, void* hi, void* lo, size_t n_elems, cudaStream_t st) {
     if (n_elems == 0) return SSB_OK;
     tc::split_rows_bf16<<<(unsigned)((n_elems + 255) / 256), 256, 0, st>>>(rows, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n_elems);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_rows_f16_err(const float* rows, void* h16, uint64_t n, uint32_t dpad, float scale, uint32_t* err, cudaStream_t st) {
+    if (n == 0) return SSB_OK;
+    tc::rows_f16_err<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rows, (__half*)h16, n, dpad, scale, err);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+int32_t launch_max_abs_f32(const float* x, size_t n, uint32_t* out_bits, cudaStream_t st) {
+    if (n == 0) return SSB_OK;
+    tc::max_abs_f32<<<296, 256, 0, st>>>(x, n, out_bits);
     SSB_CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

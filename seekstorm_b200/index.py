@@ -47,9 +47,27 @@ class VectorSimilarity(enum.IntEnum):
     Euclidean = 2
 
 
-class AnnMode(enum.Enum):
-    """vector_similarity.rs:43-67; only exhaustive search is in scope."""
-    All = "All"
+@dataclass(frozen=True)
+class AnnMode:
+    """vector_similarity.rs:43-67: which IVF clusters of each level are searched (vector.rs:1300-1392)."""
+    kind: int = 0                 # SSB_ANN_*: 0 All, 1 Nprobe, 2 Similaritythreshold, 3 NprobeSimilaritythreshold
+    n_probe: int = 0
+    threshold: float = 0.0
+
+    @staticmethod
+    def Nprobe(n):
+        return AnnMode(1, int(n))
+
+    @staticmethod
+    def Similaritythreshold(t):
+        return AnnMode(2, 0, float(t))
+
+    @staticmethod
+    def NprobeSimilaritythreshold(n, t):
+        return AnnMode(3, int(n), float(t))
+
+
+AnnMode.All = AnnMode()
 
 
 @dataclass
@@ -128,7 +146,8 @@ class Index:
                  vector_similarity: VectorSimilarity = VectorSimilarity.Cosine, max_batch: int = 4096,
                  term_key_fn: Callable[[str], int] = synthetic_term_key, vector_kernel: int = 0,
                  vector_quantization: int = 0):
-        """vector_kernel: 0 = auto, 1 = FP32 FFMA scan, 2 = tcgen05 (3xTF32) scan."""
+        """vector_kernel: SSB_VEC_KERNEL_* (0 = auto, 1 = FP32 FFMA scan, 2/3 = tcgen05 3xTF32, 4/5/6 = tcgen05 3xBF16 with 128/64/256
+        queries per pass, 7/8 = bf16 filter scan + exact f32 refine with 128/256 queries per pass)."""
         self._h = C.c_void_p()
         cfg = SsbConfig(device, max_batch, vector_dims, int(vector_similarity), vector_kernel, int(vector_quantization),
                         (C.c_uint32 * 2)(0, 0))
@@ -230,11 +249,16 @@ class Index:
         a = np.ascontiguousarray(np.asarray(list(doc_ids), dtype=np.uint64))
         check(lib().ssb_set_deleted(self._h, a.ctypes.data if a.size else None, a.size))
 
-    def add_vector_level(self, level_id: int, rows, local_ids=None):
-        """rows: [n, dims] f32 (numpy or torch, host or device), n <= 65536."""
+    def add_vector_level(self, level_id: int, rows, local_ids=None, cluster_counts=None):
+        """rows: [n, dims] f32 (numpy or torch, host or device), n <= 65536.  cluster_counts: the level's IVF cluster table (rows in
+        cluster order, medoid = first row of each cluster; vector.rs:1066-1094) or None = one cluster."""
         n, dims = int(rows.shape[0]), int(rows.shape[1])
         stride = rows.strides[0] // 4 if isinstance(rows, np.ndarray) else rows.stride(0)
-        check(lib().ssb_vector_add_level(self._h, level_id, _addr(rows), stride, _addr(local_ids), n, dims))
+        if cluster_counts is None:
+            check(lib().ssb_vector_add_level(self._h, level_id, _addr(rows), stride, _addr(local_ids), n, dims))
+        else:
+            cc = np.ascontiguousarray(cluster_counts, dtype=np.uint32)
+            check(lib().ssb_vector_add_level_clustered(self._h, level_id, _addr(rows), stride, _addr(local_ids), n, dims, cc.ctypes.data, len(cc)))
 
     def reserve_vectors(self, n_rows: int):
         """Capacity hint (ssb_vector_reserve): one allocation for n_rows rows instead of geometric growth while loading."""
@@ -329,7 +353,8 @@ class Index:
     def hits_buffer(n):
         return _hits_array(n)
 
-    def search_vector_ex(self, queries, k: int, similarity_threshold=None, int8_queries: bool = False):
+    def search_vector_ex(self, queries, k: int, similarity_threshold=None, int8_queries: bool = False, ann_mode: int = 0, n_probe: int = 0,
+                         cluster_threshold: float = 0.0):
         """ssb_search_vector_ex: threshold (vector.rs:388-399), int8 query codes, vb result fields, observed_vector_count.
         Returns (hits per query, ext structured array [nq, k], observed [nq])."""
         from ._lib import SsbHitExt, SsbVecQuery
@@ -341,7 +366,7 @@ class Index:
         ext = (SsbHitExt * max(nq * k, 1))()
         observed = np.zeros(max(nq, 1), dtype=np.uint64)
         vq = SsbVecQuery(_addr(queries), nq, k, 1 if int8_queries else 0, 0 if similarity_threshold is None else 1,
-                         0.0 if similarity_threshold is None else float(similarity_threshold), (C.c_uint32 * 3)(0, 0, 0))
+                         0.0 if similarity_threshold is None else float(similarity_threshold), int(ann_mode), int(n_probe), float(cluster_threshold))
         check(lib().ssb_search_vector_ex(self._h, C.byref(vq), hits.ctypes.data, n_hits.ctypes.data, C.addressof(ext), observed.ctypes.data))
         out = []
         for i in range(nq):
@@ -369,7 +394,8 @@ class Index:
         return dict(kernel_launches=s.kernel_launches, algorithmic_bytes=s.algorithmic_bytes, h2d_bytes=s.h2d_bytes,
                     d2h_bytes=s.d2h_bytes, postings_visited=s.postings_visited, probes=s.probes,
                     items_processed=s.items_processed, items_skipped=s.items_skipped,
-                    dominant_kernel_ns=s.dominant_kernel_ns)
+                    dominant_kernel_ns=s.dominant_kernel_ns, scan_bytes_read=s.scan_bytes_read,
+                    filter_fallbacks=s.filter_fallbacks)
 
     # ------------------------------------------------------------------ device-resident API (bench / multi-GPU)
     def search_vector_keys(self, queries_dev, k: int, keys_out_dev):
@@ -446,7 +472,9 @@ class Index:
         if want_vec:
             qv = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)
             # similarity_threshold (TopK::new, vector.rs:388-399) and observed_vector_count are handled behind the C-ABI
-            res, _, observed = self.search_vector_ex(qv, max(heap, 1), search_mode.similarity_threshold)
+            am = search_mode.ann_mode or AnnMode.All
+            res, _, observed = self.search_vector_ex(qv, max(heap, 1), search_mode.similarity_threshold, ann_mode=am.kind, n_probe=am.n_probe,
+                                                     cluster_threshold=am.threshold)
             vec = res[0][:heap]
             ro.observed_vector_count = int(observed[0])
         if search_mode.kind == "Lexical":

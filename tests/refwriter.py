@@ -158,11 +158,15 @@ def write_index_bin(levels, n_docs_total, seed=0):
 
 
 def write_vector_bin(levels):
-    """levels: list of (local_ids u16 array, rows f32 [n, dims]) per level, one cluster per level (Clustering::None)."""
+    """levels: list of (local_ids u16 array, rows f32 [n, dims][, cluster child counts]) per level — `u32 clusters; u32 child_count x clusters;
+    records` (vector.rs:1066-1094); without a table: one cluster per level (Clustering::None)."""
     out = []
-    for ids, rows in levels:
+    for lv in levels:
+        ids, rows = lv[0], lv[1]
         n = len(ids)
-        out.append(struct.pack("<II", 1, n))
+        counts = [n] if len(lv) < 3 or lv[2] is None else [int(c) for c in lv[2]]
+        assert sum(counts) == n
+        out.append(struct.pack("<I", len(counts)) + b"".join(struct.pack("<I", c) for c in counts))
         for i in range(n):
             out.append(struct.pack("<HIIffhi", int(ids[i]), 0, 0, 1.0, 1.0, 0, 0))
             out.append(np.asarray(rows[i], dtype="<f4").tobytes())

@@ -22,7 +22,7 @@ def test_stats_and_kernel_selection():
         ix.set_vector_kernel(kern)
         outs[kern] = ix.search_vector_batch(q, 10)
         st = ix.last_stats()
-        assert st["kernel_launches"] == {1: 5, 2: 6, 3: 6, 4: 5, 5: 5, 0: 5}[kern]   # FP32: prep + sample(scan, kth) + scan + merge; tf32: prep + split + sample(scan, kth) + scan + merge; bf16: fused prep/split + sample(scan, kth) + scan + merge
+        assert st["kernel_launches"] == {1: 5, 2: 6, 3: 6, 4: 5, 5: 5, 0: 8}[kern]   # FP32: prep + sample(scan, kth) + scan + merge; tf32: prep + split + sample(scan, kth) + scan + merge; bf16: fused prep/split + sample(scan, kth) + scan + merge; AUTO (50 queries) -> filter scan: + refine + fallback scan / merge (both exit at once)
         assert st["dominant_kernel_ns"] > 0
         assert st["h2d_bytes"] == 50 * 64 * 4 and st["d2h_bytes"] == 50 * 32 * 8
         passes = {1: 4, 2: 1, 3: 1, 4: 1, 5: 1, 0: 1}[kern]   # 50 queries: 4 x 16, 1 x 128, 1 x 64, AUTO -> tcgen05
@@ -32,7 +32,7 @@ def test_stats_and_kernel_selection():
             assert [d for d, _ in a] == [d for d, _ in b]
             assert np.allclose([s for _, s in a], [s for _, s in b], rtol=1e-4, atol=1e-6)
     with pytest.raises(Exception):
-        ix.set_vector_kernel(9)
+        ix.set_vector_kernel(11)
     ix.close()
 
 
@@ -304,7 +304,7 @@ def test_delete_set_lexical_vector_hybrid():
             assert int(cnt[i]) == tot, (i, k, int(cnt[i]), tot)
             assert not any(d in deleted for d, _ in got[i])
     nrows = np.stack([O.normalize(r) for r in rows])
-    for kern in (1, 4):
+    for kern in (1, 4, 7):
         ix.set_vector_kernel(kern)
         got = ix.search_vector_batch(qv, 10)
         for i in range(len(qv)):

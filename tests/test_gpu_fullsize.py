@@ -35,6 +35,17 @@ def test_c2_full_size_vector():
         ix.set_vector_kernel(kern)
         full = ix.search_vector_batch(q.cpu().numpy(), 10)
         assert ix.search_vector_batch(q[5:12].cpu().numpy(), 10) == full[5:12]
+    # the filter scan (AUTO's choice above 16 queries) against the exact 3-product tensor-core scan: same ids
+    ix.set_vector_kernel(4)
+    exact = ix.search_vector_batch(q.cpu().numpy(), 10)
+    for kern in (7, 8):
+        ix.set_vector_kernel(kern)
+        filt = ix.search_vector_batch(q.cpu().numpy(), 10)
+        st = ix.last_stats()
+        assert st["scan_bytes_read"] == n * d * 2 + 48 * 32 * d * 4 and st["filter_fallbacks"] == 0
+        for a_, g_ in zip(filt, exact):
+            assert [x for x, _ in a_] == [x for x, _ in g_]
+            assert np.allclose([s for _, s in a_], [s for _, s in g_], rtol=1e-4)
     ix.set_vector_kernel(0)
     # oracle on 4 queries (multi-threaded exhaustive scan of the normalised corpus)
     nrows = (rows / rows.norm(dim=1, keepdim=True)).cpu().numpy()

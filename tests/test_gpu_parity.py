@@ -222,7 +222,7 @@ def test_errors_are_status_codes():
     ix.close()
 
 
-@pytest.mark.parametrize("kernel", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("kernel", [2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("n,dims,sim", [(300, 32, "dot"), (5000, 128, "cos"), (40000, 768, "cos"), (1000, 100, "dot")])
 def test_vector_tcgen05_parity(n, dims, sim, kernel):
     """tcgen05 (3xTF32 split, TMEM accumulators) scan vs the oracle: same ids, scores within 1e-4 relative."""
@@ -232,11 +232,19 @@ def test_vector_tcgen05_parity(n, dims, sim, kernel):
     rows = synth.gen_vectors(n, dims, 3000 + n, "cpu").numpy()
     qs = synth.gen_vectors(150, dims, 4000 + n, "cpu").numpy()      # 150 -> padded to 256 = two query groups
     qs[3] = rows[n // 2] + 0.05 * qs[3]
-    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_kernel=kernel)   # 2/3: 3xTF32 (128/64 queries per pass), 4/5/6: 3xBF16 (128/64/256)
+    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_kernel=kernel)   # 2/3: 3xTF32 (128/64 queries per pass), 4/5/6: 3xBF16 (128/64/256), 7/8: bf16 filter + f32 refine (128/256)
     ix.add_vectors(rows)
     ref_rows = np.stack([O.normalize(r) for r in rows]) if sim == "cos" else rows
-    for k in (10, 32):
+    for k in (10, 32) if kernel < 7 else (1, 10, 16, 32):
         got = ix.search_vector_batch(qs, k)
+        if kernel >= 7:
+            # the filter scan really ran for k <= 16 (it streams 2 bytes per element + the candidate rows); k = 32 takes the exact scan
+            qt = 128 if kernel == 7 else 256
+            passes = (len(qs) + qt - 1) // qt
+            p128, p256 = (len(qs) + 127) // 128, (len(qs) + 255) // 256
+            exact_passes = p256 if (kernel == 8 and p256 * 95 < p128 * 55) else p128      # k > 16: the exact 3-product scan AUTO would pick
+            want_bytes = passes * n * dims * 2 + len(qs) * 32 * dims * 4 if k <= 16 else exact_passes * n * dims * 4
+            assert ix.last_stats()["scan_bytes_read"] == want_bytes
         for i in range(0, len(qs), 7):
             q = O.normalize(qs[i]) if sim == "cos" else qs[i]
             _check_vec(got[i], O.search_vector(ref_rows, q, k, osim))
@@ -343,4 +351,39 @@ def test_hybrid_with_int8_vectors():
         want = O.rrf(lex, vec)[:10]
         assert [d for d, _ in got[i]] == [d for d, _ in want], (i, got[i], want)
         assert np.allclose([s for _, s in got[i]], [s for _, s in want], rtol=1e-6)
+    ix.close()
+
+
+@pytest.mark.parametrize("kernel", [7, 8])
+def test_vector_filter_scan_fallback_on_dense_ties(kernel):
+    """Filter scan: when more than 32 rows sit within the error margin of the k-th best approximate score the candidate set does not
+    fit the list; those queries must be re-run by the exact fallback scan on the device (vec_refine.cu) and still return the exact top-k
+    under the canonical tie rule.  Corpus: 60 identical copies and 60 near-copies (1e-4 noise) of two base vectors among 30k others."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    n, dims = 30000, 96
+    rng = np.random.default_rng(77)
+    rows = synth.gen_vectors(n, dims, 5001, "cpu").numpy()
+    v1, v2 = rows[11].copy(), rows[12].copy()
+    dup = rng.choice(np.arange(100, n), size=120, replace=False)
+    rows[dup[:60]] = v1
+    rows[dup[60:]] = v2 + 1e-4 * rng.normal(size=(60, dims)).astype(np.float32)
+    qs = synth.gen_vectors(140, dims, 5002, "cpu").numpy()
+    qs[0] = v1 + 0.01 * qs[0]          # top = the 61 identical rows: ties broken by doc id
+    qs[1] = v2 + 0.01 * qs[1]          # top = 61 near-identical rows: exact f32 order decides
+    ix = Index(0, vector_dims=dims, vector_similarity=VectorSimilarity.Cosine, vector_kernel=kernel)
+    ix.add_vectors(rows)
+    nrows = np.stack([O.normalize(r) for r in rows])
+    for k in (10, 16):
+        got = ix.search_vector_batch(qs, k)
+        st = ix.last_stats()
+        assert st["filter_fallbacks"] >= 2, st
+        for i in (0, 1, 2, 70, 139):
+            _check_vec(got[i], O.search_vector(nrows, O.normalize(qs[i]), k, O.SIM_COSINE))
+        ident = sorted([11] + dup[:60].tolist())[:k]
+        assert [d for d, _ in got[0]] == ident
+    # a deleted duplicate never comes back through the fallback either
+    ix.set_deleted([ident[0], ident[3]])
+    got = ix.search_vector_batch(qs[:2], 10)
+    want = [d for d in sorted([11] + dup[:60].tolist()) if d not in (ident[0], ident[3])][:10]
+    assert [d for d, _ in got[0]] == want
     ix.close()

@@ -122,3 +122,43 @@ def test_group_maximum_threshold_is_a_valid_lower_bound():
             if n_groups >= 64 * k // 10:
                 assert rank <= 2 * k + 4
         # fewer groups than k: kth_from_groupmax returns "no threshold" (0), nothing to check
+
+
+def test_filter_scan_margin_bounds_the_fp16_error():
+    """Filter vector scan (vec_scan_tc.cu PREC_F16F + vec_refine.cu): with h() = round-to-fp16 of the power-of-two-scaled vectors,
+    |a.b - h(a).h(b)| <= E_a |b| + H_a |b - h(b)| with the row maxima E_a = max|a - h(a)|, H_a = max|h(a)|; hence every exact top-k row has
+    an approximate score >= (k-th best approximate) - 2 eps.  The kernel's f32 arithmetic restated in numpy."""
+    rng = np.random.default_rng(21)
+    f32 = np.float32
+    for n, d, norm in ((4000, 768, True), (3000, 100, False), (2000, 32, False)):
+        a = rng.normal(size=(n, d)).astype(np.float32) * (1.0 if norm else rng.uniform(0.1, 30.0, size=(n, 1)).astype(np.float32))
+        if norm:
+            a /= np.linalg.norm(a, axis=1, keepdims=True).astype(np.float32)
+        b = rng.normal(size=(24, d)).astype(np.float32)
+        b[3] = a[n // 2] + 0.05 * b[3]
+        if norm:
+            b /= np.linalg.norm(b, axis=1, keepdims=True).astype(np.float32)
+        sa = f32(256.0) if norm else f32(2.0 ** (7 - int(np.floor(np.log2(np.abs(a[:1500]).max())))))   # Dot: from the first level
+        h = lambda x: x.astype(np.float16).astype(np.float32)
+        a_s = a * sa
+        ah = h(a_s)
+        assert np.isfinite(ah).all()
+        Ea = f32(np.sqrt(((a_s - ah).astype(np.float64) ** 2).sum(1)).max()) * f32(1.00001)
+        Ha = f32(np.sqrt((ah.astype(np.float64) ** 2).sum(1)).max()) * f32(1.00001)
+        for j in range(b.shape[0]):
+            sb = f32(2.0 ** (7 - int(np.floor(np.log2(np.abs(b[j]).max())))))
+            b_s = b[j] * sb
+            bh = h(b_s)
+            exact = a_s.astype(np.float64) @ b_s.astype(np.float64)
+            approx = (ah @ bh).astype(np.float64)                        # f32 accumulation like the tensor core (order differs: covered by the slack)
+            nb = f32(np.linalg.norm(b_s)) * f32(1.00001); eb = f32(np.linalg.norm(b_s - bh)) * f32(1.00001)
+            eps = (Ea * nb + Ha * eb + f32(d) * f32(2.0 ** -22) * Ha * nb) * f32(1.001)
+            err = np.abs(exact - approx).max()
+            assert err <= eps, (n, d, j, err, eps)
+            for k in (1, 10, 16):
+                kth = np.sort(approx)[::-1][k - 1]
+                cand = set(np.nonzero(approx >= kth - 2.0 * float(eps))[0].tolist())
+                top = set(np.argsort(-exact, kind="stable")[:k].tolist())
+                assert top <= cand
+                if norm and d == 768:
+                    assert len(cand) <= k + 6, (k, len(cand))          # the bound is not wasteful: the candidate set fits the 32-entry list

@@ -173,3 +173,27 @@ def test_int8_reference_generators(golden):
     assert O.lib().orc_dot_i8(codes.ctypes.data, codes.ctypes.data, 128) == g["dot_codes_self"]
     # a unit vector quantises to a self-product close to 127^2
     assert abs(g["dot_codes_self"] - 127 * 127) < 200
+
+
+def test_oracle_ivf_probe_semantics():
+    """oracle.search_vector_ivf (vector.rs:1300-1467): probing every cluster equals the exhaustive scan; Nprobe(1) scans exactly the cluster
+    of the best medoid; a cluster threshold above every medoid score selects nothing; observed = vectors of the selected clusters."""
+    from helpers_ivf import clustered_levels
+    levels = clustered_levels(16, [(300, 5), (50, 1)], seed=3)
+    olevels = [(lid, rows, None, counts) for lid, rows, counts in levels]
+    allrows = np.concatenate([lv[1] for lv in levels])
+    ids = np.concatenate([np.arange(len(lv[1]), dtype=np.uint32) | np.uint32(lv[0] << 16) for lv in levels])
+    q = levels[0][1][120] + 0.05
+    full = O.search_vector(allrows, q, 10, O.SIM_DOT, doc_ids=ids)
+    got, obs = O.search_vector_ivf(olevels, q, 10, O.SIM_DOT, 1, 1000)
+    assert got == full and obs == 350
+    assert O.search_vector_ivf(olevels, q, 10, O.SIM_DOT, 0) == (full, 350)
+    got1, obs1 = O.search_vector_ivf(olevels, q, 10, O.SIM_DOT, 1, 1)
+    counts = [int(c) for c in levels[0][2]]
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    best = int(np.argmax([float(np.float32(levels[0][1][s] @ q)) for s in starts]))
+    assert obs1 == counts[best] + 50                       # the best cluster of level 0 + the single cluster of level 1
+    lo, hi = (levels[0][0] << 16) + int(starts[best]), (levels[0][0] << 16) + int(starts[best]) + counts[best]
+    assert all(lo <= d < hi or (d >> 16) == levels[1][0] for d, _ in got1)
+    assert O.search_vector_ivf(olevels, q, 10, O.SIM_DOT, 2, 0, 1.0e6) == ([], 0)
+    assert float(O.ivf_premap_threshold(0.5, O.SIM_DOT)) == 0.0 and float(O.ivf_premap_threshold(3.0, O.SIM_EUCLIDEAN)) == -3.0
