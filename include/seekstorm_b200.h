@@ -104,12 +104,12 @@ typedef struct {
     uint32_t level_id;                /* block id; doc_id = level_id<<16 | local                         */
     uint32_t n_docs;                  /* <= 65536                                                         */
     uint32_t n_terms;
-    uint32_t reserved;
+    uint32_t n_fields;                /* indexed fields: 0 / 1 = one field; F > 1 needs ssb_lexical_set_field_boosts(ix, F, ..) first  */
     const uint64_t* term_keys;        /* [n_terms] 64-bit term hash (reference key_hash), any order       */
     const uint32_t* posting_offsets;  /* [n_terms+1]                                                      */
     const uint16_t* doc_ids;          /* [n_postings] ascending within a term                            */
-    const uint16_t* tfs;              /* [n_postings]                                                     */
-    const uint8_t*  doc_len_bytes;    /* [n_docs]                                                         */
+    const uint16_t* tfs;              /* [n_postings]; F fields: [n_postings][F], 0 = the term does not occur in that field           */
+    const uint8_t*  doc_len_bytes;    /* [n_docs];     F fields: [F][n_docs] (document_length_compressed_array[field], index.rs:770-776) */
 } ssb_level_desc;
 
 /* A batch of lexical queries, already tokenised by the host (tokenizer.rs is out of scope): unique terms
@@ -138,6 +138,12 @@ int32_t ssb_lexical_add_level(ssb_index* ix, const ssb_level_desc* level);
 /* n_docs = indexed_doc_count, len_sum_normalized = positions_sum_normalized (commit.rs:318-319) of the
  * WHOLE shard (all GPUs' levels).  Builds the dictionary, bm25_component_cache (commit.rs:321-325),
  * per-(term,block) block-max (index.rs:2938-3049) and the bitmap containers for dense lists. */
+/* Several indexed fields (BM25F, get_bm25f_multiterm_multifield add_result.rs:1171-1426): n_fields <= 4 and the per-field boosts
+ * (indexed_schema_vec[f].boost; NULL = 1.0) — before the first ssb_lexical_add_level.  Score of a doc = sum over query terms (query
+ * order) and over the fields the term occurs in (ascending) of boost_f * idf_t * tf_tf*(K+1)/(tf_tf + cache[len_byte_f(doc)]),
+ * accumulated left to right like the reference.  Pruning bounds use an upper bound of the boost-weighted per-posting sum; such an
+ * index is searched by the general (one term per lane) kernel. */
+int32_t ssb_lexical_set_field_boosts(ssb_index* ix, uint32_t n_fields, const float* boosts);
 int32_t ssb_lexical_commit(ssb_index* ix, uint64_t n_docs, uint64_t len_sum_normalized);
 /* dictionary export / global document-frequency override (multi-GPU block-range sharding: idf uses the
  * global df, search.rs:3225).  keys/dfs are host pointers. */

@@ -36,15 +36,22 @@ enum class QueryType : uint32_t { Union = SSB_QUERY_UNION, Intersection = SSB_QU
 enum class ResultType : uint32_t { Count = SSB_RESULT_COUNT, Topk = SSB_RESULT_TOPK, TopkCount = SSB_RESULT_TOPKCOUNT };
 enum class VectorSimilarity : uint32_t { Dot = SSB_SIM_DOT, Cosine = SSB_SIM_COSINE, Euclidean = SSB_SIM_EUCLIDEAN };
 enum class Quantization : uint32_t { None = SSB_QUANT_NONE, ScalarQuantizationI8 = SSB_QUANT_SCALAR_I8 };   // vector.rs:230-240
-enum class AnnMode { All };   // exhaustive search only
+// AnnMode (vector_similarity.rs:43-66): which IVF clusters of each level are searched (vector.rs:1300-1392)
+struct AnnMode {
+    uint32_t kind = SSB_ANN_ALL; uint32_t n_probe = 0; float threshold = 0.f;
+    static AnnMode All() { return {}; }
+    static AnnMode Nprobe(uint32_t n) { return {SSB_ANN_NPROBE, n, 0.f}; }
+    static AnnMode Similaritythreshold(float t) { return {SSB_ANN_SIMILARITY_THRESHOLD, 0, t}; }
+    static AnnMode NprobeSimilaritythreshold(uint32_t n, float t) { return {SSB_ANN_NPROBE_SIMILARITY_THRESHOLD, n, t}; }
+};
 
 struct SearchMode {
     enum Kind { Lexical, Vector, Hybrid } kind = Lexical;
     std::optional<float> similarity_threshold;
-    AnnMode ann_mode = AnnMode::All;
-    static SearchMode lexical() { return {Lexical, std::nullopt, AnnMode::All}; }
-    static SearchMode vector(std::optional<float> t = std::nullopt) { return {Vector, t, AnnMode::All}; }
-    static SearchMode hybrid(std::optional<float> t = std::nullopt) { return {Hybrid, t, AnnMode::All}; }
+    AnnMode ann_mode = AnnMode::All();
+    static SearchMode lexical() { return {Lexical, std::nullopt, AnnMode::All()}; }
+    static SearchMode vector(std::optional<float> t = std::nullopt, AnnMode a = AnnMode::All()) { return {Vector, t, a}; }
+    static SearchMode hybrid(std::optional<float> t = std::nullopt) { return {Hybrid, t, AnnMode::All()}; }
 };
 
 struct Result { uint64_t doc_id; float score; };
@@ -156,17 +163,16 @@ public:
             const uint32_t k = static_cast<uint32_t>(heap ? heap : 1);
             vec.resize(k);
             uint32_t n = 0;
-            check(ssb_search_vector(h_, query_vector->data(), 1, k, vec.data(), &n));
+            // search_vector_shard with all of its arguments (vector.rs:1105-1115): threshold pre-map, AnnMode, observed count behind the ABI
+            ssb_vec_query vq{};
+            vq.queries = query_vector->data(); vq.n_queries = 1; vq.k = k; vq.query_format = SSB_QFMT_F32;
+            vq.has_threshold = search_mode.similarity_threshold ? 1u : 0u;
+            vq.similarity_threshold = search_mode.similarity_threshold ? *search_mode.similarity_threshold : 0.f;
+            vq.ann_mode = search_mode.ann_mode.kind; vq.n_probe = search_mode.ann_mode.n_probe; vq.cluster_threshold = search_mode.ann_mode.threshold;
+            uint64_t observed = 0;
+            check(ssb_search_vector_ex(h_, &vq, vec.data(), &n, nullptr, &observed));
             vec.resize(n < heap ? n : heap);
-            if (search_mode.similarity_threshold) {
-                // TopK::new threshold pre-map (vector.rs:388-399): (2t-1)*16129 for Dot/Cosine, -t for Euclidean
-                const float t = *search_mode.similarity_threshold;
-                const float cut = sim_ == VectorSimilarity::Euclidean ? -t : ((t * 2.0f) - 1.0f) * 16129.0f;
-                std::vector<ssb_hit> kept;
-                for (auto& h : vec) if (h.score >= cut) kept.push_back(h);
-                vec.swap(kept);
-            }
-            ro.observed_vector_count = vector_count();
+            ro.observed_vector_count = static_cast<size_t>(observed);
         }
         std::vector<ssb_hit> fused;
         if (search_mode.kind == SearchMode::Lexical) { fused = lex; ro.result_count_total = total; }

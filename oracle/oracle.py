@@ -110,6 +110,12 @@ class OracleIndex:
             lib().orc_index_free(self._h)
             self._h = None
 
+    def set_fields(self, boosts):
+        """several indexed fields (before the first level): levels then carry tfs [n_postings, n_fields], doc_len_bytes [n_fields, n_docs]"""
+        b = np.ascontiguousarray(np.asarray(boosts, dtype=np.float32))
+        lib().orc_index_set_fields.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        assert lib().orc_index_set_fields(self._h, len(b), _ptr(b)) == 0
+
     def add_level(self, lv: dict):
         keep = [np.ascontiguousarray(lv["term_keys"], dtype=np.uint64),
                 np.ascontiguousarray(lv["posting_offsets"], dtype=np.uint32),

@@ -82,10 +82,22 @@ struct orc_index {
     uint64_t n_docs, len_sum;
     float cache[256];
     int committed;
+    uint32_t n_fields;            /* indexed fields (0 / 1 = single field) */
+    float boost[ORC_MAX_FIELDS];  /* indexed_schema_vec[f].boost (add_result.rs:1258) */
     uint64_t* deleted; uint64_t n_deleted;   /* shard.delete_hashset, sorted (add_result.rs:3435) */
 };
 
 orc_index* orc_index_new(void) { return (orc_index*)calloc(1, sizeof(orc_index)); }
+
+/* several indexed fields (before the first level): every level then carries tfs[n_postings][n_fields] (0 = the term does not occur in
+ * that field) and doc_len_bytes[n_fields][n_docs]; scores follow get_bm25f_multiterm_multifield (add_result.rs:1226-1262) */
+int orc_index_set_fields(orc_index* ix, uint32_t n_fields, const float* boosts) {
+    if (!ix || ix->n_levels || n_fields == 0 || n_fields > ORC_MAX_FIELDS) return -1;
+    ix->n_fields = n_fields;
+    for (uint32_t f = 0; f < n_fields; f++) ix->boost[f] = boosts ? boosts[f] : 1.0f;
+    return 0;
+}
+static inline uint32_t nf_of(const orc_index* ix) { return ix->n_fields > 1 ? ix->n_fields : 1; }
 
 void orc_index_free(orc_index* ix) {
     if (!ix) return;
@@ -132,8 +144,8 @@ int orc_index_add_level(orc_index* ix, const orc_level* d) {
     l->term_keys = (uint64_t*)dup_mem(d->term_keys, (size_t)d->n_terms * 8);
     l->posting_offsets = (uint32_t*)dup_mem(d->posting_offsets, ((size_t)d->n_terms + 1) * 4);
     l->doc_ids = (uint16_t*)dup_mem(d->doc_ids, (size_t)np * 2);
-    l->tfs = (uint16_t*)dup_mem(d->tfs, (size_t)np * 2);
-    l->doc_len_bytes = (uint8_t*)dup_mem(d->doc_len_bytes, d->n_docs);
+    l->tfs = (uint16_t*)dup_mem(d->tfs, (size_t)np * 2 * nf_of(ix));
+    l->doc_len_bytes = (uint8_t*)dup_mem(d->doc_len_bytes, (size_t)d->n_docs * nf_of(ix));
     ix->committed = 0;
     return 0;
 }
@@ -167,7 +179,7 @@ int orc_index_commit(orc_index* ix, uint64_t n_docs, uint64_t len_sum) {
         for (uint32_t t = 0; t < l->n_terms; t++) {
             ix->dict[p].key = l->term_keys[t]; ix->dict[p].level = i; ix->dict[p].idx = t; p++;
             float m = 0.0f;
-            for (uint32_t j = l->posting_offsets[t]; j < l->posting_offsets[t + 1]; j++) {
+            if (nf_of(ix) == 1) for (uint32_t j = l->posting_offsets[t]; j < l->posting_offsets[t + 1]; j++) {
                 float c = comp_of(ix, l->tfs[j], l->doc_len_bytes[l->doc_ids[j]]);
                 if (c > m) m = c;
             }
@@ -293,10 +305,22 @@ int orc_search_lexical_not(const orc_index* ix, const uint64_t* keys, uint32_t n
             int64_t e = term_in_level(ix, &live[t], li);
             if (e < 0) continue;
             uint32_t ti = ix->dict[e].idx;
+            const uint32_t nf = nf_of(ix);
             for (uint32_t j = l->posting_offsets[ti]; j < l->posting_offsets[ti + 1]; j++) {
                 uint16_t d = l->doc_ids[j];
-                float comp = ix->cache[l->doc_len_bytes[d]];
-                acc[d] += orc_bm25_term(live[t].idf, l->tfs[j], comp);
+                if (nf == 1) {
+                    float comp = ix->cache[l->doc_len_bytes[d]];
+                    acc[d] += orc_bm25_term(live[t].idf, l->tfs[j], comp);
+                } else {
+                    /* get_bm25f_multiterm_multifield, NgramType::SingleTerm (add_result.rs:1232-1262): for every field the term occurs in,
+                     * bm25f += weight * idf * ((tf * (K + 1) / (tf + cache[len_byte of THAT field])) + SIGMA), fields in ascending order */
+                    for (uint32_t f = 0; f < nf; f++) {
+                        uint32_t tfu = l->tfs[(size_t)j * nf + f];
+                        if (!tfu) continue;
+                        float tf = (float)tfu, comp = ix->cache[l->doc_len_bytes[(size_t)f * l->n_docs + d]];
+                        acc[d] += ix->boost[f] * live[t].idf * ((tf * (ORC_K + 1.0f) / (tf + comp)) + ORC_SIGMA);
+                    }
+                }
                 cnt[d]++;
             }
         }
@@ -553,6 +577,7 @@ static void or_maxscore(orctx* c) {
 int orc_search_lexical_pruned(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, uint32_t query_type,
                               uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
                               uint64_t* count_total) {
+    if (ix && ix->n_fields > 1) return -2;   /* the reference-shaped pruned walk is restated for one indexed field only */
     if (!ix || !ix->committed || n_terms > ORC_MAX_TERMS) return -1;
     if (n_hits) *n_hits = 0;
     if (count_total) *count_total = 0;

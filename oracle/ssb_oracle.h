@@ -59,7 +59,11 @@ float orc_idf(uint64_t n_docs, uint32_t df);
 float orc_bm25_term(float idf, uint32_t tf, float comp);
 
 /* ---- index ---- */
+#define ORC_MAX_FIELDS 4
 orc_index* orc_index_new(void);
+/* several indexed fields with boosts (before the first level): tfs become [n_postings][n_fields], doc_len_bytes [n_fields][n_docs];
+ * scoring = get_bm25f_multiterm_multifield (add_result.rs:1226-1262) */
+int        orc_index_set_fields(orc_index*, uint32_t n_fields, const float* boosts);
 void       orc_index_free(orc_index*);
 int        orc_index_add_level(orc_index*, const orc_level*);   /* copies everything */
 /* global statistics (1-shard semantics); finalises the dictionary */

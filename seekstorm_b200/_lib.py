@@ -48,7 +48,7 @@ class SsbIndexBinParams(C.Structure):
 
 
 class SsbLevelDesc(C.Structure):
-    _fields_ = [("level_id", C.c_uint32), ("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("level_id", C.c_uint32), ("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("n_fields", C.c_uint32),
                 ("term_keys", C.c_void_p), ("posting_offsets", C.c_void_p), ("doc_ids", C.c_void_p),
                 ("tfs", C.c_void_p), ("doc_len_bytes", C.c_void_p)]
 
@@ -68,7 +68,7 @@ class SsbStats(C.Structure):
 # every symbol include/seekstorm_b200.h declares
 EXPORTS = [
     "ssb_abi_version", "ssb_last_error", "ssb_create", "ssb_destroy", "ssb_lexical_add_level",
-    "ssb_vector_add_level_clustered", "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
+    "ssb_vector_add_level_clustered", "ssb_lexical_set_field_boosts", "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
     "ssb_load_index_bin", "ssb_load_vector_bin", "ssb_index_bin_inspect", "ssb_set_deleted", "ssb_vector_add_level", "ssb_vector_count", "ssb_vector_reserve", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_vector_ex", "ssb_search_hybrid",
     "ssb_rrf_fuse", "ssb_comm_unique_id", "ssb_comm_init", "ssb_comm_attach", "ssb_comm_destroy", "ssb_lexical_sync_df",
     "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
@@ -98,6 +98,7 @@ def lib():
         "ssb_destroy": [vp],
         "ssb_lexical_add_level": [vp, C.POINTER(SsbLevelDesc)],
         "ssb_lexical_commit": [vp, u64, u64],
+        "ssb_lexical_set_field_boosts": [vp, u32, vp],
         "ssb_lexical_dict_size": [vp, C.POINTER(u64)],
         "ssb_lexical_dict_export": [vp, vp, vp, u64],
         "ssb_lexical_set_global_df": [vp, vp, vp, u64],

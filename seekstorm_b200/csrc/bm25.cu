@@ -74,23 +74,28 @@ __global__ void validate_keys_sorted_unique(const uint64_t* __restrict__ sorted_
 }
 // posting i belongs to the term whose offset range contains it (binary search over posting_offsets)
 __global__ void validate_level(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs, const uint32_t* __restrict__ offs,
-                               uint32_t n_terms, uint32_t n, uint32_t n_docs, uint32_t* bad) {
+                               uint32_t n_terms, uint32_t n, uint32_t n_docs, uint32_t* bad, uint32_t nf) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t lo = 0, hi = n_terms;                     // term t with offs[t] <= i < offs[t+1]
     while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (offs[m + 1] <= i) lo = m + 1; else hi = m; }
-    bool ok = lo < n_terms && ids[i] < n_docs && tfs[i] >= 1;
+    uint32_t tfmax = 0;
+    for (uint32_t f = 0; f < nf; f++) tfmax = max(tfmax, (uint32_t)tfs[(size_t)i * nf + f]);   // the term occurs in at least one field
+    bool ok = lo < n_terms && ids[i] < n_docs && tfmax >= 1;
     if (ok && i > offs[lo] && ids[i] <= ids[i - 1]) ok = false;
     if (!ok) atomicAdd(bad, 1u);
 }
 
 __global__ void build_postings(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs, const uint8_t* __restrict__ len_bytes,
-                               uint32_t* __restrict__ post, uint32_t* __restrict__ pay, uint32_t n) {
+                               uint32_t* __restrict__ post, uint32_t* __restrict__ pay, uint32_t n,
+                               uint32_t nf, uint32_t n_docs, uint32_t* __restrict__ payf /*several fields: [n][nf]*/) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t id = ids[i];
     post[i] = id;                                                 // bound16 is filled by fill_bounds at commit
-    pay[i] = (uint32_t)tfs[i] | ((uint32_t)len_bytes[id] << 16);  // tf16 | len8<<16
+    pay[i] = (uint32_t)tfs[(size_t)i * nf] | ((uint32_t)len_bytes[id] << 16);  // tf16 | len8<<16 (field 0)
+    if (nf > 1)
+        for (uint32_t f = 0; f < nf; f++) payf[(size_t)i * nf + f] = (uint32_t)tfs[(size_t)i * nf + f] | ((uint32_t)len_bytes[(size_t)f * n_docs + id] << 16);
 }
 
 // query-independent posting score component: tf*(K+1)/(tf+cache[len])   (add_result.rs:1450)
@@ -102,7 +107,20 @@ __device__ __forceinline__ float comp_of(const LexView& v, uint32_t payload) {
 __global__ void fill_bounds(LexView v, uint32_t* __restrict__ post, float* __restrict__ comp, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float c = comp_of(v, v.pay[i]);
+    float c;
+    if (v.n_fields > 1) {
+        // several fields: exact per-field components for the scorer; comp[] / the fp16 bound carry an upper bound of the posting's
+        // boost-weighted sum.  The exact score adds up to 4 products (boost*idf)*comp_f per term while a bound adds ONE idf*comp per term:
+        // the rounding of the two sums is not comparable term by term, 2^-16 of slack covers <= 128 + 32 f32 additions with room.
+        float b = 0.f;
+        for (uint32_t f = 0; f < v.n_fields; f++) {
+            const uint32_t pl = v.payf[i * v.n_fields + f];
+            const float cf = (pl & 0xFFFFu) ? comp_of(v, pl) : 0.f;
+            const_cast<float*>(v.compf)[i * v.n_fields + f] = cf;
+            b = __fadd_ru(b, __fmul_ru(v.boost[f], cf));
+        }
+        c = __fmul_ru(b, 1.0000153f);
+    } else c = comp_of(v, v.pay[i]);
     comp[i] = c;                                                  // the IEEE divide + cache lookup happen once, here
     const __half h = __float2half_ru(c);                          // rounded UP: idf*h >= idf*comp
     post[i] = (post[i] & 0xFFFFu) | ((uint32_t)__half_as_ushort(h) << 16);
@@ -323,7 +341,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         for (uint32_t s = 0; s < FAST_T; s++) {
             LvSlot sl; sl.off_lo = 0; sl.offhi_cnt = 0; sl.bmi = NONE; sl.ub = 0.f;
             float idf = 0.f;
-            if (s < nl && nl <= FAST_T) {
+            if (s < nl && nl <= v.fast_t) {
                 const QTerm qt = pl.t[s];
                 idf = qt.idf;
                 const uint32_t er = ent[s * nlv + lv];
@@ -337,7 +355,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             }
             r.t[s] = sl; r.idf[s] = idf;
         }
-        if (nl <= FAST_T) {
+        if (nl <= v.fast_t) {
             const uint32_t cs[4] = {c0, c1, c2, c3}; const float us[4] = {u0, u1, u2, u3};
             uint32_t np = 0, rank[4], crank[4];
 #pragma unroll
@@ -403,7 +421,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         pl.n_items = ni; pl.n_recs = nv;
         plans[q] = pl;
         atomicMax(&ctr[1], ni);
-        if (pl.n_live > FAST_T) atomicOr(&ctr[4], 1u);
+        if (pl.n_live > v.fast_t) atomicOr(&ctr[4], 1u);
         if (pl.n_not) atomicOr(&ctr[5], 1u);
     }
 }
@@ -441,6 +459,17 @@ __device__ __forceinline__ bool present_in(const LexView& v, uint32_t cnt, uint6
 __device__ __forceinline__ float term_score(const LexView& v, float idf, uint64_t pos) {
     // idf * ((tf*(K+1)/(tf+comp)) + SIGMA), SIGMA = 0 (x + 0.0 == x); the bracket is precomputed at commit (fill_bounds)
     return __fmul_rn(idf, __ldg(&v.comp[pos]));
+}
+// bm25f += the term's contribution, generic path.  One field: bm25f += idf * comp (add_result.rs:1450).  Several fields
+// (get_bm25f_multiterm_multifield, add_result.rs:1232-1262): for each field the term occurs in, ascending, bm25f += weight * idf * comp_f,
+// evaluated left to right and accumulated straight into the running sum.
+__device__ __forceinline__ float acc_term(const LexView& v, float score, float idf, uint64_t pos) {
+    if (v.n_fields <= 1) return __fadd_rn(score, term_score(v, idf, pos));
+    for (uint32_t f = 0; f < v.n_fields; f++) {
+        const float cf = __ldg(&v.compf[pos * v.n_fields + f]);
+        if (cf != 0.f) score = __fadd_rn(score, __fmul_rn(__fmul_rn(v.boost[f], idf), cf));
+    }
+    return score;
 }
 
 // shard.delete_hashset.contains(docid) (add_result.rs:3435): one table lookup + one bitmap word, only for exact-score survivors
@@ -986,7 +1015,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                 uint32_t rank = p; bool found = true;
                 if ((int)t != drv) { found = ok && probe(v, tc, to, tb, d, rank); st_probes += ok ? 1 : 0; }
                 ok = ok && found;
-                if (ok && c.scoring) score = __fadd_rn(score, term_score(v, ti, to + rank));
+                if (ok && c.scoring) score = acc_term(v, score, ti, to + rank);
             }
             matches += __popc(__ballot_sync(FULL, ok));
             if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
@@ -1025,12 +1054,12 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                     const uint32_t tc = __shfl_sync(FULL, tr.cnt, t); const uint64_t to = shfl64(tr.off, t);
                     const uint32_t tb = __shfl_sync(FULL, tr.bmi, t); const float ti = __shfl_sync(FULL, tr.idf, t);
                     const uint32_t trk = __shfl_sync(FULL, rk, t);
-                    if ((int)t == drv) { if (active) score = __fadd_rn(score, term_score(v, didf, doff + pp)); continue; }
+                    if ((int)t == drv) { if (active) score = acc_term(v, score, didf, doff + pp); continue; }
                     if (tc == 0 || !active || dup) continue;
                     uint32_t rank; st_probes++;
                     if (probe(v, tc, to, tb, d, rank)) {
                         if (trk < p) dup = true;
-                        else score = __fadd_rn(score, term_score(v, ti, to + rank));
+                        else score = acc_term(v, score, ti, to + rank);
                     }
                 }
                 insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
@@ -1082,7 +1111,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
 constexpr uint32_t ITEM_CHUNK = 8;
 template <bool FAST, class SM>
 __device__ __forceinline__ bool next_item(SM& it, uint32_t* counter, uint64_t total, uint32_t nq, const QueryPlan* __restrict__ plans,
-                                          int lane, uint32_t& j, uint32_t& q) {
+                                          int lane, uint32_t& j, uint32_t& q, const uint32_t fast_t = FAST_T) {
     unsigned mask = it.it_mask; uint32_t base = it.it_base;      // warp-private shared memory: keeps two registers out of the hot loops
     __syncwarp();
     while (!mask) {
@@ -1095,7 +1124,7 @@ __device__ __forceinline__ bool next_item(SM& it, uint32_t* counter, uint64_t to
         if (ok) {
             const uint32_t jj = (uint32_t)(i / nq), qq = (uint32_t)(i - (uint64_t)jj * nq);
             const QueryPlan* pl = &plans[qq];
-            ok = jj < __ldg(&pl->n_items) && ((__ldg(&pl->n_live) <= FAST_T) == FAST);
+            ok = jj < __ldg(&pl->n_items) && ((__ldg(&pl->n_live) <= fast_t) == FAST);
         }
         mask = __ballot_sync(FULL, ok); base = b;
     }
@@ -1143,6 +1172,7 @@ __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const 
                                                  const uint16_t* __restrict__ item_start, uint32_t nq, uint32_t k, uint32_t* ctr, uint64_t* theta,
                                                  int* lock, uint64_t* glist, LexStats* stats, const uint64_t* __restrict__ ceil_keys) {
     __shared__ __align__(16) WarpSm wsm[8];
+    if (v.fast_t == 0) return;                           // several indexed fields: every query takes the generic path
     WarpSm& w = wsm[(threadIdx.x >> 5) & 7];
     const int lane = threadIdx.x & 31;
     const uint64_t total = (uint64_t)(*(volatile uint32_t*)&ctr[1]) * nq;
@@ -1181,6 +1211,7 @@ __global__ void __launch_bounds__(128, 6) lex_count(LexView v, const QueryPlan* 
                                                 const uint16_t* __restrict__ item_start, uint32_t nq, uint32_t query_type, uint32_t* ctr,
                                                 uint64_t* count, LexStats* stats) {
     __shared__ __align__(16) CountSm csm[4];
+    if (v.fast_t == 0) return;                           // several indexed fields: the generic path counts as well
     CountSm& w = csm[(threadIdx.x >> 5) & 3];
     const int lane = threadIdx.x & 31;
     const uint64_t total = (uint64_t)(*(volatile uint32_t*)&ctr[1]) * nq;
@@ -1225,7 +1256,7 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
     uint32_t j, q;
     if (lane == 0) { w.it_mask = 0; w.it_base = 0; }
     __syncwarp();
-    while (next_item<false>(w, &ctr[3], total, nq, plans, lane, j, q)) {
+    while (next_item<false>(w, &ctr[3], total, nq, plans, lane, j, q, v.fast_t)) {
         const QueryPlan* pl = &plans[q];
         const uint32_t n_live = __ldg(&pl->n_live);
         const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
@@ -1381,7 +1412,18 @@ static cudaError_t to_device(void* dst, const void* src, size_t n, cudaStream_t 
     return cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, st);
 }
 
+int32_t LexIndex::set_fields(uint32_t n_fields, const float* boosts) {
+    if (n_fields == 0 || n_fields > 4) { set_error("set_field_boosts: 1..4 indexed fields"); return SSB_E_UNSUPPORTED; }
+    if (!levels_.empty()) { set_error("set_field_boosts: call it before the first level is added"); return SSB_E_STATE; }
+    n_fields_ = n_fields;
+    for (uint32_t f = 0; f < 4; f++) boosts_[f] = (boosts && f < n_fields) ? boosts[f] : 1.f;
+    for (uint32_t f = 0; f < n_fields; f++) if (!(boosts_[f] >= 0.f) || boosts_[f] > 1.0e6f) { set_error("set_field_boosts: boosts must be in [0, 1e6]"); return SSB_E_INVALID; }
+    return SSB_OK;
+}
+
 int32_t LexIndex::add_level(const ssb_level_desc* d) {
+    const uint32_t nf = n_fields_;
+    if (d && (d->n_fields > 1 ? d->n_fields : 1u) != nf) { set_error("add_level: the level carries %u field(s), the index %u", d->n_fields > 1 ? d->n_fields : 1u, nf); return SSB_E_INVALID; }
     if (!d || d->n_docs == 0 || d->n_docs > 65536) { set_error("add_level: n_docs must be in 1..65536"); return SSB_E_INVALID; }
     if (d->level_id >= 65536) { set_error("add_level: level_id must be < 65536 (doc id = level_id << 16 | local)"); return SSB_E_INVALID; }
     if (d->n_terms && (!d->term_keys || !d->posting_offsets)) { set_error("add_level: null term_keys / posting_offsets"); return SSB_E_INVALID; }
@@ -1418,10 +1460,10 @@ int32_t LexIndex::add_level(const ssb_level_desc* d) {
         if (is_device_ptr(d->doc_ids)) d_ids = d->doc_ids;
         else { SSB_CUDA_TRY(t_ids.alloc(np)); d_ids = t_ids.p; SSB_CUDA_TRY(to_device(t_ids.p, d->doc_ids, (size_t)np * 2, st_)); }
         if (is_device_ptr(d->tfs)) d_tfs = d->tfs;
-        else { SSB_CUDA_TRY(t_tfs.alloc(np)); d_tfs = t_tfs.p; SSB_CUDA_TRY(to_device(t_tfs.p, d->tfs, (size_t)np * 2, st_)); }
+        else { SSB_CUDA_TRY(t_tfs.alloc((size_t)np * nf)); d_tfs = t_tfs.p; SSB_CUDA_TRY(to_device(t_tfs.p, d->tfs, (size_t)np * nf * 2, st_)); }
         if (is_device_ptr(d->doc_len_bytes)) d_len = d->doc_len_bytes;
-        else { SSB_CUDA_TRY(t_len.alloc(d->n_docs)); d_len = t_len.p; SSB_CUDA_TRY(to_device(t_len.p, d->doc_len_bytes, d->n_docs, st_)); }
-        validate_level<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, t_offs.p, d->n_terms, np, d->n_docs, t_bad.p);
+        else { SSB_CUDA_TRY(t_len.alloc((size_t)d->n_docs * nf)); d_len = t_len.p; SSB_CUDA_TRY(to_device(t_len.p, d->doc_len_bytes, (size_t)d->n_docs * nf, st_)); }
+        validate_level<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, t_offs.p, d->n_terms, np, d->n_docs, t_bad.p, nf);
         SSB_CUDA_TRY(cudaGetLastError());
         SSB_CUDA_TRY(cudaMemcpyAsync(&bad, t_bad.p, 4, cudaMemcpyDeviceToHost, st_));
         SSB_CUDA_TRY(cudaStreamSynchronize(st_));
@@ -1432,7 +1474,9 @@ int32_t LexIndex::add_level(const ssb_level_desc* d) {
         // validated: append (n_post_ advances only after the kernels were enqueued without error)
         SSB_TRY(post_.reserve(n_post_ + np + 160, n_post_, st_));     // +160: the 16-byte vector loads of the stream may run past the end
         SSB_TRY(pay_.reserve(n_post_ + np + 160, n_post_, st_));
-        build_postings<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, d_len, post_.p + n_post_, pay_.p + n_post_, np);
+        if (nf > 1) SSB_TRY(payf_.reserve((n_post_ + np) * nf + 16, n_post_ * nf, st_));
+        build_postings<<<(np + 255) / 256, 256, 0, st_>>>(d_ids, d_tfs, d_len, post_.p + n_post_, pay_.p + n_post_, np, nf, d->n_docs,
+                                                          nf > 1 ? payf_.p + n_post_ * nf : nullptr);
         SSB_CUDA_TRY(cudaGetLastError());
         SSB_CUDA_TRY(cudaStreamSynchronize(st_));
     } else {
@@ -1482,6 +1526,8 @@ LexView LexIndex::view() const {
     v.post = post_.p; v.pay = pay_.p; v.comp = comp_.p; v.bm_words = d_bm_words_; v.bm = d_bm_; v.bm_q8 = d_bm_q8_; v.q8_step = Q8_STEP; v.level_ids = d_level_ids_;
     v.n_levels = (uint32_t)levels_.size(); v.cache = d_cache_;
     v.k1p = 1.2f + 1.0f;
+    v.payf = payf_.p; v.compf = compf_.p; v.n_fields = n_fields_; v.fast_t = n_fields_ > 1 ? 0u : FAST_T;
+    for (int f = 0; f < 4; f++) v.boost[f] = boosts_[f];
     if (del_ && del_->n) { v.del_slot = del_->d_slot; v.del_words = del_->d_words; v.del_docs = del_->d_docs; v.n_del = del_->n; }
     return v;
 }
@@ -1512,6 +1558,8 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     if (n_post_) {
         LexView v{};
         v.pay = pay_.p; v.cache = d_cache_; v.k1p = 1.2f + 1.0f;
+        v.n_fields = n_fields_; v.payf = payf_.p; for (int f = 0; f < 4; f++) v.boost[f] = boosts_[f];
+        if (n_fields_ > 1) { SSB_TRY(compf_.reserve(n_post_ * n_fields_ + 16, 0, st_, true)); v.compf = compf_.p; }
         SSB_TRY(comp_.reserve(n_post_ + 160, 0, st_, true));
         fill_bounds<<<(unsigned)((n_post_ + 255) / 256), 256, 0, st_>>>(v, post_.p, comp_.p, n_post_);
         SSB_CUDA_TRY(cudaGetLastError());

@@ -90,6 +90,13 @@ struct LexView {
     uint32_t n_levels;
     const float* cache;           // [256] bm25_component_cache
     float k1p;                    // K + 1
+    // several indexed fields (get_bm25f_multiterm_multifield, add_result.rs:1226-1262): per posting n_fields payloads / exact components;
+    // comp[] / the fp16 bounds then hold an UPPER BOUND of sum_f boost[f] * comp_f and every query takes the generic path (fast_t = 0)
+    const uint32_t* payf;         // [n_postings][n_fields] tf16 | doclen_byte << 16 of field f (tf 0 = term not in that field)
+    const float* compf;           // [n_postings][n_fields] exact component of field f (0 = absent)
+    uint32_t n_fields;            // 1 = single field (payf / compf unused)
+    uint32_t fast_t;              // queries with <= fast_t live terms take the record path (FAST_T, or 0 with several fields)
+    float boost[4];               // indexed_schema_vec[f].boost
     // delete set (shard.delete_hashset, add_result.rs:3435): null = no deleted docs
     const uint32_t* del_slot;     // [65536] level_id -> bitmap slot or 0xFFFFFFFF
     const uint64_t* del_words;    // [n_slots][1024]
@@ -150,6 +157,7 @@ public:
     explicit LexIndex(cudaStream_t st, int n_sms, uint32_t max_batch) : st_(st), n_sms_(n_sms), max_batch_(max_batch) {}
     ~LexIndex();
     int32_t add_level(const ssb_level_desc* d);
+    int32_t set_fields(uint32_t n_fields, const float* boosts);   // before the first level
     int32_t commit(uint64_t n_docs, uint64_t len_sum);
     int32_t dict_size(uint64_t* n) const { *n = n_terms_; return SSB_OK; }
     int32_t dict_export(uint64_t* keys, uint32_t* dfs, uint64_t cap) const;
@@ -177,6 +185,8 @@ private:
     std::vector<LexLevel> levels_;
     DevBuf<uint32_t> post_, pay_;
     DevBuf<float> comp_;
+    uint32_t n_fields_ = 1; float boosts_[4] = {1.f, 1.f, 1.f, 1.f};
+    DevBuf<uint32_t> payf_; DevBuf<float> compf_;   // several indexed fields: [n_post][n_fields]
     uint64_t n_post_ = 0;
     // committed structures
     uint64_t n_docs_ = 0, len_sum_ = 0;

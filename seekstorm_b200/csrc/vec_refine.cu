@@ -1,15 +1,16 @@
-// vec_refine.cu — second half of the FILTER vector scan: exact re-scoring of the candidates the bf16 filter
-// scan (scan_tc<NQ, PREC_BF16F>, vec_scan_tc.cu) kept, and the exact fallback for queries whose candidate set did not fit.
+// vec_refine.cu — second half of the FILTER vector scan: exact re-scoring of the candidates the fp16 filter
+// scan (scan_tc<NQ, PREC_F16F>, vec_scan_tc.cu) kept, and the exact fallback for queries whose candidate set did not fit.
 //
 // Reference semantics: search_vector_shard scores EVERY record with dot_f32 (vector.rs:1397-1467, vector_similarity.rs:1006-1008,
-// 1120-1142) and keeps the k best (TopK, vector.rs:410-497).  The filter scan computes s^ = hi(a).hi(b) for every record instead and
+// 1120-1142) and keeps the k best (TopK, vector.rs:410-497).  The filter scan computes s^ = h(a).h(b) (h = round to fp16) for every record instead and
 // guarantees |s - s^| <= eps_q, so the exact top-k is contained in C = {r : s^_r >= (k-th best s^) - 2 eps_q}.  refine_candidates
 // evaluates the f32 dot product of the query with the <= 32 rows of C from the f32 corpus — the returned scores are plain f32 dot
 // products (closer to the reference's than the 3-product split of the exact tensor-core scan) — and re-sorts under the canonical rule.
 // |C| > 32 cannot be represented in the 32-entry list: it shows as "the 32nd entry is still inside the margin"; those queries are
 // re-run by fallback_scan, a plain f32 scan (one corpus pass per 4 flagged queries), always enqueued and exiting at once when the
-// flag list is empty — no host round trip, so the *_keys entry points stay asynchronous.  Flags are rare by construction: eps_q is
-// ~2.5e-3 for unit vectors, the candidate set of a top-10 query over 1M x 768 Gaussian rows holds ~17 rows.
+// flag list is empty — no host round trip, so the *_keys entry points stay asynchronous.  Flags are rare by construction: 2 eps_q is
+// ~1.2e-3 for unit 768-d vectors (0.03 standard deviations of a random cosine), the candidate set of a top-10 query over 1M x 768
+// Gaussian rows holds 10-12 rows; dense near-ties (many copies of one vector) are what the fallback is for.
 #include "common.cuh"
 #include "vec_scan.h"
 

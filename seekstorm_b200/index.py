@@ -170,10 +170,17 @@ class Index:
             pass
 
     # ------------------------------------------------------------------ load
+    def set_field_boosts(self, boosts):
+        """Several indexed fields (BM25F, add_result.rs:1171-1426): per-field boosts, before the first level.  Levels then carry
+        tfs [n_postings, n_fields] (0 = term not in that field) and doc_len_bytes [n_fields, n_docs]."""
+        b = np.ascontiguousarray(np.asarray(boosts, dtype=np.float32))
+        check(lib().ssb_lexical_set_field_boosts(self._h, len(b), b.ctypes.data))
+        self._n_fields = len(b)
+
     def add_lexical_level(self, level_id: int, n_docs: int, term_keys, posting_offsets, doc_ids, tfs, doc_len_bytes):
         """One committed 64K-doc level in the neutral layout (arrays: numpy on host or torch on the device)."""
         n_terms = int(term_keys.shape[0])
-        d = SsbLevelDesc(level_id, n_docs, n_terms, 0, _addr(term_keys), _addr(posting_offsets), _addr(doc_ids),
+        d = SsbLevelDesc(level_id, n_docs, n_terms, getattr(self, "_n_fields", 1), _addr(term_keys), _addr(posting_offsets), _addr(doc_ids),
                          _addr(tfs), _addr(doc_len_bytes))
         check(lib().ssb_lexical_add_level(self._h, C.byref(d)))
 

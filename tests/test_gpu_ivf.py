@@ -36,7 +36,8 @@ def test_ivf_probe_matches_oracle(sim):
         olevels.append((lid, orows, None, counts))
     rng = np.random.default_rng(5)
     qs = rng.normal(size=(40, dims)).astype(np.float32)
-    qs[:20] = np.concatenate([lv[1][::97][:5] for lv in levels])[:20] + 0.3 * qs[:20]      # queries near real rows: clusters matter
+    allr = np.concatenate([lv[1] for lv in levels])
+    qs[:20] = allr[rng.choice(len(allr), size=20, replace=False)] + 0.3 * qs[:20]          # queries near real rows: clusters matter
     modes = MODES if sim != "euc" else [(1, 3, 0.0), (1, 1000, 0.0), (2, 0, 40.0), (3, 2, 60.0)]   # Euclidean threshold: distance^2 (pre-map -t)
     for kern, nq in ((0, 40), (0, 5), (4, 40), (7, 40), (1, 16)):
         if sim == "euc" and kern in (4, 7):
@@ -71,7 +72,7 @@ def test_ivf_through_vector_bin_and_search_mirror():
     data = refwriter.write_vector_bin([(np.arange(len(rows), dtype=np.uint16), rows, counts) for _, rows, counts in levels])
     ix = Index(0, vector_dims=dims, vector_similarity=VectorSimilarity.Dot)
     assert ix.load_vector_bin(data) == 1300
-    olevels = [(lid, rows, None, counts) for lid, rows, counts in levels]
+    olevels = [(i, rows, None, counts) for i, (_, rows, counts) in enumerate(levels)]      # the file numbers its levels 0, 1, ...
     q = levels[0][1][450] + 0.1
     for am, (mode, n_probe, thr) in ((AnnMode.Nprobe(2), (1, 2, 0.0)), (AnnMode.NprobeSimilaritythreshold(3, 0.5001), (3, 3, 0.5001))):
         ro = ix.search("", q, search_mode=SearchMode.Vector(None, am), length=10)

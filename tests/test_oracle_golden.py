@@ -197,3 +197,33 @@ def test_oracle_ivf_probe_semantics():
     assert all(lo <= d < hi or (d >> 16) == levels[1][0] for d, _ in got1)
     assert O.search_vector_ivf(olevels, q, 10, O.SIM_DOT, 2, 0, 1.0e6) == ([], 0)
     assert float(O.ivf_premap_threshold(0.5, O.SIM_DOT)) == 0.0 and float(O.ivf_premap_threshold(3.0, O.SIM_EUCLIDEAN)) == -3.0
+
+
+def test_oracle_multifield_bm25f_known_answer():
+    """get_bm25f_multiterm_multifield (add_result.rs:1226-1262) by hand: 2 fields with boosts (2, 1), one level of 3 docs, two terms.
+    score(doc) = sum over terms (query order), over the fields the term occurs in (ascending): boost * idf * (tf * 2.2 / (tf + cache[len_byte]))."""
+    f32 = np.float32
+    orc = O.OracleIndex()
+    orc.set_fields([2.0, 1.0])
+    lens = np.array([[3, 5, 9], [12, 20, 7]], dtype=np.uint8)                        # byte4 codes < 24 are the lengths themselves
+    lv = dict(level_id=0, n_docs=3, term_keys=np.array([8, 16], dtype=np.uint64), posting_offsets=np.array([0, 2, 4], dtype=np.uint32),
+              doc_ids=np.array([0, 2, 1, 2], dtype=np.uint16), tfs=np.array([[1, 0], [2, 3], [0, 4], [1, 1]], dtype=np.uint16), doc_len_bytes=lens)
+    orc.add_level(lv)
+    len_sum = int(lens.sum())
+    orc.commit(3, len_sum)
+    cache = O.bm25_cache(3, len_sum)
+    idf = [f32(O.lib().orc_idf(3, 2))] * 2
+
+    def part(boost, idf_t, tf, lb):
+        tf = f32(tf)
+        return f32(f32(f32(boost) * idf_t) * f32(f32(tf * f32(2.2)) / f32(tf + cache[lb])))
+    want2 = f32(0)
+    for x in (part(2, idf[0], 2, 9), part(1, idf[0], 3, 7), part(2, idf[1], 1, 9), part(1, idf[1], 1, 7)):
+        want2 = f32(want2 + x)
+    got, tot = orc.search([8, 16], O.QUERY_UNION, 10, O.RESULT_TOPKCOUNT)
+    assert tot == 3
+    assert dict(got)[2] == float(want2)
+    assert dict(got)[0] == float(f32(f32(0) + part(2, idf[0], 1, 3)))
+    assert dict(got)[1] == float(f32(f32(0) + part(1, idf[1], 4, 20)))
+    got_and, tot_and = orc.search([8, 16], O.QUERY_INTERSECTION, 10, O.RESULT_TOPKCOUNT)
+    assert tot_and == 1 and got_and == [(2, float(want2))]
