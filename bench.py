@@ -250,6 +250,9 @@ NCU = {"scan_ffma": {"traffic_per_pass": 3.0770e9, "source": "profiles/r02_scan_
        # bf16 hi/lo corpus planes: (6.1655 GB read + 58.7 MB written) / 2 passes; 256-query tile: 3.1087 GB + 75.5 MB, one pass
        "scan_tc": {"traffic_per_pass": 3.1121e9, "source": "profiles/r02_scan_tc_bf16_planes_v1.summary.txt", "tensor_pipe_pct": 66.1},
        "tcb256": {"traffic_per_pass": 3.1842e9, "source": "profiles/r02_scan_tc_bf16_n256_v1.summary.txt", "tensor_pipe_pct": 84.2},
+       # filter scan (fp16 plane): 128-query tile (3.0909 GB read + 60.8 MB written) / 2 passes; 256-query tile 1.5575 GB + 59.2 MB, one pass
+       "filt": {"traffic_per_pass": 1.5759e9, "source": "profiles/r02_scan_tc_filter_v1.summary.txt", "tensor_pipe_pct": 45.2},
+       "filt256": {"traffic_per_pass": 1.6167e9, "source": "profiles/r02_scan_tc_filter_n256_v1.summary.txt", "tensor_pipe_pct": 62.1},
        # int8 full scan of 1M x 768, 1024 queries = 8 passes in one launch: (6.2222 GB read + 219.8 MB written) / 8
        "scan_tc_i8": {"traffic_per_pass": 0.8052e9, "source": "profiles/r02_scan_tc_i8.summary.txt"},
        # lex_score<OR>, C3 10M docs, 4096 queries, Topk: 6.8986 GB read + 60.6 MB written (random 32-byte sector probes of the
@@ -349,8 +352,8 @@ def bench_vector(a, rank, world, out):
 
             def step_b():
                 ix.search_vector_raw(qn, TOPK, hb, nb)
-            msb = timed_steps(step_b, max(5, a.steps // 2), 2, world)
-            per = msb / max(5, a.steps // 2)
+            msb = timed_steps(step_b, max(10, a.steps), 5, world)
+            per = msb / max(10, a.steps)
             sweep[str(bs)] = {"ms_per_call": per, "queries_per_s": bs / (per / 1e3)}
     best = max(names, key=lambda k: res[k]["value"])      # headline = what SSB_VEC_KERNEL_AUTO picks for this batch size
     r = res[best]
@@ -676,16 +679,16 @@ def bench_hybrid(a, rank, world):
     ms, h2d, launches = _hybrid_steps(a, ix, qk, qv, world, steps)
     ix.close()
     peak, peak_kind = peaks()
-    passes = (nq + 127) // 128
-    alg = float(local_rows) * C2_DIMS * 4 * passes
+    passes = (nq + 255) // 256                                   # AUTO: filter scan, 256 queries per pass over the 2-byte plane
+    alg = float(local_rows) * C2_DIMS * 2 * passes
     return {"metric": "queries/sec at top-10 (hybrid: BM25 OR + 768-d cosine, RRF)", "value": nq * steps / (ms / 1e3), "unit": "queries/s",
             "ms_per_step": ms / steps, "steps": steps,
             "config": {"workload": f"C4 hybrid: {n_docs} docs (Zipf lexical index + {n_docs} x {C2_DIMS} f32 vectors), {nq} queries/step, e2e through ssb_search_hybrid (host buffers)"},
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": nq * 32 * 16, "gpu_launches": int(launches) * steps,
-            # the step is bounded below by the vector scan of the 15.4 GB corpus: 8 passes of 128 queries
+            # the step is bounded below by the vector scan: 4 filter passes of 256 queries over the 7.7 GB fp16 plane (f32-equivalent: x2)
             "roofline": {"bound": "hbm", "achieved": alg / (ms / steps / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (ms / steps / 1e3) / 1e9 / peak, "peak_kind": f"of {peak_kind}", "kernel": "whole step (scan_tc + lex_score overlapped + host RRF)",
-                         "algorithmic_bytes_per_launch": alg}}
+                         "frac": alg / (ms / steps / 1e3) / 1e9 / peak, "peak_kind": f"of {peak_kind}", "kernel": "whole step (filter scan_tc + refine, lex_score overlapped, host RRF)",
+                         "algorithmic_bytes_per_launch": alg, "f32_equivalent_gbs": 2 * alg / (ms / steps / 1e3) / 1e9}}
 
 
 def bench_c5(a, rank, world, ix):
@@ -715,8 +718,8 @@ def bench_c5(a, rank, world, ix):
         step_v(); torch.cuda.synchronize()
         kern.append(ix.last_stats()["dominant_kernel_ns"])
     peak, peak_kind = peaks()
-    passes = (a.batch + 127) // 128
-    alg = float(local_rows) * C2_DIMS * 4 * passes
+    passes = (a.batch + 255) // 256 if a.batch > 128 else 1      # AUTO: filter scan (2-byte plane), 256 (128) queries per pass
+    alg = float(local_rows) * C2_DIMS * 2 * passes
     kern_ms = float(np.median(kern)) / 1e6 if kern and min(kern) > 0 else None
     return {"metric": "queries/sec at top-10 (C5: 10M docs BM25 + 10M x 768 cosine, RRF hybrid, sharded)", "value": nq * steps / (ms / 1e3),
             "unit": "queries/s", "ms_per_step": ms / steps, "steps": steps,
@@ -726,7 +729,8 @@ def bench_c5(a, rank, world, ix):
             "vector_only": {"value": a.batch * max(3, a.steps // 2) / (msv / 1e3), "unit": "queries/s", "batch": a.batch,
                             "roofline": {"bound": "hbm", "achieved": (alg / (kern_ms / 1e3) / 1e9) if kern_ms else None, "peak": peak, "unit": "GB/s",
                                          "frac": (alg / (kern_ms / 1e3) / 1e9 / peak) if kern_ms else None, "peak_kind": f"of {peak_kind}",
-                                         "kernel": "scan_tc", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg}}}
+                                         "kernel": "scan_tc<256, f16 filter>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg,
+                                         "f32_equivalent_gbs": (2 * alg / (kern_ms / 1e3) / 1e9) if kern_ms else None}}}
 
 
 # ----------------------------------------------------------------------------------------------------------------

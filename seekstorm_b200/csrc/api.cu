@@ -289,7 +289,8 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
         if (filter) {
             vec::RefineArgs r{};
             r.rows = ix->rows.p; r.doc_ids = ix->doc_ids.p; r.n_rows = ix->n_rows; r.dpad = ix->dpad; r.queries_padded = c.qpad.p; r.margin = c.q_scale.p;
-            r.keys = merged; r.nq = nq; r.nq_pad = nq_pad; r.k = k;
+            r.keys = merged; r.keys_out = keys_out_dev;   // the refine step writes the caller's buffer directly
+            r.nq = nq; r.nq_pad = nq_pad; r.k = k;
             r.fb_lists = c.scratch.p + head_words;
             r.fb_state = reinterpret_cast<uint32_t*>(r.fb_lists + (size_t)nq_pad * ix->n_sms * LIST);
             r.del_slot = a.del_slot; r.del_words = a.del_words; r.ivf_sel = a.ivf_sel; r.ivf_words = a.ivf_words; r.row_cluster = a.row_cluster; r.n_sms = ix->n_sms; r.launches = &c.stats.kernel_launches;
@@ -299,7 +300,7 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     } else {
         SSB_TRY(vec::launch_scan_ffma(a, st));
     }
-    SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, st));
+    if (!filter) SSB_CUDA_TRY(cudaMemcpyAsync(keys_out_dev, merged, (size_t)nq * LIST * 8, cudaMemcpyDeviceToDevice, st));
     c.stats.algorithmic_bytes += (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * (ix->quant_i8 ? 1 : 4);
     // bytes the scan kernel actually streams per call: the filter scan reads the 2-byte hi plane, the refine step <= 32 f32 rows per query
     c.stats.scan_bytes_read += filter ? (uint64_t)(nq_pad / qt) * ix->n_rows * ix->dims * 2 + (uint64_t)nq * LIST * ix->dims * 4
@@ -1042,6 +1043,7 @@ int32_t ssb_comm_init(ssb_index* ix, const uint8_t* id128, uint32_t rank, uint32
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     if (ix->comm.comm) { set_error("ssb_comm_init: the index already has a communicator"); return SSB_E_STATE; }
     SSB_TRY(comm_init(ix->comm, id128, rank, world));
+    ix->lex->set_comm(&ix->comm);
     std::lock_guard<std::mutex> g2(ix->pool_mu);
     if (ix->pool.size() > 1) { ix->pool.resize(1); ix->free_ctx.clear(); ix->free_ctx.push_back(ix->pool[0].get()); ix->last_ctx = nullptr; }
     return SSB_OK;
@@ -1054,6 +1056,7 @@ int32_t ssb_comm_attach(ssb_index* ix, void* nccl_comm, uint32_t rank, uint32_t 
     std::unique_lock<std::shared_mutex> g(ix->rw);
     if (ix->comm.comm) { set_error("ssb_comm_attach: the index already has a communicator"); return SSB_E_STATE; }
     ix->comm.comm = nccl_comm; ix->comm.rank = rank; ix->comm.world = world; ix->comm.owned = false;
+    ix->lex->set_comm(&ix->comm);
     std::lock_guard<std::mutex> g2(ix->pool_mu);
     if (ix->pool.size() > 1) { ix->pool.resize(1); ix->free_ctx.clear(); ix->free_ctx.push_back(ix->pool[0].get()); ix->last_ctx = nullptr; }
     return SSB_OK;

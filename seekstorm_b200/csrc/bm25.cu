@@ -33,6 +33,7 @@
 // (__fmul_rn/__fdiv_rn/__fadd_rn), summed in query order from 0.0 (add_result.rs:1450-1452), idf and the 256-entry
 // cache computed on the host.
 #include "bm25.h"
+#include "comm.h"
 
 #include <cuda_fp16.h>
 #include <math.h>
@@ -716,6 +717,8 @@ __device__ __forceinline__ void stream_driver(const LexView& v, WarpSm& w, uint3
         const uint4 cur = nxt;
         // software pipelining: the next 128 postings are requested before these are filtered (two vectors ahead was measured:
         // the extra registers spill and cost more than the deeper prefetch gains)
+        // (L1 policy was measured too: ld.global.nc.L1::no_allocate on this stream and L1::evict_last on the coarse bytes change the
+        // kernel time by < 1 % — the coarse-byte loads stall on latency, not on evictions by the stream)
         src += 32;
         nxt = rel + 128u < r1 ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
         bool a0 = rel      >= r0 && rel      < r1 && fmaf(didf, bound_of_word(cur.x), R) >= thr.lo;
@@ -1164,6 +1167,13 @@ __device__ __forceinline__ void publish(uint64_t L, uint32_t q, uint32_t k, int 
         __threadfence();
         atomicExch(&lock[q], 0);
     }
+}
+
+// sharded index, threshold exchange (search_keys): resume == 0 hides every item but the first of each query from the next lex_score launch
+// (ctr[1] = max items per query -> 1, the real value parked in ctr[6]); resume = nq restores it and moves the score work counter to nq
+__global__ void first_wave_only(uint32_t* ctr, uint32_t resume) {
+    if (resume == 0) { ctr[6] = ctr[1]; if (ctr[1] > 1u) ctr[1] = 1u; }
+    else { ctr[1] = ctr[6]; ctr[0] = resume; }
 }
 
 // ---- scoring, queries with <= 4 live terms (ResultType Topk / TopkCount) ----
@@ -1757,8 +1767,24 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
         // batches that carry NOT terms ('-' operator) run their own instantiation: the common kernel stays free of the out-of-line probe
         const bool hn = q->term_flags != nullptr;
 #define SSB_LAUNCH_SCORE(A, N) lex_score<A, N><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev)
-        if (is_and) { if (hn) SSB_LAUNCH_SCORE(true, true); else SSB_LAUNCH_SCORE(true, false); }
-        else { if (hn) SSB_LAUNCH_SCORE(false, true); else SSB_LAUNCH_SCORE(false, false); }
+#define SSB_LAUNCH_SCORE_ALL() do { if (is_and) { if (hn) SSB_LAUNCH_SCORE(true, true); else SSB_LAUNCH_SCORE(true, false); } \
+                                    else { if (hn) SSB_LAUNCH_SCORE(false, true); else SSB_LAUNCH_SCORE(false, false); } } while (0)
+        if (comm_ && comm_->active()) {
+            // Sharded index: a shard on its own can only prune with the k-th best score of ITS docs, which is lower than the index-wide
+            // one — every rank would do more than its 1/world share of the work (measured at 2 GPUs: lex_score 2.19 -> 1.76 ms).  The
+            // first item of every query (its best levels) sets a local threshold; the element-wise MAXIMUM of those over the ranks is a
+            // valid index-wide threshold (rank r* alone already holds k docs at or above it), so it is exchanged once (8 bytes per
+            // query, ncclAllReduce max) before the remaining items run.  Keys are a total order, so the maximum of keys is exact.
+            // (the first launch sees max_items = 1, i.e. work indices [0, nq): wave 0; the kernel itself is unchanged)
+            first_wave_only<<<1, 1, 0, st>>>(ws.ctr, 0u);
+            SSB_LAUNCH_SCORE_ALL();
+            SSB_CUDA_TRY(cudaGetLastError());
+            first_wave_only<<<1, 1, 0, st>>>(ws.ctr, nq);         // restore max_items; the work counter overshoots by whole chunks: continue at index nq
+            SSB_TRY(comm_all_reduce_max_u64(*comm_, ws.theta, nq, st));
+            if (launches) *launches += 4;
+        }
+        SSB_LAUNCH_SCORE_ALL();
+#undef SSB_LAUNCH_SCORE_ALL
 #undef SSB_LAUNCH_SCORE
         SSB_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;

@@ -29,7 +29,7 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float s) {
 // one CTA per query
 __global__ void __launch_bounds__(RTHREADS)
 refine_candidates(const float* __restrict__ rows, const uint32_t* __restrict__ doc_ids, uint32_t dpad, const float* __restrict__ queries,
-                  const float* __restrict__ margin, uint64_t* __restrict__ keys, uint32_t k, uint32_t* __restrict__ fb_state) {
+                  const float* __restrict__ margin, const uint64_t* keys, uint64_t* keys_out, uint32_t k, uint32_t* __restrict__ fb_state) {
     __shared__ uint64_t ex[LIST];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t q = blockIdx.x;
@@ -61,7 +61,7 @@ refine_candidates(const float* __restrict__ rows, const uint32_t* __restrict__ d
     }
     __syncthreads();
     if (warp == 0) {
-        keys[(size_t)q * LIST + lane] = wl_sort_desc(ex[lane], lane);
+        keys_out[(size_t)q * LIST + lane] = wl_sort_desc(ex[lane], lane);   // (every warp read its `keys` before the barrier: aliasing is fine)
         // candidate-set overflow: the list is full and its last entry is still a candidate
         const uint64_t kth = shfl64(mine, (int)k - 1), last = shfl64(mine, LIST - 1);
         if (lane == 0 && last && kth) {
@@ -147,7 +147,7 @@ size_t refine_scratch_words(int n_sms, uint32_t nq_pad) { return (size_t)nq_pad 
 int32_t launch_refine(const RefineArgs& a, cudaStream_t st) {
     if (a.nq == 0) return SSB_OK;
     SSB_CUDA_TRY(cudaMemsetAsync(a.fb_state, 0, 4, st));
-    rf::refine_candidates<<<a.nq, rf::RTHREADS, 0, st>>>(a.rows, a.doc_ids, a.dpad, a.queries_padded, a.margin, a.keys, a.k, a.fb_state);
+    rf::refine_candidates<<<a.nq, rf::RTHREADS, 0, st>>>(a.rows, a.doc_ids, a.dpad, a.queries_padded, a.margin, a.keys, a.keys_out, a.k, a.fb_state);
     SSB_CUDA_TRY(cudaGetLastError());
     const int smem = rf::QF * (int)a.dpad * 4;
     if (smem > 200 * 1024) { set_error("filter scan: vector_dims too large for the fallback scan"); return SSB_E_UNSUPPORTED; }
@@ -155,7 +155,7 @@ int32_t launch_refine(const RefineArgs& a, cudaStream_t st) {
     rf::fallback_scan<<<a.n_sms, rf::FTHREADS, smem, st>>>(a.rows, a.doc_ids, a.n_rows, a.dpad, a.queries_padded, a.fb_state, a.fb_lists, a.k,
                                                            a.del_slot, a.del_words, a.ivf_sel, a.ivf_words, a.row_cluster);
     SSB_CUDA_TRY(cudaGetLastError());
-    rf::fallback_merge<<<64, 32, 0, st>>>(a.fb_state, a.fb_lists, (uint32_t)a.n_sms, a.keys);
+    rf::fallback_merge<<<64, 32, 0, st>>>(a.fb_state, a.fb_lists, (uint32_t)a.n_sms, a.keys_out);
     SSB_CUDA_TRY(cudaGetLastError());
     if (a.launches) *a.launches += 3;
     return SSB_OK;

@@ -71,7 +71,8 @@ struct RefineArgs {
     const float* rows; const uint32_t* doc_ids; uint64_t n_rows; uint32_t dpad;
     const float* queries_padded;      // [nq_pad][dpad] f32 (normalised for Cosine)
     const float* margin;              // [nq_pad] 2 eps_q
-    uint64_t* keys;                   // in: merged approximate keys [nq_pad][32] (low word = 0xFFFFFFFF - row); out: exact keys (low word = doc id)
+    const uint64_t* keys;             // in: merged approximate keys [nq_pad][32] (low word = 0xFFFFFFFF - row)
+    uint64_t* keys_out;               // out: exact keys [nq][32] (low word = 0xFFFFFFFF - doc id); may alias `keys`
     uint32_t nq, nq_pad, k;
     uint32_t* fb_state;               // [1 + nq_pad]: count of flagged queries + their indices (zeroed by the refine launch)
     uint64_t* fb_lists;               // [nq_pad][n_sms][32] fallback scratch
