@@ -1043,7 +1043,6 @@ int32_t ssb_comm_init(ssb_index* ix, const uint8_t* id128, uint32_t rank, uint32
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
     if (ix->comm.comm) { set_error("ssb_comm_init: the index already has a communicator"); return SSB_E_STATE; }
     SSB_TRY(comm_init(ix->comm, id128, rank, world));
-    ix->lex->set_comm(&ix->comm);
     std::lock_guard<std::mutex> g2(ix->pool_mu);
     if (ix->pool.size() > 1) { ix->pool.resize(1); ix->free_ctx.clear(); ix->free_ctx.push_back(ix->pool[0].get()); ix->last_ctx = nullptr; }
     return SSB_OK;
@@ -1056,7 +1055,6 @@ int32_t ssb_comm_attach(ssb_index* ix, void* nccl_comm, uint32_t rank, uint32_t 
     std::unique_lock<std::shared_mutex> g(ix->rw);
     if (ix->comm.comm) { set_error("ssb_comm_attach: the index already has a communicator"); return SSB_E_STATE; }
     ix->comm.comm = nccl_comm; ix->comm.rank = rank; ix->comm.world = world; ix->comm.owned = false;
-    ix->lex->set_comm(&ix->comm);
     std::lock_guard<std::mutex> g2(ix->pool_mu);
     if (ix->pool.size() > 1) { ix->pool.resize(1); ix->free_ctx.clear(); ix->free_ctx.push_back(ix->pool[0].get()); ix->last_ctx = nullptr; }
     return SSB_OK;

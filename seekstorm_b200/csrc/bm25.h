@@ -170,7 +170,6 @@ public:
     bool committed() const { return committed_; }
     void set_stream(cudaStream_t st) { st_ = st; }   // load-time stream (add_level / commit)
     void set_deleted(const DeleteSet* d) { del_ = d; }
-    void set_comm(const struct ShardComm* c) { comm_ = c; }   // sharded index: the per-query thresholds are exchanged once per batch (search_keys)
     static LexStats read_stats(const LexWorkspace& ws, cudaStream_t st);
     uint64_t n_postings() const { return n_post_; }
     const std::vector<uint64_t>& host_keys() const { return h_dict_keys_; }
@@ -198,7 +197,6 @@ private:
     uint32_t* d_level_ids_ = nullptr; float* d_cache_ = nullptr;
     std::vector<uint64_t> h_dict_keys_; std::vector<uint32_t> h_term_df_, h_local_df_;
     const DeleteSet* del_ = nullptr;
-    const struct ShardComm* comm_ = nullptr;
     void free_committed();
     LexView view() const;
 };
