@@ -57,7 +57,7 @@ def parse():
     p.add_argument("--c5-docs", type=int, default=10_000_000, help="C5: docs AND vectors of the sharded hybrid index")
     p.add_argument("--parity-queries", type=int, default=64, help="queries per path of the post-run oracle check")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
-    p.add_argument("--vector-kernel", default="both", choices=["both", "all", "ffma", "tc", "tc64", "tcb", "tcb64", "tcb256", "filt", "filt256"],
+    p.add_argument("--vector-kernel", default="both", choices=["both", "all", "ffma", "tc", "tc64", "tcb", "tcb64", "tcb256", "filt", "filt256", "filt256p"],
                    help="FP32 FFMA2 scan, tcgen05 scans, or both = ffma + tcb + tcb256 (headline = the fastest: what AUTO picks)")
     return p.parse_args()
 
@@ -242,7 +242,8 @@ KERNELS = {"ffma": (1, 16, "scan_ffma", "scan_ffma (TMA + packed FP32 FFMA2 + wa
            # filter scan: ONE fp16 product over the 2-byte plane selects (proven margin) the <= 32 rows that can be in the top-10, refine
            # re-scores them with the f32 dot product; the result is the exact f32 top-k
            "filt": (7, 128, "scan_tc", "scan_tc<128, f16 filter> + refine_candidates (tcgen05 1xFP16 over the 2-byte plane, exact f32 re-scoring of <= 32 candidates per query)"),
-           "filt256": (8, 256, "scan_tc", "scan_tc<256, f16 filter> + refine_candidates (256 queries per pass)")}
+           "filt256": (8, 256, "scan_tc", "scan_tc<256, f16 filter> + refine_candidates (256 queries per pass)"),
+           "filt256p": (9, 256, "scan_tc", "scan_tc2 (256-query f16 filter on CTA pairs, tcgen05 cta_group::2) + refine_candidates")}
 # DRAM traffic per corpus pass (dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture, divided by
 # the passes in that launch, 1M x 768 corpus) from the committed captures under profiles/: traffic ~= algorithmic bytes
 # (3.072 GB), i.e. no re-reads.
@@ -367,7 +368,7 @@ def bench_vector(a, rank, world, out):
         "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "clocks": r["clocks"],
         "batch_sweep_e2e": sweep,
         "kernels": {{"ffma": "scan_ffma", "tc": "scan_tc_tf32", "tc64": "scan_tc_tf32_n64", "tcb": "scan_tc_bf16", "tcb64": "scan_tc_bf16_n64", "tcb256": "scan_tc_bf16_n256",
-                     "filt": "scan_tc_f16_filter", "filt256": "scan_tc_f16_filter_n256"}[k]:
+                     "filt": "scan_tc_f16_filter", "filt256": "scan_tc_f16_filter_n256", "filt256p": "scan_tc2_f16_filter_n256_pair"}[k]:
                     {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
     })
     return ix, q_host

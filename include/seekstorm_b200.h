@@ -70,7 +70,9 @@ enum { SSB_VEC_KERNEL_AUTO = 0, SSB_VEC_KERNEL_FFMA = 1, SSB_VEC_KERNEL_TCGEN05 
        /* FILTER: one bf16 product over the 2-byte hi plane of the corpus selects, with a proven error margin, the <= 32 rows that can be
         * in the top-k (k <= 16); those are re-scored with the plain f32 dot product and queries whose candidate set did not fit are re-run
         * by an exact f32 scan on the device.  Results are the exact f32 top-k.  128 / 256 queries per corpus pass. */
-       SSB_VEC_KERNEL_TCGEN05_FILTER = 7, SSB_VEC_KERNEL_TCGEN05_FILTER_N256 = 8 };
+       SSB_VEC_KERNEL_TCGEN05_FILTER = 7, SSB_VEC_KERNEL_TCGEN05_FILTER_N256 = 8,
+       /* the 256-query filter scan on CTA pairs (tcgen05 cta_group::2, clusters of 2): the two SMs of a pair share one copy of the query block */
+       SSB_VEC_KERNEL_TCGEN05_FILTER_N256_PAIR = 9 };
 
 typedef struct ssb_index ssb_index;
 

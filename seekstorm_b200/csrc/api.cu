@@ -191,20 +191,20 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
         // filter scan + exact refine: half the bytes and a third of the tensor work per pass
         // — at every batch size: one 128-query filter pass (0.25 ms on 1M x 768) also beats the FP32 scan's 0.5 ms pass for <= 16 queries
         const uint32_t exact_kern = kern;
-        kern = nq <= 128 ? SSB_VEC_KERNEL_TCGEN05_FILTER : SSB_VEC_KERNEL_TCGEN05_FILTER_N256;
+        kern = nq <= 128 ? SSB_VEC_KERNEL_TCGEN05_FILTER : SSB_VEC_KERNEL_TCGEN05_FILTER_N256_PAIR;   // above 128 queries: 256 per pass on CTA pairs
         if (ix->quant_i8 || ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN || k > 16 || ceil_dev || !ix->rows_h16.p || !ix->vec_err.p) kern = exact_kern;
     }
     // the filter scan keeps a candidate set sized for k <= 16 in the 32-entry lists and has no paging (ceilings are exact keys): those
     // calls take the exact 3-product scan
-    bool filter = (kern == SSB_VEC_KERNEL_TCGEN05_FILTER || kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256);
+    bool filter = (kern == SSB_VEC_KERNEL_TCGEN05_FILTER || kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256 || kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256_PAIR);
     if (filter && (ix->quant_i8 || ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN || k > 16 || ceil_dev || !ix->rows_h16.p || !ix->vec_err.p)) {
-        kern = kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256 && (nq + 255u) / 256u * 95u < (nq + 127u) / 128u * 55u ? SSB_VEC_KERNEL_TCGEN05_BF16_N256 : SSB_VEC_KERNEL_TCGEN05_BF16;
+        kern = kern != SSB_VEC_KERNEL_TCGEN05_FILTER && (nq + 255u) / 256u * 95u < (nq + 127u) / 128u * 55u ? SSB_VEC_KERNEL_TCGEN05_BF16_N256 : SSB_VEC_KERNEL_TCGEN05_BF16;
         filter = false;
         if (ix->quant_i8) kern = SSB_VEC_KERNEL_TCGEN05;
     }
     const bool use_tc = ix->quant_i8 || (kern >= SSB_VEC_KERNEL_TCGEN05 && ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN);   // the int8 index is always scanned on the tensor cores
     const bool tc_bf16 = filter || kern == SSB_VEC_KERNEL_TCGEN05_BF16 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256;
-    const uint32_t qt = !use_tc ? vec::VEC_QT : (ix->quant_i8 ? 128u : (kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : ((kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256 || kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256) ? 256u : 128u));
+    const uint32_t qt = !use_tc ? vec::VEC_QT : (ix->quant_i8 ? 128u : (kern == SSB_VEC_KERNEL_TCGEN05_N64 || kern == SSB_VEC_KERNEL_TCGEN05_BF16_N64) ? 64u : ((kern == SSB_VEC_KERNEL_TCGEN05_BF16_N256 || kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256 || kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256_PAIR) ? 256u : 128u));
     const uint32_t nq_pad = (nq + qt - 1) / qt * qt;
     cudaStream_t st = c.st;
     if (!ix->quant_i8) SSB_TRY(c.qpad.reserve((size_t)nq_pad * ix->dpad, 0, st));
@@ -285,7 +285,7 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
         SSB_TRY(c.qlo.reserve((size_t)nq_pad * ix->dpad, 0, st));
         a.q_hi = c.qhi.p; a.q_lo = c.qlo.p;
         if (filter) a.q_scale = c.q_scale.p;
-        SSB_TRY(vec::launch_scan_tc(a, qt, filter ? 3 : (tc_bf16 ? 1 : 0), st));
+        SSB_TRY(vec::launch_scan_tc(a, qt, filter ? (kern == SSB_VEC_KERNEL_TCGEN05_FILTER_N256_PAIR ? 4 : 3) : (tc_bf16 ? 1 : 0), st));
         if (filter) {
             vec::RefineArgs r{};
             r.rows = ix->rows.p; r.doc_ids = ix->doc_ids.p; r.n_rows = ix->n_rows; r.dpad = ix->dpad; r.queries_padded = c.qpad.p; r.margin = c.q_scale.p;
@@ -787,7 +787,7 @@ int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n) {
 
 int32_t ssb_set_vector_kernel(ssb_index* ix, uint32_t kernel) {
     SSB_API_BEGIN
-    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_FILTER_N256) { set_error("bad vector kernel"); return SSB_E_INVALID; }
+    if (!ix || kernel > SSB_VEC_KERNEL_TCGEN05_FILTER_N256_PAIR) { set_error("bad vector kernel"); return SSB_E_INVALID; }
     std::unique_lock<std::shared_mutex> g(ix->rw);
     ix->cfg.vector_kernel = kernel;
     return SSB_OK;

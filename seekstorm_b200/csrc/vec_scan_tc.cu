@@ -529,6 +529,199 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// scan_tc2 — the 256-query filter scan on CTA PAIRS (tcgen05 cta_group::2, thread-block cluster of 2).
+// The one-CTA 256-query pass is bounded by what an SM can take in from L2: per 64-dim stage 16 KB of corpus + 32 KB of the query block
+// at ~64 B/clk (ncu: 374 us against an HBM time of 234 us).  A pair of SMs shares ONE copy of the query block: each CTA loads its own
+// 128 corpus rows (A, 16 KB) and HALF of the 256 queries (B, 16 KB) per stage, the leader's single thread issues M = 256 x N = 256 MMAs
+// that read both halves (the peer's through the pair's shared-memory path), and every SM takes in 32 KB per stage instead of 48.
+// Pipelines as in scan_tc; what changes: both CTAs' TMA loads complete on the LEADER's full barrier (cta_group::2 loads, peer bit of the
+// barrier address cleared), tcgen05.commit is multicast to both CTAs' empty / tfull barriers, the epilogue warps of BOTH CTAs arrive on
+// the leader's tempty barrier, TMEM is allocated with cta_group::2.  Filter precision only (PREC_F16F, NQ = 256); the threshold-seeding
+// sample pass stays on scan_tc<256, F16F>.
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // shared::cluster address -> the same offset in the pair's even (leader) CTA
+struct Cfg2 {
+    static constexpr int NQ = 256, NQH = 128;
+    static constexpr int A_BYTES = TM * 128;           // 128 rows x 64 halves
+    static constexpr int B_BYTES = NQH * 128;          // this CTA's half of the query block
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+    static constexpr int STAGES = 6;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + NQ * 12 + 256;
+    static constexpr int TMEM_COLS = 2 * NQ;            // double-buffered [128 lanes x 256 columns] per CTA
+};
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar_in_leader) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar_in_leader) & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs once the MMAs issued so far retire
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+scan_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, uint32_t n_rows, uint32_t n_kchunks, uint32_t n_pairs, uint32_t k,
+         const uint32_t* __restrict__ doc_ids, uint64_t* __restrict__ scratch /*[gridDim.y][gridDim.x*4][256][32]*/,
+         const uint32_t* __restrict__ thr_init, uint32_t nq_valid, const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words,
+         const float* __restrict__ q_margin, const uint32_t* __restrict__ ivf_sel, uint32_t ivf_words, const uint32_t* __restrict__ row_cluster) {
+    using C = Cfg2;
+    constexpr int NQ = C::NQ;
+    extern __shared__ __align__(1024) uint8_t base[];
+    uint8_t* stage0 = base;
+    uint64_t* lists = scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 * NQ * LIST;
+    uint32_t* thr_u = (uint32_t*)(base + C::STAGES * C::STAGE_BYTES);
+    float* qs_sm = (float*)(thr_u + NQ);
+    uint64_t* bars = (uint64_t*)(thr_u + 3 * NQ);
+    uint64_t* full = bars;                     // [STAGES]  (used in the leader only)
+    uint64_t* empty = full + MAX_STAGES;       // [STAGES]
+    uint64_t* tfull = empty + MAX_STAGES;      // [2]
+    uint64_t* tempty = tfull + 2;              // [2]       (used in the leader only: 24 arrivals = 12 epilogue warps x 2 CTAs)
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair0 = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 24); }
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < NQ; i += THREADS) {
+        thr_u[i] = blockIdx.y * NQ + i >= nq_valid ? 0xFFFFFFFFu : (thr_init ? __ldg(&thr_init[blockIdx.y * NQ + i]) : 0u);
+        qs_sm[i] = __ldg(&q_margin[blockIdx.y * NQ + i]);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // both CTAs' barriers are initialised before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = *(volatile uint32_t*)tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs): own corpus rows + own half of the query block =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+            uint32_t it = 0;
+            for (uint32_t pr = pair0; pr < n_pairs; pr += n_clusters) {
+                for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
+                    const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1u;
+                    uint8_t* st = stage0 + s * C::STAGE_BYTES;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);       // the bytes of both CTAs land on the leader's barrier
+                    tma_load_2d_pair(st, &tmA, (int)(kc * 64), (int)((pr * 2 + rank) * TM), &full[s]);
+                    tma_load_2d_pair(st + C::A_BYTES, &tmB, (int)(kc * 64), (int)(blockIdx.y * NQ + rank * C::NQH), &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: one thread of the LEADER CTA, M = 256 (128 rows per CTA) x N = 256 =====================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NQ >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+            uint32_t it = 0, ti = 0;
+            for (uint32_t pr = pair0; pr < n_pairs; pr += n_clusters, ++ti) {
+                const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
+                mbar_wait(&tempty[buf], tph ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * NQ;
+                for (uint32_t kc = 0; kc < n_kchunks; ++kc, ++it) {
+                    const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage0 + s * C::STAGE_BYTES);
+                    const uint64_t a = umma_desc_k128(sa), b = umma_desc_k128(sa + C::A_BYTES);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < 4; kk++)
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(d), "l"(a + (uint64_t)(kk * 2)), "l"(b + (uint64_t)(kk * 2)), "r"(idesc), "r"((uint32_t)((kc | kk) != 0)) : "memory");
+                    umma_commit_pair(&empty[s]);
+                    if (kc + 1 == n_kchunks) umma_commit_pair(&tfull[buf]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, 12 warps each): the f32 epilogue of scan_tc for MT = 1, filter margins =====================
+        constexpr int EG = 3;
+        constexpr int NCH3 = (NQ / CHUNK + EG - 1) / EG * EG;
+        const int ew = warp & 3, g = (warp - 4) >> 2;
+        uint64_t* mylists = lists + (size_t)ew * NQ * LIST;
+        for (int c = g; c < NQ / CHUNK; c += EG)
+            for (int i = lane; i < CHUNK * LIST; i += 32) mylists[c * CHUNK * LIST + i] = 0;
+        __syncwarp();
+        uint32_t ti = 0;
+        for (uint32_t pr = pair0; pr < n_pairs; pr += n_clusters, ++ti) {
+            const uint32_t buf = ti & 1u, tph = (ti >> 1) & 1u;
+            mbar_wait(&tfull[buf], tph);
+            tc_fence_after();
+            const uint32_t row = (pr * 2 + rank) * TM + (uint32_t)(ew * 32 + lane);
+            const bool valid = row < n_rows;
+            for (int c = g; c < NCH3; c += EG) {
+                if (c >= NQ / CHUNK) continue;
+                uint32_t v[CHUNK];
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * NQ + c * CHUNK;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                {
+                    const uint4* t4 = reinterpret_cast<const uint4*>(thr_u + c * CHUNK);
+                    const uint4 t0 = t4[0], t1 = t4[1];
+                    const bool any = (ord_f32(__uint_as_float(v[0])) >= t0.x) | (ord_f32(__uint_as_float(v[1])) >= t0.y) |
+                                     (ord_f32(__uint_as_float(v[2])) >= t0.z) | (ord_f32(__uint_as_float(v[3])) >= t0.w) |
+                                     (ord_f32(__uint_as_float(v[4])) >= t1.x) | (ord_f32(__uint_as_float(v[5])) >= t1.y) |
+                                     (ord_f32(__uint_as_float(v[6])) >= t1.z) | (ord_f32(__uint_as_float(v[7])) >= t1.w);
+                    if (!__any_sync(FULL, any && valid)) continue;
+                }
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) {
+                    const int q = c * CHUNK + j;
+                    const float sc = __uint_as_float(v[j]);
+                    const uint32_t so = ord_f32(sc);
+                    const bool pass = valid && sc == sc && so >= thr_u[q];
+                    unsigned pm = __ballot_sync(FULL, pass);
+                    if (pm) {
+                        uint64_t key = 0;
+                        if (pass) {
+                            const uint32_t doc = doc_ids ? __ldg(&doc_ids[row]) : row;
+                            key = ((uint64_t)so << 32) | (uint64_t)(0xFFFFFFFFu - row);          // filter scan: candidates are named by row
+                            if (doc_deleted(del_slot, del_words, doc) || ivf_skipped(ivf_sel, ivf_words, blockIdx.y * NQ + q, row_cluster, row)) key = 0;
+                        }
+                        if (del_slot || ivf_sel) { pm = __ballot_sync(FULL, key != 0); if (!pm) continue; }
+                        uint64_t L = mylists[q * LIST + lane];
+                        if (__popc(pm) > 3) L = wl_merge(L, wl_sort_desc(key, lane), lane);
+                        else while (pm) { const int src = __ffs(pm) - 1; pm &= pm - 1; wl_insert(L, shfl64(key, src), lane); }
+                        mylists[q * LIST + lane] = L;
+                        uint32_t kth = (uint32_t)(shfl64(L, (int)k - 1) >> 32);
+                        if (kth) kth = ord_f32(__fsub_rd(unord_f32(kth), qs_sm[q]));
+                        if (lane == 0 && kth > thr_u[q]) atomicMax(&thr_u[q], kth);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // the peer may still be reading this CTA's shared memory / arriving on its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
 // [nq_pad][dpad] f32 -> hi / lo parts: tf32 (f32 containers) or bf16
 __global__ void split_queries_tf32(const float* __restrict__ q, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -749,8 +942,39 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     return SSB_OK;
 }
 
-static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec /*0 tf32, 1 bf16, 2 int8*/, cudaStream_t st) {
+// 256-query filter scan on CTA pairs (scan_tc2): thread-block clusters of 2, one pair per 256 corpus rows and k-chunk
+static int32_t launch_tc2(const ScanArgs& a, cudaStream_t st) {
+    using C = tc::Cfg2;
+    if (!a.rows_h16 || !a.q_scale) { set_error("tcgen05 filter scan: the index holds no fp16 plane / no margins"); return SSB_E_STATE; }
+    if (a.nq_pad % C::NQ != 0) { set_error("tcgen05 pair scan: query count must be padded to 256"); return SSB_E_INVALID; }
+    CUtensorMap tmA, tmB;
+    SSB_TRY(encode_tmap_2d(&tmA, a.rows_h16, 2, a.dpad, a.n_rows, (uint64_t)a.dpad * 2, 64, tc::TM, 128));
+    SSB_TRY(encode_tmap_2d(&tmB, a.q_hi, 2, a.dpad, a.nq_pad, (uint64_t)a.dpad * 2, 64, C::NQH, 128));
+    const uint32_t n_kchunks = (a.dpad + 63) / 64, n_groups = a.nq_pad / C::NQ;
+    const uint32_t n_pairs = (uint32_t)((a.n_rows + 2 * tc::TM - 1) / (2 * tc::TM));
+    uint32_t n_clusters = (uint32_t)a.n_sms / 2;
+    if (n_clusters > n_pairs) n_clusters = n_pairs;
+    const uint32_t gx = 2 * n_clusters;
+    if ((size_t)n_groups * gx * 4 * C::NQ * LIST * 8 > a.scratch_bytes) { set_error("vector scan scratch too small"); return SSB_E_STATE; }
+    SSB_CUDA_TRY(cudaFuncSetAttribute(tc::scan_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(gx, n_groups); cfg.blockDim = dim3(tc::THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (a.ev0) cudaEventRecord(a.ev0, st);
+    SSB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::scan_tc2, tmA, tmB, (uint32_t)a.n_rows, n_kchunks, n_pairs, a.k, a.doc_ids, a.scratch, a.thr_init,
+                                    a.nq_valid ? a.nq_valid : a.nq_pad, a.del_slot, a.del_words, a.q_scale, a.ivf_sel, a.ivf_words, a.row_cluster));
+    if (a.ev1) cudaEventRecord(a.ev1, st);
+    merge_lists_generic(a.scratch, gx * 4, C::NQ, a.nq_pad, a.keys_out, st);
+    SSB_CUDA_TRY(cudaGetLastError());
+    if (a.launches) *a.launches += 2;
+    return SSB_OK;
+}
+
+static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec /*0 tf32, 1 bf16, 2 int8, 3 fp16 filter, 4 fp16 filter on CTA pairs*/, cudaStream_t st) {
     if (a.n_rows == 0 || a.nq_pad == 0) return SSB_OK;
+    if (prec == 4) return a.sample_groupmax ? launch_tc_n<256, tc::PREC_F16F>(a, st) : launch_tc2(a, st);   // the seeding pass stays on one CTA per SM
     if (prec == 2) {
         if (nq_tile != 128 || a.nq_pad % 128 != 0 || !a.rows_i8 || !a.queries_i8 || a.dpad8 % 128) { set_error("int8 scan: bad arguments"); return SSB_E_INVALID; }
         // query block resident in smem when it leaves room for >= 3 corpus stages (dims <= 1024), else streamed per stage
@@ -785,7 +1009,7 @@ int32_t launch_scan_tc(const ScanArgs& a, uint32_t nq_tile, int prec, cudaStream
     // ~1 us latency-bound list insert for an epilogue warp.  The filter scan streams a pass in half the time of the 3-product scan, so the
     // same insert load weighs twice as much: it samples more (SSB_TC_SAMPLE_TILES overrides; measured in DESIGN.md §3.2c)
     static const int env_tiles = [] { const char* e = getenv("SSB_TC_SAMPLE_TILES"); return e ? atoi(e) : 0; }();
-    const int sample_tiles = env_tiles > 0 ? (env_tiles > 16 ? 16 : env_tiles) : ((prec == 3 && nq_tile == 256) ? 2 : 1);
+    const int sample_tiles = env_tiles > 0 ? (env_tiles > 16 ? 16 : env_tiles) : ((prec >= 3 && nq_tile == 256) ? 2 : 1);
     uint64_t s = (uint64_t)a.n_sms * trows * sample_tiles;
     if (s > a.n_rows / 4) s = a.n_rows / 4 / trows * trows;
     pre.n_rows = s; pre.ev0 = nullptr; pre.ev1 = nullptr;

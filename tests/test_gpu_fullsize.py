@@ -38,7 +38,7 @@ def test_c2_full_size_vector():
     # the filter scan (AUTO's choice above 16 queries) against the exact 3-product tensor-core scan: same ids
     ix.set_vector_kernel(4)
     exact = ix.search_vector_batch(q.cpu().numpy(), 10)
-    for kern in (7, 8):
+    for kern in (7, 8, 9):
         ix.set_vector_kernel(kern)
         filt = ix.search_vector_batch(q.cpu().numpy(), 10)
         st = ix.last_stats()

@@ -222,7 +222,7 @@ def test_errors_are_status_codes():
     ix.close()
 
 
-@pytest.mark.parametrize("kernel", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("kernel", [2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("n,dims,sim", [(300, 32, "dot"), (5000, 128, "cos"), (40000, 768, "cos"), (1000, 100, "dot")])
 def test_vector_tcgen05_parity(n, dims, sim, kernel):
     """tcgen05 (3xTF32 split, TMEM accumulators) scan vs the oracle: same ids, scores within 1e-4 relative."""
@@ -232,7 +232,7 @@ def test_vector_tcgen05_parity(n, dims, sim, kernel):
     rows = synth.gen_vectors(n, dims, 3000 + n, "cpu").numpy()
     qs = synth.gen_vectors(150, dims, 4000 + n, "cpu").numpy()      # 150 -> padded to 256 = two query groups
     qs[3] = rows[n // 2] + 0.05 * qs[3]
-    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_kernel=kernel)   # 2/3: 3xTF32 (128/64 queries per pass), 4/5/6: 3xBF16 (128/64/256), 7/8: bf16 filter + f32 refine (128/256)
+    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_kernel=kernel)   # 2/3: 3xTF32 (128/64 queries per pass), 4/5/6: 3xBF16 (128/64/256), 7/8/9: fp16 filter + f32 refine (128 / 256 / 256 on CTA pairs)
     ix.add_vectors(rows)
     ref_rows = np.stack([O.normalize(r) for r in rows]) if sim == "cos" else rows
     for k in (10, 32) if kernel < 7 else (1, 10, 16, 32):
@@ -242,7 +242,7 @@ def test_vector_tcgen05_parity(n, dims, sim, kernel):
             qt = 128 if kernel == 7 else 256
             passes = (len(qs) + qt - 1) // qt
             p128, p256 = (len(qs) + 127) // 128, (len(qs) + 255) // 256
-            exact_passes = p256 if (kernel == 8 and p256 * 95 < p128 * 55) else p128      # k > 16: the exact 3-product scan AUTO would pick
+            exact_passes = p256 if (kernel in (8, 9) and p256 * 95 < p128 * 55) else p128      # k > 16: the exact 3-product scan AUTO would pick
             want_bytes = passes * n * dims * 2 + len(qs) * 32 * dims * 4 if k <= 16 else exact_passes * n * dims * 4
             assert ix.last_stats()["scan_bytes_read"] == want_bytes
         for i in range(0, len(qs), 7):
@@ -354,7 +354,7 @@ def test_hybrid_with_int8_vectors():
     ix.close()
 
 
-@pytest.mark.parametrize("kernel", [7, 8])
+@pytest.mark.parametrize("kernel", [7, 8, 9])
 def test_vector_filter_scan_fallback_on_dense_ties(kernel):
     """Filter scan: when more than 32 rows sit within the error margin of the k-th best approximate score the candidate set does not
     fit the list; those queries must be re-run by the exact fallback scan on the device (vec_refine.cu) and still return the exact top-k
