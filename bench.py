@@ -254,6 +254,8 @@ NCU = {"scan_ffma": {"traffic_per_pass": 3.0770e9, "source": "profiles/r02_scan_
        # filter scan (fp16 plane): 128-query tile (3.0909 GB read + 60.8 MB written) / 2 passes; 256-query tile 1.5575 GB + 59.2 MB, one pass
        "filt": {"traffic_per_pass": 1.5759e9, "source": "profiles/r02_scan_tc_filter_v1.summary.txt", "tensor_pipe_pct": 45.2},
        "filt256": {"traffic_per_pass": 1.6167e9, "source": "profiles/r02_scan_tc_filter_n256_v1.summary.txt", "tensor_pipe_pct": 62.1},
+       # scan_tc2 (CTA pairs): filled from profiles/r02_scan_tc2_filter_pair.summary.txt once captured (None = no capture of this kernel yet)
+       "filt256p": {"traffic_per_pass": None, "source": None, "tensor_pipe_pct": None},
        # int8 full scan of 1M x 768, 1024 queries = 8 passes in one launch: (6.2222 GB read + 219.8 MB written) / 8
        "scan_tc_i8": {"traffic_per_pass": 0.8052e9, "source": "profiles/r02_scan_tc_i8.summary.txt"},
        # lex_score<OR>, C3 10M docs, 4096 queries, Topk: 6.8986 GB read + 60.6 MB written (random 32-byte sector probes of the
@@ -309,7 +311,7 @@ def measure_vector_kernel(a, ix, kname, q_host, q_dev, keys, local_rows, rank, w
         "gpu_launches": int(launches) * a.steps, "queries_per_pass": qt, "passes_per_step": passes, "kernel_desc": klong,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     "traffic": (ncu["traffic_per_pass"] * passes * local_rows / 1e6) if (ncu and a.dims == C2_DIMS) else None,
+                     "traffic": (ncu["traffic_per_pass"] * passes * local_rows / 1e6) if (ncu and ncu.get("traffic_per_pass") and a.dims == C2_DIMS) else None,
                      "traffic_source": ncu.get("source"), "peak_kind": f"of {peak_kind}", "kernel": kshort, "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "tensor": tensor,
                      **({"f32_equivalent_gbs": float(local_rows) * a.dims * 4 * passes / (kern_ms / 1e3) / 1e9 if kern_ms else None,
@@ -339,7 +341,7 @@ def bench_vector(a, rank, world, out):
     q_host = synth.gen_vectors(a.batch, a.dims, 2002, "cpu").pin_memory()
     q_dev = q_host.to(dev)
     keys = torch.zeros((a.batch, 32), dtype=torch.int64, device=dev)
-    names = ["ffma", "tcb", "tcb256", "filt", "filt256"] if a.vector_kernel in ("both", "all") else [a.vector_kernel]
+    names = ["ffma", "tcb", "tcb256", "filt", "filt256", "filt256p"] if a.vector_kernel in ("both", "all") else [a.vector_kernel]
     res = {k: measure_vector_kernel(a, ix, k, q_host, q_dev, keys, local_rows, rank, world, dev, rank == 0) for k in names}
     # batch-size sweep through the reference-facing call (host buffers, AUTO kernel choice): latency at batch 1 .. 256
     sweep = {}

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 2
+#define SSB_ABI_VERSION 3
 #define SSB_K_MAX 32u            /* top-k capacity of one kernel pass (lane-distributed lists); *_keys calls */
 #define SSB_K_LIMIT 1024u        /* ssb_search_lexical / ssb_search_vector page beyond 32 internally         */
 #define SSB_MAX_QUERY_TERMS 32u  /* unique terms per lexical query (<= 4: record path; 5..32: one term per lane)  */
@@ -114,6 +114,27 @@ typedef struct {
     const uint8_t*  doc_len_bytes;    /* [n_docs];     F fields: [F][n_docs] (document_length_compressed_array[field], index.rs:770-776) */
 } ssb_level_desc;
 
+/* ---- facets and facet filters ---------------------------------------------------- */
+/* FieldType of a facet field (index.rs `FieldType`; FilterSparse search.rs:863-881).  Point (geo) filters are not built. */
+enum { SSB_FACET_U8 = 0, SSB_FACET_U16 = 1, SSB_FACET_U32 = 2, SSB_FACET_U64 = 3, SSB_FACET_I8 = 4, SSB_FACET_I16 = 5,
+       SSB_FACET_I32 = 6, SSB_FACET_I64 = 7, SSB_FACET_TIMESTAMP = 8, SSB_FACET_F32 = 9, SSB_FACET_F64 = 10,
+       SSB_FACET_STRING16 = 11, SSB_FACET_STRING32 = 12 };
+/* one facet field of the shard's facet file: its type and its byte offset inside a doc's row (`facet.offset`, add_result.rs:345) */
+typedef struct { uint32_t type; uint32_t offset; } ssb_facet_field;
+/* One filter of one query.  RANGE = Rust `Range<T>::contains`: start <= value < end, compared in the facet's own type (floats by
+ * PartialOrd: NaN is never inside).  start / end carry the bound widened to 8 bytes: unsigned types as u64, signed types and
+ * Timestamp as i64 (two's complement), F32 / F64 as the bits of the f64 value.  SET (String16 / String32) = `values.contains(id)`
+ * over filter_set_values[set_first .. set_first + set_count).  A facet without a filter entry is FilterSparse::None. */
+enum { SSB_FILTER_RANGE = 0, SSB_FILTER_SET = 1 };
+typedef struct ssb_facet_filter {
+    uint32_t facet;                   /* index into the fields given to ssb_set_facets                    */
+    uint32_t kind;                    /* SSB_FILTER_*                                                     */
+    uint64_t start, end;              /* RANGE bounds (see above)                                         */
+    uint32_t set_first, set_count;    /* SET: slice of ssb_lex_batch.filter_set_values                    */
+} ssb_facet_filter;
+#define SSB_MAX_FACETS 16u
+#define SSB_MAX_FILTERS_PER_QUERY 16u
+
 /* A batch of lexical queries, already tokenised by the host (tokenizer.rs is out of scope): unique terms
  * per query as 64-bit keys, CSR layout; at most SSB_MAX_QUERY_TERMS per query (checked for host arrays; with device
  * arrays extra terms are ignored).  Repeated keys inside a query count once, as in the reference's unique_terms. */
@@ -127,6 +148,12 @@ typedef struct {
     const uint64_t* term_keys;        /* [term_offsets[n_queries]]                                        */
     const uint8_t*  term_flags;       /* [term_offsets[n_queries]] SSB_TERM_* per term, or NULL (all positive); at most        */
                                       /* SSB_MAX_NOT_TERMS NOT terms per query                                                 */
+    /* facet filters (ABI v3; `facet_filter: Vec<FacetFilter>` of search_lexical_shard, search.rs:2427-2458, resolved to one      */
+    /* FilterSparse per facet, search.rs:863-881): HOST arrays or NULL.  A doc enters neither the top-k nor the counts unless      */
+    /* every filter of its query accepts its facet value (is_facet_filter, add_result.rs:340-478).  Needs ssb_set_facets.          */
+    const uint32_t* filter_offsets;           /* [n_queries+1] or NULL (no query is filtered)                                      */
+    const struct ssb_facet_filter* filters;   /* [filter_offsets[n_queries]]                                                       */
+    const uint64_t* filter_set_values;        /* value ids of the SSB_FILTER_SET filters (String16 / String32), or NULL            */
 } ssb_lex_batch;
 
 uint32_t    ssb_abi_version(void);
@@ -177,6 +204,15 @@ int32_t ssb_load_vector_bin(ssb_index* ix, const void* bytes, uint64_t len, uint
  * lexical path (add_result.rs:3435, union_count union.rs:975-1000) and in the vector scan (vector.rs:1450-1451).  doc_ids: host
  * array of shard-local ids (level << 16 | local); replaces the current set; n = 0 clears it.  Exclusive like a commit. */
 int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n);
+
+/* ---- facets ---------------------------------------------------------------------------------------------- */
+/* The shard's facet file (`facets_file_mmap`: one row of `facets_size_sum` bytes per doc, doc id = level << 16 | local;
+ * is_facet_filter reads `row_bytes * docid + field.offset`, add_result.rs:343-347).  rows: HOST array [n_docs * row_bytes] holding
+ * the rows of doc ids first_doc_id .. first_doc_id + n_docs (a shard of a sharded index passes the rows of its own level range).
+ * Every value is converted once into an order-preserving 64-bit key and kept as one column per facet in HBM (8 bytes per doc and
+ * facet); a doc outside the covered range fails every filter.  Replaces the current facets; n_docs = 0 clears them.  Exclusive. */
+int32_t ssb_set_facets(ssb_index* ix, const void* rows, uint64_t first_doc_id, uint64_t n_docs, uint32_t row_bytes,
+                       const ssb_facet_field* fields, uint32_t n_fields);
 
 /* ---- vector index -------------------------------------------------------------------------------- */
 /* rows: [n, dims] row-major f32 (row_stride_floats >= dims, 0 = dims); local_ids: [n] u16 or NULL (= 0..n-1).

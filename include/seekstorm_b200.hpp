@@ -13,6 +13,7 @@
 // Facets / filters / sort / uncommitted search / query rewriting / phrase queries are outside the GPU hot path and throw.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <functional>
 #include <optional>
 #include <sstream>
@@ -72,6 +73,19 @@ inline uint64_t fnv1a64(const std::string& term) {
     return h & ~7ull;
 }
 
+// `FacetFilter` (search.rs:735-860) resolved against the schema: facet = index of the facet field (order of set_facets), a Rust
+// `Range<T>` as start <= value < end with the bounds widened to 8 bytes (u64 / i64 two's complement / f64 bits — see ssb_facet_filter),
+// or the value ids of a String16 / String32 filter
+struct FacetFilter {
+    uint32_t facet = 0;
+    uint64_t start = 0, end = 0;
+    std::vector<uint64_t> values;
+    static FacetFilter range_u(uint32_t facet, uint64_t a, uint64_t b) { FacetFilter f; f.facet = facet; f.start = a; f.end = b; return f; }
+    static FacetFilter range_i(uint32_t facet, int64_t a, int64_t b) { return range_u(facet, static_cast<uint64_t>(a), static_cast<uint64_t>(b)); }
+    static FacetFilter range_f(uint32_t facet, double a, double b) { uint64_t x, y; std::memcpy(&x, &a, 8); std::memcpy(&y, &b, 8); return range_u(facet, x, y); }
+    static FacetFilter set(uint32_t facet, std::vector<uint64_t> ids) { FacetFilter f; f.facet = facet; f.values = std::move(ids); return f; }
+};
+
 class Index {
 public:
     using TermKeyFn = std::function<uint64_t(const std::string&)>;
@@ -101,6 +115,10 @@ public:
                           const uint16_t* local_ids = nullptr) {
         check(ssb_vector_add_level(h_, level_id, rows, row_stride, local_ids, n, dims));
     }
+    // the shard's facet file (facets_file_mmap): one row of row_bytes per doc id, typed fields at their offsets
+    void set_facets(const void* rows, uint64_t first_doc_id, uint64_t n_docs, uint32_t row_bytes, const std::vector<ssb_facet_field>& fields) {
+        check(ssb_set_facets(h_, rows, first_doc_id, n_docs, row_bytes, fields.data(), static_cast<uint32_t>(fields.size())));
+    }
     uint64_t indexed_doc_count() const { return indexed_doc_count_; }
     uint64_t vector_count() const { uint64_t n = 0; check(ssb_vector_count(h_, &n)); return n; }
 
@@ -108,11 +126,11 @@ public:
     ResultObject search(const std::string& query_string, const std::optional<std::vector<float>>& query_vector,
                         QueryType query_type_default, const SearchMode& search_mode, bool enable_empty_query, size_t offset,
                         size_t length, ResultType result_type, bool include_uncommitted = false,
-                        const std::vector<std::string>& field_filter = {}, size_t n_query_facets = 0, size_t n_facet_filter = 0,
-                        size_t n_result_sort = 0) const {
+                        const std::vector<std::string>& field_filter = {}, size_t n_query_facets = 0,
+                        const std::vector<FacetFilter>& facet_filter = {}, size_t n_result_sort = 0) const {
         (void)enable_empty_query;
-        if (include_uncommitted || !field_filter.empty() || n_query_facets || n_facet_filter || n_result_sort)
-            throw Error(SSB_E_UNSUPPORTED, "facets / filters / sort / uncommitted search are outside the GPU hot path");
+        if (include_uncommitted || !field_filter.empty() || n_query_facets || n_result_sort)
+            throw Error(SSB_E_UNSUPPORTED, "facet counts / field filters / sort / uncommitted search are outside the GPU hot path");
         ResultObject ro;
         ro.original_query = ro.query = query_string;
         const size_t heap = offset + length;                                   // search.rs:1708: per-shard length = offset+length
@@ -152,7 +170,18 @@ public:
             for (auto& t : terms) { keys.push_back(key_fn_(t)); flags.push_back(0); }
             for (auto& t : not_terms) { keys.push_back(key_fn_(t)); flags.push_back(SSB_TERM_NOT); }
             uint32_t offs[2] = {0, static_cast<uint32_t>(keys.size())};
-            ssb_lex_batch b{1, static_cast<uint32_t>(qt), offs, keys.data(), not_terms.empty() ? nullptr : flags.data()};
+            ssb_lex_batch b{1, static_cast<uint32_t>(qt), offs, keys.data(), not_terms.empty() ? nullptr : flags.data(), nullptr, nullptr, nullptr};
+            // facet_filter (search.rs:735-860 -> FilterSparse per facet): applied to every candidate of the lexical search
+            std::vector<ssb_facet_filter> ff; std::vector<uint64_t> set_values;
+            uint32_t foffs[2] = {0, static_cast<uint32_t>(facet_filter.size())};
+            for (auto& f : facet_filter) {
+                ssb_facet_filter c{};
+                c.facet = f.facet; c.kind = f.values.empty() ? SSB_FILTER_RANGE : SSB_FILTER_SET; c.start = f.start; c.end = f.end;
+                c.set_first = static_cast<uint32_t>(set_values.size()); c.set_count = static_cast<uint32_t>(f.values.size());
+                set_values.insert(set_values.end(), f.values.begin(), f.values.end());
+                ff.push_back(c);
+            }
+            if (!ff.empty()) { b.filter_offsets = foffs; b.filters = ff.data(); b.filter_set_values = set_values.data(); }
             const uint32_t k = rt == ResultType::Count ? 0u : static_cast<uint32_t>(heap);
             lex.resize(k ? k : 1);
             uint32_t n = 0;

@@ -22,6 +22,15 @@ class OrcHit(C.Structure):
     _fields_ = [("doc_id", C.c_uint64), ("score", C.c_float), ("pad", C.c_uint32)]
 
 
+class OrcFacetField(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("offset", C.c_uint32)]
+
+
+class OrcFacetFilter(C.Structure):
+    _fields_ = [("facet", C.c_uint32), ("kind", C.c_uint32), ("start", C.c_uint64), ("end", C.c_uint64),
+                ("set_first", C.c_uint32), ("set_count", C.c_uint32)]
+
+
 class OrcLevel(C.Structure):
     _fields_ = [("level_id", C.c_uint32), ("n_docs", C.c_uint32), ("n_terms", C.c_uint32),
                 ("reserved", C.c_uint32), ("term_keys", C.c_void_p), ("posting_offsets", C.c_void_p),
@@ -65,6 +74,9 @@ def lib():
                           C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_search_lexical_not.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                              C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_index_set_facets.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.orc_search_lexical_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                  C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_normalize_f32.argtypes = [C.c_void_p, C.c_uint32]
         for f in (L.orc_dot_f32, L.orc_dot_f32_lanes8, L.orc_euclidean_f32):
             f.restype = C.c_float
@@ -137,11 +149,26 @@ class OracleIndex:
     def df(self, key: int) -> int:
         return lib().orc_index_df(self._h, C.c_uint64(key))
 
-    def search(self, term_keys, query_type, k, result_type, pruned=False, not_keys=None):
+    def set_facets(self, rows: np.ndarray, fields, first_doc_id: int, n_docs: int, row_bytes: int):
+        """the shard's facet file: rows [n_docs, row_bytes] u8, fields = [(type, offset), ...] (same values as the C-ABI)"""
+        fa = (OrcFacetField * max(len(fields), 1))(*[OrcFacetField(int(t), int(o)) for t, o in fields])
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        assert lib().orc_index_set_facets(self._h, _ptr(rows), first_doc_id, n_docs, row_bytes, fa, len(fields)) == 0
+
+    def search(self, term_keys, query_type, k, result_type, pruned=False, not_keys=None, filters=None, set_values=None):
+        """filters: [(facet, kind, start_u64, end_u64, set_first, set_count), ...] in the C-ABI's encoding; set_values: the SET filters' ids"""
         keys = np.ascontiguousarray(np.array(term_keys, dtype=np.uint64))
         buf = (OrcHit * max(k, 1))()
         n = C.c_uint32(0)
         tot = C.c_uint64(0)
+        if filters:
+            nk = np.ascontiguousarray(np.array(not_keys if not_keys else [0], dtype=np.uint64))
+            fa = (OrcFacetFilter * len(filters))(*[OrcFacetFilter(*[int(x) for x in f]) for f in filters])
+            sv = np.ascontiguousarray(np.array(set_values if set_values is not None and len(set_values) else [0], dtype=np.uint64))
+            rc = lib().orc_search_lexical_filtered(self._h, _ptr(keys), len(keys), _ptr(nk), len(not_keys) if not_keys else 0, fa, len(filters), _ptr(sv),
+                                                   query_type, k, result_type, buf, C.byref(n), C.byref(tot))
+            assert rc == 0, rc
+            return _hits_to_list(buf, n.value), int(tot.value)
         if not_keys:
             nk = np.ascontiguousarray(np.array(not_keys, dtype=np.uint64))
             rc = lib().orc_search_lexical_not(self._h, _ptr(keys), len(keys), _ptr(nk), len(nk), query_type, k, result_type, buf, C.byref(n), C.byref(tot))

@@ -85,6 +85,9 @@ struct orc_index {
     uint32_t n_fields;            /* indexed fields (0 / 1 = single field) */
     float boost[ORC_MAX_FIELDS];  /* indexed_schema_vec[f].boost (add_result.rs:1258) */
     uint64_t* deleted; uint64_t n_deleted;   /* shard.delete_hashset, sorted (add_result.rs:3435) */
+    /* facets_file_mmap: one row of row_bytes per doc id (facet_first_doc + row), typed fields at their offsets (add_result.rs:343-347) */
+    uint8_t* facet_rows; uint64_t facet_n_docs, facet_first_doc; uint32_t facet_row_bytes, n_facets;
+    orc_facet_field facet_fields[ORC_MAX_FACETS];
 };
 
 orc_index* orc_index_new(void) { return (orc_index*)calloc(1, sizeof(orc_index)); }
@@ -106,7 +109,7 @@ void orc_index_free(orc_index* ix) {
         free(l->term_keys); free(l->posting_offsets); free(l->doc_ids); free(l->tfs);
         free(l->doc_len_bytes); free(l->max_comp);
     }
-    free(ix->levels); free(ix->dict); free(ix->deleted); free(ix);
+    free(ix->levels); free(ix->dict); free(ix->deleted); free(ix->facet_rows); free(ix);
 }
 
 static int cmp_u64(const void* a, const void* b) { uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b; return x < y ? -1 : (x > y); }
@@ -123,6 +126,53 @@ static inline int is_deleted(const orc_index* ix, uint64_t doc) {
     uint64_t lo = 0, hi = ix->n_deleted;
     while (lo < hi) { uint64_t m = (lo + hi) / 2; if (ix->deleted[m] < doc) lo = m + 1; else hi = m; }
     return lo < ix->n_deleted && ix->deleted[lo] == doc;
+}
+
+/* the shard's facet file (copied) */
+int orc_index_set_facets(orc_index* ix, const void* rows, uint64_t first_doc_id, uint64_t n_docs, uint32_t row_bytes,
+                         const orc_facet_field* fields, uint32_t n_fields) {
+    if (!ix || n_fields > ORC_MAX_FACETS) return -1;
+    free(ix->facet_rows); ix->facet_rows = NULL; ix->facet_n_docs = 0; ix->n_facets = 0;
+    if (!n_docs || !n_fields) return 0;
+    ix->facet_rows = (uint8_t*)malloc((size_t)n_docs * row_bytes); memcpy(ix->facet_rows, rows, (size_t)n_docs * row_bytes);
+    ix->facet_n_docs = n_docs; ix->facet_first_doc = first_doc_id; ix->facet_row_bytes = row_bytes; ix->n_facets = n_fields;
+    memcpy(ix->facet_fields, fields, n_fields * sizeof(orc_facet_field));
+    return 0;
+}
+
+/* is_facet_filter (add_result.rs:340-478): 1 = the doc is filtered OUT.  One typed read + `!range.contains(&value)` (Rust Range<T>:
+ * start <= x && x < end; floats by PartialOrd, so NaN is never contained) or `!values.contains(&id)` per filtered facet, each in the
+ * facet's own C type — deliberately NOT the order-preserving-key trick of the product. */
+#define ORC_RANGE_CASE(T, ST) { T x; ST a, b; memcpy(&x, p, sizeof(T)); memcpy(&a, &f->start, 8); memcpy(&b, &f->end, 8); if (!((ST)x >= a && (ST)x < b)) return 1; break; }
+static int is_facet_filter(const orc_index* ix, const orc_facet_filter* fl, uint32_t n_fl, const uint64_t* set_values, uint64_t doc) {
+    if (doc < ix->facet_first_doc || doc - ix->facet_first_doc >= ix->facet_n_docs) return 1;
+    const uint8_t* row = ix->facet_rows + (size_t)(doc - ix->facet_first_doc) * ix->facet_row_bytes;
+    for (uint32_t i = 0; i < n_fl; i++) {
+        const orc_facet_filter* f = &fl[i];
+        const uint8_t* p = row + ix->facet_fields[f->facet].offset;
+        switch (ix->facet_fields[f->facet].type) {
+            case ORC_FACET_U8:  ORC_RANGE_CASE(uint8_t, uint64_t)
+            case ORC_FACET_U16: ORC_RANGE_CASE(uint16_t, uint64_t)
+            case ORC_FACET_U32: ORC_RANGE_CASE(uint32_t, uint64_t)
+            case ORC_FACET_U64: ORC_RANGE_CASE(uint64_t, uint64_t)
+            case ORC_FACET_I8:  ORC_RANGE_CASE(int8_t, int64_t)
+            case ORC_FACET_I16: ORC_RANGE_CASE(int16_t, int64_t)
+            case ORC_FACET_I32: ORC_RANGE_CASE(int32_t, int64_t)
+            case ORC_FACET_I64: case ORC_FACET_TIMESTAMP: ORC_RANGE_CASE(int64_t, int64_t)
+            case ORC_FACET_F32: ORC_RANGE_CASE(float, double)     /* f32 -> f64 is exact and order-preserving; the bounds arrive as f64 */
+            case ORC_FACET_F64: ORC_RANGE_CASE(double, double)
+            case ORC_FACET_STRING16: case ORC_FACET_STRING32: {
+                uint64_t id;
+                if (ix->facet_fields[f->facet].type == ORC_FACET_STRING16) { uint16_t x; memcpy(&x, p, 2); id = x; } else { uint32_t x; memcpy(&x, p, 4); id = x; }
+                int in = 0;
+                for (uint32_t s = 0; s < f->set_count; s++) if (set_values[f->set_first + s] == id) in = 1;
+                if (!in) return 1;
+                break;
+            }
+            default: return 1;
+        }
+    }
+    return 0;
 }
 
 static void* dup_mem(const void* p, size_t n) {
@@ -254,14 +304,24 @@ static int64_t term_in_level(const orc_index* ix, const qterm_t* q, uint32_t li)
 int orc_search_lexical(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, uint32_t query_type,
                        uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
                        uint64_t* count_total) {
-    return orc_search_lexical_not(ix, keys, n_terms, NULL, 0, query_type, k, result_type, hits, n_hits, count_total);
+    return orc_search_lexical_filtered(ix, keys, n_terms, NULL, 0, NULL, 0, NULL, query_type, k, result_type, hits, n_hits, count_total);
 }
 
 /* same with NOT terms ('-' operator, not_query_list add_result.rs:3440-3496): a doc that contains any of them is neither scored nor counted */
 int orc_search_lexical_not(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, const uint64_t* not_keys, uint32_t n_not,
                            uint32_t query_type, uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
                            uint64_t* count_total) {
+    return orc_search_lexical_filtered(ix, keys, n_terms, not_keys, n_not, NULL, 0, NULL, query_type, k, result_type, hits, n_hits, count_total);
+}
+
+/* ... and with facet filters (facet_filter, add_result.rs:3498-3500: after the delete set and the NOT lists, before counting and scoring) */
+int orc_search_lexical_filtered(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, const uint64_t* not_keys, uint32_t n_not,
+                                const orc_facet_filter* filters, uint32_t n_filters, const uint64_t* set_values,
+                                uint32_t query_type, uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
+                                uint64_t* count_total) {
     if (!ix || !ix->committed || n_terms > ORC_MAX_TERMS || n_not > ORC_MAX_TERMS) return -1;
+    if (n_filters && !ix->n_facets) return -1;
+    for (uint32_t i = 0; i < n_filters; i++) if (filters[i].facet >= ix->n_facets) return -1;
     if (n_hits) *n_hits = 0;
     if (count_total) *count_total = 0;
     if (n_terms == 0) return 0;
@@ -328,6 +388,7 @@ int orc_search_lexical_not(const orc_index* ix, const uint64_t* keys, uint32_t n
             int match = query_type == ORC_QUERY_INTERSECTION ? (cnt[d] == n_live) : (cnt[d] > 0);
             if (!match || excl[d]) continue;
             if (ix->n_deleted && is_deleted(ix, ((uint64_t)l->level_id << 16) | d)) continue;
+            if (n_filters && is_facet_filter(ix, filters, n_filters, set_values, ((uint64_t)l->level_id << 16) | d)) continue;
             total++;
             if (kk) topk_push(&tk, ((uint64_t)l->level_id << 16) | d, acc[d]);
         }

@@ -84,6 +84,22 @@ int orc_search_lexical_not(const orc_index*, const uint64_t* term_keys, uint32_t
                            uint32_t query_type, uint32_t k, uint32_t result_type,
                            orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
 
+/* ---- facets and facet filters (same values as include/seekstorm_b200.h): the shard's facet file + FilterSparse per facet
+ * (search.rs:863-881), applied by is_facet_filter (add_result.rs:340-478).  Honoured by the EXHAUSTIVE search only. */
+enum { ORC_FACET_U8 = 0, ORC_FACET_U16, ORC_FACET_U32, ORC_FACET_U64, ORC_FACET_I8, ORC_FACET_I16, ORC_FACET_I32, ORC_FACET_I64,
+       ORC_FACET_TIMESTAMP, ORC_FACET_F32, ORC_FACET_F64, ORC_FACET_STRING16, ORC_FACET_STRING32 };
+enum { ORC_FILTER_RANGE = 0, ORC_FILTER_SET = 1 };
+#define ORC_MAX_FACETS 16
+typedef struct { uint32_t type; uint32_t offset; } orc_facet_field;
+/* start / end: the Range<T> bounds widened to 8 bytes (u64 / i64 / f64 bits); SET: set_values[set_first .. +set_count) */
+typedef struct { uint32_t facet, kind; uint64_t start, end; uint32_t set_first, set_count; } orc_facet_filter;
+int orc_index_set_facets(orc_index*, const void* rows, uint64_t first_doc_id, uint64_t n_docs, uint32_t row_bytes,
+                         const orc_facet_field* fields, uint32_t n_fields);
+int orc_search_lexical_filtered(const orc_index*, const uint64_t* term_keys, uint32_t n_terms, const uint64_t* not_keys, uint32_t n_not,
+                                const orc_facet_filter* filters, uint32_t n_filters, const uint64_t* set_values,
+                                uint32_t query_type, uint32_t k, uint32_t result_type,
+                                orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
+
 /* Reference-shaped search: block-max ordered, heap-pruned, same control flow as
  * single.rs:292-417, intersection.rs:2023-2301, union.rs:1168-1479.  Used as the timed CPU baseline
  * ("port") and cross-checked against the exhaustive search in tests. */

@@ -4,9 +4,9 @@ Index::search(): BM25 AND/OR top-k and the brute-force f32 vector scan (+ RRF hy
 The compute lives in libseekstorm_b200.so (hand-written CUDA, C-ABI in include/seekstorm_b200.h);
 this package is the host-side mirror of the reference's search interface.  No CPU fallback.
 """
-from .index import (AnnMode, Index, QueryType, Result, ResultObject, ResultType, SearchMode, VectorSimilarity,
+from .index import (AnnMode, FacetFilter, Index, QueryType, Result, ResultObject, ResultType, SearchMode, VectorSimilarity,
                     synthetic_term_key)
 from ._lib import SsbError, lib, LIB_PATH
 
-__all__ = ["AnnMode", "Index", "QueryType", "Result", "ResultObject", "ResultType", "SearchMode",
+__all__ = ["AnnMode", "FacetFilter", "Index", "QueryType", "Result", "ResultObject", "ResultType", "SearchMode",
            "VectorSimilarity", "SsbError", "lib", "LIB_PATH", "synthetic_term_key"]

@@ -55,7 +55,23 @@ class SsbLevelDesc(C.Structure):
 
 class SsbLexBatch(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("query_type", C.c_uint32), ("term_offsets", C.c_void_p),
-                ("term_keys", C.c_void_p), ("term_flags", C.c_void_p)]
+                ("term_keys", C.c_void_p), ("term_flags", C.c_void_p),
+                ("filter_offsets", C.c_void_p), ("filters", C.c_void_p), ("filter_set_values", C.c_void_p)]
+
+
+class SsbFacetField(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("offset", C.c_uint32)]
+
+
+class SsbFacetFilter(C.Structure):
+    _fields_ = [("facet", C.c_uint32), ("kind", C.c_uint32), ("start", C.c_uint64), ("end", C.c_uint64),
+                ("set_first", C.c_uint32), ("set_count", C.c_uint32)]
+
+
+# SSB_FACET_* (FieldType of a facet field) and SSB_FILTER_*
+FACET_U8, FACET_U16, FACET_U32, FACET_U64, FACET_I8, FACET_I16, FACET_I32, FACET_I64, FACET_TIMESTAMP, FACET_F32, FACET_F64, \
+    FACET_STRING16, FACET_STRING32 = range(13)
+FILTER_RANGE, FILTER_SET = 0, 1
 
 
 class SsbStats(C.Structure):
@@ -69,7 +85,7 @@ class SsbStats(C.Structure):
 EXPORTS = [
     "ssb_abi_version", "ssb_last_error", "ssb_create", "ssb_destroy", "ssb_lexical_add_level",
     "ssb_vector_add_level_clustered", "ssb_lexical_set_field_boosts", "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
-    "ssb_load_index_bin", "ssb_load_vector_bin", "ssb_index_bin_inspect", "ssb_set_deleted", "ssb_vector_add_level", "ssb_vector_count", "ssb_vector_reserve", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_vector_ex", "ssb_search_hybrid",
+    "ssb_load_index_bin", "ssb_load_vector_bin", "ssb_index_bin_inspect", "ssb_set_deleted", "ssb_set_facets", "ssb_vector_add_level", "ssb_vector_count", "ssb_vector_reserve", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_vector_ex", "ssb_search_hybrid",
     "ssb_rrf_fuse", "ssb_comm_unique_id", "ssb_comm_init", "ssb_comm_attach", "ssb_comm_destroy", "ssb_lexical_sync_df",
     "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
     "ssb_stream", "ssb_set_stream", "ssb_last_stats",
@@ -108,6 +124,7 @@ def lib():
         "ssb_load_vector_bin": [vp, vp, u64, C.POINTER(u64)],
         "ssb_index_bin_inspect": [vp, u64, C.POINTER(SsbIndexBinParams), vp],
         "ssb_set_deleted": [vp, vp, u64],
+        "ssb_set_facets": [vp, vp, u64, u64, u32, vp, u32],
         "ssb_vector_count": [vp, C.POINTER(u64)],
         "ssb_vector_reserve": [vp, u64],
         "ssb_set_vector_kernel": [vp, u32],

@@ -102,6 +102,7 @@ struct ssb_index {
     std::mutex stats_mu; SearchCtx* last_ctx = nullptr; ssb_stats last_stats{};
     LexIndex* lex = nullptr;
     DeleteSet del;                    // shard.delete_hashset mirrored on the device (ssb_set_deleted)
+    FacetSet facets;                  // the shard's facet file as one key column per facet (ssb_set_facets)
     ShardComm comm;                   // set: this handle is one shard of a `world`-way sharded index (one process per GPU)
     // vector index
     uint32_t dims = 0, dpad = 0, dpad8 = 0;
@@ -473,6 +474,7 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     ix->lex = new (std::nothrow) LexIndex(ix->load_st, ix->n_sms, ix->cfg.max_batch);
     if (!ix->lex) { cudaStreamDestroy(ix->load_st); set_error("out of host memory"); return SSB_E_NOMEM; }
     ix->lex->set_deleted(&ix->del);
+    ix->lex->set_facets(&ix->facets);
     ix->dims = cfg->vector_dims;
     ix->dpad = (cfg->vector_dims + 31) / 32 * 32;
     ix->dpad8 = (cfg->vector_dims + 127) / 128 * 128;
@@ -493,6 +495,7 @@ int32_t ssb_destroy(ssb_index* ix) {
         delete ix->lex; ix->lex = nullptr;
         comm_destroy(ix->comm);
         ix->del.release();
+        ix->facets.release();
         ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->row_scale.release(); ix->row_norm.release(); ix->doc_ids.release();
         cudaStreamDestroy(ix->load_st);
     }
@@ -781,6 +784,40 @@ int32_t ssb_set_deleted(ssb_index* ix, const uint64_t* doc_ids, uint64_t n) {
     SSB_CUDA_TRY(cudaMemcpy(ix->del.d_words, words.data(), words.size() * 8, cudaMemcpyHostToDevice));
     SSB_CUDA_TRY(cudaMemcpy(ix->del.d_docs, docs.data(), docs.size() * 4, cudaMemcpyHostToDevice));
     ix->del.n = (uint32_t)docs.size();
+    return SSB_OK;
+    SSB_API_END
+}
+
+// facets_file_mmap (is_facet_filter, add_result.rs:340-478, reads `facets_size_sum * docid + facet.offset`): every value becomes an
+// order-preserving 64-bit key, one column per facet, so the kernels test any FilterSparse range with two unsigned compares.
+int32_t ssb_set_facets(ssb_index* ix, const void* rows, uint64_t first_doc_id, uint64_t n_docs, uint32_t row_bytes,
+                       const ssb_facet_field* fields, uint32_t n_fields) {
+    SSB_API_BEGIN
+    if (!ix) { set_error("ssb_set_facets: null index"); return SSB_E_INVALID; }
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    for (auto& c : ix->pool) cudaStreamSynchronize(c->own_st);
+    ix->facets.release();
+    if (n_docs == 0 || n_fields == 0) return SSB_OK;
+    if (!rows || !fields) { set_error("ssb_set_facets: null argument"); return SSB_E_INVALID; }
+    if (n_fields > SSB_MAX_FACETS) { set_error("ssb_set_facets: more than %u facets", SSB_MAX_FACETS); return SSB_E_UNSUPPORTED; }
+    if (first_doc_id + n_docs > (1ull << 32)) { set_error("ssb_set_facets: doc ids must be < 2^32"); return SSB_E_INVALID; }
+    for (uint32_t f = 0; f < n_fields; f++) {
+        const uint32_t w = facet_type_bytes(fields[f].type);
+        if (!w) { set_error("ssb_set_facets: field %u has unsupported type %u (Point facets are not built)", f, fields[f].type); return SSB_E_UNSUPPORTED; }
+        if ((uint64_t)fields[f].offset + w > row_bytes) { set_error("ssb_set_facets: field %u does not fit a %u-byte row", f, row_bytes); return SSB_E_INVALID; }
+    }
+    std::vector<uint64_t> keys((size_t)n_fields * n_docs);
+    const uint8_t* base = (const uint8_t*)rows;
+    for (uint32_t f = 0; f < n_fields; f++) {
+        uint64_t* col = keys.data() + (size_t)f * n_docs;
+        const uint32_t type = fields[f].type, off = fields[f].offset;
+        for (uint64_t d = 0; d < n_docs; d++) col[d] = facet_value_key(type, base + d * row_bytes + off);
+    }
+    SSB_CUDA_TRY(cudaMalloc(&ix->facets.d_keys, keys.size() * 8));
+    SSB_CUDA_TRY(cudaMemcpy(ix->facets.d_keys, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
+    ix->facets.n_rows = n_docs; ix->facets.first_doc = (uint32_t)first_doc_id; ix->facets.n_facets = n_fields;
+    for (uint32_t f = 0; f < n_fields; f++) ix->facets.types[f] = (uint8_t)fields[f].type;
     return SSB_OK;
     SSB_API_END
 }

@@ -239,7 +239,7 @@ __device__ __forceinline__ uint32_t meta_cperm(uint32_t m, uint32_t c) { return 
 // block bound), the in-query-order suffix sums S[p] / R[p], the count order, the AND driver — and writes them as one
 // 128-byte record.  Thread 0 finally cuts the sorted record list into work items.
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
-                                                const uint8_t* __restrict__ q_flags /*or null*/, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
+                                                const uint8_t* __restrict__ q_flags /*or null*/, const uint32_t* __restrict__ f_off /*or null*/, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
                                                 uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2,
                                                 uint32_t item_w, uint32_t first_lim, uint32_t gmax) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -288,6 +288,9 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         // search.rs:3290-3296: AND with an unknown term -> empty result; OR drops the term
         if (query_type == SSB_QUERY_INTERSECTION && missing) nl = 0;
         pl.n_live = nl; pl.n_items = 0; pl.n_recs = 0; pl.n_not = nl ? nn : 0;
+        // facet filters: such a query is scored and counted by the one-term-per-lane kernel, which enumerates every match
+        pl.filt_first = f_off ? f_off[q] : 0u; pl.n_filt = f_off ? f_off[q + 1] - f_off[q] : 0u; pl.pad = 0;
+        pl.fast = (nl <= v.fast_t && pl.n_filt == 0) ? 1u : 0u;
     }
     for (uint32_t b = threadIdx.x; b < nlv; b += blockDim.x) {
         bound[b] = 0.f; cnt[b] = 0;
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
     }
     __syncthreads();
     const uint32_t nl = pl.n_live;
+    const bool fastq = pl.fast != 0;
     for (uint32_t t = 0; t < nl; t++) {   // QUERY ORDER: the bound is summed exactly like a score would be
         const QTerm qt = pl.t[t];
         for (uint32_t e = threadIdx.x; e < qt.n; e += blockDim.x) {
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         for (uint32_t s = 0; s < FAST_T; s++) {
             LvSlot sl; sl.off_lo = 0; sl.offhi_cnt = 0; sl.bmi = NONE; sl.ub = 0.f;
             float idf = 0.f;
-            if (s < nl && nl <= v.fast_t) {
+            if (s < nl && fastq) {
                 const QTerm qt = pl.t[s];
                 idf = qt.idf;
                 const uint32_t er = ent[s * nlv + lv];
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             }
             r.t[s] = sl; r.idf[s] = idf;
         }
-        if (nl <= v.fast_t) {
+        if (fastq) {
             const uint32_t cs[4] = {c0, c1, c2, c3}; const float us[4] = {u0, u1, u2, u3};
             uint32_t np = 0, rank[4], crank[4];
 #pragma unroll
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         pl.n_items = ni; pl.n_recs = nv;
         plans[q] = pl;
         atomicMax(&ctr[1], ni);
-        if (pl.n_live > v.fast_t) atomicOr(&ctr[4], 1u);
+        if (!pl.fast) atomicOr(&ctr[4], 1u);
         if (pl.n_not) atomicOr(&ctr[5], 1u);
     }
 }
@@ -505,6 +509,29 @@ __device__ __forceinline__ bool in_not_lists(const LexView& v, const QueryPlan* 
     return in_not_lists_impl(not_view(v), pl, n_not, lv, d);
 }
 
+// is_facet_filter (add_result.rs:340-478): true = the doc is filtered OUT.  The typed range / set tests of the reference run on the
+// order-preserving 64-bit keys ssb_set_facets stored per doc and facet (bounds converted the same way by the host), so one unsigned
+// compare pair covers every FilterSparse range type.  Out of line, by value, on the rare candidate / count path of lex_generic only.
+struct FacetArgs { const uint64_t* keys; uint64_t rows; const FiltDev* filt; const uint64_t* sets; uint32_t first_doc; };
+__device__ __noinline__ bool facet_rejects_impl(FacetArgs a, uint32_t f0, uint32_t nf, uint32_t doc) {
+    const uint64_t row = (uint64_t)doc - a.first_doc;
+    if (doc < a.first_doc || row >= a.rows) return true;             // no facet row for this doc
+    for (uint32_t i = 0; i < nf; i++) {
+        const FiltDev f = a.filt[f0 + i];
+        const uint64_t key = __ldg(&a.keys[(size_t)f.facet * a.rows + row]);
+        if (f.kind == FILT_RANGE) { if (!(key >= f.lo && key < f.hi)) return true; }
+        else if (f.kind == FILT_SET) {
+            bool in = false;
+            for (uint32_t s = 0; s < f.set_n; s++) in = in || __ldg(&a.sets[f.set_first + s]) == key;
+            if (!in) return true;
+        } else return true;
+    }
+    return false;
+}
+__device__ __forceinline__ bool facet_rejects(const LexView& v, uint32_t f0, uint32_t nf, uint32_t doc) {
+    return facet_rejects_impl(FacetArgs{v.facet_keys, v.facet_rows, v.filt, v.filt_sets, v.facet_first_doc}, f0, nf, doc);
+}
+
 __device__ __forceinline__ float bound_of_word(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bool cand, float score, uint32_t doc,
@@ -523,7 +550,7 @@ __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bo
 }
 
 struct ItemCtx {
-    uint32_t q, lv, n, k, docbase, bound_ord, n_not;
+    uint32_t q, lv, n, k, docbase, bound_ord, n_not, n_filt, filt_first;
     uint64_t ceil;
     bool scoring, need_count, is_and;
 };
@@ -1021,6 +1048,13 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                 ok = ok && found;
                 if (ok && c.scoring) score = acc_term(v, score, ti, to + rank);
             }
+            if (c.n_filt) {
+                // a filtered query is counted here doc by doc: filter, delete set and NOT lists at once (the correction kernels skip it)
+                ok = ok && !facet_rejects(v, c.filt_first, c.n_filt, c.docbase | d) && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d));
+                matches += __popc(__ballot_sync(FULL, ok));
+                if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
+                continue;
+            }
             matches += __popc(__ballot_sync(FULL, ok));
             if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
         }
@@ -1066,7 +1100,8 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                         else score = acc_term(v, score, ti, to + rank);
                     }
                 }
-                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
+                insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d))
+                                              && !(c.n_filt && facet_rejects(v, c.filt_first, c.n_filt, c.docbase | d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
             }
         }
     }
@@ -1081,7 +1116,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
             const int drv = __ffs(__ballot_sync(FULL, crk == p)) - 1;
             const uint32_t dcnt = __shfl_sync(FULL, tr.cnt, drv);
             if (dcnt == 0) break;
-            if (p == 0) { matches += dcnt; continue; }
+            if (p == 0 && !c.n_filt) { matches += dcnt; continue; }
             const uint64_t doff = shfl64(tr.off, drv);
             st_visited += dcnt;
             for (uint32_t base = 0; base < dcnt; base += 32) {
@@ -1096,7 +1131,10 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                     uint32_t rank; st_probes++;
                     if (probe(v, tc, to, tb, d, rank)) dup = true;
                 }
-                matches += __popc(__ballot_sync(FULL, active && !dup));
+                bool cnt_ok = active && !dup;
+                if (c.n_filt && cnt_ok)      // filtered query: every match is tested here (filter, delete set, NOT lists; the correction kernels skip it)
+                    cnt_ok = !facet_rejects(v, c.filt_first, c.n_filt, c.docbase | d) && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d));
+                matches += __popc(__ballot_sync(FULL, cnt_ok));
             }
         }
     }
@@ -1115,7 +1153,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
 constexpr uint32_t ITEM_CHUNK = 8;
 template <bool FAST, class SM>
 __device__ __forceinline__ bool next_item(SM& it, uint32_t* counter, uint64_t total, uint32_t nq, const QueryPlan* __restrict__ plans,
-                                          int lane, uint32_t& j, uint32_t& q, const uint32_t fast_t = FAST_T) {
+                                          int lane, uint32_t& j, uint32_t& q) {
     unsigned mask = it.it_mask; uint32_t base = it.it_base;      // warp-private shared memory: keeps two registers out of the hot loops
     __syncwarp();
     while (!mask) {
@@ -1128,7 +1166,7 @@ __device__ __forceinline__ bool next_item(SM& it, uint32_t* counter, uint64_t to
         if (ok) {
             const uint32_t jj = (uint32_t)(i / nq), qq = (uint32_t)(i - (uint64_t)jj * nq);
             const QueryPlan* pl = &plans[qq];
-            ok = jj < __ldg(&pl->n_items) && ((__ldg(&pl->n_live) <= fast_t) == FAST);
+            ok = jj < __ldg(&pl->n_items) && ((__ldg(&pl->fast) != 0u) == FAST);
         }
         mask = __ballot_sync(FULL, ok); base = b;
     }
@@ -1260,7 +1298,7 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
     uint32_t j, q;
     if (lane == 0) { w.it_mask = 0; w.it_base = 0; }
     __syncwarp();
-    while (next_item<false>(w, &ctr[3], total, nq, plans, lane, j, q, v.fast_t)) {
+    while (next_item<false>(w, &ctr[3], total, nq, plans, lane, j, q)) {
         const QueryPlan* pl = &plans[q];
         const uint32_t n_live = __ldg(&pl->n_live);
         const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
@@ -1271,6 +1309,7 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
         for (uint32_t ri = 0; ri < nrec; ri++) {
             ItemCtx c;
             c.ceil = ceil; c.q = q; c.n = n_live; c.k = k; c.lv = w.recs[ri].lv; c.bound_ord = ord_f32(w.recs[ri].bound); c.n_not = __ldg(&pl->n_not);
+            c.n_filt = __ldg(&pl->n_filt); c.filt_first = __ldg(&pl->filt_first);
             c.scoring = want_topk && c.bound_ord >= thr;
             c.need_count = need_count; c.is_and = query_type == SSB_QUERY_INTERSECTION; c.docbase = w.recs[ri].docbase;
             if (!c.scoring && !need_count) { st_skipped++; continue; }
@@ -1304,7 +1343,7 @@ __global__ void __launch_bounds__(256) lex_not_count(LexView v, const QueryPlan*
         const uint32_t q = (uint32_t)(it / v.n_levels), lv = (uint32_t)(it % v.n_levels);
         const QueryPlan* pl = &plans[q];
         const uint32_t n_not = pl->n_not, n = pl->n_live;
-        if (!n_not || !n) continue;
+        if (!n_not || !n || pl->n_filt) continue;                      // filtered queries were counted doc by doc in lex_generic
         const uint32_t docbase = __ldg(&v.level_ids[lv]) << 16;
         uint32_t sub = 0;
         for (uint32_t i = 0; i < n_not; i++) {
@@ -1345,7 +1384,7 @@ __global__ void lex_del_count(LexView v, const QueryPlan* __restrict__ plans, ui
     const uint32_t q = (uint32_t)(i / v.n_del), doc = __ldg(&v.del_docs[i % v.n_del]);
     const QueryPlan* pl = &plans[q];
     const uint32_t n = pl->n_live;
-    if (n == 0) return;
+    if (n == 0 || pl->n_filt) return;                               // (filtered queries were counted doc by doc in lex_generic)
     uint32_t lo = 0, hi = v.n_levels;                               // local level index of the doc's level id
     const uint32_t lid = doc >> 16, d = doc & 0xFFFFu;
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(&v.level_ids[m]) < lid) lo = m + 1; else hi = m; }
@@ -1392,7 +1431,8 @@ void LexIndex::free_committed() {
 
 void LexWorkspace::release() {
     cudaFree(plans); cudaFree(recs); cudaFree(item_start); cudaFree(theta); cudaFree(lock); cudaFree(count); cudaFree(ctr);
-    cudaFree(qoff); cudaFree(qkeys); cudaFree(qflags); cudaFree(stats);
+    cudaFree(qoff); cudaFree(qkeys); cudaFree(qflags); cudaFree(stats); cudaFree(foff); cudaFree(filt); cudaFree(fsets);
+    foff = nullptr; filt = nullptr; fsets = nullptr; cap_filt = cap_fsets = 0;
     qflags = nullptr; plans = nullptr; recs = nullptr; item_start = nullptr; theta = nullptr; lock = nullptr; count = nullptr; ctr = nullptr;
     qoff = nullptr; qkeys = nullptr; stats = nullptr; cap_q = cap_terms = cap_levels = 0;
 }
@@ -1533,6 +1573,7 @@ LexView LexIndex::view() const {
     v.payf = payf_.p; v.compf = compf_.p; v.n_fields = n_fields_; v.fast_t = n_fields_ > 1 ? 0u : FAST_T;
     for (int f = 0; f < 4; f++) v.boost[f] = boosts_[f];
     if (del_ && del_->n) { v.del_slot = del_->d_slot; v.del_words = del_->d_words; v.del_docs = del_->d_docs; v.n_del = del_->n; }
+    if (facets_ && facets_->n_facets) { v.facet_keys = facets_->d_keys; v.facet_rows = facets_->n_rows; v.facet_first_doc = facets_->first_doc; v.n_facets = facets_->n_facets; }
     return v;
 }
 
@@ -1704,6 +1745,89 @@ int32_t LexIndex::ensure_workspace(LexWorkspace& ws, uint32_t nq, uint32_t total
     return SSB_OK;
 }
 
+// ---- facet filters: FilterSparse bounds -> the key space of the facet columns ----
+// Keys: unsigned types as they are; signed types and Timestamp with the sign bit flipped; F32 / F64 through the f64 value's bits
+// (negative: all bits flipped, else sign bit set; -0.0 counts as +0.0, PartialOrd) — NaN has no key: a NaN VALUE gets ~0, which
+// no range contains (every finite / infinite bound maps below it), a NaN BOUND makes the filter reject everything.
+static inline uint64_t key_of_f64(double x) {
+    if (x == 0.0) x = 0.0;                                           // -0.0 == +0.0
+    uint64_t b; memcpy(&b, &x, 8);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+static inline bool facet_is_signed(uint32_t t) { return t == SSB_FACET_I8 || t == SSB_FACET_I16 || t == SSB_FACET_I32 || t == SSB_FACET_I64 || t == SSB_FACET_TIMESTAMP; }
+static inline bool facet_is_float(uint32_t t) { return t == SSB_FACET_F32 || t == SSB_FACET_F64; }
+uint64_t facet_value_key(uint32_t type, const uint8_t* p) {
+    switch (type) {
+        case SSB_FACET_U8: return p[0];
+        case SSB_FACET_U16: case SSB_FACET_STRING16: { uint16_t x; memcpy(&x, p, 2); return x; }
+        case SSB_FACET_U32: case SSB_FACET_STRING32: { uint32_t x; memcpy(&x, p, 4); return x; }
+        case SSB_FACET_U64: { uint64_t x; memcpy(&x, p, 8); return x; }
+        case SSB_FACET_I8: { int8_t x; memcpy(&x, p, 1); return (uint64_t)(int64_t)x ^ 0x8000000000000000ull; }
+        case SSB_FACET_I16: { int16_t x; memcpy(&x, p, 2); return (uint64_t)(int64_t)x ^ 0x8000000000000000ull; }
+        case SSB_FACET_I32: { int32_t x; memcpy(&x, p, 4); return (uint64_t)(int64_t)x ^ 0x8000000000000000ull; }
+        case SSB_FACET_I64: case SSB_FACET_TIMESTAMP: { int64_t x; memcpy(&x, p, 8); return (uint64_t)x ^ 0x8000000000000000ull; }
+        case SSB_FACET_F32: { float x; memcpy(&x, p, 4); return x != x ? ~0ull : key_of_f64((double)x); }
+        case SSB_FACET_F64: { double x; memcpy(&x, p, 8); return x != x ? ~0ull : key_of_f64(x); }
+    }
+    return ~0ull;
+}
+uint32_t facet_type_bytes(uint32_t type) {
+    switch (type) {
+        case SSB_FACET_U8: case SSB_FACET_I8: return 1;
+        case SSB_FACET_U16: case SSB_FACET_I16: case SSB_FACET_STRING16: return 2;
+        case SSB_FACET_U32: case SSB_FACET_I32: case SSB_FACET_F32: case SSB_FACET_STRING32: return 4;
+        case SSB_FACET_U64: case SSB_FACET_I64: case SSB_FACET_TIMESTAMP: case SSB_FACET_F64: return 8;
+    }
+    return 0;
+}
+
+int32_t LexIndex::stage_filters(LexWorkspace& ws, cudaStream_t st, const ssb_lex_batch* q, LexView& v, bool* any) const {
+    const uint32_t nq = q->n_queries;
+    if (is_device_ptr(q->filter_offsets) || (q->filters && is_device_ptr(q->filters))) { set_error("search_lexical: filter arrays must be host arrays"); return SSB_E_INVALID; }
+    const uint32_t nf = q->filter_offsets[nq];
+    *any = false;
+    if (nf == 0) return SSB_OK;
+    if (!q->filters) { set_error("search_lexical: null filters"); return SSB_E_INVALID; }
+    if (!facets_ || !facets_->n_facets) { set_error("search_lexical: facet filters need ssb_set_facets"); return SSB_E_STATE; }
+    std::vector<FiltDev> fd(nf);
+    uint32_t n_sets = 0;
+    for (uint32_t i = 0; i < nq; i++) {
+        if (q->filter_offsets[i + 1] < q->filter_offsets[i] || q->filter_offsets[i + 1] > nf) { set_error("query %u: filter_offsets must ascend", i); return SSB_E_INVALID; }
+        if (q->filter_offsets[i + 1] - q->filter_offsets[i] > SSB_MAX_FILTERS_PER_QUERY) { set_error("query %u: more than %u facet filters", i, SSB_MAX_FILTERS_PER_QUERY); return SSB_E_UNSUPPORTED; }
+    }
+    for (uint32_t i = 0; i < nf; i++) {
+        const ssb_facet_filter& f = q->filters[i];
+        if (f.facet >= facets_->n_facets) { set_error("facet filter %u: facet %u of %u", i, f.facet, facets_->n_facets); return SSB_E_INVALID; }
+        const uint32_t type = facets_->types[f.facet];
+        FiltDev d{}; d.facet = f.facet;
+        if (f.kind == SSB_FILTER_RANGE) {
+            if (type == SSB_FACET_STRING16 || type == SSB_FACET_STRING32) { set_error("facet filter %u: a String facet takes SSB_FILTER_SET", i); return SSB_E_INVALID; }
+            d.kind = FILT_RANGE;
+            if (facet_is_float(type)) {
+                double a, b; memcpy(&a, &f.start, 8); memcpy(&b, &f.end, 8);
+                if (a != a || b != b) d.kind = FILT_NEVER; else { d.lo = key_of_f64(a); d.hi = key_of_f64(b); }
+            } else if (facet_is_signed(type)) { d.lo = f.start ^ 0x8000000000000000ull; d.hi = f.end ^ 0x8000000000000000ull; }
+            else { d.lo = f.start; d.hi = f.end; }
+        } else if (f.kind == SSB_FILTER_SET) {
+            if (type != SSB_FACET_STRING16 && type != SSB_FACET_STRING32) { set_error("facet filter %u: SSB_FILTER_SET needs a String16 / String32 facet", i); return SSB_E_INVALID; }
+            if (f.set_count && !q->filter_set_values) { set_error("facet filter %u: null filter_set_values", i); return SSB_E_INVALID; }
+            d.kind = FILT_SET; d.set_first = f.set_first; d.set_n = f.set_count;
+            if ((uint64_t)f.set_first + f.set_count > n_sets) n_sets = f.set_first + f.set_count;
+        } else { set_error("facet filter %u: bad kind %u", i, f.kind); return SSB_E_INVALID; }
+        fd[i] = d;
+    }
+    if (!ws.foff) SSB_CUDA_TRY(cudaMalloc(&ws.foff, ((size_t)ws.cap_q + 1) * 4));
+    if (nf > ws.cap_filt) { cudaFree(ws.filt); ws.filt = nullptr; ws.cap_filt = 0; const uint32_t c = nf + nf / 2 + 64; SSB_CUDA_TRY(cudaMalloc(&ws.filt, (size_t)c * sizeof(FiltDev))); ws.cap_filt = c; }
+    if (n_sets > ws.cap_fsets) { cudaFree(ws.fsets); ws.fsets = nullptr; ws.cap_fsets = 0; const uint32_t c = n_sets + n_sets / 2 + 64; SSB_CUDA_TRY(cudaMalloc(&ws.fsets, (size_t)c * 8)); ws.cap_fsets = c; }
+    // pageable host sources: cudaMemcpyAsync returns after staging them, the vectors may go out of scope
+    SSB_CUDA_TRY(cudaMemcpyAsync(ws.foff, q->filter_offsets, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, st));
+    SSB_CUDA_TRY(cudaMemcpyAsync(ws.filt, fd.data(), (size_t)nf * sizeof(FiltDev), cudaMemcpyHostToDevice, st));
+    if (n_sets) SSB_CUDA_TRY(cudaMemcpyAsync(ws.fsets, q->filter_set_values, (size_t)n_sets * 8, cudaMemcpyHostToDevice, st));
+    v.filt = ws.filt; v.filt_sets = ws.fsets;
+    *any = true;
+    return SSB_OK;
+}
+
 int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_batch* q, uint32_t k, uint32_t result_type,
                               uint64_t* keys_out_dev, uint64_t* count_dev, uint64_t* launches, const uint64_t* ceil_dev) const {
     if (!committed_) { set_error("search before ssb_lexical_commit"); return SSB_E_STATE; }
@@ -1735,10 +1859,12 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     SSB_CUDA_TRY(to_device(ws.qoff, q->term_offsets, ((size_t)nq + 1) * 4, st));
     SSB_CUDA_TRY(to_device(ws.qkeys, q->term_keys, (size_t)total_terms * 8, st));
     if (q->term_flags) SSB_CUDA_TRY(to_device(ws.qflags, q->term_flags, (size_t)total_terms, st));
+    LexView v = view();
+    bool filtered = false;
+    if (q->filter_offsets) SSB_TRY(stage_filters(ws, st, q, v, &filtered));
     SSB_CUDA_TRY(cudaMemsetAsync(ws.ctr, 0, 32, st));
     SSB_CUDA_TRY(cudaMemsetAsync(ws.stats, 0, sizeof(LexStats), st));
 
-    const LexView v = view();
     uint32_t n_pow2 = 1; while (n_pow2 < v.n_levels) n_pow2 <<= 1;
     if (n_pow2 < 2) n_pow2 = 2;
     size_t plan_smem = (size_t)v.n_levels * (8 + 2 * FAST_T) + 16 + (size_t)n_pow2 * 8;
@@ -1748,7 +1874,7 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     // item shape (tunable for experiments; defaults measured on C3): target postings per item, levels of a query's first item, levels per item
     static const uint32_t item_w = env_u32("SSB_LEX_ITEM_W", ITEM_W, 64, 1u << 20), first_lim = env_u32("SSB_LEX_FIRST", 2, 1, GMAX),
                           gmax = env_u32("SSB_LEX_GMAX", GMAX, 1, GMAX), grid_mult = env_u32("SSB_LEX_GRID", SSB_LEX_MINB, 1, 16);
-    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
+    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, filtered ? ws.foff : nullptr, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
                                          item_w, first_lim, gmax);
     SSB_CUDA_TRY(cudaGetLastError());
     const bool is_and = q->query_type == SSB_QUERY_INTERSECTION;

@@ -68,6 +68,11 @@ struct LexLevel {
 struct BmSec { uint64_t w[2]; uint32_t meta[2]; uint32_t pad[2]; };
 static_assert(sizeof(BmSec) == 32, "BmSec must be one 32-byte sector");
 
+// One facet filter of one query, bounds already in key space (FilterSparse, search.rs:863-881): RANGE lo <= key < hi;
+// SET key in filt_sets[set_first .. +set_n); NEVER rejects every doc (a NaN bound: Range::contains is false for every value)
+enum { FILT_RANGE = 0, FILT_SET = 1, FILT_NEVER = 2 };
+struct FiltDev { uint32_t facet, kind; uint64_t lo, hi; uint32_t set_first, set_n; };
+
 // device view handed to the kernels (all pointers device)
 struct LexView {
     const uint64_t* dict_keys; uint32_t n_terms;
@@ -102,6 +107,20 @@ struct LexView {
     const uint64_t* del_words;    // [n_slots][1024]
     const uint32_t* del_docs;     // [n_del] deleted doc ids, ascending
     uint32_t n_del;
+    // facet columns (ssb_set_facets): order-preserving 64-bit keys, [n_facets][facet_rows]; row = doc id - facet_first_doc
+    const uint64_t* facet_keys;
+    uint64_t facet_rows;
+    uint32_t facet_first_doc;
+    uint32_t n_facets;
+    // per batch (filled by search_keys): the queries' facet filters, QueryPlan.filt_first / n_filt index into them
+    const FiltDev* filt;
+    const uint64_t* filt_sets;
+};
+
+// device-resident facet columns of an index (api.cu owns it, the lexical view borrows it)
+struct FacetSet {
+    uint64_t* d_keys = nullptr; uint64_t n_rows = 0; uint32_t first_doc = 0; uint32_t n_facets = 0; uint8_t types[16] = {0};
+    void release() { cudaFree(d_keys); d_keys = nullptr; n_rows = 0; n_facets = 0; }
 };
 
 // device-resident delete set shared by the lexical and the vector path
@@ -111,7 +130,8 @@ struct DeleteSet {
 };
 
 struct QTerm { uint32_t first, n; float idf; uint32_t df; };
-struct QueryPlan { QTerm t[SSB_MAX_QUERY_TERMS]; QTerm tn[SSB_MAX_NOT_TERMS]; uint32_t n_live, n_items, n_recs, n_not; };
+// fast: the query takes the record path (lex_score / lex_count): <= fast_t live terms and no facet filter; otherwise lex_generic
+struct QueryPlan { QTerm t[SSB_MAX_QUERY_TERMS]; QTerm tn[SSB_MAX_NOT_TERMS]; uint32_t n_live, n_items, n_recs, n_not; uint32_t filt_first, n_filt, fast, pad; };
 
 // One (query, level) record, built by lex_plan for queries with <= 4 live terms; 128 bytes = one cache line.
 // Slots are in QUERY order (scores are summed in query order, add_result.rs:1450-1452); cnt == 0 marks a term
@@ -144,6 +164,7 @@ struct LexWorkspace {
     QueryPlan* plans = nullptr; uint64_t* items = nullptr; LvRec* recs = nullptr; uint16_t* item_start = nullptr;
     uint64_t* theta = nullptr; int* lock = nullptr; uint64_t* count = nullptr; uint32_t* ctr = nullptr; /* [0] score / [2] count / [3] generic work counters, [1] max_items, [4] any query with > 4 live terms */
     uint32_t* qoff = nullptr; uint64_t* qkeys = nullptr; uint8_t* qflags = nullptr; LexStats* stats = nullptr;
+    uint32_t* foff = nullptr; FiltDev* filt = nullptr; uint64_t* fsets = nullptr; uint32_t cap_filt = 0, cap_fsets = 0;   // facet filters of the batch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // recorded around lex_score when set
     void release();
     ~LexWorkspace() { release(); }
@@ -170,6 +191,7 @@ public:
     bool committed() const { return committed_; }
     void set_stream(cudaStream_t st) { st_ = st; }   // load-time stream (add_level / commit)
     void set_deleted(const DeleteSet* d) { del_ = d; }
+    void set_facets(const FacetSet* f) { facets_ = f; }
     static LexStats read_stats(const LexWorkspace& ws, cudaStream_t st);
     uint64_t n_postings() const { return n_post_; }
     const std::vector<uint64_t>& host_keys() const { return h_dict_keys_; }
@@ -178,6 +200,7 @@ public:
 
 private:
     int32_t ensure_workspace(LexWorkspace& ws, uint32_t nq, uint32_t total_terms) const;
+    int32_t stage_filters(LexWorkspace& ws, cudaStream_t st, const ssb_lex_batch* q, LexView& v, bool* any) const;
     cudaStream_t st_;
     int n_sms_;
     uint32_t max_batch_;
@@ -197,9 +220,14 @@ private:
     uint32_t* d_level_ids_ = nullptr; float* d_cache_ = nullptr;
     std::vector<uint64_t> h_dict_keys_; std::vector<uint32_t> h_term_df_, h_local_df_;
     const DeleteSet* del_ = nullptr;
+    const FacetSet* facets_ = nullptr;
     void free_committed();
     LexView view() const;
 };
+
+// facet value (as stored in the reference's facet file) -> order-preserving key; byte width of a facet type (0 = unknown type)
+uint64_t facet_value_key(uint32_t type, const uint8_t* p);
+uint32_t facet_type_bytes(uint32_t type);
 
 // loader.cu: the reference's on-disk files -> index
 struct VectorLevel { uint32_t level_id; std::vector<uint16_t> ids; std::vector<float> rows; std::vector<uint32_t> cluster_counts; };

@@ -90,6 +90,17 @@ class SearchMode:
         return SearchMode("Hybrid", similarity_threshold, ann_mode)
 
 
+@dataclass(frozen=True)
+class FacetFilter:
+    """`FacetFilter` (search.rs:735-860): a range filter `start <= value < end` (Rust `Range<T>`) on a numeric / timestamp facet field, or a
+    value-id set on a String16 / String32 facet (values = the ids the reference resolves the filter strings to, FilterSparse::String16/32).
+    field: the facet's name (Index.set_facets) or its index."""
+    field: object
+    start: object = None
+    end: object = None
+    values: Optional[Sequence[int]] = None
+
+
 @dataclass
 class Result:
     """min_heap.rs:17-40."""
@@ -256,6 +267,59 @@ class Index:
         a = np.ascontiguousarray(np.asarray(list(doc_ids), dtype=np.uint64))
         check(lib().ssb_set_deleted(self._h, a.ctypes.data if a.size else None, a.size))
 
+    def set_facets(self, columns: dict, first_doc_id: int = 0, string_facets: Sequence[str] = (), timestamp_facets: Sequence[str] = ()):
+        """The shard's facet file (`facets_file_mmap`, add_result.rs:343-347): one typed value per doc and facet field.  columns: name ->
+        numpy array [n_docs] (dtype = the facet's FieldType; names in string_facets are String16 / String32 value ids, names in
+        timestamp_facets Timestamp); rows are packed field after field like the reference's facet file and handed to ssb_set_facets."""
+        from ._lib import SsbFacetField
+        kinds = {"uint8": _lib.FACET_U8, "uint16": _lib.FACET_U16, "uint32": _lib.FACET_U32, "uint64": _lib.FACET_U64, "int8": _lib.FACET_I8,
+                 "int16": _lib.FACET_I16, "int32": _lib.FACET_I32, "int64": _lib.FACET_I64, "float32": _lib.FACET_F32, "float64": _lib.FACET_F64}
+        names = list(columns)
+        n = len(next(iter(columns.values()))) if names else 0
+        fields, off, self._facet_schema = (SsbFacetField * max(len(names), 1))(), 0, {}
+        for i, name in enumerate(names):
+            a = np.asarray(columns[name])
+            t = kinds[a.dtype.name]
+            if name in string_facets:
+                t = {"uint16": _lib.FACET_STRING16, "uint32": _lib.FACET_STRING32}[a.dtype.name]
+            if name in timestamp_facets:
+                t = {"int64": _lib.FACET_TIMESTAMP}[a.dtype.name]
+            fields[i] = SsbFacetField(t, off)
+            self._facet_schema[name] = (i, t)
+            off += a.dtype.itemsize
+        rows = np.zeros((max(n, 1), max(off, 1)), dtype=np.uint8)
+        for i, name in enumerate(names):
+            a = np.ascontiguousarray(columns[name])
+            rows[:n, fields[i].offset:fields[i].offset + a.dtype.itemsize] = a.view(np.uint8).reshape(n, a.dtype.itemsize)
+        self._facet_rows = (rows, fields, int(first_doc_id), n, off)      # also what the tests hand to the oracle
+        check(lib().ssb_set_facets(self._h, rows.ctypes.data, int(first_doc_id), n, off, fields, len(names)))
+
+    def _encode_filters(self, filters):
+        """filters: per query a list of FacetFilter -> (filter_offsets, ssb_facet_filter array, set values)"""
+        from ._lib import SsbFacetFilter
+        offs = np.zeros(len(filters) + 1, dtype=np.uint32)
+        flat, sets = [], []
+        for i, fl in enumerate(filters):
+            for f in fl or ():
+                idx, t = self._facet_schema[f.field] if isinstance(f.field, str) else (int(f.field), None)
+                if t is None:
+                    t = next((v[1] for v in getattr(self, "_facet_schema", {}).values() if v[0] == idx), _lib.FACET_U64)
+                if f.values is not None:
+                    flat.append(SsbFacetFilter(idx, _lib.FILTER_SET, 0, 0, len(sets), len(f.values)))
+                    sets.extend(int(v) for v in f.values)
+                else:
+                    if t in (_lib.FACET_F32, _lib.FACET_F64):
+                        enc = lambda x: int(np.float64(x).view(np.uint64))
+                    elif t in (_lib.FACET_I8, _lib.FACET_I16, _lib.FACET_I32, _lib.FACET_I64, _lib.FACET_TIMESTAMP):
+                        enc = lambda x: int(np.int64(x).view(np.uint64))
+                    else:
+                        enc = lambda x: int(np.uint64(x))
+                    flat.append(SsbFacetFilter(idx, _lib.FILTER_RANGE, enc(f.start), enc(f.end), 0, 0))
+            offs[i + 1] = len(flat)
+        arr = (SsbFacetFilter * max(len(flat), 1))(*flat)
+        sv = np.asarray(sets if sets else [0], dtype=np.uint64)
+        return offs, arr, sv
+
     def add_vector_level(self, level_id: int, rows, local_ids=None, cluster_counts=None):
         """rows: [n, dims] f32 (numpy or torch, host or device), n <= 65536.  cluster_counts: the level's IVF cluster table (rows in
         cluster order, medoid = first row of each cluster; vector.rs:1066-1094) or None = one cluster."""
@@ -289,8 +353,10 @@ class Index:
         return n.value
 
     # ------------------------------------------------------------------ batched shard-level search
-    def _lex_batch(self, queries_keys: Sequence[Sequence[int]], query_type: QueryType, not_keys: Optional[Sequence[Sequence[int]]] = None):
-        """not_keys: per query the keys of its '-' terms (not_query_list, add_result.rs:3440-3496) or None."""
+    def _lex_batch(self, queries_keys: Sequence[Sequence[int]], query_type: QueryType, not_keys: Optional[Sequence[Sequence[int]]] = None,
+                   filters: Optional[Sequence[Sequence["FacetFilter"]]] = None):
+        """not_keys: per query the keys of its '-' terms (not_query_list, add_result.rs:3440-3496) or None.
+        filters: per query its FacetFilter list (facet_filter of search_lexical_shard) or None."""
         nots = not_keys if not_keys is not None else [[] for _ in queries_keys]
         offs = np.zeros(len(queries_keys) + 1, dtype=np.uint32)
         for i, q in enumerate(queries_keys):
@@ -309,14 +375,20 @@ class Index:
                 flags[p] = 1
                 p += 1
         b = SsbLexBatch(len(queries_keys), int(query_type), offs.ctypes.data, keys.ctypes.data,
-                        flags.ctypes.data if not_keys is not None else None)
-        return b, (offs, keys, flags)
+                        flags.ctypes.data if not_keys is not None else None, None, None, None)
+        keep = [offs, keys, flags]
+        if filters is not None:
+            foffs, farr, fsets = self._encode_filters(filters)
+            b.filter_offsets, b.filters, b.filter_set_values = foffs.ctypes.data, C.addressof(farr), fsets.ctypes.data
+            keep += [foffs, farr, fsets]
+        return b, tuple(keep)
 
     def search_lexical_batch(self, queries_keys, query_type: QueryType, k: int,
-                             result_type: ResultType = ResultType.TopkCount, not_keys=None):
-        """Batched search_lexical_shard.  Returns (list of [(doc_id, score)...], counts ndarray).  not_keys: '-' terms per query."""
+                             result_type: ResultType = ResultType.TopkCount, not_keys=None, filters=None):
+        """Batched search_lexical_shard.  Returns (list of [(doc_id, score)...], counts ndarray).  not_keys: '-' terms per query;
+        filters: FacetFilter list per query (needs set_facets)."""
         nq = len(queries_keys)
-        b, keep = self._lex_batch(queries_keys, query_type, not_keys)
+        b, keep = self._lex_batch(queries_keys, query_type, not_keys, filters)
         hits = _hits_array(max(nq * max(k, 1), 1))
         n_hits = np.zeros(max(nq, 1), dtype=np.uint32)
         counts = np.zeros(max(nq, 1), dtype=np.uint64)
@@ -443,10 +515,12 @@ class Index:
                result_sort: Sequence = (), query_rewriting=None) -> ResultObject:
         """`Search::search` (search.rs:1134-1150) for committed data, 1-shard semantics.
 
-        Unsupported reference features (facets, filters, sort, uncommitted, rewriting, phrase) raise
+        facet_filter: FacetFilter objects (range / value-set filters on the facet fields given to set_facets) — applied to the lexical
+        search like the reference does (the vector search takes no facet filter, vector.rs:1105-1115).
+        Unsupported reference features (facet counting, field filters, sort, uncommitted, rewriting, phrase) raise
         NotImplementedError rather than being silently ignored."""
-        if field_filter or query_facets or facet_filter or result_sort or include_uncommitted:
-            raise NotImplementedError("facets / filters / sort / uncommitted search are outside the GPU hot path")
+        if field_filter or query_facets or result_sort or include_uncommitted:
+            raise NotImplementedError("facet counts / field filters / sort / uncommitted search are outside the GPU hot path")
         search_mode = search_mode or SearchMode.Lexical()
         ro = ResultObject(original_query=query_string, query=query_string)
         heap = offset + length                       # search.rs:1708 per-shard length = offset+length
@@ -474,7 +548,8 @@ class Index:
         if length == 0 and rt == ResultType.TopkCount:   # search.rs:2472-2478
             rt = ResultType.Count
         if want_lex:
-            res, counts = self.search_lexical_batch([keys], qt, heap if rt != ResultType.Count else 0, rt, [nkeys] if nkeys else None)
+            res, counts = self.search_lexical_batch([keys], qt, heap if rt != ResultType.Count else 0, rt, [nkeys] if nkeys else None,
+                                                    [list(facet_filter)] if facet_filter else None)
             lex, total = res[0], int(counts[0])
         if want_vec:
             qv = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)

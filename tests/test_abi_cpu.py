@@ -29,13 +29,14 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_struct_sizes():
     L = _lib.lib()
-    assert L.ssb_abi_version() == 2
+    assert L.ssb_abi_version() == 3
     assert ctypes.sizeof(_lib.SsbHitExt) == 48
     assert ctypes.sizeof(_lib.SsbVecQuery) == 40
     assert ctypes.sizeof(_lib.SsbHit) == 16
     assert ctypes.sizeof(_lib.SsbConfig) == 32
     assert ctypes.sizeof(_lib.SsbLevelDesc) == 16 + 5 * 8
-    assert ctypes.sizeof(_lib.SsbLexBatch) == 8 + 3 * 8
+    assert ctypes.sizeof(_lib.SsbLexBatch) == 8 + 6 * 8
+    assert ctypes.sizeof(_lib.SsbFacetFilter) == 32 and ctypes.sizeof(_lib.SsbFacetField) == 8
     assert ctypes.sizeof(_lib.SsbStats) == 96
 
 

@@ -1,0 +1,78 @@
+"""CPU: the oracle's facet filter (is_facet_filter, add_result.rs:340-478) against a numpy restatement on typed columns — every
+FieldType, NaN / +-inf / +-0.0 / integer extremes, empty ranges, value sets — and the host-side filter encoding."""
+import numpy as np
+
+from oracle import oracle as O
+from helpers import level_from_postings, oracle_index, key_of
+from helpers_facets import facet_columns, numpy_pass, random_filters
+
+
+class _Enc:
+    """the host mirror's filter encoding without a GPU index (Index._encode_filters only needs the schema)"""
+    def __init__(self, cols, kinds):
+        from seekstorm_b200 import _lib
+        from seekstorm_b200.index import Index
+        m = {"uint8": _lib.FACET_U8, "uint16": _lib.FACET_U16, "uint32": _lib.FACET_U32, "uint64": _lib.FACET_U64, "int8": _lib.FACET_I8,
+             "int16": _lib.FACET_I16, "int32": _lib.FACET_I32, "int64": _lib.FACET_I64, "float32": _lib.FACET_F32, "float64": _lib.FACET_F64}
+        self._facet_schema, self.fields, off = {}, [], 0
+        for i, (name, a) in enumerate(cols.items()):
+            t = m[a.dtype.name]
+            if name in kinds["string_facets"]:
+                t = _lib.FACET_STRING16 if a.dtype == np.uint16 else _lib.FACET_STRING32
+            if name in kinds["timestamp_facets"]:
+                t = _lib.FACET_TIMESTAMP
+            self._facet_schema[name] = (i, t)
+            self.fields.append((t, off))
+            off += a.dtype.itemsize
+        self.row_bytes = off
+        self._encode_filters = Index._encode_filters.__get__(self)
+
+    def rows(self, cols, n):
+        rows = np.zeros((n, self.row_bytes), dtype=np.uint8)
+        for (t, off), a in zip(self.fields, cols.values()):
+            a = np.ascontiguousarray(a)
+            rows[:, off:off + a.dtype.itemsize] = a.view(np.uint8).reshape(n, a.dtype.itemsize)
+        return rows
+
+
+def test_oracle_facet_filter_matches_numpy_restatement():
+    n = 3000
+    rng = np.random.default_rng(5)
+    post = {f"t{t}": sorted((int(d), int(rng.integers(1, 5))) for d in rng.choice(n, int(n / (t + 2)), replace=False)) for t in range(8)}
+    lens = [O.lib().orc_int_to_byte4(int(x)) for x in rng.integers(5, 200, n)]
+    lv = level_from_postings(0, n, post, lens)
+    orc = oracle_index([lv], n, int(sum(O.lib().orc_byte4_to_int(b) for b in lens)))
+    cols, kinds = facet_columns(n, 6)
+    enc = _Enc(cols, kinds)
+    orc.set_facets(enc.rows(cols, n), enc.fields, 0, n, enc.row_bytes)
+    filters = random_filters(cols, 7, 120)
+    n_checked = 0
+    for qi, fl in enumerate(filters):
+        terms = [f"t{t}" for t in rng.choice(8, int(rng.integers(1, 4)), replace=False)]
+        keys = [key_of(t) for t in terms]
+        for qt in (O.QUERY_UNION, O.QUERY_INTERSECTION):
+            base, _ = orc.search(keys, qt, n, O.RESULT_TOPKCOUNT)                       # every match, best first
+            offs, arr, sv = enc._encode_filters([fl])
+            tup = [(arr[i].facet, arr[i].kind, arr[i].start, arr[i].end, arr[i].set_first, arr[i].set_count) for i in range(int(offs[1]))]
+            got, tot = orc.search(keys, qt, 10, O.RESULT_TOPKCOUNT, filters=tup, set_values=[int(x) for x in sv])
+            want = [(d, s) for d, s in base if numpy_pass(cols, fl, d)]
+            if not fl:
+                got, tot = orc.search(keys, qt, 10, O.RESULT_TOPKCOUNT)
+            assert got == want[:10], (qi, terms, fl)
+            assert tot == len(want), (qi, terms, fl, tot, len(want))
+            n_checked += bool(fl)
+    assert n_checked > 100
+
+
+def test_filter_encoding_of_bounds():
+    """signed bounds travel as two's complement, float bounds as f64 bits, unsigned as they are"""
+    cols, kinds = facet_columns(10, 1)
+    enc = _Enc(cols, kinds)
+    from seekstorm_b200 import FacetFilter, _lib
+    offs, arr, sv = enc._encode_filters([[FacetFilter("i8", -5, 7), FacetFilter("f32", -1.5, np.inf), FacetFilter("u64", 3, 2**64 - 1),
+                                          FacetFilter("s16", values=[4, 9])], []])
+    assert list(offs) == [0, 4, 4]
+    assert arr[0].start == 2**64 - 5 and arr[0].end == 7 and arr[0].kind == _lib.FILTER_RANGE
+    assert arr[1].start == int(np.float64(-1.5).view(np.uint64)) and arr[1].end == int(np.float64(np.inf).view(np.uint64))
+    assert arr[2].start == 3 and arr[2].end == 2**64 - 1
+    assert arr[3].kind == _lib.FILTER_SET and arr[3].set_first == 0 and arr[3].set_count == 2 and list(sv[:2]) == [4, 9]
