@@ -254,8 +254,8 @@ NCU = {"scan_ffma": {"traffic_per_pass": 3.0770e9, "source": "profiles/r02_scan_
        # filter scan (fp16 plane): 128-query tile (3.0909 GB read + 60.8 MB written) / 2 passes; 256-query tile 1.5575 GB + 59.2 MB, one pass
        "filt": {"traffic_per_pass": 1.5759e9, "source": "profiles/r02_scan_tc_filter_v1.summary.txt", "tensor_pipe_pct": 45.2},
        "filt256": {"traffic_per_pass": 1.6167e9, "source": "profiles/r02_scan_tc_filter_n256_v1.summary.txt", "tensor_pipe_pct": 62.1},
-       # scan_tc2 (CTA pairs): filled from profiles/r02_scan_tc2_filter_pair.summary.txt once captured (None = no capture of this kernel yet)
-       "filt256p": {"traffic_per_pass": None, "source": None, "tensor_pipe_pct": None},
+       # scan_tc2 (CTA pairs, 256 queries): 1.5575 GB read + 58.9 MB written in one pass of 355.5 us under ncu
+       "filt256p": {"traffic_per_pass": 1.6164e9, "source": "profiles/r02_scan_tc2_filter_pair.summary.txt", "tensor_pipe_pct": 64.3},
        # int8 full scan of 1M x 768, 1024 queries = 8 passes in one launch: (6.2222 GB read + 219.8 MB written) / 8
        "scan_tc_i8": {"traffic_per_pass": 0.8052e9, "source": "profiles/r02_scan_tc_i8.summary.txt"},
        # lex_score<OR>, C3 10M docs, 4096 queries, Topk: 6.8986 GB read + 60.6 MB written (random 32-byte sector probes of the

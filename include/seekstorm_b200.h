@@ -56,9 +56,16 @@ enum { SSB_SIM_DOT = 0, SSB_SIM_COSINE = 1, SSB_SIM_EUCLIDEAN = 2 };
  *              score = dot_i32 as f32 * query_scale * row_scale (dot_i8_quantized, :1754-1758).
  *   Euclidean: new_scale_norm (:1356-1371), the NON-AFFINE variant the reference uses for non-integer data (vector.rs:651-660);
  *              score = -max(0, query_norm + row_norm - 2*dot) (euclidean_i8_quantized, :1721-1734).  Integer-valued 0..255 data
- *              (affine quantisation) and TurboQuantI8 are not built: SSB_E_UNSUPPORTED.
+ *              (affine quantisation) is not built: SSB_E_UNSUPPORTED.
  * All three are bit-exact with the scalar CPU arithmetic (integer accumulation on tcgen05 kind::i8, reference operation order). */
-enum { SSB_QUANT_NONE = 0, SSB_QUANT_SCALAR_I8 = 1 };
+enum { SSB_QUANT_NONE = 0, SSB_QUANT_SCALAR_I8 = 1,
+       /* TurboQuantI8 (vector_similarity.rs:1825-2093): every vector (after normalize_f32 for Cosine) is zero-padded to the next power of
+        * two, sign-flipped by the index's seed mask, rotated by the normalised fast Walsh-Hadamard transform and quantised with
+        * scale = max(||x|| / sqrt(dim) / 32, 1e-8); rows are stored at next_power_of_two(dims) bytes.  Scores as in the reference:
+        * Dot / Cosine = -(dot_i32 as f32 * query_scale * row_scale) (it negates the estimate, :161-176, 220-235), Euclidean =
+        * -max(0, query_norm + row_norm - 2 * dot_i32 as f32 * query_scale * row_scale) (:2058-2069).  Bit-exact with the scalar CPU
+        * arithmetic.  Needs ssb_vector_set_turboquant_mask before the first level. */
+       SSB_QUANT_TURBO_I8 = 2 };
 /* which vector scan kernel to use */
 /* FFMA: packed-FP32 scan, 16 queries per corpus pass (HBM-bound).  TCGEN05[_N64]: tensor-core scan with the 3xTF32
  * split, 128 (or 64) queries per corpus pass.  TCGEN05_BF16[_N64]: tensor-core scan with the 3xBF16 split (half the
@@ -154,6 +161,11 @@ typedef struct {
     const uint32_t* filter_offsets;           /* [n_queries+1] or NULL (no query is filtered)                                      */
     const struct ssb_facet_filter* filters;   /* [filter_offsets[n_queries]]                                                       */
     const uint64_t* filter_set_values;        /* value ids of the SSB_FILTER_SET filters (String16 / String32), or NULL            */
+    /* field filter (`field_filter: Vec<String>` -> field_filter_set, add_result.rs:3124-3137, 3558-3571): HOST array [n_queries] or   */
+    /* NULL; bit f = indexed field f is in the query's filter, 0 = no field filter.  A doc is dropped when a query term it contains    */
+    /* occurs in none of the filter's fields (tested like the reference only when term fields + filter fields <= indexed fields);      */
+    /* scores still sum every field.  Indexes with one indexed field ignore it (the reference's test can never fire there).            */
+    const uint32_t* field_masks;
 } ssb_lex_batch;
 
 uint32_t    ssb_abi_version(void);
@@ -226,6 +238,10 @@ int32_t ssb_vector_add_level(ssb_index* ix, uint32_t level_id, const float* rows
 int32_t ssb_vector_add_level_clustered(ssb_index* ix, uint32_t level_id, const float* rows, uint64_t row_stride_floats,
                                        const uint16_t* local_ids, uint32_t n, uint32_t dims,
                                        const uint32_t* cluster_counts, uint32_t n_clusters);
+/* TurboQuantI8 indexes: the index's sign mask `TurboQuant.seed_mask` (dim = next_power_of_two(vector_dims) values of +1 / -1).  The
+ * reference draws it once per index from ChaCha8Rng::seed_from_u64(1234) (vector_similarity.rs:1845-1859, index.rs:2215-2216) — a
+ * third-party generator (rand_chacha) that this library does not restate: the host hands over the mask it holds.  Before the first level. */
+int32_t ssb_vector_set_turboquant_mask(ssb_index* ix, const float* seed_mask, uint32_t dim);
 int32_t ssb_vector_count(const ssb_index* ix, uint64_t* n_rows);
 /* capacity hint: size the vector arenas for n_rows rows up front (loading level by level otherwise grows them geometrically) */
 int32_t ssb_vector_reserve(ssb_index* ix, uint64_t n_rows);

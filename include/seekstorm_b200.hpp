@@ -36,7 +36,7 @@ inline void check(int32_t rc) {
 enum class QueryType : uint32_t { Union = SSB_QUERY_UNION, Intersection = SSB_QUERY_INTERSECTION };
 enum class ResultType : uint32_t { Count = SSB_RESULT_COUNT, Topk = SSB_RESULT_TOPK, TopkCount = SSB_RESULT_TOPKCOUNT };
 enum class VectorSimilarity : uint32_t { Dot = SSB_SIM_DOT, Cosine = SSB_SIM_COSINE, Euclidean = SSB_SIM_EUCLIDEAN };
-enum class Quantization : uint32_t { None = SSB_QUANT_NONE, ScalarQuantizationI8 = SSB_QUANT_SCALAR_I8 };   // vector.rs:230-240
+enum class Quantization : uint32_t { None = SSB_QUANT_NONE, ScalarQuantizationI8 = SSB_QUANT_SCALAR_I8, TurboQuantI8 = SSB_QUANT_TURBO_I8 };   // vector.rs:230-240
 // AnnMode (vector_similarity.rs:43-66): which IVF clusters of each level are searched (vector.rs:1300-1392)
 struct AnnMode {
     uint32_t kind = SSB_ANN_ALL; uint32_t n_probe = 0; float threshold = 0.f;
@@ -119,6 +119,11 @@ public:
     void set_facets(const void* rows, uint64_t first_doc_id, uint64_t n_docs, uint32_t row_bytes, const std::vector<ssb_facet_field>& fields) {
         check(ssb_set_facets(h_, rows, first_doc_id, n_docs, row_bytes, fields.data(), static_cast<uint32_t>(fields.size())));
     }
+    // several indexed fields: boosts (before the first level) and the fields' names in schema order (for field_filter)
+    void set_field_boosts(const std::vector<float>& boosts) { check(ssb_lexical_set_field_boosts(h_, static_cast<uint32_t>(boosts.size()), boosts.data())); }
+    void set_field_names(std::vector<std::string> names) { field_names_ = std::move(names); }
+    // TurboQuantI8 indexes: the index's +-1 sign mask (TurboQuant.seed_mask)
+    void set_turboquant_mask(const std::vector<float>& seed_mask) { check(ssb_vector_set_turboquant_mask(h_, seed_mask.data(), static_cast<uint32_t>(seed_mask.size()))); }
     uint64_t indexed_doc_count() const { return indexed_doc_count_; }
     uint64_t vector_count() const { uint64_t n = 0; check(ssb_vector_count(h_, &n)); return n; }
 
@@ -129,8 +134,16 @@ public:
                         const std::vector<std::string>& field_filter = {}, size_t n_query_facets = 0,
                         const std::vector<FacetFilter>& facet_filter = {}, size_t n_result_sort = 0) const {
         (void)enable_empty_query;
-        if (include_uncommitted || !field_filter.empty() || n_query_facets || n_result_sort)
-            throw Error(SSB_E_UNSUPPORTED, "facet counts / field filters / sort / uncommitted search are outside the GPU hot path");
+        if (include_uncommitted || n_query_facets || n_result_sort)
+            throw Error(SSB_E_UNSUPPORTED, "facet counts / sort / uncommitted search are outside the GPU hot path");
+        // field_filter: names of indexed fields (set_field_names, schema order) -> field_filter_set as a bitmask
+        uint32_t field_mask = 0;
+        for (auto& name : field_filter) {
+            size_t f = 0;
+            while (f < field_names_.size() && field_names_[f] != name) f++;
+            if (f == field_names_.size()) throw Error(SSB_E_INVALID, "field_filter: unknown indexed field " + name);
+            field_mask |= 1u << f;
+        }
         ResultObject ro;
         ro.original_query = ro.query = query_string;
         const size_t heap = offset + length;                                   // search.rs:1708: per-shard length = offset+length
@@ -170,7 +183,7 @@ public:
             for (auto& t : terms) { keys.push_back(key_fn_(t)); flags.push_back(0); }
             for (auto& t : not_terms) { keys.push_back(key_fn_(t)); flags.push_back(SSB_TERM_NOT); }
             uint32_t offs[2] = {0, static_cast<uint32_t>(keys.size())};
-            ssb_lex_batch b{1, static_cast<uint32_t>(qt), offs, keys.data(), not_terms.empty() ? nullptr : flags.data(), nullptr, nullptr, nullptr};
+            ssb_lex_batch b{1, static_cast<uint32_t>(qt), offs, keys.data(), not_terms.empty() ? nullptr : flags.data(), nullptr, nullptr, nullptr, nullptr};
             // facet_filter (search.rs:735-860 -> FilterSparse per facet): applied to every candidate of the lexical search
             std::vector<ssb_facet_filter> ff; std::vector<uint64_t> set_values;
             uint32_t foffs[2] = {0, static_cast<uint32_t>(facet_filter.size())};
@@ -182,6 +195,7 @@ public:
                 ff.push_back(c);
             }
             if (!ff.empty()) { b.filter_offsets = foffs; b.filters = ff.data(); b.filter_set_values = set_values.data(); }
+            if (field_mask) b.field_masks = &field_mask;
             const uint32_t k = rt == ResultType::Count ? 0u : static_cast<uint32_t>(heap);
             lex.resize(k ? k : 1);
             uint32_t n = 0;
@@ -224,6 +238,7 @@ private:
     TermKeyFn key_fn_;
     VectorSimilarity sim_;
     uint64_t indexed_doc_count_ = 0;
+    std::vector<std::string> field_names_;
 };
 
 }  // namespace ssb

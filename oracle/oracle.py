@@ -155,18 +155,22 @@ class OracleIndex:
         rows = np.ascontiguousarray(rows, dtype=np.uint8)
         assert lib().orc_index_set_facets(self._h, _ptr(rows), first_doc_id, n_docs, row_bytes, fa, len(fields)) == 0
 
-    def search(self, term_keys, query_type, k, result_type, pruned=False, not_keys=None, filters=None, set_values=None):
-        """filters: [(facet, kind, start_u64, end_u64, set_first, set_count), ...] in the C-ABI's encoding; set_values: the SET filters' ids"""
+    def search(self, term_keys, query_type, k, result_type, pruned=False, not_keys=None, filters=None, set_values=None, field_mask=0):
+        """filters: [(facet, kind, start_u64, end_u64, set_first, set_count), ...] in the C-ABI's encoding; set_values: the SET filters' ids;
+        field_mask: bit f = indexed field f is in the query's field filter (0 = none)"""
         keys = np.ascontiguousarray(np.array(term_keys, dtype=np.uint64))
         buf = (OrcHit * max(k, 1))()
         n = C.c_uint32(0)
         tot = C.c_uint64(0)
-        if filters:
+        if filters or field_mask:
+            filters = filters or []
             nk = np.ascontiguousarray(np.array(not_keys if not_keys else [0], dtype=np.uint64))
-            fa = (OrcFacetFilter * len(filters))(*[OrcFacetFilter(*[int(x) for x in f]) for f in filters])
+            fa = (OrcFacetFilter * max(len(filters), 1))(*[OrcFacetFilter(*[int(x) for x in f]) for f in filters])
             sv = np.ascontiguousarray(np.array(set_values if set_values is not None and len(set_values) else [0], dtype=np.uint64))
-            rc = lib().orc_search_lexical_filtered(self._h, _ptr(keys), len(keys), _ptr(nk), len(not_keys) if not_keys else 0, fa, len(filters), _ptr(sv),
-                                                   query_type, k, result_type, buf, C.byref(n), C.byref(tot))
+            lib().orc_search_lexical_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                                    C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+            rc = lib().orc_search_lexical_ex(self._h, _ptr(keys), len(keys), _ptr(nk), len(not_keys) if not_keys else 0, fa, len(filters), _ptr(sv), int(field_mask),
+                                             query_type, k, result_type, buf, C.byref(n), C.byref(tot))
             assert rc == 0, rc
             return _hits_to_list(buf, n.value), int(tot.value)
         if not_keys:
@@ -299,6 +303,38 @@ def search_vector_i8_scaled(rows_i8, row_scale, row_norm, query_i8, q_scale, q_n
     n = C.c_uint32(0)
     rc = lib().orc_search_vector_i8_scaled(_ptr(rows_i8), _ptr(rs), _ptr(rn), None if ids is None else _ptr(ids), rows_i8.shape[0], rows_i8.shape[1],
                                            rows_i8.strides[0], _ptr(q), C.c_float(q_scale), C.c_float(q_norm), similarity, k, buf, C.byref(n))
+    assert rc == 0
+    return _hits_to_list(buf, n.value)
+
+
+def turboquant_rows_i8(rows: np.ndarray, seed_mask: np.ndarray, normalize_first: bool = False):
+    """TurboQuant::quantize_f32_i8 per row (Cosine: normalize_f32 first, vector.rs:585-596) -> (codes int8 [n, dim], scale [n], norm [n]); dim = len(seed_mask)"""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    mask = np.ascontiguousarray(seed_mask, dtype=np.float32)
+    n, d = rows.shape
+    dim = mask.size
+    out = np.zeros((n, dim), dtype=np.int8); scale = np.zeros(n, dtype=np.float32); norm = np.zeros(n, dtype=np.float32)
+    s, nn = C.c_float(0), C.c_float(0)
+    lib().orc_turboquant_i8.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    for i in range(n):
+        r = normalize(rows[i]) if normalize_first else rows[i]
+        lib().orc_turboquant_i8(_ptr(r), d, dim, _ptr(mask), _ptr(out[i]), C.byref(s), C.byref(nn))
+        scale[i], norm[i] = s.value, nn.value
+    return out, scale, norm
+
+
+def search_vector_i8_turbo(rows_i8, row_scale, row_norm, query_i8, q_scale, q_norm, similarity, k, doc_ids=None):
+    rows_i8 = np.ascontiguousarray(rows_i8, dtype=np.int8)
+    rs = np.ascontiguousarray(row_scale, dtype=np.float32); rn = np.ascontiguousarray(row_norm, dtype=np.float32)
+    q = np.ascontiguousarray(query_i8, dtype=np.int8)
+    ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint32)
+    buf = (OrcHit * max(k, 1))()
+    n = C.c_uint32(0)
+    f = lib().orc_search_vector_i8_turbo
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
+                  C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    rc = f(_ptr(rows_i8), _ptr(rs), _ptr(rn), None if ids is None else _ptr(ids), rows_i8.shape[0], rows_i8.shape[1],
+           rows_i8.strides[0], _ptr(q), C.c_float(q_scale), C.c_float(q_norm), similarity, k, buf, C.byref(n))
     assert rc == 0
     return _hits_to_list(buf, n.value)
 

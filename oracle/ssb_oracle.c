@@ -319,6 +319,16 @@ int orc_search_lexical_filtered(const orc_index* ix, const uint64_t* keys, uint3
                                 const orc_facet_filter* filters, uint32_t n_filters, const uint64_t* set_values,
                                 uint32_t query_type, uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
                                 uint64_t* count_total) {
+    return orc_search_lexical_ex(ix, keys, n_terms, not_keys, n_not, filters, n_filters, set_values, 0, query_type, k, result_type, hits, n_hits, count_total);
+}
+
+/* ... and with a field filter (field_filter_set, add_result.rs:3124-3137 multi-field / 3558-3571 single-field): bit f of field_mask = indexed
+ * field f is in the filter.  For every query term the doc contains: if (fields the term occurs in) + (fields of the filter) <= indexed fields
+ * and none of the term's fields is in the filter, the doc is dropped — before it is counted or scored; the score still sums every field. */
+int orc_search_lexical_ex(const orc_index* ix, const uint64_t* keys, uint32_t n_terms, const uint64_t* not_keys, uint32_t n_not,
+                          const orc_facet_filter* filters, uint32_t n_filters, const uint64_t* set_values, uint32_t field_mask,
+                          uint32_t query_type, uint32_t k, uint32_t result_type, orc_hit* hits, uint32_t* n_hits,
+                          uint64_t* count_total) {
     if (!ix || !ix->committed || n_terms > ORC_MAX_TERMS || n_not > ORC_MAX_TERMS) return -1;
     if (n_filters && !ix->n_facets) return -1;
     for (uint32_t i = 0; i < n_filters; i++) if (filters[i].facet >= ix->n_facets) return -1;
@@ -344,6 +354,9 @@ int orc_search_lexical_filtered(const orc_index* ix, const uint64_t* keys, uint3
     float* acc = (float*)malloc(65536 * sizeof(float));
     uint8_t* cnt = (uint8_t*)malloc(65536);
     uint8_t* excl = (uint8_t*)malloc(65536);
+    uint32_t n_filter_fields = 0;
+    if (nf_of(ix) > 1) field_mask &= (1u << nf_of(ix)) - 1u; else field_mask = 0;   /* one indexed field: 1 + len <= 1 never holds */
+    for (uint32_t f = 0; f < ORC_MAX_FIELDS; f++) n_filter_fields += (field_mask >> f) & 1u;
     qterm_t nq[ORC_MAX_TERMS];
     if (n_not) resolve_terms(ix, not_keys, n_not, nq);
     uint64_t total = 0;
@@ -374,6 +387,11 @@ int orc_search_lexical_filtered(const orc_index* ix, const uint64_t* keys, uint3
                 } else {
                     /* get_bm25f_multiterm_multifield, NgramType::SingleTerm (add_result.rs:1232-1262): for every field the term occurs in,
                      * bm25f += weight * idf * ((tf * (K + 1) / (tf + cache[len_byte of THAT field])) + SIGMA), fields in ascending order */
+                    if (field_mask) {
+                        uint32_t present = 0, np = 0;
+                        for (uint32_t f = 0; f < nf; f++) if (l->tfs[(size_t)j * nf + f]) { present |= 1u << f; np++; }
+                        if (np + n_filter_fields <= nf && !(present & field_mask)) excl[d] = 1;
+                    }
                     for (uint32_t f = 0; f < nf; f++) {
                         uint32_t tfu = l->tfs[(size_t)j * nf + f];
                         if (!tfu) continue;
@@ -865,6 +883,57 @@ float orc_score_i8_scaled(const int8_t* q, float q_scale, float q_norm, const in
     volatile float s = q_norm + e_norm; volatile float t = 2.0f * d; volatile float r = s - t;
     return -(r > 0.0f ? r : 0.0f);
 }
+/* ---- TurboQuantI8 (vector_similarity.rs:1825-2093): the vector is zero-padded to the next power of two, sign-flipped by the index's seed
+ * mask (+-1, drawn once from ChaCha8Rng(seed 1234) — a third-party generator, so the mask is an INPUT here), rotated by the normalised
+ * fast Walsh-Hadamard transform and quantised with scale = max(sigma / 32, 1e-8), sigma = ||x|| / sqrt(dim).  Scalar variant
+ * (quantize_f32_i8 :1929-1958, fwht :1861-1880, calculate_scale :2035-2039): every sum left to right. */
+void orc_turboquant_i8(const float* v, uint32_t n, uint32_t dim, const float* seed_mask, int8_t* out, float* scale_out, float* norm_out) {
+    float* a = (float*)calloc(dim, sizeof(float));
+    for (uint32_t i = 0; i < dim && i < n; i++) a[i] = v[i];
+    for (uint32_t i = 0; i < dim; i++) { volatile float p = a[i] * seed_mask[i]; a[i] = p; }
+    for (uint32_t h = 1; h < dim; h *= 2)
+        for (uint32_t i = 0; i < dim; i += 2 * h)
+            for (uint32_t j = i; j < i + h; j++) { volatile float x = a[j], y = a[j + h]; volatile float s = x + y, d = x - y; a[j] = s; a[j + h] = d; }
+    volatile float nrm = sqrtf((float)dim);
+    for (uint32_t i = 0; i < dim; i++) { volatile float q = a[i] / nrm; a[i] = q; }
+    volatile float ss = 0.0f;
+    for (uint32_t i = 0; i < dim; i++) { volatile float p = a[i] * a[i]; ss = ss + p; }
+    volatile float l2 = sqrtf(ss);
+    volatile float sigma = l2 / nrm;                       /* (self.dim as f32).sqrt() */
+    volatile float sc = sigma / 32.0f;
+    float scale = sc > 1e-8f ? sc : 1e-8f;                 /* f32::max */
+    int32_t sq = 0;
+    for (uint32_t i = 0; i < dim; i++) {
+        volatile float q = a[i] / scale;
+        float r = roundf(q);
+        int8_t c = 0;
+        if (r == r) { if (r > 127.0f) r = 127.0f; if (r < -127.0f) r = -127.0f; c = (int8_t)r; }
+        out[i] = c; sq += (int32_t)c * (int32_t)c;
+    }
+    *scale_out = scale;
+    { volatile float x = (float)sq * scale; volatile float y = x * scale; *norm_out = y; }
+    free(a);
+}
+/* -dot_i8_turboquant (Dot / Cosine: vector_similarity.rs:161-176, 220-235 — the reference negates it) / -euclidean_i8_turboquant (:300-320, 2058-2069) */
+float orc_score_i8_turbo(const int8_t* q, float q_scale, float q_norm, const int8_t* e, float e_scale, float e_norm, uint32_t dim, uint32_t similarity) {
+    int32_t dot = orc_dot_i8(q, e, dim);
+    volatile float a = (float)dot * q_scale; volatile float d = a * e_scale;
+    if (similarity != ORC_SIM_EUCLIDEAN) return -d;
+    volatile float s = q_norm + e_norm; volatile float t = 2.0f * d; volatile float r = s - t;
+    return -(r > 0.0f ? r : 0.0f);
+}
+int orc_search_vector_i8_turbo(const int8_t* rows, const float* row_scale, const float* row_norm, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dim,
+                               uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm, uint32_t similarity, uint32_t k,
+                               orc_hit* hits, uint32_t* n_hits) {
+    topk_t tk = { hits, 0, k };
+    for (uint64_t r = 0; r < n_rows; r++) {
+        float s = orc_score_i8_turbo(query, q_scale, q_norm, rows + r * row_pitch, row_scale[r], row_norm[r], dim, similarity);
+        topk_push(&tk, doc_ids ? doc_ids[r] : r, s);
+    }
+    if (n_hits) *n_hits = tk.n;
+    return 0;
+}
+
 int orc_search_vector_i8_scaled(const int8_t* rows, const float* row_scale, const float* row_norm, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims,
                                 uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm, uint32_t similarity, uint32_t k,
                                 orc_hit* hits, uint32_t* n_hits) {

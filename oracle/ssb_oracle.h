@@ -100,6 +100,12 @@ int orc_search_lexical_filtered(const orc_index*, const uint64_t* term_keys, uin
                                 uint32_t query_type, uint32_t k, uint32_t result_type,
                                 orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
 
+/* + field filter: bit f of field_mask = indexed field f is in field_filter_set (add_result.rs:3124-3137); 0 = none */
+int orc_search_lexical_ex(const orc_index*, const uint64_t* term_keys, uint32_t n_terms, const uint64_t* not_keys, uint32_t n_not,
+                          const orc_facet_filter* filters, uint32_t n_filters, const uint64_t* set_values, uint32_t field_mask,
+                          uint32_t query_type, uint32_t k, uint32_t result_type,
+                          orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
+
 /* Reference-shaped search: block-max ordered, heap-pruned, same control flow as
  * single.rs:292-417, intersection.rs:2023-2301, union.rs:1168-1479.  Used as the timed CPU baseline
  * ("port") and cross-checked against the exhaustive search in tests. */
@@ -140,6 +146,15 @@ float orc_score_i8_scaled(const int8_t* q, float q_scale, float q_norm, const in
 int   orc_search_vector_i8_scaled(const int8_t* rows, const float* row_scale, const float* row_norm, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims,
                                   uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm, uint32_t similarity, uint32_t k,
                                   orc_hit* hits, uint32_t* n_hits);
+
+/* TurboQuantI8 (vector_similarity.rs:1825-2093): out [dim] codes, dim = next power of two >= n, seed_mask [dim] of +-1 (an input: the
+ * reference draws it from ChaCha8Rng(1234), a third-party generator).  Scores: Dot / Cosine = -(dot * s1 * s2) (the reference negates it,
+ * :161-176), Euclidean = -max(0, n1 + n2 - 2 * dot * s1 * s2). */
+void  orc_turboquant_i8(const float* v, uint32_t n, uint32_t dim, const float* seed_mask, int8_t* out, float* scale_out, float* norm_out);
+float orc_score_i8_turbo(const int8_t* q, float q_scale, float q_norm, const int8_t* e, float e_scale, float e_norm, uint32_t dim, uint32_t similarity);
+int   orc_search_vector_i8_turbo(const int8_t* rows, const float* row_scale, const float* row_norm, const uint32_t* doc_ids, uint64_t n_rows, uint32_t dim,
+                                 uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm, uint32_t similarity, uint32_t k,
+                                 orc_hit* hits, uint32_t* n_hits);
 
 /* ---- hybrid: search.rs:1962-2035 RRF k=0.6, rank from 0; then sort score desc (:2097-2121).
  * Tie order in the reference is hash-map iteration order; canonical here: doc id asc. */

@@ -56,7 +56,8 @@ class SsbLevelDesc(C.Structure):
 class SsbLexBatch(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("query_type", C.c_uint32), ("term_offsets", C.c_void_p),
                 ("term_keys", C.c_void_p), ("term_flags", C.c_void_p),
-                ("filter_offsets", C.c_void_p), ("filters", C.c_void_p), ("filter_set_values", C.c_void_p)]
+                ("filter_offsets", C.c_void_p), ("filters", C.c_void_p), ("filter_set_values", C.c_void_p),
+                ("field_masks", C.c_void_p)]
 
 
 class SsbFacetField(C.Structure):
@@ -85,7 +86,7 @@ class SsbStats(C.Structure):
 EXPORTS = [
     "ssb_abi_version", "ssb_last_error", "ssb_create", "ssb_destroy", "ssb_lexical_add_level",
     "ssb_vector_add_level_clustered", "ssb_lexical_set_field_boosts", "ssb_lexical_commit", "ssb_lexical_dict_size", "ssb_lexical_dict_export", "ssb_lexical_set_global_df",
-    "ssb_load_index_bin", "ssb_load_vector_bin", "ssb_index_bin_inspect", "ssb_set_deleted", "ssb_set_facets", "ssb_vector_add_level", "ssb_vector_count", "ssb_vector_reserve", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_vector_ex", "ssb_search_hybrid",
+    "ssb_load_index_bin", "ssb_load_vector_bin", "ssb_index_bin_inspect", "ssb_set_deleted", "ssb_set_facets", "ssb_vector_set_turboquant_mask", "ssb_vector_add_level", "ssb_vector_count", "ssb_vector_reserve", "ssb_set_vector_kernel", "ssb_search_lexical", "ssb_search_vector", "ssb_search_vector_ex", "ssb_search_hybrid",
     "ssb_rrf_fuse", "ssb_comm_unique_id", "ssb_comm_init", "ssb_comm_attach", "ssb_comm_destroy", "ssb_lexical_sync_df",
     "ssb_search_vector_keys", "ssb_search_lexical_keys", "ssb_merge_keys", "ssb_sync",
     "ssb_stream", "ssb_set_stream", "ssb_last_stats",
@@ -125,6 +126,7 @@ def lib():
         "ssb_index_bin_inspect": [vp, u64, C.POINTER(SsbIndexBinParams), vp],
         "ssb_set_deleted": [vp, vp, u64],
         "ssb_set_facets": [vp, vp, u64, u64, u32, vp, u32],
+        "ssb_vector_set_turboquant_mask": [vp, vp, u32],
         "ssb_vector_count": [vp, C.POINTER(u64)],
         "ssb_vector_reserve": [vp, u64],
         "ssb_set_vector_kernel": [vp, u32],

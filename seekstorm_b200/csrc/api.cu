@@ -106,7 +106,9 @@ struct ssb_index {
     ShardComm comm;                   // set: this handle is one shard of a `world`-way sharded index (one process per GPU)
     // vector index
     uint32_t dims = 0, dpad = 0, dpad8 = 0;
-    bool quant_i8 = false;            // Cosine + ScalarQuantizationI8: int8 corpus, exact int32 dot products
+    bool quant_i8 = false;            // ScalarQuantizationI8 / TurboQuantI8: int8 corpus, exact int32 dot products
+    bool turbo = false;               // TurboQuantI8: rows and queries are sign-flipped, FWHT-rotated and quantised at tq_dim = next_pow2(dims)
+    uint32_t tq_dim = 0; float* tq_mask = nullptr;   // the index's seed mask (+-1), ssb_vector_set_turboquant_mask
     bool dup_docs = false;            // some doc id occurs on more than one vector row (multi-chunk documents): results are de-duplicated
     DevBuf<float> rows;
     DevBuf<uint16_t> rows_hi, rows_lo;   // bf16 planes of `rows` (hi = bf16_rn(x), lo = bf16_rn(x - hi)): what the tcgen05 bf16 scan streams
@@ -219,8 +221,14 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     }
     if (ix->quant_i8) {
         SSB_TRY(c.q_i8.reserve((size_t)nq_pad * ix->dpad8, 0, st));
-        if (queries_i8 && ix->cfg.vector_similarity != SSB_SIM_COSINE) { set_error("int8 query codes are accepted for Cosine + ScalarQuantizationI8 only (Dot / Euclidean need the query scale)"); return SSB_E_UNSUPPORTED; }
-        if (ix->cfg.vector_similarity != SSB_SIM_COSINE) {
+        if (queries_i8 && (ix->turbo || ix->cfg.vector_similarity != SSB_SIM_COSINE)) { set_error("int8 query codes are accepted for Cosine + ScalarQuantizationI8 only (the other quantisers need the query scale)"); return SSB_E_UNSUPPORTED; }
+        if (ix->turbo) {
+            // the query goes through the same TurboQuant as the rows (search.rs:1545-1556, 1592-1602).  Dot / Cosine: the reference's score is
+            // -(dot * query_scale * row_scale) (vector_similarity.rs:161-176): the NEGATED query scale through the scaled epilogue is exactly that
+            SSB_TRY(c.q_scale.reserve(nq_pad, 0, st)); SSB_TRY(c.q_norm.reserve(nq_pad, 0, st));
+            SSB_TRY(vec::launch_quantize_rows_turbo_i8((const float*)qsrc, ix->dims, nq, nq_pad, ix->dims, ix->tq_dim, ix->tq_mask, c.q_i8.p, ix->dpad8, c.q_scale.p,
+                                                       c.q_norm.p, ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN, st));
+        } else if (ix->cfg.vector_similarity != SSB_SIM_COSINE) {
             // Dot / Euclidean: the query goes through the same QuantizedVector::new_scale[_norm] as the rows (search.rs:1499-1530)
             SSB_TRY(c.q_scale.reserve(nq_pad, 0, st)); SSB_TRY(c.q_norm.reserve(nq_pad, 0, st));
             SSB_TRY(vec::launch_quantize_rows_scale_i8((const float*)qsrc, ix->dims, nq, nq_pad, ix->dims, c.q_i8.p, ix->dpad8, c.q_scale.p, c.q_norm.p,
@@ -276,7 +284,7 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     }
     if (ix->quant_i8) {
         a.rows_i8 = ix->rows_i8.p; a.queries_i8 = c.q_i8.p; a.dpad8 = ix->dpad8;
-        if (ix->cfg.vector_similarity != SSB_SIM_COSINE) {
+        if (ix->turbo || ix->cfg.vector_similarity != SSB_SIM_COSINE) {
             a.i8_scaled = ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN ? 2 : 1;
             a.row_scale = ix->row_scale.p; a.row_norm = ix->row_norm.p; a.q_scale = c.q_scale.p; a.q_norm = c.q_norm.p;
         }
@@ -460,7 +468,8 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device visible: libseekstorm_b200 has no CPU fallback"); return SSB_E_NO_DEVICE; }
     if (cfg->device < 0 || cfg->device >= ndev) { set_error("device %d out of range (%d visible)", cfg->device, ndev); return SSB_E_INVALID; }
     if (cfg->vector_similarity > SSB_SIM_EUCLIDEAN) { set_error("bad vector_similarity"); return SSB_E_INVALID; }
-    if (cfg->vector_quantization > SSB_QUANT_SCALAR_I8) { set_error("bad vector_quantization"); return SSB_E_INVALID; }
+    if (cfg->vector_quantization > SSB_QUANT_TURBO_I8) { set_error("bad vector_quantization"); return SSB_E_INVALID; }
+    if (cfg->vector_quantization == SSB_QUANT_TURBO_I8 && cfg->vector_dims > 16384) { set_error("TurboQuantI8: vector_dims above 16384 unsupported"); return SSB_E_UNSUPPORTED; }
     SSB_CUDA_TRY(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
     SSB_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
@@ -478,7 +487,14 @@ int32_t ssb_create(const ssb_config* cfg, ssb_index** out) {
     ix->dims = cfg->vector_dims;
     ix->dpad = (cfg->vector_dims + 31) / 32 * 32;
     ix->dpad8 = (cfg->vector_dims + 127) / 128 * 128;
-    ix->quant_i8 = cfg->vector_quantization == SSB_QUANT_SCALAR_I8;
+    ix->quant_i8 = cfg->vector_quantization == SSB_QUANT_SCALAR_I8 || cfg->vector_quantization == SSB_QUANT_TURBO_I8;
+    ix->turbo = cfg->vector_quantization == SSB_QUANT_TURBO_I8;
+    if (ix->turbo) {
+        // TurboQuant::new: dim = next power of two >= vector_dims (vector_similarity.rs:1836-1859); the codes of a row span tq_dim bytes
+        uint32_t d = 1; while (d < cfg->vector_dims) d <<= 1;
+        ix->tq_dim = d;
+        ix->dpad8 = (d + 127) / 128 * 128;
+    }
     *out = ix.release();
     return SSB_OK;
     SSB_API_END
@@ -496,6 +512,7 @@ int32_t ssb_destroy(ssb_index* ix) {
         comm_destroy(ix->comm);
         ix->del.release();
         ix->facets.release();
+        cudaFree(ix->tq_mask); ix->tq_mask = nullptr;
         ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->row_scale.release(); ix->row_norm.release(); ix->doc_ids.release();
         cudaStreamDestroy(ix->load_st);
     }
@@ -611,7 +628,15 @@ static int32_t vector_add_level_impl(ssb_index* ix, uint32_t level_id, const flo
         SSB_TRY(ix->rows_i8.reserve((ix->n_rows + n) * ix->dpad8, ix->n_rows * ix->dpad8, st));
         SSB_CUDA_TRY(stage.alloc((size_t)n * dims));
         SSB_CUDA_TRY(cudaMemcpy2DAsync(stage.p, (size_t)dims * 4, rows, row_stride * 4, (size_t)dims * 4, n, cudaMemcpyDefault, st));
-        if (ix->cfg.vector_similarity == SSB_SIM_COSINE)
+        if (ix->turbo) {
+            // TurboQuant::quantize_f32_i8 for every similarity (vector.rs:684-695, 729-740), after normalize_f32 for Cosine (:585-596)
+            if (!ix->tq_mask) { set_error("TurboQuantI8: call ssb_vector_set_turboquant_mask before adding vectors"); return SSB_E_STATE; }
+            SSB_TRY(ix->row_scale.reserve(ix->n_rows + n, ix->n_rows, st));
+            SSB_TRY(ix->row_norm.reserve(ix->n_rows + n, ix->n_rows, st));
+            SSB_TRY(vec::launch_quantize_rows_turbo_i8(stage.p, dims, n, n, dims, ix->tq_dim, ix->tq_mask, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8,
+                                                       ix->row_scale.p + ix->n_rows, ix->row_norm.p + ix->n_rows,
+                                                       ix->cfg.vector_similarity == SSB_SIM_COSINE, 0, st));
+        } else if (ix->cfg.vector_similarity == SSB_SIM_COSINE)
             SSB_TRY(vec::launch_quantize_rows_i8(stage.p, dims, n, n, dims, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8, st));
         else {
             // Dot: QuantizedVector::new_scale; Euclidean: new_scale_norm — the NON-AFFINE variant the reference picks when the first
@@ -818,6 +843,25 @@ int32_t ssb_set_facets(ssb_index* ix, const void* rows, uint64_t first_doc_id, u
     SSB_CUDA_TRY(cudaMemcpy(ix->facets.d_keys, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
     ix->facets.n_rows = n_docs; ix->facets.first_doc = (uint32_t)first_doc_id; ix->facets.n_facets = n_fields;
     for (uint32_t f = 0; f < n_fields; f++) ix->facets.types[f] = (uint8_t)fields[f].type;
+    return SSB_OK;
+    SSB_API_END
+}
+
+// TurboQuant.seed_mask (vector_similarity.rs:1845-1859): the reference draws the +-1 mask once per index from ChaCha8Rng::seed_from_u64(1234)
+// (index.rs:2215-2216) — a third-party generator this library does not restate; the host hands over the mask it holds.
+int32_t ssb_vector_set_turboquant_mask(ssb_index* ix, const float* seed_mask, uint32_t dim) {
+    SSB_API_BEGIN
+    if (!ix || !seed_mask) { set_error("ssb_vector_set_turboquant_mask: null argument"); return SSB_E_INVALID; }
+    std::unique_lock<std::shared_mutex> g(ix->rw);
+    if (!ix->turbo) { set_error("ssb_vector_set_turboquant_mask: the index was not created with SSB_QUANT_TURBO_I8"); return SSB_E_STATE; }
+    if (ix->n_rows) { set_error("ssb_vector_set_turboquant_mask: call it before the first vector level"); return SSB_E_STATE; }
+    if (dim != ix->tq_dim) { set_error("ssb_vector_set_turboquant_mask: dim %u, expected next_power_of_two(vector_dims) = %u", dim, ix->tq_dim); return SSB_E_INVALID; }
+    std::vector<float> m(dim);
+    SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
+    SSB_CUDA_TRY(cudaMemcpy(m.data(), seed_mask, (size_t)dim * 4, cudaMemcpyDefault));
+    for (float x : m) if (x != 1.0f && x != -1.0f) { set_error("ssb_vector_set_turboquant_mask: the mask must hold +1 / -1"); return SSB_E_INVALID; }
+    if (!ix->tq_mask) SSB_CUDA_TRY(cudaMalloc(&ix->tq_mask, (size_t)dim * 4));
+    SSB_CUDA_TRY(cudaMemcpy(ix->tq_mask, m.data(), (size_t)dim * 4, cudaMemcpyHostToDevice));
     return SSB_OK;
     SSB_API_END
 }

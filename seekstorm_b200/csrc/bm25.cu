@@ -239,7 +239,7 @@ __device__ __forceinline__ uint32_t meta_cperm(uint32_t m, uint32_t c) { return 
 // block bound), the in-query-order suffix sums S[p] / R[p], the count order, the AND driver — and writes them as one
 // 128-byte record.  Thread 0 finally cuts the sorted record list into work items.
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
-                                                const uint8_t* __restrict__ q_flags /*or null*/, const uint32_t* __restrict__ f_off /*or null*/, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
+                                                const uint8_t* __restrict__ q_flags /*or null*/, const uint32_t* __restrict__ f_off /*or null*/, const uint32_t* __restrict__ f_mask /*or null*/, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
                                                 uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2,
                                                 uint32_t item_w, uint32_t first_lim, uint32_t gmax) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -289,8 +289,9 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
         if (query_type == SSB_QUERY_INTERSECTION && missing) nl = 0;
         pl.n_live = nl; pl.n_items = 0; pl.n_recs = 0; pl.n_not = nl ? nn : 0;
         // facet filters: such a query is scored and counted by the one-term-per-lane kernel, which enumerates every match
-        pl.filt_first = f_off ? f_off[q] : 0u; pl.n_filt = f_off ? f_off[q + 1] - f_off[q] : 0u; pl.pad = 0;
-        pl.fast = (nl <= v.fast_t && pl.n_filt == 0) ? 1u : 0u;
+        pl.filt_first = f_off ? f_off[q] : 0u; pl.n_filt = f_off ? f_off[q + 1] - f_off[q] : 0u;
+        pl.field_mask = (f_mask && v.n_fields > 1) ? (f_mask[q] & ((1u << v.n_fields) - 1u)) : 0u;   // one indexed field: the filter can never reject
+        pl.fast = (nl <= v.fast_t && pl.n_filt == 0 && pl.field_mask == 0) ? 1u : 0u;
     }
     for (uint32_t b = threadIdx.x; b < nlv; b += blockDim.x) {
         bound[b] = 0.f; cnt[b] = 0;
@@ -532,6 +533,46 @@ __device__ __forceinline__ bool facet_rejects(const LexView& v, uint32_t f0, uin
     return facet_rejects_impl(FacetArgs{v.facet_keys, v.facet_rows, v.filt, v.filt_sets, v.facet_first_doc}, f0, nf, doc);
 }
 
+// field_filter (`field_filter_set`, add_result.rs:3124-3137, 3558-3571): every query term the doc contains must occur in at least one
+// field of the filter — tested only when (fields the term occurs in) + (fields of the filter) <= indexed fields, otherwise they overlap for
+// certain.  The score still sums every field.  true = the doc is filtered OUT.  Out of line, on the filtered path of lex_generic only.
+struct FieldArgs { const uint32_t* e_level; const uint32_t* e_count; const uint32_t* e_bitmap; const uint32_t* post; const uint64_t* e_off; const BmSec* bm;
+                   const uint32_t* payf; uint32_t n_fields; };
+__device__ __noinline__ bool field_rejects_impl(FieldArgs v, const QueryPlan* pl, uint32_t n_live, uint32_t lv, uint32_t d, uint32_t field_mask) {
+    const uint32_t n_filter = (uint32_t)__popc(field_mask);
+    for (uint32_t t = 0; t < n_live; t++) {
+        const QTerm qt = pl->t[t];
+        uint32_t a = 0, b = qt.n;
+        while (a < b) { const uint32_t m = (a + b) >> 1; if (__ldg(&v.e_level[qt.first + m]) < lv) a = m + 1; else b = m; }
+        if (a >= qt.n || __ldg(&v.e_level[qt.first + a]) != lv) continue;
+        const uint32_t e = qt.first + a;
+        const uint32_t cnt = __ldg(&v.e_count[e]), bmi = __ldg(&v.e_bitmap[e]); const uint64_t off = __ldg(&v.e_off[e]);
+        uint32_t rank; bool found;
+        if (bmi != NONE) {
+            const BmSec* sec = v.bm + (size_t)bmi * 512 + (d >> 7);
+            const uint64_t w = __ldg(&sec->w[(d >> 6) & 1u]);
+            rank = (__ldg(&sec->meta[(d >> 6) & 1u]) & 0xFFFFu) + (uint32_t)__popcll(w & ((1ull << (d & 63)) - 1ull));
+            found = ((w >> (d & 63)) & 1ull) != 0;
+        } else {
+            uint32_t lo = 0, hi = cnt;
+            const uint32_t* p = v.post + off;
+            while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if ((__ldg(&p[m]) & 0xFFFFu) < d) lo = m + 1; else hi = m; }
+            rank = lo; found = lo < cnt && (__ldg(&p[lo]) & 0xFFFFu) == d;
+        }
+        if (!found) continue;                                            // the doc does not contain this term (OR)
+        uint32_t present = 0;
+        for (uint32_t f = 0; f < v.n_fields; f++) if (__ldg(&v.payf[(off + rank) * v.n_fields + f]) & 0xFFFFu) present |= 1u << f;
+        if ((uint32_t)__popc(present) + n_filter <= v.n_fields && !(present & field_mask)) return true;
+    }
+    return false;
+}
+// facet filters and the field filter of one query on one doc: true = filtered OUT
+__device__ __forceinline__ bool filters_reject(const LexView& v, const QueryPlan* pl, uint32_t f0, uint32_t nf, uint32_t field_mask, uint32_t n_live, uint32_t lv, uint32_t d, uint32_t doc) {
+    if (nf && facet_rejects(v, f0, nf, doc)) return true;
+    if (field_mask && field_rejects_impl(FieldArgs{v.e_level, v.e_count, v.e_bitmap, v.post, v.e_off, v.bm, v.payf, v.n_fields}, pl, n_live, lv, d, field_mask)) return true;
+    return false;
+}
+
 __device__ __forceinline__ float bound_of_word(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bool cand, float score, uint32_t doc,
@@ -550,7 +591,7 @@ __device__ __forceinline__ void insert_candidates(uint64_t& L, uint32_t& thr, bo
 }
 
 struct ItemCtx {
-    uint32_t q, lv, n, k, docbase, bound_ord, n_not, n_filt, filt_first;
+    uint32_t q, lv, n, k, docbase, bound_ord, n_not, n_filt /* facet filters + (field filter ? 1 : 0): 0 = unfiltered query */, n_facet_filt, filt_first, field_mask;
     uint64_t ceil;
     bool scoring, need_count, is_and;
 };
@@ -1050,7 +1091,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
             }
             if (c.n_filt) {
                 // a filtered query is counted here doc by doc: filter, delete set and NOT lists at once (the correction kernels skip it)
-                ok = ok && !facet_rejects(v, c.filt_first, c.n_filt, c.docbase | d) && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d));
+                ok = ok && !filters_reject(v, pl, c.filt_first, c.n_facet_filt, c.field_mask, c.n, c.lv, d, c.docbase | d) && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d));
                 matches += __popc(__ballot_sync(FULL, ok));
                 if (c.scoring) insert_candidates(L, thr, ok && ord_f32(score) >= thr, score, c.docbase | d, c.k, lane, dirty, c.ceil);
                 continue;
@@ -1101,7 +1142,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                     }
                 }
                 insert_candidates(L, thr, active && !dup && ord_f32(score) >= thr && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d))
-                                              && !(c.n_filt && facet_rejects(v, c.filt_first, c.n_filt, c.docbase | d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
+                                              && !(c.n_filt && filters_reject(v, pl, c.filt_first, c.n_facet_filt, c.field_mask, c.n, c.lv, d, c.docbase | d)), score, c.docbase | d, c.k, lane, dirty, c.ceil);
             }
         }
     }
@@ -1133,7 +1174,7 @@ __device__ __forceinline__ void process_item_generic(const LexView& v, const Que
                 }
                 bool cnt_ok = active && !dup;
                 if (c.n_filt && cnt_ok)      // filtered query: every match is tested here (filter, delete set, NOT lists; the correction kernels skip it)
-                    cnt_ok = !facet_rejects(v, c.filt_first, c.n_filt, c.docbase | d) && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d));
+                    cnt_ok = !filters_reject(v, pl, c.filt_first, c.n_facet_filt, c.field_mask, c.n, c.lv, d, c.docbase | d) && !is_deleted(v, c.docbase | d) && !(c.n_not && in_not_lists(v, pl, c.n_not, c.lv, d));
                 matches += __popc(__ballot_sync(FULL, cnt_ok));
             }
         }
@@ -1309,7 +1350,8 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
         for (uint32_t ri = 0; ri < nrec; ri++) {
             ItemCtx c;
             c.ceil = ceil; c.q = q; c.n = n_live; c.k = k; c.lv = w.recs[ri].lv; c.bound_ord = ord_f32(w.recs[ri].bound); c.n_not = __ldg(&pl->n_not);
-            c.n_filt = __ldg(&pl->n_filt); c.filt_first = __ldg(&pl->filt_first);
+            c.n_facet_filt = __ldg(&pl->n_filt); c.filt_first = __ldg(&pl->filt_first); c.field_mask = __ldg(&pl->field_mask);
+            c.n_filt = c.n_facet_filt + (c.field_mask ? 1u : 0u);
             c.scoring = want_topk && c.bound_ord >= thr;
             c.need_count = need_count; c.is_and = query_type == SSB_QUERY_INTERSECTION; c.docbase = w.recs[ri].docbase;
             if (!c.scoring && !need_count) { st_skipped++; continue; }
@@ -1343,7 +1385,7 @@ __global__ void __launch_bounds__(256) lex_not_count(LexView v, const QueryPlan*
         const uint32_t q = (uint32_t)(it / v.n_levels), lv = (uint32_t)(it % v.n_levels);
         const QueryPlan* pl = &plans[q];
         const uint32_t n_not = pl->n_not, n = pl->n_live;
-        if (!n_not || !n || pl->n_filt) continue;                      // filtered queries were counted doc by doc in lex_generic
+        if (!n_not || !n || pl->n_filt || pl->field_mask) continue;                      // filtered queries were counted doc by doc in lex_generic
         const uint32_t docbase = __ldg(&v.level_ids[lv]) << 16;
         uint32_t sub = 0;
         for (uint32_t i = 0; i < n_not; i++) {
@@ -1384,7 +1426,7 @@ __global__ void lex_del_count(LexView v, const QueryPlan* __restrict__ plans, ui
     const uint32_t q = (uint32_t)(i / v.n_del), doc = __ldg(&v.del_docs[i % v.n_del]);
     const QueryPlan* pl = &plans[q];
     const uint32_t n = pl->n_live;
-    if (n == 0 || pl->n_filt) return;                               // (filtered queries were counted doc by doc in lex_generic)
+    if (n == 0 || pl->n_filt || pl->field_mask) return;                               // (filtered queries were counted doc by doc in lex_generic)
     uint32_t lo = 0, hi = v.n_levels;                               // local level index of the doc's level id
     const uint32_t lid = doc >> 16, d = doc & 0xFFFFu;
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(&v.level_ids[m]) < lid) lo = m + 1; else hi = m; }
@@ -1431,8 +1473,8 @@ void LexIndex::free_committed() {
 
 void LexWorkspace::release() {
     cudaFree(plans); cudaFree(recs); cudaFree(item_start); cudaFree(theta); cudaFree(lock); cudaFree(count); cudaFree(ctr);
-    cudaFree(qoff); cudaFree(qkeys); cudaFree(qflags); cudaFree(stats); cudaFree(foff); cudaFree(filt); cudaFree(fsets);
-    foff = nullptr; filt = nullptr; fsets = nullptr; cap_filt = cap_fsets = 0;
+    cudaFree(qoff); cudaFree(qkeys); cudaFree(qflags); cudaFree(stats); cudaFree(foff); cudaFree(filt); cudaFree(fsets); cudaFree(fmask);
+    foff = nullptr; filt = nullptr; fsets = nullptr; fmask = nullptr; cap_filt = cap_fsets = 0;
     qflags = nullptr; plans = nullptr; recs = nullptr; item_start = nullptr; theta = nullptr; lock = nullptr; count = nullptr; ctr = nullptr;
     qoff = nullptr; qkeys = nullptr; stats = nullptr; cap_q = cap_terms = cap_levels = 0;
 }
@@ -1862,6 +1904,13 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     LexView v = view();
     bool filtered = false;
     if (q->filter_offsets) SSB_TRY(stage_filters(ws, st, q, v, &filtered));
+    const uint32_t* fmask_dev = nullptr;
+    if (q->field_masks && n_fields_ > 1) {                   // field_filter: one bitmask of indexed fields per query (host array)
+        if (is_device_ptr(q->field_masks)) { set_error("search_lexical: field_masks must be a host array"); return SSB_E_INVALID; }
+        if (!ws.fmask) SSB_CUDA_TRY(cudaMalloc(&ws.fmask, (size_t)ws.cap_q * 4));
+        SSB_CUDA_TRY(cudaMemcpyAsync(ws.fmask, q->field_masks, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+        fmask_dev = ws.fmask;
+    }
     SSB_CUDA_TRY(cudaMemsetAsync(ws.ctr, 0, 32, st));
     SSB_CUDA_TRY(cudaMemsetAsync(ws.stats, 0, sizeof(LexStats), st));
 
@@ -1874,7 +1923,7 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     // item shape (tunable for experiments; defaults measured on C3): target postings per item, levels of a query's first item, levels per item
     static const uint32_t item_w = env_u32("SSB_LEX_ITEM_W", ITEM_W, 64, 1u << 20), first_lim = env_u32("SSB_LEX_FIRST", 2, 1, GMAX),
                           gmax = env_u32("SSB_LEX_GMAX", GMAX, 1, GMAX), grid_mult = env_u32("SSB_LEX_GRID", SSB_LEX_MINB, 1, 16);
-    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, filtered ? ws.foff : nullptr, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
+    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, filtered ? ws.foff : nullptr, fmask_dev, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
                                          item_w, first_lim, gmax);
     SSB_CUDA_TRY(cudaGetLastError());
     const bool is_and = q->query_type == SSB_QUERY_INTERSECTION;

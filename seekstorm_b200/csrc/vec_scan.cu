@@ -338,6 +338,71 @@ __global__ void quantize_rows_scale_i8(const float* __restrict__ src, uint64_t s
     }
 }
 
+// TurboQuantI8 (TurboQuant::quantize_f32_i8, vector_similarity.rs:1929-1958): zero-pad the vector to tq_dim (a power of two), flip signs
+// by the index's seed mask, rotate with the normalised fast Walsh-Hadamard transform (fwht :1861-1880: butterflies h = 1, 2, 4, ..., then
+// every element / sqrt(n)), scale = max(sigma / 32, 1e-8) with sigma = ||x|| / sqrt(dim) (calculate_scale :2035-2039), codes =
+// round(x / scale) clamped to [-127, 127], norm = (sum of code^2) * scale * scale.  Cosine indexes normalise first (normalize_f32, vector.rs:585-596).
+// One CTA per row, the vector in shared memory.  Butterflies are element-wise (any schedule gives the same bits); the two sums of squares
+// are left-to-right chains of individually rounded products like the scalar reference, run by one thread.  negate: store -scale
+// (the reference's Dot / Cosine score is -(dot * s1 * s2): negating ONE scale gives exactly that through the scaled int8 epilogue).
+__global__ void __launch_bounds__(256) quantize_rows_turbo_i8(const float* __restrict__ src, uint64_t src_stride, uint64_t n, uint32_t dims, uint32_t tq_dim,
+                                                              const float* __restrict__ mask, int8_t* __restrict__ dst, uint32_t dpad8,
+                                                              float* __restrict__ scale_out, float* __restrict__ norm_out, int normalize, int negate) {
+    extern __shared__ float a[];                                  // [tq_dim]
+    __shared__ float s_val; __shared__ int s_sq;
+    const uint64_t row = blockIdx.x;
+    int8_t* o = dst + row * dpad8;
+    if (row >= n) { for (uint32_t i = threadIdx.x; i < dpad8; i += blockDim.x) o[i] = 0; if (threadIdx.x == 0) { scale_out[row] = 0.f; norm_out[row] = 0.f; } return; }
+    const float* r = src + row * src_stride;
+    for (uint32_t i = threadIdx.x; i < tq_dim; i += blockDim.x) a[i] = i < dims ? r[i] : 0.0f;
+    if (threadIdx.x == 0) s_sq = 0;
+    __syncthreads();
+    if (normalize) {
+        if (threadIdx.x == 0) { float s = 0.0f; for (uint32_t i = 0; i < dims; i++) s = __fadd_rn(s, __fmul_rn(a[i], a[i])); s_val = __fdiv_rn(1.0f, __fsqrt_rn(s)); }
+        __syncthreads();
+        const float f = s_val;
+        for (uint32_t i = threadIdx.x; i < dims; i += blockDim.x) a[i] = __fmul_rn(a[i], f);
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < tq_dim; i += blockDim.x) a[i] = __fmul_rn(a[i], __ldg(&mask[i]));
+    __syncthreads();
+    for (uint32_t h = 1; h < tq_dim; h <<= 1) {
+        for (uint32_t p = threadIdx.x; p < tq_dim / 2; p += blockDim.x) {
+            const uint32_t j = (p / h) * 2u * h + (p % h);
+            const float x = a[j], y = a[j + h];
+            a[j] = __fadd_rn(x, y); a[j + h] = __fsub_rn(x, y);
+        }
+        __syncthreads();
+    }
+    const float nrm = __fsqrt_rn((float)tq_dim);
+    for (uint32_t i = threadIdx.x; i < tq_dim; i += blockDim.x) a[i] = __fdiv_rn(a[i], nrm);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (uint32_t i = 0; i < tq_dim; i++) s = __fadd_rn(s, __fmul_rn(a[i], a[i]));
+        s_val = fmaxf(__fdiv_rn(__fdiv_rn(__fsqrt_rn(s), nrm), 32.0f), 1e-8f);
+    }
+    __syncthreads();
+    const float scale = s_val;
+    int sq = 0;
+    for (uint32_t i = threadIdx.x; i < dpad8; i += blockDim.x) {
+        int8_t q = 0;
+        if (i < tq_dim) {
+            float x = roundf(__fdiv_rn(a[i], scale));             // Rust f32::round (half away from zero), clamp, `as i8` (NaN -> 0)
+            x = fminf(fmaxf(x, -127.0f), 127.0f);
+            q = x == x ? (int8_t)x : (int8_t)0;
+        }
+        o[i] = q;
+        sq += (int)q * (int)q;
+    }
+    atomicAdd(&s_sq, sq);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        scale_out[row] = negate ? -scale : scale;
+        norm_out[row] = __fmul_rn(__fmul_rn((float)s_sq, scale), scale);
+    }
+}
+
 __global__ void fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (level_id << 16) | (local_ids ? (uint32_t)local_ids[i] : i);
@@ -427,6 +492,16 @@ int32_t launch_quantize_rows_scale_i8(const float* src, uint64_t src_stride, uin
                                       uint32_t dpad8, float* scale_out, float* norm_out, int want_norm, cudaStream_t st) {
     if (n_out == 0) return SSB_OK;
     quantize_rows_scale_i8<<<(unsigned)((n_out + 7) / 8), 256, 0, st>>>(src, src_stride, n, n_out, dims, dst, dpad8, scale_out, norm_out, want_norm);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int32_t launch_quantize_rows_turbo_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, uint32_t tq_dim, const float* mask,
+                                      int8_t* dst, uint32_t dpad8, float* scale_out, float* norm_out, int normalize, int negate, cudaStream_t st) {
+    if (n_out == 0) return SSB_OK;
+    const size_t smem = (size_t)tq_dim * 4;
+    if (smem > 48 * 1024) SSB_CUDA_TRY(cudaFuncSetAttribute(quantize_rows_turbo_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    quantize_rows_turbo_i8<<<(unsigned)n_out, 256, smem, st>>>(src, src_stride, n, dims, tq_dim, mask, dst, dpad8, scale_out, norm_out, normalize, negate);
     SSB_CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

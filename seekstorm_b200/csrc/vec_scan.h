@@ -116,6 +116,9 @@ int32_t launch_quantize_rows_i8(const float* src, uint64_t src_stride, uint64_t 
 // norm = sum(code^2) as f32 * scale * scale (want_norm).  Every step is order-independent (max, exact integer sum): bit-identical to the CPU.
 int32_t launch_quantize_rows_scale_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, int8_t* dst,
                                       uint32_t dpad8, float* scale_out, float* norm_out, int want_norm, cudaStream_t st);
+// TurboQuantI8 (vector_similarity.rs:1929-1958): pad to tq_dim, sign mask, FWHT, scale = max(sigma / 32, 1e-8); rows >= n are zero rows
+int32_t launch_quantize_rows_turbo_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, uint32_t tq_dim, const float* mask,
+                                      int8_t* dst, uint32_t dpad8, float* scale_out, float* norm_out, int normalize, int negate, cudaStream_t st);
 int32_t launch_normalize_rows(float* rows, uint64_t n, uint32_t dims, uint32_t dpad, int normalize, cudaStream_t st);
 int32_t launch_fill_doc_ids(uint32_t* out, const uint16_t* local_ids, uint32_t level_id, uint32_t n, cudaStream_t st);
 // in: [n_lists][nq][32] descending lists -> out [nq][32]

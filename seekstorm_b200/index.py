@@ -187,6 +187,8 @@ class Index:
         b = np.ascontiguousarray(np.asarray(boosts, dtype=np.float32))
         check(lib().ssb_lexical_set_field_boosts(self._h, len(b), b.ctypes.data))
         self._n_fields = len(b)
+        if len(getattr(self, "field_names", [])) != len(b):
+            self.field_names = [f"field{f}" for f in range(len(b))]      # names of the indexed fields in schema order (Index.search field_filter)
 
     def add_lexical_level(self, level_id: int, n_docs: int, term_keys, posting_offsets, doc_ids, tfs, doc_len_bytes):
         """One committed 64K-doc level in the neutral layout (arrays: numpy on host or torch on the device)."""
@@ -331,6 +333,11 @@ class Index:
             cc = np.ascontiguousarray(cluster_counts, dtype=np.uint32)
             check(lib().ssb_vector_add_level_clustered(self._h, level_id, _addr(rows), stride, _addr(local_ids), n, dims, cc.ctypes.data, len(cc)))
 
+    def set_turboquant_mask(self, seed_mask):
+        """TurboQuantI8 indexes (vector_quantization = 2): the index's +-1 sign mask (TurboQuant.seed_mask, next_power_of_two(dims) values)"""
+        m = np.ascontiguousarray(seed_mask, dtype=np.float32)
+        check(lib().ssb_vector_set_turboquant_mask(self._h, m.ctypes.data, m.size))
+
     def reserve_vectors(self, n_rows: int):
         """Capacity hint (ssb_vector_reserve): one allocation for n_rows rows instead of geometric growth while loading."""
         check(lib().ssb_vector_reserve(self._h, int(n_rows)))
@@ -354,7 +361,7 @@ class Index:
 
     # ------------------------------------------------------------------ batched shard-level search
     def _lex_batch(self, queries_keys: Sequence[Sequence[int]], query_type: QueryType, not_keys: Optional[Sequence[Sequence[int]]] = None,
-                   filters: Optional[Sequence[Sequence["FacetFilter"]]] = None):
+                   filters: Optional[Sequence[Sequence["FacetFilter"]]] = None, field_masks: Optional[Sequence[int]] = None):
         """not_keys: per query the keys of its '-' terms (not_query_list, add_result.rs:3440-3496) or None.
         filters: per query its FacetFilter list (facet_filter of search_lexical_shard) or None."""
         nots = not_keys if not_keys is not None else [[] for _ in queries_keys]
@@ -375,20 +382,24 @@ class Index:
                 flags[p] = 1
                 p += 1
         b = SsbLexBatch(len(queries_keys), int(query_type), offs.ctypes.data, keys.ctypes.data,
-                        flags.ctypes.data if not_keys is not None else None, None, None, None)
+                        flags.ctypes.data if not_keys is not None else None, None, None, None, None)
         keep = [offs, keys, flags]
         if filters is not None:
             foffs, farr, fsets = self._encode_filters(filters)
             b.filter_offsets, b.filters, b.filter_set_values = foffs.ctypes.data, C.addressof(farr), fsets.ctypes.data
             keep += [foffs, farr, fsets]
+        if field_masks is not None:       # field_filter: per query a bitmask of indexed fields (0 = none)
+            fm = np.ascontiguousarray(np.asarray(list(field_masks), dtype=np.uint32))
+            b.field_masks = fm.ctypes.data
+            keep.append(fm)
         return b, tuple(keep)
 
     def search_lexical_batch(self, queries_keys, query_type: QueryType, k: int,
-                             result_type: ResultType = ResultType.TopkCount, not_keys=None, filters=None):
+                             result_type: ResultType = ResultType.TopkCount, not_keys=None, filters=None, field_masks=None):
         """Batched search_lexical_shard.  Returns (list of [(doc_id, score)...], counts ndarray).  not_keys: '-' terms per query;
         filters: FacetFilter list per query (needs set_facets)."""
         nq = len(queries_keys)
-        b, keep = self._lex_batch(queries_keys, query_type, not_keys, filters)
+        b, keep = self._lex_batch(queries_keys, query_type, not_keys, filters, field_masks)
         hits = _hits_array(max(nq * max(k, 1), 1))
         n_hits = np.zeros(max(nq, 1), dtype=np.uint32)
         counts = np.zeros(max(nq, 1), dtype=np.uint64)
@@ -519,8 +530,12 @@ class Index:
         search like the reference does (the vector search takes no facet filter, vector.rs:1105-1115).
         Unsupported reference features (facet counting, field filters, sort, uncommitted, rewriting, phrase) raise
         NotImplementedError rather than being silently ignored."""
-        if field_filter or query_facets or result_sort or include_uncommitted:
-            raise NotImplementedError("facet counts / field filters / sort / uncommitted search are outside the GPU hot path")
+        if query_facets or result_sort or include_uncommitted:
+            raise NotImplementedError("facet counts / sort / uncommitted search are outside the GPU hot path")
+        # field_filter: names of indexed fields (self.field_names, in schema order) or their indices -> one bitmask
+        fmask = 0
+        for f in field_filter:
+            fmask |= 1 << (self.field_names.index(f) if isinstance(f, str) else int(f))
         search_mode = search_mode or SearchMode.Lexical()
         ro = ResultObject(original_query=query_string, query=query_string)
         heap = offset + length                       # search.rs:1708 per-shard length = offset+length
@@ -549,7 +564,7 @@ class Index:
             rt = ResultType.Count
         if want_lex:
             res, counts = self.search_lexical_batch([keys], qt, heap if rt != ResultType.Count else 0, rt, [nkeys] if nkeys else None,
-                                                    [list(facet_filter)] if facet_filter else None)
+                                                    [list(facet_filter)] if facet_filter else None, [fmask] if fmask else None)
             lex, total = res[0], int(counts[0])
         if want_vec:
             qv = np.asarray(query_vector, dtype=np.float32).reshape(1, -1)

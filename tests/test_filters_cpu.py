@@ -76,3 +76,41 @@ def test_filter_encoding_of_bounds():
     assert arr[1].start == int(np.float64(-1.5).view(np.uint64)) and arr[1].end == int(np.float64(np.inf).view(np.uint64))
     assert arr[2].start == 3 and arr[2].end == 2**64 - 1
     assert arr[3].kind == _lib.FILTER_SET and arr[3].set_first == 0 and arr[3].set_count == 2 and list(sv[:2]) == [4, 9]
+
+
+def test_oracle_field_filter_on_a_multifield_corpus():
+    """field_filter_set (add_result.rs:3124-3137) in the oracle against a direct numpy restatement over the per-field tfs"""
+    from helpers_mf import multifield_levels
+    from seekstorm_b200 import synth
+    n_docs, vocab, nf = 3000, 40, 3
+    levels, len_sum = multifield_levels(n_docs, vocab, nf, seed=3)
+    orc = O.OracleIndex(); orc.set_fields((1.5, 1.0, 0.5))
+    for lv in levels:
+        orc.add_level(lv)
+    orc.commit(n_docs, len_sum)
+    lv = levels[0]
+    post = {}                                  # term key -> {doc: mask of fields the term occurs in}
+    for ti, key in enumerate(lv["term_keys"]):
+        a, b = int(lv["posting_offsets"][ti]), int(lv["posting_offsets"][ti + 1])
+        post[int(key)] = {int(d): sum(1 << f for f in range(nf) if lv["tfs"][j, f]) for j, d in zip(range(a, b), lv["doc_ids"][a:b])}
+    rng = np.random.default_rng(4)
+    keys_all = [int(k) for k in lv["term_keys"]]
+    checked = 0
+    for _ in range(60):
+        keys = [keys_all[i] for i in rng.choice(len(keys_all), int(rng.integers(1, 4)), replace=False)]
+        mask = int(rng.integers(1, 8))
+        for qt in (O.QUERY_UNION, O.QUERY_INTERSECTION):
+            base, _ = orc.search(keys, qt, n_docs, O.RESULT_TOPKCOUNT)
+            got, tot = orc.search(keys, qt, n_docs, O.RESULT_TOPKCOUNT, field_mask=mask)
+            def ok(d):
+                for k in keys:
+                    pm = post[k].get(d)
+                    if pm is None:
+                        continue
+                    if bin(pm).count("1") + bin(mask).count("1") <= nf and not (pm & mask):
+                        return False
+                return True
+            want = [(d, s) for d, s in base if ok(d)]
+            assert got == want and tot == len(want), (keys, mask, qt)
+            checked += len(want) != len(base)
+    assert checked > 10

@@ -387,3 +387,41 @@ def test_vector_filter_scan_fallback_on_dense_ties(kernel):
     want = [d for d in sorted([11] + dup[:60].tolist()) if d not in (ident[0], ident[3])][:10]
     assert [d for d, _ in got[0]] == want
     ix.close()
+
+
+def _turbo_mask(dims, seed):
+    dim = 1
+    while dim < dims:
+        dim *= 2
+    return np.where(np.random.default_rng(seed).random(dim) < 0.5, 1.0, -1.0).astype(np.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sim", ["dot", "cos", "euc"])
+@pytest.mark.parametrize("n,dims", [(300, 100), (5000, 128), (70000, 200), (20000, 768), (2000, 1100)])
+def test_vector_turboquant_parity(n, dims, sim):
+    """TurboQuantI8 (vector_similarity.rs:1825-2093): sign mask + FWHT + sigma/32 quantiser on the device, tcgen05 kind::i8 scan over the
+    next_power_of_two(dims)-byte codes, scores rebuilt in the reference's order (Dot / Cosine NEGATED like the reference, :161-176) —
+    BIT-EXACT codes (implied by the scores), ids and scores vs the oracle."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    simv, osim = {"dot": (VectorSimilarity.Dot, O.SIM_DOT), "cos": (VectorSimilarity.Cosine, O.SIM_COSINE), "euc": (VectorSimilarity.Euclidean, O.SIM_EUCLIDEAN)}[sim]
+    rows = synth.gen_vectors(n, dims, 9000 + n, "cpu").numpy() * np.float32(0.53)
+    qs = synth.gen_vectors(24, dims, 9500 + n, "cpu").numpy()
+    qs[3] = rows[n // 2] + 0.01 * qs[3]
+    mask = _turbo_mask(dims, 17)
+    ix = Index(0, vector_dims=dims, vector_similarity=simv, vector_quantization=2)
+    with pytest.raises(Exception):
+        ix.add_vectors(rows[:10])                      # no mask yet
+    ix.set_turboquant_mask(mask)
+    ix.add_vectors(rows)
+    rc, rs, rn = O.turboquant_rows_i8(rows, mask, sim == "cos")
+    qc, qsc, qn = O.turboquant_rows_i8(qs, mask, sim == "cos")
+    for k in (1, 10, 40):
+        got = ix.search_vector_batch(qs, k)
+        for i in range(0, len(qs), 3):
+            want = O.search_vector_i8_turbo(rc, rs, rn, qc[i], float(qsc[i]), float(qn[i]), osim, k)
+            assert [d for d, _ in got[i]] == [d for d, _ in want], (i, k, got[i][:3], want[:3])
+            assert [np.float32(s) for _, s in got[i]] == [np.float32(s) for _, s in want]
+    if sim == "euc":                                   # Euclidean keeps its meaning: the planted neighbour is the best hit
+        assert ix.search_vector_batch(qs[3:4], 1)[0][0][0] == n // 2
+    ix.close()

@@ -162,3 +162,31 @@ def test_filter_scan_margin_bounds_the_fp16_error():
                 assert top <= cand
                 if norm and d == 768:
                     assert len(cand) <= k + 6, (k, len(cand))          # the bound is not wasteful: the candidate set fits the 32-entry list
+
+
+def test_turboquant_oracle_against_a_hadamard_matrix():
+    """orc_turboquant_i8 (the scalar TurboQuant::quantize_f32_i8, vector_similarity.rs:1929-1958): its butterfly FWHT equals the Sylvester
+    Hadamard matrix / sqrt(dim) in f64, scale = max(||x|| / sqrt(dim) / 32, 1e-8), codes round(x / scale) clamped to +-127,
+    norm = sum(code^2) * scale^2; the quantised dot estimates the f32 dot; an all-zero vector takes the 1e-8 floor."""
+    from scipy.linalg import hadamard
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    for d, dim in ((100, 128), (768, 1024), (64, 64), (5, 8)):
+        mask = np.where(rng.random(dim) < 0.5, 1.0, -1.0).astype(np.float32)
+        rows = (rng.normal(size=(6, d)) * 0.7).astype(np.float32)
+        rows[5] = 0
+        c, s, nrm = O.turboquant_rows_i8(rows, mask)
+        x = np.zeros((6, dim)); x[:, :d] = rows; x *= mask
+        y = x @ (hadamard(dim).astype(np.float64) / np.sqrt(dim)).T
+        sc = np.maximum(np.linalg.norm(y, axis=1) / np.sqrt(dim) / 32, 1e-8)
+        want = np.clip(np.round(y / sc[:, None]), -127, 127)
+        assert np.abs(want - c).max() <= 1 and (want != c).mean() < 0.01          # f32 vs f64 rounding at .5 boundaries only
+        assert np.allclose(s, sc, rtol=1e-5) and s[5] == np.float32(1e-8) and not c[5].any()
+        assert np.allclose(nrm, (c.astype(np.int64) ** 2).sum(1) * s.astype(np.float64) ** 2, rtol=1e-5)
+        est = (c[:5].astype(np.int32) @ c[0].astype(np.int32)) * s[:5] * s[0]
+        ref = rows[:5] @ rows[0]
+        assert np.abs(est - ref).max() < 0.05 * np.abs(ref).max() + 0.05
+    # Cosine: normalize_f32 first
+    c1, s1, _ = O.turboquant_rows_i8(rows[:2], mask, True)
+    c2, s2, _ = O.turboquant_rows_i8(np.stack([O.normalize(rows[0]), O.normalize(rows[1])]), mask, False)
+    assert (c1 == c2).all() and (s1 == s2).all()
