@@ -43,8 +43,11 @@ extern "C" {
 enum { SSB_OK = 0, SSB_E_INVALID = -1, SSB_E_CUDA = -2, SSB_E_NOMEM = -3, SSB_E_STATE = -4,
        SSB_E_UNSUPPORTED = -5, SSB_E_NO_DEVICE = -6 };
 
-/* QueryType (search.rs, enum QueryType): Union / Intersection.  Phrase is out of scope. */
-enum { SSB_QUERY_UNION = 0, SSB_QUERY_INTERSECTION = 1 };
+/* QueryType (search.rs, enum QueryType): Union / Intersection / Phrase.  A PHRASE batch lists every query's terms in phrase order,
+ * repeated terms included ("to be or not to be" = 6 keys); a doc matches when it contains all of them and token i occurs at position
+ * p + i for some p (add_result.rs:3586-3684); scores and counts as for an intersection of the unique terms.  Needs levels loaded with
+ * ssb_level_desc.positions (one indexed field); NOT terms are not accepted in a phrase batch. */
+enum { SSB_QUERY_UNION = 0, SSB_QUERY_INTERSECTION = 1, SSB_QUERY_PHRASE = 2 };
 /* ResultType (search.rs:150-175): Count / Topk / TopkCount (default) */
 enum { SSB_RESULT_COUNT = 0, SSB_RESULT_TOPK = 1, SSB_RESULT_TOPKCOUNT = 2 };
 /* VectorSimilarity (vector_similarity.rs:20-30) */
@@ -119,6 +122,9 @@ typedef struct {
     const uint16_t* doc_ids;          /* [n_postings] ascending within a term                            */
     const uint16_t* tfs;              /* [n_postings]; F fields: [n_postings][F], 0 = the term does not occur in that field           */
     const uint8_t*  doc_len_bytes;    /* [n_docs];     F fields: [F][n_docs] (document_length_compressed_array[field], index.rs:770-776) */
+    const uint16_t* positions;        /* [sum of tfs] or NULL: the term positions of every posting, in posting order, ascending inside a   */
+                                      /* posting (what get_next_position_singlefield decodes, add_result.rs:2036-2197); needed by          */
+                                      /* SSB_QUERY_PHRASE only; either every level carries them or none; one indexed field                  */
 } ssb_level_desc;
 
 /* ---- facets and facet filters ---------------------------------------------------- */

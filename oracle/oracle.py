@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libssb_oracle.so")
 
-QUERY_UNION, QUERY_INTERSECTION = 0, 1
+QUERY_UNION, QUERY_INTERSECTION, QUERY_PHRASE = 0, 1, 2
 RESULT_COUNT, RESULT_TOPK, RESULT_TOPKCOUNT = 0, 1, 2
 SIM_DOT, SIM_COSINE, SIM_EUCLIDEAN = 0, 1, 2
 
@@ -137,6 +137,22 @@ class OracleIndex:
         d = OrcLevel(lv["level_id"], lv["n_docs"], len(keep[0]), 0, *[_ptr(a) for a in keep])
         rc = lib().orc_index_add_level(self._h, C.byref(d))
         assert rc == 0
+        if lv.get("positions") is not None:      # term positions (phrase queries)
+            pos = np.ascontiguousarray(lv["positions"], dtype=np.uint16)
+            lib().orc_index_set_last_level_positions.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+            assert lib().orc_index_set_last_level_positions(self._h, _ptr(pos), pos.size) == 0
+
+    def search_phrase(self, seq_keys, k, result_type):
+        """QueryType::Phrase: seq_keys = the phrase's term keys in order (repeats included)"""
+        keys = np.ascontiguousarray(np.array(seq_keys, dtype=np.uint64))
+        buf = (OrcHit * max(k, 1))()
+        n = C.c_uint32(0)
+        tot = C.c_uint64(0)
+        f = lib().orc_search_lexical_phrase
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        rc = f(self._h, _ptr(keys), len(keys), k, result_type, buf, C.byref(n), C.byref(tot))
+        assert rc == 0, rc
+        return _hits_to_list(buf, n.value), int(tot.value)
 
     def commit(self, n_docs: int, len_sum: int):
         self.n_docs, self.len_sum = n_docs, len_sum

@@ -70,6 +70,7 @@ typedef struct {
     uint16_t* tfs;
     uint8_t* doc_len_bytes;
     float* max_comp; /* [n_terms] max over postings of tf*(K+1)/(tf+cache[len]) (block-max basis) */
+    uint16_t* positions; uint32_t* pos_off;   /* term positions of every posting, in posting order (phrase queries); pos_off = prefix sums of tfs */
 } lvl_t;
 
 typedef struct { uint64_t key; uint32_t level, idx; } dict_ent;
@@ -107,7 +108,7 @@ void orc_index_free(orc_index* ix) {
     for (uint32_t i = 0; i < ix->n_levels; i++) {
         lvl_t* l = &ix->levels[i];
         free(l->term_keys); free(l->posting_offsets); free(l->doc_ids); free(l->tfs);
-        free(l->doc_len_bytes); free(l->max_comp);
+        free(l->doc_len_bytes); free(l->max_comp); free(l->positions); free(l->pos_off);
     }
     free(ix->levels); free(ix->dict); free(ix->deleted); free(ix->facet_rows); free(ix);
 }
@@ -197,6 +198,21 @@ int orc_index_add_level(orc_index* ix, const orc_level* d) {
     l->tfs = (uint16_t*)dup_mem(d->tfs, (size_t)np * 2 * nf_of(ix));
     l->doc_len_bytes = (uint8_t*)dup_mem(d->doc_len_bytes, (size_t)d->n_docs * nf_of(ix));
     ix->committed = 0;
+    return 0;
+}
+
+/* term positions of the level added last (single field): positions [sum of tfs], posting order, ascending inside a posting */
+int orc_index_set_last_level_positions(orc_index* ix, const uint16_t* positions, uint64_t n_positions) {
+    if (!ix || !ix->n_levels || nf_of(ix) != 1) return -1;
+    lvl_t* l = &ix->levels[ix->n_levels - 1];
+    uint32_t np = l->n_terms ? l->posting_offsets[l->n_terms] : 0;
+    free(l->positions); free(l->pos_off);
+    l->pos_off = (uint32_t*)malloc(((size_t)np + 1) * 4);
+    uint64_t acc = 0;
+    for (uint32_t j = 0; j < np; j++) { l->pos_off[j] = (uint32_t)acc; acc += l->tfs[j]; }
+    l->pos_off[np] = (uint32_t)acc;
+    if (acc != n_positions) { free(l->pos_off); l->pos_off = NULL; l->positions = NULL; return -2; }
+    l->positions = (uint16_t*)dup_mem(positions, (size_t)n_positions * 2);
     return 0;
 }
 
@@ -412,6 +428,76 @@ int orc_search_lexical_ex(const orc_index* ix, const uint64_t* keys, uint32_t n_
         }
     }
     free(acc); free(cnt); free(excl);
+    if (n_hits) *n_hits = tk.n;
+    if (count_total) *count_total = total;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ phrase search (QueryType::Phrase)
+ * seq = the phrase's terms in order, repeats included (non_unique_query_list; term_index_nonunique = the index in seq).  A doc matches
+ * iff it contains every term and some start position p has seq[i] at p + i for all i (add_result.rs:3586-3684: the k-way merge over the
+ * position lists aligned by term_index_nonunique stops at the first common value, phrasematch_count >= 1).  Checked here the NAIVE way:
+ * every position of seq[0] is tried as the start and each following token is looked up by binary search.  Score = BM25 of the unique
+ * terms in first-occurrence order (query_list), count = matching docs; delete set honoured. */
+static int has_position(const lvl_t* l, uint32_t j, uint32_t want) {
+    uint32_t lo = l->pos_off[j], hi = l->pos_off[j + 1];
+    while (lo < hi) { uint32_t m = (lo + hi) / 2; if (l->positions[m] < want) lo = m + 1; else hi = m; }
+    return lo < l->pos_off[j + 1] && l->positions[lo] == want;
+}
+int orc_search_lexical_phrase(const orc_index* ix, const uint64_t* seq, uint32_t n_seq, uint32_t k, uint32_t result_type,
+                              orc_hit* hits, uint32_t* n_hits, uint64_t* count_total) {
+    if (!ix || !ix->committed || n_seq > ORC_MAX_TERMS || nf_of(ix) != 1) return -1;
+    if (n_hits) *n_hits = 0;
+    if (count_total) *count_total = 0;
+    if (n_seq < 2) return orc_search_lexical(ix, seq, n_seq, ORC_QUERY_INTERSECTION, k, result_type, hits, n_hits, count_total);
+    uint64_t ukeys[ORC_MAX_TERMS]; uint32_t uidx[ORC_MAX_TERMS], nu = 0;
+    for (uint32_t i = 0; i < n_seq; i++) {
+        uint32_t u = nu;
+        for (uint32_t t = 0; t < nu; t++) if (ukeys[t] == seq[i]) u = t;
+        if (u == nu) ukeys[nu++] = seq[i];
+        uidx[i] = u;
+    }
+    qterm_t qt[ORC_MAX_TERMS];
+    resolve_terms(ix, ukeys, nu, qt);
+    for (uint32_t t = 0; t < nu; t++) if (qt[t].df == 0) return 0;
+    uint32_t kk = k; if ((uint64_t)kk > ix->n_docs) kk = (uint32_t)ix->n_docs;
+    if (result_type == ORC_RESULT_COUNT) kk = 0;
+    topk_t tk = { hits, 0, kk };
+    float* acc = (float*)malloc(65536 * sizeof(float));
+    uint8_t* cnt = (uint8_t*)malloc(65536);
+    uint32_t* pj = (uint32_t*)malloc((size_t)nu * 65536 * 4);
+    uint64_t total = 0;
+    for (uint32_t li = 0; li < ix->n_levels; li++) {
+        const lvl_t* l = &ix->levels[li];
+        int all = 1;
+        for (uint32_t t = 0; t < nu; t++) if (term_in_level(ix, &qt[t], li) < 0) { all = 0; break; }
+        if (!all) continue;
+        if (!l->positions) { free(acc); free(cnt); free(pj); return -3; }
+        memset(acc, 0, l->n_docs * sizeof(float)); memset(cnt, 0, l->n_docs);
+        for (uint32_t t = 0; t < nu; t++) {
+            uint32_t ti = ix->dict[term_in_level(ix, &qt[t], li)].idx;
+            for (uint32_t j = l->posting_offsets[ti]; j < l->posting_offsets[ti + 1]; j++) {
+                uint16_t d = l->doc_ids[j];
+                acc[d] += orc_bm25_term(qt[t].idf, l->tfs[j], ix->cache[l->doc_len_bytes[d]]);
+                cnt[d]++; pj[(size_t)t * 65536 + d] = j;
+            }
+        }
+        for (uint32_t d = 0; d < l->n_docs; d++) {
+            if (cnt[d] != nu) continue;
+            if (ix->n_deleted && is_deleted(ix, ((uint64_t)l->level_id << 16) | d)) continue;
+            uint32_t j0 = pj[(size_t)uidx[0] * 65536 + d];
+            int match = 0;
+            for (uint32_t a = l->pos_off[j0]; a < l->pos_off[j0 + 1] && !match; a++) {
+                uint32_t p = l->positions[a]; int ok = 1;
+                for (uint32_t i = 1; i < n_seq && ok; i++) ok = has_position(l, pj[(size_t)uidx[i] * 65536 + d], p + i);
+                match = ok;
+            }
+            if (!match) continue;
+            total++;
+            if (kk) topk_push(&tk, ((uint64_t)l->level_id << 16) | d, acc[d]);
+        }
+    }
+    free(acc); free(cnt); free(pj);
     if (n_hits) *n_hits = tk.n;
     if (count_total) *count_total = total;
     return 0;

@@ -106,6 +106,12 @@ int orc_search_lexical_ex(const orc_index*, const uint64_t* term_keys, uint32_t 
                           uint32_t query_type, uint32_t k, uint32_t result_type,
                           orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
 
+/* ---- phrase queries (QueryType::Phrase, add_result.rs:3586-3684): positions of the level added last (single field; [sum of tfs], posting
+ * order, ascending inside a posting), then seq = the phrase's terms in order, repeats included */
+int orc_index_set_last_level_positions(orc_index*, const uint16_t* positions, uint64_t n_positions);
+int orc_search_lexical_phrase(const orc_index*, const uint64_t* seq, uint32_t n_seq, uint32_t k, uint32_t result_type,
+                              orc_hit* hits, uint32_t* n_hits, uint64_t* count_total);
+
 /* Reference-shaped search: block-max ordered, heap-pruned, same control flow as
  * single.rs:292-417, intersection.rs:2023-2301, union.rs:1168-1479.  Used as the timed CPU baseline
  * ("port") and cross-checked against the exhaustive search in tests. */

@@ -15,7 +15,7 @@ SSB_OK = 0
 K_MAX = 32
 MAX_QUERY_TERMS = 32
 
-QUERY_UNION, QUERY_INTERSECTION = 0, 1
+QUERY_UNION, QUERY_INTERSECTION, QUERY_PHRASE = 0, 1, 2
 RESULT_COUNT, RESULT_TOPK, RESULT_TOPKCOUNT = 0, 1, 2
 SIM_DOT, SIM_COSINE, SIM_EUCLIDEAN = 0, 1, 2
 
@@ -50,7 +50,7 @@ class SsbIndexBinParams(C.Structure):
 class SsbLevelDesc(C.Structure):
     _fields_ = [("level_id", C.c_uint32), ("n_docs", C.c_uint32), ("n_terms", C.c_uint32), ("n_fields", C.c_uint32),
                 ("term_keys", C.c_void_p), ("posting_offsets", C.c_void_p), ("doc_ids", C.c_void_p),
-                ("tfs", C.c_void_p), ("doc_len_bytes", C.c_void_p)]
+                ("tfs", C.c_void_p), ("doc_len_bytes", C.c_void_p), ("positions", C.c_void_p)]
 
 
 class SsbLexBatch(C.Structure):

@@ -86,6 +86,18 @@ __global__ void validate_level(const uint16_t* __restrict__ ids, const uint16_t*
     if (!ok) atomicAdd(bad, 1u);
 }
 
+// positions of one level: the posting's tf positions must ascend strictly (get_next_position_singlefield decodes ascending deltas)
+__global__ void validate_positions(const uint16_t* __restrict__ pos, const uint32_t* __restrict__ off, const uint16_t* __restrict__ tfs, uint32_t n, uint32_t* bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t o = off[i], tf = tfs[i];
+    for (uint32_t j = 1; j < tf; j++) if (pos[o + j] <= pos[o + j - 1]) { atomicAdd(bad, 1u); return; }
+}
+__global__ void widen_tf(const uint16_t* __restrict__ tfs, uint32_t* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tfs[i];
+}
+
 __global__ void build_postings(const uint16_t* __restrict__ ids, const uint16_t* __restrict__ tfs, const uint8_t* __restrict__ len_bytes,
                                uint32_t* __restrict__ post, uint32_t* __restrict__ pay, uint32_t n,
                                uint32_t nf, uint32_t n_docs, uint32_t* __restrict__ payf /*several fields: [n][nf]*/) {
@@ -239,7 +251,7 @@ __device__ __forceinline__ uint32_t meta_cperm(uint32_t m, uint32_t c) { return 
 // block bound), the in-query-order suffix sums S[p] / R[p], the count order, the AND driver — and writes them as one
 // 128-byte record.  Thread 0 finally cuts the sorted record list into work items.
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
-                                                const uint8_t* __restrict__ q_flags /*or null*/, const uint32_t* __restrict__ f_off /*or null*/, const uint32_t* __restrict__ f_mask /*or null*/, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
+                                                const uint8_t* __restrict__ q_flags /*or null*/, const uint32_t* __restrict__ f_off /*or null*/, const uint32_t* __restrict__ f_mask /*or null*/, uint32_t phrase, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
                                                 uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2,
                                                 uint32_t item_w, uint32_t first_lim, uint32_t gmax) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -272,6 +284,7 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t nl = 0, nn = 0; bool missing = false;
+        uint32_t n_phr = 0;
         for (uint32_t t = 0; t < nt; t++) {
             if (sflag[t] & SSB_TERM_NOT) {                  // '-' terms: exclusion lists, never scored (an unknown NOT term excludes nothing)
                 bool dup = false;
@@ -282,16 +295,21 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             if (nl >= SSB_MAX_QUERY_TERMS) continue;
             if (!st[t].n) { missing = true; continue; }
             bool dup = false;                       // the reference scores unique_terms (search.rs:3023-3039): drop repeated keys
-            for (uint32_t u = 0; u < nl; u++) dup = dup || pl.t[u].first == st[t].first;
+            uint32_t uidx = nl;
+            for (uint32_t u = 0; u < nl; u++) if (pl.t[u].first == st[t].first) { dup = true; uidx = u; }
             if (!dup) pl.t[nl++] = st[t];
+            // phrase: token n_phr of the phrase (term_index_nonunique) is unique term uidx (non_unique_query_list, add_result.rs:3594-3607)
+            if (phrase && n_phr < SSB_MAX_QUERY_TERMS) pl.phr[n_phr++] = (uint8_t)uidx;
         }
+        if (phrase && (missing || nl == 0)) n_phr = 0;
+        pl.n_phr = (phrase && n_phr >= 2 && nl) ? n_phr : 0u;      // a one-token phrase is a plain term query
         // search.rs:3290-3296: AND with an unknown term -> empty result; OR drops the term
         if (query_type == SSB_QUERY_INTERSECTION && missing) nl = 0;
         pl.n_live = nl; pl.n_items = 0; pl.n_recs = 0; pl.n_not = nl ? nn : 0;
         // facet filters: such a query is scored and counted by the one-term-per-lane kernel, which enumerates every match
         pl.filt_first = f_off ? f_off[q] : 0u; pl.n_filt = f_off ? f_off[q + 1] - f_off[q] : 0u;
         pl.field_mask = (f_mask && v.n_fields > 1) ? (f_mask[q] & ((1u << v.n_fields) - 1u)) : 0u;   // one indexed field: the filter can never reject
-        pl.fast = (nl <= v.fast_t && pl.n_filt == 0 && pl.field_mask == 0) ? 1u : 0u;
+        pl.fast = (nl <= v.fast_t && pl.n_filt == 0 && pl.field_mask == 0 && pl.n_phr == 0) ? 1u : 0u;
     }
     for (uint32_t b = threadIdx.x; b < nlv; b += blockDim.x) {
         bound[b] = 0.f; cnt[b] = 0;
@@ -566,10 +584,62 @@ __device__ __noinline__ bool field_rejects_impl(FieldArgs v, const QueryPlan* pl
     }
     return false;
 }
+// Phrase check (add_result.rs:3586-3684): the doc (already known to contain every term) matches iff some start position p has token i of
+// the phrase at p + i for every i — the reference finds it by a k-way merge of the tokens' position lists aligned by their index in the
+// phrase (term_index_nonunique); the same merge here, one thread per candidate doc, cursors on the thread's stack (rare path, out of line).
+struct PhraseArgs { const uint32_t* e_level; const uint32_t* e_count; const uint32_t* e_bitmap; const uint32_t* post; const uint64_t* e_off; const BmSec* bm;
+                    const uint32_t* pay; const uint16_t* positions; const uint32_t* pos_off; const uint64_t* lvl_pos_base; };
+__device__ __noinline__ bool phrase_rejects_impl(PhraseArgs v, const QueryPlan* pl, uint32_t n_live, uint32_t lv, uint32_t d) {
+    uint64_t ubase[SSB_MAX_QUERY_TERMS]; uint32_t utf[SSB_MAX_QUERY_TERMS];
+    const uint64_t lbase = __ldg(&v.lvl_pos_base[lv]);
+    for (uint32_t t = 0; t < n_live; t++) {
+        const QTerm qt = pl->t[t];
+        uint32_t a = 0, b = qt.n;
+        while (a < b) { const uint32_t m = (a + b) >> 1; if (__ldg(&v.e_level[qt.first + m]) < lv) a = m + 1; else b = m; }
+        if (a >= qt.n || __ldg(&v.e_level[qt.first + a]) != lv) return true;
+        const uint32_t e = qt.first + a;
+        const uint32_t cnt = __ldg(&v.e_count[e]), bmi = __ldg(&v.e_bitmap[e]); const uint64_t off = __ldg(&v.e_off[e]);
+        uint32_t rank; bool found;
+        if (bmi != NONE) {
+            const BmSec* sec = v.bm + (size_t)bmi * 512 + (d >> 7);
+            const uint64_t w = __ldg(&sec->w[(d >> 6) & 1u]);
+            rank = (__ldg(&sec->meta[(d >> 6) & 1u]) & 0xFFFFu) + (uint32_t)__popcll(w & ((1ull << (d & 63)) - 1ull));
+            found = ((w >> (d & 63)) & 1ull) != 0;
+        } else {
+            uint32_t lo = 0, hi = cnt;
+            const uint32_t* p = v.post + off;
+            while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if ((__ldg(&p[m]) & 0xFFFFu) < d) lo = m + 1; else hi = m; }
+            rank = lo; found = lo < cnt && (__ldg(&p[lo]) & 0xFFFFu) == d;
+        }
+        if (!found) return true;
+        ubase[t] = lbase + __ldg(&v.pos_off[off + rank]);
+        utf[t] = __ldg(&v.pay[off + rank]) & 0xFFFFu;
+    }
+    const uint32_t m = pl->n_phr;
+    uint32_t cur[SSB_MAX_QUERY_TERMS];
+    for (uint32_t i = 0; i < m; i++) cur[i] = 0;
+    // anchor = token 0; value searched: a start position s with positions(token i) containing s + i for every i
+    const uint32_t u0 = pl->phr[0];
+    while (cur[0] < utf[u0]) {
+        const uint32_t s = __ldg(&v.positions[ubase[u0] + cur[0]]);
+        bool all = true; uint32_t next_s = s;
+        for (uint32_t i = 1; i < m; i++) {
+            const uint32_t u = pl->phr[i];
+            while (cur[i] < utf[u] && (uint32_t)__ldg(&v.positions[ubase[u] + cur[i]]) < s + i) cur[i]++;
+            if (cur[i] >= utf[u]) return true;                              // a token's positions are exhausted: no (further) match
+            const uint32_t p = __ldg(&v.positions[ubase[u] + cur[i]]);
+            if (p != s + i) { all = false; next_s = p - i; break; }          // p > s + i: the start must move up to at least p - i
+        }
+        if (all) return false;                                               // phrasematch_count >= 1
+        while (cur[0] < utf[u0] && (uint32_t)__ldg(&v.positions[ubase[u0] + cur[0]]) < next_s) cur[0]++;
+    }
+    return true;
+}
 // facet filters and the field filter of one query on one doc: true = filtered OUT
 __device__ __forceinline__ bool filters_reject(const LexView& v, const QueryPlan* pl, uint32_t f0, uint32_t nf, uint32_t field_mask, uint32_t n_live, uint32_t lv, uint32_t d, uint32_t doc) {
     if (nf && facet_rejects(v, f0, nf, doc)) return true;
     if (field_mask && field_rejects_impl(FieldArgs{v.e_level, v.e_count, v.e_bitmap, v.post, v.e_off, v.bm, v.payf, v.n_fields}, pl, n_live, lv, d, field_mask)) return true;
+    if (pl->n_phr && phrase_rejects_impl(PhraseArgs{v.e_level, v.e_count, v.e_bitmap, v.post, v.e_off, v.bm, v.pay, v.positions, v.pos_off, v.lvl_pos_base}, pl, n_live, lv, d)) return true;
     return false;
 }
 
@@ -1351,7 +1421,7 @@ __global__ void __launch_bounds__(256) lex_generic(LexView v, const QueryPlan* _
             ItemCtx c;
             c.ceil = ceil; c.q = q; c.n = n_live; c.k = k; c.lv = w.recs[ri].lv; c.bound_ord = ord_f32(w.recs[ri].bound); c.n_not = __ldg(&pl->n_not);
             c.n_facet_filt = __ldg(&pl->n_filt); c.filt_first = __ldg(&pl->filt_first); c.field_mask = __ldg(&pl->field_mask);
-            c.n_filt = c.n_facet_filt + (c.field_mask ? 1u : 0u);
+            c.n_filt = c.n_facet_filt + (c.field_mask ? 1u : 0u) + (__ldg(&pl->n_phr) ? 1u : 0u);
             c.scoring = want_topk && c.bound_ord >= thr;
             c.need_count = need_count; c.is_and = query_type == SSB_QUERY_INTERSECTION; c.docbase = w.recs[ri].docbase;
             if (!c.scoring && !need_count) { st_skipped++; continue; }
@@ -1385,7 +1455,7 @@ __global__ void __launch_bounds__(256) lex_not_count(LexView v, const QueryPlan*
         const uint32_t q = (uint32_t)(it / v.n_levels), lv = (uint32_t)(it % v.n_levels);
         const QueryPlan* pl = &plans[q];
         const uint32_t n_not = pl->n_not, n = pl->n_live;
-        if (!n_not || !n || pl->n_filt || pl->field_mask) continue;                      // filtered queries were counted doc by doc in lex_generic
+        if (!n_not || !n || pl->n_filt || pl->field_mask || pl->n_phr) continue;                      // filtered queries were counted doc by doc in lex_generic
         const uint32_t docbase = __ldg(&v.level_ids[lv]) << 16;
         uint32_t sub = 0;
         for (uint32_t i = 0; i < n_not; i++) {
@@ -1426,7 +1496,7 @@ __global__ void lex_del_count(LexView v, const QueryPlan* __restrict__ plans, ui
     const uint32_t q = (uint32_t)(i / v.n_del), doc = __ldg(&v.del_docs[i % v.n_del]);
     const QueryPlan* pl = &plans[q];
     const uint32_t n = pl->n_live;
-    if (n == 0 || pl->n_filt || pl->field_mask) return;                               // (filtered queries were counted doc by doc in lex_generic)
+    if (n == 0 || pl->n_filt || pl->field_mask || pl->n_phr) return;                               // (filtered queries were counted doc by doc in lex_generic)
     uint32_t lo = 0, hi = v.n_levels;                               // local level index of the doc's level id
     const uint32_t lid = doc >> 16, d = doc & 0xFFFFu;
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(&v.level_ids[m]) < lid) lo = m + 1; else hi = m; }
@@ -1468,6 +1538,7 @@ void LexIndex::free_committed() {
     d_dict_keys_ = nullptr; d_term_first_ = nullptr; d_term_idf_ = nullptr; d_term_df_ = nullptr;
     d_e_level_ = nullptr; d_e_off_ = nullptr; d_e_count_ = nullptr; d_e_maxcomp_ = nullptr; d_e_bitmap_ = nullptr;
     d_bm_words_ = nullptr; d_bm_ = nullptr; d_bm_q8_ = nullptr; d_level_ids_ = nullptr; d_cache_ = nullptr;
+    cudaFree(d_lvl_pos_base_); d_lvl_pos_base_ = nullptr;
     committed_ = false;
 }
 
@@ -1569,6 +1640,37 @@ int32_t LexIndex::add_level(const ssb_level_desc* d) {
         SSB_TRY(post_.reserve(n_post_ + 160, n_post_, st_));
         SSB_TRY(pay_.reserve(n_post_ + 160, n_post_, st_));
     }
+    // term positions (phrase queries): all levels or none
+    const int has_pos = d->positions ? 1 : 0;
+    if (np) {
+        if (has_positions_ >= 0 && has_positions_ != has_pos) { set_error("add_level %u: either every level carries positions or none", d->level_id); return SSB_E_INVALID; }
+        if (has_pos && nf > 1) { set_error("add_level: positions (phrase queries) are supported for one indexed field"); return SSB_E_UNSUPPORTED; }
+    }
+    uint64_t level_positions = 0;
+    if (np && has_pos) {
+        SSB_TRY(pos_off_.reserve(n_post_ + np, n_post_, st_));
+        uint32_t* off = pos_off_.p + n_post_;
+        widen_tf<<<(np + 255) / 256, 256, 0, st_>>>(d_tfs, off, np);
+        SSB_CUDA_TRY(cudaGetLastError());
+        uint32_t last_tf = 0, last_off = 0;
+        SSB_CUDA_TRY(cudaMemcpyAsync(&last_tf, off + np - 1, 4, cudaMemcpyDeviceToHost, st_));
+        thrust::exclusive_scan(thrust::cuda::par.on(st_), thrust::device_ptr<uint32_t>(off), thrust::device_ptr<uint32_t>(off + np), thrust::device_ptr<uint32_t>(off));
+        SSB_CUDA_TRY(cudaMemcpyAsync(&last_off, off + np - 1, 4, cudaMemcpyDeviceToHost, st_));
+        SSB_CUDA_TRY(cudaStreamSynchronize(st_));
+        level_positions = (uint64_t)last_off + last_tf;
+        if (level_positions >= 0xFFFFFFFFull) { set_error("add_level %u: more than 2^32 positions in one level", d->level_id); return SSB_E_UNSUPPORTED; }
+        SSB_TRY(positions_.reserve(n_positions_ + level_positions + 8, n_positions_, st_));
+        SSB_CUDA_TRY(to_device(positions_.p + n_positions_, d->positions, (size_t)level_positions * 2, st_));
+        SSB_CUDA_TRY(cudaMemsetAsync(t_bad.p, 0, 4, st_));
+        validate_positions<<<(np + 255) / 256, 256, 0, st_>>>(positions_.p + n_positions_, off, d_tfs, np, t_bad.p);
+        SSB_CUDA_TRY(cudaGetLastError());
+        SSB_CUDA_TRY(cudaMemcpyAsync(&bad, t_bad.p, 4, cudaMemcpyDeviceToHost, st_));
+        SSB_CUDA_TRY(cudaStreamSynchronize(st_));
+        if (bad) { set_error("add_level %u: %u postings whose positions do not ascend strictly", d->level_id, bad); return SSB_E_INVALID; }
+    }
+    if (np) has_positions_ = has_pos;
+    h_lvl_pos_base_.push_back(n_positions_);
+    n_positions_ += level_positions;
     LexLevel l{};
     l.level_id = d->level_id; l.n_docs = d->n_docs; l.n_terms = d->n_terms; l.post_base = n_post_; l.n_post = np;
     l.d_term_keys = t_keys.release(); l.d_posting_offsets = t_offs.release();
@@ -1615,6 +1717,7 @@ LexView LexIndex::view() const {
     v.payf = payf_.p; v.compf = compf_.p; v.n_fields = n_fields_; v.fast_t = n_fields_ > 1 ? 0u : FAST_T;
     for (int f = 0; f < 4; f++) v.boost[f] = boosts_[f];
     if (del_ && del_->n) { v.del_slot = del_->d_slot; v.del_words = del_->d_words; v.del_docs = del_->d_docs; v.n_del = del_->n; }
+    if (has_positions_ == 1 && d_lvl_pos_base_) { v.positions = positions_.p; v.pos_off = pos_off_.p; v.lvl_pos_base = d_lvl_pos_base_; }
     if (facets_ && facets_->n_facets) { v.facet_keys = facets_->d_keys; v.facet_rows = facets_->n_rows; v.facet_first_doc = facets_->first_doc; v.n_facets = facets_->n_facets; }
     return v;
 }
@@ -1638,6 +1741,10 @@ int32_t LexIndex::commit(uint64_t n_docs, uint64_t len_sum) {
     SSB_CUDA_TRY(cudaMemcpyAsync(d_cache_, cache, 256 * 4, cudaMemcpyHostToDevice, st_));
     std::vector<uint32_t> lids(nlv ? nlv : 1); std::vector<uint64_t> lbase(nlv ? nlv : 1); std::vector<const uint32_t*> loffs(nlv ? nlv : 1);
     for (uint32_t i = 0; i < nlv; i++) { lids[i] = levels_[i].level_id; lbase[i] = levels_[i].post_base; loffs[i] = levels_[i].d_posting_offsets; }
+    if (has_positions_ == 1) {
+        SSB_CUDA_TRY(cudaMalloc(&d_lvl_pos_base_, (h_lvl_pos_base_.size() + 1) * 8));
+        SSB_CUDA_TRY(cudaMemcpyAsync(d_lvl_pos_base_, h_lvl_pos_base_.data(), h_lvl_pos_base_.size() * 8, cudaMemcpyHostToDevice, st_));
+    }
     SSB_CUDA_TRY(cudaMalloc(&d_level_ids_, lids.size() * 4));
     SSB_CUDA_TRY(cudaMemcpyAsync(d_level_ids_, lids.data(), lids.size() * 4, cudaMemcpyHostToDevice, st_));
 
@@ -1875,7 +1982,11 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     if (!committed_) { set_error("search before ssb_lexical_commit"); return SSB_E_STATE; }
     if (!q || (q->n_queries && (!q->term_offsets || !keys_out_dev))) { set_error("search_lexical: null argument"); return SSB_E_INVALID; }
     if (k > SSB_K_MAX) { set_error("k=%u exceeds SSB_K_MAX=%u", k, SSB_K_MAX); return SSB_E_UNSUPPORTED; }
-    if (result_type > SSB_RESULT_TOPKCOUNT || q->query_type > SSB_QUERY_INTERSECTION) { set_error("bad result_type/query_type"); return SSB_E_INVALID; }
+    if (result_type > SSB_RESULT_TOPKCOUNT || q->query_type > SSB_QUERY_PHRASE) { set_error("bad result_type/query_type"); return SSB_E_INVALID; }
+    const uint32_t phrase = q->query_type == SSB_QUERY_PHRASE ? 1u : 0u;
+    if (phrase && has_positions_ != 1) { set_error("phrase query: the index holds no term positions (ssb_level_desc.positions)"); return SSB_E_STATE; }
+    if (phrase && q->term_flags) { set_error("phrase query: NOT terms are not accepted inside a phrase batch"); return SSB_E_UNSUPPORTED; }
+    const uint32_t qt_eff = phrase ? (uint32_t)SSB_QUERY_INTERSECTION : q->query_type;   // a phrase is an intersection + the position check
     if (result_type != SSB_RESULT_COUNT && k == 0) result_type = SSB_RESULT_COUNT;   // search.rs:2472-2478
     const uint32_t nq = q->n_queries;
     if (nq == 0) return SSB_OK;
@@ -1923,10 +2034,10 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     // item shape (tunable for experiments; defaults measured on C3): target postings per item, levels of a query's first item, levels per item
     static const uint32_t item_w = env_u32("SSB_LEX_ITEM_W", ITEM_W, 64, 1u << 20), first_lim = env_u32("SSB_LEX_FIRST", 2, 1, GMAX),
                           gmax = env_u32("SSB_LEX_GMAX", GMAX, 1, GMAX), grid_mult = env_u32("SSB_LEX_GRID", SSB_LEX_MINB, 1, 16);
-    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, filtered ? ws.foff : nullptr, fmask_dev, q->query_type, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
+    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, filtered ? ws.foff : nullptr, fmask_dev, phrase, qt_eff, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
                                          item_w, first_lim, gmax);
     SSB_CUDA_TRY(cudaGetLastError());
-    const bool is_and = q->query_type == SSB_QUERY_INTERSECTION;
+    const bool is_and = qt_eff == SSB_QUERY_INTERSECTION;
     const bool want_topk = result_type != SSB_RESULT_COUNT && k > 0;
     const bool need_count = result_type != SSB_RESULT_TOPK;
     const uint32_t kk = k ? k : 1;
@@ -1945,21 +2056,21 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
         if (launches) *launches += 1;
     }
     if (need_count) {
-        lex_count<<<n_sms_ * 6, 128, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, q->query_type, ws.ctr, ws.count, ws.stats);
+        lex_count<<<n_sms_ * 6, 128, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, qt_eff, ws.ctr, ws.count, ws.stats);
         SSB_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }
     // queries with 5..16 live terms (the kernel returns at once when the batch has none)
-    lex_generic<<<n_sms_ * 2, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, q->query_type, result_type, kk, ws.ctr, ws.theta, ws.lock, ws.count, glist, ws.stats, ceil_dev);
+    lex_generic<<<n_sms_ * 2, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, qt_eff, result_type, kk, ws.ctr, ws.theta, ws.lock, ws.count, glist, ws.stats, ceil_dev);
     SSB_CUDA_TRY(cudaGetLastError());
     if (need_count) {     // returns at once unless some query of the batch carries NOT terms
-        lex_not_count<<<n_sms_ * 4, 256, 0, st>>>(v, ws.plans, nq, q->query_type, ws.ctr, ws.count);
+        lex_not_count<<<n_sms_ * 4, 256, 0, st>>>(v, ws.plans, nq, qt_eff, ws.ctr, ws.count);
         SSB_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }
     if (need_count && v.n_del) {
         const uint64_t pairs = (uint64_t)nq * v.n_del;
-        lex_del_count<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(v, ws.plans, nq, q->query_type, ws.count);
+        lex_del_count<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(v, ws.plans, nq, qt_eff, ws.count);
         SSB_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }

@@ -112,6 +112,10 @@ struct LexView {
     uint64_t facet_rows;
     uint32_t facet_first_doc;
     uint32_t n_facets;
+    // term positions (phrase queries): positions[lvl_pos_base[lv] + pos_off[posting] .. + tf), ascending; null = the index holds none
+    const uint16_t* positions;
+    const uint32_t* pos_off;      // [n_postings] offset of the posting's positions relative to its level's base
+    const uint64_t* lvl_pos_base; // [n_levels]
     // per batch (filled by search_keys): the queries' facet filters, QueryPlan.filt_first / n_filt index into them
     const FiltDev* filt;
     const uint64_t* filt_sets;
@@ -131,7 +135,9 @@ struct DeleteSet {
 
 struct QTerm { uint32_t first, n; float idf; uint32_t df; };
 // fast: the query takes the record path (lex_score / lex_count): <= fast_t live terms and no facet filter; otherwise lex_generic
-struct QueryPlan { QTerm t[SSB_MAX_QUERY_TERMS]; QTerm tn[SSB_MAX_NOT_TERMS]; uint32_t n_live, n_items, n_recs, n_not; uint32_t filt_first, n_filt, fast, field_mask /* field_filter: bit f = indexed field f, 0 = none */; };
+struct QueryPlan { QTerm t[SSB_MAX_QUERY_TERMS]; QTerm tn[SSB_MAX_NOT_TERMS]; uint32_t n_live, n_items, n_recs, n_not; uint32_t filt_first, n_filt, fast, field_mask /* field_filter: bit f = indexed field f, 0 = none */;
+                   // phrase query: token i of the phrase is unique term phr[i] (index into t[]); n_phr = 0: not a phrase
+                   uint8_t phr[SSB_MAX_QUERY_TERMS]; uint32_t n_phr, pad[3]; };
 
 // One (query, level) record, built by lex_plan for queries with <= 4 live terms; 128 bytes = one cache line.
 // Slots are in QUERY order (scores are summed in query order, add_result.rs:1450-1452); cnt == 0 marks a term
@@ -208,6 +214,9 @@ private:
     std::vector<LexLevel> levels_;
     DevBuf<uint32_t> post_, pay_;
     DevBuf<float> comp_;
+    // positions of every posting (phrase queries): one arena in posting order + per posting the offset inside its level
+    DevBuf<uint16_t> positions_; DevBuf<uint32_t> pos_off_; uint64_t n_positions_ = 0; int has_positions_ = -1 /* -1 unknown, 0 none, 1 all levels */;
+    std::vector<uint64_t> h_lvl_pos_base_; uint64_t* d_lvl_pos_base_ = nullptr;
     uint32_t n_fields_ = 1; float boosts_[4] = {1.f, 1.f, 1.f, 1.f};
     DevBuf<uint32_t> payf_; DevBuf<float> compf_;   // several indexed fields: [n_post][n_fields]
     uint64_t n_post_ = 0;

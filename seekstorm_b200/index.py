@@ -28,9 +28,10 @@ from ._lib import SsbConfig, SsbHit, SsbLevelDesc, SsbLexBatch, SsbStats, check,
 
 
 class QueryType(enum.IntEnum):
-    """search.rs `QueryType` (Phrase / Not are outside the hot-path scope)."""
+    """search.rs `QueryType`.  Phrase: the query's terms in phrase order, repeats included; needs levels loaded with positions."""
     Union = 0
     Intersection = 1
+    Phrase = 2
 
 
 class ResultType(enum.IntEnum):
@@ -190,11 +191,12 @@ class Index:
         if len(getattr(self, "field_names", [])) != len(b):
             self.field_names = [f"field{f}" for f in range(len(b))]      # names of the indexed fields in schema order (Index.search field_filter)
 
-    def add_lexical_level(self, level_id: int, n_docs: int, term_keys, posting_offsets, doc_ids, tfs, doc_len_bytes):
-        """One committed 64K-doc level in the neutral layout (arrays: numpy on host or torch on the device)."""
+    def add_lexical_level(self, level_id: int, n_docs: int, term_keys, posting_offsets, doc_ids, tfs, doc_len_bytes, positions=None):
+        """One committed 64K-doc level in the neutral layout (arrays: numpy on host or torch on the device).  positions: u16 [sum of tfs], the
+        term positions of every posting in posting order (phrase queries), or None."""
         n_terms = int(term_keys.shape[0])
         d = SsbLevelDesc(level_id, n_docs, n_terms, getattr(self, "_n_fields", 1), _addr(term_keys), _addr(posting_offsets), _addr(doc_ids),
-                         _addr(tfs), _addr(doc_len_bytes))
+                         _addr(tfs), _addr(doc_len_bytes), _addr(positions))
         check(lib().ssb_lexical_add_level(self._h, C.byref(d)))
 
     def add_synth_level(self, lv):
@@ -541,8 +543,11 @@ class Index:
         heap = offset + length                       # search.rs:1708 per-shard length = offset+length
         # tokenizer stand-in: whitespace, '+' = mandatory (tokenizer.rs:546-563); unique terms (search.rs:3023-3039)
         toks = query_string.split()
-        if any(t.startswith('"') for t in toks):
-            raise NotImplementedError("phrase queries are outside the GPU hot path")
+        phrase = query_type_default == QueryType.Phrase
+        if len(query_string) >= 2 and query_string.startswith('"') and query_string.endswith('"'):     # "..." = a phrase (tokenizer.rs:546-563)
+            phrase, toks = True, query_string[1:-1].split()
+        elif any(t.startswith('"') for t in toks):
+            raise NotImplementedError("a phrase mixed with other terms is outside the GPU hot path")
         not_terms = [t[1:] for t in toks if t.startswith("-") and len(t) > 1]          # '-' operator: not_query_list (tokenizer.rs:546-563)
         toks = [t for t in toks if not t.startswith("-")]
         qt = query_type_default
@@ -551,9 +556,15 @@ class Index:
         terms = []
         for t in toks:
             t = t.lstrip("+")
-            if t and t not in terms:
+            if t and (phrase or t not in terms):       # a phrase keeps its repeated terms: their order is the query
                 terms.append(t)
-        ro.query_terms = list(terms)
+        if phrase and len(terms) >= 2:
+            qt = QueryType.Phrase
+            if not_terms:
+                raise NotImplementedError("NOT terms next to a phrase are outside the GPU hot path")
+        elif phrase:
+            qt = QueryType.Intersection
+        ro.query_terms = list(dict.fromkeys(terms))
         keys = [self.term_key_fn(t) for t in terms]
         nkeys = [self.term_key_fn(t) for t in dict.fromkeys(not_terms)]
         lex, vec, total = [], [], 0

@@ -34,7 +34,7 @@ def test_abi_version_and_struct_sizes():
     assert ctypes.sizeof(_lib.SsbVecQuery) == 40
     assert ctypes.sizeof(_lib.SsbHit) == 16
     assert ctypes.sizeof(_lib.SsbConfig) == 32
-    assert ctypes.sizeof(_lib.SsbLevelDesc) == 16 + 5 * 8
+    assert ctypes.sizeof(_lib.SsbLevelDesc) == 16 + 6 * 8
     assert ctypes.sizeof(_lib.SsbLexBatch) == 8 + 7 * 8
     assert ctypes.sizeof(_lib.SsbFacetFilter) == 32 and ctypes.sizeof(_lib.SsbFacetField) == 8
     assert ctypes.sizeof(_lib.SsbStats) == 96

@@ -114,3 +114,26 @@ def test_oracle_field_filter_on_a_multifield_corpus():
             assert got == want and tot == len(want), (keys, mask, qt)
             checked += len(want) != len(base)
     assert checked > 10
+
+
+def test_oracle_phrase_search_against_substring_search():
+    """orc_search_lexical_phrase (add_result.rs:3586-3684) on a corpus of real token sequences: the matching docs are exactly those whose
+    token sequence contains the phrase; scores are the intersection's scores of the unique terms."""
+    from helpers_phrase import contains_phrase, phrase_queries, sequence_corpus
+    from helpers import query_keys
+    n, vocab = 3000, 60
+    docs, levels, ls = sequence_corpus(n, vocab, 11, docs_per_level=2000)
+    orc = oracle_index(levels, n, ls)
+    n_match = 0
+    for ph in phrase_queries(docs, 12, 150, vocab):
+        keys = query_keys([ph])[0]
+        got, tot = orc.search_phrase(keys, n, O.RESULT_TOPKCOUNT)
+        want_docs = {d for d in range(n) if contains_phrase(docs[d], ph)}
+        # doc id = level << 16 | local, 2000 docs per level
+        got_docs = {(d >> 16) * 2000 + (d & 0xFFFF) for d, _ in got}
+        assert got_docs == want_docs and tot == len(want_docs), (ph, len(got_docs), len(want_docs))
+        uniq = list(dict.fromkeys(keys))
+        base, _ = orc.search(uniq, O.QUERY_INTERSECTION, n, O.RESULT_TOPKCOUNT)
+        assert got == [(d, s) for d, s in base if ((d >> 16) * 2000 + (d & 0xFFFF)) in want_docs]
+        n_match += bool(want_docs)
+    assert n_match > 80
