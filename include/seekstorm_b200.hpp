@@ -33,7 +33,7 @@ inline void check(int32_t rc) {
     if (rc != SSB_OK) throw Error(rc, std::string("libseekstorm_b200 error ") + std::to_string(rc) + ": " + ssb_last_error());
 }
 
-enum class QueryType : uint32_t { Union = SSB_QUERY_UNION, Intersection = SSB_QUERY_INTERSECTION };
+enum class QueryType : uint32_t { Union = SSB_QUERY_UNION, Intersection = SSB_QUERY_INTERSECTION, Phrase = SSB_QUERY_PHRASE };
 enum class ResultType : uint32_t { Count = SSB_RESULT_COUNT, Topk = SSB_RESULT_TOPK, TopkCount = SSB_RESULT_TOPKCOUNT };
 enum class VectorSimilarity : uint32_t { Dot = SSB_SIM_DOT, Cosine = SSB_SIM_COSINE, Euclidean = SSB_SIM_EUCLIDEAN };
 enum class Quantization : uint32_t { None = SSB_QUANT_NONE, ScalarQuantizationI8 = SSB_QUANT_SCALAR_I8, TurboQuantI8 = SSB_QUANT_TURBO_I8 };   // vector.rs:230-240
@@ -151,10 +151,15 @@ public:
         QueryType qt = query_type_default;
         std::vector<std::string> terms, not_terms;
         {
-            std::istringstream is(query_string);
+            // "..." (or QueryType::Phrase as the default type) = a phrase: its terms in order, repeats kept (non_unique_query_list)
+            std::string qs = query_string;
+            bool phrase = query_type_default == QueryType::Phrase;
+            if (qs.size() >= 2 && qs.front() == '"' && qs.back() == '"') { phrase = true; qs = qs.substr(1, qs.size() - 2); }
+            std::istringstream is(qs);
             std::string tok; bool all_plus = true, any = false;
             while (is >> tok) {
-                if (tok[0] == '"') throw Error(SSB_E_UNSUPPORTED, "phrase queries are outside the GPU hot path");
+                if (tok[0] == '"') throw Error(SSB_E_UNSUPPORTED, "a phrase mixed with other terms is outside the GPU hot path");
+                if (phrase) { if (tok[0] == '+') tok.erase(0, 1); if (!tok.empty()) terms.push_back(tok); continue; }
                 if (tok[0] == '-') {                                            // '-' operator: not_query_list (add_result.rs:3440-3496)
                     tok.erase(0, 1);
                     bool dup = tok.empty();
@@ -170,8 +175,9 @@ public:
                 if (!dup) terms.push_back(tok);
             }
             if (any && all_plus) qt = QueryType::Intersection;
+            if (phrase) qt = terms.size() >= 2 ? QueryType::Phrase : QueryType::Intersection;
         }
-        ro.query_terms = terms;
+        for (auto& t : terms) { bool dup = false; for (auto& u : ro.query_terms) dup = dup || u == t; if (!dup) ro.query_terms.push_back(t); }
         ResultType rt = result_type;
         if (length == 0 && rt == ResultType::TopkCount) rt = ResultType::Count;   // search.rs:2472-2478
         std::vector<ssb_hit> lex, vec;
