@@ -58,8 +58,11 @@ enum { SSB_SIM_DOT = 0, SSB_SIM_COSINE = 1, SSB_SIM_EUCLIDEAN = 2 };
  *   Dot      : per-vector scale = max|x|/127, codes round(x/scale) (QuantizedVector::new_scale, vector_similarity.rs:1340-1353);
  *              score = dot_i32 as f32 * query_scale * row_scale (dot_i8_quantized, :1754-1758).
  *   Euclidean: new_scale_norm (:1356-1371), the NON-AFFINE variant the reference uses for non-integer data (vector.rs:651-660);
- *              score = -max(0, query_norm + row_norm - 2*dot) (euclidean_i8_quantized, :1721-1734).  Integer-valued 0..255 data
- *              (affine quantisation) is not built: SSB_E_UNSUPPORTED.
+ *              score = -max(0, query_norm + row_norm - 2*dot) (euclidean_i8_quantized, :1721-1734).  When the FIRST vector of the index is
+ *              integer-valued in 0..255 (SIFT-like data) the reference switches the shard to its AFFINE quantiser for good
+ *              (new_scale_norm_affine, :1414-1463: codes = round(x / scale) + zero_point with scale / zero point from the running min / max
+ *              of everything indexed so far; euclidean_i8_quantized_affine, :1770-1795) — so does this library: rows must then be added
+ *              in the reference's ingestion order, queries are quantised with the state the index has reached.
  * All three are bit-exact with the scalar CPU arithmetic (integer accumulation on tcgen05 kind::i8, reference operation order). */
 enum { SSB_QUANT_NONE = 0, SSB_QUANT_SCALAR_I8 = 1,
        /* TurboQuantI8 (vector_similarity.rs:1825-2093): every vector (after normalize_f32 for Cosine) is zero-padded to the next power of

@@ -323,6 +323,44 @@ def search_vector_i8_scaled(rows_i8, row_scale, row_norm, query_i8, q_scale, q_n
     return _hits_to_list(buf, n.value)
 
 
+def quantize_affine_rows_i8(rows: np.ndarray, state=None, update_state: bool = True):
+    """QuantizedVector::new_scale_norm_affine row after row with the shard's running (min, max) state (start: f32::MAX / f32::MIN).
+    update_state False = every row sees a COPY of the state (what the query side does, search.rs:1514-1530).
+    -> (codes int8 [n, d], scale, norm, zero_point int32, sum_q int32, state (min, max))"""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    n, d = rows.shape
+    out = np.zeros((n, d), dtype=np.int8); scale = np.zeros(n, dtype=np.float32); norm = np.zeros(n, dtype=np.float32)
+    zp = np.zeros(n, dtype=np.int32); sq = np.zeros(n, dtype=np.int32)
+    f = lib().orc_quantize_affine_i8
+    f.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    fmax = float(np.finfo(np.float32).max)
+    smin, smax = (C.c_float(fmax), C.c_float(-fmax)) if state is None else (C.c_float(state[0]), C.c_float(state[1]))
+    s, nn, z, su = C.c_float(0), C.c_float(0), C.c_int32(0), C.c_int32(0)
+    for i in range(n):
+        a, b = (smin, smax) if update_state else (C.c_float(smin.value), C.c_float(smax.value))
+        f(_ptr(rows[i]), d, C.byref(a), C.byref(b), _ptr(out[i]), C.byref(s), C.byref(nn), C.byref(z), C.byref(su))
+        scale[i], norm[i], zp[i], sq[i] = s.value, nn.value, z.value, su.value
+    return out, scale, norm, zp, sq, (smin.value, smax.value)
+
+
+def search_vector_i8_affine(rows_i8, row_scale, row_norm, row_zp, row_sum, query_i8, q_scale, q_norm, q_zp, q_sum, k, doc_ids=None):
+    rows_i8 = np.ascontiguousarray(rows_i8, dtype=np.int8)
+    rs = np.ascontiguousarray(row_scale, dtype=np.float32); rn = np.ascontiguousarray(row_norm, dtype=np.float32)
+    rz = np.ascontiguousarray(row_zp, dtype=np.int32); ru = np.ascontiguousarray(row_sum, dtype=np.int32)
+    q = np.ascontiguousarray(query_i8, dtype=np.int8)
+    ids = None if doc_ids is None else np.ascontiguousarray(doc_ids, dtype=np.uint32)
+    buf = (OrcHit * max(k, 1))()
+    n = C.c_uint32(0)
+    f = lib().orc_search_vector_i8_affine
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
+                  C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    rc = f(_ptr(rows_i8), _ptr(rs), _ptr(rn), _ptr(rz), _ptr(ru), None if ids is None else _ptr(ids), rows_i8.shape[0], rows_i8.shape[1], rows_i8.strides[0],
+           _ptr(q), C.c_float(q_scale), C.c_float(q_norm), int(q_zp), int(q_sum), k, buf, C.byref(n))
+    assert rc == 0
+    return _hits_to_list(buf, n.value)
+
+
 def turboquant_rows_i8(rows: np.ndarray, seed_mask: np.ndarray, normalize_first: bool = False):
     """TurboQuant::quantize_f32_i8 per row (Cosine: normalize_f32 first, vector.rs:585-596) -> (codes int8 [n, dim], scale [n], norm [n]); dim = len(seed_mask)"""
     rows = np.ascontiguousarray(rows, dtype=np.float32)

@@ -969,6 +969,65 @@ float orc_score_i8_scaled(const int8_t* q, float q_scale, float q_norm, const in
     volatile float s = q_norm + e_norm; volatile float t = 2.0f * d; volatile float r = s - t;
     return -(r > 0.0f ? r : 0.0f);
 }
+/* ---- affine Euclidean SQ (integer-valued 0..255 data): QuantizedVector::new_scale_norm_affine (vector_similarity.rs:1414-1463), raster_range
+ * (:1465-1472), euclidean_i8_quantized_affine (:1770-1795).  min_state / max_state = shard.min_vector_value / max_vector_value (initially
+ * f32::MAX / f32::MIN), updated in place exactly like the reference does (note its quirk: when a vector raises the maximum, the state
+ * receives the RASTERED RANGE, not the maximum). */
+static float orc_raster_range(float range) {
+    if (!(range > 1.0f)) return range;
+    uint64_t v = (uint64_t)(int64_t)range + 1u, p = 1;
+    while (p < v) p <<= 1;
+    return (float)(p - 1);
+}
+void orc_quantize_affine_i8(const float* v, uint32_t n, float* min_state, float* max_state, int8_t* out, float* scale_out, float* norm_out,
+                            int32_t* zero_point_out, int32_t* sum_q_out) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (uint32_t i = 0; i < n; i++) { mn = fminf(mn, v[i]); mx = fmaxf(mx, v[i]); }
+    if (mn < *min_state) *min_state = mn; else mn = *min_state;
+    if (mx > *max_state) { volatile float d = mx - mn; *max_state = orc_raster_range(d); } else mx = *max_state;
+    volatile float d = mx - mn;
+    volatile float range = orc_raster_range(d);
+    volatile float scale = range / 255.0f;
+    volatile float q = mn / scale;
+    volatile float zf = -128.0f - q;
+    float z = roundf(zf);
+    if (z < -128.0f) z = -128.0f;
+    if (z > 127.0f) z = 127.0f;
+    int32_t zp = z == z ? (int32_t)z : 0;
+    int32_t sq = 0, sum = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        volatile float t = v[i] / scale;
+        float r = roundf(t);
+        int64_t xi = r != r ? 0 : (r >= 2147483648.0f ? 2147483647LL : (r <= -2147483648.0f ? -2147483648LL : (int64_t)r));
+        int64_t s = xi + zp;
+        int8_t c = (int8_t)(s < -128 ? -128 : (s > 127 ? 127 : s));
+        out[i] = c; sq += (int32_t)c * c; sum += c;
+    }
+    int32_t norm_i = sq - 2 * zp * sum + (int32_t)n * zp * zp;
+    *scale_out = scale; *zero_point_out = zp; *sum_q_out = sum;
+    { volatile float a = (float)norm_i * scale; volatile float b = a * scale; *norm_out = b; }
+}
+/* -euclidean_i8_quantized_affine, query = v1 */
+float orc_score_i8_affine(const int8_t* q, float q_scale, float q_norm, int32_t q_zp, int32_t q_sum, const int8_t* e, float e_scale, float e_norm,
+                          int32_t e_zp, int32_t e_sum, uint32_t n) {
+    int32_t dot = orc_dot_i8(q, e, n);
+    dot = dot - e_zp * q_sum - q_zp * e_sum + (int32_t)n * q_zp * e_zp;
+    volatile float a = (float)dot * q_scale; volatile float d = a * e_scale;
+    volatile float s = q_norm + e_norm; volatile float t = 2.0f * d; volatile float r = s - t;
+    return -(r > 0.0f ? r : 0.0f);
+}
+int orc_search_vector_i8_affine(const int8_t* rows, const float* row_scale, const float* row_norm, const int32_t* row_zp, const int32_t* row_sum,
+                                const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims, uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm,
+                                int32_t q_zp, int32_t q_sum, uint32_t k, orc_hit* hits, uint32_t* n_hits) {
+    topk_t tk = { hits, 0, k };
+    for (uint64_t r = 0; r < n_rows; r++) {
+        float s = orc_score_i8_affine(query, q_scale, q_norm, q_zp, q_sum, rows + r * row_pitch, row_scale[r], row_norm[r], row_zp[r], row_sum[r], dims);
+        topk_push(&tk, doc_ids ? doc_ids[r] : r, s);
+    }
+    if (n_hits) *n_hits = tk.n;
+    return 0;
+}
+
 /* ---- TurboQuantI8 (vector_similarity.rs:1825-2093): the vector is zero-padded to the next power of two, sign-flipped by the index's seed
  * mask (+-1, drawn once from ChaCha8Rng(seed 1234) — a third-party generator, so the mask is an INPUT here), rotated by the normalised
  * fast Walsh-Hadamard transform and quantised with scale = max(sigma / 32, 1e-8), sigma = ||x|| / sqrt(dim).  Scalar variant

@@ -153,6 +153,16 @@ int   orc_search_vector_i8_scaled(const int8_t* rows, const float* row_scale, co
                                   uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm, uint32_t similarity, uint32_t k,
                                   orc_hit* hits, uint32_t* n_hits);
 
+/* affine Euclidean SQ for integer-valued 0..255 data (vector_similarity.rs:1414-1472, 1770-1795); min_state / max_state are the shard's
+ * running min_vector_value / max_vector_value (start: FLT_MAX / -FLT_MAX), updated in place */
+void  orc_quantize_affine_i8(const float* v, uint32_t n, float* min_state, float* max_state, int8_t* out, float* scale_out, float* norm_out,
+                             int32_t* zero_point_out, int32_t* sum_q_out);
+float orc_score_i8_affine(const int8_t* q, float q_scale, float q_norm, int32_t q_zp, int32_t q_sum, const int8_t* e, float e_scale, float e_norm,
+                          int32_t e_zp, int32_t e_sum, uint32_t n);
+int   orc_search_vector_i8_affine(const int8_t* rows, const float* row_scale, const float* row_norm, const int32_t* row_zp, const int32_t* row_sum,
+                                  const uint32_t* doc_ids, uint64_t n_rows, uint32_t dims, uint32_t row_pitch, const int8_t* query, float q_scale, float q_norm,
+                                  int32_t q_zp, int32_t q_sum, uint32_t k, orc_hit* hits, uint32_t* n_hits);
+
 /* TurboQuantI8 (vector_similarity.rs:1825-2093): out [dim] codes, dim = next power of two >= n, seed_mask [dim] of +-1 (an input: the
  * reference draws it from ChaCha8Rng(1234), a third-party generator).  Scores: Dot / Cosine = -(dot * s1 * s2) (the reference negates it,
  * :161-176), Euclidean = -max(0, n1 + n2 - 2 * dot * s1 * s2). */

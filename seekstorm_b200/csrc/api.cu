@@ -73,7 +73,7 @@ struct SearchCtx {
     cudaStream_t st = nullptr;       // stream this context launches on (its own, or the caller's after ssb_set_stream)
     cudaStream_t own_st = nullptr;
     LexWorkspace lex;
-    DevBuf<float> qpad, qstage, qhi, qlo, q_scale, q_norm; DevBuf<int8_t> q_i8;
+    DevBuf<float> qpad, qstage, qhi, qlo, q_scale, q_norm; DevBuf<int8_t> q_i8; DevBuf<int> q_aff;
     DevBuf<uint64_t> ceil, scratch, keys_a, keys_b, counts, gather;
     DevBuf<float> ivf_scores; DevBuf<uint32_t> ivf_sel; DevBuf<uint64_t> ivf_obs; std::vector<uint64_t> h_obs;   // IVF probe (vec_ivf.cu)
     std::vector<uint64_t> h_ceil, h_keys_a, h_keys_b, h_counts;
@@ -114,6 +114,9 @@ struct ssb_index {
     DevBuf<uint16_t> rows_hi, rows_lo;   // bf16 planes of `rows` (hi = bf16_rn(x), lo = bf16_rn(x - hi)): what the tcgen05 bf16 scan streams
     DevBuf<int8_t> rows_i8;
     DevBuf<float> row_scale, row_norm;   // Dot / Euclidean + ScalarQuantizationI8: per-vector scale (and norm), QuantizedVector vector_similarity.rs:1340-1371
+    // Euclidean + ScalarQuantizationI8 over integer-valued 0..255 data: the AFFINE quantiser (new_scale_norm_affine, vector_similarity.rs:1414-1463)
+    bool affine = false; float aff_min = 3.402823466e+38f /* f32::MAX */, aff_max = -3.402823466e+38f /* f32::MIN */;   // shard.min / max_vector_value
+    DevBuf<int> row_aff;                 // int2 per row: (zero_point, dims * zero_point - sum_q)
     DevBuf<uint32_t> doc_ids;
     DevBuf<uint16_t> rows_h16;        // filter scan: fp16 plane half_rn(rows * vec_scale)
     DevBuf<uint32_t> vec_err;         // filter scan: {max_r |a_r*scale - h_r|, max_r |h_r|, scratch} as f32 bits (launch_rows_f16_err)
@@ -228,6 +231,11 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
             SSB_TRY(c.q_scale.reserve(nq_pad, 0, st)); SSB_TRY(c.q_norm.reserve(nq_pad, 0, st));
             SSB_TRY(vec::launch_quantize_rows_turbo_i8((const float*)qsrc, ix->dims, nq, nq_pad, ix->dims, ix->tq_dim, ix->tq_mask, c.q_i8.p, ix->dpad8, c.q_scale.p,
                                                        c.q_norm.p, ix->cfg.vector_similarity == SSB_SIM_COSINE, ix->cfg.vector_similarity != SSB_SIM_EUCLIDEAN, st));
+        } else if (ix->affine) {
+            // affine Euclidean: the query is quantised with a COPY of the shard's (min, max) state (search.rs:1514-1530, 1562-1580)
+            SSB_TRY(c.q_scale.reserve(nq_pad, 0, st)); SSB_TRY(c.q_norm.reserve(nq_pad, 0, st)); SSB_TRY(c.q_aff.reserve((size_t)nq_pad * 2, 0, st));
+            SSB_TRY(vec::launch_quantize_rows_affine_i8((const float*)qsrc, ix->dims, nq, nq_pad, ix->dims, nullptr, nullptr, ix->aff_min, ix->aff_max, c.q_i8.p, ix->dpad8,
+                                                        c.q_scale.p, c.q_norm.p, c.q_aff.p, 1, st));
         } else if (ix->cfg.vector_similarity != SSB_SIM_COSINE) {
             // Dot / Euclidean: the query goes through the same QuantizedVector::new_scale[_norm] as the rows (search.rs:1499-1530)
             SSB_TRY(c.q_scale.reserve(nq_pad, 0, st)); SSB_TRY(c.q_norm.reserve(nq_pad, 0, st));
@@ -285,7 +293,8 @@ int32_t vec_keys(ssb_index* ix, SearchCtx& c, const void* queries, bool queries_
     if (ix->quant_i8) {
         a.rows_i8 = ix->rows_i8.p; a.queries_i8 = c.q_i8.p; a.dpad8 = ix->dpad8;
         if (ix->turbo || ix->cfg.vector_similarity != SSB_SIM_COSINE) {
-            a.i8_scaled = ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN ? 2 : 1;
+            a.i8_scaled = ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN ? (ix->affine ? 3 : 2) : 1;
+            a.row_aff = ix->row_aff.p; a.q_aff = c.q_aff.p;
             a.row_scale = ix->row_scale.p; a.row_norm = ix->row_norm.p; a.q_scale = c.q_scale.p; a.q_norm = c.q_norm.p;
         }
         SSB_TRY(vec::launch_scan_tc(a, 128, 2, st));
@@ -513,7 +522,7 @@ int32_t ssb_destroy(ssb_index* ix) {
         ix->del.release();
         ix->facets.release();
         cudaFree(ix->tq_mask); ix->tq_mask = nullptr;
-        ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->row_scale.release(); ix->row_norm.release(); ix->doc_ids.release();
+        ix->rows.release(); ix->rows_hi.release(); ix->rows_lo.release(); ix->rows_i8.release(); ix->row_scale.release(); ix->row_norm.release(); ix->row_aff.release(); ix->doc_ids.release();
         cudaStreamDestroy(ix->load_st);
     }
     delete ix;
@@ -647,13 +656,35 @@ static int32_t vector_add_level_impl(ssb_index* ix, uint32_t level_id, const flo
                 SSB_CUDA_TRY(cudaStreamSynchronize(st));
                 bool non_affine = false;
                 for (float x : first) non_affine = non_affine || x != floorf(x) || x < 0.0f || x > 255.0f;
-                if (!non_affine) { set_error("Euclidean + ScalarQuantizationI8 over integer-valued 0..255 data uses the reference's affine quantisation, which is not built"); return SSB_E_UNSUPPORTED; }
+                ix->affine = !non_affine;      // decided by the FIRST vector of the shard, for its whole life (vector.rs:657-664)
             }
+            if (ix->affine) {
+                // new_scale_norm_affine: every vector is quantised with the running (min, max) of everything indexed before it — the state is
+                // walked on the host over the level's per-row (min, max) (64K rows), the codes are written by one more kernel
+                DevTmp<float> mm, d_scale; DevTmp<int> d_zp;
+                SSB_CUDA_TRY(mm.alloc((size_t)n * 2)); SSB_CUDA_TRY(d_scale.alloc(n)); SSB_CUDA_TRY(d_zp.alloc(n));
+                SSB_TRY(vec::launch_rows_minmax(stage.p, dims, n, dims, mm.p, st));
+                std::vector<float> h_mm((size_t)n * 2), h_scale(n); std::vector<int> h_zp(n);
+                SSB_CUDA_TRY(cudaMemcpyAsync(h_mm.data(), mm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+                SSB_CUDA_TRY(cudaStreamSynchronize(st));
+                float smin = ix->aff_min, smax = ix->aff_max;
+                vec::affine_walk_rows(h_mm.data(), n, &smin, &smax, h_scale.data(), h_zp.data());
+                SSB_CUDA_TRY(cudaMemcpyAsync(d_scale.p, h_scale.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+                SSB_CUDA_TRY(cudaMemcpyAsync(d_zp.p, h_zp.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+                SSB_TRY(ix->row_scale.reserve(ix->n_rows + n, ix->n_rows, st));
+                SSB_TRY(ix->row_norm.reserve(ix->n_rows + n, ix->n_rows, st));
+                SSB_TRY(ix->row_aff.reserve((ix->n_rows + n) * 2, ix->n_rows * 2, st));
+                SSB_TRY(vec::launch_quantize_rows_affine_i8(stage.p, dims, n, n, dims, d_scale.p, d_zp.p, 0.f, 0.f, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8,
+                                                            ix->row_scale.p + ix->n_rows, ix->row_norm.p + ix->n_rows, ix->row_aff.p + ix->n_rows * 2, 0, st));
+                SSB_CUDA_TRY(cudaStreamSynchronize(st));
+                ix->aff_min = smin; ix->aff_max = smax;
+            } else {
             SSB_TRY(ix->row_scale.reserve(ix->n_rows + n, ix->n_rows, st));
             SSB_TRY(ix->row_norm.reserve(ix->n_rows + n, ix->n_rows, st));
             SSB_TRY(vec::launch_quantize_rows_scale_i8(stage.p, dims, n, n, dims, ix->rows_i8.p + ix->n_rows * ix->dpad8, ix->dpad8,
                                                        ix->row_scale.p + ix->n_rows, ix->row_norm.p + ix->n_rows,
                                                        ix->cfg.vector_similarity == SSB_SIM_EUCLIDEAN, st));
+            }
         }
     } else {
         SSB_TRY(ix->rows.reserve((ix->n_rows + n) * ix->dpad, ix->n_rows * ix->dpad, st));

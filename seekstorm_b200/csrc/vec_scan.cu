@@ -17,6 +17,7 @@
 //             keeps shared-memory wavefronts at ~55 % of the HBM-time budget), then a warp-shuffle
 //             top-k insert per finished tile.
 //   per-warp lists -> scratch; merge_lists kernel reduces them to the final per-query top-k.
+#include <limits.h>
 #include "common.cuh"
 #include "vec_scan.h"
 
@@ -338,6 +339,77 @@ __global__ void quantize_rows_scale_i8(const float* __restrict__ src, uint64_t s
     }
 }
 
+// ---- affine Euclidean SQ (QuantizedVector::new_scale_norm_affine, vector_similarity.rs:1414-1463; raster_range :1465-1472) ----
+// raster_range: a range above 1.0 is widened to 2^m - 1 ((range as i64 as u64 + 1).next_power_of_two() - 1), smaller ranges stay
+__host__ __device__ inline float ssb_raster_range(float range) {
+    if (!(range > 1.0f)) return range;
+    unsigned long long v = (unsigned long long)(long long)range + 1ull, p = 1ull;   // `as i64` truncates towards zero
+    while (p < v) p <<= 1;
+    return (float)(p - 1ull);
+}
+// one step of the reference's running state: (min_val, max_val) of the vector -> the (min, max) it is quantised with; state updated in place
+__host__ __device__ inline void ssb_affine_step(float& st_min, float& st_max, float& mn, float& mx) {
+    if (mn < st_min) st_min = mn; else mn = st_min;
+    if (mx > st_max) st_max = ssb_raster_range(mx - mn); else mx = st_max;
+}
+__global__ void rows_minmax(const float* __restrict__ src, uint64_t src_stride, uint64_t n, uint32_t dims, float2* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* r = src + row * src_stride;
+    float mn = INFINITY, mx = -INFINITY;                       // fold((INF, -INF), (min, max)): f32::min / max ignore NaN like fminf / fmaxf
+    for (uint32_t i = lane; i < dims; i += 32) { mn = fminf(mn, r[i]); mx = fmaxf(mx, r[i]); }
+    for (int m = 16; m; m >>= 1) { mn = fminf(mn, __shfl_xor_sync(FULL, mn, m)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, m)); }
+    if (lane == 0) out[row] = make_float2(mn, mx);
+}
+__global__ void quantize_rows_affine_i8(const float* __restrict__ src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims,
+                                        const float* __restrict__ scale_in, const int* __restrict__ zp_in, float st_min, float st_max,
+                                        int8_t* __restrict__ dst, uint32_t dpad8, float* __restrict__ scale_out, float* __restrict__ norm_out,
+                                        int2* __restrict__ aff_out, int is_query) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_out) return;
+    int8_t* o = dst + row * dpad8;
+    if (row >= n) {
+        for (uint32_t i = lane; i < dpad8; i += 32) o[i] = 0;
+        if (lane == 0) { scale_out[row] = 0.f; norm_out[row] = 0.f; aff_out[row] = make_int2(0, 0); }
+        return;
+    }
+    const float* r = src + row * src_stride;
+    float scale; int zp;
+    if (scale_in) { scale = __ldg(&scale_in[row]); zp = __ldg(&zp_in[row]); }
+    else {
+        float mn = INFINITY, mx = -INFINITY;
+        for (uint32_t i = lane; i < dims; i += 32) { mn = fminf(mn, r[i]); mx = fmaxf(mx, r[i]); }
+        for (int m = 16; m; m >>= 1) { mn = fminf(mn, __shfl_xor_sync(FULL, mn, m)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, m)); }
+        float a = st_min, b = st_max;
+        ssb_affine_step(a, b, mn, mx);
+        scale = __fdiv_rn(ssb_raster_range(__fsub_rn(mx, mn)), 255.0f);
+        float z = roundf(__fsub_rn(-128.0f, __fdiv_rn(mn, scale)));
+        z = fminf(fmaxf(z, -128.0f), 127.0f);
+        zp = z == z ? (int)z : 0;
+    }
+    int sq = 0, sum = 0;
+    for (uint32_t i = lane; i < dpad8; i += 32) {
+        int8_t q = 0;
+        if (i < dims) {
+            const float x = roundf(__fdiv_rn(r[i], scale));      // (x / scale).round() as i32: saturating, NaN -> 0
+            int xi = x != x ? 0 : (x >= 2147483648.0f ? INT_MAX : (x <= -2147483648.0f ? INT_MIN : (int)x));
+            long long s = (long long)xi + zp;
+            q = (int8_t)(s < -128 ? -128 : (s > 127 ? 127 : s));
+        }
+        o[i] = q;
+        sq += (int)q * (int)q; sum += (int)q;
+    }
+    for (int m = 16; m; m >>= 1) { sq += __shfl_xor_sync(FULL, sq, m); sum += __shfl_xor_sync(FULL, sum, m); }
+    if (lane == 0) {
+        const int norm_i = sq - 2 * zp * sum + (int)dims * zp * zp;
+        scale_out[row] = scale;
+        norm_out[row] = __fmul_rn(__fmul_rn((float)norm_i, scale), scale);
+        aff_out[row] = is_query ? make_int2(zp, sum) : make_int2(zp, (int)dims * zp - sum);
+    }
+}
+
 // TurboQuantI8 (TurboQuant::quantize_f32_i8, vector_similarity.rs:1929-1958): zero-pad the vector to tq_dim (a power of two), flip signs
 // by the index's seed mask, rotate with the normalised fast Walsh-Hadamard transform (fwht :1861-1880: butterflies h = 1, 2, 4, ..., then
 // every element / sqrt(n)), scale = max(sigma / 32, 1e-8) with sigma = ||x|| / sqrt(dim) (calculate_scale :2035-2039), codes =
@@ -494,6 +566,37 @@ int32_t launch_quantize_rows_scale_i8(const float* src, uint64_t src_stride, uin
     quantize_rows_scale_i8<<<(unsigned)((n_out + 7) / 8), 256, 0, st>>>(src, src_stride, n, n_out, dims, dst, dpad8, scale_out, norm_out, want_norm);
     SSB_CUDA_TRY(cudaGetLastError());
     return SSB_OK;
+}
+
+int32_t launch_rows_minmax(const float* src, uint64_t src_stride, uint64_t n, uint32_t dims, float* minmax_out, cudaStream_t st) {
+    if (n == 0) return SSB_OK;
+    rows_minmax<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(src, src_stride, n, dims, (float2*)minmax_out);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+int32_t launch_quantize_rows_affine_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, const float* scale_in, const int* zp_in,
+                                       float st_min, float st_max, int8_t* dst, uint32_t dpad8, float* scale_out, float* norm_out, int* aff_out, int is_query,
+                                       cudaStream_t st) {
+    if (n_out == 0) return SSB_OK;
+    quantize_rows_affine_i8<<<(unsigned)((n_out + 7) / 8), 256, 0, st>>>(src, src_stride, n, n_out, dims, scale_in, zp_in, st_min, st_max, dst, dpad8,
+                                                                       scale_out, norm_out, (int2*)aff_out, is_query);
+    SSB_CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+// the reference's running (min, max) state walked over the rows of one level on the host: per row the scale and zero point it is quantised
+// with (new_scale_norm_affine, vector_similarity.rs:1414-1446); st_min / st_max are updated in place
+void affine_walk_rows(const float* minmax /*[n][2]*/, uint64_t n, float* st_min, float* st_max, float* scale_out, int* zp_out) {
+    for (uint64_t r = 0; r < n; r++) {
+        float mn = minmax[2 * r], mx = minmax[2 * r + 1];
+        ssb_affine_step(*st_min, *st_max, mn, mx);
+        volatile float range = ssb_raster_range(mx - mn);
+        volatile float scale = range / 255.0f;
+        volatile float q = mn / scale;
+        volatile float zf = -128.0f - q;
+        float z = roundf(zf);
+        z = z < -128.0f ? -128.0f : (z > 127.0f ? 127.0f : z);
+        scale_out[r] = scale; zp_out[r] = z == z ? (int)z : 0;
+    }
 }
 
 int32_t launch_quantize_rows_turbo_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, uint32_t tq_dim, const float* mask,

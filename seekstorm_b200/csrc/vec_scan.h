@@ -33,9 +33,10 @@ struct ScanArgs {
     const int8_t* rows_i8 = nullptr;               // int8 path: [n_rows][dpad8] quantised corpus
     const int8_t* queries_i8 = nullptr;            //            [nq_pad][dpad8] quantised queries
     uint32_t dpad8 = 0;                            //            multiple of 128
-    int i8_scaled = 0;                             // int8 path: 0 = Cosine SQ (plain int32 dot), 1 = Dot SQ (per-vector scales), 2 = Euclidean SQ non-affine (+ norms)
+    int i8_scaled = 0;                             // int8 path: 0 = Cosine SQ (plain int32 dot), 1 = Dot SQ (per-vector scales), 2 = Euclidean SQ non-affine (+ norms), 3 = Euclidean SQ affine (+ zero points / code sums)
     const float* row_scale = nullptr; const float* row_norm = nullptr;   // [n_rows]
     const float* q_scale = nullptr; const float* q_norm = nullptr;       // [nq_pad]
+    const int* row_aff = nullptr; const int* q_aff = nullptr;            // i8_scaled 3 (affine Euclidean SQ): int2 per row (zp, dims*zp - sum_q) / per query (zp, sum_q)
     const uint32_t* del_slot = nullptr; const uint64_t* del_words = nullptr;   // delete set (null = none): deleted docs never enter a list
     bool sample_groupmax = false;                  // internal (int8): threshold-seeding pass, writes thr_buf instead of lists
     // IVF probe (vec_ivf.cu): selection mask [nq_pad][ivf_words] (bit per (query, cluster)) and each row's cluster id; null = AnnMode::All.
@@ -116,6 +117,15 @@ int32_t launch_quantize_rows_i8(const float* src, uint64_t src_stride, uint64_t 
 // norm = sum(code^2) as f32 * scale * scale (want_norm).  Every step is order-independent (max, exact integer sum): bit-identical to the CPU.
 int32_t launch_quantize_rows_scale_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, int8_t* dst,
                                       uint32_t dpad8, float* scale_out, float* norm_out, int want_norm, cudaStream_t st);
+// QuantizedVector::new_scale_norm_affine (vector_similarity.rs:1414-1463), integer-valued 0..255 data: codes = round(x / scale) + zero_point.
+// rows: scale_in / zp_in hold each row's scale and zero point (the host walked the reference's running min / max state over the rows);
+// queries (scale_in == null): every query derives them itself from the index's state (st_min, st_max), as search.rs:1514-1530 does with a copy.
+// aff_out: int2 per row — rows (zero_point, dims * zero_point - sum_q), queries (zero_point, sum_q).  minmax_out (pass 1 for rows): float2 per row.
+int32_t launch_rows_minmax(const float* src, uint64_t src_stride, uint64_t n, uint32_t dims, float* minmax_out, cudaStream_t st);
+int32_t launch_quantize_rows_affine_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, const float* scale_in, const int* zp_in,
+                                       float st_min, float st_max, int8_t* dst, uint32_t dpad8, float* scale_out, float* norm_out, int* aff_out, int is_query,
+                                       cudaStream_t st);
+void affine_walk_rows(const float* minmax, uint64_t n, float* st_min, float* st_max, float* scale_out, int* zp_out);
 // TurboQuantI8 (vector_similarity.rs:1929-1958): pad to tq_dim, sign mask, FWHT, scale = max(sigma / 32, 1e-8); rows >= n are zero rows
 int32_t launch_quantize_rows_turbo_i8(const float* src, uint64_t src_stride, uint64_t n, uint64_t n_out, uint32_t dims, uint32_t tq_dim, const float* mask,
                                       int8_t* dst, uint32_t dpad8, float* scale_out, float* norm_out, int normalize, int negate, cudaStream_t st);

@@ -131,7 +131,9 @@ __device__ __forceinline__ int ord_to_int(uint32_t o) {
 
 // SCALED (int8 only): 0 = Cosine + ScalarQuantizationI8 (score = the int32 dot product); 1 = Dot + ScalarQuantizationI8 (per-vector
 // scale, score = dot_i32 as f32 * query_scale * row_scale, dot_i8_quantized vector_similarity.rs:1754-1758); 2 = Euclidean +
-// ScalarQuantizationI8, non-affine (score = -max(0, query_norm + row_norm - 2*dot), euclidean_i8_quantized :1721-1734)
+// ScalarQuantizationI8, non-affine (score = -max(0, query_norm + row_norm - 2*dot), euclidean_i8_quantized :1721-1734); 3 = the AFFINE
+// variant (integer-valued 0..255 data, euclidean_i8_quantized_affine :1770-1795): the int32 dot product is first corrected for the two zero
+// points, dot - zp_row*sum_q(query) - zp_query*sum_q(row) + n*zp_query*zp_row, regrouped as dot - zp_row*sum_q(query) + zp_query*(n*zp_row - sum_q(row))
 template <int NQ, int PREC, bool BRES, int SCALED>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2 /*bf16: lo plane*/,
@@ -142,6 +144,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         const uint32_t* __restrict__ del_slot, const uint64_t* __restrict__ del_words /*delete set or null*/,
         const float* __restrict__ row_scale, const float* __restrict__ row_norm /*SCALED: [n_rows]*/,
         const float* __restrict__ q_scale, const float* __restrict__ q_norm /*SCALED: [gridDim.y*NQ]*/,
+        const int2* __restrict__ row_aff /*SCALED 3: [n_rows] (zero_point, dims*zero_point - sum_q)*/, const int2* __restrict__ q_aff /*SCALED 3: [gridDim.y*NQ] (zero_point, sum_q)*/,
         const uint32_t* __restrict__ ivf_sel, uint32_t ivf_words, const uint32_t* __restrict__ row_cluster /*IVF selection mask (f32 epilogue) or null*/,
         uint32_t sample_mode /*int8 only: write per-(32-row group, query) score maxima instead of lists*/) {
     using C = Cfg<NQ, PREC, BRES>;
@@ -182,7 +185,7 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         if (PREC == PREC_I8 && !SCALED) t = (uint32_t)ord_to_int(t);   // unscaled int8 path compares the raw int32 dot products
         thr_u[i] = t;
         if (PREC == PREC_F16F) qs_sm[i] = __ldg(&q_scale[blockIdx.y * NQ + i]);   // filter scan: per-query margin 2 eps_q
-        if (SCALED) { qs_sm[i] = __ldg(&q_scale[blockIdx.y * NQ + i]); qn_sm[i] = SCALED == 2 ? __ldg(&q_norm[blockIdx.y * NQ + i]) : 0.f; }
+        if (SCALED) { qs_sm[i] = __ldg(&q_scale[blockIdx.y * NQ + i]); qn_sm[i] = SCALED >= 2 ? __ldg(&q_norm[blockIdx.y * NQ + i]) : 0.f; }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
@@ -447,11 +450,14 @@ scan_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     // scaled int8: the accumulators are exact int32 dot products; the score is rebuilt with the reference's
                     // operation order so that it is bit-identical to the CPU path, then treated like an f32 score below
                     const float rs = valid ? __ldg(&row_scale[row]) : 0.f;
-                    const float rn = (SCALED == 2 && valid) ? __ldg(&row_norm[row]) : 0.f;
+                    const float rn = (SCALED >= 2 && valid) ? __ldg(&row_norm[row]) : 0.f;
+                    const int2 ra = (SCALED == 3 && valid) ? __ldg(&row_aff[row]) : make_int2(0, 0);
 #pragma unroll
                     for (int j = 0; j < CHUNK; j++) {
-                        const float dotf = __fmul_rn(__fmul_rn((float)(int)v[j], qs_sm[c * CHUNK + j]), rs);
-                        const float sc = SCALED == 2 ? -fmaxf(__fsub_rn(__fadd_rn(qn_sm[c * CHUNK + j], rn), __fmul_rn(2.0f, dotf)), 0.0f) : dotf;
+                        int di = (int)v[j];
+                        if (SCALED == 3) { const int2 qa = __ldg(&q_aff[blockIdx.y * NQ + c * CHUNK + j]); di = di - ra.x * qa.y + qa.x * ra.y; }
+                        const float dotf = __fmul_rn(__fmul_rn((float)di, qs_sm[c * CHUNK + j]), rs);
+                        const float sc = SCALED >= 2 ? -fmaxf(__fsub_rn(__fadd_rn(qn_sm[c * CHUNK + j], rn), __fmul_rn(2.0f, dotf)), 0.0f) : dotf;
                         v[j] = __float_as_uint(sc);
                     }
                 }
@@ -924,6 +930,7 @@ static int32_t launch_tc_n(const ScanArgs& a, cudaStream_t st) {
     tc::scan_tc<NQ, PREC, BRES, SCALED><<<dim3(gx, n_groups), tc::THREADS, smem, st>>>(tmA, tmA2, tmBh, tmBl, (uint32_t)a.n_rows, n_kchunks, n_tiles,
                                                                              a.k, a.doc_ids, a.scratch, a.thr_init, a.nq_valid ? a.nq_valid : a.nq_pad, a.ceil_keys, nst,
                                                                              a.del_slot, a.del_words, a.row_scale, a.row_norm, a.q_scale, a.q_norm,
+                                                                             (const int2*)a.row_aff, (const int2*)a.q_aff,
                                                                              PREC == tc::PREC_I8 ? nullptr : a.ivf_sel, a.ivf_words, a.row_cluster,
                                                                              a.sample_groupmax ? 1u : 0u);
     if (a.ev1) cudaEventRecord(a.ev1, st);
@@ -979,7 +986,8 @@ static int32_t launch_scan_tc_impl(const ScanArgs& a, uint32_t nq_tile, int prec
         if (nq_tile != 128 || a.nq_pad % 128 != 0 || !a.rows_i8 || !a.queries_i8 || a.dpad8 % 128) { set_error("int8 scan: bad arguments"); return SSB_E_INVALID; }
         // query block resident in smem when it leaves room for >= 3 corpus stages (dims <= 1024), else streamed per stage
         if (a.i8_scaled) {
-            if (!a.row_scale || !a.q_scale || (a.i8_scaled == 2 && (!a.row_norm || !a.q_norm))) { set_error("scaled int8 scan: missing scale / norm arrays"); return SSB_E_INVALID; }
+            if (!a.row_scale || !a.q_scale || (a.i8_scaled >= 2 && (!a.row_norm || !a.q_norm)) || (a.i8_scaled == 3 && (!a.row_aff || !a.q_aff))) { set_error("scaled int8 scan: missing scale / norm arrays"); return SSB_E_INVALID; }
+            if (a.i8_scaled == 3) return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true, 3>(a, st) : launch_tc_n<128, tc::PREC_I8, false, 3>(a, st);
             if (a.i8_scaled == 1) return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true, 1>(a, st) : launch_tc_n<128, tc::PREC_I8, false, 1>(a, st);
             return a.dpad8 <= 1024 ? launch_tc_n<128, tc::PREC_I8, true, 2>(a, st) : launch_tc_n<128, tc::PREC_I8, false, 2>(a, st);
         }

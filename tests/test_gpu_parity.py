@@ -425,3 +425,31 @@ def test_vector_turboquant_parity(n, dims, sim):
     if sim == "euc":                                   # Euclidean keeps its meaning: the planted neighbour is the best hit
         assert ix.search_vector_batch(qs[3:4], 1)[0][0][0] == n // 2
     ix.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dims", [(300, 100), (70000, 128), (3000, 1100)])
+def test_vector_int8_affine_parity(n, dims):
+    """Euclidean + ScalarQuantizationI8 over integer-valued 0..255 data (SIFT-like): the reference's AFFINE quantiser
+    (new_scale_norm_affine with its running min / max state, vector_similarity.rs:1414-1463) and euclidean_i8_quantized_affine (:1770-1795):
+    BIT-EXACT ids and scores vs the oracle, incl. the rows quantised while the state was still growing and several levels."""
+    from seekstorm_b200 import Index, VectorSimilarity
+    rng = np.random.default_rng(1000 + n)
+    rows = np.clip(np.abs(rng.normal(0, 45, (n, dims))).round(), 0, 255).astype(np.float32)
+    rows[0] = np.clip(rows[0], 3, 90)                     # the state starts narrow: (3, raster(87) = 127) ...
+    rows[1] = np.clip(rows[1], 1, 120)
+    rows[5, 0] = 0; rows[7, 1] = 255                      # ... and reaches (0, 255) a few rows later
+    qs = np.clip(np.abs(rng.normal(0, 45, (24, dims))).round(), 0, 255).astype(np.float32)
+    qs[3] = np.clip(rows[n // 2] + rng.integers(-2, 3, dims), 0, 255)
+    ix = Index(0, vector_dims=dims, vector_similarity=VectorSimilarity.Euclidean, vector_quantization=1)
+    ix.add_vectors(rows)
+    rc, rs, rn, rz, rsum, st = O.quantize_affine_rows_i8(rows)
+    qc, qsc, qn, qz, qsum, _ = O.quantize_affine_rows_i8(qs, st, False)
+    for k in (1, 10, 40):
+        got = ix.search_vector_batch(qs, k)
+        for i in range(0, len(qs), 3):
+            want = O.search_vector_i8_affine(rc, rs, rn, rz, rsum, qc[i], float(qsc[i]), float(qn[i]), int(qz[i]), int(qsum[i]), k)
+            assert [d for d, _ in got[i]] == [d for d, _ in want], (i, k, got[i][:3], want[:3])
+            assert [np.float32(s) for _, s in got[i]] == [np.float32(s) for _, s in want]
+    assert ix.search_vector_batch(qs[3:4], 1)[0][0][0] == n // 2
+    ix.close()

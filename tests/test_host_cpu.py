@@ -190,3 +190,27 @@ def test_turboquant_oracle_against_a_hadamard_matrix():
     c1, s1, _ = O.turboquant_rows_i8(rows[:2], mask, True)
     c2, s2, _ = O.turboquant_rows_i8(np.stack([O.normalize(rows[0]), O.normalize(rows[1])]), mask, False)
     assert (c1 == c2).all() and (s1 == s2).all()
+
+
+def test_affine_sq_oracle_is_lossless_on_sift_like_data():
+    """new_scale_norm_affine (vector_similarity.rs:1414-1463) on integer 0..255 data: once the running range has reached 255 the scale is 1 and
+    the zero point -128, codes are x - 128 and -euclidean_i8_quantized_affine equals the exact negated squared distance; before that the state
+    follows the reference's update rule (the stored maximum is the RASTERED range)."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(8)
+    rows = np.clip(np.abs(rng.normal(0, 45, (200, 128))).round(), 0, 255).astype(np.float32)
+    rows[0] = np.clip(rows[0], 3, 90)                    # first vector: min 3, max 90 -> range raster(87) = 127, scale 127/255
+    rows[1, 0] = 0; rows[1, 1] = 255
+    c, s, nrm, zp, sq, st = O.quantize_affine_rows_i8(rows)
+    assert s[0] == np.float32(127.0) / np.float32(255.0) and zp[0] == -128          # -128 - 3/scale = -134 -> clamped
+    assert st == (0.0, 255.0) and (s[1:] == 1.0).all() and (zp[1:] == -128).all()
+    assert (c[1:].astype(np.int32) == rows[1:].astype(np.int32) - 128).all()
+    q = np.clip(rows[50] + rng.integers(-3, 4, 128), 0, 255).astype(np.float32)
+    qc, qs, qn, qz, qsum, _ = O.quantize_affine_rows_i8(q[None], st, False)
+    hits = O.search_vector_i8_affine(c[1:], s[1:], nrm[1:], zp[1:], sq[1:], qc[0], qs[0], qn[0], qz[0], qsum[0], 5)
+    exact = sorted(((-float(((rows[1 + i] - q) ** 2).sum()), i) for i in range(199)), key=lambda t: (-t[0], t[1]))[:5]
+    assert [(d, s_) for d, s_ in hits] == [(i, sc) for sc, i in exact]
+    # raster_range: ranges above 1 widen to 2^m - 1
+    r2 = np.array([[0, 1, 2, 40]], dtype=np.float32)
+    _, s2, _, z2, _, st2 = O.quantize_affine_rows_i8(np.pad(r2, ((0, 0), (0, 4))))
+    assert s2[0] == np.float32(63.0) / np.float32(255.0) and st2 == (0.0, 63.0)
