@@ -447,6 +447,60 @@ def bench_vector_int8(a, rank, world):
     }
 
 
+def bench_vector_int8_variants(a, rank, world):
+    """SURVEY 8(f) row 2, the other int8 quantisers on the int8 tcgen05 scan: TurboQuantI8 (1M x 768 cosine: rows are next_power_of_two(768) =
+    1024 code bytes) and the affine Euclidean SQ of integer-valued data (SIFT-like 1M x 128).  Device-resident QPS + the scan's roofline."""
+    from seekstorm_b200 import Index, VectorSimilarity, synth
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = {}
+    peak, peak_kind = peaks()
+    nb = a.int8_batch
+    for name in ("turboquant_i8", "affine_sq_i8"):
+        dims = a.dims if name == "turboquant_i8" else 128
+        if name == "turboquant_i8":
+            ix = Index(dev.index, vector_dims=dims, vector_similarity=VectorSimilarity.Cosine, max_batch=max(nb, 16), vector_quantization=2)
+            dim2 = 1
+            while dim2 < dims:
+                dim2 *= 2
+            ix.set_turboquant_mask(np.where(np.random.default_rng(1234).random(dim2) < 0.5, 1.0, -1.0).astype(np.float32))
+            row_bytes = dim2
+        else:
+            ix = Index(dev.index, vector_dims=dims, vector_similarity=VectorSimilarity.Euclidean, max_batch=max(nb, 16), vector_quantization=1)
+            row_bytes = dims
+        ix.set_stream(torch.cuda.current_stream().cuda_stream)
+        ix.reserve_vectors(a.rows)
+        for lv in range((a.rows + 65535) // 65536):
+            r = gen_vector_level(lv, a.rows, dims, dev)
+            if name == "affine_sq_i8":
+                r = (r.abs() * (45.0 * dims ** 0.5)).round().clamp_(0, 255)       # integer-valued 0..255 rows (SIFT-like)
+            ix.add_vector_level(lv, r)
+            del r
+        q = synth.gen_vectors(nb, dims, 2002, "cpu")
+        if name == "affine_sq_i8":
+            q = (q.abs() * (45.0 * dims ** 0.5)).round().clamp_(0, 255)
+        q_dev = q.to(dev)
+        keys = torch.zeros((nb, 32), dtype=torch.int64, device=dev)
+
+        def step_dev():
+            ix.search_vector_keys(q_dev, TOPK, keys)
+        step_dev(); torch.cuda.synchronize()
+        ms = timed_steps(step_dev, a.steps, a.warmup, world)
+        kern_ns = []
+        for _ in range(3):
+            step_dev(); torch.cuda.synchronize()
+            kern_ns.append(ix.last_stats()["dominant_kernel_ns"])
+        passes = (nb + 127) // 128
+        kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
+        alg = float(a.rows) * row_bytes * passes
+        out[name] = {"value": nb * a.steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / a.steps,
+                     "config": {"workload": f"{a.rows} x {dims}, top-{TOPK}, batch {nb} queries/step ({passes} passes of 128), {row_bytes} code bytes per row"},
+                     "roofline": {"bound": "hbm", "achieved": alg / (kern_ms / 1e3) / 1e9 if kern_ms else None, "peak": peak, "unit": "GB/s",
+                                  "frac": alg / (kern_ms / 1e3) / 1e9 / peak if kern_ms else None, "peak_kind": f"of {peak_kind}", "kernel": "scan_tc_i8 (scaled epilogue)",
+                                  "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg, "traffic": None}}
+        ix.close()
+    return out
+
+
 def cpu_vector_int8_baseline(a, seconds):
     """Restated reference CPU path for Cosine + SQ-I8 (dot_i8 over the int8 corpus, linear top-k), one query per thread."""
     from oracle import oracle as O
@@ -568,6 +622,29 @@ def bm25_queries(n, seed=2003):
     return [[int(k) for k in synth.term_keys_np(np.array(q, dtype=np.int64))] for q in qs]
 
 
+def _bm25_filter_variants(a, ix, qk, out_keys, steps, world, dev):
+    """the C3 OR queries behind a facet range filter that half of the docs pass (is_facet_filter on every candidate; filtered
+    queries are scored and counted doc by doc in lex_generic) — 1024 queries per step, Topk and TopkCount."""
+    from seekstorm_b200 import FacetFilter, QueryType, ResultType
+    price = torch.randint(0, 1000, (a.bm25_docs,), dtype=torch.int32).numpy().astype(np.uint32)
+    ix.set_facets({"price": price})
+    nf = min(1024, len(qk))
+    bf, keep_f = ix._lex_batch(qk[:nf], QueryType.Union, None, [[FacetFilter("price", 0, 500)]] * nf)
+    cnt_dev = torch.zeros(nf, dtype=torch.int64, device=dev)
+    res = {}
+    for name, rt_ in (("or_topk_facet_filter", ResultType.Topk), ("or_topkcount_facet_filter", ResultType.TopkCount)):
+        def step_f():
+            ix.search_lexical_keys(bf, TOPK, rt_, out_keys, cnt_dev)
+        nv = max(2, steps // 2)
+        msv = timed_steps(step_f, nv, 2, world)
+        step_f(); torch.cuda.synchronize()
+        sv = ix.last_stats()
+        res[name] = {"value": nf * nv / (msv / 1e3), "unit": "queries/s", "kernel_ms": sv["dominant_kernel_ns"] / 1e6, "queries_per_step": nf,
+                     "selectivity": 0.5, "kernel": "lex_generic (per-candidate predicate path)"}
+    ix.set_facets({})
+    return res
+
+
 def bench_bm25(a, rank, world, keep_index=False, vector_dims=0):
     from seekstorm_b200 import QueryType, ResultType
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -613,6 +690,11 @@ def bench_bm25(a, rank, world, keep_index=False, vector_dims=0):
         sv = ix.last_stats()
         variants[name] = {"value": len(qk) * nv / (msv / 1e3), "unit": "queries/s", "kernel_ms": sv["dominant_kernel_ns"] / 1e6,
                           "algorithmic_bytes_per_launch": sv["algorithmic_bytes"]}
+    if world == 1:
+        try:
+            variants.update(_bm25_filter_variants(a, ix, qk, out_keys, steps, world, dev))
+        except Exception as e:  # pragma: no cover
+            variants["or_topk_facet_filter"] = {"error": repr(e)}
     peak, peak_kind = peaks()
     kern_ms = float(np.median(kern_ns)) / 1e6 if kern_ns and min(kern_ns) > 0 else None
     alg = st.get("algorithmic_bytes")
@@ -920,6 +1002,12 @@ def main():
         except Exception as e:  # pragma: no cover
             out["int8"] = {"error": repr(e)}
         torch.cuda.empty_cache()
+        if world == 1 and isinstance(out.get("int8"), dict):
+            try:
+                out["int8"]["variants"] = bench_vector_int8_variants(a, rank, world)
+            except Exception as e:  # pragma: no cover
+                out["int8"]["variants"] = {"error": repr(e)}
+            torch.cuda.empty_cache()
     if "hybrid" in sections:
         try:
             out["hybrid"] = bench_hybrid(a, rank, world)

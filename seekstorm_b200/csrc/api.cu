@@ -852,7 +852,7 @@ int32_t ssb_set_facets(ssb_index* ix, const void* rows, uint64_t first_doc_id, u
     if (!ix) { set_error("ssb_set_facets: null index"); return SSB_E_INVALID; }
     std::unique_lock<std::shared_mutex> g(ix->rw);
     SSB_CUDA_TRY(cudaSetDevice(ix->cfg.device));
-    for (auto& c : ix->pool) cudaStreamSynchronize(c->own_st);
+    SSB_CUDA_TRY(cudaDeviceSynchronize());        // searches may run on a caller-owned stream (ssb_set_stream): nothing may still read the old columns
     ix->facets.release();
     if (n_docs == 0 || n_fields == 0) return SSB_OK;
     if (!rows || !fields) { set_error("ssb_set_facets: null argument"); return SSB_E_INVALID; }

@@ -296,11 +296,20 @@ def test_vector_int8_config_errors():
     from seekstorm_b200._lib import SsbError
     with pytest.raises(SsbError):
         Index(0, vector_dims=64, vector_quantization=7)
-    # Euclidean + SQ over integer-valued 0..255 data would take the reference's affine quantisation: not built, fails loudly
+    # Euclidean + SQ: the FIRST vector decides the quantiser for the life of the index (vector.rs:657-664) — integer-valued 0..255 data takes the
+    # affine one (scores = exact negated squared distances here), anything else the non-affine one
     ix = Index(0, vector_dims=8, vector_similarity=VectorSimilarity.Euclidean, vector_quantization=1)
-    with pytest.raises(SsbError, match="affine"):
-        ix.add_vectors(np.arange(16, dtype=np.float32).reshape(2, 8))
+    rows = np.arange(24, dtype=np.float32).reshape(3, 8)
+    ix.add_vectors(rows)
+    got = ix.search_vector_batch(rows[1:2] + 1, 3)[0]
+    c, s, nrm, zp, sq, st = O.quantize_affine_rows_i8(rows)
+    qc, qsc, qn, qz, qsum, _ = O.quantize_affine_rows_i8(rows[1:2] + 1, st, False)
+    assert st == (0.0, 31.0) and got == O.search_vector_i8_affine(c, s, nrm, zp, sq, qc[0], qsc[0], qn[0], qz[0], qsum[0], 3)
+    assert [d for d, _ in got] == [1, 2, 0]
     ix.close()
+    with pytest.raises(SsbError):                       # TurboQuantI8 needs its sign mask before the first vector
+        ix = Index(0, vector_dims=8, vector_similarity=VectorSimilarity.Dot, vector_quantization=2)
+        ix.add_vectors(rows)
 
 
 @pytest.mark.gpu
