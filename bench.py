@@ -49,11 +49,12 @@ def parse():
     p.add_argument("--batch", type=int, default=256, help="vector queries per step")
     p.add_argument("--rows", type=int, default=C2_ROWS)
     p.add_argument("--dims", type=int, default=C2_DIMS)
-    p.add_argument("--sections", default="vector,int8,bm25,hybrid,c5,parity")
+    p.add_argument("--sections", default="vector,int8,bm25,hybrid,c5,phrase,parity")
     p.add_argument("--int8-batch", type=int, default=1024, help="queries per step of the int8 (ScalarQuantizationI8) section")
     p.add_argument("--bm25-docs", type=int, default=C3_DOCS)
     p.add_argument("--bm25-batch", type=int, default=4096, help="lexical queries per step")
     p.add_argument("--hybrid-docs", type=int, default=5_000_000)
+    p.add_argument("--phrase-docs", type=int, default=2_000_000, help="docs of the phrase-query section's corpus (with token positions)")
     p.add_argument("--c5-docs", type=int, default=10_000_000, help="C5: docs AND vectors of the sharded hybrid index")
     p.add_argument("--parity-queries", type=int, default=64, help="queries per path of the post-run oracle check")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of each cpu_baseline sample")
@@ -645,6 +646,44 @@ def _bm25_filter_variants(a, ix, qk, out_keys, steps, world, dev):
     return res
 
 
+def bench_phrase(a, rank, world):
+    """SURVEY 8(f) row 4, QueryType::Phrase: a Zipf corpus of the C3 law with token positions (2 M docs by default), 1024 phrases of 2-3 frequent
+    terms per step; intersection of the phrase's terms + the position check per candidate (lex_generic).  Device-resident QPS."""
+    from seekstorm_b200 import Index, QueryType, ResultType, synth
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = a.phrase_docs
+    ix = Index(dev.index, max_batch=1024)
+    ix.set_stream(torch.cuda.current_stream().cuda_stream)
+    ls, n_pos = 0, 0
+    t0 = time.perf_counter()
+    for lv in synth.gen_lexical_corpus(n, C3_VOCAB, 1006, dev, with_positions=True):
+        ix.add_synth_level(lv)
+        ls += lv.len_sum_normalized
+        n_pos += int(lv.positions.numel())
+    ix.commit(n, ls)
+    build_s = time.perf_counter() - t0
+    rng = np.random.default_rng(2006)
+    phrases = [[int(x) for x in np.floor(np.exp(rng.uniform(0, np.log(300), int(rng.integers(2, 4)))))] for _ in range(1024)]
+    qk = [[int(k) for k in synth.term_keys_np(np.array(p, dtype=np.int64))] for p in phrases]
+    b, keep = ix._lex_batch(qk, QueryType.Phrase)
+    out_keys = torch.zeros((len(qk), 32), dtype=torch.int64, device=dev)
+    cnt_dev = torch.zeros(len(qk), dtype=torch.int64, device=dev)
+    res = {"config": {"workload": f"{n} docs Zipf(1) V={C3_VOCAB} with positions ({n_pos} tokens), {len(qk)} phrases/step of 2-3 terms, ranks log-uniform [1,300]",
+                      "index_build_s": build_s}}
+    steps = max(3, a.steps // 2)
+    for name, rt_ in (("topk", ResultType.Topk), ("topkcount", ResultType.TopkCount)):
+        def step():
+            ix.search_lexical_keys(b, TOPK, rt_, out_keys, cnt_dev)
+        ms = timed_steps(step, steps, 2, world)
+        step(); torch.cuda.synchronize()
+        sv = ix.last_stats()
+        res[name] = {"value": len(qk) * steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / steps, "kernel_ms": sv["dominant_kernel_ns"] / 1e6,
+                     "postings_visited": sv.get("postings_visited"), "kernel": "lex_generic (intersection + phrase predicate)"}
+    res["matching_phrases"] = int((cnt_dev > 0).sum().item())
+    ix.close()
+    return res
+
+
 def bench_bm25(a, rank, world, keep_index=False, vector_dims=0):
     from seekstorm_b200 import QueryType, ResultType
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -1013,6 +1052,12 @@ def main():
             out["hybrid"] = bench_hybrid(a, rank, world)
         except Exception as e:  # pragma: no cover
             out["hybrid"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+    if "phrase" in sections and world == 1:
+        try:
+            out["phrase"] = bench_phrase(a, rank, world)
+        except Exception as e:  # pragma: no cover
+            out["phrase"] = {"error": repr(e)}
         torch.cuda.empty_cache()
     if "bm25" in sections:
         lex_ix = None

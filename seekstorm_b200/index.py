@@ -203,11 +203,11 @@ class Index:
         """Convenience: a seekstorm_b200.synth.Level (tensors on CPU or on this index's device)."""
         if lv.term_keys.is_cuda:
             self.add_lexical_level(lv.level_id, lv.n_docs, lv.term_keys, lv.posting_offsets, lv.doc_ids, lv.tfs,
-                                   lv.doc_len_bytes)
+                                   lv.doc_len_bytes, getattr(lv, "positions", None))
         else:
             n = lv.to_numpy()
             self.add_lexical_level(n["level_id"], n["n_docs"], n["term_keys"], n["posting_offsets"], n["doc_ids"],
-                                   n["tfs"], n["doc_len_bytes"])
+                                   n["tfs"], n["doc_len_bytes"], n.get("positions"))
 
     def load_index_bin(self, data, indexed_field_count: int = 1, key_head_size: int = 20, segment_number_bits: int = 11) -> int:
         """Load one shard's index.bin (bytes / mmap / numpy uint8 array, the reference's own format, index.rs:3253-3516) and commit.

@@ -93,9 +93,12 @@ class Level:
     tfs: torch.Tensor              # int16 (u16 bit pattern) [n_postings]
     doc_len_bytes: torch.Tensor    # uint8 [n_docs]
     len_sum_normalized: int        # Σ byte4_to_int(doc_len_byte)
+    positions: torch.Tensor | None = None   # int16 (u16 bit pattern) [sum of tfs]: token positions of every posting, posting order (phrase queries)
 
     def to_numpy(self) -> dict:
+        extra = {} if self.positions is None else dict(positions=self.positions.cpu().numpy().view(np.uint16).copy())
         return dict(
+            **extra,
             level_id=self.level_id, n_docs=self.n_docs,
             term_keys=self.term_keys.cpu().numpy().view(np.uint64).copy(),
             posting_offsets=self.posting_offsets.cpu().numpy().view(np.uint32).copy(),
@@ -125,8 +128,9 @@ def zipf_cdf(vocab: int, device, s: float = 1.0) -> torch.Tensor:
 
 def gen_level(level_id: int, n_docs: int, vocab: int, seed: int, device="cpu",
               cdf: torch.Tensor | None = None, mean_len: float = 80.0, sigma: float = 0.6,
-              min_len: int = 8, max_len: int = 2000) -> Level:
-    """Generate one level; deterministic in (seed, level_id) for a given device type."""
+              min_len: int = 8, max_len: int = 2000, with_positions: bool = False) -> Level:
+    """Generate one level; deterministic in (seed, level_id) for a given device type.  with_positions: also return every posting's token
+    positions (the documents ARE token sequences: position = index of the token inside its document); the postings are the same either way."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed * 1000003 + level_id)
@@ -143,8 +147,16 @@ def gen_level(level_id: int, n_docs: int, vocab: int, seed: int, device="cpu",
     del u
     docs = torch.repeat_interleave(torch.arange(n_docs, device=dev, dtype=torch.int64), lens)
     key = terms * LEVEL_DOCS + docs
+    positions = None
+    if with_positions:
+        starts = torch.cumsum(lens, 0) - lens
+        pos = torch.arange(n_tok, device=dev, dtype=torch.int64) - starts[docs]
+        key, order = torch.sort(key, stable=True)       # tokens are in (doc, position) order: a stable sort keeps positions ascending per posting
+        positions = pos[order].to(torch.int16)
+        del pos, order, starts
+    else:
+        key, _ = torch.sort(key)
     del terms, docs
-    key, _ = torch.sort(key)
     pk, tf = torch.unique_consecutive(key, return_counts=True)
     del key
     p_term = pk // LEVEL_DOCS
@@ -155,10 +167,10 @@ def gen_level(level_id: int, n_docs: int, vocab: int, seed: int, device="cpu",
     return Level(
         level_id=level_id, n_docs=n_docs, term_ids=term_ids, term_keys=term_keys_torch(term_ids),
         posting_offsets=offs.to(torch.int32), doc_ids=p_doc.to(torch.int16),
-        tfs=tf.clamp(max=65535).to(torch.int16), doc_len_bytes=doc_len_bytes, len_sum_normalized=len_sum)
+        tfs=tf.clamp(max=65535).to(torch.int16), doc_len_bytes=doc_len_bytes, len_sum_normalized=len_sum, positions=positions)
 
 
-def gen_lexical_corpus(n_docs: int, vocab: int, seed: int, device="cpu", level_ids=None):
+def gen_lexical_corpus(n_docs: int, vocab: int, seed: int, device="cpu", level_ids=None, with_positions: bool = False):
     """Yield Level objects for the corpus; `level_ids` restricts to a subset (multi-GPU block ranges).
     Returns an iterator; global stats come from `corpus_stats`."""
     dev = torch.device(device)
@@ -166,7 +178,7 @@ def gen_lexical_corpus(n_docs: int, vocab: int, seed: int, device="cpu", level_i
     n_levels = (n_docs + LEVEL_DOCS - 1) // LEVEL_DOCS
     for lv in (range(n_levels) if level_ids is None else level_ids):
         nd = min(LEVEL_DOCS, n_docs - lv * LEVEL_DOCS)
-        yield gen_level(lv, nd, vocab, seed, dev, cdf)
+        yield gen_level(lv, nd, vocab, seed, dev, cdf, with_positions=with_positions)
 
 
 def gen_queries(n_queries: int, seed: int, rank_lo: int, rank_hi: int, n_terms_choices=(2,),

@@ -173,6 +173,33 @@ def test_c3_full_size_batch_invariance_and_paging(c3_index):
         assert deep[i] == want
 
 
+def test_c3_full_size_facet_filter_identity(c3_index):
+    """C3 corpus (10 M docs) behind facet filters (a u32 range half of the docs pass + a String16 value set): 32 OR + 32 AND queries, ids / ranks /
+    scores / counts == the exhaustive oracle with the same filters (the per-candidate predicate path at BASELINE.json's size)."""
+    from seekstorm_b200 import FacetFilter, QueryType, ResultType
+    ix, orc = c3_index
+    n = 10_000_000
+    rng = np.random.default_rng(77)
+    cols = {"price": rng.integers(0, 1000, n, dtype=np.uint32), "cat": rng.integers(0, 16, n, dtype=np.uint16)}
+    ix.set_facets(cols, string_facets=("cat",))
+    rows, fields, first, nd, rb = ix._facet_rows
+    orc.set_facets(rows, [(fields[i].type, fields[i].offset) for i in range(2)], first, nd, rb)
+    fl = [FacetFilter("price", 250, 750), FacetFilter("cat", values=[1, 3, 5, 7, 9, 11])]
+    offs, arr, sv = ix._encode_filters([fl])
+    tup = [(arr[i].facet, arr[i].kind, arr[i].start, arr[i].end, arr[i].set_first, arr[i].set_count) for i in range(2)]
+    qk = _c3_queries(32, 2033)
+    try:
+        for qt, oqt in ((QueryType.Union, O.QUERY_UNION), (QueryType.Intersection, O.QUERY_INTERSECTION)):
+            got, counts = ix.search_lexical_batch(qk, qt, 10, ResultType.TopkCount, filters=[fl] * len(qk))
+            for i, kq in enumerate(qk):
+                want, tot = orc.search(kq, oqt, 10, O.RESULT_TOPKCOUNT, filters=tup, set_values=[int(x) for x in sv])
+                assert got[i] == want, (qt, i, kq, got[i][:3], want[:3])
+                assert int(counts[i]) == tot, (qt, i, counts[i], tot)
+                assert all(250 <= cols["price"][(d >> 16) * 65536 + (d & 0xFFFF)] < 750 for d, _ in got[i])
+    finally:
+        ix.set_facets({})
+
+
 def test_c4_full_size_hybrid_identity():
     """C4: 5 M docs + 5 M x 768 f32 vectors, 16 hybrid queries: fused ids / RRF scores == O.rrf of the two oracle lists
     (lexical list bit-exact; the vector list is checked to 1e-4 and must agree on ids for the RRF ranks to agree)."""

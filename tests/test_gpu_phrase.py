@@ -92,3 +92,31 @@ def test_phrase_needs_positions_and_rejects_mixed_levels():
         with pytest.raises(SsbError):                                  # positions of a posting must ascend
             ix2.add_lexical_level(lv["level_id"], lv["n_docs"], lv["term_keys"], lv["posting_offsets"], lv["doc_ids"], lv["tfs"], lv["doc_len_bytes"], bad)
     ix.close(); ix2.close()
+
+
+def test_phrase_on_the_synthetic_zipf_corpus():
+    """the bench's own corpus law (Zipf tokens, 64K-doc levels generated on the GPU) with positions: 2- and 3-token phrases of frequent terms,
+    ids / scores / counts == the oracle; lists here are long (bitmap-backed) and span 4 levels."""
+    import torch
+    from seekstorm_b200 import Index, QueryType, ResultType, synth
+    n, vocab = 200000, 50000
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    ix = Index(0)
+    orc = O.OracleIndex()
+    ls = 0
+    for lv in synth.gen_lexical_corpus(n, vocab, 41, dev, with_positions=True):
+        ix.add_synth_level(lv)
+        orc.add_level(lv.to_numpy())
+        ls += lv.len_sum_normalized
+    ix.commit(n, ls); orc.commit(n, ls)
+    rng = np.random.default_rng(42)
+    phrases = [[int(x) for x in np.floor(np.exp(rng.uniform(0, np.log(120), int(rng.integers(2, 4)))))] for _ in range(96)]
+    qk = query_keys(phrases)
+    got, cnt = ix.search_lexical_batch(qk, QueryType.Phrase, 10, ResultType.TopkCount)
+    n_hit = 0
+    for i, k in enumerate(qk):
+        want, tot = orc.search_phrase(k, 10, O.RESULT_TOPKCOUNT)
+        assert got[i] == want and int(cnt[i]) == tot, (i, phrases[i], got[i][:2], want[:2], int(cnt[i]), tot)
+        n_hit += tot > 0
+    assert n_hit > 60
+    ix.close()
