@@ -251,7 +251,7 @@ __device__ __forceinline__ uint32_t meta_cperm(uint32_t m, uint32_t c) { return 
 // block bound), the in-query-order suffix sums S[p] / R[p], the count order, the AND driver — and writes them as one
 // 128-byte record.  Thread 0 finally cuts the sorted record list into work items.
 __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __restrict__ q_off, const uint64_t* __restrict__ q_keys,
-                                                const uint8_t* __restrict__ q_flags /*or null*/, const uint32_t* __restrict__ f_off /*or null*/, const uint32_t* __restrict__ f_mask /*or null*/, uint32_t phrase, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
+                                                const uint8_t* __restrict__ q_flags /*or null*/, const uint32_t* __restrict__ f_off /*or null*/, const uint32_t* __restrict__ f_mask /*or null*/, uint32_t flags /* bit 0 phrase batch, bit 1 no counts wanted */, uint32_t query_type, QueryPlan* plans, LvRec* recs, uint16_t* item_start, uint32_t* ctr,
                                                 uint64_t* theta, int* lock, uint64_t* count, uint64_t* glist, uint32_t n_pow2,
                                                 uint32_t item_w, uint32_t first_lim, uint32_t gmax) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -299,17 +299,19 @@ __global__ void __launch_bounds__(128) lex_plan(LexView v, const uint32_t* __res
             for (uint32_t u = 0; u < nl; u++) if (pl.t[u].first == st[t].first) { dup = true; uidx = u; }
             if (!dup) pl.t[nl++] = st[t];
             // phrase: token n_phr of the phrase (term_index_nonunique) is unique term uidx (non_unique_query_list, add_result.rs:3594-3607)
-            if (phrase && n_phr < SSB_MAX_QUERY_TERMS) pl.phr[n_phr++] = (uint8_t)uidx;
+            if ((flags & 1u) && n_phr < SSB_MAX_QUERY_TERMS) pl.phr[n_phr++] = (uint8_t)uidx;
         }
-        if (phrase && (missing || nl == 0)) n_phr = 0;
-        pl.n_phr = (phrase && n_phr >= 2 && nl) ? n_phr : 0u;      // a one-token phrase is a plain term query
+        if ((flags & 1u) && (missing || nl == 0)) n_phr = 0;
+        pl.n_phr = ((flags & 1u) && n_phr >= 2 && nl) ? n_phr : 0u;      // a one-token phrase is a plain term query
         // search.rs:3290-3296: AND with an unknown term -> empty result; OR drops the term
         if (query_type == SSB_QUERY_INTERSECTION && missing) nl = 0;
         pl.n_live = nl; pl.n_items = 0; pl.n_recs = 0; pl.n_not = nl ? nn : 0;
         // facet filters: such a query is scored and counted by the one-term-per-lane kernel, which enumerates every match
         pl.filt_first = f_off ? f_off[q] : 0u; pl.n_filt = f_off ? f_off[q + 1] - f_off[q] : 0u;
         pl.field_mask = (f_mask && v.n_fields > 1) ? (f_mask[q] & ((1u << v.n_fields) - 1u)) : 0u;   // one indexed field: the filter can never reject
-        pl.fast = (nl <= v.fast_t && pl.n_filt == 0 && pl.field_mask == 0 && pl.n_phr == 0) ? 1u : 0u;
+        // facet-filtered queries stay on the record path when nothing has to be counted (flags bit 1): lex_score tests the filter on the
+        // exact-score survivors; with counts every match must be tested -> lex_generic
+        pl.fast = (nl <= v.fast_t && (pl.n_filt == 0 || (flags & 2u)) && pl.field_mask == 0 && pl.n_phr == 0) ? 1u : 0u;
     }
     for (uint32_t b = threadIdx.x; b < nlv; b += blockDim.x) {
         bound[b] = 0.f; cnt[b] = 0;
@@ -666,7 +668,7 @@ struct ItemCtx {
     bool scoring, need_count, is_and;
 };
 
-struct WarpSm { LvRec recs[GMAX]; uint2 queue[QCAP]; uint4 q2[64]; const QueryPlan* pl; uint32_t n_not; uint32_t nq2; uint32_t it_base; unsigned it_mask; uint32_t pad[2]; };   // 1024 + 1536 + 1024 + 32 B per warp
+struct WarpSm { LvRec recs[GMAX]; uint2 queue[QCAP]; uint4 q2[64]; const QueryPlan* pl; uint32_t n_not; uint32_t nq2; uint32_t it_base; unsigned it_mask; uint32_t n_filt, filt_first /* facet filters of the item's query (HAS_NOT instantiations) */; };   // 1024 + 1536 + 1024 + 32 B per warp
 
 // thresholds derived from the ordered-uint k-th score `thr` (0 = list not full yet): BM25 scores are non-negative, so
 // the per-posting tests are plain float compares against thr_lo = thr_f / INFL (rounded down).
@@ -715,7 +717,10 @@ __device__ __forceinline__ void score_queued(const LexView& v, const WarpSm& w, 
     uint32_t t = thr.u;
     alive = alive && ord_f32(score) >= thr.u;
     if (alive && is_deleted(v, rec.docbase | d)) alive = false;
-    if (HAS_NOT) { if (alive && w.n_not && in_not_lists(v, w.pl, w.n_not, rec.lv, d)) alive = false; }   // '-' terms (not_query_list); own kernel instantiation
+    if (HAS_NOT) {   // per-survivor predicates: their own kernel instantiation, the common one carries no out-of-line call
+        if (alive && w.n_not && in_not_lists(v, w.pl, w.n_not, rec.lv, d)) alive = false;                       // '-' terms (not_query_list)
+        if (alive && w.n_filt && facet_rejects(v, w.filt_first, w.n_filt, rec.docbase | d)) alive = false;      // facet filters (Topk: record path)
+    }
     insert_candidates(L, t, alive, score, rec.docbase | d, k, lane, dirty, ceil);
     if (t != thr.u) thr.set(t);
 }
@@ -1338,7 +1343,7 @@ __global__ void __launch_bounds__(256, SSB_LEX_MINB) lex_score(LexView v, const 
         const uint64_t ceil = ceil_keys ? __ldg(&ceil_keys[q]) : ~0ull;
         if (ceil == 0) continue;                         // this query's result list is already exhausted
         const uint32_t nrec = stage_item(w, recs, item_start, v.n_levels, q, j, lane);
-        if (lane == 0) { w.pl = pl; w.n_not = __ldg(&pl->n_not); w.nq2 = 0; }
+        if (lane == 0) { w.pl = pl; w.n_not = __ldg(&pl->n_not); w.nq2 = 0; w.n_filt = __ldg(&pl->n_filt); w.filt_first = __ldg(&pl->filt_first); }
         __syncwarp();
         Thr thr; thr.set((uint32_t)(__ldcg(&theta[q]) >> 32));
         if (ord_f32(w.recs[0].bound) < thr.u) { st_skipped += nrec; continue; }   // whole item below θ
@@ -2034,7 +2039,7 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     // item shape (tunable for experiments; defaults measured on C3): target postings per item, levels of a query's first item, levels per item
     static const uint32_t item_w = env_u32("SSB_LEX_ITEM_W", ITEM_W, 64, 1u << 20), first_lim = env_u32("SSB_LEX_FIRST", 2, 1, GMAX),
                           gmax = env_u32("SSB_LEX_GMAX", GMAX, 1, GMAX), grid_mult = env_u32("SSB_LEX_GRID", SSB_LEX_MINB, 1, 16);
-    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, filtered ? ws.foff : nullptr, fmask_dev, phrase, qt_eff, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
+    lex_plan<<<nq, 128, plan_smem, st>>>(v, ws.qoff, ws.qkeys, q->term_flags ? ws.qflags : nullptr, filtered ? ws.foff : nullptr, fmask_dev, phrase | (result_type == SSB_RESULT_TOPK ? 2u : 0u), qt_eff, ws.plans, ws.recs, ws.item_start, ws.ctr, ws.theta, ws.lock, ws.count, glist, n_pow2,
                                          item_w, first_lim, gmax);
     SSB_CUDA_TRY(cudaGetLastError());
     const bool is_and = qt_eff == SSB_QUERY_INTERSECTION;
@@ -2045,7 +2050,7 @@ int32_t LexIndex::search_keys(LexWorkspace& ws, cudaStream_t st, const ssb_lex_b
     if (want_topk) {
         const int grid = n_sms_ * (int)grid_mult;
         // batches that carry NOT terms ('-' operator) run their own instantiation: the common kernel stays free of the out-of-line probe
-        const bool hn = q->term_flags != nullptr;
+        const bool hn = q->term_flags != nullptr || filtered;
 #define SSB_LAUNCH_SCORE(A, N) lex_score<A, N><<<grid, 256, 0, st>>>(v, ws.plans, ws.recs, ws.item_start, nq, kk, ws.ctr, ws.theta, ws.lock, glist, ws.stats, ceil_dev)
 #define SSB_LAUNCH_SCORE_ALL() do { if (is_and) { if (hn) SSB_LAUNCH_SCORE(true, true); else SSB_LAUNCH_SCORE(true, false); } \
                                     else { if (hn) SSB_LAUNCH_SCORE(false, true); else SSB_LAUNCH_SCORE(false, false); } } while (0)
