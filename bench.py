@@ -641,7 +641,7 @@ def _bm25_filter_variants(a, ix, qk, out_keys, steps, world, dev):
         step_f(); torch.cuda.synchronize()
         sv = ix.last_stats()
         res[name] = {"value": nf * nv / (msv / 1e3), "unit": "queries/s", "kernel_ms": sv["dominant_kernel_ns"] / 1e6, "queries_per_step": nf,
-                     "selectivity": 0.5, "kernel": "lex_generic (per-candidate predicate path)"}
+                     "selectivity": 0.5, "kernel": "lex_score<.., HAS_NOT> (Topk: filter on the exact-score survivors) / lex_generic (counts: every match tested)"}
     ix.set_facets({})
     return res
 

@@ -537,7 +537,10 @@ class Index:
         # field_filter: names of indexed fields (self.field_names, in schema order) or their indices -> one bitmask
         fmask = 0
         for f in field_filter:
-            fmask |= 1 << (self.field_names.index(f) if isinstance(f, str) else int(f))
+            names = getattr(self, "field_names", [])
+            if isinstance(f, str) and f not in names:
+                raise ValueError(f"field_filter: unknown indexed field {f!r} (indexed fields: {names})")
+            fmask |= 1 << (names.index(f) if isinstance(f, str) else int(f))
         search_mode = search_mode or SearchMode.Lexical()
         ro = ResultObject(original_query=query_string, query=query_string)
         heap = offset + length                       # search.rs:1708 per-shard length = offset+length

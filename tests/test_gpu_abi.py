@@ -99,9 +99,12 @@ def test_search_mirror_vector_hybrid_and_paging():
     assert ro.results == [] and ro.result_count_total == orc.search(qk[:1], O.QUERY_UNION, 0, O.RESULT_COUNT)[1]   # length 0 -> Count
     ro = ix.search("unknownterm", None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.TopkCount)
     assert ro.results == [] and ro.result_count_total == 0                          # infallible: empty ResultObject
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                       # field_filter names a field the (single-field) index does not have
         ix.search(qs, None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.Topk, field_filter=["body"])
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):              # facet COUNTING stays outside the GPU hot path
+        ix.search(qs, None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.Topk, query_facets=["price"])
+    from seekstorm_b200 import SsbError
+    with pytest.raises(SsbError):                         # a phrase query needs levels loaded with positions
         ix.search('"t30 t700"', None, QueryType.Union, SearchMode.Lexical(), False, 0, 10, ResultType.Topk)
     ix.close()
 
