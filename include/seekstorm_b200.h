@@ -208,7 +208,7 @@ int32_t ssb_lexical_set_global_df(ssb_index* ix, const uint64_t* keys, const uin
  * add_result.rs:2036-2197).  Adds every level and commits with the file's own indexed_doc_count / positions_sum_normalized.
  * bytes: HOST memory (e.g. the mmap of the file).  params come from the shard's index.json / schema.json. */
 typedef struct {
-    uint32_t indexed_field_count;   /* schema: indexed fields; only 1 is supported (multi-field BM25F is out of scope)        */
+    uint32_t indexed_field_count;   /* schema: indexed fields; only 1 is supported by the loader (multi-field BM25F: neutral layout, ssb_lexical_set_field_boosts)        */
     uint32_t key_head_size;         /* 20 without n-gram indexing, 22 / 23 with bigram / trigram df bytes                      */
     uint32_t segment_number_bits;   /* 11 (create_shard(.., 11, ..), index.rs:3295): 2048 dictionary segments per level        */
     uint32_t reserved;

@@ -10,7 +10,8 @@
 //
 // Like the reference, `search` is infallible by type for data-dependent failures (unknown terms, empty index -> empty
 // ResultObject, search.rs:1630-1631); programming errors (k too large, no GPU, unsupported arguments) throw ssb::Error.
-// Facets / filters / sort / uncommitted search / query rewriting / phrase queries are outside the GPU hot path and throw.
+// Facet counting / sort / uncommitted search / query rewriting are outside the GPU hot path and throw; facet filters, field filter and
+// phrase queries go through the C-ABI (ssb_facet_filter / field_masks / SSB_QUERY_PHRASE).
 #pragma once
 #include <cstdint>
 #include <cstring>

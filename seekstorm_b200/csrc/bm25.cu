@@ -1,6 +1,7 @@
 // bm25.cu — BM25 AND/OR top-k over block-partitioned posting lists (sm_100a).
 //
-// Replaces, for committed data without facets/filters/phrases (all paths /root/reference/seekstorm/src/):
+// Replaces, for committed data (all paths /root/reference/seekstorm/src/; the per-candidate chain — delete set, NOT lists, facet filters,
+// field filter, phrase check: add_result.rs:3435-3500, 3124-3137, 3586-3684 — runs as predicates of the scoring kernels, see lex_generic):
 //   intersection_blockid / intersection_docid   intersection.rs:2023-2301 / 112-2013   (AND)
 //   intersection_bitmap_2                       intersection.rs:33-108                 (dense x dense: bitmap-word AND + popcount)
 //   union_docid_2 / union_docid_3 / single_blockid  union.rs:1168-1479, single.rs:292-417 (OR + block-max)
