@@ -2,7 +2,9 @@
  * ssb_oracle.h — CPU ORACLE for the seekstorm_b200 hot path.  TEST INFRASTRUCTURE ONLY.
  *
  * This is a plain-C restatement of the reference's (SeekStorm 3.3.4) query-time arithmetic for
- * BM25 AND/OR top-k, brute-force f32 vector top-k, Cosine + ScalarQuantizationI8 int8 vector top-k and RRF fusion.  Only tests/,
+ * BM25 AND / OR / phrase top-k (single- and multi-field BM25F) with the per-candidate chain (delete set, NOT lists, facet filters, field
+ * filter), brute-force f32 vector top-k, the int8 quantisers (ScalarQuantizationI8 Cosine / Dot / Euclidean incl. the affine variant,
+ * TurboQuantI8) with their scores, the IVF probe (python side) and RRF fusion.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may link or call it.
  * The product path (seekstorm_b200/csrc, libseekstorm_b200.so) never does.
  *
@@ -10,7 +12,9 @@
  * assert only result COUNTS (tests/test.rs:150-208, 693-745) plus aarch64-only kernel-vs-scalar
  * checks (seekstorm/src/vector_similarity.rs:3008-3146).  Those fixtures are reproduced in
  * tests/golden/.  BM25 scores / rank order / cosine scores / RRF scores are "parity unpinned" by
- * the reference; they are pinned here by hand-computed known-answer vectors (tests/golden/).
+ * the reference; they are pinned here by hand-computed known-answer vectors (tests/golden/) and, for the rows added in round 2, by
+ * independent restatements in tests/ (typed numpy columns for the facet filters, substring search over token sequences for phrases,
+ * a Hadamard matrix for TurboQuant, exact squared distances for the affine quantiser on integer data).
  *
  * All file:line citations are relative to /root/reference/seekstorm/src/.
  */
