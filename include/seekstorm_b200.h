@@ -211,11 +211,13 @@ typedef struct {
     uint32_t indexed_field_count;   /* schema: indexed fields; only 1 is supported by the loader (multi-field BM25F: neutral layout, ssb_lexical_set_field_boosts)        */
     uint32_t key_head_size;         /* 20 without n-gram indexing, 22 / 23 with bigram / trigram df bytes                      */
     uint32_t segment_number_bits;   /* 11 (create_shard(.., 11, ..), index.rs:3295): 2048 dictionary segments per level        */
-    uint32_t reserved;
+    uint32_t decode_positions;      /* != 0: also decode every posting's term positions (embedded layouts index_posting.rs:590-640, VINT delta  */
+                                    /* blobs compress_postinglist.rs:946-977) and load them for SSB_QUERY_PHRASE; positions above 65535 fail   */
 } ssb_index_bin_params;
 int32_t ssb_load_index_bin(ssb_index* ix, const void* bytes, uint64_t len, const ssb_index_bin_params* params, uint64_t* n_docs_out);
 /* host-only walk of an index.bin (no GPU needed): out = {levels, single-term keys, postings, sum of tf, indexed_doc_count,
- * positions_sum_normalized, FNV checksum over every (key, level, doc id, tf) in file order, 0} */
+ * positions_sum_normalized, FNV checksum over every (key, level, doc id, tf) in file order, FNV checksum over every decoded
+ * position (decode_positions) or 0} */
 int32_t ssb_index_bin_inspect(const void* bytes, uint64_t len, const ssb_index_bin_params* params, uint64_t out[8]);
 /* vector.bin of one shard (vector.rs:1066-1094; Precision::F32 records of 24 + 4*dims bytes); dims = the index's vector_dims */
 int32_t ssb_load_vector_bin(ssb_index* ix, const void* bytes, uint64_t len, uint64_t* n_vectors_out);

@@ -44,7 +44,7 @@ class SsbVecQuery(C.Structure):
 
 class SsbIndexBinParams(C.Structure):
     _fields_ = [("indexed_field_count", C.c_uint32), ("key_head_size", C.c_uint32), ("segment_number_bits", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("decode_positions", C.c_uint32)]
 
 
 class SsbLevelDesc(C.Structure):

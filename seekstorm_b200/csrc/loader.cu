@@ -61,9 +61,42 @@ bool vint(const uint8_t* b, uint64_t len, uint64_t at, uint32_t& out) {
     return true;
 }
 
+// a position blob = VINT positions_count, then positions_count VINT deltas (compress_positions, compress_postinglist.rs:946-977)
+static bool vint_len(const uint8_t* b, uint64_t len, uint64_t at, uint32_t& out, uint32_t& used) {
+    if (!vint(b, len, at, out)) return false;
+    used = (b[at] & 0x80u) ? 1u : ((b[at + 1] & 0x80u) ? 2u : 3u);
+    return true;
+}
+static bool push_positions(const uint32_t* deltas, uint32_t n, std::vector<uint16_t>& pos, const char*& why);
+static bool blob_positions(const uint8_t* body, uint64_t blen, uint64_t at, uint32_t tf, std::vector<uint16_t>& pos, const char*& why) {
+    uint32_t v = 0, used = 0, p = 0;
+    if (!vint_len(body, blen, at, v, used)) { why = "position blob out of range"; return false; }
+    at += used;
+    for (uint32_t i = 0; i < tf; i++) {
+        if (!vint_len(body, blen, at, v, used)) { why = "position blob runs past the segment body"; return false; }
+        at += used;
+        p = i == 0 ? v : p + v + 1u;
+        if (p > 65535u) { why = "term position above 65535 (positions are kept as u16)"; return false; }
+        pos.push_back((uint16_t)p);
+    }
+    return true;
+}
+
 // one posting list: doc ids + tfs appended to the level's arrays.  body = the segment's body bytes.
+// positions of one posting from its delta coding (add_result.rs:38-59 + the phrase matcher's `pos += next + 1`, :3620-3640): the first value is
+// the absolute position, every further one the gap minus one
+static bool push_positions(const uint32_t* deltas, uint32_t n, std::vector<uint16_t>& pos, const char*& why) {
+    uint32_t p = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        p = i == 0 ? deltas[0] : p + deltas[i] + 1u;
+        if (p > 65535u) { why = "term position above 65535 (positions are kept as u16)"; return false; }
+        pos.push_back((uint16_t)p);
+    }
+    return true;
+}
+
 bool decode_key(const uint8_t* body, uint64_t blen, uint32_t count, uint32_t pivot, uint32_t ctp, std::vector<uint16_t>& ids,
-                std::vector<uint16_t>& tfs, const char*& why) {
+                std::vector<uint16_t>& tfs, const char*& why, std::vector<uint16_t>* pos_out = nullptr) {
     const uint32_t type = ctp >> 30, range = ctp & 0x3FFFFFFFu;
     // intersection.rs:221-227: pivot*2 + (count - pivot)*3 pointer bytes precede the doc-id container
     const uint64_t psum = (uint64_t)pivot * 2 + (pivot <= count - 1 ? (uint64_t)(count - pivot) * 3 : 0);
@@ -100,22 +133,40 @@ bool decode_key(const uint8_t* body, uint64_t blen, uint32_t count, uint32_t piv
             const uint64_t at = (uint64_t)range + 2ull * p;
             if (at + 2 > blen) { why = "pointer past the segment body"; return false; }
             const uint32_t rp = rd16(body + at);
-            if (rp & 0x8000u) tf = (rp >> 14) == 2u ? 1u : 2u;                       // embedded: 10 -> 1 position, 11 -> 2
-            else {
+            if (rp & 0x8000u) {
+                tf = (rp >> 14) == 2u ? 1u : 2u;                                     // embedded: 10 -> 1 position, 11 -> 2
+                if (pos_out) {                                                       // 14 payload bits: one 14-bit delta or 7 + 7 (index_posting.rs:590-640)
+                    uint32_t dl[2];
+                    if (tf == 1) dl[0] = rp & 0x3FFFu; else { dl[0] = (rp >> 7) & 0x7Fu; dl[1] = rp & 0x7Fu; }
+                    if (!push_positions(dl, tf, *pos_out, why)) return false;
+                }
+            } else {
                 const uint32_t back = rp & 0x7FFFu;
                 if (back > range || !vint(body, blen, (uint64_t)range - back, tf)) { why = "position blob out of range"; return false; }
+                if (pos_out && !blob_positions(body, blen, (uint64_t)range - back, tf, *pos_out, why)) return false;
             }
         } else {
             const uint64_t at = (uint64_t)range + 3ull * p - pivot;
             if (at + 3 > blen) { why = "pointer past the segment body"; return false; }
             const uint32_t rp = (uint32_t)body[at] | ((uint32_t)body[at + 1] << 8) | ((uint32_t)body[at + 2] << 16);
-            if (rp & 0x800000u) tf = ((rp >> 21) & 3u) + 1u;                         // embedded: 100 -> 1 ... 111 -> 4
-            else {
+            if (rp & 0x800000u) {
+                tf = ((rp >> 21) & 3u) + 1u;                                         // embedded: 100 -> 1 ... 111 -> 4
+                if (pos_out) {                                                       // 21 payload bits: 21 | 10 + 11 | 7 + 7 + 7 | 5 + 5 + 5 + 6
+                    uint32_t dl[4];
+                    if (tf == 1) dl[0] = rp & 0x1FFFFFu;
+                    else if (tf == 2) { dl[0] = (rp >> 11) & 0x3FFu; dl[1] = rp & 0x7FFu; }
+                    else if (tf == 3) { dl[0] = (rp >> 14) & 0x7Fu; dl[1] = (rp >> 7) & 0x7Fu; dl[2] = rp & 0x7Fu; }
+                    else { dl[0] = (rp >> 16) & 0x1Fu; dl[1] = (rp >> 11) & 0x1Fu; dl[2] = (rp >> 6) & 0x1Fu; dl[3] = rp & 0x3Fu; }
+                    if (!push_positions(dl, tf, *pos_out, why)) return false;
+                }
+            } else {
                 const uint32_t back = rp & 0x7FFFFFu;
                 if (back > range || !vint(body, blen, (uint64_t)range - back, tf)) { why = "position blob out of range"; return false; }
+                if (pos_out && !blob_positions(body, blen, (uint64_t)range - back, tf, *pos_out, why)) return false;
             }
         }
         if (tf == 0) { why = "positions_count 0"; return false; }
+        if (pos_out && tf > 65535u) { why = "more than 65535 positions in one posting"; return false; }
         tfs[base + p] = (uint16_t)(tf > 65535u ? 65535u : tf);
     }
     return true;
@@ -136,7 +187,8 @@ static int32_t walk_index_bin(const uint8_t* bytes, uint64_t len, const ssb_inde
     if (!r.ok || major != 6) { set_error("load_index_bin: format version %u (this loader reads major version 6, index.rs:105)", (unsigned)major); return SSB_E_UNSUPPORTED; }
     uint64_t doc_count = 0, pos_sum = 0;
     uint32_t level = 0;
-    std::vector<uint64_t> keys; std::vector<uint32_t> offs; std::vector<uint16_t> ids, tfs; std::vector<std::pair<uint32_t, uint32_t>> seg;
+    std::vector<uint64_t> keys; std::vector<uint32_t> offs; std::vector<uint16_t> ids, tfs, poss; std::vector<std::pair<uint32_t, uint32_t>> seg;
+    const bool want_pos = prm->decode_positions != 0;   // term positions for phrase queries (off: tf only, as before)
     while (r.pos < len) {
         if (level == 0) r.u16();                                   // longest_field_id
         if (!r.need(65536)) break;
@@ -148,7 +200,7 @@ static int32_t walk_index_bin(const uint8_t* bytes, uint64_t len, const ssb_inde
         if (doc_count <= (uint64_t)level * 65536) { set_error("load_index_bin: level %u: indexed_doc_count %llu", level, (unsigned long long)doc_count); return SSB_E_INVALID; }
         const uint64_t rest = doc_count - (uint64_t)level * 65536;
         const uint32_t n_docs = (uint32_t)(rest < 65536 ? rest : 65536);
-        keys.clear(); offs.assign(1, 0); ids.clear(); tfs.clear();
+        keys.clear(); offs.assign(1, 0); ids.clear(); tfs.clear(); poss.clear();
         for (uint32_t s = 0; s < nseg; s++) {
             const uint64_t head_bytes = (uint64_t)seg[s].second * khs;
             if (seg[s].first < head_bytes || !r.need(seg[s].first)) { set_error("load_index_bin: level %u segment %u: block_length %u < key heads / past the end", level, s, seg[s].first); return SSB_E_INVALID; }
@@ -163,7 +215,7 @@ static int32_t walk_index_bin(const uint8_t* bytes, uint64_t len, const ssb_inde
                 const uint32_t count = (uint32_t)rd16(h + 8) + 1u;
                 const uint32_t pivot = rd16(h + khs - 6), ctp = rd32(h + khs - 4);
                 const char* why = "";
-                if (!decode_key(body, blen, count, pivot, ctp, ids, tfs, why)) {
+                if (!decode_key(body, blen, count, pivot, ctp, ids, tfs, why, want_pos ? &poss : nullptr)) {
                     set_error("load_index_bin: level %u segment %u key %016llx: %s", level, s, (unsigned long long)key, why);
                     return SSB_E_INVALID;
                 }
@@ -173,6 +225,7 @@ static int32_t walk_index_bin(const uint8_t* bytes, uint64_t len, const ssb_inde
         ssb_level_desc d{};
         d.level_id = level; d.n_docs = n_docs; d.n_terms = (uint32_t)keys.size();
         d.term_keys = keys.data(); d.posting_offsets = offs.data(); d.doc_ids = ids.data(); d.tfs = tfs.data(); d.doc_len_bytes = doclen;
+        if (want_pos) { poss.push_back(0); d.positions = poss.data(); }      // (never null, even for a level without postings)
         SSB_TRY(on_level(d));
         level++;
     }
@@ -196,7 +249,7 @@ int32_t load_index_bin(LexIndex* lex, const uint8_t* bytes, uint64_t len, const 
 // host-only walk of the file (no device work): totals + an order-dependent checksum of every (key, doc id, tf) — used by the
 // CPU tests of the parser and as a sanity check before a load
 int32_t inspect_index_bin(const uint8_t* bytes, uint64_t len, const ssb_index_bin_params* prm, uint64_t out[8]) {
-    uint64_t levels = 0, terms = 0, postings = 0, tf_sum = 0, h = 1469598103934665603ull;
+    uint64_t levels = 0, terms = 0, postings = 0, tf_sum = 0, h = 1469598103934665603ull, hp = 1469598103934665603ull;
     auto mix = [&](uint64_t x) { h = (h ^ x) * 1099511628211ull; };
     uint64_t doc_count = 0, pos_sum = 0;
     SSB_TRY(walk_index_bin(bytes, len, prm, [&](const ssb_level_desc& d) {
@@ -205,9 +258,14 @@ int32_t inspect_index_bin(const uint8_t* bytes, uint64_t len, const ssb_index_bi
             mix(d.term_keys[t]);
             for (uint32_t i = d.posting_offsets[t]; i < d.posting_offsets[t + 1]; i++) { mix(((uint64_t)d.level_id << 32) | ((uint64_t)d.doc_ids[i] << 16) | d.tfs[i]); tf_sum += d.tfs[i]; }
         }
+        if (d.positions) {     // decode_positions: a second checksum over every position, in posting order
+            uint64_t np = 0;
+            for (uint32_t i = 0; i < d.posting_offsets[d.n_terms]; i++) np += d.tfs[i];
+            for (uint64_t i = 0; i < np; i++) hp = (hp ^ d.positions[i]) * 1099511628211ull;
+        }
         return (int32_t)SSB_OK;
     }, &doc_count, &pos_sum));
-    out[0] = levels; out[1] = terms; out[2] = postings; out[3] = tf_sum; out[4] = doc_count; out[5] = pos_sum; out[6] = h; out[7] = 0;
+    out[0] = levels; out[1] = terms; out[2] = postings; out[3] = tf_sum; out[4] = doc_count; out[5] = pos_sum; out[6] = h; out[7] = prm->decode_positions ? hp : 0;
     return SSB_OK;
 }
 

@@ -209,12 +209,12 @@ class Index:
             self.add_lexical_level(n["level_id"], n["n_docs"], n["term_keys"], n["posting_offsets"], n["doc_ids"],
                                    n["tfs"], n["doc_len_bytes"], n.get("positions"))
 
-    def load_index_bin(self, data, indexed_field_count: int = 1, key_head_size: int = 20, segment_number_bits: int = 11) -> int:
+    def load_index_bin(self, data, indexed_field_count: int = 1, key_head_size: int = 20, segment_number_bits: int = 11, decode_positions: bool = False) -> int:
         """Load one shard's index.bin (bytes / mmap / numpy uint8 array, the reference's own format, index.rs:3253-3516) and commit.
         Returns indexed_doc_count."""
         from ._lib import SsbIndexBinParams
         buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
-        prm = SsbIndexBinParams(indexed_field_count, key_head_size, segment_number_bits, 0)
+        prm = SsbIndexBinParams(indexed_field_count, key_head_size, segment_number_bits, 1 if decode_positions else 0)   # positions: phrase queries
         n = C.c_uint64(0)
         check(lib().ssb_load_index_bin(self._h, buf.ctypes.data, buf.size, C.byref(prm), C.byref(n)))
         self.indexed_doc_count = n.value

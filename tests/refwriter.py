@@ -115,8 +115,15 @@ def synth_positions(doc_ids, tfs, rng):
     return out
 
 
+def deltas_of(positions):
+    """absolute ascending positions of one posting -> the reference's coding: first value absolute, then gap - 1 (the phrase matcher
+    advances with `pos += next + 1`, add_result.rs:3620-3640)"""
+    return [int(positions[0])] + [int(b) - int(a) - 1 for a, b in zip(positions[:-1], positions[1:])]
+
+
 def write_index_bin(levels, n_docs_total, seed=0):
-    """levels: neutral dicts (synth.Level.to_numpy()): level_id ascending from 0, each full (65536 docs) except the last.
+    """levels: neutral dicts (synth.Level.to_numpy()): level_id ascending from 0, each full (65536 docs) except the last.  A level that
+    carries 'positions' (u16 [sum of tfs], posting order) is written with exactly those positions, otherwise with synthetic ones.
     Returns (bytes, positions_sum_normalized)."""
     from seekstorm_b200 import synth
     rng = np.random.default_rng(seed)
@@ -135,6 +142,8 @@ def write_index_bin(levels, n_docs_total, seed=0):
         out.append(struct.pack("<QQ", cum_docs, cum_len))
         segs = [[] for _ in range(nseg)]
         offs = lv["posting_offsets"]
+        pos_all = lv.get("positions")
+        pos_off = None if pos_all is None else np.concatenate([[0], np.cumsum(lv["tfs"].astype(np.int64))])
         for t, key in enumerate(lv["term_keys"]):
             key = int(key)
             segs[(key >> 40) & (nseg - 1)].append((key, t))
@@ -145,7 +154,11 @@ def write_index_bin(levels, n_docs_total, seed=0):
             for key, t in segs[s]:
                 ids = lv["doc_ids"][offs[t]:offs[t + 1]]
                 tfs = lv["tfs"][offs[t]:offs[t + 1]]
-                kb, rng_off, pivot, ctype = _key_body(ids, synth_positions(ids, tfs, rng))
+                if pos_all is None:
+                    plist = synth_positions(ids, tfs, rng)
+                else:
+                    plist = [deltas_of(pos_all[pos_off[j]:pos_off[j + 1]]) for j in range(int(offs[t]), int(offs[t + 1]))]
+                kb, rng_off, pivot, ctype = _key_body(ids, plist)
                 ctp = (ctype << 30) | (len(body) + rng_off)
                 hb += struct.pack("<QHHHHI", key, len(ids) - 1, int(ids[0]), 0, pivot, ctp)
                 body += kb

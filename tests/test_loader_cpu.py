@@ -75,3 +75,50 @@ def test_index_bin_rejects_corrupt_files():
         p2 = _lib.SsbIndexBinParams(fields, khs, 11, 0)
         buf = np.frombuffer(data, dtype=np.uint8)
         assert L.ssb_index_bin_inspect(buf.ctypes.data, buf.size, C.byref(p2), out.ctypes.data) != 0
+
+
+def test_index_bin_positions_round_trip_host_parser():
+    """decode_positions: every term position written by the restated writer (embedded 2- / 3-byte layouts, VINT delta blobs) comes back
+    from the library's parser — checksum over all positions in file order — on a corpus of real token sequences (tests/helpers_phrase.py)
+    plus postings with long position lists and wide gaps."""
+    from helpers_phrase import sequence_corpus
+    docs, lvs, _ = sequence_corpus(3000, 120, 13, docs_per_level=65536, mean_len=25)
+    lv = lvs[0]
+    # extra keys: long position lists (blobs, 3-byte pointers further down the key) and wide gaps (2-byte VINTs)
+    extra = {0x5000: ([3, 9], [np.arange(0, 1200, 3), np.array([5, 700, 20000, 65000])]),
+             0x6000: (list(range(100, 400)), [np.array([i % 50, 60 + i % 7, 900 + i]) for i in range(300)]),
+             # 4200 blobs of 8 bytes push the key past the 2-byte pointer area; the postings behind them use the 3-byte embedded layouts
+             # (21 | 10 + 11 | 7 + 7 + 7 | 5 + 5 + 5 + 6 bits) and 3-byte blob pointers
+             0x7000: (list(range(0, 8900, 2)), [np.array([200 + i % 90, 4000 + i, 30000 + i]) for i in range(4200)]
+                      + [np.array([1000 + i]) for i in range(50)] + [np.array([i % 500, 600 + i % 900]) for i in range(50)]
+                      + [np.array([i % 100, 50 + i % 100, 100 + i % 100]) for i in range(50)]
+                      + [np.array([i % 20, 25 + i % 20, 50 + i % 20, 80 + i % 40]) for i in range(50)]
+                      + [np.array([7, 9000, 9001, 9002, 40000 + i]) for i in range(50)])}
+    keys, offs = list(lv["term_keys"]), list(lv["posting_offsets"])
+    ids, tfs, pos = [lv["doc_ids"]], [lv["tfs"]], [lv["positions"]]
+    for k, (dl, pl) in extra.items():
+        keys.append(np.uint64(k << 3)); ids.append(np.array(dl, dtype=np.uint16)); tfs.append(np.array([len(p) for p in pl], dtype=np.uint16))
+        pos.append(np.concatenate(pl).astype(np.uint16)); offs.append(offs[-1] + len(dl))
+    lv["term_keys"] = np.array(keys, dtype=np.uint64); lv["posting_offsets"] = np.array(offs, dtype=np.uint32)
+    lv["doc_ids"] = np.concatenate(ids); lv["tfs"] = np.concatenate(tfs); lv["positions"] = np.concatenate(pos)
+    data, len_sum = refwriter.write_index_bin(lvs, 3000, seed=9)
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(8, dtype=np.uint64)
+    prm = _lib.SsbIndexBinParams(1, refwriter.KEY_HEAD_SIZE, refwriter.SEGMENT_BITS, 1)
+    _lib.check(_lib.lib().ssb_index_bin_inspect(buf.ctypes.data, buf.size, C.byref(prm), out.ctypes.data))
+    terms, post, tfsum, h = _checksum(lvs)
+    assert int(out[1]) == terms and int(out[2]) == post and int(out[3]) == tfsum and int(out[6]) == h
+    # expected position checksum: positions in FILE order (segments ascending, keys ascending inside a segment)
+    nseg = 1 << refwriter.SEGMENT_BITS
+    M = (1 << 64) - 1
+    hp = 1469598103934665603
+    poff = np.concatenate([[0], np.cumsum(lv["tfs"].astype(np.int64))])
+    order = sorted(range(len(lv["term_keys"])), key=lambda t: ((int(lv["term_keys"][t]) >> 40) & (nseg - 1), int(lv["term_keys"][t])))
+    for t in order:
+        a, b = int(lv["posting_offsets"][t]), int(lv["posting_offsets"][t + 1])
+        for p in lv["positions"][poff[a]:poff[b]]:
+            hp = ((hp ^ int(p)) * 1099511628211) & M
+    assert int(out[7]) == hp
+    prm0 = _lib.SsbIndexBinParams(1, refwriter.KEY_HEAD_SIZE, refwriter.SEGMENT_BITS, 0)
+    _lib.check(_lib.lib().ssb_index_bin_inspect(buf.ctypes.data, buf.size, C.byref(prm0), out.ctypes.data))
+    assert int(out[7]) == 0 and int(out[6]) == h                    # positions off: exactly the previous behaviour
