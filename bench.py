@@ -323,6 +323,20 @@ def measure_vector_kernel(a, ix, kname, q_host, q_dev, keys, local_rows, rank, w
     }
 
 
+def best_hbm_variant(kernels: dict):
+    """Among the measured scan variants, the one that sits highest on the HBM roofline (the headline is the FASTEST variant, which at 256
+    queries per pass is bound by the tensor pipe / shared memory rather than by HBM): {"kernel", "frac", "achieved", "value", "kernel_ms"}."""
+    best = None
+    for name, r in kernels.items():
+        rf = (r or {}).get("roofline") or {}
+        if rf.get("frac") is None:
+            continue
+        if best is None or rf["frac"] > best["frac"]:
+            best = {"kernel": name, "frac": rf["frac"], "achieved": rf.get("achieved"), "unit": rf.get("unit"), "value": r.get("value"),
+                    "kernel_ms": rf.get("kernel_ms")}
+    return best
+
+
 def bench_vector(a, rank, world, out):
     from seekstorm_b200 import Index, VectorSimilarity, synth
     from seekstorm_b200.parallel import init_shard_comm
@@ -374,6 +388,10 @@ def bench_vector(a, rank, world, out):
                      "filt": "scan_tc_f16_filter", "filt256": "scan_tc_f16_filter_n256", "filt256p": "scan_tc2_f16_filter_n256_pair"}[k]:
                     {kk: vv for kk, vv in res[k].items() if kk != "kernel_desc"} for k in names},
     })
+    try:   # the same corpus pass at its most HBM-efficient tile, next to the (faster) headline kernel
+        out["roofline"] = dict(out["roofline"], best_hbm_fraction_variant=best_hbm_variant(out["kernels"]))
+    except Exception:  # pragma: no cover
+        pass
     return ix, q_host
 
 
