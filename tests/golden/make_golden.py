@@ -7,6 +7,8 @@ formulas, evaluated on tiny hand-checkable inputs:
   * byte4 codec table (index.rs:4237-4279), idf edge cases (search.rs:3225-3230), bm25 cache (commit.rs:318-325),
     BM25 scores (add_result.rs:1450-1452), RRF (search.rs:1962-2035), NEON-test vectors
     (vector_similarity.rs:3011-3021 make_f32).
+  * round 2: TurboQuantI8 on an 8-d vector (vector_similarity.rs:1929-1958), the affine Euclidean quantiser with its running state
+    (:1414-1472), typed facet-filter edge cases (add_result.rs:340-478), phrase containment (:3586-3684).
 Run:  python tests/golden/make_golden.py   (writes golden.json next to this file)
 """
 import json
@@ -170,6 +172,86 @@ def main():
             s = s + d * d
         res.append([j, -float(s)])
     out["ref_fixture_vector"] = {"n": 3, "dims": 128, "results": res, "result_count": 3}
+
+    # ---- round 2: TurboQuantI8 (vector_similarity.rs:1929-1958) on an 8-d vector, every step a float32 scalar operation
+    tq_v = [f32(x) for x in (0.5, -1.25, 2.0, 0.125, -0.75, 3.5)]                    # 6 dims -> padded to 8
+    tq_mask = [f32(x) for x in (1, -1, -1, 1, 1, -1, 1, -1)]
+    a = [tq_v[i] * tq_mask[i] if i < 6 else f32(0.0) * tq_mask[i] for i in range(8)]
+    h = 1
+    while h < 8:
+        for i in range(0, 8, 2 * h):
+            for j in range(i, i + h):
+                x, y = a[j], a[j + h]
+                a[j], a[j + h] = x + y, x - y
+        h *= 2
+    nrm = f32(math.sqrt(8.0))
+    a = [x / nrm for x in a]
+    ss = f32(0.0)
+    for x in a:
+        ss = ss + x * x
+    sigma = f32(math.sqrt(float(ss))) / nrm
+    tq_scale = max(sigma / f32(32.0), f32(1e-8))
+    codes = []
+    for x in a:
+        r = float(x / tq_scale)
+        r = math.floor(abs(r) + 0.5) * (1 if r >= 0 else -1)                         # f32::round: half away from zero
+        codes.append(int(max(-127.0, min(127.0, r))))
+    sq = sum(c * c for c in codes)
+    out["turboquant"] = {"v": [float(x) for x in tq_v], "mask": [float(x) for x in tq_mask], "codes": codes, "scale": float(tq_scale),
+                         "norm": float(f32(sq) * tq_scale * tq_scale)}
+
+    # ---- round 2: affine Euclidean SQ (vector_similarity.rs:1414-1472) — three integer vectors through the running (min, max) state
+    def raster(r):
+        if not (r > 1.0):
+            return f32(r)
+        v, p = int(r) + 1, 1
+        while p < v:
+            p <<= 1
+        return f32(p - 1)
+    smin, smax = f32(np.finfo(np.float32).max), f32(-np.finfo(np.float32).max)
+    aff = []
+    for vec in ([3, 10, 90, 40], [0, 200, 7, 7], [5, 255, 100, 1]):
+        mn, mx = f32(min(vec)), f32(max(vec))
+        if mn < smin:
+            smin = mn
+        else:
+            mn = smin
+        if mx > smax:
+            smax = raster(mx - mn)
+        else:
+            mx = smax
+        scale = raster(mx - mn) / f32(255.0)
+        zf = float(f32(-128.0) - mn / scale)
+        zp = int(max(-128.0, min(127.0, math.floor(abs(zf) + 0.5) * (1 if zf >= 0 else -1))))
+        cd = []
+        for x in vec:
+            r = float(f32(x) / scale)
+            r = math.floor(abs(r) + 0.5) * (1 if r >= 0 else -1)
+            cd.append(int(max(-128, min(127, int(r) + zp))))
+        norm_i = sum(c * c for c in cd) - 2 * zp * sum(cd) + len(cd) * zp * zp
+        aff.append({"v": vec, "scale": float(scale), "zero_point": zp, "codes": cd, "sum_q": sum(cd), "norm": float(f32(norm_i) * scale * scale),
+                    "state": [float(smin), float(smax)]})
+    out["affine_sq"] = aff
+
+    # ---- round 2: facet filters — Rust Range<T>::contains / Vec::contains on typed values (is_facet_filter, add_result.rs:340-478)
+    nan = float("nan")
+    out["facet_filter"] = [
+        {"type": "U8", "value": 255, "start": 0, "end": 255, "pass": False}, {"type": "U8", "value": 254, "start": 0, "end": 255, "pass": True},
+        {"type": "I8", "value": -128, "start": -128, "end": -127, "pass": True}, {"type": "I32", "value": -5, "start": -4, "end": 10, "pass": False},
+        {"type": "I64", "value": -(2 ** 63), "start": -(2 ** 63), "end": 0, "pass": True}, {"type": "U64", "value": 2 ** 64 - 1, "start": 0, "end": 2 ** 64 - 1, "pass": False},
+        {"type": "F32", "value": -0.0, "start": 0.0, "end": 1.0, "pass": True}, {"type": "F32", "value": nan, "start": -1e30, "end": 1e30, "pass": False},
+        {"type": "F64", "value": 1.5, "start": nan, "end": 2.0, "pass": False}, {"type": "F64", "value": float("-inf"), "start": float("-inf"), "end": 0.0, "pass": True},
+        {"type": "F32", "value": 3.0, "start": 5.0, "end": 1.0, "pass": False}, {"type": "TIMESTAMP", "value": 1700000000, "start": 1600000000, "end": 1800000000, "pass": True},
+        {"type": "STRING16", "value": 7, "values": [1, 7, 9], "pass": True}, {"type": "STRING32", "value": 8, "values": [1, 7, 9], "pass": False},
+    ]
+
+    # ---- round 2: phrase (add_result.rs:3586-3684) — docs as token sequences; a doc matches iff the phrase is a contiguous subsequence
+    pdocs = [[1, 2, 3, 1, 2], [2, 1, 3], [1, 2, 1, 2, 3], [3, 3, 3], [1, 3, 2]]
+    pcases = []
+    for ph in ([1, 2], [1, 2, 3], [2, 1], [3, 3], [1, 2, 1, 2], [2, 3, 1, 2], [3, 1]):
+        m = len(ph)
+        pcases.append({"phrase": ph, "docs": [d for d, seq in enumerate(pdocs) if any(seq[i:i + m] == ph for i in range(len(seq) - m + 1))]})
+    out["phrase"] = {"docs": pdocs, "cases": pcases}
 
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -227,3 +227,58 @@ def test_oracle_multifield_bm25f_known_answer():
     assert dict(got)[1] == float(f32(f32(0) + part(1, idf[1], 4, 20)))
     got_and, tot_and = orc.search([8, 16], O.QUERY_INTERSECTION, 10, O.RESULT_TOPKCOUNT)
     assert tot_and == 1 and got_and == [(2, float(want2))]
+
+
+def test_round2_golden_turboquant_and_affine(golden):
+    """oracle vs the committed known-answer vectors of make_golden.py (numpy-f32 restatements): TurboQuantI8 on an 8-d vector, the affine
+    Euclidean quantiser through three vectors of its running state"""
+    g = golden["turboquant"]
+    c, s, n = O.turboquant_rows_i8(np.array([g["v"]], dtype=np.float32), np.array(g["mask"], dtype=np.float32))
+    assert [int(x) for x in c[0]] == g["codes"] and s[0] == np.float32(g["scale"]) and n[0] == np.float32(g["norm"])
+    rows = np.array([a["v"] for a in golden["affine_sq"]], dtype=np.float32)
+    c, s, n, zp, sq, st = O.quantize_affine_rows_i8(rows)
+    for i, a in enumerate(golden["affine_sq"]):
+        assert [int(x) for x in c[i]] == a["codes"] and s[i] == np.float32(a["scale"]) and int(zp[i]) == a["zero_point"], (i, a)
+        assert int(sq[i]) == a["sum_q"] and n[i] == np.float32(a["norm"])
+    assert list(st) == golden["affine_sq"][-1]["state"]
+
+
+def test_round2_golden_facet_filter_and_phrase(golden):
+    from helpers import key_of, level_from_postings, oracle_index
+    from seekstorm_b200 import _lib
+    types = {"U8": (_lib.FACET_U8, np.uint8), "I8": (_lib.FACET_I8, np.int8), "I32": (_lib.FACET_I32, np.int32), "I64": (_lib.FACET_I64, np.int64),
+             "U64": (_lib.FACET_U64, np.uint64), "F32": (_lib.FACET_F32, np.float32), "F64": (_lib.FACET_F64, np.float64),
+             "TIMESTAMP": (_lib.FACET_TIMESTAMP, np.int64), "STRING16": (_lib.FACET_STRING16, np.uint16), "STRING32": (_lib.FACET_STRING32, np.uint32)}
+    lv = level_from_postings(0, 1, {"t": [(0, 1)]}, [5])
+    for case in golden["facet_filter"]:
+        t, dt = types[case["type"]]
+        orc = oracle_index([lv], 1, 5)
+        val = np.array([case["value"]], dtype=dt)
+        orc.set_facets(val.view(np.uint8).reshape(1, -1), [(t, 0)], 0, 1, val.dtype.itemsize)
+        if "values" in case:
+            flt, sv = [(0, 1, 0, 0, 0, len(case["values"]))], case["values"]
+        else:
+            if case["type"] in ("F32", "F64"):
+                enc = lambda x: int(np.float64(x).view(np.uint64))
+            elif case["type"] in ("I8", "I32", "I64", "TIMESTAMP"):
+                enc = lambda x: int(np.int64(x).view(np.uint64))
+            else:
+                enc = lambda x: int(np.uint64(x))
+            flt, sv = [(0, 0, enc(case["start"]), enc(case["end"]), 0, 0)], None
+        hits, tot = orc.search([key_of("t")], O.QUERY_UNION, 10, O.RESULT_TOPKCOUNT, filters=flt, set_values=sv)
+        assert (tot == 1) == case["pass"] and (len(hits) == 1) == case["pass"], case
+    # phrase containment on token sequences
+    docs = golden["phrase"]["docs"]
+    post, pos_by = {}, {}
+    for d, seq in enumerate(docs):
+        for p, tok in enumerate(seq):
+            pos_by.setdefault((tok, d), []).append(p)
+    for (tok, d), ps in sorted(pos_by.items()):
+        post.setdefault(f"w{tok}", []).append((d, len(ps)))
+    lvp = level_from_postings(0, len(docs), post, [len(s) for s in docs])
+    order = sorted(post.keys())          # level_from_postings lays the terms out in this order
+    lvp["positions"] = np.array([p for t in order for d, _ in post[t] for p in pos_by[(int(t[1:]), d)]], dtype=np.uint16)
+    orc = oracle_index([lvp], len(docs), sum(len(s) for s in docs))
+    for case in golden["phrase"]["cases"]:
+        hits, tot = orc.search_phrase([key_of(f"w{t}") for t in case["phrase"]], 10, O.RESULT_TOPKCOUNT)
+        assert sorted(d for d, _ in hits) == case["docs"] and tot == len(case["docs"]), case
